@@ -1,0 +1,403 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED (see oracle/README.md).
+
+ctypes driver for ``oracle/libb2o.so`` (the CPU restatement of Box2DWorld + Box2D 2.3.1).  Only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may
+import this module.  The YAML reading here uses PyYAML and is deliberately independent of the product's
+own C++ loader (box2d_sim_env_b200/csrc/yaml_env.cpp) so that the two check each other.
+
+Reference behaviour followed: /root/reference/src/sim_env/Box2DIOUtils.cpp:16-92 (file resolution and
+environment decode), /root/reference/include/sim_env/Box2DIOUtils.h:94-303 (link / joint / robot decode).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libb2o.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "libb2o.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        L = _LIB
+        L.b2o_last_error.restype = C.c_char_p
+        for name in ("b2o_env_new", "b2o_world_new", "b2o_batch_new", "b2o_batch_world"):
+            getattr(L, name).restype = C.c_void_p
+        L.b2o_env_new.argtypes = [C.c_float, C.c_void_p]
+        L.b2o_env_free.argtypes = [C.c_void_p]
+        L.b2o_env_add_object.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.b2o_env_add_link.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p] + [C.c_float] * 5
+        L.b2o_env_add_polygon.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.b2o_env_add_joint.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p,
+                                        C.c_void_p, C.c_int, C.c_char_p]
+        L.b2o_env_add_state.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.b2o_world_new.argtypes = [C.c_void_p]
+        L.b2o_world_free.argtypes = [C.c_void_p]
+        L.b2o_world_info.argtypes = [C.c_void_p, C.c_void_p]
+        L.b2o_world_set_params.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int]
+        L.b2o_world_set_continuous.argtypes = [C.c_void_p, C.c_int]
+        L.b2o_world_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.b2o_world_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2o_world_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2o_world_set_object_pose.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float]
+        L.b2o_world_get_object_pose.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.b2o_world_set_target_velocity.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.b2o_world_object_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_char_p, C.c_int]
+        for name in ("b2o_world_get_bodies", "b2o_world_get_body_model", "b2o_world_get_fat_aabbs"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
+        L.b2o_world_get_fixture_model.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2o_world_get_joints.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2o_world_get_contacts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.b2o_world_check_collision.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.b2o_world_step_record.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.b2o_world_set_link_enabled.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.b2o_world_trace_islands.argtypes = [C.c_void_p, C.c_int]
+        L.b2o_world_get_island_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.b2o_world_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.b2o_world_controller_efforts.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.b2o_sincos.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.b2o_polygon_set.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p]
+        L.b2o_collide_polygons.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]
+        L.b2o_batch_new.argtypes = [C.c_void_p, C.c_int]
+        L.b2o_batch_free.argtypes = [C.c_void_p]
+        L.b2o_batch_world.argtypes = [C.c_void_p, C.c_int]
+        L.b2o_batch_rollout.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    return _LIB
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# ---------------------------------------------------------------------------------------------------
+# environment description (plain dicts) from YAML — independent of the product loader
+# ---------------------------------------------------------------------------------------------------
+def _decode_link(node):
+    # key aliases: the reference data uses trans_friction / rot_friction, its decoder reads
+    # ground_friction / ground_torque_integral (Box2DIOUtils.h:133-134); see SURVEY.md Appendix C-1.
+    gf = node["ground_friction"] if "ground_friction" in node else node["trans_friction"]
+    gti = node["ground_torque_integral"] if "ground_torque_integral" in node else node["rot_friction"]
+    return dict(name=str(node["name"]), geometry=[[float(v) for v in poly] for poly in node["geometry"]],
+                mass=float(node["mass"]), ground_friction=float(gf), ground_torque_integral=float(gti),
+                contact_friction=float(node["contact_friction"]), restitution=float(node["restitution"]))
+
+
+def _decode_joint(node):
+    return dict(name=str(node["name"]), link_a=str(node["link_a"]), link_b=str(node["link_b"]),
+                axis=[float(v) for v in node["axis"]], axis_orientation=float(node["axis_orientation"]),
+                position_limits=[float(v) for v in node["position_limits"]],
+                velocity_limits=[float(v) for v in node["velocity_limits"]],
+                acceleration_limits=[float(v) for v in node["acceleration_limits"]],
+                joint_type=str(node["joint_type"]), actuated=bool(node["actuated"]))
+
+
+def _decode_object(path, name, static, robot):
+    import yaml
+    with open(path) as f:
+        node = yaml.safe_load(f)
+    obj = dict(name=name or str(node["name"]), static=static,
+               links=[_decode_link(l) for l in (node.get("links") or [])],
+               joints=[_decode_joint(j) for j in (node.get("joints") or [])], base_actuation=None)
+    if robot:
+        ba = node.get("base_actuation")
+        if ba is not None:
+            obj["static"] = False
+            obj["base_actuation"] = dict(
+                translational_velocity_limits=[float(v) for v in ba["translational_velocity_limits"]],
+                translational_acceleration_limits=[float(v) for v in ba["translational_acceleration_limits"]],
+                rotational_velocity_limits=[float(v) for v in ba["rotational_velocity_limits"]],
+                rotational_acceleration_limits=[float(v) for v in ba["rotational_acceleration_limits"]],
+                use_center_of_mass=bool(ba["use_center_of_mass"]))
+        else:
+            obj["static"] = True
+    return obj
+
+
+def load_env_yaml(path):
+    import yaml
+    root = os.path.dirname(os.path.abspath(path))
+    with open(path) as f:
+        node = yaml.safe_load(f)
+    env = dict(scale=float(node.get("scale", 1.0)),
+               world_bounds=[float(v) for v in node.get("world_bounds", [0, 0, 0, 0])],
+               robots=[], objects=[], states={})
+    for e in node.get("robots") or []:
+        env["robots"].append(_decode_object(os.path.join(root, e["filename"]), e.get("name"), False, True))
+    for e in node.get("objects") or []:
+        env["objects"].append(_decode_object(os.path.join(root, e["filename"]), e.get("name"),
+                                             bool(e.get("static", False)), False))
+    for s in node.get("states") or []:
+        env["states"][str(s["name"])] = dict(configuration=[float(v) for v in s["state"]["configuration"]],
+                                             velocity=[float(v) for v in s["state"]["velocity"]])
+    return env
+
+
+class OracleEnv:
+    def __init__(self, env):
+        L = lib()
+        self.desc = env
+        b = _f32(env.get("world_bounds", [0, 0, 0, 0]))
+        self.h = C.c_void_p(L.b2o_env_new(float(env["scale"]), _ptr(b)))
+        for is_robot, key in ((1, "robots"), (0, "objects")):
+            for obj in env[key]:
+                ba = obj.get("base_actuation")
+                lim = None
+                use_com = 1
+                if ba:
+                    lim = _f32(list(ba["translational_velocity_limits"]) + list(ba["translational_acceleration_limits"]) +
+                               list(ba["rotational_velocity_limits"]) + list(ba["rotational_acceleration_limits"]))
+                    use_com = int(ba.get("use_center_of_mass", True))
+                oi = L.b2o_env_add_object(self.h, obj["name"].encode(), is_robot, int(obj["static"]), _ptr(lim), use_com)
+                for link in obj["links"]:
+                    li = L.b2o_env_add_link(self.h, is_robot, oi, link["name"].encode(), link["mass"],
+                                            link["ground_friction"], link["ground_torque_integral"],
+                                            link["contact_friction"], link["restitution"])
+                    for poly in link["geometry"]:
+                        p = _f32(poly)
+                        L.b2o_env_add_polygon(self.h, is_robot, oi, li, _ptr(p), len(p))
+                for j in obj["joints"]:
+                    params = _f32(list(j["axis"]) + list(j["position_limits"]) + list(j["velocity_limits"]) +
+                                  list(j["acceleration_limits"]) + [j["axis_orientation"]])
+                    L.b2o_env_add_joint(self.h, is_robot, oi, j["name"].encode(), j["link_a"].encode(),
+                                        j["link_b"].encode(), _ptr(params), int(j["actuated"]), j["joint_type"].encode())
+        for name, st in env.get("states", {}).items():
+            c = _f32(st["configuration"])
+            v = _f32(st["velocity"])
+            L.b2o_env_add_state(self.h, name.encode(), _ptr(c), _ptr(v), len(c))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().b2o_env_free(self.h)
+            self.h = None
+
+
+class OracleWorld:
+    """One CPU world with the reference's Box2DWorld semantics."""
+
+    MAXC = 256
+
+    def __init__(self, env, _handle=None):
+        L = lib()
+        self.env = env if isinstance(env, OracleEnv) else OracleEnv(env)
+        self._owned = _handle is None
+        self.h = C.c_void_p(L.b2o_world_new(self.env.h)) if _handle is None else C.c_void_p(_handle)
+        if not self.h:
+            raise RuntimeError(L.b2o_last_error().decode())
+        info = np.zeros(6, np.int32)
+        L.b2o_world_info(self.h, _ptr(info))
+        self.n_bodies, self.n_proxies, self.n_joints, self.nq, self.n_objects = [int(x) for x in info[:5]]
+        self.objects = []
+        for i in range(self.n_objects):
+            oi = np.zeros(6, np.int32)
+            nm = C.create_string_buffer(128)
+            L.b2o_world_object_info(self.h, i, _ptr(oi), nm, 128)
+            self.objects.append(dict(name=nm.value.decode(), is_robot=bool(oi[0]), is_static=bool(oi[1]),
+                                     n_dofs=int(oi[2]), n_links=int(oi[3]), n_joints=int(oi[4]), first_body=int(oi[5])))
+
+    def __del__(self):
+        if getattr(self, "h", None) and self._owned:
+            lib().b2o_world_free(self.h)
+            self.h = None
+
+    def object_index(self, name):
+        for i, o in enumerate(self.objects):
+            if o["name"] == name:
+                return i
+        raise KeyError(name)
+
+    def set_params(self, dt=0.01, vel_iters=15, pos_iters=15):
+        lib().b2o_world_set_params(self.h, dt, vel_iters, pos_iters)
+
+    def set_continuous(self, flag):
+        lib().b2o_world_set_continuous(self.h, int(flag))
+
+    def step(self, steps=1, execute_controllers=True, allow_sleeping=True):
+        if lib().b2o_world_step(self.h, steps, int(execute_controllers), int(allow_sleeping)):
+            raise RuntimeError(lib().b2o_last_error().decode())
+
+    def get_state(self):
+        q = np.zeros(self.nq, np.float32)
+        qd = np.zeros(self.nq, np.float32)
+        lib().b2o_world_get_state(self.h, _ptr(q), _ptr(qd))
+        return q, qd
+
+    def set_state(self, q, qd):
+        q = _f32(q)
+        qd = _f32(qd)
+        assert q.size == self.nq and qd.size == self.nq
+        if lib().b2o_world_set_state(self.h, _ptr(q), _ptr(qd)):
+            raise RuntimeError(lib().b2o_last_error().decode())
+
+    def set_object_pose(self, obj, x, y, theta):
+        lib().b2o_world_set_object_pose(self.h, obj, x, y, theta)
+
+    def get_object_pose(self, obj):
+        p = np.zeros(3, np.float32)
+        lib().b2o_world_get_object_pose(self.h, obj, _ptr(p))
+        return p
+
+    def set_target_velocity(self, obj, v):
+        v = _f32(v)
+        if lib().b2o_world_set_target_velocity(self.h, obj, _ptr(v), len(v)):
+            raise RuntimeError(lib().b2o_last_error().decode())
+
+    def controller_efforts(self, obj):
+        out = np.zeros(64, np.float32)
+        n = lib().b2o_world_controller_efforts(self.h, obj, _ptr(out))
+        return out[:n].copy()
+
+    def bodies(self):
+        """[n_bodies, 16]: xf.p(2) xf.q.s xf.q.c c(2) a c0(2) a0 v(2) w sleepTime awake type"""
+        out = np.zeros((self.n_bodies, 16), np.float32)
+        lib().b2o_world_get_bodies(self.h, _ptr(out))
+        return out
+
+    def body_model(self):
+        out = np.zeros((self.n_bodies, 8), np.float32)
+        lib().b2o_world_get_body_model(self.h, _ptr(out))
+        return out
+
+    def fixture_model(self):
+        io = np.zeros((self.n_proxies, 3), np.int32)
+        fo = np.zeros((self.n_proxies, 38), np.float32)
+        lib().b2o_world_get_fixture_model(self.h, _ptr(io), _ptr(fo))
+        return io, fo
+
+    def fat_aabbs(self):
+        out = np.zeros((self.n_proxies, 4), np.float32)
+        lib().b2o_world_get_fat_aabbs(self.h, _ptr(out))
+        return out
+
+    def joints(self):
+        io = np.zeros((self.n_joints, 6), np.int32)
+        fo = np.zeros((self.n_joints, 15), np.float32)
+        lib().b2o_world_get_joints(self.h, _ptr(io), _ptr(fo))
+        return io, fo
+
+    def contacts(self):
+        io = np.zeros((self.MAXC, 8), np.int32)
+        fo = np.zeros((self.MAXC, 12), np.float32)
+        n = lib().b2o_world_get_contacts(self.h, _ptr(io), _ptr(fo), self.MAXC)
+        return io[:n].copy(), fo[:n].copy()
+
+    def check_collision(self):
+        io = np.zeros((self.MAXC, 4), np.int32)
+        fo = np.zeros((self.MAXC, 6), np.float32)
+        n = lib().b2o_world_check_collision(self.h, _ptr(io), _ptr(fo), self.MAXC)
+        return io[:n].copy(), fo[:n].copy()
+
+    def step_record(self, steps=1, execute_controllers=True, allow_sleeping=True):
+        io = np.zeros((self.MAXC, 4), np.int32)
+        fo = np.zeros((self.MAXC, 6), np.float32)
+        n = lib().b2o_world_step_record(self.h, steps, int(execute_controllers), int(allow_sleeping), _ptr(io), _ptr(fo),
+                                        self.MAXC)
+        return io[:n].copy(), fo[:n].copy()
+
+    def set_link_enabled(self, body_index, enabled):
+        lib().b2o_world_set_link_enabled(self.h, body_index, int(enabled))
+
+    def trace_islands(self, flag=True):
+        lib().b2o_world_trace_islands(self.h, int(flag))
+
+    def island_trace(self):
+        buf = np.zeros(4096, np.int32)
+        n = lib().b2o_world_get_island_trace(self.h, _ptr(buf), 4096)
+        v = buf[:n].tolist()
+        out = []
+        p = 1
+        for _ in range(v[0] if v else 0):
+            nb = v[p]; bodies = v[p + 1:p + 1 + nb]; p += 1 + nb
+            nj = v[p]; joints = v[p + 1:p + 1 + nj]; p += 1 + nj
+            nc = v[p]; cs = [(v[p + 1 + 2 * k], v[p + 2 + 2 * k]) for k in range(nc)]; p += 1 + 2 * nc
+            out.append(dict(bodies=bodies, joints=joints, contacts=cs))
+        return out
+
+    def stats(self):
+        s = np.zeros(3, np.int32)
+        lib().b2o_world_stats(self.h, _ptr(s))
+        return dict(islands=int(s[0]), toi_events=int(s[1]), toi_calls=int(s[2]))
+
+
+class OracleBatch:
+    """N independent CPU worlds stepped by a std::thread pool (the CPU baseline of SURVEY.md §8d)."""
+
+    def __init__(self, env, n):
+        self.env = env if isinstance(env, OracleEnv) else OracleEnv(env)
+        self.n = n
+        self.h = C.c_void_p(lib().b2o_batch_new(self.env.h, n))
+        if not self.h:
+            raise RuntimeError(lib().b2o_last_error().decode())
+        self.world0 = OracleWorld(self.env, _handle=lib().b2o_batch_world(self.h, 0))
+        self.nq = self.world0.nq
+
+    def world(self, i):
+        return OracleWorld(self.env, _handle=lib().b2o_batch_world(self.h, i))
+
+    def rollout(self, q0, qd0, robot_idx, targets, steps_per_target, n_threads):
+        """targets: [T, n, ndof] or None.  Returns (q, qd) after T*steps_per_target steps."""
+        q0 = _f32(q0) if q0 is not None else None
+        qd0 = _f32(qd0) if qd0 is not None else None
+        if targets is not None:
+            targets = _f32(targets)
+            T, n, ndof = targets.shape
+            assert n == self.n
+        else:
+            T, ndof = 1, 0
+        q = np.zeros((self.n, self.nq), np.float32)
+        qd = np.zeros((self.n, self.nq), np.float32)
+        failed = lib().b2o_batch_rollout(self.h, _ptr(q0), _ptr(qd0), robot_idx, _ptr(targets), ndof, T,
+                                         steps_per_target, n_threads, _ptr(q), _ptr(qd))
+        if failed:
+            raise RuntimeError("%d oracle worlds failed" % failed)
+        return q, qd
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.world0 = None
+            lib().b2o_batch_free(self.h)
+            self.h = None
+
+
+def sincos(x):
+    x = _f32(x)
+    s = np.zeros_like(x)
+    c = np.zeros_like(x)
+    lib().b2o_sincos(_ptr(x), _ptr(s), _ptr(c), x.size)
+    return s, c
+
+
+def polygon_set(points, density=1.0):
+    p = _f32(points).reshape(-1)
+    out = np.zeros(38, np.float32)
+    n = lib().b2o_polygon_set(_ptr(p), len(p) // 2, density, _ptr(out))
+    return dict(count=n, vertices=out[:16].reshape(8, 2)[:n].copy(), normals=out[16:32].reshape(8, 2)[:n].copy(),
+                centroid=out[32:34].copy(), mass=float(out[34]), center=out[35:37].copy(), I=float(out[37]))
+
+
+def collide_polygons(polyA, poseA, polyB, poseB):
+    a = _f32(polyA).reshape(-1)
+    b = _f32(polyB).reshape(-1)
+    pa = _f32(poseA)
+    pb = _f32(poseB)
+    io = np.zeros(4, np.int32)
+    fo = np.zeros(8, np.float32)
+    lib().b2o_collide_polygons(_ptr(a), len(a) // 2, _ptr(pa), _ptr(b), len(b) // 2, _ptr(pb), _ptr(io), _ptr(fo))
+    return dict(point_count=int(io[0]), type=int(io[1]), ids=[int(io[2]) & 0xFFFFFFFF, int(io[3]) & 0xFFFFFFFF],
+                local_normal=fo[0:2].copy(), local_point=fo[2:4].copy(), points=fo[4:8].reshape(2, 2).copy())

@@ -1,0 +1,193 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see b2o_math.h header).  PARITY UNPINNED.
+// CPU restatement of the sim_env wrapper semantics of the reference on top of the b2o engine:
+// model construction (/root/reference/src/sim_env/Box2DWorld.cpp:44-148, 872-948, 1292-1363,
+// 2046-2067, 3644-3721), DOF <-> body kinematics (:405-438, 759-794, 992-1028, 1507-1715,
+// 2018-2041), the velocity controller (/root/reference/src/sim_env/Box2DController.cpp:42-117,
+// 191-215), effort application (:1198-1222, 2284-2379), stepping (:3266-3333) and the collision
+// checker (:2743-2911).
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "b2o_dynamics.h"
+
+namespace b2o {
+
+struct LinkDesc {
+    std::string name;
+    std::vector<std::vector<float>> polygons;  // flat x,y lists (unscaled)
+    float mass = 0.0f;
+    float ground_friction = 0.0f;
+    float ground_torque_integral = 0.0f;
+    float contact_friction = 0.0f;
+    float restitution = 0.0f;
+};
+struct JointDesc {
+    std::string name, link_a, link_b;
+    float axis[2] = {0, 0};
+    float position_limits[2] = {0, 0};
+    float velocity_limits[2] = {0, 0};
+    float acceleration_limits[2] = {0, 0};
+    std::string joint_type = "revolute";
+    bool actuated = false;
+    float axis_orientation = 0.0f;
+};
+struct ObjectDesc {
+    std::string name;
+    std::string base_link;
+    std::vector<LinkDesc> links;
+    std::vector<JointDesc> joints;
+    bool is_static = false;
+    bool is_robot = false;
+    float translational_velocity_limits[2] = {0, 0};
+    float translational_acceleration_limits[2] = {0, 0};
+    float rotational_velocity_limits[2] = {0, 0};
+    float rotational_acceleration_limits[2] = {0, 0};
+    bool use_center_of_mass = true;
+};
+struct StateDesc {
+    std::vector<float> configuration, velocity;
+};
+struct EnvDesc {
+    float scale = 1.0f;
+    float world_bounds[4] = {0, 0, 0, 0};
+    std::vector<ObjectDesc> robots, objects;
+    std::map<std::string, StateDesc> states;
+};
+
+struct OWorld;
+struct OObject;
+struct OJoint;
+
+struct OLink {
+    std::string name;
+    OWorld* world = nullptr;
+    OObject* object = nullptr;
+    Body* body = nullptr;
+    Joint* frictionJoint = nullptr;
+    Vec2 localOriginOffset;
+    float localAabbMin[2], localAabbMax[2];
+    float contactFriction = 0, groundFriction = 0, groundTorqueIntegral = 0;
+    std::vector<OJoint*> childJoints;
+    OJoint* parentJoint = nullptr;
+    bool enabled = true;
+
+    void getPose(float pose[3]) const;
+    void setPose(const float pose[3], bool updateChildren = true, bool jointOverride = false);
+    void getVelocityVector(float v[3]) const;
+    float getMass() const { return body->GetMass(); }
+    float getInertia() const;
+    float getCOMInertia() const;
+    void getCenterOfMass(float com[2]) const;
+    void setOriginToCenterOfMass();
+    void updateBodyVelocities(const std::vector<float>& allDofVel, std::vector<std::pair<Vec2, unsigned>>& parentJoints,
+                              unsigned indexOffset);
+    void setEnabled(bool e);
+};
+
+struct OJoint {
+    std::string name;
+    OWorld* world = nullptr;
+    OObject* object = nullptr;
+    OLink* linkA = nullptr;
+    OLink* linkB = nullptr;
+    Joint* joint = nullptr;
+    unsigned jointIndex = 0, dofIndex = 0;
+    float positionLimits[2], velocityLimits[2], accelerationLimits[2];
+
+    float getPosition() const { return joint->GetJointAngle(); }
+    float getVelocity() const { return joint->GetJointSpeed(); }
+    void resetPosition(float value, bool childJointOverride);
+    void setControlTorque(float value);
+    void getAxisPosition(float axis[2]) const;
+    Vec2 getGlobalAxisPosition() const { return joint->GetAnchorA(); }
+};
+
+struct DofInfo {
+    float positionLimits[2], velocityLimits[2], accelerationLimits[2];
+};
+
+struct OObject {
+    std::string name;
+    OWorld* world = nullptr;
+    bool isStatic = false;
+    bool isRobot = false;
+    float mass = 0.0f;
+    std::map<std::string, OLink*> links;   // name order, as the reference's std::map
+    std::vector<OLink*> linksCreation;     // YAML order
+    std::vector<OJoint*> sortedJoints;     // YAML order
+    OLink* baseLink = nullptr;
+    unsigned numDofs = 0;
+    std::vector<int> activeDofs;
+    DofInfo baseDof[3];
+    // velocity controller state (Box2DRobotVelocityController)
+    std::vector<float> targetVelocity;
+    bool targetAvailable = false;
+
+    unsigned numBaseDofs() const { return isStatic ? 0 : 3; }
+    std::vector<int> allDofs() const;
+    std::vector<float> getDOFPositions(const std::vector<int>& idx) const;
+    std::vector<float> getDOFVelocities(const std::vector<int>& idx) const;
+    void getDofLimits(int dof, DofInfo* info) const;
+    void setDOFPositions(const std::vector<float>& values, const std::vector<int>& idx);
+    void setDOFVelocities(const std::vector<float>& values, const std::vector<int>& idx);
+    void setPose(float x, float y, float theta);
+    void updateBodyVelocities(const std::vector<float>& allDofVel);
+    float getInertia() const;
+    // controller
+    void setTargetVelocity(const std::vector<float>& v);
+    bool controllerCompute(const std::vector<float>& velocities, float dt, std::vector<float>& out) const;
+    float kinematicChainInertia(const OJoint* root) const;
+    void control(float dt);
+    void commandEfforts(const std::vector<float>& efforts);
+};
+
+struct OContact {
+    float point[3];
+    float normal[3];
+    int bodyA, bodyB;        // b2o body indices (fixtureA / fixtureB bodies)
+    int fixtureA, fixtureB;  // proxy ids
+};
+
+struct OWorld : ContactListener {
+    EnvDesc env;
+    std::unique_ptr<World> b2;
+    Body* ground = nullptr;
+    float scale = 1.0f;
+    float timeStep = 0.01f;
+    int velocitySteps = 15;
+    int positionSteps = 15;
+    std::vector<std::unique_ptr<OObject>> owned;
+    std::vector<std::unique_ptr<OLink>> ownedLinks;
+    std::vector<std::unique_ptr<OJoint>> ownedJoints;
+    std::map<std::string, OObject*> objects;  // name order
+    std::map<std::string, OObject*> robots;   // name order
+    std::vector<OObject*> creationOrder;      // robots then objects, file order
+    bool recordContacts = false;
+    std::vector<OContact> recorded;
+    std::vector<std::string> warnings;
+
+    explicit OWorld(const EnvDesc& e);
+    float invScale() const { return 1.0f / scale; }
+    float gravity() const { return 9.81f * scale; }
+    OObject* find(const std::string& name);
+    void stepPhysics(int steps, bool executeControllers = true, bool allowSleeping = true);
+    void stepPhysicsRecord(std::vector<OContact>& contacts, int steps, bool executeControllers, bool allowSleeping);
+    void setToRest();
+    // checkCollision(std::vector<Contact>&) — all touching contacts after UpdateContacts()
+    void updateContactCache(std::vector<OContact>& out);
+    void BeginContact(Contact* c) override;
+    OContact makeContact(Contact* c) const;
+    // full DOF state in creation order (robots, then objects): dynamic objects contribute
+    // [x, y, theta, joints...], static objects [joints...]
+    int stateDim() const;
+    void getState(std::vector<float>& q, std::vector<float>& qd) const;
+    void setState(const std::vector<float>& q, const std::vector<float>& qd);
+
+private:
+    OObject* createObject(const ObjectDesc& d);
+};
+
+}  // namespace b2o
