@@ -1,0 +1,430 @@
+"""ctypes mirror of include/b2g.h with the reference's method names.
+
+Reference interface mirrored (file:line in /root/reference):
+  Box2DWorld::loadWorld            include/sim_env/Box2DWorld.h:751
+  stepPhysics(steps, ctrl, sleep)  :780            setPhysicsTimeStep/... :784-786
+  getWorldState / setWorldState    :823-825        saveState/restoreState/dropState :820-822
+  checkCollision(contacts)         :797            clone :748 (here: a second batch of the same model)
+  Box2DRobotVelocityController::setTargetVelocity  include/sim_env/Box2DController.h:23
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class B2GError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("b2g error %d: %s" % (code, msg))
+        self.code = code
+
+
+def data_path(name="test_env.yaml"):
+    return os.path.join(_HERE, "data", name)
+
+
+class _ModelInfo(C.Structure):
+    _fields_ = [("n_bodies", C.c_int32), ("n_fixtures", C.c_int32), ("n_joints", C.c_int32), ("n_objects", C.c_int32),
+                ("n_robots", C.c_int32), ("nq", C.c_int32), ("scale", C.c_float)]
+
+
+class _ObjectInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("is_robot", C.c_int32), ("is_static", C.c_int32), ("n_dofs", C.c_int32),
+                ("dof_offset", C.c_int32), ("first_body", C.c_int32), ("n_links", C.c_int32), ("n_joints", C.c_int32)]
+
+
+# every symbol include/b2g.h declares (tests/test_abi.py checks the library exports them all)
+ABI_SYMBOLS = [
+    "b2g_last_error", "b2g_env_create", "b2g_env_load_yaml", "b2g_env_destroy", "b2g_env_add_object", "b2g_env_add_link",
+    "b2g_env_add_polygon", "b2g_env_add_joint", "b2g_env_add_state", "b2g_model_create", "b2g_model_destroy",
+    "b2g_model_get_info", "b2g_model_get_object", "b2g_model_get_dof_limits", "b2g_model_get_bodies",
+    "b2g_model_get_fixtures", "b2g_model_get_joints", "b2g_batch_create", "b2g_batch_destroy", "b2g_batch_set_params",
+    "b2g_batch_status", "b2g_batch_stream", "b2g_batch_sync", "b2g_batch_set_state", "b2g_batch_set_state_dev",
+    "b2g_batch_get_state", "b2g_batch_get_state_dev", "b2g_batch_set_object_pose", "b2g_batch_get_object_pose",
+    "b2g_batch_set_target_velocity", "b2g_batch_set_target_velocity_dev", "b2g_batch_step", "b2g_batch_rollout_dev",
+    "b2g_batch_get_bodies", "b2g_batch_get_fat_aabbs", "b2g_batch_get_joints", "b2g_batch_get_contacts",
+    "b2g_batch_check_collision", "b2g_batch_save_state", "b2g_batch_restore_state", "b2g_batch_drop_state",
+    "b2g_host_alloc", "b2g_host_free", "b2g_launch_count", "b2g_batch_take_kernel_ms",
+]
+
+
+def lib():
+    """Load libb2g.so (building it in-tree with nvcc if missing or stale)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    so = os.path.join(_HERE, "libb2g.so")
+    try:
+        from . import build as _build
+        so = _build.build()
+    except Exception:
+        if not os.path.exists(so):
+            raise
+    L = C.CDLL(so)
+    vp, ip, fp = C.c_void_p, C.c_void_p, C.c_void_p
+    L.b2g_last_error.restype = C.c_char_p
+    L.b2g_env_create.argtypes = [C.c_float, fp, C.POINTER(vp)]
+    L.b2g_env_load_yaml.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.b2g_env_destroy.argtypes = [vp]
+    L.b2g_env_destroy.restype = None
+    L.b2g_env_add_object.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, fp, C.c_int, C.POINTER(C.c_int)]
+    L.b2g_env_add_link.argtypes = [vp, C.c_int, C.c_int, C.c_char_p] + [C.c_float] * 5 + [C.POINTER(C.c_int)]
+    L.b2g_env_add_polygon.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, C.c_int]
+    L.b2g_env_add_joint.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, fp, C.c_int, C.c_char_p]
+    L.b2g_env_add_state.argtypes = [vp, C.c_char_p, fp, fp, C.c_int]
+    L.b2g_model_create.argtypes = [vp, C.POINTER(vp)]
+    L.b2g_model_destroy.argtypes = [vp]
+    L.b2g_model_destroy.restype = None
+    L.b2g_model_get_info.argtypes = [vp, C.POINTER(_ModelInfo)]
+    L.b2g_model_get_object.argtypes = [vp, C.c_int, C.POINTER(_ObjectInfo)]
+    L.b2g_model_get_dof_limits.argtypes = [vp, fp]
+    L.b2g_model_get_bodies.argtypes = [vp, fp]
+    L.b2g_model_get_fixtures.argtypes = [vp, ip, fp]
+    L.b2g_model_get_joints.argtypes = [vp, ip, fp]
+    L.b2g_batch_create.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.POINTER(vp)]
+    L.b2g_batch_destroy.argtypes = [vp]
+    L.b2g_batch_destroy.restype = None
+    L.b2g_batch_set_params.argtypes = [vp, C.c_float, C.c_int, C.c_int]
+    L.b2g_batch_status.argtypes = [vp, ip]
+    L.b2g_batch_stream.argtypes = [vp]
+    L.b2g_batch_stream.restype = C.c_void_p
+    L.b2g_batch_sync.argtypes = [vp]
+    for n in ("b2g_batch_set_state", "b2g_batch_set_state_dev"):
+        getattr(L, n).argtypes = [vp, fp, fp, C.c_int]
+    for n in ("b2g_batch_get_state", "b2g_batch_get_state_dev"):
+        getattr(L, n).argtypes = [vp, fp, fp]
+    L.b2g_batch_set_object_pose.argtypes = [vp, C.c_int, fp]
+    L.b2g_batch_get_object_pose.argtypes = [vp, C.c_int, fp]
+    L.b2g_batch_set_target_velocity.argtypes = [vp, C.c_int, fp]
+    L.b2g_batch_set_target_velocity_dev.argtypes = [vp, C.c_int, fp]
+    L.b2g_batch_step.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.b2g_batch_rollout_dev.argtypes = [vp, C.c_int, fp, C.c_int, C.c_int]
+    L.b2g_batch_get_bodies.argtypes = [vp, fp]
+    L.b2g_batch_get_fat_aabbs.argtypes = [vp, fp]
+    L.b2g_batch_get_joints.argtypes = [vp, ip, fp]
+    L.b2g_batch_get_contacts.argtypes = [vp, ip, ip, fp, C.c_int]
+    L.b2g_batch_check_collision.argtypes = [vp, ip, ip, fp, C.c_int]
+    for n in ("b2g_batch_save_state", "b2g_batch_restore_state", "b2g_batch_drop_state"):
+        getattr(L, n).argtypes = [vp]
+    L.b2g_host_alloc.argtypes = [C.POINTER(vp), C.c_uint64]
+    L.b2g_host_free.argtypes = [vp]
+    L.b2g_host_free.restype = None
+    L.b2g_launch_count.restype = C.c_uint64
+    L.b2g_batch_take_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    _LIB = L
+    return L
+
+
+def _check(code):
+    if code != 0:
+        raise B2GError(code, lib().b2g_last_error().decode())
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """numpy array backed by page-locked host memory (cudaHostAlloc through the C ABI)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    _check(lib().b2g_host_alloc(C.byref(p), max(n, 1)))
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    arr._b2g_pinned = p  # keep the handle; memory is released with b2g_host_free(arr._b2g_pinned) by the caller
+    return arr
+
+
+class Environment:
+    """Box2DEnvironmentDescription (include/sim_env/Box2DIOUtils.h:64-70)."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @classmethod
+    def from_yaml(cls, path):
+        h = C.c_void_p()
+        _check(lib().b2g_env_load_yaml(os.fsencode(path), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_dict(cls, env):
+        """Programmatic construction from the plain-dict description used by envgen / tests."""
+        L = lib()
+        h = C.c_void_p()
+        b = _f32(env.get("world_bounds", [0, 0, 0, 0]))
+        _check(L.b2g_env_create(float(env["scale"]), _ptr(b), C.byref(h)))
+        self = cls(h)
+        for is_robot, key in ((1, "robots"), (0, "objects")):
+            for obj in env[key]:
+                ba = obj.get("base_actuation")
+                lim = None
+                use_com = 1
+                if ba:
+                    lim = _f32(list(ba["translational_velocity_limits"]) + list(ba["translational_acceleration_limits"]) +
+                               list(ba["rotational_velocity_limits"]) + list(ba["rotational_acceleration_limits"]))
+                    use_com = int(ba.get("use_center_of_mass", True))
+                oi = C.c_int()
+                _check(L.b2g_env_add_object(h, obj["name"].encode(), is_robot, int(obj["static"]), _ptr(lim), use_com, C.byref(oi)))
+                for link in obj["links"]:
+                    li = C.c_int()
+                    _check(L.b2g_env_add_link(h, is_robot, oi.value, link["name"].encode(), link["mass"], link["ground_friction"],
+                                              link["ground_torque_integral"], link["contact_friction"], link["restitution"],
+                                              C.byref(li)))
+                    for poly in link["geometry"]:
+                        p = _f32(poly)
+                        _check(L.b2g_env_add_polygon(h, is_robot, oi.value, li.value, _ptr(p), len(p)))
+                for j in obj["joints"]:
+                    params = _f32(list(j["axis"]) + list(j["position_limits"]) + list(j["velocity_limits"]) +
+                                  list(j["acceleration_limits"]) + [j["axis_orientation"]])
+                    _check(L.b2g_env_add_joint(h, is_robot, oi.value, j["name"].encode(), j["link_a"].encode(),
+                                               j["link_b"].encode(), _ptr(params), int(j["actuated"]), j["joint_type"].encode()))
+        for name, st in env.get("states", {}).items():
+            cfg = _f32(st["configuration"])
+            vel = _f32(st["velocity"])
+            _check(L.b2g_env_add_state(h, name.encode(), _ptr(cfg), _ptr(vel), len(cfg)))
+        return self
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().b2g_env_destroy(self.h)
+            self.h = None
+
+
+class Model:
+    """Immutable flattened model shared by the worlds of a batch (host only; no GPU needed)."""
+
+    def __init__(self, env):
+        if isinstance(env, (str, os.PathLike)):
+            env = Environment.from_yaml(env)
+        elif isinstance(env, dict):
+            env = Environment.from_dict(env)
+        self.env = env
+        self.h = C.c_void_p()
+        _check(lib().b2g_model_create(env.h, C.byref(self.h)))
+        info = _ModelInfo()
+        _check(lib().b2g_model_get_info(self.h, C.byref(info)))
+        self.n_bodies, self.n_fixtures, self.n_joints = info.n_bodies, info.n_fixtures, info.n_joints
+        self.n_objects, self.n_robots, self.nq, self.scale = info.n_objects, info.n_robots, info.nq, info.scale
+        self.objects = []
+        for i in range(self.n_objects):
+            oi = _ObjectInfo()
+            _check(lib().b2g_model_get_object(self.h, i, C.byref(oi)))
+            self.objects.append(dict(name=oi.name.decode(), is_robot=bool(oi.is_robot), is_static=bool(oi.is_static),
+                                     n_dofs=oi.n_dofs, dof_offset=oi.dof_offset, first_body=oi.first_body,
+                                     n_links=oi.n_links, n_joints=oi.n_joints))
+
+    def object_index(self, name):
+        for i, o in enumerate(self.objects):
+            if o["name"] == name:
+                return i
+        raise KeyError(name)
+
+    def dof_limits(self):
+        out = np.zeros((self.nq, 6), np.float32)
+        _check(lib().b2g_model_get_dof_limits(self.h, _ptr(out)))
+        return out
+
+    def body_model(self):
+        out = np.zeros((self.n_bodies, 8), np.float32)
+        _check(lib().b2g_model_get_bodies(self.h, _ptr(out)))
+        return out
+
+    def fixture_model(self):
+        io = np.zeros((self.n_fixtures, 3), np.int32)
+        fo = np.zeros((self.n_fixtures, 38), np.float32)
+        _check(lib().b2g_model_get_fixtures(self.h, _ptr(io), _ptr(fo)))
+        return io, fo
+
+    def joint_model(self):
+        io = np.zeros((self.n_joints, 6), np.int32)
+        fo = np.zeros((self.n_joints, 15), np.float32)
+        _check(lib().b2g_model_get_joints(self.h, _ptr(io), _ptr(fo)))
+        return io, fo
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().b2g_model_destroy(self.h)
+            self.h = None
+
+
+class BatchBox2DWorld:
+    """N independent Box2DWorld instances stepped together on one B200.
+
+    Method names and argument meaning follow sim_env::Box2DWorld; every array gains a leading world axis.
+    """
+
+    def __init__(self, n_worlds=1, device=0, max_contacts=0):
+        self.n_worlds = int(n_worlds)
+        self.device = device
+        self.max_contacts = max_contacts
+        self.model = None
+        self.h = None
+
+    # -- loadWorld(path) / loadWorld(env_desc)  (Box2DWorld.cpp:3040-3054)
+    def loadWorld(self, env):
+        self._destroy()
+        self.model = env if isinstance(env, Model) else Model(env)
+        self.h = C.c_void_p()
+        _check(lib().b2g_batch_create(self.model.h, self.n_worlds, self.device, self.max_contacts, C.byref(self.h)))
+        self.nq = self.model.nq
+        return self
+
+    def clone(self):
+        """Box2DWorld::clone (:3021-3038): same model, state copied through get/setWorldState."""
+        other = BatchBox2DWorld(self.n_worlds, self.device, self.max_contacts).loadWorld(self.model)
+        q, qd = self.getWorldState()
+        other.setWorldState(q, qd, reset_caches=True)
+        return other
+
+    def _destroy(self):
+        if getattr(self, "h", None):
+            lib().b2g_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self._destroy()
+
+    # -- physics parameters (:3340-3368)
+    def setPhysicsTimeStep(self, dt):
+        self._dt = float(dt)
+        self._push_params()
+
+    def setVelocitySteps(self, n):
+        self._vs = int(n)
+        self._push_params()
+
+    def setPositionSteps(self, n):
+        self._ps = int(n)
+        self._push_params()
+
+    def getPhysicsTimeStep(self):
+        return getattr(self, "_dt", 0.01)
+
+    def getVelocitySteps(self):
+        return getattr(self, "_vs", 15)
+
+    def getPositionSteps(self):
+        return getattr(self, "_ps", 15)
+
+    def _push_params(self):
+        _check(lib().b2g_batch_set_params(self.h, self.getPhysicsTimeStep(), self.getVelocitySteps(), self.getPositionSteps()))
+
+    # -- stepping (:3256-3283)
+    def stepPhysics(self, steps=1, execute_controllers=True, allow_sleeping=True):
+        _check(lib().b2g_batch_step(self.h, int(steps), int(execute_controllers), int(allow_sleeping)))
+
+    # -- state (:3462-3541)
+    def getWorldState(self):
+        q = np.zeros((self.n_worlds, self.nq), np.float32)
+        qd = np.zeros((self.n_worlds, self.nq), np.float32)
+        _check(lib().b2g_batch_get_state(self.h, _ptr(q), _ptr(qd)))
+        return q, qd
+
+    def setWorldState(self, q, qd, reset_caches=False):
+        q = _f32(q)
+        qd = _f32(qd)
+        if q.shape != (self.n_worlds, self.nq) or qd.shape != (self.n_worlds, self.nq):
+            raise B2GError(1, "[sim_env::BatchBox2DWorld::setWorldState] state arrays must be [n_worlds, %d]" % self.nq)
+        _check(lib().b2g_batch_set_state(self.h, _ptr(q), _ptr(qd), int(reset_caches)))
+
+    def saveState(self):
+        _check(lib().b2g_batch_save_state(self.h))
+
+    def restoreState(self):
+        code = lib().b2g_batch_restore_state(self.h)
+        if code == 1 and b"stack is empty" in lib().b2g_last_error():
+            return False
+        _check(code)
+        return True
+
+    def dropState(self):
+        _check(lib().b2g_batch_drop_state(self.h))
+
+    def setObjectPose(self, obj, pose):
+        obj = self.model.object_index(obj) if isinstance(obj, str) else obj
+        pose = _f32(np.broadcast_to(_f32(pose), (self.n_worlds, 3)))
+        _check(lib().b2g_batch_set_object_pose(self.h, obj, _ptr(pose)))
+
+    def getObjectPose(self, obj):
+        obj = self.model.object_index(obj) if isinstance(obj, str) else obj
+        pose = np.zeros((self.n_worlds, 3), np.float32)
+        _check(lib().b2g_batch_get_object_pose(self.h, obj, _ptr(pose)))
+        return pose
+
+    # -- controller (Box2DController.h:23)
+    def setTargetVelocity(self, robot, velocity):
+        robot = self.model.object_index(robot) if isinstance(robot, str) else robot
+        nd = self.model.objects[robot]["n_dofs"]
+        v = _f32(np.broadcast_to(_f32(velocity), (self.n_worlds, nd)))
+        if v.shape[-1] != nd:
+            raise B2GError(1, "[sim_env::Box2DRobotVelocityController::setTargetVelocity]"
+                              "Provided target velocity has invalid dimension.")
+        _check(lib().b2g_batch_set_target_velocity(self.h, robot, _ptr(v)))
+
+    # -- collision (:3846-3859 through Box2DCollisionChecker::updateContactCache :2880-2911)
+    def checkCollision(self, max_per_world=32):
+        counts = np.zeros(self.n_worlds, np.int32)
+        io = np.zeros((self.n_worlds, max_per_world, 4), np.int32)
+        fo = np.zeros((self.n_worlds, max_per_world, 6), np.float32)
+        _check(lib().b2g_batch_check_collision(self.h, _ptr(counts), _ptr(io), _ptr(fo), max_per_world))
+        return counts, io, fo
+
+    # -- parity probes
+    def bodies(self):
+        out = np.zeros((self.n_worlds, self.model.n_bodies, 16), np.float32)
+        _check(lib().b2g_batch_get_bodies(self.h, _ptr(out)))
+        return out
+
+    def fat_aabbs(self):
+        out = np.zeros((self.n_worlds, self.model.n_fixtures, 4), np.float32)
+        _check(lib().b2g_batch_get_fat_aabbs(self.h, _ptr(out)))
+        return out
+
+    def joints(self):
+        io = np.zeros((self.n_worlds, self.model.n_joints, 6), np.int32)
+        fo = np.zeros((self.n_worlds, self.model.n_joints, 15), np.float32)
+        _check(lib().b2g_batch_get_joints(self.h, _ptr(io), _ptr(fo)))
+        return io, fo
+
+    def contacts(self, max_per_world=32):
+        counts = np.zeros(self.n_worlds, np.int32)
+        io = np.zeros((self.n_worlds, max_per_world, 8), np.int32)
+        fo = np.zeros((self.n_worlds, max_per_world, 12), np.float32)
+        _check(lib().b2g_batch_get_contacts(self.h, _ptr(counts), _ptr(io), _ptr(fo), max_per_world))
+        return counts, io, fo
+
+    def status(self):
+        out = np.zeros(self.n_worlds, np.int32)
+        _check(lib().b2g_batch_status(self.h, _ptr(out)))
+        return out
+
+    def take_kernel_ms(self):
+        ms = C.c_float()
+        n = C.c_int32()
+        _check(lib().b2g_batch_take_kernel_ms(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # -- device-pointer entry points (torch / CUDA interop; pointers are raw ints)
+    def set_state_dev(self, q_ptr, qd_ptr, reset_caches=True):
+        _check(lib().b2g_batch_set_state_dev(self.h, C.c_void_p(q_ptr), C.c_void_p(qd_ptr), int(reset_caches)))
+
+    def get_state_dev(self, q_ptr, qd_ptr):
+        _check(lib().b2g_batch_get_state_dev(self.h, C.c_void_p(q_ptr), C.c_void_p(qd_ptr)))
+
+    def rollout_dev(self, robot, targets_ptr, n_targets, steps_per_target):
+        robot = self.model.object_index(robot) if isinstance(robot, str) else robot
+        _check(lib().b2g_batch_rollout_dev(self.h, robot, C.c_void_p(targets_ptr), int(n_targets), int(steps_per_target)))
+
+    def stream(self):
+        return lib().b2g_batch_stream(self.h)
+
+    def sync(self):
+        _check(lib().b2g_batch_sync(self.h))

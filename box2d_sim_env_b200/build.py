@@ -1,0 +1,50 @@
+"""Build libb2g.so (CUDA kernels + C ABI) in-tree for sm_100a.
+
+nvcc cross-compiles without a GPU.  --fmad=false keeps device arithmetic identical to the scalar SSE code the
+reference is compiled to (no FMA contraction); -lineinfo lets ncu map stalls to source lines.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libb2g.so")
+SOURCES = ["b2g_kernels.cu", "b2g_capi.cpp", "yaml_env.cpp", "model_build.cpp"]
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    for root, _, files in os.walk(CSRC):
+        for f in files:
+            if os.path.getmtime(os.path.join(root, f)) > t:
+                return True
+    if os.path.getmtime(os.path.join(HERE, "..", "include", "b2g.h")) > t:
+        return True
+    return False
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "--fmad=false", "-lineinfo", "-std=c++17",
+           "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", "-o", LIB] + SOURCES
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,644 @@
+// C ABI of the batched backend (include/b2g.h).  Host-side plumbing only: handles, device buffers, copies and
+// kernel launches.  There is deliberately no CPU implementation of any compute entry point: without a CUDA
+// device every one of them fails with B2G_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/b2g.h"
+#include "b2g_launch.h"
+#include "desc.h"
+#include "model_build.h"
+
+using namespace b2g;
+
+struct b2g_env {
+    EnvironmentDescription d;
+};
+struct b2g_model {
+    EnvironmentDescription env;
+    HostModel m;
+};
+
+namespace {
+thread_local std::string g_error;
+
+b2g_status fail(b2g_status code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+b2g_status cudaFail(cudaError_t e, const char* what) {
+    return fail(B2G_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                        \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) return cudaFail(e__, #call); \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct SavedState {
+    float* q = nullptr;
+    float* qd = nullptr;
+    std::vector<std::pair<int, float*>> staticPoses;
+};
+}  // namespace
+
+struct b2g_batch {
+    HostModel m;
+    int device = 0;
+    long long N = 0;
+    uint32_t* blob = nullptr;
+    float* S = nullptr;
+    float* tmpl = nullptr;
+    cudaStream_t stream = nullptr;
+    StepParams prm{0.01f, 15, 15};
+    int block = 32;
+    DevBuf stageA, stageB, stageC;
+    std::vector<SavedState> stack;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
+    std::vector<cudaEvent_t> eventPool;
+
+    Launch L() const {
+        Launch l;
+        l.h = m.h;
+        l.blob = blob;
+        l.S = S;
+        l.N = N;
+        l.prm = prm;
+        l.stream = stream;
+        l.block = block;
+        return l;
+    }
+};
+
+namespace {
+ObjectDescription* pickObject(b2g_env* env, int isRobot, int idx) {
+    auto& v = isRobot ? env->d.robots : env->d.objects;
+    if (idx < 0 || idx >= (int)v.size()) return nullptr;
+    return &v[idx];
+}
+cudaEvent_t getEvent(b2g_batch* b) {
+    if (!b->eventPool.empty()) {
+        cudaEvent_t e = b->eventPool.back();
+        b->eventPool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+}  // namespace
+
+extern "C" {
+
+const char* b2g_last_error(void) { return g_error.c_str(); }
+
+// ------------------------------------------------------------------------------------------------ environment
+b2g_status b2g_env_create(float scale, const float world_bounds[4], b2g_env** out) {
+    if (!out) return fail(B2G_ERR_INVALID, "out is null");
+    b2g_env* e = new b2g_env();
+    e->d.scale = scale;
+    for (int i = 0; i < 4; ++i) e->d.world_bounds[i] = world_bounds ? world_bounds[i] : 0.0f;
+    *out = e;
+    return B2G_OK;
+}
+
+b2g_status b2g_env_load_yaml(const char* path, b2g_env** out) {
+    if (!path || !out) return fail(B2G_ERR_INVALID, "null argument");
+    b2g_env* e = new b2g_env();
+    try {
+        parseYAML(path, e->d);
+    } catch (const std::exception& ex) {
+        delete e;
+        return fail(B2G_ERR_IO, ex.what());
+    }
+    *out = e;
+    return B2G_OK;
+}
+
+void b2g_env_destroy(b2g_env* env) { delete env; }
+
+b2g_status b2g_env_add_object(b2g_env* env, const char* name, int is_robot, int is_static, const float* base_limits8,
+                              int use_center_of_mass, int* out_index) {
+    if (!env || !name) return fail(B2G_ERR_INVALID, "null argument");
+    ObjectDescription o;
+    o.name = name;
+    o.is_robot = is_robot != 0;
+    o.is_static = is_static != 0;
+    o.use_center_of_mass = use_center_of_mass != 0;
+    if (base_limits8) {
+        for (int k = 0; k < 2; ++k) {
+            o.translational_velocity_limits[k] = base_limits8[k];
+            o.translational_acceleration_limits[k] = base_limits8[2 + k];
+            o.rotational_velocity_limits[k] = base_limits8[4 + k];
+            o.rotational_acceleration_limits[k] = base_limits8[6 + k];
+        }
+    }
+    auto& v = is_robot ? env->d.robots : env->d.objects;
+    v.push_back(o);
+    if (out_index) *out_index = (int)v.size() - 1;
+    return B2G_OK;
+}
+
+b2g_status b2g_env_add_link(b2g_env* env, int is_robot, int object, const char* name, float mass, float ground_friction,
+                            float ground_torque_integral, float contact_friction, float restitution, int* out_index) {
+    ObjectDescription* o = env ? pickObject(env, is_robot, object) : nullptr;
+    if (!o || !name) return fail(B2G_ERR_INVALID, "unknown object");
+    LinkDescription l;
+    l.name = name;
+    l.mass = mass;
+    l.ground_friction = ground_friction;
+    l.ground_torque_integral = ground_torque_integral;
+    l.contact_friction = contact_friction;
+    l.restitution = restitution;
+    o->links.push_back(l);
+    if (out_index) *out_index = (int)o->links.size() - 1;
+    return B2G_OK;
+}
+
+b2g_status b2g_env_add_polygon(b2g_env* env, int is_robot, int object, int link, const float* xy, int n_floats) {
+    ObjectDescription* o = env ? pickObject(env, is_robot, object) : nullptr;
+    if (!o || link < 0 || link >= (int)o->links.size() || !xy) return fail(B2G_ERR_INVALID, "unknown link");
+    if (n_floats < 6 || n_floats % 2) return fail(B2G_ERR_INVALID, "a polygon needs an even number (>= 6) of floats");
+    o->links[link].polygons.emplace_back(xy, xy + n_floats);
+    return B2G_OK;
+}
+
+b2g_status b2g_env_add_joint(b2g_env* env, int is_robot, int object, const char* name, const char* link_a, const char* link_b,
+                             const float* p, int actuated, const char* joint_type) {
+    ObjectDescription* o = env ? pickObject(env, is_robot, object) : nullptr;
+    if (!o || !name || !link_a || !link_b || !p || !joint_type) return fail(B2G_ERR_INVALID, "bad joint arguments");
+    JointDescription j;
+    j.name = name;
+    j.link_a = link_a;
+    j.link_b = link_b;
+    j.axis[0] = p[0]; j.axis[1] = p[1];
+    j.position_limits[0] = p[2]; j.position_limits[1] = p[3];
+    j.velocity_limits[0] = p[4]; j.velocity_limits[1] = p[5];
+    j.acceleration_limits[0] = p[6]; j.acceleration_limits[1] = p[7];
+    j.axis_orientation = p[8];
+    j.actuated = actuated != 0;
+    j.joint_type = joint_type;
+    o->joints.push_back(j);
+    return B2G_OK;
+}
+
+b2g_status b2g_env_add_state(b2g_env* env, const char* name, const float* configuration, const float* velocity, int n) {
+    if (!env || !name || !configuration || !velocity || n < 0) return fail(B2G_ERR_INVALID, "bad state arguments");
+    StateDescription s;
+    s.configuration.assign(configuration, configuration + n);
+    s.velocity.assign(velocity, velocity + n);
+    env->d.states[name] = s;
+    return B2G_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------ model
+b2g_status b2g_model_create(const b2g_env* env, b2g_model** out) {
+    if (!env || !out) return fail(B2G_ERR_INVALID, "null argument");
+    b2g_model* m = new b2g_model();
+    m->env = env->d;
+    try {
+        for (auto& o : m->env.robots) {
+            o.is_robot = true;
+            std::string msg;
+            if (!verifyKinematicStructure(o, msg)) throw std::runtime_error("robot '" + o.name + "': " + msg);
+        }
+        for (auto& o : m->env.objects) {
+            o.is_robot = false;
+            std::string msg;
+            if (!verifyKinematicStructure(o, msg)) throw std::runtime_error("object '" + o.name + "': " + msg);
+        }
+        buildModel(m->env, 0, m->m);
+    } catch (const std::exception& ex) {
+        std::string what = ex.what();
+        delete m;
+        bool unsupported = what.find("not supported") != std::string::npos;
+        return fail(unsupported ? B2G_ERR_UNSUPPORTED : B2G_ERR_INVALID, what);
+    }
+    *out = m;
+    return B2G_OK;
+}
+
+void b2g_model_destroy(b2g_model* model) { delete model; }
+
+b2g_status b2g_model_get_info(const b2g_model* model, b2g_model_info* out) {
+    if (!model || !out) return fail(B2G_ERR_INVALID, "null argument");
+    const ModelHeader& h = model->m.h;
+    out->n_bodies = h.nb; out->n_fixtures = h.nf; out->n_joints = h.nj; out->n_objects = h.no;
+    out->n_robots = h.nrobots; out->nq = h.nq; out->scale = h.scale;
+    return B2G_OK;
+}
+
+b2g_status b2g_model_get_object(const b2g_model* model, int object, b2g_object_info* out) {
+    if (!model || !out || object < 0 || object >= (int)model->m.objects.size()) return fail(B2G_ERR_INVALID, "unknown object");
+    const HostObjectInfo& o = model->m.objects[object];
+    memset(out, 0, sizeof(*out));
+    strncpy(out->name, o.name.c_str(), sizeof(out->name) - 1);
+    out->is_robot = o.isRobot; out->is_static = o.isStatic; out->n_dofs = o.nDofs; out->dof_offset = o.dofOffset;
+    out->first_body = o.firstBody; out->n_links = o.nLinks; out->n_joints = o.nJoints;
+    return B2G_OK;
+}
+
+b2g_status b2g_model_get_dof_limits(const b2g_model* model, float* out) {
+    if (!model || !out) return fail(B2G_ERR_INVALID, "null argument");
+    memcpy(out, model->m.dofLimits.data(), model->m.dofLimits.size() * sizeof(float));
+    return B2G_OK;
+}
+b2g_status b2g_model_get_bodies(const b2g_model* model, float* out) {
+    if (!model || !out) return fail(B2G_ERR_INVALID, "null argument");
+    memcpy(out, model->m.bodyModel.data(), model->m.bodyModel.size() * sizeof(float));
+    return B2G_OK;
+}
+b2g_status b2g_model_get_fixtures(const b2g_model* model, int32_t* iout, float* fout) {
+    if (!model || !iout || !fout) return fail(B2G_ERR_INVALID, "null argument");
+    memcpy(iout, model->m.fixInts.data(), model->m.fixInts.size() * sizeof(int32_t));
+    memcpy(fout, model->m.fixFloats.data(), model->m.fixFloats.size() * sizeof(float));
+    return B2G_OK;
+}
+b2g_status b2g_model_get_joints(const b2g_model* model, int32_t* iout, float* fout) {
+    if (!model || !iout || !fout) return fail(B2G_ERR_INVALID, "null argument");
+    memcpy(iout, model->m.jointInts.data(), model->m.jointInts.size() * sizeof(int32_t));
+    memcpy(fout, model->m.jointFloats.data(), model->m.jointFloats.size() * sizeof(float));
+    return B2G_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------ batch
+b2g_status b2g_batch_create(const b2g_model* model, int64_t n_worlds, int device, int max_contacts, b2g_batch** out) {
+    if (!model || !out || n_worlds <= 0) return fail(B2G_ERR_INVALID, "bad batch arguments");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(B2G_ERR_CUDA, std::string("no CUDA device available (the batched backend has no CPU fallback): ") +
+                                      cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(B2G_ERR_INVALID, "unknown device");
+    CU(cudaSetDevice(device));
+    b2g_batch* b = new b2g_batch();
+    b->m = model->m;
+    if (max_contacts > 0) layoutState(b->m.h, max_contacts > kMaxContacts ? kMaxContacts : max_contacts);
+    b->device = device;
+    b->N = n_worlds;
+    const char* envBlock = getenv("B2G_BLOCK");
+    if (envBlock) b->block = atoi(envBlock);
+    else b->block = n_worlds <= 148 * 32 * 8 ? 32 : 64;
+    if (b->block < 32 || b->block > 1024 || (b->block & 31)) b->block = 32;
+    auto cleanup = [&](cudaError_t err, const char* what) {
+        b2g_batch_destroy(b);
+        return cudaFail(err, what);
+    };
+    if ((e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate");
+    if ((e = cudaMalloc((void**)&b->blob, b->m.blob.size() * 4)) != cudaSuccess) return cleanup(e, "cudaMalloc(model)");
+    if ((e = cudaMemcpy(b->blob, b->m.blob.data(), b->m.blob.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return cleanup(e, "cudaMemcpy(model)");
+    size_t stateBytes = (size_t)b->m.h.stateWords * (size_t)n_worlds * 4;
+    if ((e = cudaMalloc((void**)&b->S, stateBytes)) != cudaSuccess) return cleanup(e, "cudaMalloc(state)");
+    if ((e = cudaMalloc((void**)&b->tmpl, (size_t)b->m.h.stateWords * 4)) != cudaSuccess) return cleanup(e, "cudaMalloc(template)");
+    // build the freshly loaded world once (world 0 of a 1-world launch), keep it as the template, broadcast
+    {
+        Launch l = b->L();
+        l.N = 1;
+        l.S = b->tmpl;  // a 1-world state array has the template's [slot] layout
+        if ((e = launchInit(l)) != cudaSuccess) return cleanup(e, "init kernel");
+        if ((e = launchBroadcast(b->L(), b->tmpl)) != cudaSuccess) return cleanup(e, "broadcast kernel");
+        if ((e = cudaStreamSynchronize(b->stream)) != cudaSuccess) return cleanup(e, "init sync");
+    }
+    *out = b;
+    return B2G_OK;
+}
+
+void b2g_batch_destroy(b2g_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (auto& s : b->stack) {
+        cudaFree(s.q);
+        cudaFree(s.qd);
+        for (auto& p : s.staticPoses) cudaFree(p.second);
+    }
+    for (auto& p : b->timed) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (auto& ev : b->eventPool) cudaEventDestroy(ev);
+    b->stageA.release(); b->stageB.release(); b->stageC.release();
+    if (b->blob) cudaFree(b->blob);
+    if (b->S) cudaFree(b->S);
+    if (b->tmpl) cudaFree(b->tmpl);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+b2g_status b2g_batch_set_params(b2g_batch* b, float dt, int velocity_steps, int position_steps) {
+    if (!b || !(dt > 0.0f) || velocity_steps < 0 || position_steps < 0) return fail(B2G_ERR_INVALID, "bad step parameters");
+    b->prm.dt = dt;
+    b->prm.velIters = velocity_steps;
+    b->prm.posIters = position_steps;
+    return B2G_OK;
+}
+
+void* b2g_batch_stream(b2g_batch* b) { return b ? (void*)b->stream : nullptr; }
+
+b2g_status b2g_batch_sync(b2g_batch* b) {
+    if (!b) return fail(B2G_ERR_INVALID, "null batch");
+    CU(cudaSetDevice(b->device));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_status(b2g_batch* b, int32_t* out) {
+    if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    CU(b->stageA.reserve((size_t)b->N * 4));
+    CU(launchStatus(b->L(), (int*)b->stageA.p));
+    CU(cudaMemcpyAsync(out, b->stageA.p, (size_t)b->N * 4, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    for (long long i = 0; i < b->N; ++i)
+        if (out[i] & 1) return fail(B2G_ERR_CAPACITY, "world " + std::to_string(i) + " exceeded its contact-slot capacity");
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_set_state_dev(b2g_batch* b, const float* q, const float* qd, int reset_caches) {
+    if (!b || !q || !qd) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    if (reset_caches) CU(launchBroadcast(b->L(), b->tmpl));
+    CU(launchSetState(b->L(), q, qd));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_set_state(b2g_batch* b, const float* q, const float* qd, int reset_caches) {
+    if (!b || !q || !qd) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    size_t bytes = (size_t)b->N * b->m.h.nq * 4;
+    CU(b->stageA.reserve(bytes));
+    CU(b->stageB.reserve(bytes));
+    CU(cudaMemcpyAsync(b->stageA.p, q, bytes, cudaMemcpyHostToDevice, b->stream));
+    CU(cudaMemcpyAsync(b->stageB.p, qd, bytes, cudaMemcpyHostToDevice, b->stream));
+    b2g_status s = b2g_batch_set_state_dev(b, (const float*)b->stageA.p, (const float*)b->stageB.p, reset_caches);
+    if (s) return s;
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_get_state_dev(b2g_batch* b, float* q, float* qd) {
+    if (!b || !q || !qd) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    CU(launchGetState(b->L(), q, qd));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_get_state(b2g_batch* b, float* q, float* qd) {
+    if (!b || !q || !qd) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    size_t bytes = (size_t)b->N * b->m.h.nq * 4;
+    CU(b->stageA.reserve(bytes));
+    CU(b->stageB.reserve(bytes));
+    b2g_status s = b2g_batch_get_state_dev(b, (float*)b->stageA.p, (float*)b->stageB.p);
+    if (s) return s;
+    CU(cudaMemcpyAsync(q, b->stageA.p, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(qd, b->stageB.p, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_set_object_pose(b2g_batch* b, int object, const float* pose) {
+    if (!b || !pose || object < 0 || object >= b->m.h.no) return fail(B2G_ERR_INVALID, "unknown object");
+    CU(cudaSetDevice(b->device));
+    size_t bytes = (size_t)b->N * 3 * 4;
+    CU(b->stageA.reserve(bytes));
+    CU(cudaMemcpyAsync(b->stageA.p, pose, bytes, cudaMemcpyHostToDevice, b->stream));
+    CU(launchSetPose(b->L(), object, (const float*)b->stageA.p));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_get_object_pose(b2g_batch* b, int object, float* pose) {
+    if (!b || !pose || object < 0 || object >= b->m.h.no) return fail(B2G_ERR_INVALID, "unknown object");
+    CU(cudaSetDevice(b->device));
+    size_t bytes = (size_t)b->N * 3 * 4;
+    CU(b->stageA.reserve(bytes));
+    CU(launchGetPose(b->L(), object, (float*)b->stageA.p));
+    CU(cudaMemcpyAsync(pose, b->stageA.p, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+static b2g_status checkRobot(b2g_batch* b, int object) {
+    if (!b || object < 0 || object >= b->m.h.no) return fail(B2G_ERR_INVALID, "unknown object");
+    if (!b->m.objects[object].isRobot)
+        return fail(B2G_ERR_INVALID, "object '" + b->m.objects[object].name + "' is not a robot: it has no velocity controller");
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_set_target_velocity_dev(b2g_batch* b, int object, const float* v) {
+    b2g_status s = checkRobot(b, object);
+    if (s) return s;
+    if (!v) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    CU(launchSetTarget(b->L(), object, v));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_set_target_velocity(b2g_batch* b, int object, const float* v) {
+    b2g_status s = checkRobot(b, object);
+    if (s) return s;
+    if (!v) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    size_t bytes = (size_t)b->N * b->m.objects[object].nDofs * 4;
+    CU(b->stageA.reserve(bytes));
+    CU(cudaMemcpyAsync(b->stageA.p, v, bytes, cudaMemcpyHostToDevice, b->stream));
+    CU(launchSetTarget(b->L(), object, (const float*)b->stageA.p));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+static b2g_status timedStep(b2g_batch* b, int object, const float* targets, int nTargets, int stepsPerTarget, int execCtrl,
+                            int allowSleep) {
+    cudaEvent_t e0 = getEvent(b), e1 = getEvent(b);
+    CU(cudaEventRecord(e0, b->stream));
+    CU(launchStep(b->L(), object, targets, nTargets, stepsPerTarget, execCtrl, allowSleep));
+    CU(cudaEventRecord(e1, b->stream));
+    b->timed.emplace_back(e0, e1);
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_step(b2g_batch* b, int steps, int execute_controllers, int allow_sleeping) {
+    if (!b || steps < 0) return fail(B2G_ERR_INVALID, "bad step arguments");
+    CU(cudaSetDevice(b->device));
+    if (steps == 0) return B2G_OK;
+    b2g_status s = timedStep(b, 0, nullptr, 1, steps, execute_controllers, allow_sleeping);
+    if (s) return s;
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_rollout_dev(b2g_batch* b, int object, const float* targets, int n_targets, int steps_per_target) {
+    b2g_status s = checkRobot(b, object);
+    if (s) return s;
+    if (!targets || n_targets < 0 || steps_per_target < 0) return fail(B2G_ERR_INVALID, "bad rollout arguments");
+    CU(cudaSetDevice(b->device));
+    if (n_targets == 0) return B2G_OK;
+    return timedStep(b, object, targets, n_targets, steps_per_target, 1, 1);
+}
+
+b2g_status b2g_batch_take_kernel_ms(b2g_batch* b, float* out_ms, int32_t* out_launches) {
+    if (!b || !out_ms) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    CU(cudaStreamSynchronize(b->stream));
+    float total = 0.0f;
+    for (auto& p : b->timed) {
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, p.first, p.second));
+        total += ms;
+        b->eventPool.push_back(p.first);
+        b->eventPool.push_back(p.second);
+    }
+    if (out_launches) *out_launches = (int32_t)b->timed.size();
+    b->timed.clear();
+    *out_ms = total;
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_get_bodies(b2g_batch* b, float* out) {
+    if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    size_t bytes = (size_t)b->N * b->m.h.nb * 16 * 4;
+    CU(b->stageA.reserve(bytes));
+    CU(launchGetBodies(b->L(), (float*)b->stageA.p));
+    CU(cudaMemcpyAsync(out, b->stageA.p, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_get_fat_aabbs(b2g_batch* b, float* out) {
+    if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    size_t bytes = (size_t)b->N * b->m.h.nf * 4 * 4;
+    CU(b->stageA.reserve(bytes));
+    CU(launchGetFat(b->L(), (float*)b->stageA.p));
+    CU(cudaMemcpyAsync(out, b->stageA.p, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_get_joints(b2g_batch* b, int32_t* iout, float* fout) {
+    if (!b || !iout || !fout) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    size_t ib = (size_t)b->N * b->m.h.nj * 6 * 4, fb = (size_t)b->N * b->m.h.nj * 15 * 4;
+    CU(b->stageA.reserve(ib));
+    CU(b->stageB.reserve(fb));
+    CU(launchGetJoints(b->L(), (int*)b->stageA.p, (float*)b->stageB.p));
+    CU(cudaMemcpyAsync(iout, b->stageA.p, ib, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(fout, b->stageB.p, fb, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_get_contacts(b2g_batch* b, int32_t* counts, int32_t* iout, float* fout, int max_per_world) {
+    if (!b || !counts || !iout || !fout || max_per_world <= 0) return fail(B2G_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(b->device));
+    size_t cb = (size_t)b->N * 4, ib = (size_t)b->N * max_per_world * 8 * 4, fb = (size_t)b->N * max_per_world * 12 * 4;
+    CU(b->stageA.reserve(ib));
+    CU(b->stageB.reserve(fb));
+    CU(b->stageC.reserve(cb));
+    CU(cudaMemsetAsync(b->stageA.p, 0, ib, b->stream));
+    CU(cudaMemsetAsync(b->stageB.p, 0, fb, b->stream));
+    CU(launchGetContacts(b->L(), (int*)b->stageC.p, (int*)b->stageA.p, (float*)b->stageB.p, max_per_world));
+    CU(cudaMemcpyAsync(counts, b->stageC.p, cb, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(iout, b->stageA.p, ib, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(fout, b->stageB.p, fb, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_check_collision(b2g_batch* b, int32_t* counts, int32_t* iout, float* fout, int max_per_world) {
+    if (!b || !counts || !iout || !fout || max_per_world <= 0) return fail(B2G_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(b->device));
+    size_t cb = (size_t)b->N * 4, ib = (size_t)b->N * max_per_world * 4 * 4, fb = (size_t)b->N * max_per_world * 6 * 4;
+    CU(b->stageA.reserve(ib));
+    CU(b->stageB.reserve(fb));
+    CU(b->stageC.reserve(cb));
+    CU(cudaMemsetAsync(b->stageA.p, 0, ib, b->stream));
+    CU(cudaMemsetAsync(b->stageB.p, 0, fb, b->stream));
+    CU(launchCheckCollision(b->L(), (int*)b->stageC.p, (int*)b->stageA.p, (float*)b->stageB.p, max_per_world));
+    CU(cudaMemcpyAsync(counts, b->stageC.p, cb, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(iout, b->stageA.p, ib, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(fout, b->stageB.p, fb, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- state stack
+b2g_status b2g_batch_save_state(b2g_batch* b) {
+    if (!b) return fail(B2G_ERR_INVALID, "null batch");
+    CU(cudaSetDevice(b->device));
+    SavedState s;
+    size_t bytes = (size_t)b->N * b->m.h.nq * 4;
+    CU(cudaMalloc((void**)&s.q, bytes));
+    CU(cudaMalloc((void**)&s.qd, bytes));
+    CU(launchGetState(b->L(), s.q, s.qd));
+    for (int o = 0; o < b->m.h.no; ++o) {
+        if (!b->m.objects[o].isStatic) continue;
+        float* p = nullptr;
+        CU(cudaMalloc((void**)&p, (size_t)b->N * 3 * 4));
+        CU(launchGetPose(b->L(), o, p));
+        s.staticPoses.emplace_back(o, p);
+    }
+    b->stack.push_back(s);
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_drop_state(b2g_batch* b) {
+    if (!b) return fail(B2G_ERR_INVALID, "null batch");
+    if (b->stack.empty()) return B2G_OK;
+    CU(cudaSetDevice(b->device));
+    SavedState s = b->stack.back();
+    b->stack.pop_back();
+    cudaFree(s.q);
+    cudaFree(s.qd);
+    for (auto& p : s.staticPoses) cudaFree(p.second);
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_restore_state(b2g_batch* b) {
+    if (!b) return fail(B2G_ERR_INVALID, "null batch");
+    if (b->stack.empty()) return fail(B2G_ERR_INVALID, "state stack is empty");  // reference returns false (:3526-3528)
+    CU(cudaSetDevice(b->device));
+    SavedState& s = b->stack.back();
+    for (auto& p : s.staticPoses) CU(launchSetPose(b->L(), p.first, p.second));
+    CU(launchSetState(b->L(), s.q, s.qd));
+    CU(cudaStreamSynchronize(b->stream));
+    return b2g_batch_drop_state(b);
+}
+
+// ------------------------------------------------------------------------------------------------------ misc
+b2g_status b2g_host_alloc(void** out, uint64_t bytes) {
+    if (!out) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return B2G_OK;
+}
+void b2g_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+uint64_t b2g_launch_count(void) { return launchCount(); }
+
+}  // extern "C"

@@ -1,0 +1,563 @@
+// Device-side building blocks of the batched Box2D backend (sm_100a, one world per thread).
+//
+// Data layout: every mutable quantity of world w lives in one word array S[slot][world] (world index
+// fastest), so a warp touching the same slot of 32 consecutive worlds issues one coalesced 128-byte
+// request.  The immutable model blob (model.h) is staged in shared memory by every CTA.
+//
+// Arithmetic: IEEE single precision, compiled with --fmad=false, IEEE division and square root, and a
+// fixed-sequence sin/cos, so that results are reproducible bit for bit across launches, GPU counts and
+// against the CPU oracle.  Formulas follow Box2D 2.3.1, which is what the
+// reference calls through b2World::Step (src/sim_env/Box2DWorld.cpp:3279).
+#pragma once
+#include <cfloat>
+#include <cstdint>
+
+#include "model.h"
+
+namespace b2g {
+
+// ---- Box2D constants (b2Settings.h 2.3.1) ------------------------------------------------------------
+#define B2G_PI 3.14159265359f
+#define B2G_LINEAR_SLOP 0.005f
+#define B2G_ANGULAR_SLOP (2.0f / 180.0f * B2G_PI)
+#define B2G_POLYGON_RADIUS (2.0f * B2G_LINEAR_SLOP)
+#define B2G_AABB_EXTENSION 0.1f
+#define B2G_AABB_MULTIPLIER 2.0f
+#define B2G_MAX_SUB_STEPS 8
+#define B2G_MAX_TOI_CONTACTS 32
+#define B2G_VELOCITY_THRESHOLD 1.0f
+#define B2G_MAX_LINEAR_CORRECTION 0.2f
+#define B2G_MAX_ANGULAR_CORRECTION (8.0f / 180.0f * B2G_PI)
+#define B2G_MAX_TRANSLATION 2.0f
+#define B2G_MAX_ROTATION (0.5f * B2G_PI)
+#define B2G_BAUMGARTE 0.2f
+#define B2G_TOI_BAUMGARTE 0.75f
+#define B2G_TIME_TO_SLEEP 0.5f
+#define B2G_LINEAR_SLEEP_TOL 0.01f
+#define B2G_ANGULAR_SLEEP_TOL (2.0f / 180.0f * B2G_PI)
+
+#define DEV __device__ __forceinline__
+#define DEVN __device__ __noinline__
+
+struct V2 {
+    float x, y;
+};
+struct V3 {
+    float x, y, z;
+};
+struct Rot {
+    float s, c;
+};
+struct XF {
+    V2 p;
+    Rot q;
+};
+
+DEV V2 mk(float x, float y) { V2 v; v.x = x; v.y = y; return v; }
+DEV V2 operator+(V2 a, V2 b) { return mk(a.x + b.x, a.y + b.y); }
+DEV V2 operator-(V2 a, V2 b) { return mk(a.x - b.x, a.y - b.y); }
+DEV V2 operator-(V2 a) { return mk(-a.x, -a.y); }
+DEV V2 operator*(float s, V2 a) { return mk(s * a.x, s * a.y); }
+DEV float dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
+DEV float cross(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }
+DEV V2 cross(V2 a, float s) { return mk(s * a.y, -s * a.x); }
+DEV V2 cross(float s, V2 a) { return mk(-s * a.y, s * a.x); }
+DEV float fminT(float a, float b) { return a < b ? a : b; }  // b2Min / b2Max are ternaries, not fminf
+DEV float fmaxT(float a, float b) { return a > b ? a : b; }
+DEV float clampT(float a, float lo, float hi) { return fmaxT(lo, fminT(a, hi)); }
+DEV float absT(float a) { return a > 0.0f ? a : -a; }
+DEV float length(V2 v) { return sqrtf(v.x * v.x + v.y * v.y); }
+DEV float normalize(V2& v) {
+    float len = length(v);
+    if (len < FLT_EPSILON) return 0.0f;
+    float inv = 1.0f / len;
+    v.x *= inv;
+    v.y *= inv;
+    return len;
+}
+
+// Shared deterministic sin/cos: Cody-Waite reduction by pi/2 + Cephes single-precision cores.
+DEV Rot rotOf(float x) {
+    float kf = rintf(x * 0.636619772367581343f);
+    float r = x - kf * 1.5703125f;
+    r = r - kf * 4.837512969970703125e-4f;
+    r = r - kf * 7.54978995489188216e-8f;
+    float z = r * r;
+    float ps = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
+    float pc = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z;
+    pc = pc - 0.5f * z;
+    pc = pc + 1.0f;
+    int q = ((int)kf) & 3;
+    Rot o;
+    if (q == 0) { o.s = ps; o.c = pc; }
+    else if (q == 1) { o.s = pc; o.c = -ps; }
+    else if (q == 2) { o.s = -ps; o.c = -pc; }
+    else { o.s = -pc; o.c = ps; }
+    return o;
+}
+
+DEV V2 mul(Rot q, V2 v) { return mk(q.c * v.x - q.s * v.y, q.s * v.x + q.c * v.y); }
+DEV V2 mulT(Rot q, V2 v) { return mk(q.c * v.x + q.s * v.y, -q.s * v.x + q.c * v.y); }
+DEV V2 mul(const XF& T, V2 v) {
+    float x = (T.q.c * v.x - T.q.s * v.y) + T.p.x;
+    float y = (T.q.s * v.x + T.q.c * v.y) + T.p.y;
+    return mk(x, y);
+}
+DEV V2 mulT(const XF& T, V2 v) {
+    float px = v.x - T.p.x;
+    float py = v.y - T.p.y;
+    return mk((T.q.c * px + T.q.s * py), (-T.q.s * px + T.q.c * py));
+}
+DEV XF mulT(const XF& A, const XF& B) {
+    XF C;
+    C.q.s = A.q.c * B.q.s - A.q.s * B.q.c;
+    C.q.c = A.q.c * B.q.c + A.q.s * B.q.s;
+    C.p = mulT(A.q, B.p - A.p);
+    return C;
+}
+DEV V2 solve22(float a11, float a12, float a21, float a22, V2 b) {
+    float det = a11 * a22 - a12 * a21;
+    if (det != 0.0f) det = 1.0f / det;
+    V2 x;
+    x.x = det * (a22 * b.x - a12 * b.y);
+    x.y = det * (a11 * b.y - a21 * b.x);
+    return x;
+}
+
+// ---- world context ----------------------------------------------------------------------------------------
+struct Ctx {
+    float* S;                  // &state[world]; slot s lives at S[s * N]
+    size_t N;                  // number of worlds (slot stride)
+    const uint32_t* M;         // model blob (shared memory)
+    const ModelHeader* h;      // model header (shared memory)
+    float dt, inv_dt;
+    int velIters, posIters;
+};
+
+DEV float ldF(const Ctx& c, int slot) { return c.S[(size_t)slot * c.N]; }
+DEV void stF(const Ctx& c, int slot, float v) { c.S[(size_t)slot * c.N] = v; }
+DEV int ldI(const Ctx& c, int slot) { return __float_as_int(c.S[(size_t)slot * c.N]); }
+DEV void stI(const Ctx& c, int slot, int v) { c.S[(size_t)slot * c.N] = __int_as_float(v); }
+DEV float mF(const Ctx& c, int off) { return __uint_as_float(c.M[off]); }
+DEV int mI(const Ctx& c, int off) { return (int)c.M[off]; }
+
+DEV int bslot(const Ctx& c, int b, int f) { return c.h->sBody + b * SB_STRIDE + f; }
+DEV int jslot(const Ctx& c, int j, int f) { return c.h->sJoint + j * SJ_STRIDE + f; }
+DEV int jwslot(const Ctx& c, int j, int f) { return c.h->sJointW + j * WJ_STRIDE + f; }
+DEV int cslot(const Ctx& c, int k, int f) { return c.h->sCont + k * SC_STRIDE + f; }
+DEV int cwslot(const Ctx& c, int k, int f) { return c.h->sContW + k * WC_STRIDE + f; }
+DEV int sslot(const Ctx& c, int f) { return c.h->sScalar + f; }
+DEV int mbody(const Ctx& c, int b, int f) { return c.h->oBody + b * MB_STRIDE + f; }
+DEV int mfix(const Ctx& c, int f, int k) { return c.h->oFix + f * MF_STRIDE + k; }
+DEV int mjoint(const Ctx& c, int j, int f) { return c.h->oJoint + j * MJ_STRIDE + f; }
+DEV int mobj(const Ctx& c, int o, int f) { return c.h->oObj + o * MO_STRIDE + f; }
+
+DEV V2 ldV2(const Ctx& c, int slot) { return mk(ldF(c, slot), ldF(c, slot + 1)); }
+DEV void stV2(const Ctx& c, int slot, V2 v) { stF(c, slot, v.x); stF(c, slot + 1, v.y); }
+DEV XF ldXF(const Ctx& c, int b) {
+    XF x;
+    x.p = ldV2(c, bslot(c, b, SB_PX));
+    x.q.s = ldF(c, bslot(c, b, SB_QS));
+    x.q.c = ldF(c, bslot(c, b, SB_QC));
+    return x;
+}
+DEV void stXF(const Ctx& c, int b, const XF& x) {
+    stV2(c, bslot(c, b, SB_PX), x.p);
+    stF(c, bslot(c, b, SB_QS), x.q.s);
+    stF(c, bslot(c, b, SB_QC), x.q.c);
+}
+DEV V2 localCenter(const Ctx& c, int b) { return mk(mF(c, mbody(c, b, MB_LCX)), mF(c, mbody(c, b, MB_LCY))); }
+DEV bool isAwake(const Ctx& c, int b) { return (ldI(c, bslot(c, b, SB_FLAGS)) & 1) != 0; }
+DEV int bodyType(const Ctx& c, int b) { return mI(c, mbody(c, b, MB_TYPE)); }
+
+// b2Body::SetAwake
+DEV void wakeBody(const Ctx& c, int b) {
+    int f = ldI(c, bslot(c, b, SB_FLAGS));
+    if ((f & 1) == 0) {
+        stI(c, bslot(c, b, SB_FLAGS), f | 1);
+        stF(c, bslot(c, b, SB_SLEEP), 0.0f);
+    }
+}
+DEV void sleepBody(const Ctx& c, int b) {
+    int f = ldI(c, bslot(c, b, SB_FLAGS));
+    stI(c, bslot(c, b, SB_FLAGS), f & ~1);
+    stF(c, bslot(c, b, SB_SLEEP), 0.0f);
+    stF(c, bslot(c, b, SB_VX), 0.0f);
+    stF(c, bslot(c, b, SB_VY), 0.0f);
+    stF(c, bslot(c, b, SB_W), 0.0f);
+    stF(c, bslot(c, b, SB_FX), 0.0f);
+    stF(c, bslot(c, b, SB_FY), 0.0f);
+    stF(c, bslot(c, b, SB_TORQUE), 0.0f);
+}
+
+// ---- broad phase: fat AABBs, move buffer as a 64-bit mask ---------------------------------------------------
+struct Box {
+    float lx, ly, ux, uy;
+};
+DEV Box ldFat(const Ctx& c, int f) {
+    Box b;
+    int s = c.h->sFix + f * 4;
+    b.lx = ldF(c, s); b.ly = ldF(c, s + 1); b.ux = ldF(c, s + 2); b.uy = ldF(c, s + 3);
+    return b;
+}
+DEV bool boxOverlap(const Box& a, const Box& b) {
+    float d1x = b.lx - a.ux, d1y = b.ly - a.uy;
+    float d2x = a.lx - b.ux, d2y = a.ly - b.uy;
+    if (d1x > 0.0f || d1y > 0.0f) return false;
+    if (d2x > 0.0f || d2y > 0.0f) return false;
+    return true;
+}
+DEV uint64_t ldMoved(const Ctx& c) {
+    return (uint64_t)(uint32_t)ldI(c, sslot(c, SS_MOVED_LO)) | ((uint64_t)(uint32_t)ldI(c, sslot(c, SS_MOVED_HI)) << 32);
+}
+DEV void stMoved(const Ctx& c, uint64_t m) {
+    stI(c, sslot(c, SS_MOVED_LO), (int)(uint32_t)(m & 0xffffffffull));
+    stI(c, sslot(c, SS_MOVED_HI), (int)(uint32_t)(m >> 32));
+}
+
+// b2PolygonShape::ComputeAABB
+DEV Box fixtureAABB(const Ctx& c, int f, const XF& xf) {
+    int n = mI(c, mfix(c, f, MF_COUNT));
+    int vo = mfix(c, f, MF_VERTS);
+    V2 lower = mul(xf, mk(mF(c, vo), mF(c, vo + 1)));
+    V2 upper = lower;
+    for (int i = 1; i < n; ++i) {
+        V2 v = mul(xf, mk(mF(c, vo + 2 * i), mF(c, vo + 2 * i + 1)));
+        lower = mk(fminT(lower.x, v.x), fminT(lower.y, v.y));
+        upper = mk(fmaxT(upper.x, v.x), fmaxT(upper.y, v.y));
+    }
+    Box b;
+    b.lx = lower.x - B2G_POLYGON_RADIUS; b.ly = lower.y - B2G_POLYGON_RADIUS;
+    b.ux = upper.x + B2G_POLYGON_RADIUS; b.uy = upper.y + B2G_POLYGON_RADIUS;
+    return b;
+}
+
+// b2Fixture::Synchronize + b2DynamicTree::MoveProxy; returns the bit to add to the move buffer
+DEV uint64_t syncFixture(const Ctx& c, int f, const XF& xf1, const XF& xf2) {
+    Box a1 = fixtureAABB(c, f, xf1);
+    Box a2 = fixtureAABB(c, f, xf2);
+    Box a;
+    a.lx = fminT(a1.lx, a2.lx); a.ly = fminT(a1.ly, a2.ly);
+    a.ux = fmaxT(a1.ux, a2.ux); a.uy = fmaxT(a1.uy, a2.uy);
+    V2 disp = xf2.p - xf1.p;
+    Box fat = ldFat(c, f);
+    bool contains = fat.lx <= a.lx && fat.ly <= a.ly && a.ux <= fat.ux && a.uy <= fat.uy;
+    if (contains) return 0ull;
+    Box b;
+    b.lx = a.lx - B2G_AABB_EXTENSION; b.ly = a.ly - B2G_AABB_EXTENSION;
+    b.ux = a.ux + B2G_AABB_EXTENSION; b.uy = a.uy + B2G_AABB_EXTENSION;
+    V2 d = B2G_AABB_MULTIPLIER * disp;
+    if (d.x < 0.0f) b.lx += d.x; else b.ux += d.x;
+    if (d.y < 0.0f) b.ly += d.y; else b.uy += d.y;
+    int s = c.h->sFix + f * 4;
+    stF(c, s, b.lx); stF(c, s + 1, b.ly); stF(c, s + 2, b.ux); stF(c, s + 3, b.uy);
+    return 1ull << f;
+}
+
+// b2Body::SynchronizeFixtures / SetTransform tail: fixtures in upstream list order (newest first)
+DEV uint64_t syncBodyFixtures(const Ctx& c, int b, const XF& xf1, const XF& xf2) {
+    int start = mI(c, mbody(c, b, MB_FIX_START));
+    int cnt = mI(c, mbody(c, b, MB_FIX_COUNT));
+    uint64_t moved = 0ull;
+    for (int f = start + cnt - 1; f >= start; --f) moved |= syncFixture(c, f, xf1, xf2);
+    return moved;
+}
+
+// b2Body::SetTransform (2.3.1: no FindNewContacts here)
+DEV void setTransform(const Ctx& c, int b, V2 position, float angle) {
+    XF xf;
+    xf.q = rotOf(angle);
+    xf.p = position;
+    stXF(c, b, xf);
+    V2 cc = mul(xf, localCenter(c, b));
+    stV2(c, bslot(c, b, SB_CX), cc);
+    stF(c, bslot(c, b, SB_A), angle);
+    stV2(c, bslot(c, b, SB_C0X), cc);
+    stF(c, bslot(c, b, SB_A0), angle);
+    uint64_t moved = syncBodyFixtures(c, b, xf, xf);
+    if (moved) stMoved(c, ldMoved(c) | moved);
+}
+
+// b2Body::SynchronizeTransform
+DEV void syncTransform(const Ctx& c, int b) {
+    XF xf;
+    float a = ldF(c, bslot(c, b, SB_A));
+    xf.q = rotOf(a);
+    V2 cc = ldV2(c, bslot(c, b, SB_CX));
+    xf.p = cc - mul(xf.q, localCenter(c, b));
+    stXF(c, b, xf);
+}
+
+// ---- narrow phase: b2CollidePolygons (2.3.1) ---------------------------------------------------------------
+struct Manifold {
+    int type;        // 1 faceA, 2 faceB
+    int pointCount;
+    V2 localNormal, localPoint;
+    V2 pt[2];
+    uint32_t id[2];
+};
+
+DEV uint32_t makeId(int indexA, int indexB, int typeA, int typeB) {
+    return (uint32_t)(indexA & 0xff) | ((uint32_t)(indexB & 0xff) << 8) | ((uint32_t)(typeA & 0xff) << 16) |
+           ((uint32_t)(typeB & 0xff) << 24);
+}
+
+struct ClipV {
+    V2 v;
+    uint32_t id;
+};
+
+DEV int clipSegmentToLine(ClipV out[2], const ClipV in[2], V2 normal, float offset, int vertexIndexA) {
+    int numOut = 0;
+    float distance0 = dot(normal, in[0].v) - offset;
+    float distance1 = dot(normal, in[1].v) - offset;
+    if (distance0 <= 0.0f) out[numOut++] = in[0];
+    if (distance1 <= 0.0f) out[numOut++] = in[1];
+    if (distance0 * distance1 < 0.0f) {
+        float interp = distance0 / (distance0 - distance1);
+        out[numOut].v = in[0].v + interp * (in[1].v - in[0].v);
+        // vertex (type 0) of A hitting face (type 1) of B
+        out[numOut].id = makeId(vertexIndexA, (in[0].id >> 8) & 0xff, 0, 1);
+        ++numOut;
+    }
+    return numOut;
+}
+
+DEV V2 fixVert(const Ctx& c, int f, int i) { int o = mfix(c, f, MF_VERTS) + 2 * i; return mk(mF(c, o), mF(c, o + 1)); }
+DEV V2 fixNormal(const Ctx& c, int f, int i) { int o = mfix(c, f, MF_NORMALS) + 2 * i; return mk(mF(c, o), mF(c, o + 1)); }
+
+DEV float findMaxSeparation(const Ctx& c, int* edgeIndex, int f1, const XF& xf1, int f2, const XF& xf2) {
+    int count1 = mI(c, mfix(c, f1, MF_COUNT));
+    int count2 = mI(c, mfix(c, f2, MF_COUNT));
+    XF xf = mulT(xf2, xf1);
+    int bestIndex = 0;
+    float maxSeparation = -FLT_MAX;
+    for (int i = 0; i < count1; ++i) {
+        V2 n = mul(xf.q, fixNormal(c, f1, i));
+        V2 v1 = mul(xf, fixVert(c, f1, i));
+        float si = FLT_MAX;
+        for (int j = 0; j < count2; ++j) {
+            float sij = dot(n, fixVert(c, f2, j) - v1);
+            if (sij < si) si = sij;
+        }
+        if (si > maxSeparation) { maxSeparation = si; bestIndex = i; }
+    }
+    *edgeIndex = bestIndex;
+    return maxSeparation;
+}
+
+DEVN void collidePolygons(const Ctx& c, Manifold& m, int fA, const XF& xfA, int fB, const XF& xfB) {
+    m.pointCount = 0;
+    const float totalRadius = B2G_POLYGON_RADIUS + B2G_POLYGON_RADIUS;
+    int edgeA = 0;
+    float separationA = findMaxSeparation(c, &edgeA, fA, xfA, fB, xfB);
+    if (separationA > totalRadius) return;
+    int edgeB = 0;
+    float separationB = findMaxSeparation(c, &edgeB, fB, xfB, fA, xfA);
+    if (separationB > totalRadius) return;
+
+    int f1, f2, edge1, flip;
+    XF xf1, xf2;
+    const float k_tol = 0.1f * B2G_LINEAR_SLOP;
+    if (separationB > separationA + k_tol) {
+        f1 = fB; f2 = fA; xf1 = xfB; xf2 = xfA; edge1 = edgeB; m.type = 2; flip = 1;
+    } else {
+        f1 = fA; f2 = fB; xf1 = xfA; xf2 = xfB; edge1 = edgeA; m.type = 1; flip = 0;
+    }
+    // b2FindIncidentEdge
+    ClipV incident[2];
+    {
+        int count2 = mI(c, mfix(c, f2, MF_COUNT));
+        V2 normal1 = mulT(xf2.q, mul(xf1.q, fixNormal(c, f1, edge1)));
+        int index = 0;
+        float minDot = FLT_MAX;
+        for (int i = 0; i < count2; ++i) {
+            float d = dot(normal1, fixNormal(c, f2, i));
+            if (d < minDot) { minDot = d; index = i; }
+        }
+        int i1 = index;
+        int i2 = i1 + 1 < count2 ? i1 + 1 : 0;
+        incident[0].v = mul(xf2, fixVert(c, f2, i1));
+        incident[0].id = makeId(edge1, i1, 1, 0);
+        incident[1].v = mul(xf2, fixVert(c, f2, i2));
+        incident[1].id = makeId(edge1, i2, 1, 0);
+    }
+    int count1 = mI(c, mfix(c, f1, MF_COUNT));
+    int iv1 = edge1;
+    int iv2 = edge1 + 1 < count1 ? edge1 + 1 : 0;
+    V2 v11 = fixVert(c, f1, iv1);
+    V2 v12 = fixVert(c, f1, iv2);
+    V2 localTangent = v12 - v11;
+    normalize(localTangent);
+    V2 localNormal = cross(localTangent, 1.0f);
+    V2 planePoint = 0.5f * (v11 + v12);
+    V2 tangent = mul(xf1.q, localTangent);
+    V2 normal = cross(tangent, 1.0f);
+    v11 = mul(xf1, v11);
+    v12 = mul(xf1, v12);
+    float frontOffset = dot(normal, v11);
+    float sideOffset1 = -dot(tangent, v11) + totalRadius;
+    float sideOffset2 = dot(tangent, v12) + totalRadius;
+
+    ClipV clip1[2], clip2[2];
+    int np = clipSegmentToLine(clip1, incident, -tangent, sideOffset1, iv1);
+    if (np < 2) return;
+    np = clipSegmentToLine(clip2, clip1, tangent, sideOffset2, iv2);
+    if (np < 2) return;
+
+    m.localNormal = localNormal;
+    m.localPoint = planePoint;
+    int pointCount = 0;
+    for (int i = 0; i < 2; ++i) {
+        float separation = dot(normal, clip2[i].v) - frontOffset;
+        if (separation <= totalRadius) {
+            m.pt[pointCount] = mulT(xf2, clip2[i].v);
+            uint32_t id = clip2[i].id;
+            if (flip) id = ((id & 0xffu) << 8) | ((id >> 8) & 0xffu) | (((id >> 16) & 0xffu) << 24) | (((id >> 24) & 0xffu) << 16);
+            m.id[pointCount] = id;
+            ++pointCount;
+        }
+    }
+    m.pointCount = pointCount;
+}
+
+// ---- contact slots ---------------------------------------------------------------------------------------
+#define CF_TOUCHING 1
+#define CF_ENABLED 2
+#define CF_FILTER 4
+#define CF_TOI 16
+
+DEV int contactCount(const Ctx& c) { return ldI(c, sslot(c, SS_NCONTACTS)); }
+DEV void contactFixtures(const Ctx& c, int k, int& fA, int& fB) {
+    int p = ldI(c, cslot(c, k, SC_FIX));
+    fA = p & 0xff;
+    fB = (p >> 8) & 0xff;
+}
+
+// b2Contact::Update for slot k.  Returns bit0 = now touching, bit1 = was touching.
+DEVN int updateContact(const Ctx& c, int k) {
+    int fA, fB;
+    contactFixtures(c, k, fA, fB);
+    int bA = mI(c, mfix(c, fA, MF_BODY));
+    int bB = mI(c, mfix(c, fB, MF_BODY));
+    int flags = ldI(c, cslot(c, k, SC_FLAGS));
+    flags |= CF_ENABLED;
+    bool wasTouching = (flags & CF_TOUCHING) != 0;
+    int oldMan = ldI(c, cslot(c, k, SC_MANIFOLD));
+    int oldCount = (oldMan >> 8) & 0xff;
+    uint32_t oldId0 = (uint32_t)ldI(c, cslot(c, k, SC_ID0));
+    uint32_t oldId1 = (uint32_t)ldI(c, cslot(c, k, SC_ID1));
+    float oldN0 = ldF(c, cslot(c, k, SC_N0)), oldT0 = ldF(c, cslot(c, k, SC_T0));
+    float oldN1 = ldF(c, cslot(c, k, SC_N1)), oldT1 = ldF(c, cslot(c, k, SC_T1));
+
+    XF xfA = ldXF(c, bA);
+    XF xfB = ldXF(c, bB);
+    Manifold m;
+    m.type = oldMan & 0xff;
+    collidePolygons(c, m, fA, xfA, fB, xfB);
+    bool touching = m.pointCount > 0;
+    if (touching) {
+        // b2CollidePolygons returns early (pointCount = 0) without touching the rest of the manifold, so the
+        // other fields are only rewritten when points were produced
+        stV2(c, cslot(c, k, SC_LNX), m.localNormal);
+        stV2(c, cslot(c, k, SC_LPX), m.localPoint);
+        for (int i = 0; i < m.pointCount; ++i) {
+            float ni = 0.0f, ti = 0.0f;
+            uint32_t id2 = m.id[i];
+            if (oldCount > 0 && oldId0 == id2) { ni = oldN0; ti = oldT0; }
+            else if (oldCount > 1 && oldId1 == id2) { ni = oldN1; ti = oldT1; }
+            int base = i == 0 ? SC_P0X : SC_P1X;
+            stV2(c, cslot(c, k, base), m.pt[i]);
+            stF(c, cslot(c, k, base + 2), ni);
+            stF(c, cslot(c, k, base + 3), ti);
+            stI(c, cslot(c, k, i == 0 ? SC_ID0 : SC_ID1), (int)id2);
+        }
+    }
+    stI(c, cslot(c, k, SC_MANIFOLD), (m.type & 0xff) | (m.pointCount << 8));
+    if (touching != wasTouching) {
+        wakeBody(c, bA);
+        wakeBody(c, bB);
+    }
+    if (touching) flags |= CF_TOUCHING; else flags &= ~CF_TOUCHING;
+    stI(c, cslot(c, k, SC_FLAGS), flags);
+    return (touching ? 1 : 0) | (wasTouching ? 2 : 0);
+}
+
+// b2ContactManager::Destroy + b2Contact::Destroy for slot k; later slots move down (creation order kept)
+DEVN void destroyContact(const Ctx& c, int k) {
+    int fA, fB;
+    contactFixtures(c, k, fA, fB);
+    int pc = (ldI(c, cslot(c, k, SC_MANIFOLD)) >> 8) & 0xff;
+    if (pc > 0) {
+        wakeBody(c, mI(c, mfix(c, fA, MF_BODY)));
+        wakeBody(c, mI(c, mfix(c, fB, MF_BODY)));
+    }
+    int n = contactCount(c);
+    for (int i = k; i + 1 < n; ++i)
+        for (int f = 0; f < SC_STRIDE; ++f) stF(c, cslot(c, i, f), ldF(c, cslot(c, i + 1, f)));
+    stI(c, sslot(c, SS_NCONTACTS), n - 1);
+}
+
+// b2ContactManager::AddPair (fixture a < fixture b by proxy id; filters are folded into the pair mask)
+DEV void addPair(const Ctx& c, int a, int b) {
+    int n = contactCount(c);
+    int key = a | (b << 8);
+    for (int k = 0; k < n; ++k)
+        if (ldI(c, cslot(c, k, SC_FIX)) == key) return;
+    if (n >= c.h->maxc) {
+        stI(c, sslot(c, SS_STATUS), ldI(c, sslot(c, SS_STATUS)) | 1);
+        return;
+    }
+    stI(c, cslot(c, n, SC_FIX), key);
+    stI(c, cslot(c, n, SC_FLAGS), CF_ENABLED);
+    stI(c, cslot(c, n, SC_MANIFOLD), 0);
+    stI(c, cslot(c, n, SC_ID0), 0);
+    stI(c, cslot(c, n, SC_ID1), 0);
+    for (int f = SC_LNX; f < SC_TOI; ++f) stF(c, cslot(c, n, f), 0.0f);
+    stF(c, cslot(c, n, SC_TOI), 1.0f);
+    stI(c, sslot(c, SS_NCONTACTS), n + 1);
+    wakeBody(c, mI(c, mfix(c, a, MF_BODY)));
+    wakeBody(c, mI(c, mfix(c, b, MF_BODY)));
+}
+
+// b2ContactManager::FindNewContacts -> b2BroadPhase::UpdatePairs.  Upstream queries the tree for every
+// buffered proxy, sorts the (min,max) pairs and drops duplicates; iterating a < b in order over pairs with
+// at least one moved member and overlapping fat boxes visits exactly that sorted, de-duplicated sequence.
+DEVN void findNewContacts(const Ctx& c) {
+    uint64_t moved = ldMoved(c);
+    if (moved == 0ull) return;
+    int nf = c.h->nf;
+    for (int a = 0; a < nf; ++a) {
+        uint64_t cand = (uint64_t)(uint32_t)mI(c, mfix(c, a, MF_PAIR_LO)) | ((uint64_t)(uint32_t)mI(c, mfix(c, a, MF_PAIR_HI)) << 32);
+        cand &= ~((2ull << a) - 1ull);
+        if (((moved >> a) & 1ull) == 0ull) cand &= moved;
+        if (cand == 0ull) continue;
+        Box fa = ldFat(c, a);
+        while (cand) {
+            int b = __ffsll((long long)cand) - 1;
+            cand &= cand - 1ull;
+            Box fb = ldFat(c, b);
+            if (boxOverlap(fb, fa)) addPair(c, a, b);
+        }
+    }
+    stMoved(c, 0ull);
+}
+
+// b2ContactManager::Collide: contacts in upstream list order (newest first)
+DEVN void collide(const Ctx& c) {
+    for (int k = contactCount(c) - 1; k >= 0; --k) {
+        int fA, fB;
+        contactFixtures(c, k, fA, fB);
+        int bA = mI(c, mfix(c, fA, MF_BODY));
+        int bB = mI(c, mfix(c, fB, MF_BODY));
+        bool activeA = isAwake(c, bA) && bodyType(c, bA) != 0;
+        bool activeB = isAwake(c, bB) && bodyType(c, bB) != 0;
+        if (!activeA && !activeB) continue;
+        Box a = ldFat(c, fA);
+        Box b = ldFat(c, fB);
+        if (!boxOverlap(a, b)) { destroyContact(c, k); continue; }
+        updateContact(c, k);
+    }
+}
+
+}  // namespace b2g

@@ -1,0 +1,335 @@
+// CUDA kernels of the batched Box2D backend (sm_100a).  One thread owns one world; the model blob is staged
+// in shared memory once per CTA; all per-world state lives in HBM as S[slot][world].
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false -lineinfo (see build.py).  --fmad=false and
+// IEEE div/sqrt keep the arithmetic identical to the scalar SSE code the reference is compiled to
+// (/root/reference/CMakeLists.txt:54-59: -O3, no -march, no fast-math).
+#include <cuda_runtime.h>
+
+#include "b2g_launch.h"
+#include "b2g_world.cuh"
+
+namespace b2g {
+
+// Stage header + blob into shared memory and build the per-thread context.
+#define B2G_PROLOGUE()                                                                          \
+    extern __shared__ uint32_t smem[];                                                          \
+    {                                                                                           \
+        const uint32_t* hsrc = reinterpret_cast<const uint32_t*>(&hdr);                         \
+        const int hw = (int)(sizeof(ModelHeader) / 4);                                          \
+        for (int i = threadIdx.x; i < hw; i += blockDim.x) smem[i] = hsrc[i];                   \
+        for (int i = threadIdx.x; i < hdr.words; i += blockDim.x) smem[hw + i] = blob[i];       \
+    }                                                                                           \
+    __syncthreads();                                                                            \
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;                       \
+    if (w >= N) return;                                                                         \
+    Ctx c;                                                                                      \
+    c.S = S + w;                                                                                \
+    c.N = (size_t)N;                                                                            \
+    c.h = reinterpret_cast<const ModelHeader*>(smem);                                           \
+    c.M = smem + sizeof(ModelHeader) / 4;                                                       \
+    c.dt = prm.dt;                                                                              \
+    c.inv_dt = prm.dt > 0.0f ? 1.0f / prm.dt : 0.0f;                                            \
+    c.velIters = prm.velIters;                                                                  \
+    c.posIters = prm.posIters;
+
+__global__ void k_init(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
+                       long long N, StepParams prm) {
+    B2G_PROLOGUE();
+    initWorld(c);
+}
+
+// broadcast the state of a template world (stored [slot]) to every world: S[slot][w] = tmpl[slot]
+__global__ void k_broadcast(float* S, const float* __restrict__ tmpl, long long N, int words) {
+    long long total = (long long)words * N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        S[i] = tmpl[i / N];
+    }
+}
+
+__global__ void k_extract_world(const float* S, float* tmpl, long long N, int words, long long world) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) tmpl[i] = S[(size_t)i * N + world];
+}
+
+__global__ void k_set_state(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
+                            long long N, StepParams prm, const float* __restrict__ q, const float* __restrict__ qd) {
+    B2G_PROLOGUE();
+    const int nq = c.h->nq;
+    for (int o = 0; o < c.h->no; ++o) {
+        int n = mI(c, mobj(c, o, MO_NDOFS));
+        int off = mI(c, mobj(c, o, MO_DOF_OFFSET));
+        float lq[kMaxDofsPerObject], lqd[kMaxDofsPerObject];
+        for (int i = 0; i < n; ++i) {
+            lq[i] = q[w * nq + off + i];
+            lqd[i] = qd[w * nq + off + i];
+        }
+        objectSetState(c, o, lq, lqd);
+    }
+}
+
+__global__ void k_get_state(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
+                            long long N, StepParams prm, float* __restrict__ q, float* __restrict__ qd) {
+    B2G_PROLOGUE();
+    const int nq = c.h->nq;
+    for (int o = 0; o < c.h->no; ++o) {
+        int n = mI(c, mobj(c, o, MO_NDOFS));
+        int off = mI(c, mobj(c, o, MO_DOF_OFFSET));
+        float lq[kMaxDofsPerObject], lqd[kMaxDofsPerObject];
+        getDofPositions(c, o, lq);
+        getDofVelocities(c, o, lqd);
+        for (int i = 0; i < n; ++i) {
+            q[w * nq + off + i] = lq[i];
+            qd[w * nq + off + i] = lqd[i];
+        }
+    }
+}
+
+__global__ void k_set_pose(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
+                           long long N, StepParams prm, int object, const float* __restrict__ pose) {
+    B2G_PROLOGUE();
+    objectSetPose(c, object, pose[w * 3], pose[w * 3 + 1], pose[w * 3 + 2]);
+}
+
+__global__ void k_get_pose(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
+                           long long N, StepParams prm, int object, float* __restrict__ pose) {
+    B2G_PROLOGUE();
+    float p[3];
+    basePose(c, object, p);
+    pose[w * 3] = p[0];
+    pose[w * 3 + 1] = p[1];
+    pose[w * 3 + 2] = p[2];
+}
+
+// Box2DRobotVelocityController::setTargetVelocity (Box2DController.cpp:42-63).  scaleToLimits belongs to the
+// missing sim_env package; assumed: one uniform factor that brings every component inside its velocity limits.
+DEV void setTarget(const Ctx& c, int object, const float* v) {
+    int n = mI(c, mobj(c, object, MO_NDOFS));
+    int off = mI(c, mobj(c, object, MO_DOF_OFFSET));
+    int tOff = c.h->sTarget + mI(c, mobj(c, object, MO_TARGET_OFFSET));
+    float factor = 1.0f;
+    for (int i = 0; i < n; ++i) {
+        float lo = dofLimit(c, off + i, 2), hi = dofLimit(c, off + i, 3);
+        if (v[i] > hi && v[i] > 0.0f) factor = fminf(factor, hi / v[i]);
+        if (v[i] < lo && v[i] < 0.0f) factor = fminf(factor, lo / v[i]);
+    }
+    for (int i = 0; i < n; ++i) stF(c, tOff + i, factor < 1.0f ? factor * v[i] : v[i]);
+    int slot = 0;
+    for (int r = 0; r < c.h->nrobots; ++r)
+        if (mI(c, c.h->oRobotOrder + r) == object) slot = r;
+    stI(c, sslot(c, SS_TARGET_AVAIL), ldI(c, sslot(c, SS_TARGET_AVAIL)) | (1 << slot));
+}
+
+__global__ void k_set_target(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
+                             long long N, StepParams prm, int object, const float* __restrict__ v) {
+    B2G_PROLOGUE();
+    int n = mI(c, mobj(c, object, MO_NDOFS));
+    float lv[kMaxDofsPerObject];
+    for (int i = 0; i < n; ++i) lv[i] = v[w * n + i];
+    setTarget(c, object, lv);
+}
+
+// stepPhysics / rollout: nTargets segments of stepsPerTarget steps; targets == nullptr keeps the stored target
+__global__ void k_step(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
+                       StepParams prm, int object, const float* __restrict__ targets, int nTargets, int stepsPerTarget,
+                       int executeControllers, int allowSleeping) {
+    B2G_PROLOGUE();
+    for (int t = 0; t < nTargets; ++t) {
+        if (targets != nullptr) {
+            int n = mI(c, mobj(c, object, MO_NDOFS));
+            float lv[kMaxDofsPerObject];
+            for (int i = 0; i < n; ++i) lv[i] = targets[((size_t)t * N + w) * n + i];
+            setTarget(c, object, lv);
+        }
+        for (int s = 0; s < stepsPerTarget; ++s) stepWorld(c, executeControllers != 0, allowSleeping != 0);
+    }
+}
+
+__global__ void k_get_bodies(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
+                             long long N, StepParams prm, float* __restrict__ out) {
+    B2G_PROLOGUE();
+    const int nb = c.h->nb;
+    for (int b = 0; b < nb; ++b) {
+        float* o = out + ((size_t)w * nb + b) * 16;
+        o[0] = ldF(c, bslot(c, b, SB_PX)); o[1] = ldF(c, bslot(c, b, SB_PY));
+        o[2] = ldF(c, bslot(c, b, SB_QS)); o[3] = ldF(c, bslot(c, b, SB_QC));
+        o[4] = ldF(c, bslot(c, b, SB_CX)); o[5] = ldF(c, bslot(c, b, SB_CY)); o[6] = ldF(c, bslot(c, b, SB_A));
+        o[7] = ldF(c, bslot(c, b, SB_C0X)); o[8] = ldF(c, bslot(c, b, SB_C0Y)); o[9] = ldF(c, bslot(c, b, SB_A0));
+        o[10] = ldF(c, bslot(c, b, SB_VX)); o[11] = ldF(c, bslot(c, b, SB_VY)); o[12] = ldF(c, bslot(c, b, SB_W));
+        o[13] = ldF(c, bslot(c, b, SB_SLEEP));
+        o[14] = (ldI(c, bslot(c, b, SB_FLAGS)) & 1) ? 1.0f : 0.0f;
+        o[15] = (float)bodyType(c, b);
+    }
+}
+
+__global__ void k_get_fat(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
+                          long long N, StepParams prm, float* __restrict__ out) {
+    B2G_PROLOGUE();
+    const int nf = c.h->nf;
+    for (int f = 0; f < nf; ++f)
+        for (int k = 0; k < 4; ++k) out[((size_t)w * nf + f) * 4 + k] = ldF(c, c.h->sFix + f * 4 + k);
+}
+
+__global__ void k_get_joints(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
+                             long long N, StepParams prm, int* __restrict__ iout, float* __restrict__ fout) {
+    B2G_PROLOGUE();
+    const int nj = c.h->nj;
+    for (int j = 0; j < nj; ++j) {
+        int* io = iout + ((size_t)w * nj + j) * 6;
+        float* fo = fout + ((size_t)w * nj + j) * 15;
+        int type = mI(c, mjoint(c, j, MJ_TYPE));
+        int flags = ldI(c, jslot(c, j, SJ_FLAGS));
+        io[0] = type; io[1] = mI(c, mjoint(c, j, MJ_BODYA)); io[2] = mI(c, mjoint(c, j, MJ_BODYB));
+        io[3] = flags & 3; io[4] = (flags >> 2) & 1; io[5] = mI(c, mjoint(c, j, MJ_FLAGS)) & 1;
+        fo[0] = ldF(c, jslot(c, j, SJ_IX)); fo[1] = ldF(c, jslot(c, j, SJ_IY)); fo[2] = ldF(c, jslot(c, j, SJ_IZ));
+        fo[3] = type == 0 ? 0.0f : ldF(c, jslot(c, j, SJ_MOTOR_IMPULSE));
+        fo[4] = ldF(c, jslot(c, j, SJ_MAX_MOTOR_TORQUE)); fo[5] = ldF(c, jslot(c, j, SJ_MOTOR_SPEED));
+        fo[6] = mF(c, mjoint(c, j, MJ_MAXFORCE)); fo[7] = mF(c, mjoint(c, j, MJ_MAXTORQUE));
+        fo[8] = mF(c, mjoint(c, j, MJ_LAX)); fo[9] = mF(c, mjoint(c, j, MJ_LAY));
+        fo[10] = mF(c, mjoint(c, j, MJ_LBX)); fo[11] = mF(c, mjoint(c, j, MJ_LBY));
+        fo[12] = mF(c, mjoint(c, j, MJ_REF)); fo[13] = mF(c, mjoint(c, j, MJ_LOWER)); fo[14] = mF(c, mjoint(c, j, MJ_UPPER));
+    }
+}
+
+__global__ void k_get_contacts(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
+                               long long N, StepParams prm, int* __restrict__ counts, int* __restrict__ iout,
+                               float* __restrict__ fout, int maxPer) {
+    B2G_PROLOGUE();
+    int n = contactCount(c);
+    counts[w] = n;
+    for (int k = 0; k < n && k < maxPer; ++k) {
+        int* io = iout + ((size_t)w * maxPer + k) * 8;
+        float* fo = fout + ((size_t)w * maxPer + k) * 12;
+        int fA, fB;
+        contactFixtures(c, k, fA, fB);
+        int flags = ldI(c, cslot(c, k, SC_FLAGS));
+        int man = ldI(c, cslot(c, k, SC_MANIFOLD));
+        io[0] = fA; io[1] = fB; io[2] = flags & CF_TOUCHING ? 1 : 0; io[3] = flags & CF_ENABLED ? 1 : 0;
+        io[4] = (man >> 8) & 0xff; io[5] = man & 0xff;
+        io[6] = ldI(c, cslot(c, k, SC_ID0)); io[7] = ldI(c, cslot(c, k, SC_ID1));
+        for (int f = 0; f < 12; ++f) fo[f] = ldF(c, cslot(c, k, SC_LNX + f));
+    }
+}
+
+// Box2DCollisionChecker::updateContactCache (:2880-2911): UpdateContacts() = FindNewContacts + Collide (assumed
+// meaning of the fork-only call at :2898), then the touching+enabled contacts in contact-list order
+__global__ void k_check_collision(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
+                                  long long N, StepParams prm, int* __restrict__ counts, int* __restrict__ iout,
+                                  float* __restrict__ fout, int maxPer) {
+    B2G_PROLOGUE();
+    findNewContacts(c);
+    collide(c);
+    int n = 0;
+    float inv = c.h->invScale;
+    for (int k = contactCount(c) - 1; k >= 0; --k) {
+        int flags = ldI(c, cslot(c, k, SC_FLAGS));
+        if ((flags & CF_TOUCHING) == 0 || (flags & CF_ENABLED) == 0) continue;
+        if (n < maxPer) {
+            int bA, bB, fA, fB;
+            contactBodies(c, k, bA, bB, fA, fB);
+            // b2Contact::GetWorldManifold with the bodies' current transforms; only points[0] is reported (:2857-2862)
+            XF xfA = ldXF(c, bA), xfB = ldXF(c, bB);
+            int type = ldI(c, cslot(c, k, SC_MANIFOLD)) & 0xff;
+            V2 localNormal = ldV2(c, cslot(c, k, SC_LNX));
+            V2 localPoint = ldV2(c, cslot(c, k, SC_LPX));
+            V2 lp = ldV2(c, cslot(c, k, SC_P0X));
+            V2 normal, point;
+            const float radius = B2G_POLYGON_RADIUS;
+            if (type == 1) {
+                normal = mul(xfA.q, localNormal);
+                V2 planePoint = mul(xfA, localPoint);
+                V2 clipPoint = mul(xfB, lp);
+                V2 cA = clipPoint + (radius - dot(clipPoint - planePoint, normal)) * normal;
+                V2 cB = clipPoint - radius * normal;
+                point = 0.5f * (cA + cB);
+            } else {
+                normal = mul(xfB.q, localNormal);
+                V2 planePoint = mul(xfB, localPoint);
+                V2 clipPoint = mul(xfA, lp);
+                V2 cB = clipPoint + (radius - dot(clipPoint - planePoint, normal)) * normal;
+                V2 cA = clipPoint - radius * normal;
+                point = 0.5f * (cA + cB);
+                normal = -normal;
+            }
+            int* io = iout + ((size_t)w * maxPer + n) * 4;
+            float* fo = fout + ((size_t)w * maxPer + n) * 6;
+            io[0] = bA; io[1] = bB; io[2] = fA; io[3] = fB;
+            fo[0] = inv * point.x; fo[1] = inv * point.y; fo[2] = 0.0f;
+            fo[3] = inv * normal.x; fo[4] = inv * normal.y; fo[5] = 0.0f;
+        }
+        ++n;
+    }
+    counts[w] = n;
+}
+
+__global__ void k_status(const float* S, long long N, int statusSlot, int* __restrict__ out) {
+    long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < N) out[w] = __float_as_int(S[(size_t)statusSlot * N + w]);
+}
+
+// gather / scatter of the world state vector and static poses for the save/restore stack
+// ---------------------------------------------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------------------------------------------
+static unsigned long long g_launches = 0;
+unsigned long long launchCount() { return g_launches; }
+
+static inline size_t smemBytes(const ModelHeader& h) { return sizeof(ModelHeader) + (size_t)h.words * 4; }
+
+static cudaError_t prepare(const void* fn, const ModelHeader& h) {
+    size_t bytes = smemBytes(h);
+    if (bytes > 48 * 1024) return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return cudaSuccess;
+}
+
+#define LAUNCH(kernel, ...)                                                                         \
+    do {                                                                                            \
+        cudaError_t e = prepare((const void*)kernel, L.h);                                          \
+        if (e != cudaSuccess) return e;                                                             \
+        int threads = L.block;                                                                      \
+        unsigned blocks = (unsigned)((L.N + threads - 1) / threads);                                \
+        kernel<<<blocks, threads, smemBytes(L.h), L.stream>>>(L.h, L.blob, L.S, L.N, L.prm, ##__VA_ARGS__); \
+        ++g_launches;                                                                               \
+        return cudaGetLastError();                                                                  \
+    } while (0)
+
+cudaError_t launchInit(const Launch& L) { LAUNCH(k_init); }
+cudaError_t launchSetState(const Launch& L, const float* q, const float* qd) { LAUNCH(k_set_state, q, qd); }
+cudaError_t launchGetState(const Launch& L, float* q, float* qd) { LAUNCH(k_get_state, q, qd); }
+cudaError_t launchSetPose(const Launch& L, int object, const float* pose) { LAUNCH(k_set_pose, object, pose); }
+cudaError_t launchGetPose(const Launch& L, int object, float* pose) { LAUNCH(k_get_pose, object, pose); }
+cudaError_t launchSetTarget(const Launch& L, int object, const float* v) { LAUNCH(k_set_target, object, v); }
+cudaError_t launchStep(const Launch& L, int object, const float* targets, int nTargets, int stepsPerTarget, int execCtrl,
+                       int allowSleep) {
+    LAUNCH(k_step, object, targets, nTargets, stepsPerTarget, execCtrl, allowSleep);
+}
+cudaError_t launchGetBodies(const Launch& L, float* out) { LAUNCH(k_get_bodies, out); }
+cudaError_t launchGetFat(const Launch& L, float* out) { LAUNCH(k_get_fat, out); }
+cudaError_t launchGetJoints(const Launch& L, int* iout, float* fout) { LAUNCH(k_get_joints, iout, fout); }
+cudaError_t launchGetContacts(const Launch& L, int* counts, int* iout, float* fout, int maxPer) {
+    LAUNCH(k_get_contacts, counts, iout, fout, maxPer);
+}
+cudaError_t launchCheckCollision(const Launch& L, int* counts, int* iout, float* fout, int maxPer) {
+    LAUNCH(k_check_collision, counts, iout, fout, maxPer);
+}
+cudaError_t launchBroadcast(const Launch& L, const float* tmpl) {
+    long long total = (long long)L.h.stateWords * L.N;
+    int threads = 256;
+    long long want = (total + threads - 1) / threads;
+    unsigned blocks = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+    k_broadcast<<<blocks, threads, 0, L.stream>>>(L.S, tmpl, L.N, L.h.stateWords);
+    ++g_launches;
+    return cudaGetLastError();
+}
+cudaError_t launchExtractWorld(const Launch& L, float* tmpl, long long world) {
+    k_extract_world<<<(L.h.stateWords + 255) / 256, 256, 0, L.stream>>>(L.S, tmpl, L.N, L.h.stateWords, world);
+    ++g_launches;
+    return cudaGetLastError();
+}
+cudaError_t launchStatus(const Launch& L, int* out) {
+    int threads = 256;
+    k_status<<<(unsigned)((L.N + threads - 1) / threads), threads, 0, L.stream>>>(L.S, L.N, L.h.sScalar + SS_STATUS, out);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+}  // namespace b2g

@@ -1,0 +1,42 @@
+// Host-visible launch interface between the C ABI (b2g_capi.cu) and the kernels (b2g_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "model.h"
+
+namespace b2g {
+
+struct StepParams {
+    float dt;
+    int velIters, posIters;
+};
+
+struct Launch {
+    ModelHeader h;
+    const uint32_t* blob;  // device copy of the model blob
+    float* S;              // device state, [stateWords][N]
+    long long N;
+    StepParams prm;
+    cudaStream_t stream;
+    int block;             // threads per CTA
+};
+
+unsigned long long launchCount();
+cudaError_t launchInit(const Launch& L);
+cudaError_t launchBroadcast(const Launch& L, const float* tmpl);
+cudaError_t launchExtractWorld(const Launch& L, float* tmpl, long long world);
+cudaError_t launchSetState(const Launch& L, const float* q, const float* qd);
+cudaError_t launchGetState(const Launch& L, float* q, float* qd);
+cudaError_t launchSetPose(const Launch& L, int object, const float* pose);
+cudaError_t launchGetPose(const Launch& L, int object, float* pose);
+cudaError_t launchSetTarget(const Launch& L, int object, const float* v);
+cudaError_t launchStep(const Launch& L, int object, const float* targets, int nTargets, int stepsPerTarget, int execCtrl,
+                       int allowSleep);
+cudaError_t launchGetBodies(const Launch& L, float* out);
+cudaError_t launchGetFat(const Launch& L, float* out);
+cudaError_t launchGetJoints(const Launch& L, int* iout, float* fout);
+cudaError_t launchGetContacts(const Launch& L, int* counts, int* iout, float* fout, int maxPer);
+cudaError_t launchCheckCollision(const Launch& L, int* counts, int* iout, float* fout, int maxPer);
+cudaError_t launchStatus(const Launch& L, int* out);
+
+}  // namespace b2g

@@ -1,0 +1,380 @@
+// Per-world wrapper semantics on the device: DOF <-> body kinematics, the robot velocity controller,
+// effort application and the stepPhysics driver.  Each routine cites the reference lines it replaces
+// (/root/reference/src/sim_env/Box2DWorld.cpp, Box2DController.cpp).
+#pragma once
+#include "b2g_solver.cuh"
+#include "b2g_toi.cuh"
+
+namespace b2g {
+
+DEV int olink(const Ctx& c, int o, int pos, int f) { return c.h->oLink + (mI(c, mobj(c, o, MO_LINK_START)) + pos) * ML_STRIDE + f; }
+DEV float dofLimit(const Ctx& c, int dof, int k) { return mF(c, c.h->oDof + dof * 6 + k); }
+DEV float clampStd(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }  // sim_env::utils::math::clamp
+
+// Box2DLink::getPose (:215-224) for the base link of object o
+DEV void basePose(const Ctx& c, int o, float pose[3]) {
+    int b = mI(c, mobj(c, o, MO_BASE_BODY));
+    XF xf = ldXF(c, b);
+    V2 pos = mul(xf, mk(mF(c, mobj(c, o, MO_ORIGIN_X)), mF(c, mobj(c, o, MO_ORIGIN_Y))));
+    float inv = c.h->invScale;
+    pose[0] = inv * pos.x;
+    pose[1] = inv * pos.y;
+    pose[2] = ldF(c, bslot(c, b, SB_A));
+}
+
+// b2RevoluteJoint::GetJointAngle / GetJointSpeed (:972, :1037)
+DEV float jointAngle(const Ctx& c, int j) {
+    int bA = mI(c, mjoint(c, j, MJ_BODYA)), bB = mI(c, mjoint(c, j, MJ_BODYB));
+    return ldF(c, bslot(c, bB, SB_A)) - ldF(c, bslot(c, bA, SB_A)) - mF(c, mjoint(c, j, MJ_REF));
+}
+DEV float jointSpeed(const Ctx& c, int j) {
+    int bA = mI(c, mjoint(c, j, MJ_BODYA)), bB = mI(c, mjoint(c, j, MJ_BODYB));
+    return ldF(c, bslot(c, bB, SB_W)) - ldF(c, bslot(c, bA, SB_W));
+}
+DEV int objJoint(const Ctx& c, int o, int i) { return mI(c, c.h->oObjJoint + mI(c, mobj(c, o, MO_JOINT_START)) + i) & 0xffff; }
+DEV int objJointChildPos(const Ctx& c, int o, int i) { return mI(c, c.h->oObjJoint + mI(c, mobj(c, o, MO_JOINT_START)) + i) >> 16; }
+DEV V2 jointAnchorA(const Ctx& c, int j) {  // b2RevoluteJoint::GetAnchorA
+    int bA = mI(c, mjoint(c, j, MJ_BODYA));
+    return mul(ldXF(c, bA), mk(mF(c, mjoint(c, j, MJ_LAX)), mF(c, mjoint(c, j, MJ_LAY))));
+}
+
+// Box2DObject::getDOFPositions / getDOFVelocities over all DOFs (:1507-1528, :1628-1649)
+DEV void getDofPositions(const Ctx& c, int o, float* q) {
+    int isStatic = mI(c, mobj(c, o, MO_STATIC));
+    int n = 0;
+    if (!isStatic) {
+        float pose[3];
+        basePose(c, o, pose);
+        q[0] = pose[0]; q[1] = pose[1]; q[2] = pose[2];
+        n = 3;
+    }
+    int nj = mI(c, mobj(c, o, MO_JOINT_COUNT));
+    for (int i = 0; i < nj; ++i) q[n + i] = jointAngle(c, objJoint(c, o, i));
+}
+DEV void getDofVelocities(const Ctx& c, int o, float* qd) {
+    int isStatic = mI(c, mobj(c, o, MO_STATIC));
+    int n = 0;
+    if (!isStatic) {
+        int b = mI(c, mobj(c, o, MO_BASE_BODY));
+        float inv = c.h->invScale;
+        qd[0] = inv * ldF(c, bslot(c, b, SB_VX));
+        qd[1] = inv * ldF(c, bslot(c, b, SB_VY));
+        qd[2] = ldF(c, bslot(c, b, SB_W));
+        n = 3;
+    }
+    int nj = mI(c, mobj(c, o, MO_JOINT_COUNT));
+    for (int i = 0; i < nj; ++i) qd[n + i] = jointSpeed(c, objJoint(c, o, i));
+}
+
+// Box2DLink::setPose(pose, update_children = true, joint_override) (:405-438) together with the
+// Box2DJoint::resetPosition recursion (:992-1028), flattened: every joint value of the subtree is read
+// before anything moves (that is what the recursion does), then links are placed parent first.
+// `pos` is the position of the subtree root in the object's pre-order link list.
+DEVN void placeSubtree(const Ctx& c, int o, int pos, const float pose[3], bool jointOverride) {
+    int count = mI(c, olink(c, o, pos, ML_SUBTREE));
+    float jv[kMaxLinksPerObject];
+    for (int i = 1; i < count; ++i) {
+        int j = mI(c, olink(c, o, pos + i, ML_PARENT_JOINT));
+        jv[i] = jointOverride ? 0.0f : jointAngle(c, j);
+    }
+    float s = c.h->scale, inv = c.h->invScale;
+    for (int i = 0; i < count; ++i) {
+        int b = mI(c, olink(c, o, pos + i, ML_BODY));
+        float px, py, th;
+        if (i == 0) {
+            px = pose[0]; py = pose[1]; th = pose[2];
+        } else {
+            int j = mI(c, olink(c, o, pos + i, ML_PARENT_JOINT));
+            int bA = mI(c, mjoint(c, j, MJ_BODYA));
+            int dof = mI(c, mjoint(c, j, MJ_DOF));
+            float clamped = clampStd(jv[i], dofLimit(c, dof, 0), dofLimit(c, dof, 1));
+            th = ldF(c, bslot(c, bA, SB_A)) + clamped + mF(c, mjoint(c, j, MJ_REF));
+            V2 axisWorld = jointAnchorA(c, j);
+            px = inv * axisWorld.x;
+            py = inv * axisWorld.y;
+        }
+        // only the base link of an object carries a non-zero origin offset (:653-671)
+        V2 off = mk(0.0f, 0.0f);
+        if (mI(c, olink(c, o, pos + i, ML_PARENT_POS)) < 0) off = mk(mF(c, mobj(c, o, MO_ORIGIN_X)), mF(c, mobj(c, o, MO_ORIGIN_Y)));
+        V2 baseTranslation = mk(s * px, s * py);
+        Rot r = rotOf(th);
+        V2 offset = mul(r, off);
+        setTransform(c, b, baseTranslation - offset, th);
+    }
+}
+
+// Box2DObject::updateBodyVelocities + Box2DLink::updateBodyVelocities (:2018-2041, :759-794).
+// qd holds all DOF velocities of the object (object-local indexing).
+DEVN void updateBodyVelocities(const Ctx& c, int o, const float* qd) {
+    int isStatic = mI(c, mobj(c, o, MO_STATIC));
+    int nl = mI(c, mobj(c, o, MO_LINK_COUNT));
+    float s = c.h->scale;
+    float pose[3];
+    basePose(c, o, pose);
+    V2 baseAxis = mk(s * pose[0], s * pose[1]);
+    float bvx = isStatic ? 0.0f : qd[0];
+    float bvy = isStatic ? 0.0f : qd[1];
+    float bw = isStatic ? 0.0f : qd[2];
+    int dofOffset = mI(c, mobj(c, o, MO_DOF_OFFSET));
+    for (int p = 0; p < nl; ++p) {
+        int b = mI(c, olink(c, o, p, ML_BODY));
+        V2 lin = mk(s * bvx, s * bvy);
+        float ang = 0.0f;
+        V2 com = ldV2(c, bslot(c, b, SB_CX));
+        {
+            V2 r = com - baseAxis;
+            lin.x -= bw * r.y;
+            lin.y += bw * r.x;
+            ang += bw;
+        }
+        int cs = c.h->oChain + mI(c, olink(c, o, p, ML_CHAIN_START));
+        int cl = mI(c, olink(c, o, p, ML_CHAIN_LEN));
+        for (int e = 0; e < cl; ++e) {
+            int j = mI(c, cs + e);
+            float w = qd[mI(c, mjoint(c, j, MJ_DOF)) - dofOffset];
+            V2 r = com - jointAnchorA(c, j);
+            lin.x -= w * r.y;
+            lin.y += w * r.x;
+            ang += w;
+        }
+        if (bodyType(c, b) != 0) {  // b2Body::SetLinearVelocity / SetAngularVelocity
+            if (dot(lin, lin) > 0.0f) wakeBody(c, b);
+            stV2(c, bslot(c, b, SB_VX), lin);
+            if (ang * ang > 0.0f) wakeBody(c, b);
+            stF(c, bslot(c, b, SB_W), ang);
+        }
+    }
+}
+
+// Box2DObject::setPose(x, y, theta) / setTransform (:1940-1947, :1419-1433)
+DEVN void objectSetPose(const Ctx& c, int o, float x, float y, float theta) {
+    float qd[kMaxDofsPerObject];
+    getDofVelocities(c, o, qd);
+    float pose[3] = {x, y, theta};
+    placeSubtree(c, o, 0, pose, false);
+    updateBodyVelocities(c, o, qd);
+}
+
+// Box2DObject::setDOFPositions over all DOFs (:1585-1626)
+DEVN void objectSetDofPositions(const Ctx& c, int o, const float* q) {
+    float qd[kMaxDofsPerObject];
+    getDofVelocities(c, o, qd);
+    int isStatic = mI(c, mobj(c, o, MO_STATIC));
+    int n = 0;
+    if (!isStatic) {
+        float pose[3] = {q[0], q[1], q[2]};
+        placeSubtree(c, o, 0, pose, false);
+        n = 3;
+    }
+    int nj = mI(c, mobj(c, o, MO_JOINT_COUNT));
+    for (int i = 0; i < nj; ++i) {
+        // Box2DJoint::resetPosition(values[i], false)
+        int j = objJoint(c, o, i);
+        int bA = mI(c, mjoint(c, j, MJ_BODYA));
+        int dof = mI(c, mjoint(c, j, MJ_DOF));
+        float clamped = clampStd(q[n + i], dofLimit(c, dof, 0), dofLimit(c, dof, 1));
+        float pose[3];
+        V2 axisWorld = jointAnchorA(c, j);
+        pose[0] = c.h->invScale * axisWorld.x;
+        pose[1] = c.h->invScale * axisWorld.y;
+        pose[2] = ldF(c, bslot(c, bA, SB_A)) + clamped + mF(c, mjoint(c, j, MJ_REF));
+        placeSubtree(c, o, objJointChildPos(c, o, i), pose, false);
+    }
+    updateBodyVelocities(c, o, qd);
+}
+
+// Box2DObject::setDOFVelocities over all DOFs (:1691-1715)
+DEVN void objectSetDofVelocities(const Ctx& c, int o, const float* v) {
+    float qd[kMaxDofsPerObject];
+    int n = mI(c, mobj(c, o, MO_NDOFS));
+    int dofOffset = mI(c, mobj(c, o, MO_DOF_OFFSET));
+    for (int i = 0; i < n; ++i) qd[i] = clampStd(v[i], dofLimit(c, dofOffset + i, 2), dofLimit(c, dofOffset + i, 3));
+    updateBodyVelocities(c, o, qd);
+}
+
+// Box2DObject::setState (:1980-1989) for object o; q/qd are the object's slices of the world state vector
+DEV void objectSetState(const Ctx& c, int o, const float* q, const float* qd) {
+    if (!mI(c, mobj(c, o, MO_STATIC))) objectSetPose(c, o, q[0], q[1], q[2]);
+    objectSetDofPositions(c, o, q);
+    objectSetDofVelocities(c, o, qd);
+}
+
+// ---- freshly loaded world: what createWorld leaves behind (:3664-3721) ------------------------------------------
+DEVN void initWorld(const Ctx& c) {
+    const ModelHeader& h = *c.h;
+    for (int b = 0; b < h.nb; ++b) {
+        XF xf;
+        xf.p = mk(mF(c, mbody(c, b, MB_PX)), mF(c, mbody(c, b, MB_PY)));
+        xf.q.s = 0.0f;
+        xf.q.c = 1.0f;
+        stXF(c, b, xf);
+        V2 cc = mul(xf, localCenter(c, b));  // b2Body::ResetMassData: c = Mul(xf, localCenter)
+        if (bodyType(c, b) == 0) cc = xf.p;
+        stV2(c, bslot(c, b, SB_CX), cc);
+        stV2(c, bslot(c, b, SB_C0X), cc);
+        stF(c, bslot(c, b, SB_A), 0.0f);
+        stF(c, bslot(c, b, SB_A0), 0.0f);
+        stF(c, bslot(c, b, SB_VX), 0.0f); stF(c, bslot(c, b, SB_VY), 0.0f); stF(c, bslot(c, b, SB_W), 0.0f);
+        stF(c, bslot(c, b, SB_SLEEP), 0.0f);
+        stI(c, bslot(c, b, SB_FLAGS), 1);
+        stF(c, bslot(c, b, SB_ALPHA0), 0.0f);
+        stF(c, bslot(c, b, SB_FX), 0.0f); stF(c, bslot(c, b, SB_FY), 0.0f); stF(c, bslot(c, b, SB_TORQUE), 0.0f);
+    }
+    for (int f = 0; f < h.nf; ++f)
+        for (int k = 0; k < 4; ++k) stF(c, h.sFix + f * 4 + k, mF(c, mfix(c, f, MF_FAT0 + k)));
+    for (int j = 0; j < h.nj; ++j) {
+        for (int k = 0; k < SJ_STRIDE; ++k) stF(c, jslot(c, j, k), 0.0f);
+        int enableMotor = (mI(c, mjoint(c, j, MJ_FLAGS)) >> 1) & 1;
+        stI(c, jslot(c, j, SJ_FLAGS), enableMotor << 2);
+        for (int k = 0; k < WJ_STRIDE; ++k) stF(c, jwslot(c, j, k), 0.0f);
+    }
+    for (int k = 0; k < h.maxc; ++k) {
+        for (int f = 0; f < SC_STRIDE; ++f) stF(c, cslot(c, k, f), 0.0f);
+        for (int f = 0; f < WC_STRIDE; ++f) stF(c, cwslot(c, k, f), 0.0f);
+    }
+    stF(c, sslot(c, SS_INV_DT0), 0.0f);
+    stI(c, sslot(c, SS_FLAGS), 1);  // e_newFixture
+    stI(c, sslot(c, SS_NCONTACTS), 0);
+    stI(c, sslot(c, SS_STATUS), 0);
+    stMoved(c, h.nf >= 64 ? ~0ull : ((1ull << h.nf) - 1ull));  // every proxy is buffered at creation
+    stI(c, sslot(c, SS_TARGET_AVAIL), 0);
+    stI(c, sslot(c, SS_SPARE), 0);
+    for (int t = 0; t < h.ntarget; ++t) stF(c, h.sTarget + t, 0.0f);
+
+    // Box2DObject ctor: _base_link->setPose((0,0,0), true, true) (:1335)
+    for (int o = 0; o < h.no; ++o) {
+        float zero[3] = {0.0f, 0.0f, 0.0f};
+        placeSubtree(c, o, 0, zero, true);
+    }
+    // YAML `states` (:3684-3717)
+    for (int o = 0; o < h.no; ++o) {
+        int is = h.oInit + mI(c, mobj(c, o, MO_INIT_START));
+        if (!mI(c, is)) continue;
+        int n = mI(c, is + 1);
+        float q[kMaxDofsPerObject + 3], qd[kMaxDofsPerObject + 3];
+        for (int i = 0; i < n; ++i) { q[i] = mF(c, is + 2 + i); qd[i] = mF(c, is + 2 + n + i); }
+        if (!mI(c, mobj(c, o, MO_STATIC))) {
+            objectSetDofPositions(c, o, q);
+            objectSetDofVelocities(c, o, qd);
+        } else {
+            objectSetPose(c, o, q[0], q[1], q[2]);
+            objectSetDofPositions(c, o, q + 3);
+            objectSetDofVelocities(c, o, qd + 3);
+        }
+    }
+}
+
+// ---- controller ------------------------------------------------------------------------------------------------
+// Box2DRobot::control (:2284-2310) = Box2DRobotVelocityController::control (Box2DController.cpp:65-117)
+// followed by Box2DRobot::commandEfforts (:2319-2379) and Box2DJoint::setControlTorque (:1198-1222).
+DEVN void robotControl(const Ctx& c, int o, int robotSlot) {
+    if (((ldI(c, sslot(c, SS_TARGET_AVAIL)) >> robotSlot) & 1) == 0) return;  // "No target available."
+    int n = mI(c, mobj(c, o, MO_NDOFS));
+    int isStatic = mI(c, mobj(c, o, MO_STATIC));
+    int baseDofs = isStatic ? 0 : 3;
+    int dofOffset = mI(c, mobj(c, o, MO_DOF_OFFSET));
+    int tOff = c.h->sTarget + mI(c, mobj(c, o, MO_TARGET_OFFSET));
+    float vel[kMaxDofsPerObject], effort[kMaxDofsPerObject];
+    getDofVelocities(c, o, vel);
+    float inv = c.h->invScale, s = c.h->scale;
+    int baseBody = mI(c, mobj(c, o, MO_BASE_BODY));
+    for (int i = 0; i < n; ++i) {
+        float massInertia;
+        if (i < baseDofs) {
+            if (i < 2) {
+                massInertia = mF(c, mobj(c, o, MO_MASS));
+            } else {
+                // Box2DObject::getInertia (:1909-1921): links in name order, parallel axis about the base COM
+                V2 bc = ldV2(c, bslot(c, baseBody, SB_CX));
+                float comx = inv * bc.x, comy = inv * bc.y;
+                float inertia = 0.0f;
+                int ns = c.h->oName + mI(c, mobj(c, o, MO_NAME_START));
+                int nl = mI(c, mobj(c, o, MO_LINK_COUNT));
+                for (int l = 0; l < nl; ++l) {
+                    int b = mI(c, ns + l);
+                    V2 lc = ldV2(c, bslot(c, b, SB_CX));
+                    float dx = inv * lc.x - comx, dy = inv * lc.y - comy;
+                    float distance = sqrtf(dx * dx + dy * dy);
+                    // Box2DLink::getCOMInertia (:557-566)
+                    float m = mF(c, mbody(c, b, MB_MASS));
+                    V2 loc = localCenter(c, b);
+                    float bodyInertia = mF(c, mbody(c, b, MB_I)) + m * dot(loc, loc);  // b2Body::GetInertia
+                    float comDist = length(loc);
+                    float comInertia = bodyInertia - m * comDist * comDist;
+                    float linkComInertia = inv * inv * comInertia;
+                    inertia += linkComInertia + distance * distance * m;
+                }
+                massInertia = inertia;
+            }
+        } else {
+            // computeKinematicChainInertia (Box2DController.cpp:191-215): only the joint's own child link
+            int j = objJoint(c, o, i - baseDofs);
+            int child = mI(c, mjoint(c, j, MJ_BODYB));
+            XF xfc = ldXF(c, child);
+            V2 origin = mul(xfc, mk(0.0f, 0.0f));  // child getPose: GetWorldPoint(local origin offset = 0)
+            float ax = inv * origin.x, ay = inv * origin.y;
+            V2 cc = ldV2(c, bslot(c, child, SB_CX));
+            float dx = inv * cc.x - ax, dy = inv * cc.y - ay;
+            float distance = sqrtf(dx * dx + dy * dy);
+            float m = mF(c, mbody(c, child, MB_MASS));
+            V2 loc = localCenter(c, child);
+            float bodyInertia = mF(c, mbody(c, child, MB_I)) + m * dot(loc, loc);
+            float linkInertia = inv * inv * bodyInertia;  // Box2DLink::getInertia (:549-555)
+            massInertia = 0.0f + (linkInertia + m * distance * distance);
+        }
+        float accel = (ldF(c, tOff + i) - vel[i]) / c.dt;
+        accel = fminf(dofLimit(c, dofOffset + i, 5), fmaxf(accel, dofLimit(c, dofOffset + i, 4)));
+        effort[i] = massInertia * accel;
+    }
+    // commandEfforts
+    for (int i = 0; i < n; ++i) {
+        if (i < baseDofs) {
+            if (i < 2) {  // b2Body::ApplyForceToCenter(force, wake = true)
+                wakeBody(c, baseBody);
+                V2 f = ldV2(c, bslot(c, baseBody, SB_FX));
+                V2 add = i == 0 ? mk(s * effort[i], 0.0f) : mk(0.0f, s * effort[i]);
+                stV2(c, bslot(c, baseBody, SB_FX), f + add);
+            } else {      // b2Body::ApplyTorque
+                wakeBody(c, baseBody);
+                stF(c, bslot(c, baseBody, SB_TORQUE), ldF(c, bslot(c, baseBody, SB_TORQUE)) + s * s * effort[i]);
+            }
+        } else {
+            int j = objJoint(c, o, i - baseDofs);
+            wakeBody(c, mI(c, mjoint(c, j, MJ_BODYA)));
+            wakeBody(c, mI(c, mjoint(c, j, MJ_BODYB)));
+            stI(c, jslot(c, j, SJ_FLAGS), ldI(c, jslot(c, j, SJ_FLAGS)) | 4);  // EnableMotor(true)
+            stF(c, jslot(c, j, SJ_MAX_MOTOR_TORQUE), s * s * fabsf(effort[i]));
+            float sgn = effort[i] > 0.0f ? 1.0f : -1.0f;
+            stF(c, jslot(c, j, SJ_MOTOR_SPEED), sgn * FLT_MAX);
+        }
+    }
+}
+
+// Box2DWorld::stepPhysics body for one step (:3270-3282) = controllers + b2World::Step + ClearForces
+DEVN void stepWorld(const Ctx& c, bool executeControllers, bool allowSleeping) {
+    const ModelHeader& h = *c.h;
+    if (executeControllers) {
+        for (int r = 0; r < h.nrobots; ++r) robotControl(c, mI(c, h.oRobotOrder + r), r);
+    }
+    if (!allowSleeping) {  // b2World::SetAllowSleeping(false) wakes every body
+        for (int b = h.nb - 1; b >= 0; --b) wakeBody(c, b);
+    }
+    // b2World::Step
+    int flags = ldI(c, sslot(c, SS_FLAGS));
+    if (flags & 1) {
+        findNewContacts(c);
+        stI(c, sslot(c, SS_FLAGS), flags & ~1);
+    }
+    float dtRatio = ldF(c, sslot(c, SS_INV_DT0)) * c.dt;
+    collide(c);
+    solveIslands(c, dtRatio, allowSleeping);
+    solveTOI(c);
+    stF(c, sslot(c, SS_INV_DT0), c.inv_dt);
+    for (int b = 0; b < h.nb; ++b) {  // ClearForces
+        stF(c, bslot(c, b, SB_FX), 0.0f);
+        stF(c, bslot(c, b, SB_FY), 0.0f);
+        stF(c, bslot(c, b, SB_TORQUE), 0.0f);
+    }
+}
+
+}  // namespace b2g

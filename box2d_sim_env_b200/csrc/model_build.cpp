@@ -1,0 +1,744 @@
+// Host model builder (setup time).  Re-derives what Box2DWorld::createWorld and the Box2DLink / Box2DJoint /
+// Box2DObject / Box2DRobot constructors leave behind in Box2D (src/sim_env/Box2DWorld.cpp:44-148, 872-948,
+// 1292-1363, 2046-2067, 3644-3721), using Box2D 2.3.1's published shape arithmetic (b2PolygonShape::Set,
+// ComputeMass; b2Body::ResetMassData), and flattens it into the word blob described in model.h.
+#include "model_build.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <stdexcept>
+
+namespace b2g {
+namespace {
+
+struct P2 {
+    float x, y;
+};
+inline P2 sub(P2 a, P2 b) { return P2{a.x - b.x, a.y - b.y}; }
+inline float cross2(P2 a, P2 b) { return a.x * b.y - a.y * b.x; }
+inline float dot2(P2 a, P2 b) { return a.x * b.x + a.y * b.y; }
+
+constexpr float kLinearSlop = 0.005f;
+constexpr float kPolygonRadius = 2.0f * kLinearSlop;
+constexpr float kAabbExtension = 0.1f;
+constexpr int kMaxPolyVerts = 8;
+
+struct Hull {
+    int n = 0;
+    P2 v[kMaxPolyVerts];
+    P2 nrm[kMaxPolyVerts];
+    P2 centroid{0.0f, 0.0f};
+};
+
+void boxHull(Hull& h, float hx, float hy) {
+    h.n = 4;
+    h.v[0] = P2{-hx, -hy}; h.v[1] = P2{hx, -hy}; h.v[2] = P2{hx, hy}; h.v[3] = P2{-hx, hy};
+    h.nrm[0] = P2{0.0f, -1.0f}; h.nrm[1] = P2{1.0f, 0.0f}; h.nrm[2] = P2{0.0f, 1.0f}; h.nrm[3] = P2{-1.0f, 0.0f};
+    h.centroid = P2{0.0f, 0.0f};
+}
+
+// b2PolygonShape::Set (2.3.1): weld, gift-wrap from the right-most point, normals, centroid
+void convexHull(Hull& h, const std::vector<P2>& in) {
+    int n = std::min((int)in.size(), kMaxPolyVerts);
+    if (n < 3) { boxHull(h, 1.0f, 1.0f); return; }
+    P2 pts[kMaxPolyVerts];
+    int np = 0;
+    for (int i = 0; i < n; ++i) {
+        bool keep = true;
+        for (int j = 0; j < np && keep; ++j) {
+            P2 d = sub(in[i], pts[j]);
+            if (dot2(d, d) < 0.5f * kLinearSlop) keep = false;
+        }
+        if (keep) pts[np++] = in[i];
+    }
+    if (np < 3) { boxHull(h, 1.0f, 1.0f); return; }
+    int start = 0;
+    float bestX = pts[0].x;
+    for (int i = 1; i < np; ++i) {
+        float x = pts[i].x;
+        if (x > bestX || (x == bestX && pts[i].y < pts[start].y)) { start = i; bestX = x; }
+    }
+    int order[kMaxPolyVerts];
+    int m = 0;
+    int cur = start;
+    while (true) {
+        order[m] = cur;
+        int next = 0;
+        for (int j = 1; j < np; ++j) {
+            if (next == cur) { next = j; continue; }
+            P2 r = sub(pts[next], pts[order[m]]);
+            P2 v = sub(pts[j], pts[order[m]]);
+            float c = cross2(r, v);
+            if (c < 0.0f) next = j;
+            if (c == 0.0f && dot2(v, v) > dot2(r, r)) next = j;
+        }
+        ++m;
+        cur = next;
+        if (next == start) break;
+    }
+    if (m < 3) { boxHull(h, 1.0f, 1.0f); return; }
+    h.n = m;
+    for (int i = 0; i < m; ++i) h.v[i] = pts[order[i]];
+    for (int i = 0; i < m; ++i) {
+        P2 e = sub(h.v[(i + 1 < m) ? i + 1 : 0], h.v[i]);
+        P2 nr{1.0f * e.y, -1.0f * e.x};  // b2Cross(edge, 1.0f)
+        float len = sqrtf(nr.x * nr.x + nr.y * nr.y);
+        if (!(len < FLT_EPSILON)) {
+            float inv = 1.0f / len;
+            nr.x *= inv;
+            nr.y *= inv;
+        }
+        h.nrm[i] = nr;
+    }
+    // centroid by triangle fan about the origin
+    P2 c{0.0f, 0.0f};
+    float area = 0.0f;
+    const float third = 1.0f / 3.0f;
+    for (int i = 0; i < m; ++i) {
+        P2 p1{0.0f, 0.0f};
+        P2 p2 = h.v[i];
+        P2 p3 = (i + 1 < m) ? h.v[i + 1] : h.v[0];
+        float D = cross2(sub(p2, p1), sub(p3, p1));
+        float tri = 0.5f * D;
+        area += tri;
+        float wgt = tri * third;
+        c.x += wgt * (p1.x + p2.x + p3.x);
+        c.y += wgt * (p1.y + p2.y + p3.y);
+    }
+    float ia = 1.0f / area;
+    c.x *= ia;
+    c.y *= ia;
+    h.centroid = c;
+}
+
+struct Mass {
+    float mass, cx, cy, I;
+};
+
+// b2PolygonShape::ComputeMass
+Mass hullMass(const Hull& h, float density) {
+    P2 center{0.0f, 0.0f};
+    float area = 0.0f, I = 0.0f;
+    P2 s{0.0f, 0.0f};
+    for (int i = 0; i < h.n; ++i) { s.x += h.v[i].x; s.y += h.v[i].y; }
+    float invn = 1.0f / h.n;
+    s.x *= invn;
+    s.y *= invn;
+    const float third = 1.0f / 3.0f;
+    for (int i = 0; i < h.n; ++i) {
+        P2 e1 = sub(h.v[i], s);
+        P2 e2 = (i + 1 < h.n) ? sub(h.v[i + 1], s) : sub(h.v[0], s);
+        float D = cross2(e1, e2);
+        float tri = 0.5f * D;
+        area += tri;
+        float wgt = tri * third;
+        center.x += wgt * (e1.x + e2.x);
+        center.y += wgt * (e1.y + e2.y);
+        float intx2 = e1.x * e1.x + e2.x * e1.x + e2.x * e2.x;
+        float inty2 = e1.y * e1.y + e2.y * e1.y + e2.y * e2.y;
+        I += (0.25f * third * D) * (intx2 + inty2);
+    }
+    Mass m;
+    m.mass = density * area;
+    float ia = 1.0f / area;
+    center.x *= ia;
+    center.y *= ia;
+    m.cx = center.x + s.x;
+    m.cy = center.y + s.y;
+    m.I = density * I;
+    m.I += m.mass * ((m.cx * m.cx + m.cy * m.cy) - (center.x * center.x + center.y * center.y));
+    return m;
+}
+
+// boost::geometry::area of the (corrected) polygon; its surveyor strategy accumulates float
+// coordinates in double (Box2DWorld.cpp:94-101)
+double polygonArea(const std::vector<float>& p) {
+    size_t n = p.size() / 2;
+    double acc = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+        size_t j = (i + 1 == n) ? 0 : i + 1;
+        acc += ((double)p[2 * i] + (double)p[2 * j]) * ((double)p[2 * i + 1] - (double)p[2 * j + 1]);
+    }
+    acc /= 2.0;
+    return acc < 0.0 ? -acc : acc;
+}
+
+struct BBody {
+    int type = 0;  // 0 static, 2 dynamic
+    float mass = 0, invMass = 0, I = 0, invI = 0, lcx = 0, lcy = 0;
+    int fixStart = 0, fixCount = 0, object = -1;
+    float px = 0, py = 0;  // creation position (ground only)
+    std::string name;
+};
+struct BFix {
+    int body;
+    Hull hull;
+    float friction, restitution, density;
+    bool sensor;
+};
+struct BJoint {
+    int type, bodyA, bodyB, flags;
+    float lax, lay, lbx, lby, ref, lower, upper, maxForce, maxTorque;
+    int dof = -1, object = -1;
+};
+struct BLink {
+    int body;
+    int parentJoint = -1;  // model joint
+    int parentPos = -1;
+    int subtree = 1;
+    std::vector<int> chain;
+};
+
+uint32_t fbits(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+}
+
+}  // namespace
+
+void layoutState(ModelHeader& h, int maxContacts) {
+    h.maxc = maxContacts;
+    int s = 0;
+    h.sBody = s; s += h.nb * SB_STRIDE;
+    h.sFix = s; s += h.nf * 4;
+    h.sJoint = s; s += h.nj * SJ_STRIDE;
+    h.sJointW = s; s += h.nj * WJ_STRIDE;
+    h.sCont = s; s += h.maxc * SC_STRIDE;
+    h.sContW = s; s += h.maxc * WC_STRIDE;
+    h.sScalar = s; s += SS_STRIDE;
+    h.sTarget = s; s += h.ntarget;
+    h.stateWords = s;
+}
+
+void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& out) {
+    const float scale = env.scale;
+    if (!(scale > 0.0f)) throw std::runtime_error("scale must be positive");
+    std::vector<BBody> bodies;
+    std::vector<BFix> fixtures;
+    std::vector<BJoint> joints;
+
+    // ---- ground (createGround, Box2DWorld.cpp:3644-3662)
+    float wb[4] = {env.world_bounds[0], env.world_bounds[1], env.world_bounds[2], env.world_bounds[3]};
+    float nrm = sqrtf(wb[0] * wb[0] + wb[1] * wb[1] + wb[2] * wb[2] + wb[3] * wb[3]);
+    if (nrm == 0.0) {
+        wb[0] = scale * -100.0f; wb[1] = scale * -100.0f; wb[2] = scale * 100.0f; wb[3] = scale * 100.0f;
+    }
+    {
+        BBody g;
+        g.type = 0;
+        g.px = 0.5f * scale * (wb[0] + wb[2]);
+        g.py = 0.5f * scale * (wb[1] + wb[3]);
+        g.fixStart = 0;
+        g.fixCount = 1;
+        g.name = "GROUND_BODY";
+        bodies.push_back(g);
+        BFix f;
+        f.body = 0;
+        boxHull(f.hull, scale * (wb[2] - wb[0]), scale * (wb[3] - wb[1]));
+        f.friction = 0.2f;
+        f.restitution = 0.0f;
+        f.density = 0.0f;
+        f.sensor = true;
+        fixtures.push_back(f);
+    }
+
+    struct BObject {
+        const ObjectDescription* d;
+        int firstBody, nLinks;
+        int baseBody;
+        float originX = 0, originY = 0, mass = 0;
+        std::vector<int> jointList;      // model joints, YAML order
+        std::vector<int> jointChildPos;  // pre-order position of the child link
+        std::vector<BLink> links;        // pre-order
+        std::vector<int> nameOrder;      // bodies in link-name order
+        int nDofs = 0, dofOffset = 0;
+    };
+    std::vector<BObject> objects;
+    std::vector<const ObjectDescription*> descs;
+    for (auto& r : env.robots) descs.push_back(&r);
+    for (auto& o : env.objects) descs.push_back(&o);
+    {
+        std::map<std::string, int> seen;
+        for (auto* d : descs)
+            if (seen[d->name]++) throw std::runtime_error("duplicate object name '" + d->name + "'");
+    }
+
+    int nq = 0;
+    for (size_t oi = 0; oi < descs.size(); ++oi) {
+        const ObjectDescription& d = *descs[oi];
+        if (d.links.empty()) throw std::runtime_error("object '" + d.name + "' has no links");
+        if ((int)d.links.size() > kMaxLinksPerObject) throw std::runtime_error("object '" + d.name + "' has too many links");
+        BObject ob;
+        ob.d = &d;
+        ob.firstBody = (int)bodies.size();
+        ob.nLinks = (int)d.links.size();
+        std::map<std::string, int> linkBody;
+        std::map<std::string, std::pair<float, float>> aabbMin, aabbMax;
+        // ---- links (Box2DLink ctor :44-148)
+        for (const LinkDescription& ld : d.links) {
+            if (linkBody.count(ld.name)) throw std::runtime_error("duplicate link name '" + ld.name + "'");
+            BBody b;
+            b.type = d.is_static ? 0 : 2;
+            b.object = (int)oi;
+            b.fixStart = (int)fixtures.size();
+            b.name = d.name + "/" + ld.name;
+            float area = 0.0f;
+            float mnx = std::numeric_limits<float>::max(), mny = mnx;
+            float mxx = std::numeric_limits<float>::lowest(), mxy = mxx;
+            std::vector<Hull> hulls;
+            if (ld.polygons.empty()) throw std::runtime_error("link '" + ld.name + "' has no geometry");
+            for (const std::vector<float>& poly : ld.polygons) {
+                std::vector<P2> pts;
+                for (size_t i = 0; i < poly.size() / 2; ++i) {
+                    mnx = std::min(poly[2 * i], mnx);
+                    mny = std::min(poly[2 * i + 1], mny);
+                    mxx = std::max(poly[2 * i], mxx);
+                    mxy = std::max(poly[2 * i + 1], mxy);
+                    pts.push_back(P2{scale * poly[2 * i], scale * poly[2 * i + 1]});
+                }
+                area += scale * scale * polygonArea(poly);
+                Hull h;
+                convexHull(h, pts);
+                hulls.push_back(h);
+            }
+            if (!(area > 0.0f)) throw std::runtime_error("link '" + ld.name + "' has zero area");
+            float density = ld.mass / area;
+            for (const Hull& h : hulls) {
+                BFix f;
+                f.body = (int)bodies.size();
+                f.hull = h;
+                f.friction = ld.contact_friction;
+                f.restitution = ld.restitution;
+                f.density = density;
+                f.sensor = false;
+                fixtures.push_back(f);
+            }
+            b.fixCount = (int)hulls.size();
+            // b2Body::ResetMassData after the last CreateFixture (fixture list is newest first)
+            if (b.type == 2) {
+                float m = 0.0f, I = 0.0f, lx = 0.0f, ly = 0.0f;
+                for (int k = (int)hulls.size() - 1; k >= 0; --k) {
+                    if (density == 0.0f) continue;
+                    Mass md = hullMass(hulls[k], density);
+                    m += md.mass;
+                    lx += md.mass * md.cx;
+                    ly += md.mass * md.cy;
+                    I += md.I;
+                }
+                if (m > 0.0f) {
+                    b.invMass = 1.0f / m;
+                    lx *= b.invMass;
+                    ly *= b.invMass;
+                } else {
+                    m = 1.0f;
+                    b.invMass = 1.0f;
+                }
+                if (I > 0.0f) {
+                    I -= m * (lx * lx + ly * ly);
+                    b.invI = 1.0f / I;
+                } else {
+                    I = 0.0f;
+                    b.invI = 0.0f;
+                }
+                b.mass = m;
+                b.I = I;
+                b.lcx = lx;
+                b.lcy = ly;
+            }
+            linkBody[ld.name] = (int)bodies.size();
+            aabbMin[ld.name] = {mnx, mny};
+            aabbMax[ld.name] = {mxx, mxy};
+            ob.mass += b.mass * (b.type == 2 ? 1.0f : 0.0f);  // b2Body::GetMass() of a static body is 0
+            // friction joint to the ground (:131-147)
+            BJoint fj;
+            fj.type = 0;
+            fj.bodyA = 0;
+            fj.bodyB = (int)bodies.size();
+            fj.flags = 0;
+            fj.lax = 0.0f; fj.lay = 0.0f;
+            fj.lbx = b.lcx; fj.lby = b.lcy;
+            fj.ref = 0.0f; fj.lower = 0.0f; fj.upper = 0.0f;
+            float gravity = 9.81f * scale;
+            float bodyMass = (b.type == 2) ? b.mass : 0.0f;
+            fj.maxForce = ld.ground_friction * gravity * bodyMass;
+            fj.maxTorque = ld.ground_friction * ld.ground_torque_integral * scale * scale;
+            fj.object = (int)oi;
+            joints.push_back(fj);
+            bodies.push_back(b);
+        }
+        // Box2DObject::_mass accumulates link->getMass() in YAML order (:1303)
+        {
+            float m = 0.0f;
+            for (int k = 0; k < ob.nLinks; ++k) {
+                const BBody& b = bodies[ob.firstBody + k];
+                m += (b.type == 2) ? b.mass : 0.0f;
+            }
+            ob.mass = m;
+        }
+        // ---- base link and origin (:1307-1312, 653-671)
+        std::string base = d.base_link;
+        if (base.empty()) {
+            ObjectDescription tmp = d;
+            std::string msg;
+            if (!verifyKinematicStructure(tmp, msg)) throw std::runtime_error("object '" + d.name + "': " + msg);
+            base = tmp.base_link;
+        }
+        if (!linkBody.count(base)) throw std::runtime_error("object '" + d.name + "': unknown base link '" + base + "'");
+        ob.baseBody = linkBody[base];
+        if (d.is_static) {
+            float cx = 0.5f * (aabbMin[base].first + aabbMax[base].first);
+            float cy = 0.5f * (aabbMin[base].second + aabbMax[base].second);
+            ob.originX = scale * cx;
+            ob.originY = scale * cy;
+        } else {
+            ob.originX = bodies[ob.baseBody].lcx;
+            ob.originY = bodies[ob.baseBody].lcy;
+        }
+        // ---- joints (Box2DJoint ctor :872-948)
+        int baseDofs = d.is_static ? 0 : 3;
+        ob.dofOffset = nq;
+        std::map<int, std::vector<std::pair<int, int>>> children;  // parent body -> (joint, child body), registration order
+        std::map<int, int> parentJointOf;
+        for (const JointDescription& jd : d.joints) {
+            if (jd.joint_type != "revolute")
+                throw std::runtime_error("joint '" + jd.name + "': joint_type '" + jd.joint_type +
+                                         "' is not supported (the reference cannot drive prismatic joints either: "
+                                         "Box2DWorld.cpp:1204-1208)");
+            if (!linkBody.count(jd.link_a) || !linkBody.count(jd.link_b))
+                throw std::runtime_error("joint '" + jd.name + "' names an unknown link");
+            BJoint j;
+            j.type = 1;
+            j.bodyA = linkBody[jd.link_a];
+            j.bodyB = linkBody[jd.link_b];
+            j.lax = scale * jd.axis[0];
+            j.lay = scale * jd.axis[1];
+            j.lbx = 0.0f;
+            j.lby = 0.0f;
+            j.ref = jd.axis_orientation;
+            j.lower = jd.position_limits[0];
+            j.upper = jd.position_limits[1];
+            float n2 = sqrtf(jd.position_limits[0] * jd.position_limits[0] + jd.position_limits[1] * jd.position_limits[1]);
+            j.flags = (n2 > 0.0 ? 1 : 0) | (jd.actuated ? 2 : 0);
+            j.maxForce = 0.0f;
+            j.maxTorque = 0.0f;
+            j.dof = nq + baseDofs + (int)ob.jointList.size();
+            j.object = (int)oi;
+            children[j.bodyA].push_back({(int)joints.size(), j.bodyB});
+            parentJointOf[j.bodyB] = (int)joints.size();
+            ob.jointList.push_back((int)joints.size());
+            joints.push_back(j);
+        }
+        ob.nDofs = baseDofs + (int)ob.jointList.size();
+        if (ob.nDofs > kMaxDofsPerObject) throw std::runtime_error("object '" + d.name + "' has too many DOFs");
+        nq += ob.nDofs;
+        // ---- pre-order link list with ancestor chains
+        {
+            struct Item { int body, parentJoint, parentPos; std::vector<int> chain; };
+            std::vector<Item> stack;
+            stack.push_back(Item{ob.baseBody, -1, -1, {}});
+            while (!stack.empty()) {
+                Item it = stack.back();
+                stack.pop_back();
+                BLink l;
+                l.body = it.body;
+                l.parentJoint = it.parentJoint;
+                l.parentPos = it.parentPos;
+                l.chain = it.chain;
+                int pos = (int)ob.links.size();
+                ob.links.push_back(l);
+                auto& ch = children[it.body];
+                for (int k = (int)ch.size() - 1; k >= 0; --k) {  // reversed push -> registration order when popped
+                    std::vector<int> c2 = it.chain;
+                    c2.push_back(ch[k].first);
+                    stack.push_back(Item{ch[k].second, ch[k].first, pos, c2});
+                }
+            }
+            if ((int)ob.links.size() != ob.nLinks)
+                throw std::runtime_error("object '" + d.name + "': links are not one kinematic tree");
+            for (int p = ob.nLinks - 1; p >= 0; --p)
+                if (ob.links[p].parentPos >= 0) ob.links[ob.links[p].parentPos].subtree += ob.links[p].subtree;
+            for (int jm : ob.jointList) {
+                int child = joints[jm].bodyB;
+                int pos = -1;
+                for (int p = 0; p < ob.nLinks; ++p)
+                    if (ob.links[p].body == child) pos = p;
+                ob.jointChildPos.push_back(pos);
+            }
+        }
+        for (auto& kv : linkBody) ob.nameOrder.push_back(kv.second);  // std::map iterates in name order
+        objects.push_back(ob);
+    }
+
+    int nb = (int)bodies.size(), nf = (int)fixtures.size(), nj = (int)joints.size(), no = (int)objects.size();
+    if (nb > kMaxBodies) throw std::runtime_error("too many bodies (max " + std::to_string(kMaxBodies) + ")");
+    if (nf > kMaxFixtures) throw std::runtime_error("too many fixtures (max " + std::to_string(kMaxFixtures) + ")");
+    if (nj > kMaxJoints) throw std::runtime_error("too many joints (max " + std::to_string(kMaxJoints) + ")");
+
+    // ---- joint edges per body, newest joint first; collide masks
+    std::vector<std::vector<std::pair<int, int>>> jedges(nb);
+    std::vector<uint64_t> collide(nb, 0);
+    for (int j = nj - 1; j >= 0; --j) {
+        jedges[joints[j].bodyA].push_back({j, joints[j].bodyB});
+        jedges[joints[j].bodyB].push_back({j, joints[j].bodyA});
+    }
+    for (int a = 0; a < nb; ++a)
+        for (int b = 0; b < nb; ++b) {
+            if (a == b) continue;
+            if (bodies[a].type != 2 && bodies[b].type != 2) continue;
+            bool jointed = false;
+            for (auto& e : jedges[a])
+                if (e.second == b) jointed = true;  // every joint the reference creates has collideConnected == false
+            if (!jointed) collide[a] |= (1ull << b);
+        }
+    std::vector<uint64_t> pairMask(nf, 0);
+    int nPairs = 0;
+    for (int f = 0; f < nf; ++f)
+        for (int g = 0; g < nf; ++g) {
+            if (f == g) continue;
+            int ba = fixtures[f].body, bb = fixtures[g].body;
+            if (ba == bb) continue;
+            if (!(collide[ba] >> bb & 1ull)) continue;
+            pairMask[f] |= (1ull << g);
+            if (f < g) ++nPairs;
+        }
+
+    // ---- robots in name order (std::map<std::string, Box2DRobotPtr> _robots, Box2DWorld.h)
+    std::vector<int> robotOrder;
+    {
+        std::map<std::string, int> byName;
+        for (int oi = 0; oi < no; ++oi)
+            if (objects[oi].d->is_robot) byName[objects[oi].d->name] = oi;
+        for (auto& kv : byName) robotOrder.push_back(kv.second);
+    }
+    std::vector<int> targetOffset(no, -1);
+    int ntarget = 0;
+    for (int oi = 0; oi < no; ++oi)
+        if (objects[oi].d->is_robot) {
+            targetOffset[oi] = ntarget;
+            ntarget += objects[oi].nDofs;
+        }
+
+    // ---- flatten
+    ModelHeader& h = out.h;
+    memset(&h, 0, sizeof(h));
+    h.nb = nb; h.nf = nf; h.nj = nj; h.no = no; h.nrobots = (int)robotOrder.size(); h.nq = nq; h.ntarget = ntarget;
+    h.scale = scale;
+    h.invScale = 1.0f / scale;
+    std::vector<uint32_t>& B = out.blob;
+    B.clear();
+    auto allocWords = [&](int n) { int o = (int)B.size(); B.resize(B.size() + n, 0u); return o; };
+
+    h.oJEdge = allocWords(0);
+    std::vector<int> jeStart(nb);
+    for (int b = 0; b < nb; ++b) {
+        jeStart[b] = (int)B.size() - h.oJEdge;
+        for (auto& e : jedges[b]) B.push_back((uint32_t)(e.first | (e.second << 16)));
+    }
+    h.oBody = allocWords(nb * MB_STRIDE);
+    for (int b = 0; b < nb; ++b) {
+        uint32_t* w = &B[h.oBody + b * MB_STRIDE];
+        const BBody& bd = bodies[b];
+        w[MB_INVMASS] = fbits(bd.invMass); w[MB_INVI] = fbits(bd.invI);
+        w[MB_MASS] = fbits(bd.type == 2 ? bd.mass : 0.0f); w[MB_I] = fbits(bd.I);
+        w[MB_LCX] = fbits(bd.lcx); w[MB_LCY] = fbits(bd.lcy);
+        w[MB_TYPE] = bd.type; w[MB_JE_START] = jeStart[b]; w[MB_JE_COUNT] = (uint32_t)jedges[b].size();
+        w[MB_FIX_START] = bd.fixStart; w[MB_FIX_COUNT] = bd.fixCount; w[MB_OBJECT] = (uint32_t)bd.object;
+        w[MB_COLLIDE_LO] = (uint32_t)(collide[b] & 0xffffffffull); w[MB_COLLIDE_HI] = (uint32_t)(collide[b] >> 32);
+        w[MB_PX] = fbits(bd.px); w[MB_PY] = fbits(bd.py);
+    }
+    h.oFix = allocWords(nf * MF_STRIDE);
+    for (int f = 0; f < nf; ++f) {
+        uint32_t* w = &B[h.oFix + f * MF_STRIDE];
+        const BFix& fx = fixtures[f];
+        w[MF_BODY] = fx.body; w[MF_COUNT] = fx.hull.n;
+        w[MF_FRICTION] = fbits(fx.friction); w[MF_RESTITUTION] = fbits(fx.restitution);
+        w[MF_PAIR_LO] = (uint32_t)(pairMask[f] & 0xffffffffull); w[MF_PAIR_HI] = (uint32_t)(pairMask[f] >> 32);
+        // fat AABB at creation: b2PolygonShape::ComputeAABB with the body at its creation pose (angle 0)
+        float px = bodies[fx.body].px, py = bodies[fx.body].py;
+        float lx = 0, ly = 0, ux = 0, uy = 0;
+        for (int i = 0; i < fx.hull.n; ++i) {
+            float x = (1.0f * fx.hull.v[i].x - 0.0f * fx.hull.v[i].y) + px;
+            float y = (0.0f * fx.hull.v[i].x + 1.0f * fx.hull.v[i].y) + py;
+            if (i == 0) { lx = ux = x; ly = uy = y; }
+            else {
+                lx = lx < x ? lx : x; ly = ly < y ? ly : y;
+                ux = ux > x ? ux : x; uy = uy > y ? uy : y;
+            }
+        }
+        lx -= kPolygonRadius; ly -= kPolygonRadius; ux += kPolygonRadius; uy += kPolygonRadius;
+        w[MF_FAT0 + 0] = fbits(lx - kAabbExtension); w[MF_FAT0 + 1] = fbits(ly - kAabbExtension);
+        w[MF_FAT0 + 2] = fbits(ux + kAabbExtension); w[MF_FAT0 + 3] = fbits(uy + kAabbExtension);
+        for (int i = 0; i < kMaxPolyVerts; ++i) {
+            P2 v = i < fx.hull.n ? fx.hull.v[i] : P2{0.0f, 0.0f};
+            P2 n = i < fx.hull.n ? fx.hull.nrm[i] : P2{0.0f, 0.0f};
+            w[MF_VERTS + 2 * i] = fbits(v.x); w[MF_VERTS + 2 * i + 1] = fbits(v.y);
+            w[MF_NORMALS + 2 * i] = fbits(n.x); w[MF_NORMALS + 2 * i + 1] = fbits(n.y);
+        }
+    }
+    h.oJoint = allocWords(nj * MJ_STRIDE);
+    for (int j = 0; j < nj; ++j) {
+        uint32_t* w = &B[h.oJoint + j * MJ_STRIDE];
+        const BJoint& jt = joints[j];
+        w[MJ_TYPE] = jt.type; w[MJ_BODYA] = jt.bodyA; w[MJ_BODYB] = jt.bodyB; w[MJ_FLAGS] = jt.flags;
+        w[MJ_LAX] = fbits(jt.lax); w[MJ_LAY] = fbits(jt.lay); w[MJ_LBX] = fbits(jt.lbx); w[MJ_LBY] = fbits(jt.lby);
+        w[MJ_REF] = fbits(jt.ref); w[MJ_LOWER] = fbits(jt.lower); w[MJ_UPPER] = fbits(jt.upper);
+        w[MJ_MAXFORCE] = fbits(jt.maxForce); w[MJ_MAXTORQUE] = fbits(jt.maxTorque);
+        w[MJ_DOF] = (uint32_t)jt.dof; w[MJ_OBJECT] = (uint32_t)jt.object;
+    }
+    // links / chains / object joints / name order / init
+    h.oLink = allocWords(0);
+    std::vector<int> linkStart(no);
+    std::vector<std::vector<int>> chainStarts(no);
+    {
+        int total = 0;
+        for (int oi = 0; oi < no; ++oi) { linkStart[oi] = total; total += objects[oi].nLinks; }
+        allocWords(total * ML_STRIDE);
+    }
+    h.oChain = allocWords(0);
+    for (int oi = 0; oi < no; ++oi)
+        for (int p = 0; p < objects[oi].nLinks; ++p) {
+            const BLink& l = objects[oi].links[p];
+            uint32_t* w = &B[h.oLink + (linkStart[oi] + p) * ML_STRIDE];
+            w[ML_BODY] = l.body; w[ML_PARENT_JOINT] = (uint32_t)l.parentJoint; w[ML_PARENT_POS] = (uint32_t)l.parentPos;
+            w[ML_SUBTREE] = l.subtree; w[ML_CHAIN_START] = (int)B.size() - h.oChain; w[ML_CHAIN_LEN] = (uint32_t)l.chain.size();
+            for (int c : l.chain) B.push_back((uint32_t)c);
+            // (B may reallocate: w is not used after push_back)
+        }
+    h.oObjJoint = allocWords(0);
+    std::vector<int> ojStart(no);
+    for (int oi = 0; oi < no; ++oi) {
+        ojStart[oi] = (int)B.size() - h.oObjJoint;
+        for (size_t k = 0; k < objects[oi].jointList.size(); ++k)
+            B.push_back((uint32_t)(objects[oi].jointList[k] | (objects[oi].jointChildPos[k] << 16)));
+    }
+    h.oName = allocWords(0);
+    std::vector<int> nameStart(no);
+    for (int oi = 0; oi < no; ++oi) {
+        nameStart[oi] = (int)B.size() - h.oName;
+        for (int b : objects[oi].nameOrder) B.push_back((uint32_t)b);
+    }
+    h.oRobotOrder = allocWords(0);
+    for (int r : robotOrder) B.push_back((uint32_t)r);
+    h.oInit = allocWords(0);
+    std::vector<int> initStart(no);
+    for (int oi = 0; oi < no; ++oi) {
+        initStart[oi] = (int)B.size() - h.oInit;
+        auto it = env.states.find(objects[oi].d->name);
+        const BObject& ob = objects[oi];
+        if (it == env.states.end()) {
+            B.push_back(0u);
+            B.push_back(0u);
+            continue;
+        }
+        const StateDescription& sd = it->second;
+        int expect = ob.d->is_static ? ob.nDofs + 3 : ob.nDofs;
+        if ((int)sd.configuration.size() != expect || (int)sd.velocity.size() != expect)
+            throw std::runtime_error("state of '" + ob.d->name + "' needs " + std::to_string(expect) + " values");
+        B.push_back(1u);
+        B.push_back((uint32_t)expect);
+        for (float v : sd.configuration) B.push_back(fbits(v));
+        for (float v : sd.velocity) B.push_back(fbits(v));
+    }
+    h.oDof = allocWords(nq * 6);
+    out.dofLimits.assign(nq * 6, 0.0f);
+    {
+        const float lo = std::numeric_limits<float>::lowest(), hi = std::numeric_limits<float>::max();
+        for (int oi = 0; oi < no; ++oi) {
+            const BObject& ob = objects[oi];
+            const ObjectDescription& d = *ob.d;
+            int baseDofs = d.is_static ? 0 : 3;
+            for (int k = 0; k < ob.nDofs; ++k) {
+                float lim[6] = {lo, hi, lo, hi, lo, hi};
+                if (k < baseDofs) {
+                    if (k == 2) { lim[0] = (float)-M_PI; lim[1] = (float)M_PI; }
+                    if (d.is_robot) {  // Box2DRobot ctor :2056-2066
+                        const float* vl = k < 2 ? d.translational_velocity_limits : d.rotational_velocity_limits;
+                        const float* al = k < 2 ? d.translational_acceleration_limits : d.rotational_acceleration_limits;
+                        lim[2] = vl[0]; lim[3] = vl[1]; lim[4] = al[0]; lim[5] = al[1];
+                    }
+                } else {
+                    const JointDescription& jd = d.joints[k - baseDofs];
+                    lim[0] = jd.position_limits[0]; lim[1] = jd.position_limits[1];
+                    lim[2] = jd.velocity_limits[0]; lim[3] = jd.velocity_limits[1];
+                    lim[4] = jd.acceleration_limits[0]; lim[5] = jd.acceleration_limits[1];
+                }
+                for (int c = 0; c < 6; ++c) {
+                    B[h.oDof + (ob.dofOffset + k) * 6 + c] = fbits(lim[c]);
+                    out.dofLimits[(ob.dofOffset + k) * 6 + c] = lim[c];
+                }
+            }
+        }
+    }
+    h.oObj = allocWords(no * MO_STRIDE);
+    for (int oi = 0; oi < no; ++oi) {
+        uint32_t* w = &B[h.oObj + oi * MO_STRIDE];
+        const BObject& ob = objects[oi];
+        w[MO_STATIC] = ob.d->is_static; w[MO_ROBOT] = ob.d->is_robot; w[MO_BASE_BODY] = ob.baseBody;
+        w[MO_NDOFS] = ob.nDofs; w[MO_DOF_OFFSET] = ob.dofOffset;
+        w[MO_LINK_START] = linkStart[oi]; w[MO_LINK_COUNT] = ob.nLinks;
+        w[MO_JOINT_START] = ojStart[oi]; w[MO_JOINT_COUNT] = (uint32_t)ob.jointList.size();
+        w[MO_ORIGIN_X] = fbits(ob.originX); w[MO_ORIGIN_Y] = fbits(ob.originY); w[MO_MASS] = fbits(ob.mass);
+        w[MO_NAME_START] = nameStart[oi]; w[MO_TARGET_OFFSET] = (uint32_t)targetOffset[oi];
+        w[MO_INIT_START] = initStart[oi];
+    }
+    h.words = (int)B.size();
+
+    if (maxContacts <= 0) maxContacts = std::min(nPairs, std::max(16, 2 * nf));
+    if (maxContacts < 1) maxContacts = 1;
+    if (maxContacts > kMaxContacts) maxContacts = kMaxContacts;
+    layoutState(h, maxContacts);
+
+    // ---- introspection
+    out.objects.clear();
+    for (int oi = 0; oi < no; ++oi) {
+        HostObjectInfo info;
+        info.name = objects[oi].d->name;
+        info.isRobot = objects[oi].d->is_robot;
+        info.isStatic = objects[oi].d->is_static;
+        info.nDofs = objects[oi].nDofs;
+        info.dofOffset = objects[oi].dofOffset;
+        info.firstBody = objects[oi].firstBody;
+        info.nLinks = objects[oi].nLinks;
+        info.nJoints = (int)objects[oi].jointList.size();
+        out.objects.push_back(info);
+    }
+    out.bodyNames.clear();
+    out.bodyModel.assign(nb * 8, 0.0f);
+    for (int b = 0; b < nb; ++b) {
+        out.bodyNames.push_back(bodies[b].name);
+        float* o = &out.bodyModel[b * 8];
+        o[0] = bodies[b].type == 2 ? bodies[b].mass : 0.0f; o[1] = bodies[b].invMass; o[2] = bodies[b].I; o[3] = bodies[b].invI;
+        o[4] = bodies[b].lcx; o[5] = bodies[b].lcy; o[6] = (float)bodies[b].type; o[7] = (float)bodies[b].fixCount;
+    }
+    out.fixInts.assign(nf * 3, 0);
+    out.fixFloats.assign(nf * 38, 0.0f);
+    for (int f = 0; f < nf; ++f) {
+        out.fixInts[f * 3] = fixtures[f].body; out.fixInts[f * 3 + 1] = fixtures[f].hull.n; out.fixInts[f * 3 + 2] = fixtures[f].sensor;
+        float* o = &out.fixFloats[f * 38];
+        for (int i = 0; i < fixtures[f].hull.n; ++i) {
+            o[2 * i] = fixtures[f].hull.v[i].x; o[2 * i + 1] = fixtures[f].hull.v[i].y;
+            o[16 + 2 * i] = fixtures[f].hull.nrm[i].x; o[16 + 2 * i + 1] = fixtures[f].hull.nrm[i].y;
+        }
+        o[32] = fixtures[f].hull.centroid.x; o[33] = fixtures[f].hull.centroid.y;
+        o[34] = fixtures[f].friction; o[35] = fixtures[f].restitution; o[36] = fixtures[f].density; o[37] = kPolygonRadius;
+    }
+    out.jointInts.assign(nj * 6, 0);
+    out.jointFloats.assign(nj * 15, 0.0f);
+    for (int j = 0; j < nj; ++j) {
+        int32_t* io = &out.jointInts[j * 6];
+        float* fo = &out.jointFloats[j * 15];
+        io[0] = joints[j].type; io[1] = joints[j].bodyA; io[2] = joints[j].bodyB; io[3] = 0;
+        io[4] = (joints[j].flags >> 1) & 1; io[5] = joints[j].flags & 1;
+        fo[6] = joints[j].maxForce; fo[7] = joints[j].maxTorque;
+        fo[8] = joints[j].lax; fo[9] = joints[j].lay; fo[10] = joints[j].lbx; fo[11] = joints[j].lby;
+        fo[12] = joints[j].ref; fo[13] = joints[j].lower; fo[14] = joints[j].upper;
+    }
+    out.warnings = env.warnings;
+}
+
+}  // namespace b2g

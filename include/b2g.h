@@ -1,0 +1,187 @@
+/* b2g.h — C ABI of the B200-native batched Box2D backend (libb2g.so).
+ *
+ * This is the drop-in boundary for the hot path of JoshuaHaustein/box2d_sim_env: every entry point
+ * replaces one (family of) sim_env::World / Box2DWorld method(s), applied to N independent worlds at
+ * once.  Citations are file:line in /root/reference.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - All functions return b2g_status (0 = ok).  b2g_last_error() gives the message of the last failure
+ *     on the calling thread (the reference throws std::logic_error / std::runtime_error instead,
+ *     e.g. src/sim_env/Box2DWorld.cpp:1700-1704).
+ *   - Arrays are row-major with the world index leading: q[n_worlds][nq].
+ *   - Units are the reference's user units (metres, radians, seconds); the `scale` of the YAML file
+ *     is applied internally exactly as Box2DWorld does (include/sim_env/Box2DWorld.h:829-841).
+ *   - "_dev" variants take device pointers (on the batch's device) and are asynchronous on the batch's
+ *     CUDA stream; the plain variants take host pointers, copy, and synchronise.
+ *   - A batch handle is not thread-safe (the reference serialises every call on one recursive mutex,
+ *     include/sim_env/Box2DWorld.h:852).
+ *   - There is no CPU fallback: every compute entry point fails with B2G_ERR_CUDA when no usable
+ *     sm_100 device is present.
+ */
+#ifndef B2G_H_
+#define B2G_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t b2g_status;
+enum {
+    B2G_OK = 0,
+    B2G_ERR_INVALID = 1,   /* bad argument / size mismatch (reference: std::runtime_error) */
+    B2G_ERR_IO = 2,        /* file missing or YAML not decodable */
+    B2G_ERR_CUDA = 3,      /* CUDA runtime failure or no device */
+    B2G_ERR_UNSUPPORTED = 4, /* e.g. prismatic joints (reference throws too: Box2DWorld.cpp:1204-1208) */
+    B2G_ERR_CAPACITY = 5   /* a world exceeded its contact-slot capacity (see b2g_batch_status) */
+};
+
+typedef struct b2g_env b2g_env;     /* mutable environment description (Box2DEnvironmentDescription) */
+typedef struct b2g_model b2g_model; /* immutable flattened model shared by all worlds of a batch */
+typedef struct b2g_batch b2g_batch; /* N worlds resident in HBM on one device */
+
+const char* b2g_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Environment description.  Replaces parseYAML (src/sim_env/Box2DIOUtils.cpp:63-92) and the description
+ * structs of include/sim_env/Box2DIOUtils.h:18-70.  The YAML reader accepts both the decoder's key names
+ * (ground_friction, ground_torque_integral; Box2DIOUtils.h:133-134) and the stale names of the shipped
+ * data (trans_friction, rot_friction; test_data/robots/test_robot.yaml:14-15) and ignores unknown keys.
+ * ------------------------------------------------------------------------------------------------- */
+b2g_status b2g_env_create(float scale, const float world_bounds[4], b2g_env** out);
+b2g_status b2g_env_load_yaml(const char* path, b2g_env** out);
+void b2g_env_destroy(b2g_env* env);
+/* base_limits8 = translational velocity(2), translational acceleration(2), rotational velocity(2),
+ * rotational acceleration(2); NULL for plain objects.  Returns the object index through *out_index
+ * (robots and objects are indexed separately, file order). */
+b2g_status b2g_env_add_object(b2g_env* env, const char* name, int is_robot, int is_static,
+                              const float* base_limits8, int use_center_of_mass, int* out_index);
+b2g_status b2g_env_add_link(b2g_env* env, int is_robot, int object, const char* name, float mass,
+                            float ground_friction, float ground_torque_integral, float contact_friction,
+                            float restitution, int* out_index);
+b2g_status b2g_env_add_polygon(b2g_env* env, int is_robot, int object, int link, const float* xy, int n_floats);
+/* params9 = axis(2), position_limits(2), velocity_limits(2), acceleration_limits(2), axis_orientation */
+b2g_status b2g_env_add_joint(b2g_env* env, int is_robot, int object, const char* name, const char* link_a,
+                             const char* link_b, const float* params9, int actuated, const char* joint_type);
+b2g_status b2g_env_add_state(b2g_env* env, const char* name, const float* configuration, const float* velocity, int n);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Model.  Replaces Box2DWorld::createWorld / createGround and the Box2DLink / Box2DJoint / Box2DObject /
+ * Box2DRobot constructors (src/sim_env/Box2DWorld.cpp:3664-3721, 3644-3662, 44-148, 872-948, 1292-1363,
+ * 2046-2067): polygon hulls, densities, mass data, friction joints to the ground, revolute joints,
+ * creation order, DOF indexing.
+ * ------------------------------------------------------------------------------------------------- */
+b2g_status b2g_model_create(const b2g_env* env, b2g_model** out);
+void b2g_model_destroy(b2g_model* model);
+
+typedef struct b2g_model_info {
+    int32_t n_bodies;    /* incl. the ground body (index 0) */
+    int32_t n_fixtures;  /* broad-phase proxies incl. the ground sensor (index 0) */
+    int32_t n_joints;    /* friction + revolute joints, creation order */
+    int32_t n_objects;   /* robots first, then objects (creation order) */
+    int32_t n_robots;
+    int32_t nq;          /* DOFs of the world state vector (Box2DObject::getDOFPositions over all objects) */
+    float scale;
+} b2g_model_info;
+b2g_status b2g_model_get_info(const b2g_model* model, b2g_model_info* out);
+
+typedef struct b2g_object_info {
+    char name[64];
+    int32_t is_robot, is_static;
+    int32_t n_dofs;      /* 3 base DOFs unless static + one per joint (Box2DWorld.cpp:1314-1331) */
+    int32_t dof_offset;  /* first index in the world state vector */
+    int32_t first_body, n_links, n_joints;
+} b2g_object_info;
+b2g_status b2g_model_get_object(const b2g_model* model, int object, b2g_object_info* out);
+/* DOF limits in world-state order: out[nq][6] = position lo/hi, velocity lo/hi, acceleration lo/hi
+ * (Box2DObject::getDOFInformation, Box2DWorld.cpp:1557-1583) */
+b2g_status b2g_model_get_dof_limits(const b2g_model* model, float* out);
+/* per body [8]: mass invMass I invI localCenter(2) type n_fixtures  (parity probe; b2Body mass data) */
+b2g_status b2g_model_get_bodies(const b2g_model* model, float* out);
+/* per fixture: iout[3] = body, vertex count, sensor; fout[38] = vertices(16) normals(16) centroid(2)
+ * friction restitution density radius  (b2PolygonShape::Set results) */
+b2g_status b2g_model_get_fixtures(const b2g_model* model, int32_t* iout, float* fout);
+/* per joint: iout[6] = kind(0 friction,1 revolute) bodyA bodyB 0 enableMotor enableLimit;
+ * fout[15] = 0 0 0 0 0 0 maxForce maxTorque anchorA(2) anchorB(2) referenceAngle lower upper */
+b2g_status b2g_model_get_joints(const b2g_model* model, int32_t* iout, float* fout);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Batch of worlds.  b2g_batch_create == N x Box2DWorld::loadWorld (Box2DWorld.cpp:3040-3054): every world
+ * starts in the state createWorld leaves (bodies placed, YAML `states` applied, nothing stepped).
+ * max_contacts <= 0 selects a default from the model.
+ * ------------------------------------------------------------------------------------------------- */
+b2g_status b2g_batch_create(const b2g_model* model, int64_t n_worlds, int device, int max_contacts, b2g_batch** out);
+void b2g_batch_destroy(b2g_batch* batch);
+/* setPhysicsTimeStep / setVelocitySteps / setPositionSteps (Box2DWorld.cpp:3340-3353); defaults 0.01, 15, 15 */
+b2g_status b2g_batch_set_params(b2g_batch* batch, float dt, int velocity_steps, int position_steps);
+/* per-world status after the last call: 0 ok, bit0 contact capacity exceeded, bit1 non-finite state */
+b2g_status b2g_batch_status(b2g_batch* batch, int32_t* out);
+void* b2g_batch_stream(b2g_batch* batch); /* cudaStream_t the batch launches on */
+b2g_status b2g_batch_sync(b2g_batch* batch);
+
+/* setWorldState (Box2DWorld.cpp:3492-3513 -> Box2DObject::setState :1980-1989): per object
+ * setTransform(pose) [pose = first three DOFs; static objects keep their pose], setDOFPositions(all),
+ * setDOFVelocities(all).  reset_caches != 0 first returns every world to the freshly loaded state
+ * (what clone(), :3026-3038, gives a planner: no contacts, zero warm-start impulses, inv_dt0 = 0).
+ * q, qd: [n_worlds][nq]. */
+b2g_status b2g_batch_set_state(b2g_batch* batch, const float* q, const float* qd, int reset_caches);
+b2g_status b2g_batch_set_state_dev(b2g_batch* batch, const float* q, const float* qd, int reset_caches);
+/* getWorldState (:3462-3474): dof_positions / dof_velocities of every object */
+b2g_status b2g_batch_get_state(b2g_batch* batch, float* q, float* qd);
+b2g_status b2g_batch_get_state_dev(b2g_batch* batch, float* q, float* qd);
+/* Box2DObject::setPose(x, y, theta) (:1940-1947) for one object in every world; pose: [n_worlds][3] */
+b2g_status b2g_batch_set_object_pose(b2g_batch* batch, int object, const float* pose);
+b2g_status b2g_batch_get_object_pose(b2g_batch* batch, int object, float* pose);
+
+/* Box2DRobotVelocityController::setTargetVelocity (src/sim_env/Box2DController.cpp:42-63) for robot
+ * `object` in every world; v: [n_worlds][n_dofs of that robot].  The controller is then evaluated
+ * in-kernel before every step (Box2DRobot::control, Box2DWorld.cpp:2284-2310). */
+b2g_status b2g_batch_set_target_velocity(b2g_batch* batch, int object, const float* v);
+b2g_status b2g_batch_set_target_velocity_dev(b2g_batch* batch, int object, const float* v);
+
+/* Box2DWorld::stepPhysics(steps, execute_controllers, allow_sleeping) (:3266-3283). */
+b2g_status b2g_batch_step(b2g_batch* batch, int steps, int execute_controllers, int allow_sleeping);
+/* "propagate" (planner-side composition): for t in [0, n_targets): setTargetVelocity(
+ * targets[t]) on robot `object`, stepPhysics(steps_per_target).  targets: [n_targets][n_worlds][n_dofs]
+ * on the device. One kernel launch. */
+b2g_status b2g_batch_rollout_dev(b2g_batch* batch, int object, const float* targets, int n_targets, int steps_per_target);
+
+/* Parity probes (b2Body / b2Joint / b2Contact state).  bodies: [n_worlds][n_bodies][16] =
+ * xf.p(2) xf.q.s xf.q.c c(2) a c0(2) a0 v(2) w sleepTime awake type */
+b2g_status b2g_batch_get_bodies(b2g_batch* batch, float* out);
+/* fat AABBs: [n_worlds][n_fixtures][4] */
+b2g_status b2g_batch_get_fat_aabbs(b2g_batch* batch, float* out);
+/* joints: iout [n_worlds][n_joints][6], fout [n_worlds][n_joints][15] (layout of b2g_model_get_joints with the
+ * impulses, limit state, motor settings filled in) */
+b2g_status b2g_batch_get_joints(b2g_batch* batch, int32_t* iout, float* fout);
+/* contacts in creation order (b2World contact list reversed): counts [n_worlds]; iout [n_worlds][max][8] =
+ * fixtureA fixtureB touching enabled pointCount type id0 id1; fout [n_worlds][max][12] = localNormal(2)
+ * localPoint(2) p0(2) n0 t0 p1(2) n1 t1 */
+b2g_status b2g_batch_get_contacts(b2g_batch* batch, int32_t* counts, int32_t* iout, float* fout, int max_per_world);
+
+/* Box2DCollisionChecker::updateContactCache (:2880-2911): b2World::UpdateContacts() then every contact with
+ * IsTouching && IsEnabled, in b2World contact-list order.  counts [n_worlds]; iout [n_worlds][max][4] = bodyA
+ * bodyB fixtureA fixtureB; fout [n_worlds][max][6] = contact_point(3) contact_normal(3), both multiplied by
+ * 1/scale exactly as the reference does (:2857-2862). */
+b2g_status b2g_batch_check_collision(b2g_batch* batch, int32_t* counts, int32_t* iout, float* fout, int max_per_world);
+
+/* saveState / restoreState / dropState (:3515-3541): a stack of world states (q, qd and static poses) */
+b2g_status b2g_batch_save_state(b2g_batch* batch);
+b2g_status b2g_batch_restore_state(b2g_batch* batch);
+b2g_status b2g_batch_drop_state(b2g_batch* batch);
+
+/* pinned host memory for the end-to-end path */
+b2g_status b2g_host_alloc(void** out, uint64_t bytes);
+void b2g_host_free(void* p);
+
+/* counters: kernels launched by this library since load (bench evidence) */
+uint64_t b2g_launch_count(void);
+/* device-side timing of the launches made since the last call (CUDA events on the batch stream):
+ * returns the accumulated milliseconds of step/rollout kernels and resets the accumulator */
+b2g_status b2g_batch_take_kernel_ms(b2g_batch* batch, float* out_ms, int32_t* out_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2G_H_ */

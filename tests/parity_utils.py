@@ -1,0 +1,84 @@
+"""Helpers shared by the parity tests: scenario generation and oracle <-> CUDA comparison."""
+import numpy as np
+
+import box2d_sim_env_b200 as b2g
+from oracle import b2o
+
+ENV_A = "test_env.yaml"
+ENV_B = "test_env_rigid_robot.yaml"
+
+
+def load_env_dict(name):
+    return b2o.load_env_yaml(b2g.data_path(name))
+
+
+def random_states(model, n, seed, spread=1.2, vel=1.0):
+    """Random world states inside the DOF limits: objects scattered around the origin so contacts happen."""
+    rng = np.random.default_rng(seed)
+    lim = model.dof_limits()
+    q = np.zeros((n, model.nq), np.float32)
+    qd = np.zeros((n, model.nq), np.float32)
+    for o in model.objects:
+        off, nd = o["dof_offset"], o["n_dofs"]
+        base = 0 if o["is_static"] else 3
+        if base:
+            q[:, off:off + 2] = rng.uniform(-spread, spread, (n, 2))
+            q[:, off + 2] = rng.uniform(-np.pi, np.pi, n)
+            qd[:, off:off + 2] = rng.uniform(-vel, vel, (n, 2))
+            qd[:, off + 2] = rng.uniform(-vel, vel, n)
+        for k in range(base, nd):
+            lo, hi = lim[off + k, 0], lim[off + k, 1]
+            q[:, off + k] = rng.uniform(0.9 * lo, 0.9 * hi, n)
+            qd[:, off + k] = rng.uniform(-vel, vel, n)
+    return q, qd
+
+
+def random_targets(model, robot, n, seed, segments=1):
+    rng = np.random.default_rng(seed)
+    lim = model.dof_limits()
+    o = model.objects[robot]
+    off, nd = o["dof_offset"], o["n_dofs"]
+    t = rng.uniform(lim[off:off + nd, 2], lim[off:off + nd, 3], (segments, n, nd)).astype(np.float32)
+    return t
+
+
+def oracle_worlds(env_dict, n, continuous=True):
+    env = b2o.OracleEnv(env_dict)
+    ws = [b2o.OracleWorld(env) for _ in range(n)]
+    for w in ws:
+        w.set_continuous(continuous)
+    return ws
+
+
+def contact_table(io, fo=None):
+    """Canonical (fixtureA, fixtureB, touching, pointCount) rows in creation order."""
+    return [tuple(int(x) for x in r[[0, 1, 2, 4]]) for r in io]
+
+
+def compare_world(batch_bodies, batch_contacts, w, oracle_world, atol=0.0):
+    """Returns a list of human-readable differences between world `w` of the batch and the oracle world."""
+    diffs = []
+    ob = oracle_world.bodies()
+    gb = batch_bodies[w]
+    names = ["px", "py", "qs", "qc", "cx", "cy", "a", "c0x", "c0y", "a0", "vx", "vy", "w", "sleep", "awake", "type"]
+    bad = np.argwhere(~((np.abs(ob - gb) <= atol) | (ob == gb) | (np.isnan(ob) & np.isnan(gb))))
+    for b, f in bad:
+        diffs.append("body %d %s: oracle %.9g cuda %.9g" % (b, names[f], ob[b, f], gb[b, f]))
+    counts, cio, cfo = batch_contacts
+    oio, ofo = oracle_world.contacts()
+    n = int(counts[w])
+    if n != len(oio):
+        diffs.append("contact count: oracle %d cuda %d" % (len(oio), n))
+    else:
+        for k in range(n):
+            if not np.array_equal(oio[k, :6], cio[w, k, :6]):
+                diffs.append("contact %d ints: oracle %s cuda %s" % (k, oio[k].tolist(), cio[w, k].tolist()))
+            elif oio[k, 4] > 0:
+                npts = int(oio[k, 4])
+                if not np.array_equal(oio[k, 6:6 + npts], cio[w, k, 6:6 + npts]):
+                    diffs.append("contact %d ids: oracle %s cuda %s" % (k, oio[k, 6:].tolist(), cio[w, k, 6:].tolist()))
+                sel = list(range(4 + 4 * npts))
+                a, b = ofo[k, sel], cfo[w, k, sel]
+                if not np.all((np.abs(a - b) <= atol) | (a == b)):
+                    diffs.append("contact %d floats: oracle %s cuda %s" % (k, a.tolist(), b.tolist()))
+    return diffs

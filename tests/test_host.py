@@ -1,0 +1,122 @@
+"""CPU-side tests of the product: YAML loader, model builder (against the oracle's independent builder), C ABI
+surface, and loud failure without a GPU.  No compute entry point is exercised here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from parity_utils import ENV_A, ENV_B, load_env_dict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol(b2g):
+    header = open(os.path.join(ROOT, "include", "b2g.h")).read()
+    declared = set(re.findall(r"^(?:b2g_status|void\*?|const char\*|uint64_t)\s+(b2g_[a-z0-9_]+)\s*\(", header, re.M))
+    assert declared, "no declarations found"
+    L = b2g.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), "libb2g.so does not export %s" % name
+    from box2d_sim_env_b200.batch_world import ABI_SYMBOLS
+    assert declared == set(ABI_SYMBOLS)
+
+
+@pytest.mark.parametrize("env_name", [ENV_A, ENV_B])
+def test_model_matches_oracle_builder(b2g, oracle, env_name):
+    m = b2g.Model(b2g.data_path(env_name))
+    w = oracle.OracleWorld(load_env_dict(env_name))
+    assert (m.n_bodies, m.n_fixtures, m.n_joints, m.nq) == (w.n_bodies, w.n_proxies, w.n_joints, w.nq)
+    assert np.array_equal(m.body_model(), w.body_model())          # bit-exact mass data
+    mi, mf = m.fixture_model()
+    oi, of = w.fixture_model()
+    assert np.array_equal(mi, oi) and np.array_equal(mf, of)       # bit-exact hulls / normals / densities
+    ji, jf = m.joint_model()
+    oji, ojf = w.joints()
+    assert np.array_equal(ji[:, [0, 1, 2, 4, 5]], oji[:, [0, 1, 2, 4, 5]])
+    assert np.array_equal(jf[:, 6:], ojf[:, 6:])
+    assert [o["name"] for o in m.objects] == [o["name"] for o in w.objects]
+    assert [o["n_dofs"] for o in m.objects] == [o["n_dofs"] for o in w.objects]
+
+
+def test_programmatic_env_equals_yaml(b2g):
+    a = b2g.Model(b2g.data_path(ENV_A))
+    b = b2g.Model(load_env_dict(ENV_A))       # dict -> b2g_env_* builder calls
+    assert np.array_equal(a.body_model(), b.body_model())
+    assert np.array_equal(a.fixture_model()[1], b.fixture_model()[1])
+    assert np.array_equal(a.joint_model()[1], b.joint_model()[1])
+    assert np.array_equal(a.dof_limits(), b.dof_limits())
+
+
+def test_dof_layout(b2g):
+    m = b2g.Model(b2g.data_path(ENV_A))
+    assert [(o["name"], o["n_dofs"], o["dof_offset"]) for o in m.objects] == [("my_robot", 7, 0), ("obj1", 3, 7), ("obj2", 1, 10)]
+    lim = m.dof_limits()
+    assert lim[0, 2:].tolist() == pytest.approx([-2, 2, -2, 2])
+    assert lim[2].tolist() == pytest.approx([-np.pi, np.pi, -1.54, 1.54, -1.4, 1.4])
+    assert lim[4].tolist() == pytest.approx([-1.05, 1.05, -10, 10, -30, 30])
+    assert lim[10].tolist() == pytest.approx([-1.57, 1.57, -10, 10, -1, 1])
+
+
+def test_yaml_stale_keys_are_aliased(b2g, tmp_path):
+    """The reference data says trans_friction / rot_friction, its decoder reads ground_friction /
+    ground_torque_integral: both spellings must load to the same model."""
+    src = b2g.data_path("")
+    import shutil
+    dst = tmp_path / "data"
+    shutil.copytree(src, dst)
+    for sub in ("objects", "robots"):
+        for f in os.listdir(dst / sub):
+            p = dst / sub / f
+            t = open(p).read().replace("ground_friction", "trans_friction").replace("ground_torque_integral", "rot_friction")
+            open(p, "w").write(t)
+    a = b2g.Model(b2g.data_path(ENV_A))
+    b = b2g.Model(str(dst / ENV_A))
+    assert np.array_equal(a.joint_model()[1], b.joint_model()[1])
+
+
+def test_yaml_errors_are_loud(b2g, tmp_path):
+    with pytest.raises(b2g.B2GError) as e:
+        b2g.Model(str(tmp_path / "missing.yaml"))
+    assert e.value.code == 2
+    bad = tmp_path / "bad.yaml"
+    bad.write_text("scale: 10.0\nrobots:\n  - name: r\n    filename: nothing.yaml\n")
+    with pytest.raises(b2g.B2GError):
+        b2g.Model(str(bad))
+
+
+def test_prismatic_is_rejected(b2g):
+    env = load_env_dict(ENV_A)
+    env["robots"][0]["joints"][0]["joint_type"] = "prismatic"
+    with pytest.raises(b2g.B2GError) as e:
+        b2g.Model(env)
+    assert e.value.code == 4
+
+
+def test_kinematic_structure_is_validated(b2g):
+    env = load_env_dict(ENV_A)
+    env["robots"][0]["joints"][0]["link_b"] = "nonexistent"
+    with pytest.raises(b2g.B2GError):
+        b2g.Model(env)
+
+
+def test_no_cpu_fallback(b2g):
+    """Without a CUDA device the product must fail loudly instead of computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(b2g.B2GError) as e:
+        b2g.BatchBox2DWorld(4).loadWorld(b2g.data_path(ENV_A))
+    assert e.value.code == 3
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under box2d_sim_env_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "box2d_sim_env_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, f), errors="ignore").read()
+                assert "libb2o" not in text and "from oracle" not in text and "import oracle" not in text, f

@@ -1,0 +1,190 @@
+"""Known answers derived from first principles pin the oracle's shape, mass and ordering
+arithmetic.  The reference itself holds no golden vectors for this path (parity unpinned), so these double-precision
+derivations are the anchor."""
+import numpy as np
+import pytest
+
+from parity_utils import ENV_A, ENV_B, load_env_dict
+
+
+def test_sincos_accuracy(oracle):
+    x = np.concatenate([np.linspace(-40, 40, 200001), np.array([0.0, 1e-8, -1e-8, np.pi / 2, np.pi, 100.0, -250.0])]).astype(np.float32)
+    s, c = oracle.sincos(x)
+    es = np.abs(s.astype(np.float64) - np.sin(x.astype(np.float64)))
+    ec = np.abs(c.astype(np.float64) - np.cos(x.astype(np.float64)))
+    assert es.max() < 2.5e-7 and ec.max() < 2.5e-7     # <= ~2 ulp at magnitude 1
+    s0, c0 = oracle.sincos(np.zeros(1, np.float32))
+    assert s0[0] == 0.0 and c0[0] == 1.0
+
+
+def test_hull_order_square(oracle):
+    # obj1: 0.1 x 0.1 square scaled by 10 -> hull order [1,2,3,0]
+    p = oracle.polygon_set([[0, 0], [1, 0], [1, 1], [0, 1]], density=0.1)
+    assert p["count"] == 4
+    assert p["vertices"].tolist() == [[1, 0], [1, 1], [0, 1], [0, 0]]
+    assert p["normals"].tolist() == [[1, 0], [0, 1], [-1, 0], [0, -1]]
+    assert p["mass"] == pytest.approx(0.1, rel=1e-6)
+    assert p["center"].tolist() == pytest.approx([0.5, 0.5], rel=1e-6)
+    # inertia about the body origin: I_com + m*|c|^2 = 0.1/6 + 0.1*0.5
+    assert p["I"] == pytest.approx(0.1 / 6 + 0.05, rel=1e-5)
+
+
+def test_hull_order_triangle(oracle):
+    # robot base triangle [(0,0),(4,-4),(8,0)] -> [2,0,1]
+    p = oracle.polygon_set([[0, 0], [4, -4], [8, 0]])
+    assert p["vertices"].tolist() == [[8, 0], [0, 0], [4, -4]]
+
+
+def test_hull_welds_and_drops_collinear(oracle):
+    p = oracle.polygon_set([[0, 0], [1, 0], [2, 0], [2, 2], [0, 2], [0.00001, 0.00001]])
+    assert p["count"] == 4
+
+
+def test_mass_data_shape_a(oracle):
+    w = oracle.OracleWorld(load_env_dict(ENV_A))
+    bm = w.body_model()
+    # mass, local COM, I about COM, invMass, invI
+    expect = {
+        1: (10.1, (4.0, -0.1666667), 60.3194, 0.0990099, 0.0165784),
+        2: (0.3, (0.0, 2.0), 0.425, 3.33333, 2.35294),
+        3: (0.1, (0.0, 1.0), 0.0416667, 10.0, 24.0),
+        4: (0.3, (0.0, 2.0), 0.425, 3.33333, 2.35294),
+        5: (0.1, (0.0, 1.0), 0.0416667, 10.0, 24.0),
+        6: (0.1, (0.5, 0.5), 0.0166667, 10.0, 60.0),
+    }
+    for b, (m, com, I, im, ii) in expect.items():
+        assert bm[b, 0] == pytest.approx(m, rel=2e-6)
+        assert bm[b, 4:6].tolist() == pytest.approx(com, rel=2e-6, abs=1e-6)
+        assert bm[b, 2] == pytest.approx(I, rel=5e-6)
+        assert bm[b, 1] == pytest.approx(im, rel=5e-6)
+        assert bm[b, 3] == pytest.approx(ii, rel=5e-6)
+    for b in (0, 7, 8):   # ground and the static obj2 links carry no mass in Box2D
+        assert bm[b, :4].tolist() == [0, 0, 0, 0]
+
+
+def test_mass_data_rigid_base(oracle):
+    w = oracle.OracleWorld(load_env_dict(ENV_B))
+    bm = w.body_model()
+    assert bm[1, 0] == pytest.approx(10.1, rel=2e-6)
+    assert bm[1, 4:6].tolist() == pytest.approx([4.0, 0.468254], rel=2e-6)
+    assert bm[1, 2] == pytest.approx(85.8398, rel=5e-6)
+    assert bm[1, 3] == pytest.approx(0.0116496, rel=5e-6)
+
+
+def test_creation_order_and_joints(oracle):
+    w = oracle.OracleWorld(load_env_dict(ENV_A))
+    assert (w.n_bodies, w.n_proxies, w.n_joints, w.nq) == (9, 10, 13, 11)
+    jio, jfo = w.joints()
+    # fric_base, fric_fl1, fric_fl2, fric_fr1, fric_fr2, rev_l1, rev_l2, rev_r1, rev_r2, fric_obj1, fric_o2a, fric_o2b, rev_obj2
+    assert jio[:, 0].tolist() == [0, 0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0, 1]
+    assert jio[:, 1].tolist() == [0, 0, 0, 0, 0, 1, 2, 1, 4, 0, 0, 0, 7]
+    assert jio[:, 2].tolist() == [1, 2, 3, 4, 5, 2, 3, 4, 5, 6, 7, 8, 8]
+    # revolute anchors in the parent frame (Box2D units) and limits
+    assert jfo[5, 8:10].tolist() == pytest.approx([1, 1]) and jfo[6, 8:10].tolist() == pytest.approx([0, 3.5])
+    assert jfo[7, 8:10].tolist() == pytest.approx([7, 1]) and jfo[8, 8:10].tolist() == pytest.approx([0, 3.5])
+    assert np.allclose(jfo[5:9, 13], -1.05) and np.allclose(jfo[5:9, 14], 1.05)
+    # friction joints: maxForce = mu_g * 98.1 * m, maxTorque = mu_g * integral * 100
+    assert jfo[0, 6] == pytest.approx(0.1 * 98.1 * 10.1, rel=1e-5) and jfo[0, 7] == pytest.approx(0.1 * 0.1 * 100, rel=1e-5)
+    assert jfo[9, 6] == pytest.approx(0.001 * 98.1 * 0.1, rel=1e-5)
+
+
+def test_initial_state_matches_yaml(oracle):
+    w = oracle.OracleWorld(load_env_dict(ENV_A))
+    q, qd = w.get_state()
+    assert q.tolist() == pytest.approx([0, 0, 0, 0, 0, 0, 0, 0.9, 1.0, -1.0, 0.0], abs=2e-7)
+    assert qd.tolist() == pytest.approx([0, 0, 0, 0, -5.5, 0, 0, -0.2, -0.1, 1.0, 0.0], abs=1e-6)
+    # initial obj1 transform the reference's test passes to the sim_env suite (tests/test_Box2DWorld.cpp:38)
+    assert w.get_object_pose(1).tolist() == pytest.approx([0.9, 1.0, -1.0], abs=2e-7)
+    # static obj2 at (2.9, 1.2, -6.12) (test_env.yaml:23-25)
+    assert w.get_object_pose(2).tolist() == pytest.approx([2.9, 1.2, -6.12], abs=1e-6)
+
+
+def test_island_order_no_contacts(oracle):
+    w = oracle.OracleWorld(load_env_dict(ENV_A))
+    w.trace_islands(True)
+    w.step(1)
+    tr = w.island_trace()
+    # island 1 seeds at obj1, island 2 at finger_r_2; joints in DFS order
+    assert tr[0]["bodies"] == [6, 0] and tr[0]["joints"] == [9]
+    assert tr[1]["bodies"] == [5, 0, 4, 1, 2, 3]
+    assert tr[1]["joints"] == [8, 4, 7, 3, 5, 0, 6, 1, 2]
+
+
+def test_momentum_free_flight(oracle):
+    """With (almost) no ground friction and no contacts a box keeps its velocity: checks the integrator."""
+    env = load_env_dict(ENV_A)
+    for o in env["objects"]:
+        for l in o["links"]:
+            l["ground_friction"] = 0.0
+    env["states"]["obj1"] = dict(configuration=[-1.5, -1.5, 0.3], velocity=[0.3, -0.2, 0.7])
+    w = oracle.OracleWorld(env)
+    q0, qd0 = w.get_state()
+    w.step(50)
+    q1, qd1 = w.get_state()
+    assert qd1[7:10].tolist() == pytest.approx([0.3, -0.2, 0.7], rel=1e-6)
+    assert q1[7:10].tolist() == pytest.approx([-1.5 + 0.5 * 0.3, -1.5 - 0.5 * 0.2, 0.3 + 0.5 * 0.7], rel=1e-5)
+
+
+def test_ground_friction_decelerates(oracle):
+    """Coulomb ground friction: a sliding box loses mu*g per second (b2FrictionJoint maxForce = mu*m*g)."""
+    env = load_env_dict(ENV_A)
+    for l in env["objects"][0]["links"]:
+        l["ground_friction"] = 0.05
+        l["ground_torque_integral"] = 0.0
+    env["states"]["obj1"] = dict(configuration=[-1.5, -1.5, 0.0], velocity=[1.0, 0.0, 0.0])
+    w = oracle.OracleWorld(env)
+    w.step(100)
+    _, qd = w.get_state()
+    assert qd[7] == pytest.approx(1.0 - 0.05 * 9.81 * 1.0, rel=2e-3)
+
+
+def test_joint_limits_respected_and_anchor_drift(oracle):
+    w = oracle.OracleWorld(load_env_dict(ENV_A))
+    w.set_target_velocity(0, [0.5, 0.0, 0.3, 0.5, -0.5, -0.5, 0.5])
+    for _ in range(300):
+        w.step(1)
+        q, _ = w.get_state()
+        assert np.all(np.abs(q[3:7]) <= 1.05 + 2.0 / 180.0 * np.pi + 1e-3)
+    b = w.bodies()
+    # revolute anchor drift <= linearSlop-ish: child origin (xf.p) vs parent anchor
+    jio, jfo = w.joints()
+    for j in (5, 6, 7, 8):
+        a, c = jio[j, 1], jio[j, 2]
+        s, co = b[a, 2], b[a, 3]
+        ax = co * jfo[j, 8] - s * jfo[j, 9] + b[a, 0]
+        ay = s * jfo[j, 8] + co * jfo[j, 9] + b[a, 1]
+        assert np.hypot(ax - b[c, 0], ay - b[c, 1]) < 0.02
+
+
+def test_velocity_controller_reaches_target(oracle):
+    w = oracle.OracleWorld(load_env_dict(ENV_A))
+    w.set_target_velocity(0, [0.3, -0.2, 0.2, 0, 0, 0, 0])
+    w.step(200)
+    _, qd = w.get_state()
+    assert qd[:3].tolist() == pytest.approx([0.3, -0.2, 0.2], abs=0.05)
+
+
+def test_sleep_zeroes_velocity(oracle):
+    w = oracle.OracleWorld(load_env_dict(ENV_A))
+    q, qd = w.get_state()
+    qd[:] = 0
+    w.set_state(q, qd)
+    w.step(80)   # > timeToSleep / dt = 50 steps of rest
+    b = w.bodies()
+    assert np.all(b[1:7, 14] == 0.0)        # every dynamic body asleep
+    assert np.all(b[1:7, 10:13] == 0.0)
+
+
+def test_contact_and_toi_vs_static(oracle):
+    """A box thrown at the static obstacle must not tunnel (TOI path) and must bounce (restitution 1)."""
+    env = load_env_dict(ENV_A)
+    env["states"]["obj1"] = dict(configuration=[2.9, 0.4, 0.0], velocity=[0.0, 8.0, 0.0])
+    w = oracle.OracleWorld(env)
+    toi_events = 0
+    for _ in range(40):
+        w.step(1)
+        toi_events += w.stats()["toi_events"]
+    q, qd = w.get_state()
+    assert toi_events > 0
+    assert q[8] < 1.2            # did not pass through the bar centred at y = 1.2
+    assert qd[8] < 0.0           # bounced back
