@@ -688,7 +688,7 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
     }
     h.words = (int)B.size();
 
-    if (maxContacts <= 0) maxContacts = std::min(nPairs, std::max(16, 2 * nf));
+    if (maxContacts <= 0) maxContacts = std::min(nPairs, std::max(32, 2 * nf));
     if (maxContacts < 1) maxContacts = 1;
     if (maxContacts > kMaxContacts) maxContacts = kMaxContacts;
     layoutState(h, maxContacts);

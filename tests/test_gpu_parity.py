@@ -62,29 +62,42 @@ def test_set_state_parity(b2g, env_name):
         assert np.array_equal(gq[w], oq) and np.array_equal(gqd[w], oqd)
 
 
-@pytest.mark.parametrize("env_name,continuous", [(ENV_A, False), (ENV_B, False), (ENV_A, True), (ENV_B, True)])
-def test_single_step_parity(b2g, env_name, continuous):
-    """fresh world -> set_state -> one stepPhysics with the velocity controller running."""
+def scatter_obstacle(batch, worlds, seed, spread=0.6):
+    """Move the static obstacle obj2 near the origin (per-world random pose) so that dynamic-vs-static contacts,
+    i.e. TOI candidates, occur."""
+    n = len(worlds)
+    rng = np.random.default_rng(seed)
+    poses = np.concatenate([rng.uniform(-spread, spread, (n, 2)), rng.uniform(-3.1, 3.1, (n, 1))], axis=1).astype(np.float32)
+    batch.setObjectPose("obj2", poses)
+    for w, ow in enumerate(worlds):
+        ow.set_object_pose(2, *[float(x) for x in poses[w]])
+
+
+@pytest.mark.parametrize("env_name", [ENV_A, ENV_B])
+def test_single_step_parity(b2g, env_name):
+    """fresh world -> set_state -> one stepPhysics with the velocity controller running (BASELINE.json's
+    single-step gate: <= 1e-5 on poses and velocities, bit-exact contact sets; here everything is bit-exact)."""
     n = 256
     batch = make_batch(b2g, env_name, n)
-    worlds = oracle_worlds(load_env_dict(env_name), n, continuous=continuous)
-    if not continuous:
-        pytest.skip("the CUDA path always runs continuous physics, as the reference does")
-    q, qd = random_states(batch.model, n, seed=11)
+    worlds = oracle_worlds(load_env_dict(env_name), n)
+    q, qd = random_states(batch.model, n, seed=11, spread=0.6)
     tgt = random_targets(batch.model, 0, n, seed=12)[0]
     batch.setWorldState(q, qd, reset_caches=True)
     batch.setTargetVelocity(0, tgt)
-    batch.stepPhysics(1)
     for w, ow in enumerate(worlds):
         ow.set_state(q[w], qd[w])
         ow.set_target_velocity(0, tgt[w])
+    scatter_obstacle(batch, worlds, seed=13)
+    batch.stepPhysics(1)
+    for ow in worlds:
         ow.step(1)
     assert_same(batch, worlds, "single step")
-    # the tolerance BASELINE.json asks for (1e-5 m, rad, m/s) holds trivially when bits match
     gq, gqd = batch.getWorldState()
     oq = np.stack([ow.get_state()[0] for ow in worlds])
     oqd = np.stack([ow.get_state()[1] for ow in worlds])
     assert np.max(np.abs(gq - oq)) <= 1e-5 and np.max(np.abs(gqd - oqd)) <= 1e-5
+    counts, cio, _ = batch.contacts()
+    assert int(cio[..., 2].sum()) > 20, "scenario produced too few touching contacts"
 
 
 @pytest.mark.parametrize("env_name", [ENV_A, ENV_B])
@@ -94,12 +107,14 @@ def test_multi_step_trajectory_parity(b2g, env_name):
     n = 128
     batch = make_batch(b2g, env_name, n)
     worlds = oracle_worlds(load_env_dict(env_name), n)
-    q, qd = random_states(batch.model, n, seed=21, spread=0.8)
+    q, qd = random_states(batch.model, n, seed=21, spread=0.6)
     tg = random_targets(batch.model, 0, n, seed=22, segments=12)
     batch.setWorldState(q, qd, reset_caches=True)
     for w, ow in enumerate(worlds):
         ow.set_state(q[w], qd[w])
+    scatter_obstacle(batch, worlds, seed=23)
     touching_seen = 0
+    toi_events = 0
     for seg in range(12):
         batch.setTargetVelocity(0, tg[seg])
         batch.stepPhysics(10)
@@ -109,7 +124,9 @@ def test_multi_step_trajectory_parity(b2g, env_name):
         assert_same(batch, worlds, "segment %d" % seg)
         counts, cio, _ = batch.contacts()
         touching_seen += int(cio[..., 2].sum())
-    assert touching_seen > 0, "scenario produced no touching contacts; parity would be vacuous"
+        toi_events += sum(ow.stats()["toi_events"] for ow in worlds)
+    assert touching_seen > 100, "scenario produced too few touching contacts; parity would be vacuous"
+    assert toi_events > 0, "scenario never exercised the TOI sub-step path"
     assert np.all(batch.status() == 0)
 
 

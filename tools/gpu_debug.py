@@ -33,12 +33,19 @@ for env_name in (ENV_A, ENV_B):
         return nbad
 
     check("fresh")
-    q, qd = random_states(batch.model, n, seed=21, spread=0.8)
+    q, qd = random_states(batch.model, n, seed=21, spread=0.6)
     tg = random_targets(batch.model, 0, n, seed=22, segments=segs)
     batch.setWorldState(q, qd, reset_caches=True)
     for w, ow in enumerate(worlds):
         ow.set_state(q[w], qd[w])
     check("set_state")
+    # put the static obstacle near the origin so that dynamic-vs-static contacts (TOI candidates) happen
+    rng = np.random.default_rng(5)
+    poses = np.concatenate([rng.uniform(-0.6, 0.6, (n, 2)), rng.uniform(-3.1, 3.1, (n, 1))], axis=1).astype(np.float32)
+    batch.setObjectPose("obj2", poses)
+    for w, ow in enumerate(worlds):
+        ow.set_object_pose(2, *[float(x) for x in poses[w]])
+    check("set obj2 pose")
     for seg in range(segs):
         batch.setTargetVelocity(0, tg[seg])
         for w, ow in enumerate(worlds):
@@ -49,6 +56,7 @@ for env_name in (ENV_A, ENV_B):
                 ow.step(1)
             if check("seg %d step %d" % (seg, s)):
                 sys.exit(1)
+        print("   toi events this segment (oracle):", sum(ow.stats()["toi_events"] for ow in worlds), "calls", sum(ow.stats()["toi_calls"] for ow in worlds))
     print("status", np.unique(batch.status()))
     t0 = time.time(); batch.stepPhysics(100); print("100 steps x", n, "worlds:", time.time() - t0, "s", batch.take_kernel_ms())
 print("ALL OK")
