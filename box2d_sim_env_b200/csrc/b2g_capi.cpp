@@ -74,7 +74,7 @@ struct b2g_batch {
     float* S = nullptr;
     float* tmpl = nullptr;
     cudaStream_t stream = nullptr;
-    StepParams prm{0.01f, 15, 15};
+    StepParams prm{0.01f, 1.0f / 0.01f, 15, 15};
     int block = 32;
     DevBuf stageA, stageB, stageC;
     std::vector<SavedState> stack;
@@ -312,15 +312,17 @@ b2g_status b2g_batch_create(const b2g_model* model, int64_t n_worlds, int device
     if ((e = cudaMalloc((void**)&b->blob, b->m.blob.size() * 4)) != cudaSuccess) return cleanup(e, "cudaMalloc(model)");
     if ((e = cudaMemcpy(b->blob, b->m.blob.data(), b->m.blob.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
         return cleanup(e, "cudaMemcpy(model)");
-    size_t stateBytes = (size_t)b->m.h.stateWords * (size_t)n_worlds * 4;
+    // state[tile][chunk][lane]: tiles of 32 worlds, 16-byte chunks (model.h)
+    size_t tiles = ((size_t)n_worlds + kTileWorlds - 1) / kTileWorlds;
+    size_t stateBytes = tiles * (size_t)b->m.h.stateChunks * kChunkBytes;
     if ((e = cudaMalloc((void**)&b->S, stateBytes)) != cudaSuccess) return cleanup(e, "cudaMalloc(state)");
-    if ((e = cudaMalloc((void**)&b->tmpl, (size_t)b->m.h.stateWords * 4)) != cudaSuccess) return cleanup(e, "cudaMalloc(template)");
-    // build the freshly loaded world once (world 0 of a 1-world launch), keep it as the template, broadcast
+    if ((e = cudaMalloc((void**)&b->tmpl, (size_t)b->m.h.stateChunks * 16)) != cudaSuccess) return cleanup(e, "cudaMalloc(template)");
+    // build the freshly loaded world once (world 0), keep its chunks as the template, broadcast to every world
     {
         Launch l = b->L();
         l.N = 1;
-        l.S = b->tmpl;  // a 1-world state array has the template's [slot] layout
         if ((e = launchInit(l)) != cudaSuccess) return cleanup(e, "init kernel");
+        if ((e = launchExtractWorld(b->L(), b->tmpl, 0)) != cudaSuccess) return cleanup(e, "extract kernel");
         if ((e = launchBroadcast(b->L(), b->tmpl)) != cudaSuccess) return cleanup(e, "broadcast kernel");
         if ((e = cudaStreamSynchronize(b->stream)) != cudaSuccess) return cleanup(e, "init sync");
     }
@@ -350,6 +352,7 @@ void b2g_batch_destroy(b2g_batch* b) {
 b2g_status b2g_batch_set_params(b2g_batch* b, float dt, int velocity_steps, int position_steps) {
     if (!b || !(dt > 0.0f) || velocity_steps < 0 || position_steps < 0) return fail(B2G_ERR_INVALID, "bad step parameters");
     b->prm.dt = dt;
+    b->prm.inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;
     b->prm.velIters = velocity_steps;
     b->prm.posIters = position_steps;
     return B2G_OK;

@@ -1,8 +1,8 @@
 // Device-side building blocks of the batched Box2D backend (sm_100a, one world per thread).
 //
-// Data layout: every mutable quantity of world w lives in one word array S[slot][world] (world index
-// fastest), so a warp touching the same slot of 32 consecutive worlds issues one coalesced 128-byte
-// request.  The immutable model blob (model.h) is staged in shared memory by every CTA.
+// Data layout: the mutable state of the batch is one array of 16-byte chunks tiled by warp,
+// state[tile][chunk][lane] (model.h), so a warp touching chunk k of its 32 worlds issues one coalesced 512-byte
+// LDG.128 / STG.128.  The immutable model blob (model.h) is staged in shared memory by every CTA.
 //
 // Arithmetic: IEEE single precision, compiled with --fmad=false, IEEE division and square root, and a
 // fixed-sequence sin/cos, so that results are reproducible bit for bit across launches, GPU counts and
@@ -125,79 +125,92 @@ DEV V2 solve22(float a11, float a12, float a21, float a22, V2 b) {
 }
 
 // ---- world context ----------------------------------------------------------------------------------------
+// Shared memory of every kernel: [ModelHeader][StepParams][pad to 16 B][model blob].  It is addressed through this
+// one extern array so that the compiler emits LDS (never generic loads) and knows model reads cannot alias the
+// global-memory state.
+extern __shared__ __align__(16) uint32_t g_sm[];
+constexpr int kHdrWords = (int)((sizeof(ModelHeader) + sizeof(StepParams) + 15) / 16 * 4);
+
+DEV const ModelHeader& H() { return *reinterpret_cast<const ModelHeader*>(g_sm); }
+DEV const StepParams& PRM() { return *reinterpret_cast<const StepParams*>(g_sm + sizeof(ModelHeader) / 4); }
+
 struct Ctx {
-    float* S;                  // &state[world]; slot s lives at S[s * N]
-    size_t N;                  // number of worlds (slot stride)
-    const uint32_t* M;         // model blob (shared memory)
-    const ModelHeader* h;      // model header (shared memory)
-    float dt, inv_dt;
-    int velIters, posIters;
+    char* P;  // &state[tile][0][lane]: chunk k of this thread's world is the float4 at P + k * 512
 };
 
-DEV float ldF(const Ctx& c, int slot) { return c.S[(size_t)slot * c.N]; }
-DEV void stF(const Ctx& c, int slot, float v) { c.S[(size_t)slot * c.N] = v; }
-DEV int ldI(const Ctx& c, int slot) { return __float_as_int(c.S[(size_t)slot * c.N]); }
-DEV void stI(const Ctx& c, int slot, int v) { c.S[(size_t)slot * c.N] = __int_as_float(v); }
-DEV float mF(const Ctx& c, int off) { return __uint_as_float(c.M[off]); }
-DEV int mI(const Ctx& c, int off) { return (int)c.M[off]; }
+// per-world state access: `off` is a byte offset (chunk * 512 + word * 4, see model.h); signed so that constant
+// field offsets fold into the instruction's immediate
+DEV char* sp(Ctx c, int off) {
+    __builtin_assume(__isGlobal(c.P));
+    return c.P + off;
+}
+DEV float ldF(Ctx c, int off) { return *reinterpret_cast<const float*>(sp(c, off)); }
+DEV void stF(Ctx c, int off, float v) { *reinterpret_cast<float*>(sp(c, off)) = v; }
+DEV int ldI(Ctx c, int off) { return *reinterpret_cast<const int*>(sp(c, off)); }
+DEV void stI(Ctx c, int off, int v) { *reinterpret_cast<int*>(sp(c, off)) = v; }
+DEV float4 ld4(Ctx c, int off) { return *reinterpret_cast<const float4*>(sp(c, off)); }
+DEV void st4(Ctx c, int off, float4 v) { *reinterpret_cast<float4*>(sp(c, off)) = v; }
+DEV float2 ld2(Ctx c, int off) { return *reinterpret_cast<const float2*>(sp(c, off)); }
+DEV void st2(Ctx c, int off, float2 v) { *reinterpret_cast<float2*>(sp(c, off)) = v; }
+DEV float4 mk4(float x, float y, float z, float w) { return make_float4(x, y, z, w); }
 
-DEV int bslot(const Ctx& c, int b, int f) { return c.h->sBody + b * SB_STRIDE + f; }
-DEV int jslot(const Ctx& c, int j, int f) { return c.h->sJoint + j * SJ_STRIDE + f; }
-DEV int jwslot(const Ctx& c, int j, int f) { return c.h->sJointW + j * WJ_STRIDE + f; }
-DEV int cslot(const Ctx& c, int k, int f) { return c.h->sCont + k * SC_STRIDE + f; }
-DEV int cwslot(const Ctx& c, int k, int f) { return c.h->sContW + k * WC_STRIDE + f; }
-DEV int sslot(const Ctx& c, int f) { return c.h->sScalar + f; }
-DEV int mbody(const Ctx& c, int b, int f) { return c.h->oBody + b * MB_STRIDE + f; }
-DEV int mfix(const Ctx& c, int f, int k) { return c.h->oFix + f * MF_STRIDE + k; }
-DEV int mjoint(const Ctx& c, int j, int f) { return c.h->oJoint + j * MJ_STRIDE + f; }
-DEV int mobj(const Ctx& c, int o, int f) { return c.h->oObj + o * MO_STRIDE + f; }
+// model blob access (shared memory, warp-uniform addresses: broadcast reads)
+DEV float mF(Ctx, int off) { return __uint_as_float(g_sm[kHdrWords + off]); }
+DEV int mI(Ctx, int off) { return (int)g_sm[kHdrWords + off]; }
+DEV float4 m4(Ctx, int off) { return *reinterpret_cast<const float4*>(g_sm + kHdrWords + off); }  // off % 4 == 0
+DEV float2 m2(Ctx, int off) { return *reinterpret_cast<const float2*>(g_sm + kHdrWords + off); }  // off % 2 == 0
 
-DEV V2 ldV2(const Ctx& c, int slot) { return mk(ldF(c, slot), ldF(c, slot + 1)); }
-DEV void stV2(const Ctx& c, int slot, V2 v) { stF(c, slot, v.x); stF(c, slot + 1, v.y); }
-DEV XF ldXF(const Ctx& c, int b) {
+DEV int bslot(Ctx c, int b, int f) { return (H().cBody + b * SB_CHUNKS) * kChunkBytes + f; }
+DEV int fslot(Ctx c, int f) { return (H().cFix + f) * kChunkBytes; }
+DEV int jslot(Ctx c, int j, int f) { return (H().cJoint + j * SJ_CHUNKS) * kChunkBytes + f; }
+DEV int jwslot(Ctx c, int j, int f) { return (H().cJointW + j * WJ_CHUNKS) * kChunkBytes + f; }
+DEV int cslot(Ctx c, int k, int f) { return (H().cCont + k * SC_CHUNKS) * kChunkBytes + f; }
+DEV int cwslot(Ctx c, int k, int f) { return (H().cContW + k * WC_CHUNKS) * kChunkBytes + f; }
+DEV int sslot(Ctx c, int f) { return H().cScalar * kChunkBytes + f; }
+DEV int tslot(Ctx c, int t) { return (H().cTarget + (t >> 2)) * kChunkBytes + (t & 3) * 4; }
+DEV int mbody(Ctx c, int b, int f) { return H().oBody + b * MB_STRIDE + f; }
+DEV int mfix(Ctx c, int f, int k) { return H().oFix + f * MF_STRIDE + k; }
+DEV int mjoint(Ctx c, int j, int f) { return H().oJoint + j * MJ_STRIDE + f; }
+DEV int mobj(Ctx c, int o, int f) { return H().oObj + o * MO_STRIDE + f; }
+
+DEV V2 ldV2(Ctx c, int off) { float2 v = ld2(c, off); return mk(v.x, v.y); }  // x, y share a chunk, 8-byte aligned
+DEV void stV2(Ctx c, int off, V2 v) { st2(c, off, make_float2(v.x, v.y)); }
+DEV XF ldXF(Ctx c, int b) {
+    float4 v = ld4(c, bslot(c, b, SB_XF4));
     XF x;
-    x.p = ldV2(c, bslot(c, b, SB_PX));
-    x.q.s = ldF(c, bslot(c, b, SB_QS));
-    x.q.c = ldF(c, bslot(c, b, SB_QC));
+    x.p = mk(v.x, v.y);
+    x.q.s = v.z;
+    x.q.c = v.w;
     return x;
 }
-DEV void stXF(const Ctx& c, int b, const XF& x) {
-    stV2(c, bslot(c, b, SB_PX), x.p);
-    stF(c, bslot(c, b, SB_QS), x.q.s);
-    stF(c, bslot(c, b, SB_QC), x.q.c);
-}
-DEV V2 localCenter(const Ctx& c, int b) { return mk(mF(c, mbody(c, b, MB_LCX)), mF(c, mbody(c, b, MB_LCY))); }
-DEV bool isAwake(const Ctx& c, int b) { return (ldI(c, bslot(c, b, SB_FLAGS)) & 1) != 0; }
-DEV int bodyType(const Ctx& c, int b) { return mI(c, mbody(c, b, MB_TYPE)); }
+DEV void stXF(Ctx c, int b, const XF& x) { st4(c, bslot(c, b, SB_XF4), mk4(x.p.x, x.p.y, x.q.s, x.q.c)); }
+DEV V2 localCenter(Ctx c, int b) { float2 v = m2(c, mbody(c, b, MB_LCX)); return mk(v.x, v.y); }
+DEV bool isAwake(Ctx c, int b) { return (ldI(c, bslot(c, b, SB_FLAGS)) & 1) != 0; }
+DEV int bodyType(Ctx c, int b) { return mI(c, mbody(c, b, MB_TYPE)); }
 
 // b2Body::SetAwake
-DEV void wakeBody(const Ctx& c, int b) {
+DEV void wakeBody(Ctx c, int b) {
     int f = ldI(c, bslot(c, b, SB_FLAGS));
     if ((f & 1) == 0) {
         stI(c, bslot(c, b, SB_FLAGS), f | 1);
         stF(c, bslot(c, b, SB_SLEEP), 0.0f);
     }
 }
-DEV void sleepBody(const Ctx& c, int b) {
+DEV void sleepBody(Ctx c, int b) {
     int f = ldI(c, bslot(c, b, SB_FLAGS));
-    stI(c, bslot(c, b, SB_FLAGS), f & ~1);
+    st4(c, bslot(c, b, SB_VEL4), mk4(0.0f, 0.0f, 0.0f, __int_as_float(f & ~1)));
     stF(c, bslot(c, b, SB_SLEEP), 0.0f);
-    stF(c, bslot(c, b, SB_VX), 0.0f);
-    stF(c, bslot(c, b, SB_VY), 0.0f);
-    stF(c, bslot(c, b, SB_W), 0.0f);
-    stF(c, bslot(c, b, SB_FX), 0.0f);
-    stF(c, bslot(c, b, SB_FY), 0.0f);
-    stF(c, bslot(c, b, SB_TORQUE), 0.0f);
+    st4(c, bslot(c, b, SB_FORCE4), mk4(0.0f, 0.0f, 0.0f, 0.0f));
 }
 
 // ---- broad phase: fat AABBs, move buffer as a 64-bit mask ---------------------------------------------------
 struct Box {
     float lx, ly, ux, uy;
 };
-DEV Box ldFat(const Ctx& c, int f) {
+DEV Box ldFat(Ctx c, int f) {
+    float4 v = ld4(c, fslot(c, f));
     Box b;
-    int s = c.h->sFix + f * 4;
-    b.lx = ldF(c, s); b.ly = ldF(c, s + 1); b.ux = ldF(c, s + 2); b.uy = ldF(c, s + 3);
+    b.lx = v.x; b.ly = v.y; b.ux = v.z; b.uy = v.w;
     return b;
 }
 DEV bool boxOverlap(const Box& a, const Box& b) {
@@ -207,22 +220,24 @@ DEV bool boxOverlap(const Box& a, const Box& b) {
     if (d2x > 0.0f || d2y > 0.0f) return false;
     return true;
 }
-DEV uint64_t ldMoved(const Ctx& c) {
+DEV uint64_t ldMoved(Ctx c) {
     return (uint64_t)(uint32_t)ldI(c, sslot(c, SS_MOVED_LO)) | ((uint64_t)(uint32_t)ldI(c, sslot(c, SS_MOVED_HI)) << 32);
 }
-DEV void stMoved(const Ctx& c, uint64_t m) {
+DEV void stMoved(Ctx c, uint64_t m) {
     stI(c, sslot(c, SS_MOVED_LO), (int)(uint32_t)(m & 0xffffffffull));
     stI(c, sslot(c, SS_MOVED_HI), (int)(uint32_t)(m >> 32));
 }
 
+DEV V2 fixVertAt(Ctx c, int base, int i) { float2 v = m2(c, base + 2 * i); return mk(v.x, v.y); }
+
 // b2PolygonShape::ComputeAABB
-DEV Box fixtureAABB(const Ctx& c, int f, const XF& xf) {
+DEV Box fixtureAABB(Ctx c, int f, const XF& xf) {
     int n = mI(c, mfix(c, f, MF_COUNT));
     int vo = mfix(c, f, MF_VERTS);
-    V2 lower = mul(xf, mk(mF(c, vo), mF(c, vo + 1)));
+    V2 lower = mul(xf, fixVertAt(c, vo, 0));
     V2 upper = lower;
     for (int i = 1; i < n; ++i) {
-        V2 v = mul(xf, mk(mF(c, vo + 2 * i), mF(c, vo + 2 * i + 1)));
+        V2 v = mul(xf, fixVertAt(c, vo, i));
         lower = mk(fminT(lower.x, v.x), fminT(lower.y, v.y));
         upper = mk(fmaxT(upper.x, v.x), fmaxT(upper.y, v.y));
     }
@@ -233,7 +248,7 @@ DEV Box fixtureAABB(const Ctx& c, int f, const XF& xf) {
 }
 
 // b2Fixture::Synchronize + b2DynamicTree::MoveProxy; returns the bit to add to the move buffer
-DEV uint64_t syncFixture(const Ctx& c, int f, const XF& xf1, const XF& xf2) {
+DEV uint64_t syncFixture(Ctx c, int f, const XF& xf1, const XF& xf2) {
     Box a1 = fixtureAABB(c, f, xf1);
     Box a2 = fixtureAABB(c, f, xf2);
     Box a;
@@ -249,13 +264,12 @@ DEV uint64_t syncFixture(const Ctx& c, int f, const XF& xf1, const XF& xf2) {
     V2 d = B2G_AABB_MULTIPLIER * disp;
     if (d.x < 0.0f) b.lx += d.x; else b.ux += d.x;
     if (d.y < 0.0f) b.ly += d.y; else b.uy += d.y;
-    int s = c.h->sFix + f * 4;
-    stF(c, s, b.lx); stF(c, s + 1, b.ly); stF(c, s + 2, b.ux); stF(c, s + 3, b.uy);
+    st4(c, fslot(c, f), mk4(b.lx, b.ly, b.ux, b.uy));
     return 1ull << f;
 }
 
 // b2Body::SynchronizeFixtures / SetTransform tail: fixtures in upstream list order (newest first)
-DEV uint64_t syncBodyFixtures(const Ctx& c, int b, const XF& xf1, const XF& xf2) {
+DEV uint64_t syncBodyFixtures(Ctx c, int b, const XF& xf1, const XF& xf2) {
     int start = mI(c, mbody(c, b, MB_FIX_START));
     int cnt = mI(c, mbody(c, b, MB_FIX_COUNT));
     uint64_t moved = 0ull;
@@ -264,7 +278,7 @@ DEV uint64_t syncBodyFixtures(const Ctx& c, int b, const XF& xf1, const XF& xf2)
 }
 
 // b2Body::SetTransform (2.3.1: no FindNewContacts here)
-DEV void setTransform(const Ctx& c, int b, V2 position, float angle) {
+DEV void setTransform(Ctx c, int b, V2 position, float angle) {
     XF xf;
     xf.q = rotOf(angle);
     xf.p = position;
@@ -279,7 +293,7 @@ DEV void setTransform(const Ctx& c, int b, V2 position, float angle) {
 }
 
 // b2Body::SynchronizeTransform
-DEV void syncTransform(const Ctx& c, int b) {
+DEV void syncTransform(Ctx c, int b) {
     XF xf;
     float a = ldF(c, bslot(c, b, SB_A));
     xf.q = rotOf(a);
@@ -323,10 +337,10 @@ DEV int clipSegmentToLine(ClipV out[2], const ClipV in[2], V2 normal, float offs
     return numOut;
 }
 
-DEV V2 fixVert(const Ctx& c, int f, int i) { int o = mfix(c, f, MF_VERTS) + 2 * i; return mk(mF(c, o), mF(c, o + 1)); }
-DEV V2 fixNormal(const Ctx& c, int f, int i) { int o = mfix(c, f, MF_NORMALS) + 2 * i; return mk(mF(c, o), mF(c, o + 1)); }
+DEV V2 fixVert(Ctx c, int f, int i) { return fixVertAt(c, mfix(c, f, MF_VERTS), i); }
+DEV V2 fixNormal(Ctx c, int f, int i) { return fixVertAt(c, mfix(c, f, MF_NORMALS), i); }
 
-DEV float findMaxSeparation(const Ctx& c, int* edgeIndex, int f1, const XF& xf1, int f2, const XF& xf2) {
+DEV float findMaxSeparation(Ctx c, int* edgeIndex, int f1, const XF& xf1, int f2, const XF& xf2) {
     int count1 = mI(c, mfix(c, f1, MF_COUNT));
     int count2 = mI(c, mfix(c, f2, MF_COUNT));
     XF xf = mulT(xf2, xf1);
@@ -346,7 +360,7 @@ DEV float findMaxSeparation(const Ctx& c, int* edgeIndex, int f1, const XF& xf1,
     return maxSeparation;
 }
 
-DEVN void collidePolygons(const Ctx& c, Manifold& m, int fA, const XF& xfA, int fB, const XF& xfB) {
+DEVN void collidePolygons(Ctx c, Manifold& m, int fA, const XF& xfA, int fB, const XF& xfB) {
     m.pointCount = 0;
     const float totalRadius = B2G_POLYGON_RADIUS + B2G_POLYGON_RADIUS;
     int edgeA = 0;
@@ -427,28 +441,32 @@ DEVN void collidePolygons(const Ctx& c, Manifold& m, int fA, const XF& xfA, int 
 #define CF_FILTER 4
 #define CF_TOI 16
 
-DEV int contactCount(const Ctx& c) { return ldI(c, sslot(c, SS_NCONTACTS)); }
-DEV void contactFixtures(const Ctx& c, int k, int& fA, int& fB) {
+DEV int contactCount(Ctx c) { return ldI(c, sslot(c, SS_NCONTACTS)); }
+DEV void contactFixtures(Ctx c, int k, int& fA, int& fB) {
     int p = ldI(c, cslot(c, k, SC_FIX));
     fA = p & 0xff;
     fB = (p >> 8) & 0xff;
 }
 
 // b2Contact::Update for slot k.  Returns bit0 = now touching, bit1 = was touching.
-DEVN int updateContact(const Ctx& c, int k) {
-    int fA, fB;
-    contactFixtures(c, k, fA, fB);
+DEVN int updateContact(Ctx c, int k) {
+    const int ck = cslot(c, k, 0);
+    float4 head = ld4(c, ck + SC_HEAD4);
+    float4 idn = ld4(c, ck + SC_ID4);
+    float4 p0 = ld4(c, ck + SC_P04);
+    float4 p1 = ld4(c, ck + SC_P14);
+    int fA = __float_as_int(head.x) & 0xff, fB = (__float_as_int(head.x) >> 8) & 0xff;
     int bA = mI(c, mfix(c, fA, MF_BODY));
     int bB = mI(c, mfix(c, fB, MF_BODY));
-    int flags = ldI(c, cslot(c, k, SC_FLAGS));
+    int flags = __float_as_int(head.y);
     flags |= CF_ENABLED;
     bool wasTouching = (flags & CF_TOUCHING) != 0;
-    int oldMan = ldI(c, cslot(c, k, SC_MANIFOLD));
+    int oldMan = __float_as_int(head.z);
     int oldCount = (oldMan >> 8) & 0xff;
-    uint32_t oldId0 = (uint32_t)ldI(c, cslot(c, k, SC_ID0));
-    uint32_t oldId1 = (uint32_t)ldI(c, cslot(c, k, SC_ID1));
-    float oldN0 = ldF(c, cslot(c, k, SC_N0)), oldT0 = ldF(c, cslot(c, k, SC_T0));
-    float oldN1 = ldF(c, cslot(c, k, SC_N1)), oldT1 = ldF(c, cslot(c, k, SC_T1));
+    uint32_t oldId0 = (uint32_t)__float_as_int(idn.x);
+    uint32_t oldId1 = (uint32_t)__float_as_int(idn.y);
+    float oldN0 = p0.z, oldT0 = p0.w;
+    float oldN1 = p1.z, oldT1 = p1.w;
 
     XF xfA = ldXF(c, bA);
     XF xfB = ldXF(c, bB);
@@ -459,32 +477,32 @@ DEVN int updateContact(const Ctx& c, int k) {
     if (touching) {
         // b2CollidePolygons returns early (pointCount = 0) without touching the rest of the manifold, so the
         // other fields are only rewritten when points were produced
-        stV2(c, cslot(c, k, SC_LNX), m.localNormal);
-        stV2(c, cslot(c, k, SC_LPX), m.localPoint);
+        idn.z = m.localNormal.x;
+        idn.w = m.localNormal.y;
+        stV2(c, ck + SC_LPX, m.localPoint);
         for (int i = 0; i < m.pointCount; ++i) {
             float ni = 0.0f, ti = 0.0f;
             uint32_t id2 = m.id[i];
             if (oldCount > 0 && oldId0 == id2) { ni = oldN0; ti = oldT0; }
             else if (oldCount > 1 && oldId1 == id2) { ni = oldN1; ti = oldT1; }
-            int base = i == 0 ? SC_P0X : SC_P1X;
-            stV2(c, cslot(c, k, base), m.pt[i]);
-            stF(c, cslot(c, k, base + 2), ni);
-            stF(c, cslot(c, k, base + 3), ti);
-            stI(c, cslot(c, k, i == 0 ? SC_ID0 : SC_ID1), (int)id2);
+            st4(c, ck + (i == 0 ? SC_P04 : SC_P14), mk4(m.pt[i].x, m.pt[i].y, ni, ti));
+            if (i == 0) idn.x = __int_as_float((int)id2); else idn.y = __int_as_float((int)id2);
         }
+        st4(c, ck + SC_ID4, idn);
     }
-    stI(c, cslot(c, k, SC_MANIFOLD), (m.type & 0xff) | (m.pointCount << 8));
     if (touching != wasTouching) {
         wakeBody(c, bA);
         wakeBody(c, bB);
     }
     if (touching) flags |= CF_TOUCHING; else flags &= ~CF_TOUCHING;
-    stI(c, cslot(c, k, SC_FLAGS), flags);
+    head.y = __int_as_float(flags);
+    head.z = __int_as_float((m.type & 0xff) | (m.pointCount << 8));
+    st4(c, ck + SC_HEAD4, head);
     return (touching ? 1 : 0) | (wasTouching ? 2 : 0);
 }
 
 // b2ContactManager::Destroy + b2Contact::Destroy for slot k; later slots move down (creation order kept)
-DEVN void destroyContact(const Ctx& c, int k) {
+DEVN void destroyContact(Ctx c, int k) {
     int fA, fB;
     contactFixtures(c, k, fA, fB);
     int pc = (ldI(c, cslot(c, k, SC_MANIFOLD)) >> 8) & 0xff;
@@ -494,27 +512,27 @@ DEVN void destroyContact(const Ctx& c, int k) {
     }
     int n = contactCount(c);
     for (int i = k; i + 1 < n; ++i)
-        for (int f = 0; f < SC_STRIDE; ++f) stF(c, cslot(c, i, f), ldF(c, cslot(c, i + 1, f)));
+        for (int f = 0; f < SC_CHUNKS; ++f) st4(c, cslot(c, i, f * kChunkBytes), ld4(c, cslot(c, i + 1, f * kChunkBytes)));
     stI(c, sslot(c, SS_NCONTACTS), n - 1);
 }
 
 // b2ContactManager::AddPair (fixture a < fixture b by proxy id; filters are folded into the pair mask)
-DEV void addPair(const Ctx& c, int a, int b) {
+DEV void addPair(Ctx c, int a, int b) {
     int n = contactCount(c);
     int key = a | (b << 8);
     for (int k = 0; k < n; ++k)
         if (ldI(c, cslot(c, k, SC_FIX)) == key) return;
-    if (n >= c.h->maxc) {
+    if (n >= H().maxc) {
         stI(c, sslot(c, SS_STATUS), ldI(c, sslot(c, SS_STATUS)) | 1);
         return;
     }
-    stI(c, cslot(c, n, SC_FIX), key);
-    stI(c, cslot(c, n, SC_FLAGS), CF_ENABLED);
-    stI(c, cslot(c, n, SC_MANIFOLD), 0);
-    stI(c, cslot(c, n, SC_ID0), 0);
-    stI(c, cslot(c, n, SC_ID1), 0);
-    for (int f = SC_LNX; f < SC_TOI; ++f) stF(c, cslot(c, n, f), 0.0f);
-    stF(c, cslot(c, n, SC_TOI), 1.0f);
+    const int cn = cslot(c, n, 0);
+    st4(c, cn + SC_HEAD4, mk4(__int_as_float(key), __int_as_float(CF_ENABLED), 0.0f, 1.0f));
+    const float4 zero = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    st4(c, cn + SC_ID4, zero);
+    st4(c, cn + SC_LP4, zero);
+    st4(c, cn + SC_P04, zero);
+    st4(c, cn + SC_P14, zero);
     stI(c, sslot(c, SS_NCONTACTS), n + 1);
     wakeBody(c, mI(c, mfix(c, a, MF_BODY)));
     wakeBody(c, mI(c, mfix(c, b, MF_BODY)));
@@ -523,10 +541,10 @@ DEV void addPair(const Ctx& c, int a, int b) {
 // b2ContactManager::FindNewContacts -> b2BroadPhase::UpdatePairs.  Upstream queries the tree for every
 // buffered proxy, sorts the (min,max) pairs and drops duplicates; iterating a < b in order over pairs with
 // at least one moved member and overlapping fat boxes visits exactly that sorted, de-duplicated sequence.
-DEVN void findNewContacts(const Ctx& c) {
+DEVN void findNewContacts(Ctx c) {
     uint64_t moved = ldMoved(c);
     if (moved == 0ull) return;
-    int nf = c.h->nf;
+    int nf = H().nf;
     for (int a = 0; a < nf; ++a) {
         uint64_t cand = (uint64_t)(uint32_t)mI(c, mfix(c, a, MF_PAIR_LO)) | ((uint64_t)(uint32_t)mI(c, mfix(c, a, MF_PAIR_HI)) << 32);
         cand &= ~((2ull << a) - 1ull);
@@ -544,7 +562,7 @@ DEVN void findNewContacts(const Ctx& c) {
 }
 
 // b2ContactManager::Collide: contacts in upstream list order (newest first)
-DEVN void collide(const Ctx& c) {
+DEVN void collide(Ctx c) {
     for (int k = contactCount(c) - 1; k >= 0; --k) {
         int fA, fB;
         contactFixtures(c, k, fA, fB);

@@ -13,25 +13,24 @@ namespace b2g {
 
 // Stage header + blob into shared memory and build the per-thread context.
 #define B2G_PROLOGUE()                                                                          \
-    extern __shared__ uint32_t smem[];                                                          \
     {                                                                                           \
         const uint32_t* hsrc = reinterpret_cast<const uint32_t*>(&hdr);                         \
-        const int hw = (int)(sizeof(ModelHeader) / 4);                                          \
-        for (int i = threadIdx.x; i < hw; i += blockDim.x) smem[i] = hsrc[i];                   \
-        for (int i = threadIdx.x; i < hdr.words; i += blockDim.x) smem[hw + i] = blob[i];       \
+        const uint32_t* psrc = reinterpret_cast<const uint32_t*>(&prm);                         \
+        const int hw = (int)(sizeof(ModelHeader) / 4), pw = (int)(sizeof(StepParams) / 4);      \
+        for (int i = threadIdx.x; i < hw; i += blockDim.x) g_sm[i] = hsrc[i];                   \
+        for (int i = threadIdx.x; i < pw; i += blockDim.x) g_sm[hw + i] = psrc[i];              \
+        for (int i = threadIdx.x; i < hdr.words; i += blockDim.x) g_sm[kHdrWords + i] = blob[i]; \
     }                                                                                           \
     __syncthreads();                                                                            \
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;                       \
     if (w >= N) return;                                                                         \
     Ctx c;                                                                                      \
-    c.S = S + w;                                                                                \
-    c.N = (size_t)N;                                                                            \
-    c.h = reinterpret_cast<const ModelHeader*>(smem);                                           \
-    c.M = smem + sizeof(ModelHeader) / 4;                                                       \
-    c.dt = prm.dt;                                                                              \
-    c.inv_dt = prm.dt > 0.0f ? 1.0f / prm.dt : 0.0f;                                            \
-    c.velIters = prm.velIters;                                                                  \
-    c.posIters = prm.posIters;
+    c.P = worldBase(S, hdr.stateChunks, w);
+
+// &state[tile][0][lane] of world w
+DEV char* worldBase(float* S, int stateChunks, long long w) {
+    return reinterpret_cast<char*>(S) + (size_t)(w >> 5) * ((size_t)stateChunks * kChunkBytes) + (size_t)(w & 31) * 16;
+}
 
 __global__ void k_init(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
                        long long N, StepParams prm) {
@@ -39,23 +38,24 @@ __global__ void k_init(const __grid_constant__ ModelHeader hdr, const uint32_t* 
     initWorld(c);
 }
 
-// broadcast the state of a template world (stored [slot]) to every world: S[slot][w] = tmpl[slot]
-__global__ void k_broadcast(float* S, const float* __restrict__ tmpl, long long N, int words) {
-    long long total = (long long)words * N;
+// broadcast the state of a template world (stored [chunk]) to every world: state[tile][chunk][lane] = tmpl[chunk]
+__global__ void k_broadcast(float4* S, const float4* __restrict__ tmpl, long long tiles, int chunks) {
+    long long total = tiles * chunks * kTileWorlds;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        S[i] = tmpl[i / N];
+        S[i] = tmpl[(i >> 5) % chunks];
     }
 }
 
-__global__ void k_extract_world(const float* S, float* tmpl, long long N, int words, long long world) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) tmpl[i] = S[(size_t)i * N + world];
+__global__ void k_extract_world(const float4* S, float4* tmpl, int chunks, long long world) {
+    const float4* base = S + (size_t)(world >> 5) * ((size_t)chunks * kTileWorlds) + (world & 31);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += gridDim.x * blockDim.x) tmpl[i] = base[(size_t)i * kTileWorlds];
 }
 
 __global__ void k_set_state(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
                             long long N, StepParams prm, const float* __restrict__ q, const float* __restrict__ qd) {
     B2G_PROLOGUE();
-    const int nq = c.h->nq;
-    for (int o = 0; o < c.h->no; ++o) {
+    const int nq = H().nq;
+    for (int o = 0; o < H().no; ++o) {
         int n = mI(c, mobj(c, o, MO_NDOFS));
         int off = mI(c, mobj(c, o, MO_DOF_OFFSET));
         float lq[kMaxDofsPerObject], lqd[kMaxDofsPerObject];
@@ -70,8 +70,8 @@ __global__ void k_set_state(const __grid_constant__ ModelHeader hdr, const uint3
 __global__ void k_get_state(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
                             long long N, StepParams prm, float* __restrict__ q, float* __restrict__ qd) {
     B2G_PROLOGUE();
-    const int nq = c.h->nq;
-    for (int o = 0; o < c.h->no; ++o) {
+    const int nq = H().nq;
+    for (int o = 0; o < H().no; ++o) {
         int n = mI(c, mobj(c, o, MO_NDOFS));
         int off = mI(c, mobj(c, o, MO_DOF_OFFSET));
         float lq[kMaxDofsPerObject], lqd[kMaxDofsPerObject];
@@ -105,17 +105,17 @@ __global__ void k_get_pose(const __grid_constant__ ModelHeader hdr, const uint32
 DEV void setTarget(const Ctx& c, int object, const float* v) {
     int n = mI(c, mobj(c, object, MO_NDOFS));
     int off = mI(c, mobj(c, object, MO_DOF_OFFSET));
-    int tOff = c.h->sTarget + mI(c, mobj(c, object, MO_TARGET_OFFSET));
+    int tOff = mI(c, mobj(c, object, MO_TARGET_OFFSET));
     float factor = 1.0f;
     for (int i = 0; i < n; ++i) {
         float lo = dofLimit(c, off + i, 2), hi = dofLimit(c, off + i, 3);
         if (v[i] > hi && v[i] > 0.0f) factor = fminf(factor, hi / v[i]);
         if (v[i] < lo && v[i] < 0.0f) factor = fminf(factor, lo / v[i]);
     }
-    for (int i = 0; i < n; ++i) stF(c, tOff + i, factor < 1.0f ? factor * v[i] : v[i]);
+    for (int i = 0; i < n; ++i) stF(c, tslot(c, tOff + i), factor < 1.0f ? factor * v[i] : v[i]);
     int slot = 0;
-    for (int r = 0; r < c.h->nrobots; ++r)
-        if (mI(c, c.h->oRobotOrder + r) == object) slot = r;
+    for (int r = 0; r < H().nrobots; ++r)
+        if (mI(c, H().oRobotOrder + r) == object) slot = r;
     stI(c, sslot(c, SS_TARGET_AVAIL), ldI(c, sslot(c, SS_TARGET_AVAIL)) | (1 << slot));
 }
 
@@ -147,7 +147,7 @@ __global__ void k_step(const __grid_constant__ ModelHeader hdr, const uint32_t* 
 __global__ void k_get_bodies(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
                              long long N, StepParams prm, float* __restrict__ out) {
     B2G_PROLOGUE();
-    const int nb = c.h->nb;
+    const int nb = H().nb;
     for (int b = 0; b < nb; ++b) {
         float* o = out + ((size_t)w * nb + b) * 16;
         o[0] = ldF(c, bslot(c, b, SB_PX)); o[1] = ldF(c, bslot(c, b, SB_PY));
@@ -164,15 +164,15 @@ __global__ void k_get_bodies(const __grid_constant__ ModelHeader hdr, const uint
 __global__ void k_get_fat(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
                           long long N, StepParams prm, float* __restrict__ out) {
     B2G_PROLOGUE();
-    const int nf = c.h->nf;
+    const int nf = H().nf;
     for (int f = 0; f < nf; ++f)
-        for (int k = 0; k < 4; ++k) out[((size_t)w * nf + f) * 4 + k] = ldF(c, c.h->sFix + f * 4 + k);
+        *reinterpret_cast<float4*>(out + ((size_t)w * nf + f) * 4) = ld4(c, fslot(c, f));
 }
 
 __global__ void k_get_joints(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
                              long long N, StepParams prm, int* __restrict__ iout, float* __restrict__ fout) {
     B2G_PROLOGUE();
-    const int nj = c.h->nj;
+    const int nj = H().nj;
     for (int j = 0; j < nj; ++j) {
         int* io = iout + ((size_t)w * nj + j) * 6;
         float* fo = fout + ((size_t)w * nj + j) * 15;
@@ -206,7 +206,10 @@ __global__ void k_get_contacts(const __grid_constant__ ModelHeader hdr, const ui
         io[0] = fA; io[1] = fB; io[2] = flags & CF_TOUCHING ? 1 : 0; io[3] = flags & CF_ENABLED ? 1 : 0;
         io[4] = (man >> 8) & 0xff; io[5] = man & 0xff;
         io[6] = ldI(c, cslot(c, k, SC_ID0)); io[7] = ldI(c, cslot(c, k, SC_ID1));
-        for (int f = 0; f < 12; ++f) fo[f] = ldF(c, cslot(c, k, SC_LNX + f));
+        const int ck = cslot(c, k, 0);
+        fo[0] = ldF(c, ck + SC_LNX); fo[1] = ldF(c, ck + SC_LNY); fo[2] = ldF(c, ck + SC_LPX); fo[3] = ldF(c, ck + SC_LPY);
+        fo[4] = ldF(c, ck + SC_P0X); fo[5] = ldF(c, ck + SC_P0Y); fo[6] = ldF(c, ck + SC_N0); fo[7] = ldF(c, ck + SC_T0);
+        fo[8] = ldF(c, ck + SC_P1X); fo[9] = ldF(c, ck + SC_P1Y); fo[10] = ldF(c, ck + SC_N1); fo[11] = ldF(c, ck + SC_T1);
     }
 }
 
@@ -219,7 +222,7 @@ __global__ void k_check_collision(const __grid_constant__ ModelHeader hdr, const
     findNewContacts(c);
     collide(c);
     int n = 0;
-    float inv = c.h->invScale;
+    float inv = H().invScale;
     for (int k = contactCount(c) - 1; k >= 0; --k) {
         int flags = ldI(c, cslot(c, k, SC_FLAGS));
         if ((flags & CF_TOUCHING) == 0 || (flags & CF_ENABLED) == 0) continue;
@@ -261,9 +264,9 @@ __global__ void k_check_collision(const __grid_constant__ ModelHeader hdr, const
     counts[w] = n;
 }
 
-__global__ void k_status(const float* S, long long N, int statusSlot, int* __restrict__ out) {
+__global__ void k_status(float* S, long long N, int stateChunks, int statusOff, int* __restrict__ out) {
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w < N) out[w] = __float_as_int(S[(size_t)statusSlot * N + w]);
+    if (w < N) out[w] = *reinterpret_cast<const int*>(worldBase(S, stateChunks, w) + statusOff);
 }
 
 // gather / scatter of the world state vector and static poses for the save/restore stack
@@ -273,7 +276,7 @@ __global__ void k_status(const float* S, long long N, int statusSlot, int* __res
 static unsigned long long g_launches = 0;
 unsigned long long launchCount() { return g_launches; }
 
-static inline size_t smemBytes(const ModelHeader& h) { return sizeof(ModelHeader) + (size_t)h.words * 4; }
+static inline size_t smemBytes(const ModelHeader& h) { return (size_t)kHdrWords * 4 + (size_t)h.words * 4; }
 
 static cudaError_t prepare(const void* fn, const ModelHeader& h) {
     size_t bytes = smemBytes(h);
@@ -312,22 +315,26 @@ cudaError_t launchCheckCollision(const Launch& L, int* counts, int* iout, float*
     LAUNCH(k_check_collision, counts, iout, fout, maxPer);
 }
 cudaError_t launchBroadcast(const Launch& L, const float* tmpl) {
-    long long total = (long long)L.h.stateWords * L.N;
+    long long tiles = (L.N + kTileWorlds - 1) / kTileWorlds;
+    long long total = tiles * L.h.stateChunks * kTileWorlds;
     int threads = 256;
     long long want = (total + threads - 1) / threads;
     unsigned blocks = (unsigned)(want < 148 * 16 ? want : 148 * 16);
-    k_broadcast<<<blocks, threads, 0, L.stream>>>(L.S, tmpl, L.N, L.h.stateWords);
+    k_broadcast<<<blocks, threads, 0, L.stream>>>(reinterpret_cast<float4*>(L.S), reinterpret_cast<const float4*>(tmpl), tiles,
+                                                 L.h.stateChunks);
     ++g_launches;
     return cudaGetLastError();
 }
 cudaError_t launchExtractWorld(const Launch& L, float* tmpl, long long world) {
-    k_extract_world<<<(L.h.stateWords + 255) / 256, 256, 0, L.stream>>>(L.S, tmpl, L.N, L.h.stateWords, world);
+    k_extract_world<<<(L.h.stateChunks + 255) / 256, 256, 0, L.stream>>>(reinterpret_cast<const float4*>(L.S),
+                                                                        reinterpret_cast<float4*>(tmpl), L.h.stateChunks, world);
     ++g_launches;
     return cudaGetLastError();
 }
 cudaError_t launchStatus(const Launch& L, int* out) {
     int threads = 256;
-    k_status<<<(unsigned)((L.N + threads - 1) / threads), threads, 0, L.stream>>>(L.S, L.N, L.h.sScalar + SS_STATUS, out);
+    k_status<<<(unsigned)((L.N + threads - 1) / threads), threads, 0, L.stream>>>(L.S, L.N, L.h.stateChunks,
+                                                                                  L.h.cScalar * kChunkBytes + SS_STATUS, out);
     ++g_launches;
     return cudaGetLastError();
 }

@@ -6,11 +6,6 @@
 
 namespace b2g {
 
-struct StepParams {
-    float dt;
-    int velIters, posIters;
-};
-
 struct Launch {
     ModelHeader h;
     const uint32_t* blob;  // device copy of the model blob

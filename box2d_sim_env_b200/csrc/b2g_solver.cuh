@@ -9,56 +9,59 @@
 namespace b2g {
 
 // ---- body velocity / position access (solver works in place on the world state) ---------------------------
+// One LDG.128 / STG.128 per body: the 4th word of the chunk (awake flags / alpha0) rides along untouched.
 struct Vel {
     V2 v;
     float w;
+    float keep;
 };
-DEV Vel ldVel(const Ctx& c, int b) {
+DEV Vel ldVel(Ctx c, int b) {
+    float4 q = ld4(c, bslot(c, b, SB_VEL4));
     Vel r;
-    r.v = ldV2(c, bslot(c, b, SB_VX));
-    r.w = ldF(c, bslot(c, b, SB_W));
+    r.v = mk(q.x, q.y);
+    r.w = q.z;
+    r.keep = q.w;
     return r;
 }
-DEV void stVel(const Ctx& c, int b, const Vel& r) {
-    stV2(c, bslot(c, b, SB_VX), r.v);
-    stF(c, bslot(c, b, SB_W), r.w);
-}
+DEV void stVel(Ctx c, int b, const Vel& r) { st4(c, bslot(c, b, SB_VEL4), mk4(r.v.x, r.v.y, r.w, r.keep)); }
 struct Pos {
     V2 c;
     float a;
+    float keep;
 };
-DEV Pos ldPos(const Ctx& c, int b) {
+DEV Pos ldPos(Ctx c, int b) {
+    float4 q = ld4(c, bslot(c, b, SB_POS4));
     Pos r;
-    r.c = ldV2(c, bslot(c, b, SB_CX));
-    r.a = ldF(c, bslot(c, b, SB_A));
+    r.c = mk(q.x, q.y);
+    r.a = q.z;
+    r.keep = q.w;
     return r;
 }
-DEV void stPos(const Ctx& c, int b, const Pos& r) {
-    stV2(c, bslot(c, b, SB_CX), r.c);
-    stF(c, bslot(c, b, SB_A), r.a);
-}
-DEV float invMass(const Ctx& c, int b) { return mF(c, mbody(c, b, MB_INVMASS)); }
-DEV float invI(const Ctx& c, int b) { return mF(c, mbody(c, b, MB_INVI)); }
+DEV void stPos(Ctx c, int b, const Pos& r) { st4(c, bslot(c, b, SB_POS4), mk4(r.c.x, r.c.y, r.a, r.keep)); }
+DEV float invMass(Ctx c, int b) { return mF(c, mbody(c, b, MB_INVMASS)); }
+DEV float invI(Ctx c, int b) { return mF(c, mbody(c, b, MB_INVI)); }
 
 // =================================================================================================== joints
 // b2FrictionJoint / b2RevoluteJoint::InitVelocityConstraints
-DEVN void jointInit(const Ctx& c, int j, float dtRatio) {
-    int type = mI(c, mjoint(c, j, MJ_TYPE));
-    int bA = mI(c, mjoint(c, j, MJ_BODYA));
-    int bB = mI(c, mjoint(c, j, MJ_BODYB));
+DEVN void jointInit(Ctx c, int j, float dtRatio) {
+    const int4 jh = *reinterpret_cast<const int4*>(g_sm + kHdrWords + mjoint(c, j, MJ_TYPE));  // type bodyA bodyB flags
+    const int type = jh.x, bA = jh.y, bB = jh.z;
+    const float4 anchors = m4(c, mjoint(c, j, MJ_LAX));
+    const float4 bmA = m4(c, mbody(c, bA, MB_INVMASS));  // invMass invI lc.x lc.y
+    const float4 bmB = m4(c, mbody(c, bB, MB_INVMASS));
     float aA = ldF(c, bslot(c, bA, SB_A));
     float aB = ldF(c, bslot(c, bB, SB_A));
     Vel A = ldVel(c, bA);
     Vel B = ldVel(c, bB);
     Rot qA = rotOf(aA), qB = rotOf(aB);
-    V2 la = mk(mF(c, mjoint(c, j, MJ_LAX)), mF(c, mjoint(c, j, MJ_LAY)));
-    V2 lb = mk(mF(c, mjoint(c, j, MJ_LBX)), mF(c, mjoint(c, j, MJ_LBY)));
-    V2 rA = mul(qA, la - localCenter(c, bA));
-    V2 rB = mul(qB, lb - localCenter(c, bB));
-    float mA = invMass(c, bA), mB = invMass(c, bB);
-    float iA = invI(c, bA), iB = invI(c, bB);
-    stV2(c, jwslot(c, j, WJ_RAX), rA);
-    stV2(c, jwslot(c, j, WJ_RBX), rB);
+    V2 la = mk(anchors.x, anchors.y);
+    V2 lb = mk(anchors.z, anchors.w);
+    V2 rA = mul(qA, la - mk(bmA.z, bmA.w));
+    V2 rB = mul(qB, lb - mk(bmB.z, bmB.w));
+    float mA = bmA.x, mB = bmB.x;
+    float iA = bmA.y, iB = bmB.y;
+    const int jw = jwslot(c, j, 0), js = jslot(c, j, 0);
+    st4(c, jw + WJ_R4, mk4(rA.x, rA.y, rB.x, rB.y));
 
     if (type == 0) {
         float kxx = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
@@ -69,18 +72,14 @@ DEVN void jointInit(const Ctx& c, int j, float dtRatio) {
         float a = kxx, b = kyx, cc = kxy, d = kyy;
         float det = a * d - b * cc;
         if (det != 0.0f) det = 1.0f / det;
-        stF(c, jwslot(c, j, WJ_M0 + 0), det * d);    // ex.x
-        stF(c, jwslot(c, j, WJ_M0 + 1), -det * cc);  // ex.y
-        stF(c, jwslot(c, j, WJ_M0 + 2), -det * b);   // ey.x
-        stF(c, jwslot(c, j, WJ_M0 + 3), det * a);    // ey.y
+        st4(c, jw + WJ_M0, mk4(det * d, -det * cc, -det * b, det * a));  // ex.x ex.y ey.x ey.y
         float angularMass = iA + iB;
         if (angularMass > 0.0f) angularMass = 1.0f / angularMass;
-        stF(c, jwslot(c, j, WJ_M0 + 4), angularMass);
         // warm start
-        V2 P = mk(ldF(c, jslot(c, j, SJ_IX)) * dtRatio, ldF(c, jslot(c, j, SJ_IY)) * dtRatio);
-        float ang = ldF(c, jslot(c, j, SJ_IZ)) * dtRatio;
-        stV2(c, jslot(c, j, SJ_IX), P);
-        stF(c, jslot(c, j, SJ_IZ), ang);
+        float4 imp = ld4(c, js + SJ_IMPULSE4);
+        V2 P = mk(imp.x * dtRatio, imp.y * dtRatio);
+        float ang = imp.z * dtRatio;
+        st4(c, js + SJ_IMPULSE4, mk4(P.x, P.y, ang, angularMass));
         A.v = A.v - mA * P;
         A.w -= iA * (cross(rA, P) + ang);
         B.v = B.v + mB * P;
@@ -90,30 +89,28 @@ DEVN void jointInit(const Ctx& c, int j, float dtRatio) {
         float exx = mA + mB + rA.y * rA.y * iA + rB.y * rB.y * iB;
         float eyx = -rA.y * rA.x * iA - rB.y * rB.x * iB;
         float ezx = -rA.y * iA - rB.y * iB;
-        float exy = eyx;
         float eyy = mA + mB + rA.x * rA.x * iA + rB.x * rB.x * iB;
         float ezy = rA.x * iA + rB.x * iB;
-        float exz = ezx;
-        float eyz = ezy;
-        float ezz = iA + iB;
-        stF(c, jwslot(c, j, WJ_M0 + 0), exx); stF(c, jwslot(c, j, WJ_M0 + 1), exy); stF(c, jwslot(c, j, WJ_M0 + 2), exz);
-        stF(c, jwslot(c, j, WJ_M0 + 3), eyx); stF(c, jwslot(c, j, WJ_M0 + 4), eyy); stF(c, jwslot(c, j, WJ_M0 + 5), eyz);
-        stF(c, jwslot(c, j, WJ_M0 + 6), ezx); stF(c, jwslot(c, j, WJ_M0 + 7), ezy); stF(c, jwslot(c, j, WJ_M0 + 8), ezz);
+        // symmetric: ex.y = ey.x, ex.z = ez.x, ey.z = ez.y; ez.z = iA + iB is recomputed by the solver
+        st4(c, jw + WJ_M0, mk4(exx, eyx, eyy, 0.0f));
+        st4(c, jw + WJ_M1, mk4(ezx, ezy, 0.0f, 0.0f));
         float motorMass = iA + iB;
         if (motorMass > 0.0f) motorMass = 1.0f / motorMass;
-        stF(c, jwslot(c, j, WJ_M0 + 9), motorMass);
 
-        int flags = ldI(c, jslot(c, j, SJ_FLAGS));
+        float4 mot = ld4(c, js + SJ_MOTOR4);  // flags maxMotorTorque motorSpeed motorMass
+        int flags = __float_as_int(mot.x);
         bool enableMotor = (flags & 4) != 0;
         int limitState = flags & 3;
-        bool enableLimit = (mI(c, mjoint(c, j, MJ_FLAGS)) & 1) != 0;
-        float motorImpulse = ldF(c, jslot(c, j, SJ_MOTOR_IMPULSE));
+        bool enableLimit = (jh.w & 1) != 0;
+        float4 si = ld4(c, js + SJ_IMPULSE4);
+        float motorImpulse = si.w;
         V3 imp;
-        imp.x = ldF(c, jslot(c, j, SJ_IX)); imp.y = ldF(c, jslot(c, j, SJ_IY)); imp.z = ldF(c, jslot(c, j, SJ_IZ));
+        imp.x = si.x; imp.y = si.y; imp.z = si.z;
         if (enableMotor == false || fixedRotation) motorImpulse = 0.0f;
         if (enableLimit && fixedRotation == false) {
-            float lower = mF(c, mjoint(c, j, MJ_LOWER)), upper = mF(c, mjoint(c, j, MJ_UPPER));
-            float jointAngle = aB - aA - mF(c, mjoint(c, j, MJ_REF));
+            const float4 lim = m4(c, mjoint(c, j, MJ_REF));  // ref lower upper maxForce
+            float lower = lim.y, upper = lim.z;
+            float jointAngle = aB - aA - lim.x;
             if (absT(upper - lower) < 2.0f * B2G_ANGULAR_SLOP) {
                 limitState = 3;
             } else if (jointAngle <= lower) {
@@ -129,11 +126,12 @@ DEVN void jointInit(const Ctx& c, int j, float dtRatio) {
         } else {
             limitState = 0;
         }
-        stI(c, jslot(c, j, SJ_FLAGS), (flags & ~3) | limitState);
+        mot.x = __int_as_float((flags & ~3) | limitState);
+        mot.w = motorMass;
+        st4(c, js + SJ_MOTOR4, mot);
         imp.x *= dtRatio; imp.y *= dtRatio; imp.z *= dtRatio;
         motorImpulse *= dtRatio;
-        stF(c, jslot(c, j, SJ_IX), imp.x); stF(c, jslot(c, j, SJ_IY), imp.y); stF(c, jslot(c, j, SJ_IZ), imp.z);
-        stF(c, jslot(c, j, SJ_MOTOR_IMPULSE), motorImpulse);
+        st4(c, js + SJ_IMPULSE4, mk4(imp.x, imp.y, imp.z, motorImpulse));
         V2 P = mk(imp.x, imp.y);
         A.v = A.v - mA * P;
         A.w -= iA * (cross(rA, P) + motorImpulse + imp.z);
@@ -145,46 +143,55 @@ DEVN void jointInit(const Ctx& c, int j, float dtRatio) {
 }
 
 // b2FrictionJoint::SolveVelocityConstraints
-DEV void frictionSolveVel(const Ctx& c, int j) {
-    int bA = mI(c, mjoint(c, j, MJ_BODYA));
-    int bB = mI(c, mjoint(c, j, MJ_BODYB));
+DEV void frictionSolveVel(Ctx c, int j, int bA, int bB) {
+    const float4 bmA = m4(c, mbody(c, bA, MB_INVMASS));
+    const float4 bmB = m4(c, mbody(c, bB, MB_INVMASS));
+    const float2 maxFT = m2(c, mjoint(c, j, MJ_UPPER));  // (upper,) maxForce at +1 ; maxTorque follows in the next group
+    const float maxForce = maxFT.y;
+    const float maxTorque = mF(c, mjoint(c, j, MJ_MAXTORQUE));
     Vel A = ldVel(c, bA);
     Vel B = ldVel(c, bB);
-    float mA = invMass(c, bA), mB = invMass(c, bB);
-    float iA = invI(c, bA), iB = invI(c, bB);
-    V2 rA = ldV2(c, jwslot(c, j, WJ_RAX));
-    V2 rB = ldV2(c, jwslot(c, j, WJ_RBX));
-    float h = c.dt;
+    float mA = bmA.x, mB = bmB.x;
+    float iA = bmA.y, iB = bmB.y;
+    const int jw = jwslot(c, j, 0), js = jslot(c, j, 0);
+    const float4 r = ld4(c, jw + WJ_R4);
+    const float4 lm = ld4(c, jw + WJ_M0);
+    float4 acc4 = ld4(c, js + SJ_IMPULSE4);  // linearImpulse.xy angularImpulse angularMass
+    V2 rA = mk(r.x, r.y);
+    V2 rB = mk(r.z, r.w);
+    float h = PRM().dt;
     {
         float Cdot = B.w - A.w;
-        float impulse = -ldF(c, jwslot(c, j, WJ_M0 + 4)) * Cdot;
-        float oldImpulse = ldF(c, jslot(c, j, SJ_IZ));
-        float maxImpulse = h * mF(c, mjoint(c, j, MJ_MAXTORQUE));
+        float impulse = -acc4.w * Cdot;
+        float oldImpulse = acc4.z;
+        float maxImpulse = h * maxTorque;
         float acc = clampT(oldImpulse + impulse, -maxImpulse, maxImpulse);
-        stF(c, jslot(c, j, SJ_IZ), acc);
+        acc4.z = acc;
         impulse = acc - oldImpulse;
         A.w -= iA * impulse;
         B.w += iB * impulse;
     }
     {
         V2 Cdot = B.v + cross(B.w, rB) - A.v - cross(A.w, rA);
-        float exx = ldF(c, jwslot(c, j, WJ_M0 + 0)), exy = ldF(c, jwslot(c, j, WJ_M0 + 1));
-        float eyx = ldF(c, jwslot(c, j, WJ_M0 + 2)), eyy = ldF(c, jwslot(c, j, WJ_M0 + 3));
+        float exx = lm.x, exy = lm.y;
+        float eyx = lm.z, eyy = lm.w;
         V2 impulse = -mk(exx * Cdot.x + eyx * Cdot.y, exy * Cdot.x + eyy * Cdot.y);
-        V2 oldImpulse = ldV2(c, jslot(c, j, SJ_IX));
+        V2 oldImpulse = mk(acc4.x, acc4.y);
         V2 acc = oldImpulse + impulse;
-        float maxImpulse = h * mF(c, mjoint(c, j, MJ_MAXFORCE));
+        float maxImpulse = h * maxForce;
         if (dot(acc, acc) > maxImpulse * maxImpulse) {
             normalize(acc);
             acc = mk(acc.x * maxImpulse, acc.y * maxImpulse);
         }
-        stV2(c, jslot(c, j, SJ_IX), acc);
+        acc4.x = acc.x;
+        acc4.y = acc.y;
         impulse = acc - oldImpulse;
         A.v = A.v - mA * impulse;
         A.w -= iA * cross(rA, impulse);
         B.v = B.v + mB * impulse;
         B.w += iB * cross(rB, impulse);
     }
+    st4(c, js + SJ_IMPULSE4, acc4);
     stVel(c, bA, A);
     stVel(c, bB, B);
 }
@@ -204,43 +211,47 @@ DEV V3 solve33(const float* m, V3 b) {  // m = ex.xyz ey.xyz ez.xyz ; b2Mat33::S
 }
 
 // b2RevoluteJoint::SolveVelocityConstraints
-DEV void revoluteSolveVel(const Ctx& c, int j) {
-    int bA = mI(c, mjoint(c, j, MJ_BODYA));
-    int bB = mI(c, mjoint(c, j, MJ_BODYB));
+DEV void revoluteSolveVel(Ctx c, int j, int bA, int bB, int modelFlags) {
+    const float4 bmA = m4(c, mbody(c, bA, MB_INVMASS));
+    const float4 bmB = m4(c, mbody(c, bB, MB_INVMASS));
     Vel A = ldVel(c, bA);
     Vel B = ldVel(c, bB);
-    float mA = invMass(c, bA), mB = invMass(c, bB);
-    float iA = invI(c, bA), iB = invI(c, bB);
-    V2 rA = ldV2(c, jwslot(c, j, WJ_RAX));
-    V2 rB = ldV2(c, jwslot(c, j, WJ_RBX));
-    int flags = ldI(c, jslot(c, j, SJ_FLAGS));
+    float mA = bmA.x, mB = bmB.x;
+    float iA = bmA.y, iB = bmB.y;
+    const int jw = jwslot(c, j, 0), js = jslot(c, j, 0);
+    const float4 r = ld4(c, jw + WJ_R4);
+    const float4 k0 = ld4(c, jw + WJ_M0);     // ex.x ex.y(=ey.x) ey.y -
+    const float4 mot = ld4(c, js + SJ_MOTOR4);  // flags maxMotorTorque motorSpeed motorMass
+    float4 imp4 = ld4(c, js + SJ_IMPULSE4);     // impulse.xyz motorImpulse
+    V2 rA = mk(r.x, r.y);
+    V2 rB = mk(r.z, r.w);
+    int flags = __float_as_int(mot.x);
     bool enableMotor = (flags & 4) != 0;
     int limitState = flags & 3;
-    bool enableLimit = (mI(c, mjoint(c, j, MJ_FLAGS)) & 1) != 0;
+    bool enableLimit = (modelFlags & 1) != 0;
     bool fixedRotation = (iA + iB == 0.0f);
 
     if (enableMotor && limitState != 3 && fixedRotation == false) {
-        float Cdot = B.w - A.w - ldF(c, jslot(c, j, SJ_MOTOR_SPEED));
-        float impulse = -ldF(c, jwslot(c, j, WJ_M0 + 9)) * Cdot;
-        float oldImpulse = ldF(c, jslot(c, j, SJ_MOTOR_IMPULSE));
-        float maxImpulse = c.dt * ldF(c, jslot(c, j, SJ_MAX_MOTOR_TORQUE));
+        float Cdot = B.w - A.w - mot.z;
+        float impulse = -mot.w * Cdot;
+        float oldImpulse = imp4.w;
+        float maxImpulse = PRM().dt * mot.y;
         float acc = clampT(oldImpulse + impulse, -maxImpulse, maxImpulse);
-        stF(c, jslot(c, j, SJ_MOTOR_IMPULSE), acc);
+        imp4.w = acc;
         impulse = acc - oldImpulse;
         A.w -= iA * impulse;
         B.w += iB * impulse;
     }
-    float m[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) m[i] = ldF(c, jwslot(c, j, WJ_M0 + i));
     if (enableLimit && limitState != 0 && fixedRotation == false) {
+        const float4 k1 = ld4(c, jw + WJ_M1);  // ez.x(=ex.z) ez.y(=ey.z)
+        float m[9] = {k0.x, k0.y, k1.x, k0.y, k0.z, k1.y, k1.x, k1.y, iA + iB};
         V2 Cdot1 = B.v + cross(B.w, rB) - A.v - cross(A.w, rA);
         float Cdot2 = B.w - A.w;
         V3 Cdot = {Cdot1.x, Cdot1.y, Cdot2};
         V3 s = solve33(m, Cdot);
         V3 impulse = {-s.x, -s.y, -s.z};
         V3 acc;
-        acc.x = ldF(c, jslot(c, j, SJ_IX)); acc.y = ldF(c, jslot(c, j, SJ_IY)); acc.z = ldF(c, jslot(c, j, SJ_IZ));
+        acc.x = imp4.x; acc.y = imp4.y; acc.z = imp4.z;
         if (limitState == 3) {
             acc.x += impulse.x; acc.y += impulse.y; acc.z += impulse.z;
         } else {
@@ -259,7 +270,7 @@ DEV void revoluteSolveVel(const Ctx& c, int j) {
                 acc.x += impulse.x; acc.y += impulse.y; acc.z += impulse.z;
             }
         }
-        stF(c, jslot(c, j, SJ_IX), acc.x); stF(c, jslot(c, j, SJ_IY), acc.y); stF(c, jslot(c, j, SJ_IZ), acc.z);
+        imp4.x = acc.x; imp4.y = acc.y; imp4.z = acc.z;
         V2 P = mk(impulse.x, impulse.y);
         A.v = A.v - mA * P;
         A.w -= iA * (cross(rA, P) + impulse.z);
@@ -267,35 +278,40 @@ DEV void revoluteSolveVel(const Ctx& c, int j) {
         B.w += iB * (cross(rB, P) + impulse.z);
     } else {
         V2 Cdot = B.v + cross(B.w, rB) - A.v - cross(A.w, rA);
-        V2 impulse = solve22(m[0], m[3], m[1], m[4], -Cdot);
-        stF(c, jslot(c, j, SJ_IX), ldF(c, jslot(c, j, SJ_IX)) + impulse.x);
-        stF(c, jslot(c, j, SJ_IY), ldF(c, jslot(c, j, SJ_IY)) + impulse.y);
+        V2 impulse = solve22(k0.x, k0.y, k0.y, k0.z, -Cdot);
+        imp4.x = imp4.x + impulse.x;
+        imp4.y = imp4.y + impulse.y;
         A.v = A.v - mA * impulse;
         A.w -= iA * cross(rA, impulse);
         B.v = B.v + mB * impulse;
         B.w += iB * cross(rB, impulse);
     }
+    st4(c, js + SJ_IMPULSE4, imp4);
     stVel(c, bA, A);
     stVel(c, bB, B);
 }
 
 // b2RevoluteJoint::SolvePositionConstraints (friction joints have none and report true)
-DEV bool revoluteSolvePos(const Ctx& c, int j) {
-    int bA = mI(c, mjoint(c, j, MJ_BODYA));
-    int bB = mI(c, mjoint(c, j, MJ_BODYB));
+DEV bool revoluteSolvePos(Ctx c, int j) {
+    const int4 jh = *reinterpret_cast<const int4*>(g_sm + kHdrWords + mjoint(c, j, MJ_TYPE));
+    const int bA = jh.y, bB = jh.z;
+    const float4 bmA = m4(c, mbody(c, bA, MB_INVMASS));
+    const float4 bmB = m4(c, mbody(c, bB, MB_INVMASS));
     Pos A = ldPos(c, bA);
     Pos B = ldPos(c, bB);
-    float mA = invMass(c, bA), mB = invMass(c, bB);
-    float iA = invI(c, bA), iB = invI(c, bB);
-    int limitState = ldI(c, jslot(c, j, SJ_FLAGS)) & 3;
-    bool enableLimit = (mI(c, mjoint(c, j, MJ_FLAGS)) & 1) != 0;
+    float mA = bmA.x, mB = bmB.x;
+    float iA = bmA.y, iB = bmB.y;
+    const float4 mot = ld4(c, jslot(c, j, SJ_MOTOR4));
+    int limitState = __float_as_int(mot.x) & 3;
+    bool enableLimit = (jh.w & 1) != 0;
     float angularError = 0.0f;
     float positionError = 0.0f;
     bool fixedRotation = (iA + iB == 0.0f);
     if (enableLimit && limitState != 0 && fixedRotation == false) {
-        float motorMass = ldF(c, jwslot(c, j, WJ_M0 + 9));
-        float lower = mF(c, mjoint(c, j, MJ_LOWER)), upper = mF(c, mjoint(c, j, MJ_UPPER));
-        float angle = B.a - A.a - mF(c, mjoint(c, j, MJ_REF));
+        float motorMass = mot.w;
+        const float4 lim = m4(c, mjoint(c, j, MJ_REF));
+        float lower = lim.y, upper = lim.z;
+        float angle = B.a - A.a - lim.x;
         float limitImpulse = 0.0f;
         if (limitState == 3) {
             float C = clampT(angle - lower, -B2G_MAX_ANGULAR_CORRECTION, B2G_MAX_ANGULAR_CORRECTION);
@@ -317,10 +333,11 @@ DEV bool revoluteSolvePos(const Ctx& c, int j) {
     }
     {
         Rot qA = rotOf(A.a), qB = rotOf(B.a);
-        V2 la = mk(mF(c, mjoint(c, j, MJ_LAX)), mF(c, mjoint(c, j, MJ_LAY)));
-        V2 lb = mk(mF(c, mjoint(c, j, MJ_LBX)), mF(c, mjoint(c, j, MJ_LBY)));
-        V2 rA = mul(qA, la - localCenter(c, bA));
-        V2 rB = mul(qB, lb - localCenter(c, bB));
+        const float4 anchors = m4(c, mjoint(c, j, MJ_LAX));
+        V2 la = mk(anchors.x, anchors.y);
+        V2 lb = mk(anchors.z, anchors.w);
+        V2 rA = mul(qA, la - mk(bmA.z, bmA.w));
+        V2 rB = mul(qB, lb - mk(bmB.z, bmB.w));
         V2 C = B.c + rB - A.c - rA;
         positionError = length(C);
         float kxx = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
@@ -339,36 +356,43 @@ DEV bool revoluteSolvePos(const Ctx& c, int j) {
 }
 
 // ================================================================================================= contacts
-DEV void contactBodies(const Ctx& c, int k, int& bA, int& bB, int& fA, int& fB) {
+DEV void contactBodies(Ctx c, int k, int& bA, int& bB, int& fA, int& fB) {
     contactFixtures(c, k, fA, fB);
     bA = mI(c, mfix(c, fA, MF_BODY));
     bB = mI(c, mfix(c, fB, MF_BODY));
 }
 
 // b2ContactSolver constructor (impulse hand-over) + InitializeVelocityConstraints for slot k
-DEVN void contactInit(const Ctx& c, int k, float dtRatio, bool warmStarting) {
-    int bA, bB, fA, fB;
-    contactBodies(c, k, bA, bB, fA, fB);
-    int man = ldI(c, cslot(c, k, SC_MANIFOLD));
+DEVN void contactInit(Ctx c, int k, float dtRatio, bool warmStarting) {
+    const int ck = cslot(c, k, 0), cw = cwslot(c, k, 0);
+    const float4 head = ld4(c, ck + SC_HEAD4);
+    const float4 idn = ld4(c, ck + SC_ID4);
+    const int fA = __float_as_int(head.x) & 0xff, fB = (__float_as_int(head.x) >> 8) & 0xff;
+    const float4 fmA = m4(c, mfix(c, fA, MF_BODY));  // body count friction restitution
+    const float4 fmB = m4(c, mfix(c, fB, MF_BODY));
+    const int bA = __float_as_int(fmA.x), bB = __float_as_int(fmB.x);
+    int man = __float_as_int(head.z);
     int type = man & 0xff;
     int pointCount = (man >> 8) & 0xff;
-    float mA = invMass(c, bA), mB = invMass(c, bB);
-    float iA = invI(c, bA), iB = invI(c, bB);
+    const float4 bmA = m4(c, mbody(c, bA, MB_INVMASS));
+    const float4 bmB = m4(c, mbody(c, bB, MB_INVMASS));
+    float mA = bmA.x, mB = bmB.x;
+    float iA = bmA.y, iB = bmB.y;
     Pos PA = ldPos(c, bA), PB = ldPos(c, bB);
     Vel A = ldVel(c, bA), B = ldVel(c, bB);
     XF xfA, xfB;
     xfA.q = rotOf(PA.a);
     xfB.q = rotOf(PB.a);
-    xfA.p = PA.c - mul(xfA.q, localCenter(c, bA));
-    xfB.p = PB.c - mul(xfB.q, localCenter(c, bB));
-    float restitution;
-    {
-        float rA_ = mF(c, mfix(c, fA, MF_RESTITUTION)), rB_ = mF(c, mfix(c, fB, MF_RESTITUTION));
-        restitution = rA_ > rB_ ? rA_ : rB_;
-    }
+    xfA.p = PA.c - mul(xfA.q, mk(bmA.z, bmA.w));
+    xfB.p = PB.c - mul(xfB.q, mk(bmB.z, bmB.w));
+    float restitution = fmA.w > fmB.w ? fmA.w : fmB.w;        // b2MixRestitution
+    float friction = sqrtf(fmA.z * fmB.z);                     // b2MixFriction
     // b2WorldManifold::Initialize
-    V2 localNormal = ldV2(c, cslot(c, k, SC_LNX));
-    V2 localPoint = ldV2(c, cslot(c, k, SC_LPX));
+    V2 localNormal = mk(idn.z, idn.w);
+    V2 localPoint = ldV2(c, ck + SC_LPX);
+    float4 pts[2];
+    pts[0] = ld4(c, ck + SC_P04);
+    pts[1] = ld4(c, ck + SC_P14);
     V2 normal;
     V2 wp[2];
     const float radius = B2G_POLYGON_RADIUS;
@@ -376,7 +400,7 @@ DEVN void contactInit(const Ctx& c, int k, float dtRatio, bool warmStarting) {
         normal = mul(xfA.q, localNormal);
         V2 planePoint = mul(xfA, localPoint);
         for (int i = 0; i < pointCount; ++i) {
-            V2 clipPoint = mul(xfB, ldV2(c, cslot(c, k, i == 0 ? SC_P0X : SC_P1X)));
+            V2 clipPoint = mul(xfB, mk(pts[i].x, pts[i].y));
             V2 cA = clipPoint + (radius - dot(clipPoint - planePoint, normal)) * normal;
             V2 cB = clipPoint - radius * normal;
             wp[i] = 0.5f * (cA + cB);
@@ -385,17 +409,18 @@ DEVN void contactInit(const Ctx& c, int k, float dtRatio, bool warmStarting) {
         normal = mul(xfB.q, localNormal);
         V2 planePoint = mul(xfB, localPoint);
         for (int i = 0; i < pointCount; ++i) {
-            V2 clipPoint = mul(xfA, ldV2(c, cslot(c, k, i == 0 ? SC_P0X : SC_P1X)));
+            V2 clipPoint = mul(xfA, mk(pts[i].x, pts[i].y));
             V2 cB = clipPoint + (radius - dot(clipPoint - planePoint, normal)) * normal;
             V2 cA = clipPoint - radius * normal;
             wp[i] = 0.5f * (cA + cB);
         }
         normal = -normal;
     }
-    stV2(c, cwslot(c, k, WC_NX), normal);
     V2 rAs[2], rBs[2];
+    float nMass[2] = {0.0f, 0.0f}, tMass[2] = {0.0f, 0.0f}, bias[2] = {0.0f, 0.0f};
+    float nImp[2] = {0.0f, 0.0f}, tImp[2] = {0.0f, 0.0f};
+    rAs[0] = rAs[1] = rBs[0] = rBs[1] = mk(0.0f, 0.0f);
     for (int jn = 0; jn < pointCount; ++jn) {
-        int base = WC_PT0 + jn * WC_PT_STRIDE;
         V2 rA = wp[jn] - PA.c;
         V2 rB = wp[jn] - PB.c;
         rAs[jn] = rA;
@@ -403,71 +428,69 @@ DEVN void contactInit(const Ctx& c, int k, float dtRatio, bool warmStarting) {
         float rnA = cross(rA, normal);
         float rnB = cross(rB, normal);
         float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
-        float normalMass = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
+        nMass[jn] = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
         V2 tangent = cross(normal, 1.0f);
         float rtA = cross(rA, tangent);
         float rtB = cross(rB, tangent);
         float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
-        float tangentMass = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
-        float velocityBias = 0.0f;
+        tMass[jn] = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
         float vRel = dot(normal, B.v + cross(B.w, rB) - A.v - cross(A.w, rA));
-        if (vRel < -B2G_VELOCITY_THRESHOLD) velocityBias = -restitution * vRel;
-        float ni = 0.0f, ti = 0.0f;
+        if (vRel < -B2G_VELOCITY_THRESHOLD) bias[jn] = -restitution * vRel;
         if (warmStarting) {
-            ni = dtRatio * ldF(c, cslot(c, k, jn == 0 ? SC_N0 : SC_N1));
-            ti = dtRatio * ldF(c, cslot(c, k, jn == 0 ? SC_T0 : SC_T1));
+            nImp[jn] = dtRatio * pts[jn].z;
+            tImp[jn] = dtRatio * pts[jn].w;
         }
-        stV2(c, cwslot(c, k, base + 0), rA);
-        stV2(c, cwslot(c, k, base + 2), rB);
-        stF(c, cwslot(c, k, base + 4), normalMass);
-        stF(c, cwslot(c, k, base + 5), tangentMass);
-        stF(c, cwslot(c, k, base + 6), velocityBias);
-        stF(c, cwslot(c, k, base + 7), ni);
-        stF(c, cwslot(c, k, base + 8), ti);
     }
     int vcCount = pointCount;
+    float k11 = 0.0f, k12 = 0.0f, k22 = 0.0f, n11 = 0.0f, n12 = 0.0f, n22 = 0.0f;
     if (pointCount == 2) {
         float rn1A = cross(rAs[0], normal);
         float rn1B = cross(rBs[0], normal);
         float rn2A = cross(rAs[1], normal);
         float rn2B = cross(rBs[1], normal);
-        float k11 = mA + mB + iA * rn1A * rn1A + iB * rn1B * rn1B;
-        float k22 = mA + mB + iA * rn2A * rn2A + iB * rn2B * rn2B;
-        float k12 = mA + mB + iA * rn1A * rn2A + iB * rn1B * rn2B;
+        k11 = mA + mB + iA * rn1A * rn1A + iB * rn1B * rn1B;
+        k22 = mA + mB + iA * rn2A * rn2A + iB * rn2B * rn2B;
+        k12 = mA + mB + iA * rn1A * rn2A + iB * rn1B * rn2B;
         const float k_maxConditionNumber = 1000.0f;
         if (k11 * k11 < k_maxConditionNumber * (k11 * k22 - k12 * k12)) {
-            stF(c, cwslot(c, k, WC_K + 0), k11);
-            stF(c, cwslot(c, k, WC_K + 1), k12);
-            stF(c, cwslot(c, k, WC_K + 2), k22);
             // K = [ex=(k11,k12), ey=(k12,k22)]; GetInverse
             float a = k11, b = k12, cc = k12, d = k22;
             float det = a * d - b * cc;
             if (det != 0.0f) det = 1.0f / det;
-            stF(c, cwslot(c, k, WC_NM + 0), det * d);    // ex.x
-            stF(c, cwslot(c, k, WC_NM + 1), -det * cc);  // ex.y ( == ey.x )
-            stF(c, cwslot(c, k, WC_NM + 2), det * a);    // ey.y
+            n11 = det * d;     // ex.x
+            n12 = -det * cc;   // ex.y ( == ey.x )
+            n22 = det * a;     // ey.y
         } else {
             vcCount = 1;
         }
     }
-    stI(c, cwslot(c, k, WC_COUNT), vcCount);
+    st4(c, cw + WC_N4, mk4(normal.x, normal.y, __int_as_float(vcCount), friction));
+    st4(c, cw + WC_R0, mk4(rAs[0].x, rAs[0].y, rBs[0].x, rBs[0].y));
+    st4(c, cw + WC_R1, mk4(rAs[1].x, rAs[1].y, rBs[1].x, rBs[1].y));
+    st4(c, cw + WC_MASS, mk4(nMass[0], tMass[0], nMass[1], tMass[1]));
+    st4(c, cw + WC_BK4, mk4(bias[0], bias[1], k11, k12));
+    st4(c, cw + WC_KN4, mk4(k22, n11, n12, n22));
+    st4(c, cw + WC_IMP, mk4(nImp[0], tImp[0], nImp[1], tImp[1]));
 }
 
 // b2ContactSolver::WarmStart for slot k
-DEV void contactWarmStart(const Ctx& c, int k) {
+DEV void contactWarmStart(Ctx c, int k) {
     int bA, bB, fA, fB;
     contactBodies(c, k, bA, bB, fA, fB);
     float mA = invMass(c, bA), mB = invMass(c, bB);
     float iA = invI(c, bA), iB = invI(c, bB);
     Vel A = ldVel(c, bA), B = ldVel(c, bB);
-    V2 normal = ldV2(c, cwslot(c, k, WC_NX));
+    const int cw = cwslot(c, k, 0);
+    const float4 n4 = ld4(c, cw + WC_N4);
+    const float4 imp = ld4(c, cw + WC_IMP);
+    V2 normal = mk(n4.x, n4.y);
     V2 tangent = cross(normal, 1.0f);
-    int pointCount = ldI(c, cwslot(c, k, WC_COUNT));
+    int pointCount = __float_as_int(n4.z);
     for (int jn = 0; jn < pointCount; ++jn) {
-        int base = WC_PT0 + jn * WC_PT_STRIDE;
-        V2 rA = ldV2(c, cwslot(c, k, base + 0));
-        V2 rB = ldV2(c, cwslot(c, k, base + 2));
-        V2 P = ldF(c, cwslot(c, k, base + 7)) * normal + ldF(c, cwslot(c, k, base + 8)) * tangent;
+        const float4 r = ld4(c, cw + (jn == 0 ? WC_R0 : WC_R1));
+        V2 rA = mk(r.x, r.y);
+        V2 rB = mk(r.z, r.w);
+        V2 P = (jn == 0 ? imp.x : imp.z) * normal + (jn == 0 ? imp.y : imp.w) * tangent;
         A.w -= iA * cross(rA, P);
         A.v = A.v - mA * P;
         B.w += iB * cross(rB, P);
@@ -478,29 +501,36 @@ DEV void contactWarmStart(const Ctx& c, int k) {
 }
 
 // b2ContactSolver::SolveVelocityConstraints for slot k
-DEVN void contactSolveVel(const Ctx& c, int k) {
+DEVN void contactSolveVel(Ctx c, int k) {
     int bA, bB, fA, fB;
     contactBodies(c, k, bA, bB, fA, fB);
     float mA = invMass(c, bA), mB = invMass(c, bB);
     float iA = invI(c, bA), iB = invI(c, bB);
     Vel A = ldVel(c, bA), B = ldVel(c, bB);
-    V2 normal = ldV2(c, cwslot(c, k, WC_NX));
+    const int cw = cwslot(c, k, 0);
+    const float4 n4 = ld4(c, cw + WC_N4);
+    const float4 r0 = ld4(c, cw + WC_R0);
+    const float4 mass = ld4(c, cw + WC_MASS);
+    const float4 bk = ld4(c, cw + WC_BK4);
+    float4 imp = ld4(c, cw + WC_IMP);  // n0 t0 n1 t1
+    V2 normal = mk(n4.x, n4.y);
     V2 tangent = cross(normal, 1.0f);
-    float friction = sqrtf(mF(c, mfix(c, fA, MF_FRICTION)) * mF(c, mfix(c, fB, MF_FRICTION)));
-    int pointCount = ldI(c, cwslot(c, k, WC_COUNT));
+    float friction = n4.w;
+    int pointCount = __float_as_int(n4.z);
+    float4 r1 = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (pointCount == 2) r1 = ld4(c, cw + WC_R1);
 
     for (int jn = 0; jn < pointCount; ++jn) {
-        int base = WC_PT0 + jn * WC_PT_STRIDE;
-        V2 rA = ldV2(c, cwslot(c, k, base + 0));
-        V2 rB = ldV2(c, cwslot(c, k, base + 2));
+        V2 rA = jn == 0 ? mk(r0.x, r0.y) : mk(r1.x, r1.y);
+        V2 rB = jn == 0 ? mk(r0.z, r0.w) : mk(r1.z, r1.w);
         V2 dv = B.v + cross(B.w, rB) - A.v - cross(A.w, rA);
         float vt = dot(dv, tangent) - 0.0f;
-        float lambda = ldF(c, cwslot(c, k, base + 5)) * (-vt);
-        float maxFriction = friction * ldF(c, cwslot(c, k, base + 7));
-        float oldT = ldF(c, cwslot(c, k, base + 8));
+        float lambda = (jn == 0 ? mass.y : mass.w) * (-vt);
+        float maxFriction = friction * (jn == 0 ? imp.x : imp.z);
+        float oldT = jn == 0 ? imp.y : imp.w;
         float newImpulse = clampT(oldT + lambda, -maxFriction, maxFriction);
         lambda = newImpulse - oldT;
-        stF(c, cwslot(c, k, base + 8), newImpulse);
+        if (jn == 0) imp.y = newImpulse; else imp.w = newImpulse;
         V2 P = lambda * tangent;
         A.v = A.v - mA * P;
         A.w -= iA * cross(rA, P);
@@ -508,35 +538,34 @@ DEVN void contactSolveVel(const Ctx& c, int k) {
         B.w += iB * cross(rB, P);
     }
     if (pointCount == 1) {
-        int base = WC_PT0;
-        V2 rA = ldV2(c, cwslot(c, k, base + 0));
-        V2 rB = ldV2(c, cwslot(c, k, base + 2));
+        V2 rA = mk(r0.x, r0.y);
+        V2 rB = mk(r0.z, r0.w);
         V2 dv = B.v + cross(B.w, rB) - A.v - cross(A.w, rA);
         float vn = dot(dv, normal);
-        float lambda = -ldF(c, cwslot(c, k, base + 4)) * (vn - ldF(c, cwslot(c, k, base + 6)));
-        float oldN = ldF(c, cwslot(c, k, base + 7));
+        float lambda = -mass.x * (vn - bk.x);
+        float oldN = imp.x;
         float newImpulse = fmaxT(oldN + lambda, 0.0f);
         lambda = newImpulse - oldN;
-        stF(c, cwslot(c, k, base + 7), newImpulse);
+        imp.x = newImpulse;
         V2 P = lambda * normal;
         A.v = A.v - mA * P;
         A.w -= iA * cross(rA, P);
         B.v = B.v + mB * P;
         B.w += iB * cross(rB, P);
     } else if (pointCount == 2) {
-        int b1 = WC_PT0, b2 = WC_PT0 + WC_PT_STRIDE;
-        V2 rA1 = ldV2(c, cwslot(c, k, b1 + 0)), rB1 = ldV2(c, cwslot(c, k, b1 + 2));
-        V2 rA2 = ldV2(c, cwslot(c, k, b2 + 0)), rB2 = ldV2(c, cwslot(c, k, b2 + 2));
-        V2 a = mk(ldF(c, cwslot(c, k, b1 + 7)), ldF(c, cwslot(c, k, b2 + 7)));
+        const float4 kn = ld4(c, cw + WC_KN4);
+        V2 rA1 = mk(r0.x, r0.y), rB1 = mk(r0.z, r0.w);
+        V2 rA2 = mk(r1.x, r1.y), rB2 = mk(r1.z, r1.w);
+        V2 a = mk(imp.x, imp.z);
         V2 dv1 = B.v + cross(B.w, rB1) - A.v - cross(A.w, rA1);
         V2 dv2 = B.v + cross(B.w, rB2) - A.v - cross(A.w, rA2);
         float vn1 = dot(dv1, normal);
         float vn2 = dot(dv2, normal);
         V2 b;
-        b.x = vn1 - ldF(c, cwslot(c, k, b1 + 6));
-        b.y = vn2 - ldF(c, cwslot(c, k, b2 + 6));
-        float k11 = ldF(c, cwslot(c, k, WC_K + 0)), k12 = ldF(c, cwslot(c, k, WC_K + 1)), k22 = ldF(c, cwslot(c, k, WC_K + 2));
-        float n11 = ldF(c, cwslot(c, k, WC_NM + 0)), n12 = ldF(c, cwslot(c, k, WC_NM + 1)), n22 = ldF(c, cwslot(c, k, WC_NM + 2));
+        b.x = vn1 - bk.x;
+        b.y = vn2 - bk.y;
+        float k11 = bk.z, k12 = bk.w, k22 = kn.x;
+        float n11 = kn.y, n12 = kn.z, n22 = kn.w;
         b = b - mk(k11 * a.x + k12 * a.y, k12 * a.x + k22 * a.y);
         V2 x;
         bool solved = false;
@@ -544,14 +573,14 @@ DEVN void contactSolveVel(const Ctx& c, int k) {
         x = -mk(n11 * b.x + n12 * b.y, n12 * b.x + n22 * b.y);
         if (x.x >= 0.0f && x.y >= 0.0f) solved = true;
         if (!solved) {  // case 2
-            x.x = -ldF(c, cwslot(c, k, b1 + 4)) * b.x;
+            x.x = -mass.x * b.x;
             x.y = 0.0f;
             vn2 = k12 * x.x + b.y;
             if (x.x >= 0.0f && vn2 >= 0.0f) solved = true;
         }
         if (!solved) {  // case 3
             x.x = 0.0f;
-            x.y = -ldF(c, cwslot(c, k, b2 + 4)) * b.y;
+            x.y = -mass.z * b.y;
             vn1 = k12 * x.y + b.x;
             if (x.y >= 0.0f && vn1 >= 0.0f) solved = true;
         }
@@ -570,43 +599,48 @@ DEVN void contactSolveVel(const Ctx& c, int k) {
             A.w -= iA * (cross(rA1, P1) + cross(rA2, P2));
             B.v = B.v + mB * (P1 + P2);
             B.w += iB * (cross(rB1, P1) + cross(rB2, P2));
-            stF(c, cwslot(c, k, b1 + 7), x.x);
-            stF(c, cwslot(c, k, b2 + 7), x.y);
+            imp.x = x.x;
+            imp.z = x.y;
         }
     }
+    st4(c, cw + WC_IMP, imp);
     stVel(c, bA, A);
     stVel(c, bB, B);
 }
 
 // b2ContactSolver::StoreImpulses for slot k
-DEV void contactStoreImpulses(const Ctx& c, int k) {
-    int n = ldI(c, cwslot(c, k, WC_COUNT));
-    for (int jn = 0; jn < n; ++jn) {
-        int base = WC_PT0 + jn * WC_PT_STRIDE;
-        stF(c, cslot(c, k, jn == 0 ? SC_N0 : SC_N1), ldF(c, cwslot(c, k, base + 7)));
-        stF(c, cslot(c, k, jn == 0 ? SC_T0 : SC_T1), ldF(c, cwslot(c, k, base + 8)));
-    }
+DEV void contactStoreImpulses(Ctx c, int k) {
+    const int cw = cwslot(c, k, 0);
+    int n = ldI(c, cw + WC_COUNT);
+    const float4 imp = ld4(c, cw + WC_IMP);
+    if (n > 0) stV2(c, cslot(c, k, SC_N0), mk(imp.x, imp.y));
+    if (n > 1) stV2(c, cslot(c, k, SC_N1), mk(imp.z, imp.w));
 }
 
 // b2ContactSolver::SolvePositionConstraints / SolveTOIPositionConstraints for slot k.
 // toiA/toiB < 0 selects the regular solver.  Returns the minimum separation seen.
-DEVN float contactSolvePos(const Ctx& c, int k, int toiA, int toiB, float minSeparation) {
-    int bA, bB, fA, fB;
-    contactBodies(c, k, bA, bB, fA, fB);
-    int man = ldI(c, cslot(c, k, SC_MANIFOLD));
+DEVN float contactSolvePos(Ctx c, int k, int toiA, int toiB, float minSeparation) {
+    const int ck = cslot(c, k, 0);
+    const float4 head = ld4(c, ck + SC_HEAD4);
+    const float4 idn = ld4(c, ck + SC_ID4);
+    const int fA = __float_as_int(head.x) & 0xff, fB = (__float_as_int(head.x) >> 8) & 0xff;
+    const int bA = mI(c, mfix(c, fA, MF_BODY)), bB = mI(c, mfix(c, fB, MF_BODY));
+    int man = __float_as_int(head.z);
     int type = man & 0xff;
     int pointCount = (man >> 8) & 0xff;
     bool toi = toiA >= 0;
-    float mA = invMass(c, bA), iA = invI(c, bA);
-    float mB = invMass(c, bB), iB = invI(c, bB);
+    const float4 bmA = m4(c, mbody(c, bA, MB_INVMASS));
+    const float4 bmB = m4(c, mbody(c, bB, MB_INVMASS));
+    float mA = bmA.x, iA = bmA.y;
+    float mB = bmB.x, iB = bmB.y;
     if (toi) {
         if (!(bA == toiA || bA == toiB)) { mA = 0.0f; iA = 0.0f; }
         if (!(bB == toiA || bB == toiB)) { mB = 0.0f; iB = 0.0f; }
     }
-    V2 lcA = localCenter(c, bA), lcB = localCenter(c, bB);
+    V2 lcA = mk(bmA.z, bmA.w), lcB = mk(bmB.z, bmB.w);
     Pos A = ldPos(c, bA), B = ldPos(c, bB);
-    V2 localNormal = ldV2(c, cslot(c, k, SC_LNX));
-    V2 localPoint = ldV2(c, cslot(c, k, SC_LPX));
+    V2 localNormal = mk(idn.z, idn.w);
+    V2 localPoint = ldV2(c, ck + SC_LPX);
     const float radius = B2G_POLYGON_RADIUS;
     for (int jn = 0; jn < pointCount; ++jn) {
         XF xfA, xfB;
@@ -614,7 +648,7 @@ DEVN float contactSolvePos(const Ctx& c, int k, int toiA, int toiB, float minSep
         xfB.q = rotOf(B.a);
         xfA.p = A.c - mul(xfA.q, lcA);
         xfB.p = B.c - mul(xfB.q, lcB);
-        V2 lp = ldV2(c, cslot(c, k, jn == 0 ? SC_P0X : SC_P1X));
+        V2 lp = ldV2(c, ck + (jn == 0 ? SC_P0X : SC_P1X));
         V2 normal, point;
         float separation;
         if (type == 1) {
@@ -659,7 +693,7 @@ struct Island {
 };
 
 // integrate positions with the translation / rotation caps (b2Island::Solve step 6, also SolveTOI)
-DEV void integratePosition(const Ctx& c, int b, float h) {
+DEV void integratePosition(Ctx c, int b, float h) {
     Pos P = ldPos(c, b);
     Vel V = ldVel(c, b);
     V2 translation = h * V.v;
@@ -679,8 +713,8 @@ DEV void integratePosition(const Ctx& c, int b, float h) {
 }
 
 // b2Island::Solve
-DEVN void islandSolve(const Ctx& c, const Island& isl, float dtRatio, bool allowSleep) {
-    float h = c.dt;
+DEVN void islandSolve(Ctx c, const Island& isl, float dtRatio, bool allowSleep) {
+    float h = PRM().dt;
     for (int i = 0; i < isl.nb; ++i) {
         int b = isl.bodies[i];
         Pos P = ldPos(c, b);
@@ -705,11 +739,13 @@ DEVN void islandSolve(const Ctx& c, const Island& isl, float dtRatio, bool allow
     for (int i = 0; i < isl.nc; ++i) contactWarmStart(c, isl.contacts[i]);
     for (int i = 0; i < isl.nj; ++i) jointInit(c, isl.joints[i], dtRatio);
 
-    for (int it = 0; it < c.velIters; ++it) {
+    const int velIters = PRM().velIters, posIters = PRM().posIters;
+    for (int it = 0; it < velIters; ++it) {
         for (int i = 0; i < isl.nj; ++i) {
             int j = isl.joints[i];
-            if (mI(c, mjoint(c, j, MJ_TYPE)) == 0) frictionSolveVel(c, j);
-            else revoluteSolveVel(c, j);
+            const int4 jh = *reinterpret_cast<const int4*>(g_sm + kHdrWords + mjoint(c, j, MJ_TYPE));  // type bodyA bodyB flags
+            if (jh.x == 0) frictionSolveVel(c, j, jh.y, jh.z);
+            else revoluteSolveVel(c, j, jh.y, jh.z, jh.w);
         }
         for (int i = 0; i < isl.nc; ++i) contactSolveVel(c, isl.contacts[i]);
     }
@@ -718,7 +754,7 @@ DEVN void islandSolve(const Ctx& c, const Island& isl, float dtRatio, bool allow
     for (int i = 0; i < isl.nb; ++i) integratePosition(c, isl.bodies[i], h);
 
     bool positionSolved = false;
-    for (int it = 0; it < c.posIters; ++it) {
+    for (int it = 0; it < posIters; ++it) {
         float minSeparation = 0.0f;
         for (int i = 0; i < isl.nc; ++i) minSeparation = contactSolvePos(c, isl.contacts[i], -1, -1, minSeparation);
         bool contactsOkay = minSeparation >= -3.0f * B2G_LINEAR_SLOP;
@@ -760,8 +796,8 @@ DEVN void islandSolve(const Ctx& c, const Island& isl, float dtRatio, bool allow
 }
 
 // b2World::Solve: islands by DFS in upstream order, then SynchronizeFixtures + FindNewContacts
-DEVN void solveIslands(const Ctx& c, float dtRatio, bool allowSleep) {
-    const int nb = c.h->nb;
+DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
+    const int nb = H().nb;
     uint64_t bodyFlag = 0ull;
     uint64_t jointFlag[2] = {0ull, 0ull};
     uint64_t contactFlag[2] = {0ull, 0ull};
@@ -798,7 +834,7 @@ DEVN void solveIslands(const Ctx& c, float dtRatio, bool allowSleep) {
                 bodyFlag |= 1ull << other;
             }
             // joint edges of b, newest first
-            int js = c.h->oJEdge + mI(c, mbody(c, b, MB_JE_START));
+            int js = H().oJEdge + mI(c, mbody(c, b, MB_JE_START));
             int jc = mI(c, mbody(c, b, MB_JE_COUNT));
             for (int e = 0; e < jc; ++e) {
                 int packed = mI(c, js + e);

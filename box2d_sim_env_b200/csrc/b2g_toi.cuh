@@ -12,22 +12,21 @@ struct Sweep {
     float a0, a, alpha0;
 };
 
-DEV Sweep ldSweep(const Ctx& c, int b) {
+DEV Sweep ldSweep(Ctx c, int b) {
     Sweep s;
     s.lc = localCenter(c, b);
-    s.c0 = ldV2(c, bslot(c, b, SB_C0X));
-    s.c = ldV2(c, bslot(c, b, SB_CX));
-    s.a0 = ldF(c, bslot(c, b, SB_A0));
-    s.a = ldF(c, bslot(c, b, SB_A));
-    s.alpha0 = ldF(c, bslot(c, b, SB_ALPHA0));
+    float4 p = ld4(c, bslot(c, b, SB_POS4)), p0 = ld4(c, bslot(c, b, SB_POS04));
+    s.c0 = mk(p0.x, p0.y);
+    s.c = mk(p.x, p.y);
+    s.a0 = p0.z;
+    s.a = p.z;
+    s.alpha0 = p.w;
     return s;
 }
-DEV void stSweep(const Ctx& c, int b, const Sweep& s) {
+DEV void stSweep(Ctx c, int b, const Sweep& s) {
+    st4(c, bslot(c, b, SB_POS4), mk4(s.c.x, s.c.y, s.a, s.alpha0));
     stV2(c, bslot(c, b, SB_C0X), s.c0);
-    stV2(c, bslot(c, b, SB_CX), s.c);
     stF(c, bslot(c, b, SB_A0), s.a0);
-    stF(c, bslot(c, b, SB_A), s.a);
-    stF(c, bslot(c, b, SB_ALPHA0), s.alpha0);
 }
 DEV void sweepAdvance(Sweep& s, float alpha) {  // b2Sweep::Advance
     float beta = (alpha - s.alpha0) / (1.0f - s.alpha0);
@@ -50,7 +49,7 @@ DEV void sweepNormalize(Sweep& s) {  // b2Sweep::Normalize
     s.a -= d;
 }
 // b2Body::Advance
-DEV void bodyAdvance(const Ctx& c, int b, float alpha) {
+DEV void bodyAdvance(Ctx c, int b, float alpha) {
     Sweep s = ldSweep(c, b);
     sweepAdvance(s, alpha);
     s.c = s.c0;
@@ -59,7 +58,7 @@ DEV void bodyAdvance(const Ctx& c, int b, float alpha) {
     syncTransform(c, b);
 }
 
-DEV int fixSupport(const Ctx& c, int f, V2 d) {  // b2DistanceProxy::GetSupport
+DEV int fixSupport(Ctx c, int f, V2 d) {  // b2DistanceProxy::GetSupport
     int n = mI(c, mfix(c, f, MF_COUNT));
     int best = 0;
     float bestValue = dot(fixVert(c, f, 0), d);
@@ -143,7 +142,7 @@ DEV void simplexSolve3(Simplex& s) {
 }
 
 // b2Distance without radii (the only mode b2TimeOfImpact uses); returns the distance, updates the cache
-DEVN float distanceGJK(const Ctx& c, SimplexCache& cache, int fA, const XF& xfA, int fB, const XF& xfB) {
+DEVN float distanceGJK(Ctx c, SimplexCache& cache, int fA, const XF& xfA, int fB, const XF& xfB) {
     Simplex s;
     // ReadCache
     s.count = cache.count;
@@ -228,7 +227,7 @@ struct SepFn {
     V2 localPoint, axis;
 };
 
-DEV void sepInit(const Ctx& c, SepFn& f, const SimplexCache& cache, int fA, const Sweep& sA, int fB, const Sweep& sB, float t1) {
+DEV void sepInit(Ctx c, SepFn& f, const SimplexCache& cache, int fA, const Sweep& sA, int fB, const Sweep& sB, float t1) {
     XF xfA = sweepXF(sA, t1), xfB = sweepXF(sB, t1);
     if (cache.count == 1) {
         f.type = 0;
@@ -264,7 +263,7 @@ DEV void sepInit(const Ctx& c, SepFn& f, const SimplexCache& cache, int fA, cons
 }
 
 // FindMinSeparation (find = true: choose support points) and Evaluate (find = false) share everything else
-DEV float sepEval(const Ctx& c, const SepFn& f, int fA, const Sweep& sA, int fB, const Sweep& sB, int& indexA, int& indexB,
+DEV float sepEval(Ctx c, const SepFn& f, int fA, const Sweep& sA, int fB, const Sweep& sB, int& indexA, int& indexB,
                   float t, bool find) {
     XF xfA = sweepXF(sA, t), xfB = sweepXF(sB, t);
     if (f.type == 0) {
@@ -297,7 +296,7 @@ DEV float sepEval(const Ctx& c, const SepFn& f, int fA, const Sweep& sA, int fB,
 }
 
 // returns true when the output state is e_touching; t receives output.t
-DEVN bool timeOfImpact(const Ctx& c, int fA, Sweep sweepA, int fB, Sweep sweepB, float& tOut) {
+DEVN bool timeOfImpact(Ctx c, int fA, Sweep sweepA, int fB, Sweep sweepB, float& tOut) {
     const float tMax = 1.0f;
     tOut = tMax;
     sweepNormalize(sweepA);
@@ -353,7 +352,7 @@ DEVN bool timeOfImpact(const Ctx& c, int fA, Sweep sweepA, int fB, Sweep sweepB,
 }
 
 // ---- b2World::SolveTOI ----------------------------------------------------------------------------------------------
-DEV void clearToiFlags(const Ctx& c, int body) {  // invalidate cached TOIs of every contact on `body`
+DEV void clearToiFlags(Ctx c, int body) {  // invalidate cached TOIs of every contact on `body`
     for (int k = contactCount(c) - 1; k >= 0; --k) {
         int fA, fB;
         contactFixtures(c, k, fA, fB);
@@ -362,8 +361,8 @@ DEV void clearToiFlags(const Ctx& c, int body) {  // invalidate cached TOIs of e
     }
 }
 
-DEVN void solveTOI(const Ctx& c) {
-    const int nb = c.h->nb;
+DEVN void solveTOI(Ctx c) {
+    const int nb = H().nb;
     // m_stepComplete is always true here (no sub-stepping mode): reset sweeps' alpha0 and the contacts' TOI cache
     bool candidates = false;
     for (int k = contactCount(c) - 1; k >= 0; --k) {
@@ -484,7 +483,7 @@ DEVN void solveTOI(const Ctx& c) {
         }
 
         // b2Island::SolveTOI with subStep.dt = (1 - minAlpha) * dt, 20 position iterations, no warm starting
-        float h = (1.0f - minAlpha) * c.dt;
+        float h = (1.0f - minAlpha) * PRM().dt;
         for (int it = 0; it < 20; ++it) {
             float minSeparation = 0.0f;
             for (int i = 0; i < nic; ++i) minSeparation = contactSolvePos(c, icontacts[i], bA, bB, minSeparation);
@@ -495,7 +494,7 @@ DEVN void solveTOI(const Ctx& c) {
         stV2(c, bslot(c, bB, SB_C0X), ldV2(c, bslot(c, bB, SB_CX)));
         stF(c, bslot(c, bB, SB_A0), ldF(c, bslot(c, bB, SB_A)));
         for (int i = 0; i < nic; ++i) contactInit(c, icontacts[i], 1.0f, false);
-        for (int it = 0; it < c.velIters; ++it)
+        for (int it = 0, nv = PRM().velIters; it < nv; ++it)
             for (int i = 0; i < nic; ++i) contactSolveVel(c, icontacts[i]);
         for (int i = 0; i < nib; ++i) {
             integratePosition(c, ibodies[i], h);

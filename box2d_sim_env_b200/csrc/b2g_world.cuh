@@ -7,39 +7,39 @@
 
 namespace b2g {
 
-DEV int olink(const Ctx& c, int o, int pos, int f) { return c.h->oLink + (mI(c, mobj(c, o, MO_LINK_START)) + pos) * ML_STRIDE + f; }
-DEV float dofLimit(const Ctx& c, int dof, int k) { return mF(c, c.h->oDof + dof * 6 + k); }
+DEV int olink(Ctx c, int o, int pos, int f) { return H().oLink + (mI(c, mobj(c, o, MO_LINK_START)) + pos) * ML_STRIDE + f; }
+DEV float dofLimit(Ctx c, int dof, int k) { return mF(c, H().oDof + dof * 6 + k); }
 DEV float clampStd(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }  // sim_env::utils::math::clamp
 
 // Box2DLink::getPose (:215-224) for the base link of object o
-DEV void basePose(const Ctx& c, int o, float pose[3]) {
+DEV void basePose(Ctx c, int o, float pose[3]) {
     int b = mI(c, mobj(c, o, MO_BASE_BODY));
     XF xf = ldXF(c, b);
     V2 pos = mul(xf, mk(mF(c, mobj(c, o, MO_ORIGIN_X)), mF(c, mobj(c, o, MO_ORIGIN_Y))));
-    float inv = c.h->invScale;
+    float inv = H().invScale;
     pose[0] = inv * pos.x;
     pose[1] = inv * pos.y;
     pose[2] = ldF(c, bslot(c, b, SB_A));
 }
 
 // b2RevoluteJoint::GetJointAngle / GetJointSpeed (:972, :1037)
-DEV float jointAngle(const Ctx& c, int j) {
+DEV float jointAngle(Ctx c, int j) {
     int bA = mI(c, mjoint(c, j, MJ_BODYA)), bB = mI(c, mjoint(c, j, MJ_BODYB));
     return ldF(c, bslot(c, bB, SB_A)) - ldF(c, bslot(c, bA, SB_A)) - mF(c, mjoint(c, j, MJ_REF));
 }
-DEV float jointSpeed(const Ctx& c, int j) {
+DEV float jointSpeed(Ctx c, int j) {
     int bA = mI(c, mjoint(c, j, MJ_BODYA)), bB = mI(c, mjoint(c, j, MJ_BODYB));
     return ldF(c, bslot(c, bB, SB_W)) - ldF(c, bslot(c, bA, SB_W));
 }
-DEV int objJoint(const Ctx& c, int o, int i) { return mI(c, c.h->oObjJoint + mI(c, mobj(c, o, MO_JOINT_START)) + i) & 0xffff; }
-DEV int objJointChildPos(const Ctx& c, int o, int i) { return mI(c, c.h->oObjJoint + mI(c, mobj(c, o, MO_JOINT_START)) + i) >> 16; }
-DEV V2 jointAnchorA(const Ctx& c, int j) {  // b2RevoluteJoint::GetAnchorA
+DEV int objJoint(Ctx c, int o, int i) { return mI(c, H().oObjJoint + mI(c, mobj(c, o, MO_JOINT_START)) + i) & 0xffff; }
+DEV int objJointChildPos(Ctx c, int o, int i) { return mI(c, H().oObjJoint + mI(c, mobj(c, o, MO_JOINT_START)) + i) >> 16; }
+DEV V2 jointAnchorA(Ctx c, int j) {  // b2RevoluteJoint::GetAnchorA
     int bA = mI(c, mjoint(c, j, MJ_BODYA));
     return mul(ldXF(c, bA), mk(mF(c, mjoint(c, j, MJ_LAX)), mF(c, mjoint(c, j, MJ_LAY))));
 }
 
 // Box2DObject::getDOFPositions / getDOFVelocities over all DOFs (:1507-1528, :1628-1649)
-DEV void getDofPositions(const Ctx& c, int o, float* q) {
+DEV void getDofPositions(Ctx c, int o, float* q) {
     int isStatic = mI(c, mobj(c, o, MO_STATIC));
     int n = 0;
     if (!isStatic) {
@@ -51,12 +51,12 @@ DEV void getDofPositions(const Ctx& c, int o, float* q) {
     int nj = mI(c, mobj(c, o, MO_JOINT_COUNT));
     for (int i = 0; i < nj; ++i) q[n + i] = jointAngle(c, objJoint(c, o, i));
 }
-DEV void getDofVelocities(const Ctx& c, int o, float* qd) {
+DEV void getDofVelocities(Ctx c, int o, float* qd) {
     int isStatic = mI(c, mobj(c, o, MO_STATIC));
     int n = 0;
     if (!isStatic) {
         int b = mI(c, mobj(c, o, MO_BASE_BODY));
-        float inv = c.h->invScale;
+        float inv = H().invScale;
         qd[0] = inv * ldF(c, bslot(c, b, SB_VX));
         qd[1] = inv * ldF(c, bslot(c, b, SB_VY));
         qd[2] = ldF(c, bslot(c, b, SB_W));
@@ -70,14 +70,14 @@ DEV void getDofVelocities(const Ctx& c, int o, float* qd) {
 // Box2DJoint::resetPosition recursion (:992-1028), flattened: every joint value of the subtree is read
 // before anything moves (that is what the recursion does), then links are placed parent first.
 // `pos` is the position of the subtree root in the object's pre-order link list.
-DEVN void placeSubtree(const Ctx& c, int o, int pos, const float pose[3], bool jointOverride) {
+DEVN void placeSubtree(Ctx c, int o, int pos, const float pose[3], bool jointOverride) {
     int count = mI(c, olink(c, o, pos, ML_SUBTREE));
     float jv[kMaxLinksPerObject];
     for (int i = 1; i < count; ++i) {
         int j = mI(c, olink(c, o, pos + i, ML_PARENT_JOINT));
         jv[i] = jointOverride ? 0.0f : jointAngle(c, j);
     }
-    float s = c.h->scale, inv = c.h->invScale;
+    float s = H().scale, inv = H().invScale;
     for (int i = 0; i < count; ++i) {
         int b = mI(c, olink(c, o, pos + i, ML_BODY));
         float px, py, th;
@@ -105,10 +105,10 @@ DEVN void placeSubtree(const Ctx& c, int o, int pos, const float pose[3], bool j
 
 // Box2DObject::updateBodyVelocities + Box2DLink::updateBodyVelocities (:2018-2041, :759-794).
 // qd holds all DOF velocities of the object (object-local indexing).
-DEVN void updateBodyVelocities(const Ctx& c, int o, const float* qd) {
+DEVN void updateBodyVelocities(Ctx c, int o, const float* qd) {
     int isStatic = mI(c, mobj(c, o, MO_STATIC));
     int nl = mI(c, mobj(c, o, MO_LINK_COUNT));
-    float s = c.h->scale;
+    float s = H().scale;
     float pose[3];
     basePose(c, o, pose);
     V2 baseAxis = mk(s * pose[0], s * pose[1]);
@@ -127,7 +127,7 @@ DEVN void updateBodyVelocities(const Ctx& c, int o, const float* qd) {
             lin.y += bw * r.x;
             ang += bw;
         }
-        int cs = c.h->oChain + mI(c, olink(c, o, p, ML_CHAIN_START));
+        int cs = H().oChain + mI(c, olink(c, o, p, ML_CHAIN_START));
         int cl = mI(c, olink(c, o, p, ML_CHAIN_LEN));
         for (int e = 0; e < cl; ++e) {
             int j = mI(c, cs + e);
@@ -147,7 +147,7 @@ DEVN void updateBodyVelocities(const Ctx& c, int o, const float* qd) {
 }
 
 // Box2DObject::setPose(x, y, theta) / setTransform (:1940-1947, :1419-1433)
-DEVN void objectSetPose(const Ctx& c, int o, float x, float y, float theta) {
+DEVN void objectSetPose(Ctx c, int o, float x, float y, float theta) {
     float qd[kMaxDofsPerObject];
     getDofVelocities(c, o, qd);
     float pose[3] = {x, y, theta};
@@ -156,7 +156,7 @@ DEVN void objectSetPose(const Ctx& c, int o, float x, float y, float theta) {
 }
 
 // Box2DObject::setDOFPositions over all DOFs (:1585-1626)
-DEVN void objectSetDofPositions(const Ctx& c, int o, const float* q) {
+DEVN void objectSetDofPositions(Ctx c, int o, const float* q) {
     float qd[kMaxDofsPerObject];
     getDofVelocities(c, o, qd);
     int isStatic = mI(c, mobj(c, o, MO_STATIC));
@@ -175,8 +175,8 @@ DEVN void objectSetDofPositions(const Ctx& c, int o, const float* q) {
         float clamped = clampStd(q[n + i], dofLimit(c, dof, 0), dofLimit(c, dof, 1));
         float pose[3];
         V2 axisWorld = jointAnchorA(c, j);
-        pose[0] = c.h->invScale * axisWorld.x;
-        pose[1] = c.h->invScale * axisWorld.y;
+        pose[0] = H().invScale * axisWorld.x;
+        pose[1] = H().invScale * axisWorld.y;
         pose[2] = ldF(c, bslot(c, bA, SB_A)) + clamped + mF(c, mjoint(c, j, MJ_REF));
         placeSubtree(c, o, objJointChildPos(c, o, i), pose, false);
     }
@@ -184,7 +184,7 @@ DEVN void objectSetDofPositions(const Ctx& c, int o, const float* q) {
 }
 
 // Box2DObject::setDOFVelocities over all DOFs (:1691-1715)
-DEVN void objectSetDofVelocities(const Ctx& c, int o, const float* v) {
+DEVN void objectSetDofVelocities(Ctx c, int o, const float* v) {
     float qd[kMaxDofsPerObject];
     int n = mI(c, mobj(c, o, MO_NDOFS));
     int dofOffset = mI(c, mobj(c, o, MO_DOF_OFFSET));
@@ -193,15 +193,15 @@ DEVN void objectSetDofVelocities(const Ctx& c, int o, const float* v) {
 }
 
 // Box2DObject::setState (:1980-1989) for object o; q/qd are the object's slices of the world state vector
-DEV void objectSetState(const Ctx& c, int o, const float* q, const float* qd) {
+DEV void objectSetState(Ctx c, int o, const float* q, const float* qd) {
     if (!mI(c, mobj(c, o, MO_STATIC))) objectSetPose(c, o, q[0], q[1], q[2]);
     objectSetDofPositions(c, o, q);
     objectSetDofVelocities(c, o, qd);
 }
 
 // ---- freshly loaded world: what createWorld leaves behind (:3664-3721) ------------------------------------------
-DEVN void initWorld(const Ctx& c) {
-    const ModelHeader& h = *c.h;
+DEVN void initWorld(Ctx c) {
+    const ModelHeader& h = H();
     for (int b = 0; b < h.nb; ++b) {
         XF xf;
         xf.p = mk(mF(c, mbody(c, b, MB_PX)), mF(c, mbody(c, b, MB_PY)));
@@ -220,17 +220,18 @@ DEVN void initWorld(const Ctx& c) {
         stF(c, bslot(c, b, SB_ALPHA0), 0.0f);
         stF(c, bslot(c, b, SB_FX), 0.0f); stF(c, bslot(c, b, SB_FY), 0.0f); stF(c, bslot(c, b, SB_TORQUE), 0.0f);
     }
-    for (int f = 0; f < h.nf; ++f)
-        for (int k = 0; k < 4; ++k) stF(c, h.sFix + f * 4 + k, mF(c, mfix(c, f, MF_FAT0 + k)));
+    for (int f = 0; f < h.nf; ++f) st4(c, fslot(c, f), m4(c, mfix(c, f, MF_FAT0)));
     for (int j = 0; j < h.nj; ++j) {
-        for (int k = 0; k < SJ_STRIDE; ++k) stF(c, jslot(c, j, k), 0.0f);
+        const float4 zero = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int k = 0; k < SJ_CHUNKS; ++k) st4(c, jslot(c, j, k * kChunkBytes), zero);
         int enableMotor = (mI(c, mjoint(c, j, MJ_FLAGS)) >> 1) & 1;
         stI(c, jslot(c, j, SJ_FLAGS), enableMotor << 2);
-        for (int k = 0; k < WJ_STRIDE; ++k) stF(c, jwslot(c, j, k), 0.0f);
+        for (int k = 0; k < WJ_CHUNKS; ++k) st4(c, jwslot(c, j, k * kChunkBytes), zero);
     }
     for (int k = 0; k < h.maxc; ++k) {
-        for (int f = 0; f < SC_STRIDE; ++f) stF(c, cslot(c, k, f), 0.0f);
-        for (int f = 0; f < WC_STRIDE; ++f) stF(c, cwslot(c, k, f), 0.0f);
+        const float4 zero = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int f = 0; f < SC_CHUNKS; ++f) st4(c, cslot(c, k, f * kChunkBytes), zero);
+        for (int f = 0; f < WC_CHUNKS; ++f) st4(c, cwslot(c, k, f * kChunkBytes), zero);
     }
     stF(c, sslot(c, SS_INV_DT0), 0.0f);
     stI(c, sslot(c, SS_FLAGS), 1);  // e_newFixture
@@ -239,7 +240,7 @@ DEVN void initWorld(const Ctx& c) {
     stMoved(c, h.nf >= 64 ? ~0ull : ((1ull << h.nf) - 1ull));  // every proxy is buffered at creation
     stI(c, sslot(c, SS_TARGET_AVAIL), 0);
     stI(c, sslot(c, SS_SPARE), 0);
-    for (int t = 0; t < h.ntarget; ++t) stF(c, h.sTarget + t, 0.0f);
+    for (int t = 0; t < ((h.ntarget + 3) & ~3); ++t) stF(c, tslot(c, t), 0.0f);
 
     // Box2DObject ctor: _base_link->setPose((0,0,0), true, true) (:1335)
     for (int o = 0; o < h.no; ++o) {
@@ -267,16 +268,16 @@ DEVN void initWorld(const Ctx& c) {
 // ---- controller ------------------------------------------------------------------------------------------------
 // Box2DRobot::control (:2284-2310) = Box2DRobotVelocityController::control (Box2DController.cpp:65-117)
 // followed by Box2DRobot::commandEfforts (:2319-2379) and Box2DJoint::setControlTorque (:1198-1222).
-DEVN void robotControl(const Ctx& c, int o, int robotSlot) {
+DEVN void robotControl(Ctx c, int o, int robotSlot) {
     if (((ldI(c, sslot(c, SS_TARGET_AVAIL)) >> robotSlot) & 1) == 0) return;  // "No target available."
     int n = mI(c, mobj(c, o, MO_NDOFS));
     int isStatic = mI(c, mobj(c, o, MO_STATIC));
     int baseDofs = isStatic ? 0 : 3;
     int dofOffset = mI(c, mobj(c, o, MO_DOF_OFFSET));
-    int tOff = c.h->sTarget + mI(c, mobj(c, o, MO_TARGET_OFFSET));
+    int tOff = mI(c, mobj(c, o, MO_TARGET_OFFSET));
     float vel[kMaxDofsPerObject], effort[kMaxDofsPerObject];
     getDofVelocities(c, o, vel);
-    float inv = c.h->invScale, s = c.h->scale;
+    float inv = H().invScale, s = H().scale;
     int baseBody = mI(c, mobj(c, o, MO_BASE_BODY));
     for (int i = 0; i < n; ++i) {
         float massInertia;
@@ -288,7 +289,7 @@ DEVN void robotControl(const Ctx& c, int o, int robotSlot) {
                 V2 bc = ldV2(c, bslot(c, baseBody, SB_CX));
                 float comx = inv * bc.x, comy = inv * bc.y;
                 float inertia = 0.0f;
-                int ns = c.h->oName + mI(c, mobj(c, o, MO_NAME_START));
+                int ns = H().oName + mI(c, mobj(c, o, MO_NAME_START));
                 int nl = mI(c, mobj(c, o, MO_LINK_COUNT));
                 for (int l = 0; l < nl; ++l) {
                     int b = mI(c, ns + l);
@@ -322,7 +323,7 @@ DEVN void robotControl(const Ctx& c, int o, int robotSlot) {
             float linkInertia = inv * inv * bodyInertia;  // Box2DLink::getInertia (:549-555)
             massInertia = 0.0f + (linkInertia + m * distance * distance);
         }
-        float accel = (ldF(c, tOff + i) - vel[i]) / c.dt;
+        float accel = (ldF(c, tslot(c, tOff + i)) - vel[i]) / PRM().dt;
         accel = fminf(dofLimit(c, dofOffset + i, 5), fmaxf(accel, dofLimit(c, dofOffset + i, 4)));
         effort[i] = massInertia * accel;
     }
@@ -351,8 +352,8 @@ DEVN void robotControl(const Ctx& c, int o, int robotSlot) {
 }
 
 // Box2DWorld::stepPhysics body for one step (:3270-3282) = controllers + b2World::Step + ClearForces
-DEVN void stepWorld(const Ctx& c, bool executeControllers, bool allowSleeping) {
-    const ModelHeader& h = *c.h;
+DEVN void stepWorld(Ctx c, bool executeControllers, bool allowSleeping) {
+    const ModelHeader& h = H();
     if (executeControllers) {
         for (int r = 0; r < h.nrobots; ++r) robotControl(c, mI(c, h.oRobotOrder + r), r);
     }
@@ -365,15 +366,13 @@ DEVN void stepWorld(const Ctx& c, bool executeControllers, bool allowSleeping) {
         findNewContacts(c);
         stI(c, sslot(c, SS_FLAGS), flags & ~1);
     }
-    float dtRatio = ldF(c, sslot(c, SS_INV_DT0)) * c.dt;
+    float dtRatio = ldF(c, sslot(c, SS_INV_DT0)) * PRM().dt;
     collide(c);
     solveIslands(c, dtRatio, allowSleeping);
     solveTOI(c);
-    stF(c, sslot(c, SS_INV_DT0), c.inv_dt);
+    stF(c, sslot(c, SS_INV_DT0), PRM().inv_dt);
     for (int b = 0; b < h.nb; ++b) {  // ClearForces
-        stF(c, bslot(c, b, SB_FX), 0.0f);
-        stF(c, bslot(c, b, SB_FY), 0.0f);
-        stF(c, bslot(c, b, SB_TORQUE), 0.0f);
+        st4(c, bslot(c, b, SB_FORCE4), mk4(0.0f, 0.0f, 0.0f, 0.0f));
     }
 }
 

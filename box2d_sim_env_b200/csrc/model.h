@@ -18,14 +18,15 @@ constexpr int kMaxLinksPerObject = 16;
 constexpr int kMaxDofsPerObject = 3 + kMaxLinksPerObject;
 
 // ---- model blob strides / fields --------------------------------------------------------------------
-enum BodyField {  // per body
-    MB_INVMASS = 0, MB_INVI, MB_MASS, MB_I, MB_LCX, MB_LCY,
+enum BodyField {  // per body; 16-byte groups are read with one LDS.128
+    MB_INVMASS = 0, MB_INVI, MB_LCX, MB_LCY,
+    MB_MASS, MB_I,
     MB_TYPE,      // 0 static, 2 dynamic (b2BodyType)
+    MB_OBJECT,
     MB_JE_START,  // first joint edge (upstream list order: newest joint first)
     MB_JE_COUNT,
     MB_FIX_START, // fixtures of a body are consecutive proxies
     MB_FIX_COUNT,
-    MB_OBJECT,
     MB_COLLIDE_LO, MB_COLLIDE_HI,  // bit b: b2Body::ShouldCollide(this, b)
     MB_PX, MB_PY,  // creation position (non-zero for the ground body only)
     MB_STRIDE
@@ -33,6 +34,7 @@ enum BodyField {  // per body
 enum FixtureField {  // per fixture / broad-phase proxy (creation order == proxy id order)
     MF_BODY = 0, MF_COUNT, MF_FRICTION, MF_RESTITUTION,
     MF_PAIR_LO, MF_PAIR_HI,  // bit g: fixture g can ever form a contact with this one
+    MF_SPARE0, MF_SPARE1,
     MF_FAT0,                  // fat AABB at creation (4 floats)
     MF_VERTS = MF_FAT0 + 4,   // 8 x (x, y)
     MF_NORMALS = MF_VERTS + 16,
@@ -42,7 +44,9 @@ enum JointField {
     MJ_TYPE = 0,  // 0 friction, 1 revolute
     MJ_BODYA, MJ_BODYB,
     MJ_FLAGS,     // bit0 enableLimit, bit1 enableMotor at creation
-    MJ_LAX, MJ_LAY, MJ_LBX, MJ_LBY, MJ_REF, MJ_LOWER, MJ_UPPER, MJ_MAXFORCE, MJ_MAXTORQUE,
+    MJ_LAX, MJ_LAY, MJ_LBX, MJ_LBY,
+    MJ_REF, MJ_LOWER, MJ_UPPER, MJ_MAXFORCE,
+    MJ_MAXTORQUE,
     MJ_DOF,       // index in the world state vector (revolute joints of objects), -1 otherwise
     MJ_OBJECT,
     MJ_SPARE,
@@ -72,72 +76,97 @@ enum LinkField {  // pre-order (parent first) list per object
     ML_STRIDE
 };
 
+struct StepParams {
+    float dt, inv_dt;  // inv_dt = dt > 0 ? 1 / dt : 0 (b2TimeStep)
+    int velIters, posIters;
+};
+
 struct ModelHeader {
     int32_t nb, nf, nj, no, nrobots, nq, ntarget;
     int32_t words;  // blob size in 32-bit words
     float scale, invScale;
-    // blob offsets
+    // blob offsets (words; body / fixture / joint records start on 16-byte boundaries)
     int32_t oBody, oFix, oJoint, oJEdge, oObj, oLink, oObjJoint, oChain, oDof, oName, oRobotOrder, oInit;
-    // per-world state layout (word slots; state is stored [slot][world])
+    // per-world state layout, in 16-byte chunks (see below)
     int32_t maxc;       // contact slots per world
-    int32_t sBody, sFix, sJoint, sJointW, sCont, sContW, sScalar, sTarget;
-    int32_t stateWords;
+    int32_t cBody, cFix, cJoint, cJointW, cCont, cContW, cScalar, cTarget;
+    int32_t stateChunks;
 };
 
-// ---- per-world state strides / fields -----------------------------------------------------------------
+// ---- per-world state ------------------------------------------------------------------------------------
+// The state of a batch is one array of 16-byte chunks tiled by warp: state[tile][chunk][lane] with
+// tile = world / 32, lane = world % 32.  A warp touching chunk k of its 32 worlds issues one coalesced 512-byte
+// LDG.128 / STG.128, and all chunks of a tile are contiguous, so a thread reaches any word of its world at
+//     base(tile, lane) + chunk * 512 + word * 4
+// Field enumerators below are such byte offsets relative to the first chunk of their record.
+constexpr int kTileWorlds = 32;
+constexpr int kChunkBytes = 16 * kTileWorlds;  // 512
+#define B2G_F(chunk, word) ((chunk) * 512 + (word) * 4)
+
 enum BodyState {
-    SB_PX = 0, SB_PY, SB_QS, SB_QC,  // b2Body::m_xf
-    SB_CX, SB_CY, SB_A,              // m_sweep.c, a
-    SB_C0X, SB_C0Y, SB_A0,           // m_sweep.c0, a0
-    SB_VX, SB_VY, SB_W,
-    SB_SLEEP,                         // m_sleepTime
-    SB_FLAGS,                         // bit0 awake
-    SB_ALPHA0,                        // m_sweep.alpha0
-    SB_FX, SB_FY, SB_TORQUE,
-    SB_STRIDE
+    SB_PX = B2G_F(0, 0), SB_PY = B2G_F(0, 1), SB_QS = B2G_F(0, 2), SB_QC = B2G_F(0, 3),    // b2Body::m_xf
+    SB_CX = B2G_F(1, 0), SB_CY = B2G_F(1, 1), SB_A = B2G_F(1, 2), SB_ALPHA0 = B2G_F(1, 3),  // m_sweep.c, a, alpha0
+    SB_C0X = B2G_F(2, 0), SB_C0Y = B2G_F(2, 1), SB_A0 = B2G_F(2, 2),                        // m_sweep.c0, a0
+    SB_SLEEP = B2G_F(2, 3),                                                                // m_sleepTime
+    SB_VX = B2G_F(3, 0), SB_VY = B2G_F(3, 1), SB_W = B2G_F(3, 2),
+    SB_FLAGS = B2G_F(3, 3),                                                                // bit0 awake
+    SB_FX = B2G_F(4, 0), SB_FY = B2G_F(4, 1), SB_TORQUE = B2G_F(4, 2),
+    SB_XF4 = B2G_F(0, 0), SB_POS4 = B2G_F(1, 0), SB_POS04 = B2G_F(2, 0), SB_VEL4 = B2G_F(3, 0), SB_FORCE4 = B2G_F(4, 0),
+    SB_CHUNKS = 5
 };
 enum JointState {
-    SJ_IX = 0, SJ_IY, SJ_IZ,  // friction: linearImpulse.xy, angularImpulse; revolute: m_impulse
-    SJ_MOTOR_IMPULSE,
-    SJ_FLAGS,                  // bits0-1 limitState, bit2 enableMotor
-    SJ_MAX_MOTOR_TORQUE, SJ_MOTOR_SPEED,
-    SJ_SPARE,
-    SJ_STRIDE
+    SJ_IX = B2G_F(0, 0), SJ_IY = B2G_F(0, 1), SJ_IZ = B2G_F(0, 2),  // friction: linearImpulse.xy, angularImpulse; revolute: m_impulse
+    SJ_MOTOR_IMPULSE = B2G_F(0, 3),                                 // revolute only
+    SJ_ANGULAR_MASS = B2G_F(0, 3),                                  // friction only (solver scratch kept next to the impulses)
+    SJ_FLAGS = B2G_F(1, 0),                                         // bits0-1 limitState, bit2 enableMotor
+    SJ_MAX_MOTOR_TORQUE = B2G_F(1, 1), SJ_MOTOR_SPEED = B2G_F(1, 2),
+    SJ_MOTOR_MASS = B2G_F(1, 3),                                    // revolute solver scratch
+    SJ_IMPULSE4 = B2G_F(0, 0), SJ_MOTOR4 = B2G_F(1, 0),
+    SJ_CHUNKS = 2
 };
 enum JointWork {  // solver scratch, valid inside one island solve
-    WJ_RAX = 0, WJ_RAY, WJ_RBX, WJ_RBY,
-    WJ_M0,  // friction: linearMass ex.x ex.y ey.x ey.y, angularMass; revolute: mass ex.xyz ey.xyz ez.xyz, motorMass
-    WJ_STRIDE = WJ_M0 + 12
+    WJ_RAX = B2G_F(0, 0), WJ_RAY = B2G_F(0, 1), WJ_RBX = B2G_F(0, 2), WJ_RBY = B2G_F(0, 3),
+    // friction: linearMass = [ex.x ex.y ey.x ey.y];  revolute: the symmetric 3x3 K is stored as
+    // [ex.x ex.y(=ey.x) ey.y -] [ez.x(=ex.z) ez.y(=ey.z) - -]; ez.z = iA + iB is recomputed
+    WJ_M0 = B2G_F(1, 0), WJ_M1 = B2G_F(2, 0),
+    WJ_R4 = B2G_F(0, 0),
+    WJ_CHUNKS = 3
 };
 enum ContactState {
-    SC_FIX = 0,    // fixtureA | fixtureB << 8
-    SC_FLAGS,      // bit0 touching, bit1 enabled, bit2 filter, bit4 toi valid; bits 8.. toiCount
-    SC_MANIFOLD,   // type | pointCount << 8
-    SC_ID0, SC_ID1,
-    SC_LNX, SC_LNY, SC_LPX, SC_LPY,
-    SC_P0X, SC_P0Y, SC_N0, SC_T0,
-    SC_P1X, SC_P1Y, SC_N1, SC_T1,
-    SC_TOI,
-    SC_STRIDE
+    SC_FIX = B2G_F(0, 0),       // fixtureA | fixtureB << 8
+    SC_FLAGS = B2G_F(0, 1),     // bit0 touching, bit1 enabled, bit2 filter, bit4 toi valid; bits 8.. toiCount
+    SC_MANIFOLD = B2G_F(0, 2),  // type | pointCount << 8
+    SC_TOI = B2G_F(0, 3),
+    SC_ID0 = B2G_F(1, 0), SC_ID1 = B2G_F(1, 1), SC_LNX = B2G_F(1, 2), SC_LNY = B2G_F(1, 3),
+    SC_LPX = B2G_F(2, 0), SC_LPY = B2G_F(2, 1),
+    SC_P0X = B2G_F(3, 0), SC_P0Y = B2G_F(3, 1), SC_N0 = B2G_F(3, 2), SC_T0 = B2G_F(3, 3),
+    SC_P1X = B2G_F(4, 0), SC_P1Y = B2G_F(4, 1), SC_N1 = B2G_F(4, 2), SC_T1 = B2G_F(4, 3),
+    SC_HEAD4 = B2G_F(0, 0), SC_ID4 = B2G_F(1, 0), SC_LP4 = B2G_F(2, 0), SC_P04 = B2G_F(3, 0), SC_P14 = B2G_F(4, 0),
+    SC_PT_STRIDE = B2G_F(1, 0),  // SC_P1* - SC_P0*
+    SC_CHUNKS = 5
 };
-enum ContactWork {
-    WC_NX = 0, WC_NY,
-    WC_PT0,                       // per point: rA(2) rB(2) normalMass tangentMass velocityBias normalImpulse tangentImpulse
-    WC_PT_STRIDE = 9,
-    WC_K = WC_PT0 + 2 * WC_PT_STRIDE,  // k11 k12 k22
-    WC_NM = WC_K + 3,                  // normalMass: ex.x, ex.y(=ey.x), ey.y
-    WC_COUNT = WC_NM + 3,              // velocity-constraint point count (may drop to 1)
-    WC_STRIDE
+enum ContactWork {  // b2ContactVelocityConstraint, valid inside one island / TOI solve
+    WC_NX = B2G_F(0, 0), WC_NY = B2G_F(0, 1),
+    WC_COUNT = B2G_F(0, 2),     // velocity-constraint point count (may drop to 1)
+    WC_FRICTION = B2G_F(0, 3),
+    WC_R0 = B2G_F(1, 0),        // point 0: rA.xy rB.xy
+    WC_R1 = B2G_F(2, 0),        // point 1
+    WC_MASS = B2G_F(3, 0),      // normalMass0 tangentMass0 normalMass1 tangentMass1
+    WC_BIAS0 = B2G_F(4, 0), WC_BIAS1 = B2G_F(4, 1), WC_K11 = B2G_F(4, 2), WC_K12 = B2G_F(4, 3),
+    WC_K22 = B2G_F(5, 0), WC_NM11 = B2G_F(5, 1), WC_NM12 = B2G_F(5, 2), WC_NM22 = B2G_F(5, 3),  // normalMass = K^-1 (symmetric)
+    WC_IMP = B2G_F(6, 0),       // normalImpulse0 tangentImpulse0 normalImpulse1 tangentImpulse1
+    WC_N4 = B2G_F(0, 0), WC_BK4 = B2G_F(4, 0), WC_KN4 = B2G_F(5, 0),
+    WC_CHUNKS = 7
 };
 enum ScalarState {
-    SS_INV_DT0 = 0,
-    SS_FLAGS,     // bit0 newFixture
-    SS_NCONTACTS,
-    SS_STATUS,    // bit0 contact capacity exceeded, bit1 non-finite
-    SS_MOVED_LO, SS_MOVED_HI,
-    SS_TARGET_AVAIL,  // bit r: robot r has a controller target
-    SS_SPARE,
-    SS_STRIDE
+    SS_INV_DT0 = B2G_F(0, 0),
+    SS_FLAGS = B2G_F(0, 1),      // bit0 newFixture
+    SS_NCONTACTS = B2G_F(0, 2),
+    SS_STATUS = B2G_F(0, 3),     // bit0 contact capacity exceeded, bit1 non-finite
+    SS_MOVED_LO = B2G_F(1, 0), SS_MOVED_HI = B2G_F(1, 1),
+    SS_TARGET_AVAIL = B2G_F(1, 2),  // bit r: robot r has a controller target
+    SS_SPARE = B2G_F(1, 3),
+    SS_CHUNKS = 2
 };
 
 }  // namespace b2g

@@ -203,16 +203,16 @@ uint32_t fbits(float f) {
 
 void layoutState(ModelHeader& h, int maxContacts) {
     h.maxc = maxContacts;
-    int s = 0;
-    h.sBody = s; s += h.nb * SB_STRIDE;
-    h.sFix = s; s += h.nf * 4;
-    h.sJoint = s; s += h.nj * SJ_STRIDE;
-    h.sJointW = s; s += h.nj * WJ_STRIDE;
-    h.sCont = s; s += h.maxc * SC_STRIDE;
-    h.sContW = s; s += h.maxc * WC_STRIDE;
-    h.sScalar = s; s += SS_STRIDE;
-    h.sTarget = s; s += h.ntarget;
-    h.stateWords = s;
+    int s = 0;  // 16-byte chunks
+    h.cBody = s; s += h.nb * SB_CHUNKS;
+    h.cFix = s; s += h.nf;
+    h.cJoint = s; s += h.nj * SJ_CHUNKS;
+    h.cJointW = s; s += h.nj * WJ_CHUNKS;
+    h.cCont = s; s += h.maxc * SC_CHUNKS;
+    h.cContW = s; s += h.maxc * WC_CHUNKS;
+    h.cScalar = s; s += SS_CHUNKS;
+    h.cTarget = s; s += (h.ntarget + 3) / 4;
+    h.stateChunks = s;
 }
 
 void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& out) {
@@ -532,6 +532,7 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
     std::vector<uint32_t>& B = out.blob;
     B.clear();
     auto allocWords = [&](int n) { int o = (int)B.size(); B.resize(B.size() + n, 0u); return o; };
+    auto align4 = [&]() { while (B.size() % 4) B.push_back(0u); };  // records read with LDS.128 start on 16 bytes
 
     h.oJEdge = allocWords(0);
     std::vector<int> jeStart(nb);
@@ -539,6 +540,7 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
         jeStart[b] = (int)B.size() - h.oJEdge;
         for (auto& e : jedges[b]) B.push_back((uint32_t)(e.first | (e.second << 16)));
     }
+    align4();
     h.oBody = allocWords(nb * MB_STRIDE);
     for (int b = 0; b < nb; ++b) {
         uint32_t* w = &B[h.oBody + b * MB_STRIDE];
@@ -551,6 +553,7 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
         w[MB_COLLIDE_LO] = (uint32_t)(collide[b] & 0xffffffffull); w[MB_COLLIDE_HI] = (uint32_t)(collide[b] >> 32);
         w[MB_PX] = fbits(bd.px); w[MB_PY] = fbits(bd.py);
     }
+    align4();
     h.oFix = allocWords(nf * MF_STRIDE);
     for (int f = 0; f < nf; ++f) {
         uint32_t* w = &B[h.oFix + f * MF_STRIDE];
@@ -580,6 +583,7 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
             w[MF_NORMALS + 2 * i] = fbits(n.x); w[MF_NORMALS + 2 * i + 1] = fbits(n.y);
         }
     }
+    align4();
     h.oJoint = allocWords(nj * MJ_STRIDE);
     for (int j = 0; j < nj; ++j) {
         uint32_t* w = &B[h.oJoint + j * MJ_STRIDE];
