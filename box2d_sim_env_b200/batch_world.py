@@ -46,7 +46,7 @@ ABI_SYMBOLS = [
     "b2g_batch_get_state", "b2g_batch_get_state_dev", "b2g_batch_set_object_pose", "b2g_batch_get_object_pose",
     "b2g_batch_set_target_velocity", "b2g_batch_set_target_velocity_dev", "b2g_batch_step", "b2g_batch_rollout_dev",
     "b2g_batch_get_bodies", "b2g_batch_get_fat_aabbs", "b2g_batch_get_joints", "b2g_batch_get_contacts",
-    "b2g_batch_check_collision", "b2g_batch_save_state", "b2g_batch_restore_state", "b2g_batch_drop_state",
+    "b2g_batch_check_collision", "b2g_batch_check_collision_dev", "b2g_batch_save_state", "b2g_batch_restore_state", "b2g_batch_drop_state",
     "b2g_host_alloc", "b2g_host_free", "b2g_launch_count", "b2g_batch_take_kernel_ms",
 ]
 
@@ -107,6 +107,7 @@ def lib():
     L.b2g_batch_get_joints.argtypes = [vp, ip, fp]
     L.b2g_batch_get_contacts.argtypes = [vp, ip, ip, fp, C.c_int]
     L.b2g_batch_check_collision.argtypes = [vp, ip, ip, fp, C.c_int]
+    L.b2g_batch_check_collision_dev.argtypes = [vp, ip, ip, fp, C.c_int]
     for n in ("b2g_batch_save_state", "b2g_batch_restore_state", "b2g_batch_drop_state"):
         getattr(L, n).argtypes = [vp]
     L.b2g_host_alloc.argtypes = [C.POINTER(vp), C.c_uint64]
@@ -422,6 +423,10 @@ class BatchBox2DWorld:
     def rollout_dev(self, robot, targets_ptr, n_targets, steps_per_target):
         robot = self.model.object_index(robot) if isinstance(robot, str) else robot
         _check(lib().b2g_batch_rollout_dev(self.h, robot, C.c_void_p(targets_ptr), int(n_targets), int(steps_per_target)))
+
+    def check_collision_dev(self, counts_ptr, io_ptr=None, fo_ptr=None, max_per_world=0):
+        _check(lib().b2g_batch_check_collision_dev(self.h, C.c_void_p(counts_ptr), C.c_void_p(io_ptr) if io_ptr else None,
+                                                   C.c_void_p(fo_ptr) if fo_ptr else None, int(max_per_world)))
 
     def stream(self):
         return lib().b2g_batch_stream(self.h)

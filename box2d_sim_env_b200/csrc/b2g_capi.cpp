@@ -572,6 +572,14 @@ b2g_status b2g_batch_get_contacts(b2g_batch* b, int32_t* counts, int32_t* iout, 
     return B2G_OK;
 }
 
+b2g_status b2g_batch_check_collision_dev(b2g_batch* b, int32_t* counts, int32_t* iout, float* fout, int max_per_world) {
+    if (!b || !counts || max_per_world < 0) return fail(B2G_ERR_INVALID, "bad arguments");
+    if (!iout || !fout) max_per_world = 0;
+    CU(cudaSetDevice(b->device));
+    CU(launchCheckCollision(b->L(), counts, iout, fout, max_per_world));
+    return B2G_OK;
+}
+
 b2g_status b2g_batch_check_collision(b2g_batch* b, int32_t* counts, int32_t* iout, float* fout, int max_per_world) {
     if (!b || !counts || !iout || !fout || max_per_world <= 0) return fail(B2G_ERR_INVALID, "bad arguments");
     CU(cudaSetDevice(b->device));

@@ -6,6 +6,8 @@
 // (/root/reference/CMakeLists.txt:54-59: -O3, no -march, no fast-math).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "b2g_launch.h"
 #include "b2g_world.cuh"
 
@@ -20,6 +22,12 @@ namespace b2g {
         for (int i = threadIdx.x; i < hw; i += blockDim.x) g_sm[i] = hsrc[i];                   \
         for (int i = threadIdx.x; i < pw; i += blockDim.x) g_sm[hw + i] = psrc[i];              \
         for (int i = threadIdx.x; i < hdr.words; i += blockDim.x) g_sm[kHdrWords + i] = blob[i]; \
+    }                                                                                           \
+    __syncthreads();                                                                            \
+    for (int j = threadIdx.x; j < hdr.nj; j += blockDim.x) { /* dt-dependent joint constants */ \
+        uint32_t* jr = g_sm + kHdrWords + hdr.oJoint + j * MJ_STRIDE;                           \
+        jr[MJ_HMAXFORCE] = __float_as_uint(prm.dt * __uint_as_float(jr[MJ_MAXFORCE]));          \
+        jr[MJ_HMAXTORQUE] = __float_as_uint(prm.dt * __uint_as_float(jr[MJ_MAXTORQUE]));        \
     }                                                                                           \
     __syncthreads();                                                                            \
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;                       \
@@ -276,7 +284,15 @@ __global__ void k_status(float* S, long long N, int stateChunks, int statusOff, 
 static unsigned long long g_launches = 0;
 unsigned long long launchCount() { return g_launches; }
 
-static inline size_t smemBytes(const ModelHeader& h) { return (size_t)kHdrWords * 4 + (size_t)h.words * 4; }
+static size_t smemPad() {  // tuning knob: extra dynamic shared memory per CTA throttles occupancy (B2G_SMEM_PAD bytes)
+    static long pad = -1;
+    if (pad < 0) {
+        const char* e = getenv("B2G_SMEM_PAD");
+        pad = e ? atol(e) : 0;
+    }
+    return (size_t)pad;
+}
+static inline size_t smemBytes(const ModelHeader& h) { return (size_t)kHdrWords * 4 + (size_t)h.words * 4 + smemPad(); }
 
 static cudaError_t prepare(const void* fn, const ModelHeader& h) {
     size_t bytes = smemBytes(h);

@@ -42,25 +42,60 @@ DEV float invMass(Ctx c, int b) { return mF(c, mbody(c, b, MB_INVMASS)); }
 DEV float invI(Ctx c, int b) { return mF(c, mbody(c, b, MB_INVI)); }
 
 // =================================================================================================== joints
+// Every joint has a 128-byte solver record in the model blob (model.h: JointField) with precomputed state byte
+// offsets, anchor arms and inverse masses, so a solve is LDS.128 broadcasts + LDG.128/STG.128 on the state.
+struct JointRec {
+    int base;  // word offset of the record in the blob
+};
+DEV JointRec jrec(Ctx c, int j) { JointRec r; r.base = mjoint(c, j, 0); return r; }
+DEV int4 mi4(Ctx, int off) { return *reinterpret_cast<const int4*>(g_sm + kHdrWords + off); }
+DEV Vel ldVelAt(Ctx c, int boff) {
+    float4 q = ld4(c, boff + SB_VEL4);
+    Vel r;
+    r.v = mk(q.x, q.y);
+    r.w = q.z;
+    r.keep = q.w;
+    return r;
+}
+DEV void stVelAt(Ctx c, int boff, const Vel& r) { st4(c, boff + SB_VEL4, mk4(r.v.x, r.v.y, r.w, r.keep)); }
+DEV Pos ldPosAt(Ctx c, int boff) {
+    float4 q = ld4(c, boff + SB_POS4);
+    Pos r;
+    r.c = mk(q.x, q.y);
+    r.a = q.z;
+    r.keep = q.w;
+    return r;
+}
+DEV void stPosAt(Ctx c, int boff, const Pos& r) { st4(c, boff + SB_POS4, mk4(r.c.x, r.c.y, r.a, r.keep)); }
+// A static body never moves: b2Island copies v = w = +0 for it and every solver update is x -= 0 * impulse, which
+// leaves +0 for any finite impulse.  Its velocity is therefore neither loaded nor stored.
+DEV Vel zeroVel() {
+    Vel r;
+    r.v = mk(0.0f, 0.0f);
+    r.w = 0.0f;
+    r.keep = 0.0f;
+    return r;
+}
+
 // b2FrictionJoint / b2RevoluteJoint::InitVelocityConstraints
 DEVN void jointInit(Ctx c, int j, float dtRatio) {
-    const int4 jh = *reinterpret_cast<const int4*>(g_sm + kHdrWords + mjoint(c, j, MJ_TYPE));  // type bodyA bodyB flags
-    const int type = jh.x, bA = jh.y, bB = jh.z;
-    const float4 anchors = m4(c, mjoint(c, j, MJ_LAX));
-    const float4 bmA = m4(c, mbody(c, bA, MB_INVMASS));  // invMass invI lc.x lc.y
-    const float4 bmB = m4(c, mbody(c, bB, MB_INVMASS));
-    float aA = ldF(c, bslot(c, bA, SB_A));
-    float aB = ldF(c, bslot(c, bB, SB_A));
-    Vel A = ldVel(c, bA);
-    Vel B = ldVel(c, bB);
+    const int jr = mjoint(c, j, 0);
+    const int4 jh = mi4(c, jr + MJ_TYPE);     // type bodyA bodyB flags
+    const int4 off = mi4(c, jr + MJ_SOFF);    // js jw bodyA bodyB (state byte offsets)
+    const float4 arm = m4(c, jr + MJ_RA0X);   // localAnchorA - localCenterA, localAnchorB - localCenterB
+    const float4 im = m4(c, jr + MJ_MA);      // mA iA mB iB
+    const int type = jh.x;
+    const bool staticA = (jh.w & 4) != 0, staticB = (jh.w & 8) != 0;
+    const int js = off.x, jw = off.y;
+    float aA = ldF(c, off.z + SB_A);
+    float aB = ldF(c, off.w + SB_A);
+    Vel A = staticA ? zeroVel() : ldVelAt(c, off.z);
+    Vel B = staticB ? zeroVel() : ldVelAt(c, off.w);
     Rot qA = rotOf(aA), qB = rotOf(aB);
-    V2 la = mk(anchors.x, anchors.y);
-    V2 lb = mk(anchors.z, anchors.w);
-    V2 rA = mul(qA, la - mk(bmA.z, bmA.w));
-    V2 rB = mul(qB, lb - mk(bmB.z, bmB.w));
-    float mA = bmA.x, mB = bmB.x;
-    float iA = bmA.y, iB = bmB.y;
-    const int jw = jwslot(c, j, 0), js = jslot(c, j, 0);
+    V2 rA = mul(qA, mk(arm.x, arm.y));
+    V2 rB = mul(qB, mk(arm.z, arm.w));
+    float mA = im.x, mB = im.z;
+    float iA = im.y, iB = im.w;
     st4(c, jw + WJ_R4, mk4(rA.x, rA.y, rB.x, rB.y));
 
     if (type == 0) {
@@ -108,7 +143,7 @@ DEVN void jointInit(Ctx c, int j, float dtRatio) {
         imp.x = si.x; imp.y = si.y; imp.z = si.z;
         if (enableMotor == false || fixedRotation) motorImpulse = 0.0f;
         if (enableLimit && fixedRotation == false) {
-            const float4 lim = m4(c, mjoint(c, j, MJ_REF));  // ref lower upper maxForce
+            const float4 lim = m4(c, jr + MJ_REF);  // ref lower upper maxForce
             float lower = lim.y, upper = lim.z;
             float jointAngle = aB - aA - lim.x;
             if (absT(upper - lower) < 2.0f * B2G_ANGULAR_SLOP) {
@@ -138,33 +173,32 @@ DEVN void jointInit(Ctx c, int j, float dtRatio) {
         B.v = B.v + mB * P;
         B.w += iB * (cross(rB, P) + motorImpulse + imp.z);
     }
-    stVel(c, bA, A);
-    stVel(c, bB, B);
+    if (!staticA) stVelAt(c, off.z, A);
+    if (!staticB) stVelAt(c, off.w, B);
 }
 
-// b2FrictionJoint::SolveVelocityConstraints
-DEV void frictionSolveVel(Ctx c, int j, int bA, int bB) {
-    const float4 bmA = m4(c, mbody(c, bA, MB_INVMASS));
-    const float4 bmB = m4(c, mbody(c, bB, MB_INVMASS));
-    const float2 maxFT = m2(c, mjoint(c, j, MJ_UPPER));  // (upper,) maxForce at +1 ; maxTorque follows in the next group
-    const float maxForce = maxFT.y;
-    const float maxTorque = mF(c, mjoint(c, j, MJ_MAXTORQUE));
-    Vel A = ldVel(c, bA);
-    Vel B = ldVel(c, bB);
-    float mA = bmA.x, mB = bmB.x;
-    float iA = bmA.y, iB = bmB.y;
-    const int jw = jwslot(c, j, 0), js = jslot(c, j, 0);
+// b2FrictionJoint::SolveVelocityConstraints.  STATIC_A: bodyA is static (the ground for every link's friction
+// joint, Box2DWorld.cpp:134-147) -- its velocity is the constant +0 and all of its updates are dead code.
+template <bool STATIC_A>
+DEV void frictionSolveVel(Ctx c, int jr) {
+    const int4 off = mi4(c, jr + MJ_SOFF);     // js jw bodyA bodyB
+    const float4 im = m4(c, jr + MJ_MA);       // mA iA mB iB
+    const float2 hmax = m2(c, jr + MJ_HMAXFORCE);  // dt * maxForce, dt * maxTorque
+    const int js = off.x, jw = off.y;
+    Vel A = STATIC_A ? zeroVel() : ldVelAt(c, off.z);
+    Vel B = ldVelAt(c, off.w);
+    float mA = im.x, mB = im.z;
+    float iA = im.y, iB = im.w;
     const float4 r = ld4(c, jw + WJ_R4);
     const float4 lm = ld4(c, jw + WJ_M0);
     float4 acc4 = ld4(c, js + SJ_IMPULSE4);  // linearImpulse.xy angularImpulse angularMass
     V2 rA = mk(r.x, r.y);
     V2 rB = mk(r.z, r.w);
-    float h = PRM().dt;
     {
         float Cdot = B.w - A.w;
         float impulse = -acc4.w * Cdot;
         float oldImpulse = acc4.z;
-        float maxImpulse = h * maxTorque;
+        float maxImpulse = hmax.y;
         float acc = clampT(oldImpulse + impulse, -maxImpulse, maxImpulse);
         acc4.z = acc;
         impulse = acc - oldImpulse;
@@ -178,7 +212,7 @@ DEV void frictionSolveVel(Ctx c, int j, int bA, int bB) {
         V2 impulse = -mk(exx * Cdot.x + eyx * Cdot.y, exy * Cdot.x + eyy * Cdot.y);
         V2 oldImpulse = mk(acc4.x, acc4.y);
         V2 acc = oldImpulse + impulse;
-        float maxImpulse = h * maxForce;
+        float maxImpulse = hmax.x;
         if (dot(acc, acc) > maxImpulse * maxImpulse) {
             normalize(acc);
             acc = mk(acc.x * maxImpulse, acc.y * maxImpulse);
@@ -192,8 +226,8 @@ DEV void frictionSolveVel(Ctx c, int j, int bA, int bB) {
         B.w += iB * cross(rB, impulse);
     }
     st4(c, js + SJ_IMPULSE4, acc4);
-    stVel(c, bA, A);
-    stVel(c, bB, B);
+    if (!STATIC_A) stVelAt(c, off.z, A);
+    stVelAt(c, off.w, B);
 }
 
 DEV V3 solve33(const float* m, V3 b) {  // m = ex.xyz ey.xyz ez.xyz ; b2Mat33::Solve33
@@ -211,14 +245,15 @@ DEV V3 solve33(const float* m, V3 b) {  // m = ex.xyz ey.xyz ez.xyz ; b2Mat33::S
 }
 
 // b2RevoluteJoint::SolveVelocityConstraints
-DEV void revoluteSolveVel(Ctx c, int j, int bA, int bB, int modelFlags) {
-    const float4 bmA = m4(c, mbody(c, bA, MB_INVMASS));
-    const float4 bmB = m4(c, mbody(c, bB, MB_INVMASS));
-    Vel A = ldVel(c, bA);
-    Vel B = ldVel(c, bB);
-    float mA = bmA.x, mB = bmB.x;
-    float iA = bmA.y, iB = bmB.y;
-    const int jw = jwslot(c, j, 0), js = jslot(c, j, 0);
+DEV void revoluteSolveVel(Ctx c, int jr, int modelFlags) {
+    const int4 off = mi4(c, jr + MJ_SOFF);  // js jw bodyA bodyB
+    const float4 im = m4(c, jr + MJ_MA);    // mA iA mB iB
+    const int js = off.x, jw = off.y;
+    const bool staticA = (modelFlags & 4) != 0, staticB = (modelFlags & 8) != 0;
+    Vel A = staticA ? zeroVel() : ldVelAt(c, off.z);
+    Vel B = staticB ? zeroVel() : ldVelAt(c, off.w);
+    float mA = im.x, mB = im.z;
+    float iA = im.y, iB = im.w;
     const float4 r = ld4(c, jw + WJ_R4);
     const float4 k0 = ld4(c, jw + WJ_M0);     // ex.x ex.y(=ey.x) ey.y -
     const float4 mot = ld4(c, js + SJ_MOTOR4);  // flags maxMotorTorque motorSpeed motorMass
@@ -287,29 +322,28 @@ DEV void revoluteSolveVel(Ctx c, int j, int bA, int bB, int modelFlags) {
         B.w += iB * cross(rB, impulse);
     }
     st4(c, js + SJ_IMPULSE4, imp4);
-    stVel(c, bA, A);
-    stVel(c, bB, B);
+    if (!staticA) stVelAt(c, off.z, A);
+    if (!staticB) stVelAt(c, off.w, B);
 }
 
 // b2RevoluteJoint::SolvePositionConstraints (friction joints have none and report true)
-DEV bool revoluteSolvePos(Ctx c, int j) {
-    const int4 jh = *reinterpret_cast<const int4*>(g_sm + kHdrWords + mjoint(c, j, MJ_TYPE));
-    const int bA = jh.y, bB = jh.z;
-    const float4 bmA = m4(c, mbody(c, bA, MB_INVMASS));
-    const float4 bmB = m4(c, mbody(c, bB, MB_INVMASS));
-    Pos A = ldPos(c, bA);
-    Pos B = ldPos(c, bB);
-    float mA = bmA.x, mB = bmB.x;
-    float iA = bmA.y, iB = bmB.y;
-    const float4 mot = ld4(c, jslot(c, j, SJ_MOTOR4));
+DEV bool revoluteSolvePos(Ctx c, int jr, int modelFlags) {
+    const int4 off = mi4(c, jr + MJ_SOFF);  // js jw bodyA bodyB
+    const float4 im = m4(c, jr + MJ_MA);    // mA iA mB iB
+    const float4 arm = m4(c, jr + MJ_RA0X);
+    Pos A = ldPosAt(c, off.z);
+    Pos B = ldPosAt(c, off.w);
+    float mA = im.x, mB = im.z;
+    float iA = im.y, iB = im.w;
+    const float4 mot = ld4(c, off.x + SJ_MOTOR4);
     int limitState = __float_as_int(mot.x) & 3;
-    bool enableLimit = (jh.w & 1) != 0;
+    bool enableLimit = (modelFlags & 1) != 0;
     float angularError = 0.0f;
     float positionError = 0.0f;
     bool fixedRotation = (iA + iB == 0.0f);
     if (enableLimit && limitState != 0 && fixedRotation == false) {
         float motorMass = mot.w;
-        const float4 lim = m4(c, mjoint(c, j, MJ_REF));
+        const float4 lim = m4(c, jr + MJ_REF);
         float lower = lim.y, upper = lim.z;
         float angle = B.a - A.a - lim.x;
         float limitImpulse = 0.0f;
@@ -333,11 +367,8 @@ DEV bool revoluteSolvePos(Ctx c, int j) {
     }
     {
         Rot qA = rotOf(A.a), qB = rotOf(B.a);
-        const float4 anchors = m4(c, mjoint(c, j, MJ_LAX));
-        V2 la = mk(anchors.x, anchors.y);
-        V2 lb = mk(anchors.z, anchors.w);
-        V2 rA = mul(qA, la - mk(bmA.z, bmA.w));
-        V2 rB = mul(qB, lb - mk(bmB.z, bmB.w));
+        V2 rA = mul(qA, mk(arm.x, arm.y));
+        V2 rB = mul(qB, mk(arm.z, arm.w));
         V2 C = B.c + rB - A.c - rA;
         positionError = length(C);
         float kxx = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
@@ -350,8 +381,8 @@ DEV bool revoluteSolvePos(Ctx c, int j) {
         B.c = B.c + mB * impulse;
         B.a += iB * cross(rB, impulse);
     }
-    stPos(c, bA, A);
-    stPos(c, bB, B);
+    stPosAt(c, off.z, A);
+    stPosAt(c, off.w, B);
     return positionError <= B2G_LINEAR_SLOP && angularError <= B2G_ANGULAR_SLOP;
 }
 
@@ -742,10 +773,14 @@ DEVN void islandSolve(Ctx c, const Island& isl, float dtRatio, bool allowSleep) 
     const int velIters = PRM().velIters, posIters = PRM().posIters;
     for (int it = 0; it < velIters; ++it) {
         for (int i = 0; i < isl.nj; ++i) {
-            int j = isl.joints[i];
-            const int4 jh = *reinterpret_cast<const int4*>(g_sm + kHdrWords + mjoint(c, j, MJ_TYPE));  // type bodyA bodyB flags
-            if (jh.x == 0) frictionSolveVel(c, j, jh.y, jh.z);
-            else revoluteSolveVel(c, j, jh.y, jh.z, jh.w);
+            const int jr = mjoint(c, isl.joints[i], 0);
+            const int4 jh = mi4(c, jr + MJ_TYPE);  // type bodyA bodyB flags
+            if (jh.x == 0) {
+                if (jh.w & 4) frictionSolveVel<true>(c, jr);
+                else frictionSolveVel<false>(c, jr);
+            } else {
+                revoluteSolveVel(c, jr, jh.w);
+            }
         }
         for (int i = 0; i < isl.nc; ++i) contactSolveVel(c, isl.contacts[i]);
     }
@@ -760,9 +795,10 @@ DEVN void islandSolve(Ctx c, const Island& isl, float dtRatio, bool allowSleep) 
         bool contactsOkay = minSeparation >= -3.0f * B2G_LINEAR_SLOP;
         bool jointsOkay = true;
         for (int i = 0; i < isl.nj; ++i) {
-            int j = isl.joints[i];
+            const int jr = mjoint(c, isl.joints[i], 0);
+            const int4 jh = mi4(c, jr + MJ_TYPE);
             bool ok = true;
-            if (mI(c, mjoint(c, j, MJ_TYPE)) == 1) ok = revoluteSolvePos(c, j);
+            if (jh.x == 1) ok = revoluteSolvePos(c, jr, jh.w);
             jointsOkay = jointsOkay && ok;
         }
         if (contactsOkay && jointsOkay) {

@@ -29,6 +29,8 @@ enum BodyField {  // per body; 16-byte groups are read with one LDS.128
     MB_FIX_COUNT,
     MB_COLLIDE_LO, MB_COLLIDE_HI,  // bit b: b2Body::ShouldCollide(this, b)
     MB_PX, MB_PY,  // creation position (non-zero for the ground body only)
+    MB_SOFF,       // byte offset of this body's first state chunk (see the per-world state below)
+    MB_SPARE1, MB_SPARE2, MB_SPARE3,
     MB_STRIDE
 };
 enum FixtureField {  // per fixture / broad-phase proxy (creation order == proxy id order)
@@ -43,13 +45,19 @@ enum FixtureField {  // per fixture / broad-phase proxy (creation order == proxy
 enum JointField {
     MJ_TYPE = 0,  // 0 friction, 1 revolute
     MJ_BODYA, MJ_BODYB,
-    MJ_FLAGS,     // bit0 enableLimit, bit1 enableMotor at creation
+    MJ_FLAGS,     // bit0 enableLimit, bit1 enableMotor at creation, bit2 bodyA is static, bit3 bodyB is static
     MJ_LAX, MJ_LAY, MJ_LBX, MJ_LBY,
     MJ_REF, MJ_LOWER, MJ_UPPER, MJ_MAXFORCE,
     MJ_MAXTORQUE,
     MJ_DOF,       // index in the world state vector (revolute joints of objects), -1 otherwise
     MJ_OBJECT,
     MJ_SPARE,
+    // solver record: everything the velocity / position sweeps need, 16-byte groups, no dependent look-ups
+    MJ_SOFF, MJ_WOFF, MJ_BAOFF, MJ_BBOFF,  // byte offsets into the per-world state: joint state, joint scratch, bodyA, bodyB
+    MJ_RA0X, MJ_RA0Y, MJ_RB0X, MJ_RB0Y,    // localAnchorA - localCenterA, localAnchorB - localCenterB
+    MJ_HMAXFORCE, MJ_HMAXTORQUE,           // dt * maxForce, dt * maxTorque: written by the kernel prologue (depends on dt)
+    MJ_SPARE2, MJ_SPARE3,
+    MJ_MA, MJ_IA, MJ_MB, MJ_IB,            // invMass / invI of bodyA and bodyB
     MJ_STRIDE
 };
 enum ObjectField {

@@ -552,6 +552,7 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
         w[MB_FIX_START] = bd.fixStart; w[MB_FIX_COUNT] = bd.fixCount; w[MB_OBJECT] = (uint32_t)bd.object;
         w[MB_COLLIDE_LO] = (uint32_t)(collide[b] & 0xffffffffull); w[MB_COLLIDE_HI] = (uint32_t)(collide[b] >> 32);
         w[MB_PX] = fbits(bd.px); w[MB_PY] = fbits(bd.py);
+        w[MB_SOFF] = (uint32_t)(b * SB_CHUNKS * kChunkBytes);  // layoutState puts the bodies first (cBody == 0)
     }
     align4();
     h.oFix = allocWords(nf * MF_STRIDE);
@@ -593,6 +594,19 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
         w[MJ_REF] = fbits(jt.ref); w[MJ_LOWER] = fbits(jt.lower); w[MJ_UPPER] = fbits(jt.upper);
         w[MJ_MAXFORCE] = fbits(jt.maxForce); w[MJ_MAXTORQUE] = fbits(jt.maxTorque);
         w[MJ_DOF] = (uint32_t)jt.dof; w[MJ_OBJECT] = (uint32_t)jt.object;
+        const BBody& A = bodies[jt.bodyA];
+        const BBody& Bd = bodies[jt.bodyB];
+        if (A.type == 0) w[MJ_FLAGS] |= 4u;
+        if (Bd.type == 0) w[MJ_FLAGS] |= 8u;
+        // state offsets: bodies, fixtures, joint state, joint scratch come first in layoutState and do not depend on maxc
+        const int cJoint = nb * SB_CHUNKS + nf, cJointW = cJoint + nj * SJ_CHUNKS;
+        w[MJ_SOFF] = (uint32_t)((cJoint + j * SJ_CHUNKS) * kChunkBytes);
+        w[MJ_WOFF] = (uint32_t)((cJointW + j * WJ_CHUNKS) * kChunkBytes);
+        w[MJ_BAOFF] = (uint32_t)(jt.bodyA * SB_CHUNKS * kChunkBytes);
+        w[MJ_BBOFF] = (uint32_t)(jt.bodyB * SB_CHUNKS * kChunkBytes);
+        w[MJ_RA0X] = fbits(jt.lax - A.lcx); w[MJ_RA0Y] = fbits(jt.lay - A.lcy);
+        w[MJ_RB0X] = fbits(jt.lbx - Bd.lcx); w[MJ_RB0Y] = fbits(jt.lby - Bd.lcy);
+        w[MJ_MA] = fbits(A.invMass); w[MJ_IA] = fbits(A.invI); w[MJ_MB] = fbits(Bd.invMass); w[MJ_IB] = fbits(Bd.invI);
     }
     // links / chains / object joints / name order / init
     h.oLink = allocWords(0);

@@ -165,6 +165,8 @@ b2g_status b2g_batch_get_contacts(b2g_batch* batch, int32_t* counts, int32_t* io
  * bodyB fixtureA fixtureB; fout [n_worlds][max][6] = contact_point(3) contact_normal(3), both multiplied by
  * 1/scale exactly as the reference does (:2857-2862). */
 b2g_status b2g_batch_check_collision(b2g_batch* batch, int32_t* counts, int32_t* iout, float* fout, int max_per_world);
+/* same with device pointers, asynchronous on the batch's stream; iout / fout may be NULL to get the counts only */
+b2g_status b2g_batch_check_collision_dev(b2g_batch* batch, int32_t* counts, int32_t* iout, float* fout, int max_per_world);
 
 /* saveState / restoreState / dropState (:3515-3541): a stack of world states (q, qd and static poses) */
 b2g_status b2g_batch_save_state(b2g_batch* batch);

@@ -207,3 +207,53 @@ def test_error_behaviour(b2g):
         batch.setWorldState(np.zeros((4, 3)), np.zeros((4, 3)))      # reference: std::runtime_error (:1700-1704)
     with pytest.raises(b2g.B2GError):
         batch.setTargetVelocity("obj1", np.zeros((4, 3)))            # only robots have a velocity controller
+
+
+def test_clutter_shape_c_parity(b2g):
+    """Shape C (BASELINE.json configs[3]): robot + 32 convex polygons, 38 bodies / 39 proxies / 41 joints per world.
+    Dense sliding clutter: many simultaneous contacts, multi-body islands, contact creation/destruction order."""
+    from box2d_sim_env_b200 import envgen
+    n = 24
+    env = envgen.clutter_env()
+    batch = b2g.BatchBox2DWorld(n).loadWorld(b2g.Model(env))
+    worlds = oracle_worlds(env, n)
+    assert_same(batch, worlds, "fresh clutter world")
+    q, qd = envgen.clutter_states(n, seed=5, speed=3.0)
+    tg = random_targets(batch.model, 0, n, seed=6, segments=6)
+    batch.setWorldState(q, qd, reset_caches=True)
+    for w, ow in enumerate(worlds):
+        ow.set_state(q[w], qd[w])
+    touching = 0
+    for seg in range(6):
+        batch.setTargetVelocity(0, tg[seg])
+        batch.stepPhysics(10)
+        for w, ow in enumerate(worlds):
+            ow.set_target_velocity(0, tg[seg][w])
+            ow.step(10)
+        assert_same(batch, worlds, "clutter segment %d" % seg)
+        counts, cio, _ = batch.contacts(max_per_world=80)
+        touching += int(cio[..., 2].sum())
+    assert touching > 30, "clutter scenario produced too few touching contacts"
+    assert np.all(batch.status() == 0)
+    # batched checkCollision on the same worlds
+    counts, io, fo = batch.checkCollision(max_per_world=80)
+    for w, ow in enumerate(worlds):
+        oio, ofo = ow.check_collision()
+        assert counts[w] == len(oio) and np.array_equal(io[w, :len(oio)], oio) and np.array_equal(fo[w, :len(oio)], ofo)
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 95])
+def test_ragged_batch_sizes(b2g, n):
+    """Batch sizes that do not fill the last 32-world tile: the padding lanes must never be touched or read."""
+    batch = make_batch(b2g, ENV_A, n)
+    worlds = oracle_worlds(load_env_dict(ENV_A), n)
+    q, qd = random_states(batch.model, n, seed=61, spread=0.6)
+    tg = random_targets(batch.model, 0, n, seed=62)[0]
+    batch.setWorldState(q, qd, reset_caches=True)
+    batch.setTargetVelocity(0, tg)
+    batch.stepPhysics(15)
+    for w, ow in enumerate(worlds):
+        ow.set_state(q[w], qd[w])
+        ow.set_target_velocity(0, tg[w])
+        ow.step(15)
+    assert_same(batch, worlds, "ragged batch n=%d" % n)

@@ -1,18 +1,22 @@
-"""Small fixed case for ncu: one rollout launch of `steps` physics steps on n worlds."""
+"""Fixed case for ncu: the bench rollout (set_state, then ONE k_step launch of 10 targets x 10 steps) on n worlds."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
+import torch
 import box2d_sim_env_b200 as b2g
 import bench
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
-steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-model = b2g.Model(b2g.data_path("test_env.yaml"))
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+env = sys.argv[3] if len(sys.argv) > 3 else "test_env.yaml"
+model = b2g.Model(b2g.data_path(env))
 batch = b2g.BatchBox2DWorld(n).loadWorld(model)
 q, qd, tg = bench.synth_inputs(model.dof_limits(), n, 1)
+d_tg = torch.from_numpy(tg).cuda()
 for r in range(reps):
     batch.setWorldState(q, qd, reset_caches=True)
-    batch.setTargetVelocity(0, tg[0])
-    batch.stepPhysics(steps)
-ms, nl = batch.take_kernel_ms()
-print("n=%d steps=%d: %.3f ms per launch -> %.3e world-steps/s" % (n, steps, ms / nl, n * steps * nl / (ms * 1e-3)))
+    batch.take_kernel_ms()
+    batch.rollout_dev(0, d_tg.data_ptr(), bench.N_TARGETS, bench.STEPS_PER_TARGET)
+    ms, nl = batch.take_kernel_ms()
+counts, cio, _ = batch.contacts()
+print("n=%d: %.3f ms per 100-step rollout launch -> %.3e world-steps/s; live contacts/world %.2f touching %.2f" %
+      (n, ms / nl, n * 100 * nl / (ms * 1e-3), counts.mean(), cio[..., 2].sum() / n))
