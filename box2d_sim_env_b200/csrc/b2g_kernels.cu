@@ -14,7 +14,7 @@
 namespace b2g {
 
 // Stage header + blob into shared memory and build the per-thread context.
-#define B2G_PROLOGUE()                                                                          \
+#define B2G_STAGE()                                                                             \
     {                                                                                           \
         const uint32_t* hsrc = reinterpret_cast<const uint32_t*>(&hdr);                         \
         const uint32_t* psrc = reinterpret_cast<const uint32_t*>(&prm);                         \
@@ -29,7 +29,10 @@ namespace b2g {
         jr[MJ_HMAXFORCE] = __float_as_uint(prm.dt * __uint_as_float(jr[MJ_MAXFORCE]));          \
         jr[MJ_HMAXTORQUE] = __float_as_uint(prm.dt * __uint_as_float(jr[MJ_MAXTORQUE]));        \
     }                                                                                           \
-    __syncthreads();                                                                            \
+    __syncthreads();
+
+#define B2G_PROLOGUE()                                                                          \
+    B2G_STAGE()                                                                                 \
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;                       \
     if (w >= N) return;                                                                         \
     Ctx c;                                                                                      \

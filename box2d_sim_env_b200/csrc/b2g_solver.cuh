@@ -716,11 +716,22 @@ DEVN float contactSolvePos(Ctx c, int k, int toiA, int toiB, float minSeparation
 }
 
 // ================================================================================================== islands
-struct Island {
-    unsigned char bodies[kMaxBodies];
-    unsigned char joints[kMaxJoints];
+// b2World::Solve builds one island at a time and solves it before looking for the next seed.  Islands never share
+// a dynamic body, static bodies are never modified by the solver, and solving an island cannot change which bodies
+// a later DFS reaches (connectivity = joints + touching contacts, both fixed during Solve), so here ALL islands of
+// the world are built first (same seeds, same DFS, same per-island order) and then solved together phase by phase
+// over the concatenated constraint lists.  Per-island semantics that remain are carried by an island id per body:
+// the early exit of the position iterations and the sleep decision.  Why: with one world per thread, 32 worlds
+// whose islands differ (sleeping objects, merged islands) would otherwise serialise island by island; over flat
+// lists every lane just walks its own list and the warp stays converged.
+struct WorldLists {
+    unsigned char dyn[kMaxBodies];       // dynamic bodies in island order (each belongs to exactly one island)
+    unsigned char bodyIsl[kMaxBodies];   // island id per body (static bodies: the LAST island that contained them)
+    unsigned char joints[kMaxJoints];    // joints, island by island, each island in DFS order
     unsigned char contacts[kMaxContacts];
-    int nb, nj, nc;
+    unsigned char cA[kMaxContacts], cB[kMaxContacts];  // bodies of every live contact slot
+    unsigned char jStart[kMaxBodies + 1], cStart[kMaxBodies + 1];  // first joint / contact of every island
+    int ndyn, nj, nc, nIslands;
 };
 
 // integrate positions with the translation / rotation caps (b2Island::Solve step 6, also SolveTOI)
@@ -743,131 +754,61 @@ DEV void integratePosition(Ctx c, int b, float h) {
     stVel(c, b, V);
 }
 
-// b2Island::Solve
-DEVN void islandSolve(Ctx c, const Island& isl, float dtRatio, bool allowSleep) {
-    float h = PRM().dt;
-    for (int i = 0; i < isl.nb; ++i) {
-        int b = isl.bodies[i];
-        Pos P = ldPos(c, b);
-        stV2(c, bslot(c, b, SB_C0X), P.c);
-        stF(c, bslot(c, b, SB_A0), P.a);
-        if (bodyType(c, b) == 2) {
-            Vel V = ldVel(c, b);
-            V2 f = ldV2(c, bslot(c, b, SB_FX));
-            float tq = ldF(c, bslot(c, b, SB_TORQUE));
-            float im = invMass(c, b), ii = invI(c, b);
-            // gravity is (0,0), gravityScale 1, damping 0 (Box2DWorld.cpp:3668; b2BodyDef defaults)
-            V2 acc = 1.0f * mk(0.0f, 0.0f) + im * f;
-            V.v = V.v + h * acc;
-            V.w += h * ii * tq;
-            float ld = 1.0f / (1.0f + h * 0.0f);
-            V.v = mk(V.v.x * ld, V.v.y * ld);
-            V.w *= ld;
-            stVel(c, b, V);
-        }
-    }
-    for (int i = 0; i < isl.nc; ++i) contactInit(c, isl.contacts[i], dtRatio, true);
-    for (int i = 0; i < isl.nc; ++i) contactWarmStart(c, isl.contacts[i]);
-    for (int i = 0; i < isl.nj; ++i) jointInit(c, isl.joints[i], dtRatio);
 
-    const int velIters = PRM().velIters, posIters = PRM().posIters;
-    for (int it = 0; it < velIters; ++it) {
-        for (int i = 0; i < isl.nj; ++i) {
-            const int jr = mjoint(c, isl.joints[i], 0);
-            const int4 jh = mi4(c, jr + MJ_TYPE);  // type bodyA bodyB flags
-            if (jh.x == 0) {
-                if (jh.w & 4) frictionSolveVel<true>(c, jr);
-                else frictionSolveVel<false>(c, jr);
-            } else {
-                revoluteSolveVel(c, jr, jh.w);
-            }
-        }
-        for (int i = 0; i < isl.nc; ++i) contactSolveVel(c, isl.contacts[i]);
-    }
-    for (int i = 0; i < isl.nc; ++i) contactStoreImpulses(c, isl.contacts[i]);
-
-    for (int i = 0; i < isl.nb; ++i) integratePosition(c, isl.bodies[i], h);
-
-    bool positionSolved = false;
-    for (int it = 0; it < posIters; ++it) {
-        float minSeparation = 0.0f;
-        for (int i = 0; i < isl.nc; ++i) minSeparation = contactSolvePos(c, isl.contacts[i], -1, -1, minSeparation);
-        bool contactsOkay = minSeparation >= -3.0f * B2G_LINEAR_SLOP;
-        bool jointsOkay = true;
-        for (int i = 0; i < isl.nj; ++i) {
-            const int jr = mjoint(c, isl.joints[i], 0);
-            const int4 jh = mi4(c, jr + MJ_TYPE);
-            bool ok = true;
-            if (jh.x == 1) ok = revoluteSolvePos(c, jr, jh.w);
-            jointsOkay = jointsOkay && ok;
-        }
-        if (contactsOkay && jointsOkay) {
-            positionSolved = true;
-            break;
-        }
-    }
-    for (int i = 0; i < isl.nb; ++i) syncTransform(c, isl.bodies[i]);
-
-    if (allowSleep) {
-        float minSleepTime = FLT_MAX;
-        const float linTolSqr = B2G_LINEAR_SLEEP_TOL * B2G_LINEAR_SLEEP_TOL;
-        const float angTolSqr = B2G_ANGULAR_SLEEP_TOL * B2G_ANGULAR_SLEEP_TOL;
-        for (int i = 0; i < isl.nb; ++i) {
-            int b = isl.bodies[i];
-            if (bodyType(c, b) == 0) continue;
-            Vel V = ldVel(c, b);
-            if (V.w * V.w > angTolSqr || dot(V.v, V.v) > linTolSqr) {
-                stF(c, bslot(c, b, SB_SLEEP), 0.0f);
-                minSleepTime = 0.0f;
-            } else {
-                float st = ldF(c, bslot(c, b, SB_SLEEP)) + h;
-                stF(c, bslot(c, b, SB_SLEEP), st);
-                minSleepTime = fminT(minSleepTime, st);
-            }
-        }
-        if (minSleepTime >= B2G_TIME_TO_SLEEP && positionSolved) {
-            for (int i = 0; i < isl.nb; ++i) sleepBody(c, isl.bodies[i]);
-        }
-    }
-}
-
-// b2World::Solve: islands by DFS in upstream order, then SynchronizeFixtures + FindNewContacts
+// b2World::Solve + b2Island::Solve for every island of the world, then SynchronizeFixtures + FindNewContacts
 DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
     const int nb = H().nb;
-    uint64_t bodyFlag = 0ull;
+    const float h = PRM().dt;
+    WorldLists L;
+    L.ndyn = 0; L.nj = 0; L.nc = 0; L.nIslands = 0;
+    uint64_t bodyFlag = 0ull;      // dynamic bodies that are in some island
+    uint64_t staticSeen = 0ull;    // static bodies that joined at least one island
     uint64_t jointFlag[2] = {0ull, 0ull};
     uint64_t contactFlag[2] = {0ull, 0ull};
+    uint64_t contactLive[2] = {0ull, 0ull};  // enabled && touching
+    const int ncAll = contactCount(c);
+    for (int k = 0; k < ncAll; ++k) {
+        const float4 head = ld4(c, cslot(c, k, SC_HEAD4));
+        int fx = __float_as_int(head.x), fl = __float_as_int(head.y);
+        L.cA[k] = (unsigned char)mI(c, mfix(c, fx & 0xff, MF_BODY));
+        L.cB[k] = (unsigned char)mI(c, mfix(c, (fx >> 8) & 0xff, MF_BODY));
+        if ((fl & CF_ENABLED) != 0 && (fl & CF_TOUCHING) != 0) contactLive[k >> 6] |= 1ull << (k & 63);
+    }
+
+    // ---- islands by DFS in upstream order (body list: newest first)
     unsigned char stack[kMaxBodies];
-    Island isl;
-    for (int seed = nb - 1; seed >= 0; --seed) {  // body list: newest first
+    for (int seed = nb - 1; seed >= 0; --seed) {
         if ((bodyFlag >> seed) & 1ull) continue;
-        if (!isAwake(c, seed)) continue;
         if (bodyType(c, seed) == 0) continue;
-        isl.nb = 0; isl.nj = 0; isl.nc = 0;
+        if (!isAwake(c, seed)) continue;
+        const int isl = L.nIslands++;
+        L.jStart[isl] = (unsigned char)L.nj;
+        L.cStart[isl] = (unsigned char)L.nc;
+        uint64_t staticFlag = 0ull;  // static bodies join every island that reaches them, once per island
         int sp = 0;
         stack[sp++] = (unsigned char)seed;
         bodyFlag |= 1ull << seed;
         while (sp > 0) {
             int b = stack[--sp];
-            isl.bodies[isl.nb++] = (unsigned char)b;
+            L.bodyIsl[b] = (unsigned char)isl;
+            if (bodyType(c, b) == 0) {
+                staticSeen |= 1ull << b;  // its awake flag is settled after the sleep decisions (see below)
+                continue;
+            }
+            L.dyn[L.ndyn++] = (unsigned char)b;
             wakeBody(c, b);
-            if (bodyType(c, b) == 0) continue;
             // contact edges of b, newest first
-            for (int k = contactCount(c) - 1; k >= 0; --k) {
-                int fA, fB;
-                contactFixtures(c, k, fA, fB);
-                int cA = mI(c, mfix(c, fA, MF_BODY));
-                int cB = mI(c, mfix(c, fB, MF_BODY));
+            for (int k = ncAll - 1; k >= 0; --k) {
+                int cA = L.cA[k], cB = L.cB[k];
                 if (cA != b && cB != b) continue;
                 if ((contactFlag[k >> 6] >> (k & 63)) & 1ull) continue;
-                int fl = ldI(c, cslot(c, k, SC_FLAGS));
-                if ((fl & CF_ENABLED) == 0 || (fl & CF_TOUCHING) == 0) continue;
-                isl.contacts[isl.nc++] = (unsigned char)k;
+                if (((contactLive[k >> 6] >> (k & 63)) & 1ull) == 0ull) continue;
+                L.contacts[L.nc++] = (unsigned char)k;
                 contactFlag[k >> 6] |= 1ull << (k & 63);
                 int other = cA == b ? cB : cA;
-                if ((bodyFlag >> other) & 1ull) continue;
+                if (((bodyFlag | staticFlag) >> other) & 1ull) continue;
                 stack[sp++] = (unsigned char)other;
-                bodyFlag |= 1ull << other;
+                if (bodyType(c, other) == 0) staticFlag |= 1ull << other; else bodyFlag |= 1ull << other;
             }
             // joint edges of b, newest first
             int js = H().oJEdge + mI(c, mbody(c, b, MB_JE_START));
@@ -877,23 +818,148 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
                 int j = packed & 0xffff;
                 int other = packed >> 16;
                 if ((jointFlag[j >> 6] >> (j & 63)) & 1ull) continue;
-                isl.joints[isl.nj++] = (unsigned char)j;
+                L.joints[L.nj++] = (unsigned char)j;
                 jointFlag[j >> 6] |= 1ull << (j & 63);
-                if ((bodyFlag >> other) & 1ull) continue;
+                if (((bodyFlag | staticFlag) >> other) & 1ull) continue;
                 stack[sp++] = (unsigned char)other;
-                bodyFlag |= 1ull << other;
+                if (bodyType(c, other) == 0) staticFlag |= 1ull << other; else bodyFlag |= 1ull << other;
             }
         }
-        islandSolve(c, isl, dtRatio, allowSleep);
-        for (int i = 0; i < isl.nb; ++i) {
-            int b = isl.bodies[i];
-            if (bodyType(c, b) == 0) bodyFlag &= ~(1ull << b);
-        }
     }
+
+    // The order of islands inside the flat lists is free (they are independent).  Upstream finds them newest body
+    // first, which puts the free objects before the robot; emitting them in the opposite order keeps the lanes of
+    // a warp aligned on the robot's joints (same model, same DFS) and leaves the part that differs from world to
+    // world (which objects are awake) at the tail, where every entry has the same type.
+    if (L.nIslands > 1) {
+        unsigned char tmp[kMaxJoints];
+        L.jStart[L.nIslands] = (unsigned char)L.nj;
+        L.cStart[L.nIslands] = (unsigned char)L.nc;
+        int n = 0;
+        for (int isl = L.nIslands - 1; isl >= 0; --isl)
+            for (int i = L.jStart[isl]; i < L.jStart[isl + 1]; ++i) tmp[n++] = L.joints[i];
+        for (int i = 0; i < n; ++i) L.joints[i] = tmp[i];
+        n = 0;
+        for (int isl = L.nIslands - 1; isl >= 0; --isl)
+            for (int i = L.cStart[isl]; i < L.cStart[isl + 1]; ++i) tmp[n++] = L.contacts[i];
+        for (int i = 0; i < n; ++i) L.contacts[i] = tmp[i];
+    }
+
+    // ---- b2Island::Solve, all islands together
+    for (int i = 0; i < L.ndyn; ++i) {  // c0 = c, integrate velocities
+        const int bo = bslot(c, L.dyn[i], 0);
+        const float4 bm = m4(c, mbody(c, L.dyn[i], MB_INVMASS));
+        Pos P = ldPosAt(c, bo);
+        stV2(c, bo + SB_C0X, P.c);
+        stF(c, bo + SB_A0, P.a);
+        Vel V = ldVelAt(c, bo);
+        const float4 ft = ld4(c, bo + SB_FORCE4);
+        V2 f = mk(ft.x, ft.y);
+        float tq = ft.z;
+        float im = bm.x, ii = bm.y;
+        // gravity is (0,0), gravityScale 1, damping 0 (Box2DWorld.cpp:3668; b2BodyDef defaults)
+        V2 acc = 1.0f * mk(0.0f, 0.0f) + im * f;
+        V.v = V.v + h * acc;
+        V.w += h * ii * tq;
+        float ld = 1.0f / (1.0f + h * 0.0f);
+        V.v = mk(V.v.x * ld, V.v.y * ld);
+        V.w *= ld;
+        stVelAt(c, bo, V);
+    }
+    for (int i = 0; i < L.nc; ++i) contactInit(c, L.contacts[i], dtRatio, true);
+    for (int i = 0; i < L.nc; ++i) contactWarmStart(c, L.contacts[i]);
+    for (int i = 0; i < L.nj; ++i) jointInit(c, L.joints[i], dtRatio);
+
+    const int velIters = PRM().velIters, posIters = PRM().posIters;
+    for (int it = 0; it < velIters; ++it) {
+        for (int i = 0; i < L.nj; ++i) {
+            const int jr = mjoint(c, L.joints[i], 0);
+            const int4 jh = mi4(c, jr + MJ_TYPE);  // type bodyA bodyB flags
+#ifdef B2G_PREFETCH
+            {   // pull the next joint's scratch, impulses and body velocities towards L1 while this one is solved
+                const int jn = mjoint(c, L.joints[i + 1 < L.nj ? i + 1 : 0], 0);
+                const int4 on = mi4(c, jn + MJ_SOFF);
+                pf(c, on.y + WJ_R4); pf(c, on.y + WJ_M0); pf(c, on.x + SJ_IMPULSE4); pf(c, on.x + SJ_MOTOR4);
+                pf(c, on.z + SB_VEL4); pf(c, on.w + SB_VEL4);
+            }
+#endif
+            if (jh.x == 0) {
+                if (jh.w & 4) frictionSolveVel<true>(c, jr);
+                else frictionSolveVel<false>(c, jr);
+            } else {
+                revoluteSolveVel(c, jr, jh.w);
+            }
+        }
+        for (int i = 0; i < L.nc; ++i) contactSolveVel(c, L.contacts[i]);
+    }
+    for (int i = 0; i < L.nc; ++i) contactStoreImpulses(c, L.contacts[i]);
+
+    for (int i = 0; i < L.ndyn; ++i) integratePosition(c, L.dyn[i], h);
+
+    // position iterations: every island leaves the loop on its own (b2Island::Solve breaks when contactsOkay &&
+    // jointsOkay); `open` = islands still iterating, `solved` = islands that reported positionSolved
+    const uint64_t allIslands = L.nIslands >= 64 ? ~0ull : ((1ull << L.nIslands) - 1ull);
+    uint64_t open = allIslands, solved = 0ull;
+    for (int it = 0; it < posIters && open != 0ull; ++it) {
+        uint64_t bad = 0ull;  // islands whose contacts or joints are not okay in this iteration
+        for (int i = 0; i < L.nc; ++i) {
+            const int k = L.contacts[i];
+            // a contact's island is the island of its dynamic body (both, if both are dynamic)
+            const int a = L.cA[k];
+            const int isl = L.bodyIsl[bodyType(c, a) != 0 ? a : L.cB[k]];
+            if (((open >> isl) & 1ull) == 0ull) continue;
+            // minSeparation of an island is the minimum over its contacts: okay iff every contact's own minimum is
+            float sep = contactSolvePos(c, k, -1, -1, 0.0f);
+            if (!(sep >= -3.0f * B2G_LINEAR_SLOP)) bad |= 1ull << isl;
+        }
+        for (int i = 0; i < L.nj; ++i) {
+            const int jr = mjoint(c, L.joints[i], 0);
+            const int4 jh = mi4(c, jr + MJ_TYPE);
+            if (jh.x != 1) continue;
+            const int isl = L.bodyIsl[(jh.w & 4) ? jh.z : jh.y];
+            if (((open >> isl) & 1ull) == 0ull) continue;
+            if (!revoluteSolvePos(c, jr, jh.w)) bad |= 1ull << isl;
+        }
+        solved |= open & ~bad;
+        open &= bad;
+    }
+    for (int i = 0; i < L.ndyn; ++i) syncTransform(c, L.dyn[i]);
+    for (uint64_t m = staticSeen; m; m &= m - 1ull) syncTransform(c, __ffsll((long long)m) - 1);
+
+    // sleep decision per island; static bodies take the state their last island leaves them in (the DFS wakes
+    // every body it reaches, a sleeping island then puts all of its bodies to sleep, static ones included)
+    uint64_t asleep = 0ull;
+    if (allowSleep) {
+        float minSleep[kMaxBodies];
+        for (int i = 0; i < L.nIslands; ++i) minSleep[i] = FLT_MAX;
+        const float linTolSqr = B2G_LINEAR_SLEEP_TOL * B2G_LINEAR_SLEEP_TOL;
+        const float angTolSqr = B2G_ANGULAR_SLEEP_TOL * B2G_ANGULAR_SLEEP_TOL;
+        for (int i = 0; i < L.ndyn; ++i) {
+            const int b = L.dyn[i], isl = L.bodyIsl[b];
+            Vel V = ldVel(c, b);
+            if (V.w * V.w > angTolSqr || dot(V.v, V.v) > linTolSqr) {
+                stF(c, bslot(c, b, SB_SLEEP), 0.0f);
+                minSleep[isl] = 0.0f;
+            } else {
+                float st = ldF(c, bslot(c, b, SB_SLEEP)) + h;
+                stF(c, bslot(c, b, SB_SLEEP), st);
+                minSleep[isl] = fminT(minSleep[isl], st);
+            }
+        }
+        for (int i = 0; i < L.nIslands; ++i)
+            if (minSleep[i] >= B2G_TIME_TO_SLEEP && ((solved >> i) & 1ull)) asleep |= 1ull << i;
+        if (asleep)
+            for (int i = 0; i < L.ndyn; ++i)
+                if ((asleep >> L.bodyIsl[L.dyn[i]]) & 1ull) sleepBody(c, L.dyn[i]);
+    }
+    for (uint64_t m = staticSeen; m; m &= m - 1ull) {
+        const int b = __ffsll((long long)m) - 1;
+        if ((asleep >> L.bodyIsl[b]) & 1ull) sleepBody(c, b); else wakeBody(c, b);
+    }
+
     uint64_t moved = 0ull;
     for (int b = nb - 1; b >= 0; --b) {
         if (((bodyFlag >> b) & 1ull) == 0ull) continue;
-        if (bodyType(c, b) == 0) continue;
         XF xf1;
         xf1.q = rotOf(ldF(c, bslot(c, b, SB_A0)));
         xf1.p = ldV2(c, bslot(c, b, SB_C0X)) - mul(xf1.q, localCenter(c, b));
