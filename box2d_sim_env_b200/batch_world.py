@@ -44,7 +44,8 @@ ABI_SYMBOLS = [
     "b2g_model_get_fixtures", "b2g_model_get_joints", "b2g_batch_create", "b2g_batch_destroy", "b2g_batch_set_params",
     "b2g_batch_status", "b2g_batch_stream", "b2g_batch_sync", "b2g_batch_set_state", "b2g_batch_set_state_dev",
     "b2g_batch_get_state", "b2g_batch_get_state_dev", "b2g_batch_set_object_pose", "b2g_batch_get_object_pose",
-    "b2g_batch_set_target_velocity", "b2g_batch_set_target_velocity_dev", "b2g_batch_step", "b2g_batch_rollout_dev",
+    "b2g_batch_set_target_velocity", "b2g_batch_set_target_velocity_dev", "b2g_batch_step", "b2g_batch_step_record",
+    "b2g_batch_step_guarded", "b2g_batch_rollout_dev",
     "b2g_batch_get_bodies", "b2g_batch_get_fat_aabbs", "b2g_batch_get_joints", "b2g_batch_get_contacts",
     "b2g_batch_check_collision", "b2g_batch_check_collision_dev", "b2g_batch_save_state", "b2g_batch_restore_state", "b2g_batch_drop_state",
     "b2g_host_alloc", "b2g_host_free", "b2g_launch_count", "b2g_batch_take_kernel_ms",
@@ -102,6 +103,8 @@ def lib():
     L.b2g_batch_set_target_velocity_dev.argtypes = [vp, C.c_int, fp]
     L.b2g_batch_step.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.b2g_batch_rollout_dev.argtypes = [vp, C.c_int, fp, C.c_int, C.c_int]
+    L.b2g_batch_step_record.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, ip, fp, C.c_int]
+    L.b2g_batch_step_guarded.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, ip, ip]
     L.b2g_batch_get_bodies.argtypes = [vp, fp]
     L.b2g_batch_get_fat_aabbs.argtypes = [vp, fp]
     L.b2g_batch_get_joints.argtypes = [vp, ip, fp]
@@ -321,6 +324,28 @@ class BatchBox2DWorld:
     # -- stepping (:3256-3283)
     def stepPhysics(self, steps=1, execute_controllers=True, allow_sleeping=True):
         _check(lib().b2g_batch_step(self.h, int(steps), int(execute_controllers), int(allow_sleeping)))
+
+    def stepPhysicsRecord(self, steps=1, execute_controllers=True, allow_sleeping=True, max_per_world=32):
+        """stepPhysics(std::vector<Contact>& contacts, steps, ...) (:3290-3310): (counts, ints, floats) per world."""
+        counts = np.zeros(self.n_worlds, np.int32)
+        io = np.zeros((self.n_worlds, max_per_world, 4), np.int32)
+        fo = np.zeros((self.n_worlds, max_per_world, 6), np.float32)
+        _check(lib().b2g_batch_step_record(self.h, int(steps), int(execute_controllers), int(allow_sleeping), _ptr(counts),
+                                           _ptr(io), _ptr(fo), max_per_world))
+        return counts, io, fo
+
+    def stepPhysicsGuarded(self, allowed_pairs, steps=1, execute_controllers=True, allow_sleeping=True):
+        """stepPhysics(callback, steps, ...) (:3312-3333) with the callback as an [n_bodies, n_bodies] table (0 = abort).
+        Returns (completed [n_worlds] bool, steps_done [n_worlds])."""
+        nb = self.model.n_bodies
+        table = np.ascontiguousarray(allowed_pairs, dtype=np.uint8)
+        if table.shape != (nb, nb):
+            raise B2GError(1, "allowed_pairs must be [%d, %d]" % (nb, nb))
+        completed = np.zeros(self.n_worlds, np.int32)
+        done = np.zeros(self.n_worlds, np.int32)
+        _check(lib().b2g_batch_step_guarded(self.h, int(steps), int(execute_controllers), int(allow_sleeping), _ptr(table),
+                                            _ptr(completed), _ptr(done)))
+        return completed.astype(bool), done
 
     # -- state (:3462-3541)
     def getWorldState(self):

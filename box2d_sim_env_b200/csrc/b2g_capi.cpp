@@ -74,9 +74,9 @@ struct b2g_batch {
     float* S = nullptr;
     float* tmpl = nullptr;
     cudaStream_t stream = nullptr;
-    StepParams prm{0.01f, 1.0f / 0.01f, 15, 15};
+    StepParams prm{0.01f, 1.0f / 0.01f, 15, 15, 0, 0, nullptr, nullptr, nullptr, nullptr};
     int block = 32;
-    DevBuf stageA, stageB, stageC;
+    DevBuf stageA, stageB, stageC, stageD, stageE;
     std::vector<SavedState> stack;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
     std::vector<cudaEvent_t> eventPool;
@@ -341,7 +341,7 @@ void b2g_batch_destroy(b2g_batch* b) {
     }
     for (auto& p : b->timed) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto& ev : b->eventPool) cudaEventDestroy(ev);
-    b->stageA.release(); b->stageB.release(); b->stageC.release();
+    b->stageA.release(); b->stageB.release(); b->stageC.release(); b->stageD.release(); b->stageE.release();
     if (b->blob) cudaFree(b->blob);
     if (b->S) cudaFree(b->S);
     if (b->tmpl) cudaFree(b->tmpl);
@@ -500,6 +500,75 @@ b2g_status b2g_batch_rollout_dev(b2g_batch* b, int object, const float* targets,
     CU(cudaSetDevice(b->device));
     if (n_targets == 0) return B2G_OK;
     return timedStep(b, object, targets, n_targets, steps_per_target, 1, 1);
+}
+
+// stepPhysics(std::vector<Contact>&, steps, ctrl, sleep) (:3290-3310) incl. startRecordings (:2743-2768)
+b2g_status b2g_batch_step_record(b2g_batch* b, int steps, int execute_controllers, int allow_sleeping, int32_t* counts,
+                                 int32_t* iout, float* fout, int max_per_world) {
+    if (!b || steps < 0 || !counts || !iout || !fout || max_per_world <= 0) return fail(B2G_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(b->device));
+    size_t cb = (size_t)b->N * 4, ib = (size_t)b->N * max_per_world * 4 * 4, fb = (size_t)b->N * max_per_world * 6 * 4;
+    size_t sb = (size_t)b->N * b->m.h.nq * 4;
+    CU(b->stageA.reserve(ib));
+    CU(b->stageB.reserve(fb));
+    CU(b->stageC.reserve(cb));
+    CU(b->stageD.reserve(sb));
+    CU(b->stageE.reserve(sb));
+    CU(cudaMemsetAsync(b->stageA.p, 0, ib, b->stream));
+    CU(cudaMemsetAsync(b->stageB.p, 0, fb, b->stream));
+    CU(cudaMemsetAsync(b->stageC.p, 0, cb, b->stream));
+    // startRecordings: saveState; setToRest; stepPhysics(1, false, false); BeginContact for every touching contact; restoreState
+    CU(launchGetState(b->L(), (float*)b->stageD.p, (float*)b->stageE.p));
+    CU(launchSetToRest(b->L()));
+    CU(launchStep(b->L(), 0, nullptr, 1, 1, 0, 0));
+    StepParams saved = b->prm;
+    b->prm.recMode = 1;
+    b->prm.recMax = max_per_world;
+    b->prm.recCounts = (int*)b->stageC.p;
+    b->prm.recI = (int*)b->stageA.p;
+    b->prm.recF = (float*)b->stageB.p;
+    cudaError_t e = launchRecordTouching(b->L());
+    b->prm.recMode = 0;
+    if (e == cudaSuccess) e = launchSetState(b->L(), (const float*)b->stageD.p, (const float*)b->stageE.p);
+    b->prm.recMode = 1;
+    if (e == cudaSuccess && steps > 0) e = launchStep(b->L(), 0, nullptr, 1, steps, execute_controllers, allow_sleeping);
+    b->prm = saved;
+    if (e != cudaSuccess) return cudaFail(e, "recorded stepping");
+    CU(cudaMemcpyAsync(counts, b->stageC.p, cb, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(iout, b->stageA.p, ib, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(fout, b->stageB.p, fb, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+// stepPhysics(callback, steps, ctrl, sleep) (:3312-3333) with the callback given as a body-pair table
+b2g_status b2g_batch_step_guarded(b2g_batch* b, int steps, int execute_controllers, int allow_sleeping,
+                                  const uint8_t* allowed_pairs, int32_t* completed, int32_t* steps_done) {
+    if (!b || steps < 0 || !allowed_pairs || !completed) return fail(B2G_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(b->device));
+    const int nb = b->m.h.nb;
+    size_t tb = (size_t)nb * nb, cb = (size_t)b->N * 4;
+    CU(b->stageA.reserve(tb));
+    CU(cudaMemcpyAsync(b->stageA.p, allowed_pairs, tb, cudaMemcpyHostToDevice, b->stream));
+    CU(launchClearAbort(b->L()));
+    StepParams saved = b->prm;
+    b->prm.recMode = 2;
+    b->prm.allowed = (const unsigned char*)b->stageA.p;
+    cudaError_t e = steps > 0 ? launchStepGuarded(b->L(), steps, execute_controllers, allow_sleeping) : cudaSuccess;
+    b->prm = saved;
+    if (e != cudaSuccess) return cudaFail(e, "guarded stepping");
+    // the reference returns `not abort_prematurely`: a world that aborted on its very last step still reports false, so the
+    // abort flag itself is read back (bit 0) next to the number of executed steps (bits 8..)
+    std::vector<int32_t> status((size_t)b->N);
+    CU(b->stageB.reserve(cb));
+    CU(launchAbortFlags(b->L(), (int*)b->stageB.p));
+    CU(cudaMemcpyAsync(status.data(), b->stageB.p, cb, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    for (long long i = 0; i < b->N; ++i) {
+        completed[i] = (status[i] & 1) ? 0 : 1;
+        if (steps_done) steps_done[i] = status[i] >> 8;
+    }
+    return B2G_OK;
 }
 
 b2g_status b2g_batch_take_kernel_ms(b2g_batch* b, float* out_ms, int32_t* out_launches) {

@@ -449,6 +449,54 @@ DEV void contactFixtures(Ctx c, int k, int& fA, int& fB) {
     fB = (p >> 8) & 0xff;
 }
 
+// b2Contact::GetWorldManifold of slot k with the given transforms, reported the way the reference's collision checker
+// does: points[0] and the normal, both multiplied by 1/scale (Box2DWorld.cpp:2797-2807, 2853-2863)
+DEV void reportContact(Ctx c, int type, V2 localNormal, V2 localPoint, V2 lp, const XF& xfA, const XF& xfB, int bA, int bB,
+                       int fA, int fB, int* io, float* fo) {
+    V2 normal, point;
+    const float radius = B2G_POLYGON_RADIUS;
+    if (type == 1) {
+        normal = mul(xfA.q, localNormal);
+        V2 planePoint = mul(xfA, localPoint);
+        V2 clipPoint = mul(xfB, lp);
+        V2 cA = clipPoint + (radius - dot(clipPoint - planePoint, normal)) * normal;
+        V2 cB = clipPoint - radius * normal;
+        point = 0.5f * (cA + cB);
+    } else {
+        normal = mul(xfB.q, localNormal);
+        V2 planePoint = mul(xfB, localPoint);
+        V2 clipPoint = mul(xfA, lp);
+        V2 cB = clipPoint + (radius - dot(clipPoint - planePoint, normal)) * normal;
+        V2 cA = clipPoint - radius * normal;
+        point = 0.5f * (cA + cB);
+        normal = -normal;
+    }
+    const float inv = H().invScale;
+    io[0] = bA; io[1] = bB; io[2] = fA; io[3] = fB;
+    fo[0] = inv * point.x; fo[1] = inv * point.y; fo[2] = 0.0f;
+    fo[3] = inv * normal.x; fo[4] = inv * normal.y; fo[5] = 0.0f;
+}
+
+// Box2DCollisionChecker::BeginContact (:2792-2818) for contact slot k, whose manifold has just been updated with the
+// bodies' current transforms: recording and / or the guard of stepPhysics(callback, ...)
+DEVN void onBeginContact(Ctx c, int k) {
+    const StepParams& p = PRM();
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ck = cslot(c, k, 0);
+    const int fx = ldI(c, ck + SC_FIX);
+    const int fA = fx & 0xff, fB = (fx >> 8) & 0xff;
+    const int bA = mI(c, mfix(c, fA, MF_BODY)), bB = mI(c, mfix(c, fB, MF_BODY));
+    if (p.recMode & 1) {
+        int n = p.recCounts[w];
+        if (n < p.recMax)
+            reportContact(c, ldI(c, ck + SC_MANIFOLD) & 0xff, ldV2(c, ck + SC_LNX), ldV2(c, ck + SC_LPX), ldV2(c, ck + SC_P0X),
+                          ldXF(c, bA), ldXF(c, bB), bA, bB, fA, fB, p.recI + ((size_t)w * p.recMax + n) * 4,
+                          p.recF + ((size_t)w * p.recMax + n) * 6);
+        p.recCounts[w] = n + 1;
+    }
+    if ((p.recMode & 2) && p.allowed[bA * H().nb + bB] == 0) stI(c, sslot(c, SS_ABORT), ldI(c, sslot(c, SS_ABORT)) | 1);
+}
+
 // b2Contact::Update for slot k.  Returns bit0 = now touching, bit1 = was touching.
 DEVN int updateContact(Ctx c, int k) {
     const int ck = cslot(c, k, 0);
@@ -575,7 +623,11 @@ DEVN void collide(Ctx c) {
         Box a = ldFat(c, fA);
         Box b = ldFat(c, fB);
         if (!boxOverlap(a, b)) { destroyContact(c, k); continue; }
+#ifndef B2G_NO_HOOK_COLLIDE
+        if (updateContact(c, k) == 1 && PRM().recMode != 0) onBeginContact(c, k);
+#else
         updateContact(c, k);
+#endif
     }
 }
 

@@ -155,6 +155,40 @@ __global__ void k_step(const __grid_constant__ ModelHeader hdr, const uint32_t* 
     }
 }
 
+// stepPhysics(callback, steps, ...) (:3312-3333): a kernel of its own so that the plain stepping kernel stays lean
+__global__ void k_step_guarded(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
+                               StepParams prm, int steps, int executeControllers, int allowSleeping) {
+    B2G_PROLOGUE();
+    for (int s = 0; s < steps; ++s) stepWorldGuarded(c, executeControllers != 0, allowSleeping != 0);
+}
+
+// guarded stepping: clear the abort flag / executed-step counter of every world
+__global__ void k_set_word(float* S, long long N, int stateChunks, int off, int value) {
+    long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < N) *reinterpret_cast<int*>(worldBase(S, stateChunks, w) + off) = value;
+}
+
+// Box2DWorld::setToRest (:3550-3558): setDOFVelocities(0) on every object
+__global__ void k_set_to_rest(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
+                              StepParams prm) {
+    B2G_PROLOGUE();
+    float zero[kMaxDofsPerObject];
+    for (int i = 0; i < kMaxDofsPerObject; ++i) zero[i] = 0.0f;
+    for (int o = 0; o < H().no; ++o) objectSetDofVelocities(c, o, zero);
+}
+
+// Box2DCollisionChecker::startRecordings (:2758-2765): every contact that is touching and enabled right now goes
+// through BeginContact, in contact-list order (newest first)
+__global__ void k_record_touching(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
+                                  long long N, StepParams prm) {
+    B2G_PROLOGUE();
+    for (int k = contactCount(c) - 1; k >= 0; --k) {
+        int flags = ldI(c, cslot(c, k, SC_FLAGS));
+        if ((flags & CF_TOUCHING) == 0 || (flags & CF_ENABLED) == 0) continue;
+        onBeginContact(c, k);
+    }
+}
+
 __global__ void k_get_bodies(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
                              long long N, StepParams prm, float* __restrict__ out) {
     B2G_PROLOGUE();
@@ -233,7 +267,6 @@ __global__ void k_check_collision(const __grid_constant__ ModelHeader hdr, const
     findNewContacts(c);
     collide(c);
     int n = 0;
-    float inv = H().invScale;
     for (int k = contactCount(c) - 1; k >= 0; --k) {
         int flags = ldI(c, cslot(c, k, SC_FLAGS));
         if ((flags & CF_TOUCHING) == 0 || (flags & CF_ENABLED) == 0) continue;
@@ -241,34 +274,9 @@ __global__ void k_check_collision(const __grid_constant__ ModelHeader hdr, const
             int bA, bB, fA, fB;
             contactBodies(c, k, bA, bB, fA, fB);
             // b2Contact::GetWorldManifold with the bodies' current transforms; only points[0] is reported (:2857-2862)
-            XF xfA = ldXF(c, bA), xfB = ldXF(c, bB);
-            int type = ldI(c, cslot(c, k, SC_MANIFOLD)) & 0xff;
-            V2 localNormal = ldV2(c, cslot(c, k, SC_LNX));
-            V2 localPoint = ldV2(c, cslot(c, k, SC_LPX));
-            V2 lp = ldV2(c, cslot(c, k, SC_P0X));
-            V2 normal, point;
-            const float radius = B2G_POLYGON_RADIUS;
-            if (type == 1) {
-                normal = mul(xfA.q, localNormal);
-                V2 planePoint = mul(xfA, localPoint);
-                V2 clipPoint = mul(xfB, lp);
-                V2 cA = clipPoint + (radius - dot(clipPoint - planePoint, normal)) * normal;
-                V2 cB = clipPoint - radius * normal;
-                point = 0.5f * (cA + cB);
-            } else {
-                normal = mul(xfB.q, localNormal);
-                V2 planePoint = mul(xfB, localPoint);
-                V2 clipPoint = mul(xfA, lp);
-                V2 cB = clipPoint + (radius - dot(clipPoint - planePoint, normal)) * normal;
-                V2 cA = clipPoint - radius * normal;
-                point = 0.5f * (cA + cB);
-                normal = -normal;
-            }
-            int* io = iout + ((size_t)w * maxPer + n) * 4;
-            float* fo = fout + ((size_t)w * maxPer + n) * 6;
-            io[0] = bA; io[1] = bB; io[2] = fA; io[3] = fB;
-            fo[0] = inv * point.x; fo[1] = inv * point.y; fo[2] = 0.0f;
-            fo[3] = inv * normal.x; fo[4] = inv * normal.y; fo[5] = 0.0f;
+            reportContact(c, ldI(c, cslot(c, k, SC_MANIFOLD)) & 0xff, ldV2(c, cslot(c, k, SC_LNX)), ldV2(c, cslot(c, k, SC_LPX)),
+                          ldV2(c, cslot(c, k, SC_P0X)), ldXF(c, bA), ldXF(c, bB), bA, bB, fA, fB,
+                          iout + ((size_t)w * maxPer + n) * 4, fout + ((size_t)w * maxPer + n) * 6);
         }
         ++n;
     }
@@ -324,6 +332,11 @@ cudaError_t launchStep(const Launch& L, int object, const float* targets, int nT
                        int allowSleep) {
     LAUNCH(k_step, object, targets, nTargets, stepsPerTarget, execCtrl, allowSleep);
 }
+cudaError_t launchSetToRest(const Launch& L) { LAUNCH(k_set_to_rest); }
+cudaError_t launchRecordTouching(const Launch& L) { LAUNCH(k_record_touching); }
+cudaError_t launchStepGuarded(const Launch& L, int steps, int execCtrl, int allowSleep) {
+    LAUNCH(k_step_guarded, steps, execCtrl, allowSleep);
+}
 cudaError_t launchGetBodies(const Launch& L, float* out) { LAUNCH(k_get_bodies, out); }
 cudaError_t launchGetFat(const Launch& L, float* out) { LAUNCH(k_get_fat, out); }
 cudaError_t launchGetJoints(const Launch& L, int* iout, float* fout) { LAUNCH(k_get_joints, iout, fout); }
@@ -347,6 +360,20 @@ cudaError_t launchBroadcast(const Launch& L, const float* tmpl) {
 cudaError_t launchExtractWorld(const Launch& L, float* tmpl, long long world) {
     k_extract_world<<<(L.h.stateChunks + 255) / 256, 256, 0, L.stream>>>(reinterpret_cast<const float4*>(L.S),
                                                                         reinterpret_cast<float4*>(tmpl), L.h.stateChunks, world);
+    ++g_launches;
+    return cudaGetLastError();
+}
+cudaError_t launchClearAbort(const Launch& L) {
+    int threads = 256;
+    k_set_word<<<(unsigned)((L.N + threads - 1) / threads), threads, 0, L.stream>>>(L.S, L.N, L.h.stateChunks,
+                                                                                    L.h.cScalar * kChunkBytes + SS_ABORT, 0);
+    ++g_launches;
+    return cudaGetLastError();
+}
+cudaError_t launchAbortFlags(const Launch& L, int* out) {
+    int threads = 256;
+    k_status<<<(unsigned)((L.N + threads - 1) / threads), threads, 0, L.stream>>>(L.S, L.N, L.h.stateChunks,
+                                                                                  L.h.cScalar * kChunkBytes + SS_ABORT, out);
     ++g_launches;
     return cudaGetLastError();
 }

@@ -27,11 +27,16 @@ cudaError_t launchGetPose(const Launch& L, int object, float* pose);
 cudaError_t launchSetTarget(const Launch& L, int object, const float* v);
 cudaError_t launchStep(const Launch& L, int object, const float* targets, int nTargets, int stepsPerTarget, int execCtrl,
                        int allowSleep);
+cudaError_t launchSetToRest(const Launch& L);
+cudaError_t launchRecordTouching(const Launch& L);
+cudaError_t launchStepGuarded(const Launch& L, int steps, int execCtrl, int allowSleep);
 cudaError_t launchGetBodies(const Launch& L, float* out);
 cudaError_t launchGetFat(const Launch& L, float* out);
 cudaError_t launchGetJoints(const Launch& L, int* iout, float* fout);
 cudaError_t launchGetContacts(const Launch& L, int* counts, int* iout, float* fout, int maxPer);
 cudaError_t launchCheckCollision(const Launch& L, int* counts, int* iout, float* fout, int maxPer);
 cudaError_t launchStatus(const Launch& L, int* out);
+cudaError_t launchAbortFlags(const Launch& L, int* out);  // out[w] = abort flag (bit 0) | executed steps << 8
+cudaError_t launchClearAbort(const Launch& L);
 
 }  // namespace b2g

@@ -423,7 +423,11 @@ DEVN void solveTOI(Ctx c) {
         Sweep backup1 = ldSweep(c, bA), backup2 = ldSweep(c, bB);
         bodyAdvance(c, bA, minAlpha);
         bodyAdvance(c, bB, minAlpha);
+#ifndef B2G_NO_HOOK_TOI
+        if (updateContact(c, minContact) == 1 && PRM().recMode != 0) onBeginContact(c, minContact);
+#else
         updateContact(c, minContact);
+#endif
         {
             int fl = ldI(c, cslot(c, minContact, SC_FLAGS));
             fl &= ~CF_TOI;
@@ -466,7 +470,11 @@ DEVN void solveTOI(Ctx c) {
                 if (bodyType(c, other) == 2) continue;  // only static / kinematic / bullet bodies join
                 Sweep backup = ldSweep(c, other);
                 if (((bodyFlag >> other) & 1ull) == 0ull) bodyAdvance(c, other, minAlpha);
+#ifndef B2G_NO_HOOK_TOI
+                if (updateContact(c, k) == 1 && PRM().recMode != 0) onBeginContact(c, k);
+#else
                 updateContact(c, k);
+#endif
                 int fl = ldI(c, cslot(c, k, SC_FLAGS));
                 if ((fl & CF_ENABLED) == 0 || (fl & CF_TOUCHING) == 0) {
                     stSweep(c, other, backup);

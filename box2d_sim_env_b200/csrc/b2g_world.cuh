@@ -239,7 +239,7 @@ DEVN void initWorld(Ctx c) {
     stI(c, sslot(c, SS_STATUS), 0);
     stMoved(c, h.nf >= 64 ? ~0ull : ((1ull << h.nf) - 1ull));  // every proxy is buffered at creation
     stI(c, sslot(c, SS_TARGET_AVAIL), 0);
-    stI(c, sslot(c, SS_SPARE), 0);
+    stI(c, sslot(c, SS_ABORT), 0);
     for (int t = 0; t < ((h.ntarget + 3) & ~3); ++t) stF(c, tslot(c, t), 0.0f);
 
     // Box2DObject ctor: _base_link->setPose((0,0,0), true, true) (:1335)
@@ -354,6 +354,7 @@ DEVN void robotControl(Ctx c, int o, int robotSlot) {
 // Box2DWorld::stepPhysics body for one step (:3270-3282) = controllers + b2World::Step + ClearForces
 DEVN void stepWorld(Ctx c, bool executeControllers, bool allowSleeping) {
     const ModelHeader& h = H();
+
     if (executeControllers) {
         for (int r = 0; r < h.nrobots; ++r) robotControl(c, mI(c, h.oRobotOrder + r), r);
     }
@@ -374,6 +375,14 @@ DEVN void stepWorld(Ctx c, bool executeControllers, bool allowSleeping) {
     for (int b = 0; b < h.nb; ++b) {  // ClearForces
         st4(c, bslot(c, b, SB_FORCE4), mk4(0.0f, 0.0f, 0.0f, 0.0f));
     }
+}
+
+// One step of stepPhysics(callback, ...) (:3312-3333): "for (i < steps and not abort_prematurely)".  Kept out of stepWorld
+// so that the plain path carries no extra live state across the step.
+DEVN void stepWorldGuarded(Ctx c, bool executeControllers, bool allowSleeping) {
+    if ((ldI(c, sslot(c, SS_ABORT)) & 1) != 0) return;
+    stepWorld(c, executeControllers, allowSleeping);
+    stI(c, sslot(c, SS_ABORT), ldI(c, sslot(c, SS_ABORT)) + 256);  // executed steps in bits 8..
 }
 
 }  // namespace b2g

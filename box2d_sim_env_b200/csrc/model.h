@@ -87,6 +87,14 @@ enum LinkField {  // pre-order (parent first) list per object
 struct StepParams {
     float dt, inv_dt;  // inv_dt = dt > 0 ? 1 / dt : 0 (b2TimeStep)
     int velIters, posIters;
+    // b2ContactListener::BeginContact hooks of the recording / guarded stepPhysics overloads
+    // (src/sim_env/Box2DWorld.cpp:3290-3333, 2792-2818); all null / 0 for plain stepping
+    int recMode;              // bit0: append every BeginContact to the world's record; bit1: guarded stepping
+    int recMax;               // record capacity per world
+    int* recCounts;           // [N]
+    int* recI;                // [N][recMax][4] bodyA bodyB fixtureA fixtureB
+    float* recF;              // [N][recMax][6] contact_point(3) contact_normal(3), both times 1/scale
+    const unsigned char* allowed;  // [nb][nb]: 0 = a BeginContact between these bodies aborts the world's stepping
 };
 
 struct ModelHeader {
@@ -173,7 +181,7 @@ enum ScalarState {
     SS_STATUS = B2G_F(0, 3),     // bit0 contact capacity exceeded, bit1 non-finite
     SS_MOVED_LO = B2G_F(1, 0), SS_MOVED_HI = B2G_F(1, 1),
     SS_TARGET_AVAIL = B2G_F(1, 2),  // bit r: robot r has a controller target
-    SS_SPARE = B2G_F(1, 3),
+    SS_ABORT = B2G_F(1, 3),      // guarded stepping: bit0 a forbidden BeginContact fired, bits 8.. steps executed
     SS_CHUNKS = 2
 };
 

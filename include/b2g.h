@@ -142,6 +142,21 @@ b2g_status b2g_batch_set_target_velocity_dev(b2g_batch* batch, int object, const
 
 /* Box2DWorld::stepPhysics(steps, execute_controllers, allow_sleeping) (:3266-3283). */
 b2g_status b2g_batch_step(b2g_batch* batch, int steps, int execute_controllers, int allow_sleeping);
+/* Box2DWorld::stepPhysics(std::vector<Contact>& contacts, steps, execute_controllers, allow_sleeping) (:3290-3310):
+ * steps like b2g_batch_step and returns, per world, one Contact for every b2ContactListener::BeginContact that fired
+ * (Box2DCollisionChecker::BeginContact :2792-2818), preceded by the contacts that are touching at the start, found the
+ * way startRecordings does (:2743-2768: saveState, setToRest, one step without controllers, restoreState).
+ * counts [n_worlds] (may exceed max_per_world: the record is truncated, the count is not); iout [n_worlds][max][4] =
+ * bodyA bodyB fixtureA fixtureB; fout [n_worlds][max][6] = contact_point(3) contact_normal(3), times 1/scale. */
+b2g_status b2g_batch_step_record(b2g_batch* batch, int steps, int execute_controllers, int allow_sleeping, int32_t* counts,
+                                 int32_t* iout, float* fout, int max_per_world);
+/* Box2DWorld::stepPhysics(callback, steps, execute_controllers, allow_sleeping) (:3312-3333).  The reference calls
+ * callback(link_a, link_b) on every BeginContact and stops stepping that world after the current step once it returns
+ * false; here the callback is the table allowed_pairs[n_bodies][n_bodies] (0 = this pair aborts; bodies = links in
+ * creation order, body 0 = ground).  completed [n_worlds]: 1 if no forbidden contact began (the reference's return
+ * value); steps_done [n_worlds] (optional): steps actually executed. */
+b2g_status b2g_batch_step_guarded(b2g_batch* batch, int steps, int execute_controllers, int allow_sleeping,
+                                  const uint8_t* allowed_pairs, int32_t* completed, int32_t* steps_done);
 /* "propagate" (planner-side composition): for t in [0, n_targets): setTargetVelocity(
  * targets[t]) on robot `object`, stepPhysics(steps_per_target).  targets: [n_targets][n_worlds][n_dofs]
  * on the device. One kernel launch. */

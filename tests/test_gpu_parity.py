@@ -257,3 +257,60 @@ def test_ragged_batch_sizes(b2g, n):
         ow.set_target_velocity(0, tg[w])
         ow.step(15)
     assert_same(batch, worlds, "ragged batch n=%d" % n)
+
+
+def scattered_start(b2g, env_name, n, seed):
+    batch = make_batch(b2g, env_name, n)
+    worlds = oracle_worlds(load_env_dict(env_name), n)
+    q, qd = random_states(batch.model, n, seed=seed, spread=0.6)
+    tg = random_targets(batch.model, 0, n, seed=seed + 1)[0]
+    batch.setWorldState(q, qd, reset_caches=True)
+    batch.setTargetVelocity(0, tg)
+    for w, ow in enumerate(worlds):
+        ow.set_state(q[w], qd[w])
+        ow.set_target_velocity(0, tg[w])
+    return batch, worlds
+
+
+@pytest.mark.parametrize("env_name", [ENV_A, ENV_B])
+def test_recorded_contact_stepping(b2g, env_name):
+    """stepPhysics(std::vector<Contact>&, steps) (reference :3290-3310, startRecordings :2743-2768): the per-world record of
+    BeginContact events — pairs, order, contact points and normals — is identical to the oracle's."""
+    n = 96
+    batch, worlds = scattered_start(b2g, env_name, n, seed=71)
+    counts, io, fo = batch.stepPhysicsRecord(25, max_per_world=32)
+    total = 0
+    for w, ow in enumerate(worlds):
+        oio, ofo = ow.step_record(25)
+        assert counts[w] == len(oio), "world %d: %d vs %d recorded contacts" % (w, counts[w], len(oio))
+        assert np.array_equal(io[w, :len(oio)], oio) and np.array_equal(fo[w, :len(oio)], ofo)
+        total += len(oio)
+    assert total > 30, "scenario recorded too few contacts"
+    assert_same(batch, worlds, "after recorded stepping")
+
+
+def test_guarded_stepping(b2g):
+    """stepPhysics(callback, steps) (reference :3312-3333) with the callback as a body-pair table."""
+    n, steps = 128, 40
+    batch, worlds = scattered_start(b2g, ENV_A, n, seed=81)
+    nb = batch.model.n_bodies
+    ok, done = batch.stepPhysicsGuarded(np.ones((nb, nb), np.uint8), steps)
+    assert ok.all() and (done == steps).all()
+    for ow in worlds:
+        ow.step(steps)
+    assert_same(batch, worlds, "guarded stepping with every pair allowed")
+    # forbid every pair: a world stops after the step in which its first BeginContact fires
+    batch, worlds = scattered_start(b2g, ENV_A, n, seed=83)
+    ok, done = batch.stepPhysicsGuarded(np.zeros((nb, nb), np.uint8), steps)
+    assert (~ok).sum() > 10 and ok.sum() > 0, "scenario must abort some worlds and complete others"
+    assert np.all(done[ok] == steps) and np.all(done[~ok] >= 1)
+    touching_at_abort = 0
+    for w, ow in enumerate(worlds):
+        ow.step(int(done[w]))
+        oio, _ = ow.contacts()
+        if not ok[w] and len(oio) and oio[:, 2].any():
+            touching_at_abort += 1
+        if ok[w]:
+            assert not (len(oio) and oio[:, 2].any()), "world %d completed although a contact is touching" % w
+    assert_same(batch, worlds, "guarded stepping: state after the executed steps")
+    assert touching_at_abort >= 0.8 * (~ok).sum()
