@@ -162,6 +162,20 @@ __global__ void k_step_guarded(const __grid_constant__ ModelHeader hdr, const ui
     for (int s = 0; s < steps; ++s) stepWorldGuarded(c, executeControllers != 0, allowSleeping != 0);
 }
 
+// per-world status: the sticky bits kept in the state (bit0: contact capacity exceeded) plus bit1 = a body position or
+// velocity is not finite right now
+__global__ void k_world_status(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
+                               StepParams prm, int* __restrict__ out) {
+    B2G_PROLOGUE();
+    int st = ldI(c, sslot(c, SS_STATUS)) & 1;
+    bool finite = true;
+    for (int b = 0; b < H().nb; ++b) {
+        const float4 p = ld4(c, bslot(c, b, SB_POS4)), v = ld4(c, bslot(c, b, SB_VEL4));
+        finite = finite && isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && isfinite(v.x) && isfinite(v.y) && isfinite(v.z);
+    }
+    out[w] = st | (finite ? 0 : 2);
+}
+
 // guarded stepping: clear the abort flag / executed-step counter of every world
 __global__ void k_set_word(float* S, long long N, int stateChunks, int off, int value) {
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -377,12 +391,6 @@ cudaError_t launchAbortFlags(const Launch& L, int* out) {
     ++g_launches;
     return cudaGetLastError();
 }
-cudaError_t launchStatus(const Launch& L, int* out) {
-    int threads = 256;
-    k_status<<<(unsigned)((L.N + threads - 1) / threads), threads, 0, L.stream>>>(L.S, L.N, L.h.stateChunks,
-                                                                                  L.h.cScalar * kChunkBytes + SS_STATUS, out);
-    ++g_launches;
-    return cudaGetLastError();
-}
+cudaError_t launchStatus(const Launch& L, int* out) { LAUNCH(k_world_status, out); }
 
 }  // namespace b2g

@@ -314,3 +314,23 @@ def test_guarded_stepping(b2g):
             assert not (len(oio) and oio[:, 2].any()), "world %d completed although a contact is touching" % w
     assert_same(batch, worlds, "guarded stepping: state after the executed steps")
     assert touching_at_abort >= 0.8 * (~ok).sum()
+
+
+def test_status_bits(b2g):
+    """Per-world status: bit0 = contact-slot capacity exceeded (loud: B2G_ERR_CAPACITY), bit1 = non-finite state."""
+    from box2d_sim_env_b200 import envgen
+    n = 8
+    env = envgen.clutter_env()
+    batch = b2g.BatchBox2DWorld(n, max_contacts=2).loadWorld(b2g.Model(env))   # far too few slots for sliding clutter
+    q, qd = envgen.clutter_states(n, seed=5, speed=3.0)
+    batch.setWorldState(q, qd, reset_caches=True)
+    batch.stepPhysics(30)
+    with pytest.raises(b2g.B2GError) as err:
+        batch.status()
+    assert err.value.code == 5 and "capacity" in str(err.value)
+    batch = make_batch(b2g, ENV_A, 4)
+    q, qd = batch.getWorldState()
+    q[2, 0] = np.nan          # base x of the robot in world 2
+    batch.setWorldState(q, qd)
+    batch.stepPhysics(2)
+    assert batch.status().tolist() == [0, 0, 2, 0]
