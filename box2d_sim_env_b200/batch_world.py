@@ -44,6 +44,7 @@ ABI_SYMBOLS = [
     "b2g_model_get_fixtures", "b2g_model_get_joints", "b2g_batch_create", "b2g_batch_destroy", "b2g_batch_set_params",
     "b2g_batch_status", "b2g_batch_stream", "b2g_batch_sync", "b2g_batch_set_state", "b2g_batch_set_state_dev",
     "b2g_batch_get_state", "b2g_batch_get_state_dev", "b2g_batch_set_object_pose", "b2g_batch_get_object_pose",
+    "b2g_batch_set_to_rest", "b2g_batch_at_rest", "b2g_batch_set_link_enabled",
     "b2g_batch_set_target_velocity", "b2g_batch_set_target_velocity_dev", "b2g_batch_step", "b2g_batch_step_record",
     "b2g_batch_step_guarded", "b2g_batch_rollout_dev",
     "b2g_batch_get_bodies", "b2g_batch_get_fat_aabbs", "b2g_batch_get_joints", "b2g_batch_get_contacts",
@@ -99,6 +100,9 @@ def lib():
         getattr(L, n).argtypes = [vp, fp, fp]
     L.b2g_batch_set_object_pose.argtypes = [vp, C.c_int, fp]
     L.b2g_batch_get_object_pose.argtypes = [vp, C.c_int, fp]
+    L.b2g_batch_set_to_rest.argtypes = [vp]
+    L.b2g_batch_at_rest.argtypes = [vp, C.c_float, ip]
+    L.b2g_batch_set_link_enabled.argtypes = [vp, C.c_int, vp, C.c_int]
     L.b2g_batch_set_target_velocity.argtypes = [vp, C.c_int, fp]
     L.b2g_batch_set_target_velocity_dev.argtypes = [vp, C.c_int, fp]
     L.b2g_batch_step.argtypes = [vp, C.c_int, C.c_int, C.c_int]
@@ -384,6 +388,26 @@ class BatchBox2DWorld:
         pose = np.zeros((self.n_worlds, 3), np.float32)
         _check(lib().b2g_batch_get_object_pose(self.h, obj, _ptr(pose)))
         return pose
+
+    def setToRest(self):
+        """Box2DWorld::setToRest (:3550-3558)."""
+        _check(lib().b2g_batch_set_to_rest(self.h))
+
+    def atRest(self, threshold=0.0001):
+        """Box2DWorld::atRest (:3435-3452), one bool per world."""
+        out = np.zeros(self.n_worlds, np.int32)
+        _check(lib().b2g_batch_at_rest(self.h, float(threshold), _ptr(out)))
+        return out.astype(bool)
+
+    def setLinkEnabled(self, body, enabled):
+        """Box2DLink::setEnabled (:802-822) for the link with body index `body`; enabled: bool or [n_worlds] array."""
+        if np.isscalar(enabled):
+            _check(lib().b2g_batch_set_link_enabled(self.h, int(body), None, int(bool(enabled))))
+        else:
+            e = np.ascontiguousarray(enabled, dtype=np.uint8)
+            if e.shape != (self.n_worlds,):
+                raise B2GError(1, "enabled must be a bool or an [n_worlds] array")
+            _check(lib().b2g_batch_set_link_enabled(self.h, int(body), _ptr(e), 0))
 
     # -- controller (Box2DController.h:23)
     def setTargetVelocity(self, robot, velocity):

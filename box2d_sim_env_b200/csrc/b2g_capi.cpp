@@ -502,6 +502,38 @@ b2g_status b2g_batch_rollout_dev(b2g_batch* b, int object, const float* targets,
     return timedStep(b, object, targets, n_targets, steps_per_target, 1, 1);
 }
 
+b2g_status b2g_batch_set_to_rest(b2g_batch* b) {
+    if (!b) return fail(B2G_ERR_INVALID, "null batch");
+    CU(cudaSetDevice(b->device));
+    CU(launchSetToRest(b->L()));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_at_rest(b2g_batch* b, float threshold, int32_t* out) {
+    if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    CU(b->stageC.reserve((size_t)b->N * 4));
+    CU(launchAtRest(b->L(), threshold, (int*)b->stageC.p));
+    CU(cudaMemcpyAsync(out, b->stageC.p, (size_t)b->N * 4, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_set_link_enabled(b2g_batch* b, int body, const uint8_t* enabled, int enabled_all) {
+    if (!b || body <= 0 || body >= b->m.h.nb) return fail(B2G_ERR_INVALID, "unknown link (body 0 is the ground)");
+    CU(cudaSetDevice(b->device));
+    const unsigned char* dev = nullptr;
+    if (enabled) {
+        CU(b->stageC.reserve((size_t)b->N));
+        CU(cudaMemcpyAsync(b->stageC.p, enabled, (size_t)b->N, cudaMemcpyHostToDevice, b->stream));
+        dev = (const unsigned char*)b->stageC.p;
+    }
+    CU(launchSetLinkEnabled(b->L(), body, dev, enabled_all));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
 // stepPhysics(std::vector<Contact>&, steps, ctrl, sleep) (:3290-3310) incl. startRecordings (:2743-2768)
 b2g_status b2g_batch_step_record(b2g_batch* b, int steps, int execute_controllers, int allow_sleeping, int32_t* counts,
                                  int32_t* iout, float* fout, int max_per_world) {

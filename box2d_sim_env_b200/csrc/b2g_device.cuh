@@ -566,7 +566,18 @@ DEVN void destroyContact(Ctx c, int k) {
 }
 
 // b2ContactManager::AddPair (fixture a < fixture b by proxy id; filters are folded into the pair mask)
+DEV uint64_t ldDisabled(Ctx c) {
+    return (uint64_t)(uint32_t)ldI(c, sslot(c, SS_DISABLED_LO)) | ((uint64_t)(uint32_t)ldI(c, sslot(c, SS_DISABLED_HI)) << 32);
+}
+// b2ContactFilter::ShouldCollide with the only filter data the reference ever sets: categoryBits = enabled ? 1 : 0,
+// maskBits = 0xFFFF, groupIndex = 0 (Box2DWorld.cpp:815-821)
+DEV bool filterShouldCollide(Ctx c, int a, int b) {
+    uint64_t d = ldDisabled(c);
+    return ((d >> a) & 1ull) == 0ull && ((d >> b) & 1ull) == 0ull;
+}
+
 DEV void addPair(Ctx c, int a, int b) {
+    if (!filterShouldCollide(c, a, b)) return;
     int n = contactCount(c);
     int key = a | (b << 8);
     for (int k = 0; k < n; ++k)
@@ -617,6 +628,13 @@ DEVN void collide(Ctx c) {
         contactFixtures(c, k, fA, fB);
         int bA = mI(c, mfix(c, fA, MF_BODY));
         int bB = mI(c, mfix(c, fB, MF_BODY));
+        {   // contact flagged for filtering (b2Fixture::Refilter): body-level ShouldCollide is static here (pair masks)
+            int fl = ldI(c, cslot(c, k, SC_FLAGS));
+            if (fl & CF_FILTER) {
+                if (!filterShouldCollide(c, fA, fB)) { destroyContact(c, k); continue; }
+                stI(c, cslot(c, k, SC_FLAGS), fl & ~CF_FILTER);
+            }
+        }
         bool activeA = isAwake(c, bA) && bodyType(c, bA) != 0;
         bool activeB = isAwake(c, bB) && bodyType(c, bB) != 0;
         if (!activeA && !activeB) continue;

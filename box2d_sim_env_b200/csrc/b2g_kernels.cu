@@ -176,6 +176,43 @@ __global__ void k_world_status(const __grid_constant__ ModelHeader hdr, const ui
     out[w] = st | (finite ? 0 : 2);
 }
 
+// Box2DLink::setEnabled (:802-822) for the link with body index `body`: categoryBits of its fixtures (newest first),
+// b2Fixture::Refilter = flag the fixture's contacts for filtering and touch its proxy.  enabled == nullptr: `all`.
+__global__ void k_set_link_enabled(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
+                                   StepParams prm, int body, const unsigned char* __restrict__ enabled, int all) {
+    B2G_PROLOGUE();
+    const bool on = enabled ? enabled[w] != 0 : all != 0;
+    const int start = mI(c, mbody(c, body, MB_FIX_START)), cnt = mI(c, mbody(c, body, MB_FIX_COUNT));
+    uint64_t bits = 0ull;
+    for (int f = start; f < start + cnt; ++f) bits |= 1ull << f;
+    uint64_t d = ldDisabled(c);
+    const bool wasOn = (d & bits) == 0ull;   // Box2DLink keeps one flag per link: "if (b_enable == _enabled) return"
+    if (on == wasOn) return;
+    d = on ? (d & ~bits) : (d | bits);
+    stI(c, sslot(c, SS_DISABLED_LO), (int)(uint32_t)(d & 0xffffffffull));
+    stI(c, sslot(c, SS_DISABLED_HI), (int)(uint32_t)(d >> 32));
+    for (int k = contactCount(c) - 1; k >= 0; --k) {
+        int fA, fB;
+        contactFixtures(c, k, fA, fB);
+        if (((bits >> fA) & 1ull) || ((bits >> fB) & 1ull)) stI(c, cslot(c, k, SC_FLAGS), ldI(c, cslot(c, k, SC_FLAGS)) | CF_FILTER);
+    }
+    stMoved(c, ldMoved(c) | bits);
+}
+
+// Box2DWorld::atRest(threshold) (:3435-3452): every object's DOF velocities are within the threshold (infinity norm)
+__global__ void k_at_rest(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
+                          StepParams prm, float threshold, int* __restrict__ out) {
+    B2G_PROLOGUE();
+    bool rest = true;
+    for (int o = 0; o < H().no; ++o) {
+        float qd[kMaxDofsPerObject];
+        getDofVelocities(c, o, qd);
+        int n = mI(c, mobj(c, o, MO_NDOFS));
+        for (int i = 0; i < n; ++i) rest = rest && (fabsf(qd[i]) <= threshold);
+    }
+    out[w] = rest ? 1 : 0;
+}
+
 // guarded stepping: clear the abort flag / executed-step counter of every world
 __global__ void k_set_word(float* S, long long N, int stateChunks, int off, int value) {
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -347,6 +384,10 @@ cudaError_t launchStep(const Launch& L, int object, const float* targets, int nT
     LAUNCH(k_step, object, targets, nTargets, stepsPerTarget, execCtrl, allowSleep);
 }
 cudaError_t launchSetToRest(const Launch& L) { LAUNCH(k_set_to_rest); }
+cudaError_t launchSetLinkEnabled(const Launch& L, int body, const unsigned char* enabled, int all) {
+    LAUNCH(k_set_link_enabled, body, enabled, all);
+}
+cudaError_t launchAtRest(const Launch& L, float threshold, int* out) { LAUNCH(k_at_rest, threshold, out); }
 cudaError_t launchRecordTouching(const Launch& L) { LAUNCH(k_record_touching); }
 cudaError_t launchStepGuarded(const Launch& L, int steps, int execCtrl, int allowSleep) {
     LAUNCH(k_step_guarded, steps, execCtrl, allowSleep);

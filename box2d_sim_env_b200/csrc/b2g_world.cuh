@@ -240,6 +240,7 @@ DEVN void initWorld(Ctx c) {
     stMoved(c, h.nf >= 64 ? ~0ull : ((1ull << h.nf) - 1ull));  // every proxy is buffered at creation
     stI(c, sslot(c, SS_TARGET_AVAIL), 0);
     stI(c, sslot(c, SS_ABORT), 0);
+    st4(c, sslot(c, SS_DISABLED_LO), mk4(0.0f, 0.0f, 0.0f, 0.0f));
     for (int t = 0; t < ((h.ntarget + 3) & ~3); ++t) stF(c, tslot(c, t), 0.0f);
 
     // Box2DObject ctor: _base_link->setPose((0,0,0), true, true) (:1335)
@@ -370,7 +371,9 @@ DEVN void stepWorld(Ctx c, bool executeControllers, bool allowSleeping) {
     float dtRatio = ldF(c, sslot(c, SS_INV_DT0)) * PRM().dt;
     collide(c);
     solveIslands(c, dtRatio, allowSleeping);
+#ifndef B2G_EXPERIMENT_NO_TOI  /* tuning experiment only: wrong physics, shows the register cost of the TOI call chain */
     solveTOI(c);
+#endif
     stF(c, sslot(c, SS_INV_DT0), PRM().inv_dt);
     for (int b = 0; b < h.nb; ++b) {  // ClearForces
         st4(c, bslot(c, b, SB_FORCE4), mk4(0.0f, 0.0f, 0.0f, 0.0f));

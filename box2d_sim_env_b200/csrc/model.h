@@ -182,7 +182,8 @@ enum ScalarState {
     SS_MOVED_LO = B2G_F(1, 0), SS_MOVED_HI = B2G_F(1, 1),
     SS_TARGET_AVAIL = B2G_F(1, 2),  // bit r: robot r has a controller target
     SS_ABORT = B2G_F(1, 3),      // guarded stepping: bit0 a forbidden BeginContact fired, bits 8.. steps executed
-    SS_CHUNKS = 2
+    SS_DISABLED_LO = B2G_F(2, 0), SS_DISABLED_HI = B2G_F(2, 1),  // bit f: fixture f has categoryBits = 0 (Box2DLink::setEnabled(false))
+    SS_CHUNKS = 3
 };
 
 }  // namespace b2g

@@ -134,6 +134,15 @@ b2g_status b2g_batch_get_state_dev(b2g_batch* batch, float* q, float* qd);
 b2g_status b2g_batch_set_object_pose(b2g_batch* batch, int object, const float* pose);
 b2g_status b2g_batch_get_object_pose(b2g_batch* batch, int object, float* pose);
 
+/* Box2DWorld::setToRest (:3550-3558): setDOFVelocities(0) on every object of every world */
+b2g_status b2g_batch_set_to_rest(b2g_batch* batch);
+/* Box2DWorld::atRest(threshold) (:3435-3452): out[w] = 1 iff every DOF velocity of world w is within the threshold */
+b2g_status b2g_batch_at_rest(b2g_batch* batch, float threshold, int32_t* out);
+/* Box2DLink::setEnabled (:802-822) for the link whose body index is `body` (links in creation order, body 0 = ground):
+ * a disabled link keeps its body but collides with nothing (categoryBits = 0).  enabled: [n_worlds] or NULL to apply
+ * enabled_all to every world. */
+b2g_status b2g_batch_set_link_enabled(b2g_batch* batch, int body, const uint8_t* enabled, int enabled_all);
+
 /* Box2DRobotVelocityController::setTargetVelocity (src/sim_env/Box2DController.cpp:42-63) for robot
  * `object` in every world; v: [n_worlds][n_dofs of that robot].  The controller is then evaluated
  * in-kernel before every step (Box2DRobot::control, Box2DWorld.cpp:2284-2310). */

@@ -334,3 +334,38 @@ def test_status_bits(b2g):
     batch.setWorldState(q, qd)
     batch.stepPhysics(2)
     assert batch.status().tolist() == [0, 0, 2, 0]
+
+
+def test_link_enable_disable_rest(b2g):
+    """Box2DLink::setEnabled (reference :802-822): a disabled link stops colliding (contacts are filtered out on the next
+    Collide), re-enabling brings the pairs back; plus setToRest / atRest."""
+    n = 64
+    batch, worlds = scattered_start(b2g, ENV_A, n, seed=91)
+    batch.stepPhysics(10)
+    for ow in worlds:
+        ow.step(10)
+    obj1_body = batch.model.objects[1]["first_body"]
+    flags = (np.arange(n) % 2 == 0)
+    batch.setLinkEnabled(obj1_body, ~flags)          # disable obj1 in the even worlds
+    for w, ow in enumerate(worlds):
+        ow.set_link_enabled(obj1_body, not flags[w])
+    batch.stepPhysics(15)
+    for ow in worlds:
+        ow.step(15)
+    assert_same(batch, worlds, "after disabling obj1 in half of the worlds")
+    counts, cio, _ = batch.contacts()
+    fix_of_obj1 = {f for f, row in enumerate(batch.model.fixture_model()[0]) if row[0] == obj1_body}
+    for w in np.nonzero(flags)[0]:
+        assert not any(int(f) in fix_of_obj1 for f in cio[w, :counts[w], :2].reshape(-1)), "disabled link still has contacts"
+    batch.setLinkEnabled(obj1_body, True)
+    for ow in worlds:
+        ow.set_link_enabled(obj1_body, True)
+    batch.stepPhysics(15)
+    for ow in worlds:
+        ow.step(15)
+    assert_same(batch, worlds, "after re-enabling obj1")
+    assert not batch.atRest().all()
+    batch.setToRest()
+    assert batch.atRest().all()
+    gq, gqd = batch.getWorldState()
+    assert not gqd.any()
