@@ -44,7 +44,8 @@ ABI_SYMBOLS = [
     "b2g_model_get_fixtures", "b2g_model_get_joints", "b2g_batch_create", "b2g_batch_destroy", "b2g_batch_set_params",
     "b2g_batch_status", "b2g_batch_stream", "b2g_batch_sync", "b2g_batch_set_state", "b2g_batch_set_state_dev",
     "b2g_batch_get_state", "b2g_batch_get_state_dev", "b2g_batch_set_object_pose", "b2g_batch_get_object_pose",
-    "b2g_batch_set_to_rest", "b2g_batch_at_rest", "b2g_batch_set_link_enabled",
+    "b2g_batch_set_to_rest", "b2g_batch_at_rest", "b2g_batch_set_link_enabled", "b2g_batch_objects_in_aabb",
+    "b2g_batch_is_physically_feasible",
     "b2g_batch_set_target_velocity", "b2g_batch_set_target_velocity_dev", "b2g_batch_step", "b2g_batch_step_record",
     "b2g_batch_step_guarded", "b2g_batch_rollout_dev",
     "b2g_batch_get_bodies", "b2g_batch_get_fat_aabbs", "b2g_batch_get_joints", "b2g_batch_get_contacts",
@@ -103,6 +104,8 @@ def lib():
     L.b2g_batch_set_to_rest.argtypes = [vp]
     L.b2g_batch_at_rest.argtypes = [vp, C.c_float, ip]
     L.b2g_batch_set_link_enabled.argtypes = [vp, C.c_int, vp, C.c_int]
+    L.b2g_batch_objects_in_aabb.argtypes = [vp, fp, C.c_int, vp]
+    L.b2g_batch_is_physically_feasible.argtypes = [vp, ip]
     L.b2g_batch_set_target_velocity.argtypes = [vp, C.c_int, fp]
     L.b2g_batch_set_target_velocity_dev.argtypes = [vp, C.c_int, fp]
     L.b2g_batch_step.argtypes = [vp, C.c_int, C.c_int, C.c_int]
@@ -388,6 +391,19 @@ class BatchBox2DWorld:
         pose = np.zeros((self.n_worlds, 3), np.float32)
         _check(lib().b2g_batch_get_object_pose(self.h, obj, _ptr(pose)))
         return pose
+
+    def getObjects(self, aabb, exclude_robots=True):
+        """Box2DWorld::getObjects(aabb, ...) (:3207-3254): bool [n_worlds, n_objects] (model object order)."""
+        box = _f32(aabb)
+        hits = np.zeros((self.n_worlds, self.model.n_objects), np.uint8)
+        _check(lib().b2g_batch_objects_in_aabb(self.h, _ptr(box), int(exclude_robots), _ptr(hits)))
+        return hits.astype(bool)
+
+    def isPhysicallyFeasible(self):
+        """Box2DWorld::isPhysicallyFeasible (:3370-3400), one bool per world."""
+        out = np.zeros(self.n_worlds, np.int32)
+        _check(lib().b2g_batch_is_physically_feasible(self.h, _ptr(out)))
+        return out.astype(bool)
 
     def setToRest(self):
         """Box2DWorld::setToRest (:3550-3558)."""

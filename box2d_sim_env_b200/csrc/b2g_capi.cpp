@@ -520,6 +520,34 @@ b2g_status b2g_batch_at_rest(b2g_batch* b, float threshold, int32_t* out) {
     return B2G_OK;
 }
 
+// getObjects(aabb, objects, exclude_robots) (:3207-3254): the box is scaled like the reference does (:3210-3214)
+b2g_status b2g_batch_objects_in_aabb(b2g_batch* b, const float aabb[4], int exclude_robots, uint8_t* hits) {
+    if (!b || !aabb || !hits) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    const float s = b->m.h.scale;
+    const int no = b->m.h.no;
+    size_t bytes = (size_t)b->N * no;
+    CU(b->stageC.reserve(bytes));
+    CU(launchObjectsInAABB(b->L(), s * aabb[0], s * aabb[1], s * aabb[2], s * aabb[3], (unsigned char*)b->stageC.p));
+    CU(cudaMemcpyAsync(hits, b->stageC.p, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    if (exclude_robots)
+        for (long long w = 0; w < b->N; ++w)
+            for (int o = 0; o < no; ++o)
+                if (b->m.objects[o].isRobot) hits[(size_t)w * no + o] = 0;
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_is_physically_feasible(b2g_batch* b, int32_t* out) {
+    if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    CU(b->stageC.reserve((size_t)b->N * 4));
+    CU(launchPhysicallyFeasible(b->L(), (int*)b->stageC.p));
+    CU(cudaMemcpyAsync(out, b->stageC.p, (size_t)b->N * 4, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
 b2g_status b2g_batch_set_link_enabled(b2g_batch* b, int body, const uint8_t* enabled, int enabled_all) {
     if (!b || body <= 0 || body >= b->m.h.nb) return fail(B2G_ERR_INVALID, "unknown link (body 0 is the ground)");
     CU(cudaSetDevice(b->device));

@@ -9,6 +9,7 @@
 #include <cstdlib>
 
 #include "b2g_launch.h"
+#include "b2g_query.cuh"
 #include "b2g_world.cuh"
 
 namespace b2g {
@@ -213,6 +214,40 @@ __global__ void k_at_rest(const __grid_constant__ ModelHeader hdr, const uint32_
     out[w] = rest ? 1 : 0;
 }
 
+// Box2DWorld::getObjects(aabb, ...) (:3207-3254) for every world: hits [N][no].  The query box lives in a scratch fixture
+// record behind the model blob (index fQuery) so that GJK reads it like any other proxy.
+__global__ void k_objects_in_aabb(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
+                                  StepParams prm, float lx, float ly, float ux, float uy, int fQuery,
+                                  unsigned char* __restrict__ hits) {
+    B2G_STAGE();
+    if (threadIdx.x == 0) {
+        uint32_t* r = g_sm + kHdrWords + hdr.oFix + fQuery * MF_STRIDE;
+        const float hx = 0.5f * (ux - lx), hy = 0.5f * (uy - ly);  // b2AABB::GetExtents -> SetAsBox(hx, hy)
+        const float vx[4] = {-hx, hx, hx, -hx}, vy[4] = {-hy, -hy, hy, hy};
+        r[MF_BODY] = 0;
+        r[MF_COUNT] = 4;
+        for (int i = 0; i < 4; ++i) {
+            r[MF_VERTS + 2 * i] = __float_as_uint(vx[i]);
+            r[MF_VERTS + 2 * i + 1] = __float_as_uint(vy[i]);
+        }
+    }
+    __syncthreads();
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= N) return;
+    Ctx c;
+    c.P = worldBase(S, hdr.stateChunks, w);
+    unsigned char h8[kMaxBodies];
+    objectsInAABB(c, lx, ly, ux, uy, fQuery, h8);
+    for (int o = 0; o < hdr.no; ++o) hits[(size_t)w * hdr.no + o] = h8[o];
+}
+
+// Box2DWorld::isPhysicallyFeasible (:3370-3400) for every world
+__global__ void k_physically_feasible(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
+                                      long long N, StepParams prm, int* __restrict__ out) {
+    B2G_PROLOGUE();
+    out[w] = physicallyFeasible(c) ? 1 : 0;
+}
+
 // guarded stepping: clear the abort flag / executed-step counter of every world
 __global__ void k_set_word(float* S, long long N, int stateChunks, int off, int value) {
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -388,6 +423,21 @@ cudaError_t launchSetLinkEnabled(const Launch& L, int body, const unsigned char*
     LAUNCH(k_set_link_enabled, body, enabled, all);
 }
 cudaError_t launchAtRest(const Launch& L, float threshold, int* out) { LAUNCH(k_at_rest, threshold, out); }
+cudaError_t launchPhysicallyFeasible(const Launch& L, int* out) { LAUNCH(k_physically_feasible, out); }
+cudaError_t launchObjectsInAABB(const Launch& L, float lx, float ly, float ux, float uy, unsigned char* hits) {
+    // scratch fixture record: first MF_STRIDE-aligned slot (relative to oFix) behind the blob
+    const int fQuery = (L.h.words - L.h.oFix + MF_STRIDE - 1) / MF_STRIDE;
+    const size_t bytes = ((size_t)kHdrWords + L.h.oFix + (size_t)(fQuery + 1) * MF_STRIDE) * 4 + smemPad();
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)k_objects_in_aabb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+    }
+    int threads = L.block;
+    unsigned blocks = (unsigned)((L.N + threads - 1) / threads);
+    k_objects_in_aabb<<<blocks, threads, bytes, L.stream>>>(L.h, L.blob, L.S, L.N, L.prm, lx, ly, ux, uy, fQuery, hits);
+    ++g_launches;
+    return cudaGetLastError();
+}
 cudaError_t launchRecordTouching(const Launch& L) { LAUNCH(k_record_touching); }
 cudaError_t launchStepGuarded(const Launch& L, int steps, int execCtrl, int allowSleep) {
     LAUNCH(k_step_guarded, steps, execCtrl, allowSleep);

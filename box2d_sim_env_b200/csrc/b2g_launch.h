@@ -30,6 +30,8 @@ cudaError_t launchStep(const Launch& L, int object, const float* targets, int nT
 cudaError_t launchSetToRest(const Launch& L);
 cudaError_t launchSetLinkEnabled(const Launch& L, int body, const unsigned char* enabled, int all);
 cudaError_t launchAtRest(const Launch& L, float threshold, int* out);
+cudaError_t launchPhysicallyFeasible(const Launch& L, int* out);
+cudaError_t launchObjectsInAABB(const Launch& L, float lx, float ly, float ux, float uy, unsigned char* hits);
 cudaError_t launchRecordTouching(const Launch& L);
 cudaError_t launchStepGuarded(const Launch& L, int steps, int execCtrl, int allowSleep);
 cudaError_t launchGetBodies(const Launch& L, float* out);

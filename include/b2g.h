@@ -138,6 +138,13 @@ b2g_status b2g_batch_get_object_pose(b2g_batch* batch, int object, float* pose);
 b2g_status b2g_batch_set_to_rest(b2g_batch* batch);
 /* Box2DWorld::atRest(threshold) (:3435-3452): out[w] = 1 iff every DOF velocity of world w is within the threshold */
 b2g_status b2g_batch_at_rest(b2g_batch* batch, float threshold, int32_t* out);
+/* Box2DWorld::getObjects(aabb, objects, exclude_robots) (:3207-3254, Box2DAABBQuery :2979-2998): which objects have a
+ * fixture overlapping the box aabb = (min_x, min_y, max_x, max_y) in user units — fat-AABB query, then the exact
+ * b2TestOverlap (GJK) against the box.  One box for all worlds; hits [n_worlds][n_objects] (model object order). */
+b2g_status b2g_batch_objects_in_aabb(b2g_batch* batch, const float aabb[4], int exclude_robots, uint8_t* hits);
+/* Box2DWorld::isPhysicallyFeasible (:3370-3400): out[w] = 0 iff two touching links of world w overlap by more than
+ * 1e-4 m^2 (convex-polygon clipping in place of boost::geometry::intersection). Runs checkCollision first. */
+b2g_status b2g_batch_is_physically_feasible(b2g_batch* batch, int32_t* out);
 /* Box2DLink::setEnabled (:802-822) for the link whose body index is `body` (links in creation order, body 0 = ground):
  * a disabled link keeps its body but collides with nothing (categoryBits = 0).  enabled: [n_worlds] or NULL to apply
  * enabled_all to every world. */

@@ -172,6 +172,26 @@ public:
         return hit;
     }
 
+    // getObjects(aabb, objects, exclude_robots) (:3207-3254): hits[w * n_objects + o]
+    std::vector<uint8_t> getObjects(const float aabb[4], bool exclude_robots = true) {
+        std::vector<uint8_t> hits((size_t)_n * _objects.size());
+        check(b2g_batch_objects_in_aabb(_batch, aabb, exclude_robots, hits.data()));
+        return hits;
+    }
+    // isPhysicallyFeasible (:3370-3400), atRest (:3435-3452), setToRest (:3550-3558), Box2DLink::setEnabled (:802-822)
+    std::vector<bool> isPhysicallyFeasible() {
+        std::vector<int32_t> out(_n);
+        check(b2g_batch_is_physically_feasible(_batch, out.data()));
+        return std::vector<bool>(out.begin(), out.end());
+    }
+    std::vector<bool> atRest(float threshold = 0.0001f) {
+        std::vector<int32_t> out(_n);
+        check(b2g_batch_at_rest(_batch, threshold, out.data()));
+        return std::vector<bool>(out.begin(), out.end());
+    }
+    void setToRest() { check(b2g_batch_set_to_rest(_batch)); }
+    void setLinkEnabled(int body, bool enabled) { check(b2g_batch_set_link_enabled(_batch, body, nullptr, enabled)); }
+
     // per-world status after the last call (contact capacity exceeded -> std::runtime_error)
     std::vector<int32_t> status() {
         std::vector<int32_t> s(_n);

@@ -60,6 +60,8 @@ def lib():
         L.b2o_world_get_joints.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2o_world_get_contacts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.b2o_world_check_collision.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.b2o_world_objects_in_aabb.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.b2o_world_is_physically_feasible.argtypes = [C.c_void_p]
         L.b2o_world_step_record.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.b2o_world_set_link_enabled.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.b2o_world_trace_islands.argtypes = [C.c_void_p, C.c_int]
@@ -302,6 +304,16 @@ class OracleWorld:
         fo = np.zeros((self.MAXC, 6), np.float32)
         n = lib().b2o_world_check_collision(self.h, _ptr(io), _ptr(fo), self.MAXC)
         return io[:n].copy(), fo[:n].copy()
+
+    def objects_in_aabb(self, aabb, exclude_robots=True, n_objects=None):
+        n = n_objects if n_objects is not None else len(self.env.desc["robots"]) + len(self.env.desc["objects"])
+        hits = np.zeros(n, np.int32)
+        box = _f32(aabb)
+        lib().b2o_world_objects_in_aabb(self.h, _ptr(box), int(exclude_robots), _ptr(hits))
+        return hits.astype(bool)
+
+    def is_physically_feasible(self):
+        return bool(lib().b2o_world_is_physically_feasible(self.h))
 
     def step_record(self, steps=1, execute_controllers=True, allow_sleeping=True):
         io = np.zeros((self.MAXC, 4), np.int32)

@@ -307,6 +307,14 @@ int b2o_world_check_collision(void* wp, int* iout, float* fout, int maxContacts)
     return writeContacts(cs, iout, fout, maxContacts);
 }
 
+// getObjects(aabb): hits[i] for creation-order object i; isPhysicallyFeasible
+void b2o_world_objects_in_aabb(void* wp, const float* aabb, int excludeRobots, int* hits) {
+    std::vector<int> h;
+    ((OWorld*)wp)->getObjectsInAABB(aabb, excludeRobots != 0, h);
+    for (size_t i = 0; i < h.size(); ++i) hits[i] = h[i];
+}
+int b2o_world_is_physically_feasible(void* wp) { return ((OWorld*)wp)->isPhysicallyFeasible() ? 1 : 0; }
+
 int b2o_world_step_record(void* wp, int steps, int execCtrl, int allowSleep, int* iout, float* fout, int maxContacts) {
     std::vector<OContact> cs;
     ((OWorld*)wp)->stepPhysicsRecord(cs, steps, execCtrl != 0, allowSleep != 0);

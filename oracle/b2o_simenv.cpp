@@ -600,6 +600,87 @@ void OWorld::stepPhysicsRecord(std::vector<OContact>& contacts, int steps, bool 
     contacts = recorded;
 }
 
+void OWorld::getObjectsInAABB(const float aabb[4], bool excludeRobots, std::vector<int>& hits) {
+    hits.assign(creationOrder.size(), 0);
+    AABB query;
+    query.lowerBound = Vec2(scale * aabb[0], scale * aabb[1]);  // :3210-3214
+    query.upperBound = Vec2(scale * aabb[2], scale * aabb[3]);
+    Vec2 extents = 0.5f * (query.upperBound - query.lowerBound);  // b2AABB::GetExtents
+    Vec2 center = 0.5f * (query.lowerBound + query.upperBound);   // b2AABB::GetCenter
+    PolygonShape box;
+    box.SetAsBox(extents.x, extents.y);
+    Transform xfQ;
+    xfQ.p = center;
+    xfQ.q.s = 0.0f;  // b2Transform::Set(center, 0)
+    xfQ.q.c = 1.0f;
+    // b2World::QueryAABB: every proxy whose fat AABB overlaps the box is reported
+    for (Body* body : b2->bodies) {
+        if (body == ground) continue;  // b_collision_ignore (:2988)
+        OLink* link = (OLink*)body->userData;
+        for (Fixture* f : body->fixtures) {
+            if (!TestOverlap(query, f->fatAABB)) continue;
+            if (!TestOverlapShapes(&box, &f->shape, xfQ, body->xf)) continue;
+            for (size_t i = 0; i < creationOrder.size(); ++i)
+                if (creationOrder[i] == link->object && !(excludeRobots && link->object->isRobot)) hits[i] = 1;
+        }
+    }
+}
+
+namespace {
+// Sutherland-Hodgman: area of the intersection of two convex counter-clockwise polygons
+float convexIntersectionArea(const Vec2* a, int na, const Vec2* b, int nb) {
+    Vec2 bufA[18], bufB[18];
+    Vec2* in = bufA;
+    Vec2* out = bufB;
+    int n = na;
+    for (int i = 0; i < na; ++i) in[i] = a[i];
+    for (int e = 0; e < nb && n > 0; ++e) {
+        const Vec2 c1 = b[e], c2 = b[e + 1 < nb ? e + 1 : 0];
+        const Vec2 edge = c2 - c1;
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const Vec2 p = in[i], q = in[i + 1 < n ? i + 1 : 0];
+            const float dp = Cross(edge, p - c1), dq = Cross(edge, q - c1);
+            if (dq >= 0.0f) {
+                if (dp < 0.0f) { float t = dp / (dp - dq); out[m++] = p + t * (q - p); }
+                out[m++] = q;
+            } else if (dp >= 0.0f) {
+                float t = dp / (dp - dq);
+                out[m++] = p + t * (q - p);
+            }
+        }
+        Vec2* tmp = in; in = out; out = tmp;
+        n = m;
+    }
+    if (n < 3) return 0.0f;
+    float twice = 0.0f;
+    for (int i = 1; i + 1 < n; ++i) twice += Cross(in[i] - in[0], in[i + 1] - in[0]);
+    return 0.5f * twice;
+}
+}  // namespace
+
+bool OWorld::isPhysicallyFeasible() {
+    b2->UpdateContacts();  // checkCollision(contacts) :3373
+    const float inv = invScale();
+    for (int k = (int)b2->contacts.size() - 1; k >= 0; --k) {
+        Contact* c = b2->contacts[k];
+        if (!(c->IsTouching() && c->IsEnabled())) continue;
+        Body* bA = c->fixtureA->body;
+        Body* bB = c->fixtureB->body;
+        for (Fixture* fa : bA->fixtures) {
+            Vec2 va[kMaxPolygonVertices];
+            for (int i = 0; i < fa->shape.count; ++i) va[i] = Mul(bA->xf, fa->shape.vertices[i]);
+            for (Fixture* fb : bB->fixtures) {
+                Vec2 vb[kMaxPolygonVertices];
+                for (int i = 0; i < fb->shape.count; ++i) vb[i] = Mul(bB->xf, fb->shape.vertices[i]);
+                float area = convexIntersectionArea(va, fa->shape.count, vb, fb->shape.count);
+                if (inv * inv * area > 0.0001f) return false;  // MAX_ALLOWED_INTERSECTION_AREA (:22)
+            }
+        }
+    }
+    return true;
+}
+
 int OWorld::stateDim() const {
     int n = 0;
     for (OObject* o : creationOrder) n += (int)o->numDofs;

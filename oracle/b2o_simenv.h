@@ -179,6 +179,10 @@ struct OWorld : ContactListener {
     // checkCollision(std::vector<Contact>&) — all touching contacts after UpdateContacts()
     void updateContactCache(std::vector<OContact>& out);
     void BeginContact(Contact* c) override;
+    // getObjects(aabb, ...) (:3207-3254, Box2DAABBQuery :2979-2998): hits[i] = 1 for creationOrder[i]
+    void getObjectsInAABB(const float aabb[4], bool excludeRobots, std::vector<int>& hits);
+    // isPhysicallyFeasible (:3370-3400); convex clipping in place of boost::geometry::intersection
+    bool isPhysicallyFeasible();
     OContact makeContact(Contact* c) const;
     // full DOF state in creation order (robots, then objects): dynamic objects contribute
     // [x, y, theta, joints...], static objects [joints...]

@@ -369,3 +369,28 @@ def test_link_enable_disable_rest(b2g):
     assert batch.atRest().all()
     gq, gqd = batch.getWorldState()
     assert not gqd.any()
+
+
+def test_region_query_and_feasibility(b2g):
+    """getObjects(aabb) (reference :3207-3254) and isPhysicallyFeasible (:3370-3400) against the oracle on worlds whose
+    objects are scattered over (and into) each other."""
+    n = 192
+    batch = make_batch(b2g, ENV_A, n)
+    worlds = oracle_worlds(load_env_dict(ENV_A), n)
+    q, qd = random_states(batch.model, n, seed=95, spread=0.5)
+    batch.setWorldState(q, qd, reset_caches=True)
+    for w, ow in enumerate(worlds):
+        ow.set_state(q[w], qd[w])
+    seen = set()
+    for box, excl in (([-0.3, -0.3, 0.3, 0.3], False), ([0.0, 0.0, 1.0, 1.0], True), ([-3.0, -3.0, 3.0, 3.0], False),
+                      ([5.0, 5.0, 6.0, 6.0], False)):
+        hits = batch.getObjects(box, exclude_robots=excl)
+        for w, ow in enumerate(worlds):
+            assert np.array_equal(hits[w], ow.objects_in_aabb(box, exclude_robots=excl)), "world %d box %s" % (w, box)
+        seen |= {tuple(r) for r in hits.tolist()}
+    assert len(seen) >= 4, "region queries should see several different hit patterns"
+    feas = batch.isPhysicallyFeasible()
+    ofeas = np.array([ow.is_physically_feasible() for ow in worlds])
+    assert np.array_equal(feas, ofeas)
+    assert 0 < feas.sum() < n, "scenario must contain feasible and infeasible worlds"
+    assert_same(batch, worlds, "after isPhysicallyFeasible (runs UpdateContacts)")

@@ -188,3 +188,24 @@ def test_contact_and_toi_vs_static(oracle):
     assert toi_events > 0
     assert q[8] < 1.2            # did not pass through the bar centred at y = 1.2
     assert qd[8] < 0.0           # bounced back
+
+
+def test_region_query_known_answers(oracle):
+    """getObjects(aabb): obj1 sits at (0.9, 1.0) in test_env.yaml, the robot at the origin, obj2 at (2.9, 1.2)."""
+    w = oracle.OracleWorld(load_env_dict(ENV_A))
+    assert w.objects_in_aabb([0.5, 0.5, 1.5, 1.5], exclude_robots=False).tolist() == [False, True, False]
+    assert w.objects_in_aabb([-5, -5, 5, 5], exclude_robots=True).tolist() == [False, True, True]
+    assert w.objects_in_aabb([-5, -5, 5, 5], exclude_robots=False).tolist() == [True, True, True]
+    assert not w.objects_in_aabb([10, 10, 11, 11], exclude_robots=False).any()
+    # a box that only reaches the fat AABB margin of obj1 but not its shape must not report it (exact GJK test)
+    lo_x = 0.9 + 0.1 + 0.0015 + 0.003   # obj1 is a 0.2 m box: half width + polygon radius (1 mm) ... + a bit
+    assert not w.objects_in_aabb([lo_x + 0.05, 0.0, lo_x + 0.5, 2.0], exclude_robots=False)[1]
+
+
+def test_feasibility_known_answers(oracle):
+    w = oracle.OracleWorld(load_env_dict(ENV_A))
+    assert w.is_physically_feasible()
+    w.set_object_pose(1, 0.2, 0.0, 0.0)      # obj1 pushed into the robot base: overlap area >> 1e-4 m^2
+    assert not w.is_physically_feasible()
+    w.set_object_pose(1, 3.0, -3.0, 0.0)     # far away again
+    assert w.is_physically_feasible()
