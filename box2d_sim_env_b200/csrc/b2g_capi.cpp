@@ -76,6 +76,7 @@ struct b2g_batch {
     cudaStream_t stream = nullptr;
     StepParams prm{0.01f, 1.0f / 0.01f, 15, 15, 0, 0, nullptr, nullptr, nullptr, nullptr};
     int block = 32;
+    int stepBlock = 32;
     DevBuf stageA, stageB, stageC, stageD, stageE;
     std::vector<SavedState> stack;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
@@ -90,6 +91,7 @@ struct b2g_batch {
         l.prm = prm;
         l.stream = stream;
         l.block = block;
+        l.stepBlock = stepBlock;
         return l;
     }
 };
@@ -303,7 +305,18 @@ b2g_status b2g_batch_create(const b2g_model* model, int64_t n_worlds, int device
     const char* envBlock = getenv("B2G_BLOCK");
     if (envBlock) b->block = atoi(envBlock);
     else b->block = n_worlds <= 148 * 32 * 8 ? 32 : 64;
-    if (b->block < 32 || b->block > 1024 || (b->block & 31)) b->block = 32;
+    if (b->block < 32 || b->block > 1024 || (b->block & (b->block - 1))) b->block = 32;
+    // CTA size of the stepping kernel: its warps walk the solver phases together (phase barriers), which keeps the
+    // instruction cache on one phase; one warp per CTA while the batch does not fill the GPU anyway
+    const char* envStep = getenv("B2G_STEP_BLOCK");
+    if (envStep) b->stepBlock = atoi(envStep);
+    else if (envBlock) b->stepBlock = b->block;
+    else {  // about two CTAs per SM once the batch is large enough (measured optimum on B200, tools/block_sweep.sh)
+        long long want = (n_worlds + 295) / 296;
+        b->stepBlock = 32;
+        while (b->stepBlock < want && b->stepBlock < 256) b->stepBlock *= 2;
+    }
+    if (b->stepBlock < 32 || b->stepBlock > kWorldPad || (b->stepBlock & (b->stepBlock - 1))) b->stepBlock = 32;
     auto cleanup = [&](cudaError_t err, const char* what) {
         b2g_batch_destroy(b);
         return cudaFail(err, what);
@@ -313,7 +326,9 @@ b2g_status b2g_batch_create(const b2g_model* model, int64_t n_worlds, int device
     if ((e = cudaMemcpy(b->blob, b->m.blob.data(), b->m.blob.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
         return cleanup(e, "cudaMemcpy(model)");
     // state[tile][chunk][lane]: tiles of 32 worlds, 16-byte chunks (model.h)
-    size_t tiles = ((size_t)n_worlds + kTileWorlds - 1) / kTileWorlds;
+    // padded to a multiple of kWorldPad worlds: the padding worlds are idle copies that let every thread of a k_step CTA
+    // take part in the phase barriers
+    size_t tiles = ((size_t)n_worlds + kWorldPad - 1) / kWorldPad * (kWorldPad / kTileWorlds);
     size_t stateBytes = tiles * (size_t)b->m.h.stateChunks * kChunkBytes;
     if ((e = cudaMalloc((void**)&b->S, stateBytes)) != cudaSuccess) return cleanup(e, "cudaMalloc(state)");
     if ((e = cudaMalloc((void**)&b->tmpl, (size_t)b->m.h.stateChunks * 16)) != cudaSuccess) return cleanup(e, "cudaMalloc(template)");

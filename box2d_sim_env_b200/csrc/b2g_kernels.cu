@@ -144,15 +144,21 @@ __global__ void k_set_target(const __grid_constant__ ModelHeader hdr, const uint
 __global__ void k_step(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
                        StepParams prm, int object, const float* __restrict__ targets, int nTargets, int stepsPerTarget,
                        int executeControllers, int allowSleeping) {
-    B2G_PROLOGUE();
+    // CTA-synchronised stepping: every thread of the CTA owns a world that exists in memory (the state array is padded to
+    // a multiple of kWorldPad worlds, the padding worlds are valid idle copies of the loaded world), so all threads walk
+    // the phase barriers of stepWorld<true> together.
+    B2G_STAGE();
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    Ctx c;
+    c.P = worldBase(S, hdr.stateChunks, w);
     for (int t = 0; t < nTargets; ++t) {
-        if (targets != nullptr) {
+        if (targets != nullptr && w < N) {
             int n = mI(c, mobj(c, object, MO_NDOFS));
             float lv[kMaxDofsPerObject];
             for (int i = 0; i < n; ++i) lv[i] = targets[((size_t)t * N + w) * n + i];
             setTarget(c, object, lv);
         }
-        for (int s = 0; s < stepsPerTarget; ++s) stepWorld(c, executeControllers != 0, allowSleeping != 0);
+        for (int s = 0; s < stepsPerTarget; ++s) stepWorld<true>(c, executeControllers != 0, allowSleeping != 0);
     }
 }
 
@@ -416,7 +422,14 @@ cudaError_t launchGetPose(const Launch& L, int object, float* pose) { LAUNCH(k_g
 cudaError_t launchSetTarget(const Launch& L, int object, const float* v) { LAUNCH(k_set_target, object, v); }
 cudaError_t launchStep(const Launch& L, int object, const float* targets, int nTargets, int stepsPerTarget, int execCtrl,
                        int allowSleep) {
-    LAUNCH(k_step, object, targets, nTargets, stepsPerTarget, execCtrl, allowSleep);
+    cudaError_t e = prepare((const void*)k_step, L.h);
+    if (e != cudaSuccess) return e;
+    int threads = L.stepBlock;
+    unsigned blocks = (unsigned)((L.N + threads - 1) / threads);  // every thread has a (possibly padding) world
+    k_step<<<blocks, threads, smemBytes(L.h), L.stream>>>(L.h, L.blob, L.S, L.N, L.prm, object, targets, nTargets, stepsPerTarget,
+                                                       execCtrl, allowSleep);
+    ++g_launches;
+    return cudaGetLastError();
 }
 cudaError_t launchSetToRest(const Launch& L) { LAUNCH(k_set_to_rest); }
 cudaError_t launchSetLinkEnabled(const Launch& L, int body, const unsigned char* enabled, int all) {
@@ -452,7 +465,7 @@ cudaError_t launchCheckCollision(const Launch& L, int* counts, int* iout, float*
     LAUNCH(k_check_collision, counts, iout, fout, maxPer);
 }
 cudaError_t launchBroadcast(const Launch& L, const float* tmpl) {
-    long long tiles = (L.N + kTileWorlds - 1) / kTileWorlds;
+    long long tiles = (L.N + kWorldPad - 1) / kWorldPad * (kWorldPad / kTileWorlds);  // padding worlds included
     long long total = tiles * L.h.stateChunks * kTileWorlds;
     int threads = 256;
     long long want = (total + threads - 1) / threads;

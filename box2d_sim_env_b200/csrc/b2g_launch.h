@@ -14,6 +14,7 @@ struct Launch {
     StepParams prm;
     cudaStream_t stream;
     int block;             // threads per CTA
+    int stepBlock;         // threads per CTA of k_step (power of two <= kWorldPad)
 };
 
 unsigned long long launchCount();

@@ -326,6 +326,82 @@ DEV void revoluteSolveVel(Ctx c, int jr, int modelFlags) {
     if (!staticB) stVelAt(c, off.w, B);
 }
 
+// b2Island::Solve's joint work for an island that consists of one dynamic body and its ground-friction joint:
+// InitVelocityConstraints (warm start included) and all velocity iterations of b2FrictionJoint with the body's
+// velocity, the joint's effective masses and its accumulated impulses held in registers -- the same operations in
+// the same order as jointInit + velIters x frictionSolveVel<true>, minus the round trips through memory.
+DEVN void frictionIslandSolve(Ctx c, int j, float dtRatio, int velIters) {
+    const int jr = mjoint(c, j, 0);
+    const int4 off = mi4(c, jr + MJ_SOFF);    // js jw bodyA bodyB (state byte offsets)
+    const float4 arm = m4(c, jr + MJ_RA0X);   // localAnchorA - localCenterA, localAnchorB - localCenterB
+    const float4 im = m4(c, jr + MJ_MA);      // mA iA mB iB
+    const float2 hmax = m2(c, jr + MJ_HMAXFORCE);
+    const int js = off.x;
+    float aA = ldF(c, off.z + SB_A);
+    float aB = ldF(c, off.w + SB_A);
+    Vel A = zeroVel();
+    Vel B = ldVelAt(c, off.w);
+    float4 acc4 = ld4(c, js + SJ_IMPULSE4);
+    Rot qA = rotOf(aA), qB = rotOf(aB);
+    V2 rA = mul(qA, mk(arm.x, arm.y));
+    V2 rB = mul(qB, mk(arm.z, arm.w));
+    float mA = im.x, mB = im.z;
+    float iA = im.y, iB = im.w;
+    // ---- InitVelocityConstraints
+    float kxx = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
+    float kxy = -iA * rA.x * rA.y - iB * rB.x * rB.y;
+    float kyx = kxy;
+    float kyy = mA + mB + iA * rA.x * rA.x + iB * rB.x * rB.x;
+    float a = kxx, b = kyx, cc = kxy, d = kyy;
+    float det = a * d - b * cc;
+    if (det != 0.0f) det = 1.0f / det;
+    const float exx = det * d, exy = -det * cc, eyx = -det * b, eyy = det * a;
+    float angularMass = iA + iB;
+    if (angularMass > 0.0f) angularMass = 1.0f / angularMass;
+    {
+        V2 P = mk(acc4.x * dtRatio, acc4.y * dtRatio);
+        float ang = acc4.z * dtRatio;
+        acc4 = mk4(P.x, P.y, ang, angularMass);
+        A.v = A.v - mA * P;
+        A.w -= iA * (cross(rA, P) + ang);
+        B.v = B.v + mB * P;
+        B.w += iB * (cross(rB, P) + ang);
+    }
+    // a static bodyA is written back unchanged by the reference (x -= 0 * impulse); here it stays the constant +0
+    A = zeroVel();
+    // ---- velocity iterations
+    for (int it = 0; it < velIters; ++it) {
+        {
+            float Cdot = B.w - A.w;
+            float impulse = -acc4.w * Cdot;
+            float oldImpulse = acc4.z;
+            float maxImpulse = hmax.y;
+            float acc = clampT(oldImpulse + impulse, -maxImpulse, maxImpulse);
+            acc4.z = acc;
+            impulse = acc - oldImpulse;
+            B.w += iB * impulse;
+        }
+        {
+            V2 Cdot = B.v + cross(B.w, rB) - A.v - cross(A.w, rA);
+            V2 impulse = -mk(exx * Cdot.x + eyx * Cdot.y, exy * Cdot.x + eyy * Cdot.y);
+            V2 oldImpulse = mk(acc4.x, acc4.y);
+            V2 acc = oldImpulse + impulse;
+            float maxImpulse = hmax.x;
+            if (dot(acc, acc) > maxImpulse * maxImpulse) {
+                normalize(acc);
+                acc = mk(acc.x * maxImpulse, acc.y * maxImpulse);
+            }
+            acc4.x = acc.x;
+            acc4.y = acc.y;
+            impulse = acc - oldImpulse;
+            B.v = B.v + mB * impulse;
+            B.w += iB * cross(rB, impulse);
+        }
+    }
+    st4(c, js + SJ_IMPULSE4, acc4);
+    stVelAt(c, off.w, B);
+}
+
 // b2RevoluteJoint::SolvePositionConstraints (friction joints have none and report true)
 DEV bool revoluteSolvePos(Ctx c, int jr, int modelFlags) {
     const int4 off = mi4(c, jr + MJ_SOFF);  // js jw bodyA bodyB
@@ -755,7 +831,17 @@ DEV void integratePosition(Ctx c, int b, float h) {
 }
 
 
+// Phase barrier of the CTA-synchronised stepping kernel.  The step is ~8k distinct instructions (k_step is 270 KB of
+// SASS); 16 resident warps that drift through different phases thrash the SM's instruction cache ("no_instructions"
+// was the top stall).  With SYNC every warp of the CTA walks the phases together, so the cache holds one phase.
+// All threads of the CTA must reach every phaseSync: they sit outside data-dependent control flow only.
+template <bool SYNC>
+DEV void phaseSync() {
+    if (SYNC) __syncthreads();
+}
+
 // b2World::Solve + b2Island::Solve for every island of the world, then SynchronizeFixtures + FindNewContacts
+template <bool SYNC>
 DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
     const int nb = H().nb;
     const float h = PRM().dt;
@@ -831,14 +917,35 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
     // first, which puts the free objects before the robot; emitting them in the opposite order keeps the lanes of
     // a warp aligned on the robot's joints (same model, same DFS) and leaves the part that differs from world to
     // world (which objects are awake) at the tail, where every entry has the same type.
-    if (L.nIslands > 1) {
+    phaseSync<SYNC>();
+    //
+    // "Simple" islands -- one dynamic body held by its ground-friction joint, no contacts: a free object, or a rigid
+    // robot that touches nothing -- leave the lists altogether: their 15 velocity iterations only ever touch one body
+    // and one joint, so they run in registers (frictionIslandSolve) instead of streaming the same chunks through
+    // L1/L2 fifteen times.  `simple` = mask of those islands, their joints go to the tail of L.joints.
+    uint64_t simple = 0ull;
+    int nSimple = 0;
+    {
         unsigned char tmp[kMaxJoints];
+        unsigned char tail[kMaxBodies];
         L.jStart[L.nIslands] = (unsigned char)L.nj;
         L.cStart[L.nIslands] = (unsigned char)L.nc;
         int n = 0;
-        for (int isl = L.nIslands - 1; isl >= 0; --isl)
-            for (int i = L.jStart[isl]; i < L.jStart[isl + 1]; ++i) tmp[n++] = L.joints[i];
+        for (int isl = L.nIslands - 1; isl >= 0; --isl) {
+            const int j0 = L.jStart[isl], nj = L.jStart[isl + 1] - j0, nc = L.cStart[isl + 1] - L.cStart[isl];
+            if (nj == 1 && nc == 0) {
+                const int4 jh = mi4(c, mjoint(c, L.joints[j0], MJ_TYPE));
+                if (jh.x == 0 && (jh.w & 12) == 4) {  // friction joint, bodyA static, bodyB dynamic
+                    simple |= 1ull << isl;
+                    tail[nSimple++] = L.joints[j0];
+                    continue;
+                }
+            }
+            for (int i = j0; i < j0 + nj; ++i) tmp[n++] = L.joints[i];
+        }
         for (int i = 0; i < n; ++i) L.joints[i] = tmp[i];
+        for (int i = 0; i < nSimple; ++i) L.joints[n + i] = tail[i];
+        L.nj = n;
         n = 0;
         for (int isl = L.nIslands - 1; isl >= 0; --isl)
             for (int i = L.cStart[isl]; i < L.cStart[isl + 1]; ++i) tmp[n++] = L.contacts[i];
@@ -866,11 +973,13 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
         V.w *= ld;
         stVelAt(c, bo, V);
     }
+    phaseSync<SYNC>();
     for (int i = 0; i < L.nc; ++i) contactInit(c, L.contacts[i], dtRatio, true);
     for (int i = 0; i < L.nc; ++i) contactWarmStart(c, L.contacts[i]);
     for (int i = 0; i < L.nj; ++i) jointInit(c, L.joints[i], dtRatio);
 
     const int velIters = PRM().velIters, posIters = PRM().posIters;
+    phaseSync<SYNC>();
     for (int it = 0; it < velIters; ++it) {
         for (int i = 0; i < L.nj; ++i) {
             const int jr = mjoint(c, L.joints[i], 0);
@@ -892,15 +1001,20 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
         }
         for (int i = 0; i < L.nc; ++i) contactSolveVel(c, L.contacts[i]);
     }
+    phaseSync<SYNC>();
     for (int i = 0; i < L.nc; ++i) contactStoreImpulses(c, L.contacts[i]);
+    for (int i = 0; i < nSimple; ++i) frictionIslandSolve(c, L.joints[L.nj + i], dtRatio, velIters);
 
+    phaseSync<SYNC>();
     for (int i = 0; i < L.ndyn; ++i) integratePosition(c, L.dyn[i], h);
 
     // position iterations: every island leaves the loop on its own (b2Island::Solve breaks when contactsOkay &&
     // jointsOkay); `open` = islands still iterating, `solved` = islands that reported positionSolved
     const uint64_t allIslands = L.nIslands >= 64 ? ~0ull : ((1ull << L.nIslands) - 1ull);
-    uint64_t open = allIslands, solved = 0ull;
-    for (int it = 0; it < posIters && open != 0ull; ++it) {
+    // simple islands have neither contacts nor position constraints: solved in their first (empty) iteration
+    uint64_t open = posIters > 0 ? allIslands & ~simple : 0ull, solved = posIters > 0 ? simple : 0ull;
+    // SYNC: the loop runs while any world of the CTA still iterates, so that the barrier inside stays convergent
+    for (int it = 0; it < posIters && (SYNC ? __syncthreads_or(open != 0ull) != 0 : open != 0ull); ++it) {
         uint64_t bad = 0ull;  // islands whose contacts or joints are not okay in this iteration
         for (int i = 0; i < L.nc; ++i) {
             const int k = L.contacts[i];
@@ -923,6 +1037,7 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
         solved |= open & ~bad;
         open &= bad;
     }
+    phaseSync<SYNC>();
     for (int i = 0; i < L.ndyn; ++i) syncTransform(c, L.dyn[i]);
     for (uint64_t m = staticSeen; m; m &= m - 1ull) syncTransform(c, __ffsll((long long)m) - 1);
 
@@ -957,6 +1072,7 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
         if ((asleep >> L.bodyIsl[b]) & 1ull) sleepBody(c, b); else wakeBody(c, b);
     }
 
+    phaseSync<SYNC>();
     uint64_t moved = 0ull;
     for (int b = nb - 1; b >= 0; --b) {
         if (((bodyFlag >> b) & 1ull) == 0ull) continue;

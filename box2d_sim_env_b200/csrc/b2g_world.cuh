@@ -353,6 +353,7 @@ DEVN void robotControl(Ctx c, int o, int robotSlot) {
 }
 
 // Box2DWorld::stepPhysics body for one step (:3270-3282) = controllers + b2World::Step + ClearForces
+template <bool SYNC>
 DEVN void stepWorld(Ctx c, bool executeControllers, bool allowSleeping) {
     const ModelHeader& h = H();
 
@@ -369,8 +370,11 @@ DEVN void stepWorld(Ctx c, bool executeControllers, bool allowSleeping) {
         stI(c, sslot(c, SS_FLAGS), flags & ~1);
     }
     float dtRatio = ldF(c, sslot(c, SS_INV_DT0)) * PRM().dt;
+    phaseSync<SYNC>();
     collide(c);
-    solveIslands(c, dtRatio, allowSleeping);
+    phaseSync<SYNC>();
+    solveIslands<SYNC>(c, dtRatio, allowSleeping);
+    phaseSync<SYNC>();
 #ifndef B2G_EXPERIMENT_NO_TOI  /* tuning experiment only: wrong physics, shows the register cost of the TOI call chain */
     solveTOI(c);
 #endif
@@ -384,7 +388,7 @@ DEVN void stepWorld(Ctx c, bool executeControllers, bool allowSleeping) {
 // so that the plain path carries no extra live state across the step.
 DEVN void stepWorldGuarded(Ctx c, bool executeControllers, bool allowSleeping) {
     if ((ldI(c, sslot(c, SS_ABORT)) & 1) != 0) return;
-    stepWorld(c, executeControllers, allowSleeping);
+    stepWorld<false>(c, executeControllers, allowSleeping);
     stI(c, sslot(c, SS_ABORT), ldI(c, sslot(c, SS_ABORT)) + 256);  // executed steps in bits 8..
 }
 

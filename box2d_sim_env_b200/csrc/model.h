@@ -116,6 +116,7 @@ struct ModelHeader {
 //     base(tile, lane) + chunk * 512 + word * 4
 // Field enumerators below are such byte offsets relative to the first chunk of their record.
 constexpr int kTileWorlds = 32;
+constexpr int kWorldPad = 1024;  // the state array holds a multiple of this many worlds (= the largest CTA of k_step)
 constexpr int kChunkBytes = 16 * kTileWorlds;  // 512
 #define B2G_F(chunk, word) ((chunk) * 512 + (word) * 4)
 
