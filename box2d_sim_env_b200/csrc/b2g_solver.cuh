@@ -840,6 +840,7 @@ DEV void phaseSync() {
     if (SYNC) __syncthreads();
 }
 
+
 // b2World::Solve + b2Island::Solve for every island of the world, then SynchronizeFixtures + FindNewContacts
 template <bool SYNC>
 DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
@@ -1013,8 +1014,7 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
     const uint64_t allIslands = L.nIslands >= 64 ? ~0ull : ((1ull << L.nIslands) - 1ull);
     // simple islands have neither contacts nor position constraints: solved in their first (empty) iteration
     uint64_t open = posIters > 0 ? allIslands & ~simple : 0ull, solved = posIters > 0 ? simple : 0ull;
-    // SYNC: the loop runs while any world of the CTA still iterates, so that the barrier inside stays convergent
-    for (int it = 0; it < posIters && (SYNC ? __syncthreads_or(open != 0ull) != 0 : open != 0ull); ++it) {
+    for (int it = 0; it < posIters && open != 0ull; ++it) {
         uint64_t bad = 0ull;  // islands whose contacts or joints are not okay in this iteration
         for (int i = 0; i < L.nc; ++i) {
             const int k = L.contacts[i];
