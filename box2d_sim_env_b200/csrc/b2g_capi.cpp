@@ -74,9 +74,10 @@ struct b2g_batch {
     float* S = nullptr;
     float* tmpl = nullptr;
     cudaStream_t stream = nullptr;
-    StepParams prm{0.01f, 1.0f / 0.01f, 15, 15, 0, 0, nullptr, nullptr, nullptr, nullptr};
+    StepParams prm{0.01f, 1.0f / 0.01f, 15, 15, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
     int block = 32;
     int stepBlock = 32;
+    int stepLanes = 32;
     DevBuf stageA, stageB, stageC, stageD, stageE;
     std::vector<SavedState> stack;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
@@ -89,9 +90,11 @@ struct b2g_batch {
         l.S = S;
         l.N = N;
         l.prm = prm;
+        l.prm.stateBase = (const char*)S;
         l.stream = stream;
         l.block = block;
         l.stepBlock = stepBlock;
+        l.stepLanes = stepLanes;
         return l;
     }
 };
@@ -317,6 +320,15 @@ b2g_status b2g_batch_create(const b2g_model* model, int64_t n_worlds, int device
         while (b->stepBlock < want && b->stepBlock < 256) b->stepBlock *= 2;
     }
     if (b->stepBlock < 32 || b->stepBlock > kWorldPad || (b->stepBlock & (b->stepBlock - 1))) b->stepBlock = 32;
+    // worlds per warp: a B200 has 148 x 4 warp schedulers; a batch with fewer than 592 full warps is spread over narrower
+    // warps (k_step_narrow) so that rare per-world events serialise fewer neighbours
+    const char* envLanes = getenv("B2G_LANES");
+    if (envLanes) b->stepLanes = atoi(envLanes);
+    else {
+        b->stepLanes = 1;
+        while (b->stepLanes < 32 && n_worlds > 592LL * b->stepLanes) b->stepLanes *= 2;
+    }
+    if (b->stepLanes < 1 || b->stepLanes > 32 || (b->stepLanes & (b->stepLanes - 1))) b->stepLanes = 32;
     auto cleanup = [&](cudaError_t err, const char* what) {
         b2g_batch_destroy(b);
         return cudaFail(err, what);

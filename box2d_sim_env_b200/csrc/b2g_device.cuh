@@ -479,9 +479,17 @@ DEV void reportContact(Ctx c, int type, V2 localNormal, V2 localPoint, V2 lp, co
 
 // Box2DCollisionChecker::BeginContact (:2792-2818) for contact slot k, whose manifold has just been updated with the
 // bodies' current transforms: recording and / or the guard of stepPhysics(callback, ...)
+// world index of the calling thread, recovered from its state pointer (threads are mapped to worlds differently by
+// the different stepping kernels)
+DEV long long worldIndex(Ctx c) {
+    const size_t off = (size_t)(c.P - PRM().stateBase);
+    const size_t tileBytes = (size_t)H().stateChunks * kChunkBytes;
+    return (long long)(off / tileBytes) * kTileWorlds + (long long)((off % tileBytes) >> 4);
+}
+
 DEVN void onBeginContact(Ctx c, int k) {
     const StepParams& p = PRM();
-    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long w = worldIndex(c);
     const int ck = cslot(c, k, 0);
     const int fx = ldI(c, ck + SC_FIX);
     const int fA = fx & 0xff, fB = (fx >> 8) & 0xff;

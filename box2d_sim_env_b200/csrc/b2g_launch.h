@@ -15,6 +15,7 @@ struct Launch {
     cudaStream_t stream;
     int block;             // threads per CTA
     int stepBlock;         // threads per CTA of k_step (power of two <= kWorldPad)
+    int stepLanes;         // worlds per warp of the stepping kernel: 32, or a smaller power of two for small batches
 };
 
 unsigned long long launchCount();

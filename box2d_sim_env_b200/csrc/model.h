@@ -95,6 +95,7 @@ struct StepParams {
     int* recI;                // [N][recMax][4] bodyA bodyB fixtureA fixtureB
     float* recF;              // [N][recMax][6] contact_point(3) contact_normal(3), both times 1/scale
     const unsigned char* allowed;  // [nb][nb]: 0 = a BeginContact between these bodies aborts the world's stepping
+    const char* stateBase;    // start of the state array (world index of a thread = f(its state pointer), see worldIndex)
 };
 
 struct ModelHeader {

@@ -2,6 +2,8 @@
 precision in the same operation order on both sides (--fmad=false, shared deterministic sin/cos), so the bar is
 BIT-EXACT for poses, velocities, fat AABBs, joint impulses, contact sets, manifold ids and impulses — far inside
 the 1e-5 single-step tolerance BASELINE.json states."""
+import os
+
 import numpy as np
 import pytest
 
@@ -394,3 +396,26 @@ def test_region_query_and_feasibility(b2g):
     assert np.array_equal(feas, ofeas)
     assert 0 < feas.sum() < n, "scenario must contain feasible and infeasible worlds"
     assert_same(batch, worlds, "after isPhysicallyFeasible (runs UpdateContacts)")
+
+
+@pytest.mark.parametrize("env_name,n", [(ENV_A, 20000), (ENV_B, 12345)])
+def test_large_batch_full_warp_path(b2g, env_name, n):
+    """Batches large enough for the full-warp, CTA-synchronised stepping kernel (phase barriers, padding worlds in the
+    last CTA; small batches use the narrow-warp kernel): final states of a 60-step rollout, all worlds, bit-exact."""
+    from oracle import b2o
+    batch = make_batch(b2g, env_name, n)
+    nd = batch.model.objects[0]["n_dofs"]
+    q, qd = random_states(batch.model, n, seed=97, spread=0.6)
+    tg = random_targets(batch.model, 0, n, seed=98, segments=6)
+    batch.setWorldState(q, qd, reset_caches=True)
+    for seg in range(6):
+        batch.setTargetVelocity(0, tg[seg])
+        batch.stepPhysics(10)
+    gq, gqd = batch.getWorldState()
+    ob = b2o.OracleBatch(load_env_dict(env_name), n)
+    oq, oqd = ob.rollout(q, qd, 0, tg, 10, os.cpu_count() or 4)
+    bad = np.nonzero(~(np.all(gq == oq, axis=1) & np.all(gqd == oqd, axis=1)))[0]
+    assert bad.size == 0, "%d of %d worlds differ, first %s" % (bad.size, n, bad[:5].tolist())
+    counts, cio, _ = batch.contacts(max_per_world=4)
+    assert int(cio[..., 2].sum()) > 50
+    assert np.all(batch.status() == 0)
