@@ -33,17 +33,19 @@ class _ModelInfo(C.Structure):
 
 class _ObjectInfo(C.Structure):
     _fields_ = [("name", C.c_char * 64), ("is_robot", C.c_int32), ("is_static", C.c_int32), ("n_dofs", C.c_int32),
-                ("dof_offset", C.c_int32), ("first_body", C.c_int32), ("n_links", C.c_int32), ("n_joints", C.c_int32)]
+                ("dof_offset", C.c_int32), ("first_body", C.c_int32), ("n_links", C.c_int32), ("n_joints", C.c_int32),
+                ("n_balls", C.c_int32)]
 
 
 # every symbol include/b2g.h declares (tests/test_abi.py checks the library exports them all)
 ABI_SYMBOLS = [
     "b2g_last_error", "b2g_env_create", "b2g_env_load_yaml", "b2g_env_destroy", "b2g_env_add_object", "b2g_env_add_link",
-    "b2g_env_add_polygon", "b2g_env_add_joint", "b2g_env_add_state", "b2g_model_create", "b2g_model_destroy",
+    "b2g_env_add_polygon", "b2g_env_add_ball", "b2g_env_add_joint", "b2g_env_add_state", "b2g_model_create", "b2g_model_destroy",
     "b2g_model_get_info", "b2g_model_get_object", "b2g_model_get_dof_limits", "b2g_model_get_bodies",
-    "b2g_model_get_fixtures", "b2g_model_get_joints", "b2g_batch_create", "b2g_batch_destroy", "b2g_batch_set_params",
+    "b2g_model_get_fixtures", "b2g_model_get_joints", "b2g_model_get_balls", "b2g_batch_get_ball_approximation",
+    "b2g_batch_create", "b2g_batch_destroy", "b2g_batch_set_params",
     "b2g_batch_status", "b2g_batch_stream", "b2g_batch_sync", "b2g_batch_set_state", "b2g_batch_set_state_dev",
-    "b2g_batch_get_state", "b2g_batch_get_state_dev", "b2g_batch_set_object_pose", "b2g_batch_get_object_pose",
+    "b2g_batch_get_state", "b2g_batch_get_state_dev", "b2g_batch_set_object_pose", "b2g_batch_set_object_dofs", "b2g_batch_get_object_dofs", "b2g_batch_select_worlds", "b2g_batch_get_object_pose",
     "b2g_batch_set_to_rest", "b2g_batch_at_rest", "b2g_batch_set_link_enabled", "b2g_batch_objects_in_aabb",
     "b2g_batch_is_physically_feasible",
     "b2g_batch_set_target_velocity", "b2g_batch_set_target_velocity_dev", "b2g_batch_step", "b2g_batch_step_record",
@@ -76,6 +78,9 @@ def lib():
     L.b2g_env_add_object.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, fp, C.c_int, C.POINTER(C.c_int)]
     L.b2g_env_add_link.argtypes = [vp, C.c_int, C.c_int, C.c_char_p] + [C.c_float] * 5 + [C.POINTER(C.c_int)]
     L.b2g_env_add_polygon.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, C.c_int]
+    L.b2g_env_add_ball.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, C.c_float]
+    L.b2g_model_get_balls.argtypes = [vp, C.c_int, ip, fp]
+    L.b2g_batch_get_ball_approximation.argtypes = [vp, C.c_int, fp]
     L.b2g_env_add_joint.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, fp, C.c_int, C.c_char_p]
     L.b2g_env_add_state.argtypes = [vp, C.c_char_p, fp, fp, C.c_int]
     L.b2g_model_create.argtypes = [vp, C.POINTER(vp)]
@@ -99,6 +104,9 @@ def lib():
         getattr(L, n).argtypes = [vp, fp, fp, C.c_int]
     for n in ("b2g_batch_get_state", "b2g_batch_get_state_dev"):
         getattr(L, n).argtypes = [vp, fp, fp]
+    L.b2g_batch_set_object_dofs.argtypes = [vp, C.c_int, C.c_int, ip, C.c_int, fp]
+    L.b2g_batch_get_object_dofs.argtypes = [vp, C.c_int, C.c_int, ip, C.c_int, fp]
+    L.b2g_batch_select_worlds.argtypes = [vp, C.c_int64, C.c_int64]
     L.b2g_batch_set_object_pose.argtypes = [vp, C.c_int, fp]
     L.b2g_batch_get_object_pose.argtypes = [vp, C.c_int, fp]
     L.b2g_batch_set_to_rest.argtypes = [vp]
@@ -192,6 +200,9 @@ class Environment:
                     for poly in link["geometry"]:
                         p = _f32(poly)
                         _check(L.b2g_env_add_polygon(h, is_robot, oi.value, li.value, _ptr(p), len(p)))
+                    for ball in link.get("balls") or []:
+                        c = _f32(ball[:3])
+                        _check(L.b2g_env_add_ball(h, is_robot, oi.value, li.value, _ptr(c), float(ball[3])))
                 for j in obj["joints"]:
                     params = _f32(list(j["axis"]) + list(j["position_limits"]) + list(j["velocity_limits"]) +
                                   list(j["acceleration_limits"]) + [j["axis_orientation"]])
@@ -230,7 +241,7 @@ class Model:
             _check(lib().b2g_model_get_object(self.h, i, C.byref(oi)))
             self.objects.append(dict(name=oi.name.decode(), is_robot=bool(oi.is_robot), is_static=bool(oi.is_static),
                                      n_dofs=oi.n_dofs, dof_offset=oi.dof_offset, first_body=oi.first_body,
-                                     n_links=oi.n_links, n_joints=oi.n_joints))
+                                     n_links=oi.n_links, n_joints=oi.n_joints, n_balls=oi.n_balls))
 
     def object_index(self, name):
         for i, o in enumerate(self.objects):
@@ -253,6 +264,16 @@ class Model:
         fo = np.zeros((self.n_fixtures, 38), np.float32)
         _check(lib().b2g_model_get_fixtures(self.h, _ptr(io), _ptr(fo)))
         return io, fo
+
+    def local_ball_approximation(self, obj):
+        """Box2DLink::getLocalBallApproximation (:727-731) of every link of the object, links in name order:
+        (bodies [n_balls], xyzr [n_balls, 4])."""
+        obj = self.object_index(obj) if isinstance(obj, str) else obj
+        n = self.objects[obj]["n_balls"]
+        bodies = np.zeros(n, np.int32)
+        xyzr = np.zeros((n, 4), np.float32)
+        _check(lib().b2g_model_get_balls(self.h, obj, _ptr(bodies), _ptr(xyzr)))
+        return bodies, xyzr
 
     def joint_model(self):
         io = np.zeros((self.n_joints, 6), np.int32)
@@ -356,15 +377,15 @@ class BatchBox2DWorld:
 
     # -- state (:3462-3541)
     def getWorldState(self):
-        q = np.zeros((self.n_worlds, self.nq), np.float32)
-        qd = np.zeros((self.n_worlds, self.nq), np.float32)
+        q = np.zeros((self._rows(), self.nq), np.float32)
+        qd = np.zeros((self._rows(), self.nq), np.float32)
         _check(lib().b2g_batch_get_state(self.h, _ptr(q), _ptr(qd)))
         return q, qd
 
     def setWorldState(self, q, qd, reset_caches=False):
         q = _f32(q)
         qd = _f32(qd)
-        if q.shape != (self.n_worlds, self.nq) or qd.shape != (self.n_worlds, self.nq):
+        if q.shape != (self._rows(), self.nq) or qd.shape != (self._rows(), self.nq):
             raise B2GError(1, "[sim_env::BatchBox2DWorld::setWorldState] state arrays must be [n_worlds, %d]" % self.nq)
         _check(lib().b2g_batch_set_state(self.h, _ptr(q), _ptr(qd), int(reset_caches)))
 
@@ -383,25 +404,64 @@ class BatchBox2DWorld:
 
     def setObjectPose(self, obj, pose):
         obj = self.model.object_index(obj) if isinstance(obj, str) else obj
-        pose = _f32(np.broadcast_to(_f32(pose), (self.n_worlds, 3)))
+        pose = _f32(np.broadcast_to(_f32(pose), (self._rows(), 3)))
         _check(lib().b2g_batch_set_object_pose(self.h, obj, _ptr(pose)))
 
     def getObjectPose(self, obj):
         obj = self.model.object_index(obj) if isinstance(obj, str) else obj
-        pose = np.zeros((self.n_worlds, 3), np.float32)
+        pose = np.zeros((self._rows(), 3), np.float32)
         _check(lib().b2g_batch_get_object_pose(self.h, obj, _ptr(pose)))
         return pose
+
+    # ---- per-object DOF access (Box2DObject::get/setDOFPositions, get/setDOFVelocities with an index subset)
+    def _dofs(self, obj, indices):
+        obj = self.model.object_index(obj) if isinstance(obj, str) else obj
+        ix = None if indices is None else np.ascontiguousarray(indices, np.int32)
+        return obj, ix, (self.model.objects[obj]["n_dofs"] if ix is None else len(ix))
+
+    def getDOFPositions(self, obj, indices=None, velocities=False):
+        obj, ix, n = self._dofs(obj, indices)
+        out = np.zeros((self._rows(), n), np.float32)
+        _check(lib().b2g_batch_get_object_dofs(self.h, obj, int(velocities), _ptr(ix), 0 if ix is None else n, _ptr(out)))
+        return out
+
+    def getDOFVelocities(self, obj, indices=None):
+        return self.getDOFPositions(obj, indices, velocities=True)
+
+    def setDOFPositions(self, obj, values, indices=None, velocities=False):
+        obj, ix, n = self._dofs(obj, indices)
+        v = _f32(np.broadcast_to(_f32(values), (self._rows(), n)))
+        _check(lib().b2g_batch_set_object_dofs(self.h, obj, int(velocities), _ptr(ix), 0 if ix is None else n, _ptr(v)))
+
+    def setDOFVelocities(self, obj, values, indices=None):
+        self.setDOFPositions(obj, values, indices, velocities=True)
+
+    def selectWorlds(self, first=0, count=0):
+        """Restrict the per-world calls to worlds [first, first + count) (count <= 0: the whole batch again)."""
+        _check(lib().b2g_batch_select_worlds(self.h, int(first), int(count)))
+        self._sel = (int(first), int(count)) if count > 0 else None
+
+    def _rows(self):
+        sel = getattr(self, "_sel", None)
+        return sel[1] if sel else self.n_worlds
+
+    def getBallApproximation(self, obj):
+        """Box2DObject::getBallApproximation (:1754-1763) in every world: [n_worlds, n_balls, 4] = centre, radius."""
+        obj = self.model.object_index(obj) if isinstance(obj, str) else obj
+        out = np.zeros((self._rows(), self.model.objects[obj]["n_balls"], 4), np.float32)
+        _check(lib().b2g_batch_get_ball_approximation(self.h, obj, _ptr(out)))
+        return out
 
     def getObjects(self, aabb, exclude_robots=True):
         """Box2DWorld::getObjects(aabb, ...) (:3207-3254): bool [n_worlds, n_objects] (model object order)."""
         box = _f32(aabb)
-        hits = np.zeros((self.n_worlds, self.model.n_objects), np.uint8)
+        hits = np.zeros((self._rows(), self.model.n_objects), np.uint8)
         _check(lib().b2g_batch_objects_in_aabb(self.h, _ptr(box), int(exclude_robots), _ptr(hits)))
         return hits.astype(bool)
 
     def isPhysicallyFeasible(self):
         """Box2DWorld::isPhysicallyFeasible (:3370-3400), one bool per world."""
-        out = np.zeros(self.n_worlds, np.int32)
+        out = np.zeros(self._rows(), np.int32)
         _check(lib().b2g_batch_is_physically_feasible(self.h, _ptr(out)))
         return out.astype(bool)
 
@@ -411,7 +471,7 @@ class BatchBox2DWorld:
 
     def atRest(self, threshold=0.0001):
         """Box2DWorld::atRest (:3435-3452), one bool per world."""
-        out = np.zeros(self.n_worlds, np.int32)
+        out = np.zeros(self._rows(), np.int32)
         _check(lib().b2g_batch_at_rest(self.h, float(threshold), _ptr(out)))
         return out.astype(bool)
 
@@ -421,7 +481,7 @@ class BatchBox2DWorld:
             _check(lib().b2g_batch_set_link_enabled(self.h, int(body), None, int(bool(enabled))))
         else:
             e = np.ascontiguousarray(enabled, dtype=np.uint8)
-            if e.shape != (self.n_worlds,):
+            if e.shape != (self._rows(),):
                 raise B2GError(1, "enabled must be a bool or an [n_worlds] array")
             _check(lib().b2g_batch_set_link_enabled(self.h, int(body), _ptr(e), 0))
 
@@ -429,7 +489,7 @@ class BatchBox2DWorld:
     def setTargetVelocity(self, robot, velocity):
         robot = self.model.object_index(robot) if isinstance(robot, str) else robot
         nd = self.model.objects[robot]["n_dofs"]
-        v = _f32(np.broadcast_to(_f32(velocity), (self.n_worlds, nd)))
+        v = _f32(np.broadcast_to(_f32(velocity), (self._rows(), nd)))
         if v.shape[-1] != nd:
             raise B2GError(1, "[sim_env::Box2DRobotVelocityController::setTargetVelocity]"
                               "Provided target velocity has invalid dimension.")
@@ -437,38 +497,38 @@ class BatchBox2DWorld:
 
     # -- collision (:3846-3859 through Box2DCollisionChecker::updateContactCache :2880-2911)
     def checkCollision(self, max_per_world=32):
-        counts = np.zeros(self.n_worlds, np.int32)
-        io = np.zeros((self.n_worlds, max_per_world, 4), np.int32)
-        fo = np.zeros((self.n_worlds, max_per_world, 6), np.float32)
+        counts = np.zeros(self._rows(), np.int32)
+        io = np.zeros((self._rows(), max_per_world, 4), np.int32)
+        fo = np.zeros((self._rows(), max_per_world, 6), np.float32)
         _check(lib().b2g_batch_check_collision(self.h, _ptr(counts), _ptr(io), _ptr(fo), max_per_world))
         return counts, io, fo
 
     # -- parity probes
     def bodies(self):
-        out = np.zeros((self.n_worlds, self.model.n_bodies, 16), np.float32)
+        out = np.zeros((self._rows(), self.model.n_bodies, 16), np.float32)
         _check(lib().b2g_batch_get_bodies(self.h, _ptr(out)))
         return out
 
     def fat_aabbs(self):
-        out = np.zeros((self.n_worlds, self.model.n_fixtures, 4), np.float32)
+        out = np.zeros((self._rows(), self.model.n_fixtures, 4), np.float32)
         _check(lib().b2g_batch_get_fat_aabbs(self.h, _ptr(out)))
         return out
 
     def joints(self):
-        io = np.zeros((self.n_worlds, self.model.n_joints, 6), np.int32)
-        fo = np.zeros((self.n_worlds, self.model.n_joints, 15), np.float32)
+        io = np.zeros((self._rows(), self.model.n_joints, 6), np.int32)
+        fo = np.zeros((self._rows(), self.model.n_joints, 15), np.float32)
         _check(lib().b2g_batch_get_joints(self.h, _ptr(io), _ptr(fo)))
         return io, fo
 
     def contacts(self, max_per_world=32):
-        counts = np.zeros(self.n_worlds, np.int32)
-        io = np.zeros((self.n_worlds, max_per_world, 8), np.int32)
-        fo = np.zeros((self.n_worlds, max_per_world, 12), np.float32)
+        counts = np.zeros(self._rows(), np.int32)
+        io = np.zeros((self._rows(), max_per_world, 8), np.int32)
+        fo = np.zeros((self._rows(), max_per_world, 12), np.float32)
         _check(lib().b2g_batch_get_contacts(self.h, _ptr(counts), _ptr(io), _ptr(fo), max_per_world))
         return counts, io, fo
 
     def status(self):
-        out = np.zeros(self.n_worlds, np.int32)
+        out = np.zeros(self._rows(), np.int32)
         _check(lib().b2g_batch_status(self.h, _ptr(out)))
         return out
 

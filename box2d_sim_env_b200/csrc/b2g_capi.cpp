@@ -70,11 +70,15 @@ struct b2g_batch {
     HostModel m;
     int device = 0;
     long long N = 0;
+    long long selFirst = 0, selCount = 0;  // b2g_batch_select_worlds: per-world calls act on [selFirst, selFirst + selCount)
+    long long n() const { return selCount; }
+    bool allSelected() const { return selFirst == 0 && selCount == N; }
     uint32_t* blob = nullptr;
     float* S = nullptr;
     float* tmpl = nullptr;
+    float* balls = nullptr;  // device copy of HostModel::balls (ball approximation queries)
     cudaStream_t stream = nullptr;
-    StepParams prm{0.01f, 1.0f / 0.01f, 15, 15, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
+    StepParams prm{0.01f, 1.0f / 0.01f, 15, 15, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr};
     int block = 32;
     int stepBlock = 32;
     int stepLanes = 32;
@@ -88,8 +92,9 @@ struct b2g_batch {
         l.h = m.h;
         l.blob = blob;
         l.S = S;
-        l.N = N;
+        l.N = selCount;
         l.prm = prm;
+        l.prm.worldOffset = selFirst;
         l.prm.stateBase = (const char*)S;
         l.stream = stream;
         l.block = block;
@@ -192,6 +197,13 @@ b2g_status b2g_env_add_polygon(b2g_env* env, int is_robot, int object, int link,
     return B2G_OK;
 }
 
+b2g_status b2g_env_add_ball(b2g_env* env, int is_robot, int object, int link, const float center[3], float radius) {
+    ObjectDescription* o = env ? pickObject(env, is_robot, object) : nullptr;
+    if (!o || link < 0 || link >= (int)o->links.size() || !center) return fail(B2G_ERR_INVALID, "unknown link");
+    o->links[link].balls.push_back({center[0], center[1], center[2], radius});
+    return B2G_OK;
+}
+
 b2g_status b2g_env_add_joint(b2g_env* env, int is_robot, int object, const char* name, const char* link_a, const char* link_b,
                              const float* p, int actuated, const char* joint_type) {
     ObjectDescription* o = env ? pickObject(env, is_robot, object) : nullptr;
@@ -264,6 +276,19 @@ b2g_status b2g_model_get_object(const b2g_model* model, int object, b2g_object_i
     strncpy(out->name, o.name.c_str(), sizeof(out->name) - 1);
     out->is_robot = o.isRobot; out->is_static = o.isStatic; out->n_dofs = o.nDofs; out->dof_offset = o.dofOffset;
     out->first_body = o.firstBody; out->n_links = o.nLinks; out->n_joints = o.nJoints;
+    out->n_balls = o.nBalls;
+    return B2G_OK;
+}
+
+b2g_status b2g_model_get_balls(const b2g_model* model, int object, int32_t* bodies, float* xyzr) {
+    if (!model || object < 0 || object >= (int)model->m.objects.size()) return fail(B2G_ERR_INVALID, "unknown object");
+    const HostObjectInfo& o = model->m.objects[object];
+    if (o.nBalls > 0 && (!bodies || !xyzr)) return fail(B2G_ERR_INVALID, "null argument");
+    for (int i = 0; i < o.nBalls; ++i) {
+        const float* r = &model->m.balls[(size_t)(o.ballStart + i) * 8];
+        bodies[i] = (int32_t)r[0];
+        for (int k = 0; k < 4; ++k) xyzr[i * 4 + k] = r[3 + k];
+    }
     return B2G_OK;
 }
 
@@ -305,6 +330,8 @@ b2g_status b2g_batch_create(const b2g_model* model, int64_t n_worlds, int device
     if (max_contacts > 0) layoutState(b->m.h, max_contacts > kMaxContacts ? kMaxContacts : max_contacts);
     b->device = device;
     b->N = n_worlds;
+    b->selFirst = 0;
+    b->selCount = n_worlds;
     const char* envBlock = getenv("B2G_BLOCK");
     if (envBlock) b->block = atoi(envBlock);
     else b->block = n_worlds <= 148 * 32 * 8 ? 32 : 64;
@@ -372,8 +399,18 @@ void b2g_batch_destroy(b2g_batch* b) {
     if (b->blob) cudaFree(b->blob);
     if (b->S) cudaFree(b->S);
     if (b->tmpl) cudaFree(b->tmpl);
+    if (b->balls) cudaFree(b->balls);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
+}
+
+b2g_status b2g_batch_select_worlds(b2g_batch* b, int64_t first, int64_t count) {
+    if (!b) return fail(B2G_ERR_INVALID, "null batch");
+    if (count <= 0) { first = 0; count = b->N; }
+    if (first < 0 || first + count > b->N) return fail(B2G_ERR_INVALID, "world range outside the batch");
+    b->selFirst = first;
+    b->selCount = count;
+    return B2G_OK;
 }
 
 b2g_status b2g_batch_set_params(b2g_batch* b, float dt, int velocity_steps, int position_steps) {
@@ -397,11 +434,11 @@ b2g_status b2g_batch_sync(b2g_batch* b) {
 b2g_status b2g_batch_status(b2g_batch* b, int32_t* out) {
     if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
     CU(cudaSetDevice(b->device));
-    CU(b->stageA.reserve((size_t)b->N * 4));
+    CU(b->stageA.reserve((size_t)b->n() * 4));
     CU(launchStatus(b->L(), (int*)b->stageA.p));
-    CU(cudaMemcpyAsync(out, b->stageA.p, (size_t)b->N * 4, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(out, b->stageA.p, (size_t)b->n() * 4, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
-    for (long long i = 0; i < b->N; ++i)
+    for (long long i = 0; i < b->n(); ++i)
         if (out[i] & 1) return fail(B2G_ERR_CAPACITY, "world " + std::to_string(i) + " exceeded its contact-slot capacity");
     return B2G_OK;
 }
@@ -417,7 +454,7 @@ b2g_status b2g_batch_set_state_dev(b2g_batch* b, const float* q, const float* qd
 b2g_status b2g_batch_set_state(b2g_batch* b, const float* q, const float* qd, int reset_caches) {
     if (!b || !q || !qd) return fail(B2G_ERR_INVALID, "null argument");
     CU(cudaSetDevice(b->device));
-    size_t bytes = (size_t)b->N * b->m.h.nq * 4;
+    size_t bytes = (size_t)b->n() * b->m.h.nq * 4;
     CU(b->stageA.reserve(bytes));
     CU(b->stageB.reserve(bytes));
     CU(cudaMemcpyAsync(b->stageA.p, q, bytes, cudaMemcpyHostToDevice, b->stream));
@@ -438,7 +475,7 @@ b2g_status b2g_batch_get_state_dev(b2g_batch* b, float* q, float* qd) {
 b2g_status b2g_batch_get_state(b2g_batch* b, float* q, float* qd) {
     if (!b || !q || !qd) return fail(B2G_ERR_INVALID, "null argument");
     CU(cudaSetDevice(b->device));
-    size_t bytes = (size_t)b->N * b->m.h.nq * 4;
+    size_t bytes = (size_t)b->n() * b->m.h.nq * 4;
     CU(b->stageA.reserve(bytes));
     CU(b->stageB.reserve(bytes));
     b2g_status s = b2g_batch_get_state_dev(b, (float*)b->stageA.p, (float*)b->stageB.p);
@@ -449,10 +486,62 @@ b2g_status b2g_batch_get_state(b2g_batch* b, float* q, float* qd) {
     return B2G_OK;
 }
 
+namespace {
+// object-local DOF selection of the per-object DOF calls: null / 0 = all DOFs; indices ascending (Box2DWorld.cpp:1611)
+b2g_status makeSel(const b2g_batch* b, int object, const int32_t* indices, int n, DofSel& sel) {
+    if (!b || object < 0 || object >= b->m.h.no) return fail(B2G_ERR_INVALID, "unknown object");
+    const int nd = b->m.objects[object].nDofs;
+    if (!indices || n <= 0) {
+        sel.n = nd;
+        for (int i = 0; i < nd; ++i) sel.idx[i] = i;
+        return B2G_OK;
+    }
+    if (n > nd) return fail(B2G_ERR_INVALID, "more DOF indices than the object has DOFs");
+    sel.n = n;
+    for (int i = 0; i < n; ++i) {
+        if (indices[i] < 0 || indices[i] >= nd) return fail(B2G_ERR_INVALID, "DOF index out of range");
+        if (i > 0 && indices[i] <= indices[i - 1]) return fail(B2G_ERR_INVALID, "DOF indices must be ascending");
+        sel.idx[i] = indices[i];
+    }
+    return B2G_OK;
+}
+}  // namespace
+
+b2g_status b2g_batch_set_object_dofs(b2g_batch* b, int object, int velocities, const int32_t* indices, int n_indices,
+                                     const float* values) {
+    DofSel sel;
+    b2g_status st = makeSel(b, object, indices, n_indices, sel);
+    if (st) return st;
+    if (sel.n == 0) return B2G_OK;
+    if (!values) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    size_t bytes = (size_t)b->n() * sel.n * 4;
+    CU(b->stageA.reserve(bytes));
+    CU(cudaMemcpyAsync(b->stageA.p, values, bytes, cudaMemcpyHostToDevice, b->stream));
+    CU(launchSetObjectDofs(b->L(), object, sel, (const float*)b->stageA.p, velocities));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_get_object_dofs(b2g_batch* b, int object, int velocities, const int32_t* indices, int n_indices, float* out) {
+    DofSel sel;
+    b2g_status st = makeSel(b, object, indices, n_indices, sel);
+    if (st) return st;
+    if (sel.n == 0) return B2G_OK;
+    if (!out) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    size_t bytes = (size_t)b->n() * sel.n * 4;
+    CU(b->stageA.reserve(bytes));
+    CU(launchGetObjectDofs(b->L(), object, sel, (float*)b->stageA.p, velocities));
+    CU(cudaMemcpyAsync(out, b->stageA.p, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
 b2g_status b2g_batch_set_object_pose(b2g_batch* b, int object, const float* pose) {
     if (!b || !pose || object < 0 || object >= b->m.h.no) return fail(B2G_ERR_INVALID, "unknown object");
     CU(cudaSetDevice(b->device));
-    size_t bytes = (size_t)b->N * 3 * 4;
+    size_t bytes = (size_t)b->n() * 3 * 4;
     CU(b->stageA.reserve(bytes));
     CU(cudaMemcpyAsync(b->stageA.p, pose, bytes, cudaMemcpyHostToDevice, b->stream));
     CU(launchSetPose(b->L(), object, (const float*)b->stageA.p));
@@ -463,7 +552,7 @@ b2g_status b2g_batch_set_object_pose(b2g_batch* b, int object, const float* pose
 b2g_status b2g_batch_get_object_pose(b2g_batch* b, int object, float* pose) {
     if (!b || !pose || object < 0 || object >= b->m.h.no) return fail(B2G_ERR_INVALID, "unknown object");
     CU(cudaSetDevice(b->device));
-    size_t bytes = (size_t)b->N * 3 * 4;
+    size_t bytes = (size_t)b->n() * 3 * 4;
     CU(b->stageA.reserve(bytes));
     CU(launchGetPose(b->L(), object, (float*)b->stageA.p));
     CU(cudaMemcpyAsync(pose, b->stageA.p, bytes, cudaMemcpyDeviceToHost, b->stream));
@@ -492,7 +581,7 @@ b2g_status b2g_batch_set_target_velocity(b2g_batch* b, int object, const float* 
     if (s) return s;
     if (!v) return fail(B2G_ERR_INVALID, "null argument");
     CU(cudaSetDevice(b->device));
-    size_t bytes = (size_t)b->N * b->m.objects[object].nDofs * 4;
+    size_t bytes = (size_t)b->n() * b->m.objects[object].nDofs * 4;
     CU(b->stageA.reserve(bytes));
     CU(cudaMemcpyAsync(b->stageA.p, v, bytes, cudaMemcpyHostToDevice, b->stream));
     CU(launchSetTarget(b->L(), object, (const float*)b->stageA.p));
@@ -512,6 +601,7 @@ static b2g_status timedStep(b2g_batch* b, int object, const float* targets, int 
 
 b2g_status b2g_batch_step(b2g_batch* b, int steps, int execute_controllers, int allow_sleeping) {
     if (!b || steps < 0) return fail(B2G_ERR_INVALID, "bad step arguments");
+    if (!b->allSelected()) return fail(B2G_ERR_INVALID, "stepping and the state stack act on the whole batch: call b2g_batch_select_worlds(batch, 0, 0) first");
     CU(cudaSetDevice(b->device));
     if (steps == 0) return B2G_OK;
     b2g_status s = timedStep(b, 0, nullptr, 1, steps, execute_controllers, allow_sleeping);
@@ -524,6 +614,7 @@ b2g_status b2g_batch_rollout_dev(b2g_batch* b, int object, const float* targets,
     b2g_status s = checkRobot(b, object);
     if (s) return s;
     if (!targets || n_targets < 0 || steps_per_target < 0) return fail(B2G_ERR_INVALID, "bad rollout arguments");
+    if (!b->allSelected()) return fail(B2G_ERR_INVALID, "stepping and the state stack act on the whole batch: call b2g_batch_select_worlds(batch, 0, 0) first");
     CU(cudaSetDevice(b->device));
     if (n_targets == 0) return B2G_OK;
     return timedStep(b, object, targets, n_targets, steps_per_target, 1, 1);
@@ -540,9 +631,9 @@ b2g_status b2g_batch_set_to_rest(b2g_batch* b) {
 b2g_status b2g_batch_at_rest(b2g_batch* b, float threshold, int32_t* out) {
     if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
     CU(cudaSetDevice(b->device));
-    CU(b->stageC.reserve((size_t)b->N * 4));
+    CU(b->stageC.reserve((size_t)b->n() * 4));
     CU(launchAtRest(b->L(), threshold, (int*)b->stageC.p));
-    CU(cudaMemcpyAsync(out, b->stageC.p, (size_t)b->N * 4, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(out, b->stageC.p, (size_t)b->n() * 4, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
     return B2G_OK;
 }
@@ -553,13 +644,13 @@ b2g_status b2g_batch_objects_in_aabb(b2g_batch* b, const float aabb[4], int excl
     CU(cudaSetDevice(b->device));
     const float s = b->m.h.scale;
     const int no = b->m.h.no;
-    size_t bytes = (size_t)b->N * no;
+    size_t bytes = (size_t)b->n() * no;
     CU(b->stageC.reserve(bytes));
     CU(launchObjectsInAABB(b->L(), s * aabb[0], s * aabb[1], s * aabb[2], s * aabb[3], (unsigned char*)b->stageC.p));
     CU(cudaMemcpyAsync(hits, b->stageC.p, bytes, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
     if (exclude_robots)
-        for (long long w = 0; w < b->N; ++w)
+        for (long long w = 0; w < b->n(); ++w)
             for (int o = 0; o < no; ++o)
                 if (b->m.objects[o].isRobot) hits[(size_t)w * no + o] = 0;
     return B2G_OK;
@@ -568,9 +659,9 @@ b2g_status b2g_batch_objects_in_aabb(b2g_batch* b, const float aabb[4], int excl
 b2g_status b2g_batch_is_physically_feasible(b2g_batch* b, int32_t* out) {
     if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
     CU(cudaSetDevice(b->device));
-    CU(b->stageC.reserve((size_t)b->N * 4));
+    CU(b->stageC.reserve((size_t)b->n() * 4));
     CU(launchPhysicallyFeasible(b->L(), (int*)b->stageC.p));
-    CU(cudaMemcpyAsync(out, b->stageC.p, (size_t)b->N * 4, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(out, b->stageC.p, (size_t)b->n() * 4, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
     return B2G_OK;
 }
@@ -580,8 +671,8 @@ b2g_status b2g_batch_set_link_enabled(b2g_batch* b, int body, const uint8_t* ena
     CU(cudaSetDevice(b->device));
     const unsigned char* dev = nullptr;
     if (enabled) {
-        CU(b->stageC.reserve((size_t)b->N));
-        CU(cudaMemcpyAsync(b->stageC.p, enabled, (size_t)b->N, cudaMemcpyHostToDevice, b->stream));
+        CU(b->stageC.reserve((size_t)b->n()));
+        CU(cudaMemcpyAsync(b->stageC.p, enabled, (size_t)b->n(), cudaMemcpyHostToDevice, b->stream));
         dev = (const unsigned char*)b->stageC.p;
     }
     CU(launchSetLinkEnabled(b->L(), body, dev, enabled_all));
@@ -593,9 +684,10 @@ b2g_status b2g_batch_set_link_enabled(b2g_batch* b, int body, const uint8_t* ena
 b2g_status b2g_batch_step_record(b2g_batch* b, int steps, int execute_controllers, int allow_sleeping, int32_t* counts,
                                  int32_t* iout, float* fout, int max_per_world) {
     if (!b || steps < 0 || !counts || !iout || !fout || max_per_world <= 0) return fail(B2G_ERR_INVALID, "bad arguments");
+    if (!b->allSelected()) return fail(B2G_ERR_INVALID, "stepping and the state stack act on the whole batch: call b2g_batch_select_worlds(batch, 0, 0) first");
     CU(cudaSetDevice(b->device));
-    size_t cb = (size_t)b->N * 4, ib = (size_t)b->N * max_per_world * 4 * 4, fb = (size_t)b->N * max_per_world * 6 * 4;
-    size_t sb = (size_t)b->N * b->m.h.nq * 4;
+    size_t cb = (size_t)b->n() * 4, ib = (size_t)b->n() * max_per_world * 4 * 4, fb = (size_t)b->n() * max_per_world * 6 * 4;
+    size_t sb = (size_t)b->n() * b->m.h.nq * 4;
     CU(b->stageA.reserve(ib));
     CU(b->stageB.reserve(fb));
     CU(b->stageC.reserve(cb));
@@ -632,9 +724,10 @@ b2g_status b2g_batch_step_record(b2g_batch* b, int steps, int execute_controller
 b2g_status b2g_batch_step_guarded(b2g_batch* b, int steps, int execute_controllers, int allow_sleeping,
                                   const uint8_t* allowed_pairs, int32_t* completed, int32_t* steps_done) {
     if (!b || steps < 0 || !allowed_pairs || !completed) return fail(B2G_ERR_INVALID, "bad arguments");
+    if (!b->allSelected()) return fail(B2G_ERR_INVALID, "stepping and the state stack act on the whole batch: call b2g_batch_select_worlds(batch, 0, 0) first");
     CU(cudaSetDevice(b->device));
     const int nb = b->m.h.nb;
-    size_t tb = (size_t)nb * nb, cb = (size_t)b->N * 4;
+    size_t tb = (size_t)nb * nb, cb = (size_t)b->n() * 4;
     CU(b->stageA.reserve(tb));
     CU(cudaMemcpyAsync(b->stageA.p, allowed_pairs, tb, cudaMemcpyHostToDevice, b->stream));
     CU(launchClearAbort(b->L()));
@@ -646,12 +739,12 @@ b2g_status b2g_batch_step_guarded(b2g_batch* b, int steps, int execute_controlle
     if (e != cudaSuccess) return cudaFail(e, "guarded stepping");
     // the reference returns `not abort_prematurely`: a world that aborted on its very last step still reports false, so the
     // abort flag itself is read back (bit 0) next to the number of executed steps (bits 8..)
-    std::vector<int32_t> status((size_t)b->N);
+    std::vector<int32_t> status((size_t)b->n());
     CU(b->stageB.reserve(cb));
     CU(launchAbortFlags(b->L(), (int*)b->stageB.p));
     CU(cudaMemcpyAsync(status.data(), b->stageB.p, cb, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
-    for (long long i = 0; i < b->N; ++i) {
+    for (long long i = 0; i < b->n(); ++i) {
         completed[i] = (status[i] & 1) ? 0 : 1;
         if (steps_done) steps_done[i] = status[i] >> 8;
     }
@@ -679,7 +772,7 @@ b2g_status b2g_batch_take_kernel_ms(b2g_batch* b, float* out_ms, int32_t* out_la
 b2g_status b2g_batch_get_bodies(b2g_batch* b, float* out) {
     if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
     CU(cudaSetDevice(b->device));
-    size_t bytes = (size_t)b->N * b->m.h.nb * 16 * 4;
+    size_t bytes = (size_t)b->n() * b->m.h.nb * 16 * 4;
     CU(b->stageA.reserve(bytes));
     CU(launchGetBodies(b->L(), (float*)b->stageA.p));
     CU(cudaMemcpyAsync(out, b->stageA.p, bytes, cudaMemcpyDeviceToHost, b->stream));
@@ -690,9 +783,27 @@ b2g_status b2g_batch_get_bodies(b2g_batch* b, float* out) {
 b2g_status b2g_batch_get_fat_aabbs(b2g_batch* b, float* out) {
     if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
     CU(cudaSetDevice(b->device));
-    size_t bytes = (size_t)b->N * b->m.h.nf * 4 * 4;
+    size_t bytes = (size_t)b->n() * b->m.h.nf * 4 * 4;
     CU(b->stageA.reserve(bytes));
     CU(launchGetFat(b->L(), (float*)b->stageA.p));
+    CU(cudaMemcpyAsync(out, b->stageA.p, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_get_ball_approximation(b2g_batch* b, int object, float* out) {
+    if (!b || object < 0 || object >= b->m.h.no) return fail(B2G_ERR_INVALID, "unknown object");
+    const HostObjectInfo& o = b->m.objects[object];
+    if (o.nBalls == 0) return B2G_OK;
+    if (!out) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    if (!b->balls) {  // the ball table of the model, uploaded on first use
+        CU(cudaMalloc((void**)&b->balls, b->m.balls.size() * sizeof(float)));
+        CU(cudaMemcpyAsync(b->balls, b->m.balls.data(), b->m.balls.size() * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+    }
+    size_t bytes = (size_t)b->n() * o.nBalls * 4 * 4;
+    CU(b->stageA.reserve(bytes));
+    CU(launchGetBalls(b->L(), b->balls, o.ballStart, o.nBalls, (float*)b->stageA.p));
     CU(cudaMemcpyAsync(out, b->stageA.p, bytes, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
     return B2G_OK;
@@ -701,7 +812,7 @@ b2g_status b2g_batch_get_fat_aabbs(b2g_batch* b, float* out) {
 b2g_status b2g_batch_get_joints(b2g_batch* b, int32_t* iout, float* fout) {
     if (!b || !iout || !fout) return fail(B2G_ERR_INVALID, "null argument");
     CU(cudaSetDevice(b->device));
-    size_t ib = (size_t)b->N * b->m.h.nj * 6 * 4, fb = (size_t)b->N * b->m.h.nj * 15 * 4;
+    size_t ib = (size_t)b->n() * b->m.h.nj * 6 * 4, fb = (size_t)b->n() * b->m.h.nj * 15 * 4;
     CU(b->stageA.reserve(ib));
     CU(b->stageB.reserve(fb));
     CU(launchGetJoints(b->L(), (int*)b->stageA.p, (float*)b->stageB.p));
@@ -714,7 +825,7 @@ b2g_status b2g_batch_get_joints(b2g_batch* b, int32_t* iout, float* fout) {
 b2g_status b2g_batch_get_contacts(b2g_batch* b, int32_t* counts, int32_t* iout, float* fout, int max_per_world) {
     if (!b || !counts || !iout || !fout || max_per_world <= 0) return fail(B2G_ERR_INVALID, "bad arguments");
     CU(cudaSetDevice(b->device));
-    size_t cb = (size_t)b->N * 4, ib = (size_t)b->N * max_per_world * 8 * 4, fb = (size_t)b->N * max_per_world * 12 * 4;
+    size_t cb = (size_t)b->n() * 4, ib = (size_t)b->n() * max_per_world * 8 * 4, fb = (size_t)b->n() * max_per_world * 12 * 4;
     CU(b->stageA.reserve(ib));
     CU(b->stageB.reserve(fb));
     CU(b->stageC.reserve(cb));
@@ -739,7 +850,7 @@ b2g_status b2g_batch_check_collision_dev(b2g_batch* b, int32_t* counts, int32_t*
 b2g_status b2g_batch_check_collision(b2g_batch* b, int32_t* counts, int32_t* iout, float* fout, int max_per_world) {
     if (!b || !counts || !iout || !fout || max_per_world <= 0) return fail(B2G_ERR_INVALID, "bad arguments");
     CU(cudaSetDevice(b->device));
-    size_t cb = (size_t)b->N * 4, ib = (size_t)b->N * max_per_world * 4 * 4, fb = (size_t)b->N * max_per_world * 6 * 4;
+    size_t cb = (size_t)b->n() * 4, ib = (size_t)b->n() * max_per_world * 4 * 4, fb = (size_t)b->n() * max_per_world * 6 * 4;
     CU(b->stageA.reserve(ib));
     CU(b->stageB.reserve(fb));
     CU(b->stageC.reserve(cb));
@@ -756,16 +867,17 @@ b2g_status b2g_batch_check_collision(b2g_batch* b, int32_t* counts, int32_t* iou
 // ---------------------------------------------------------------------------------------------- state stack
 b2g_status b2g_batch_save_state(b2g_batch* b) {
     if (!b) return fail(B2G_ERR_INVALID, "null batch");
+    if (!b->allSelected()) return fail(B2G_ERR_INVALID, "stepping and the state stack act on the whole batch: call b2g_batch_select_worlds(batch, 0, 0) first");
     CU(cudaSetDevice(b->device));
     SavedState s;
-    size_t bytes = (size_t)b->N * b->m.h.nq * 4;
+    size_t bytes = (size_t)b->n() * b->m.h.nq * 4;
     CU(cudaMalloc((void**)&s.q, bytes));
     CU(cudaMalloc((void**)&s.qd, bytes));
     CU(launchGetState(b->L(), s.q, s.qd));
     for (int o = 0; o < b->m.h.no; ++o) {
         if (!b->m.objects[o].isStatic) continue;
         float* p = nullptr;
-        CU(cudaMalloc((void**)&p, (size_t)b->N * 3 * 4));
+        CU(cudaMalloc((void**)&p, (size_t)b->n() * 3 * 4));
         CU(launchGetPose(b->L(), o, p));
         s.staticPoses.emplace_back(o, p);
     }
@@ -788,6 +900,7 @@ b2g_status b2g_batch_drop_state(b2g_batch* b) {
 
 b2g_status b2g_batch_restore_state(b2g_batch* b) {
     if (!b) return fail(B2G_ERR_INVALID, "null batch");
+    if (!b->allSelected()) return fail(B2G_ERR_INVALID, "stepping and the state stack act on the whole batch: call b2g_batch_select_worlds(batch, 0, 0) first");
     if (b->stack.empty()) return fail(B2G_ERR_INVALID, "state stack is empty");  // reference returns false (:3526-3528)
     CU(cudaSetDevice(b->device));
     SavedState& s = b->stack.back();

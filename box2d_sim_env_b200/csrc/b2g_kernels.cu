@@ -37,7 +37,7 @@ namespace b2g {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;                       \
     if (w >= N) return;                                                                         \
     Ctx c;                                                                                      \
-    c.P = worldBase(S, hdr.stateChunks, w);
+    c.P = worldBase(S, hdr.stateChunks, w + prm.worldOffset);
 
 // &state[tile][0][lane] of world w
 DEV char* worldBase(float* S, int stateChunks, long long w) {
@@ -94,6 +94,33 @@ __global__ void k_get_state(const __grid_constant__ ModelHeader hdr, const uint3
             qd[w * nq + off + i] = lqd[i];
         }
     }
+}
+
+// Box2DObject::setDOFPositions / setDOFVelocities(values, indices) (:1585-1626, :1691-1715) of one object in every world;
+// values: [N][sel.n]
+__global__ void k_set_object_dofs(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
+                                  long long N, StepParams prm, int object, const __grid_constant__ DofSel sel,
+                                  const float* __restrict__ values, int velocities) {
+    B2G_PROLOGUE();
+    float v[kMaxDofsPerObject];
+    int idx[kMaxDofsPerObject];
+    for (int i = 0; i < sel.n; ++i) {
+        v[i] = values[w * sel.n + i];
+        idx[i] = sel.idx[i];
+    }
+    if (velocities) objectSetDofVelocitiesIdx(c, object, v, idx, sel.n);
+    else objectSetDofPositionsIdx(c, object, v, idx, sel.n);
+}
+
+// Box2DObject::getDOFPositions / getDOFVelocities(indices) (:1507-1528, :1628-1649); out: [N][sel.n]
+__global__ void k_get_object_dofs(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
+                                  long long N, StepParams prm, int object, const __grid_constant__ DofSel sel,
+                                  float* __restrict__ out, int velocities) {
+    B2G_PROLOGUE();
+    float all[kMaxDofsPerObject];
+    if (velocities) getDofVelocities(c, object, all);
+    else getDofPositions(c, object, all);
+    for (int i = 0; i < sel.n; ++i) out[w * sel.n + i] = all[sel.idx[i]];
 }
 
 __global__ void k_set_pose(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
@@ -268,7 +295,7 @@ __global__ void k_objects_in_aabb(const __grid_constant__ ModelHeader hdr, const
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= N) return;
     Ctx c;
-    c.P = worldBase(S, hdr.stateChunks, w);
+    c.P = worldBase(S, hdr.stateChunks, w + prm.worldOffset);
     unsigned char h8[kMaxBodies];
     objectsInAABB(c, lx, ly, ux, uy, fQuery, h8);
     for (int o = 0; o < hdr.no; ++o) hits[(size_t)w * hdr.no + o] = h8[o];
@@ -331,6 +358,28 @@ __global__ void k_get_fat(const __grid_constant__ ModelHeader hdr, const uint32_
     const int nf = H().nf;
     for (int f = 0; f < nf; ++f)
         *reinterpret_cast<float4*>(out + ((size_t)w * nf + f) * 4) = ld4(c, fslot(c, f));
+}
+
+// Box2DObject::getBallApproximation / Box2DLink::updateBallApproximation (:709-747, 1754-1763): centre = getTransform() * ball
+// centre with getTransform() (:193-213) = rotation by the body angle about z plus invScale * GetWorldPoint(_local_origin_offset);
+// the radius passes through.  balls: rows of 8 = body, origin offset x y, centre x y z, radius (HostModel::balls).
+__global__ void k_get_balls(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
+                            StepParams prm, const float* __restrict__ balls, int first, int count, float* __restrict__ out) {
+    B2G_PROLOGUE();
+    const float inv = H().invScale;
+    for (int i = 0; i < count; ++i) {
+        const float* r = balls + (size_t)(first + i) * 8;
+        const XF xf = ldXF(c, (int)r[0]);
+        const V2 pos = mul(xf, mk(r[1], r[2]));
+        const float m00 = xf.q.c, m01 = -xf.q.s, m10 = -m01, m11 = m00;
+        const float tx = inv * pos.x, ty = inv * pos.y;
+        float4 o;
+        o.x = ((m00 * r[3] + m01 * r[4]) + 0.0f * r[5]) + tx;  // Eigen Affine3f * Vector3f: linear part, then translation
+        o.y = ((m10 * r[3] + m11 * r[4]) + 0.0f * r[5]) + ty;
+        o.z = ((0.0f * r[3] + 0.0f * r[4]) + 1.0f * r[5]) + 0.0f;
+        o.w = r[6];
+        *reinterpret_cast<float4*>(out + ((size_t)w * count + i) * 4) = o;
+    }
 }
 
 __global__ void k_get_joints(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
@@ -446,6 +495,12 @@ cudaError_t launchSetState(const Launch& L, const float* q, const float* qd) { L
 cudaError_t launchGetState(const Launch& L, float* q, float* qd) { LAUNCH(k_get_state, q, qd); }
 cudaError_t launchSetPose(const Launch& L, int object, const float* pose) { LAUNCH(k_set_pose, object, pose); }
 cudaError_t launchGetPose(const Launch& L, int object, float* pose) { LAUNCH(k_get_pose, object, pose); }
+cudaError_t launchSetObjectDofs(const Launch& L, int object, const DofSel& sel, const float* values, int velocities) {
+    LAUNCH(k_set_object_dofs, object, sel, values, velocities);
+}
+cudaError_t launchGetObjectDofs(const Launch& L, int object, const DofSel& sel, float* out, int velocities) {
+    LAUNCH(k_get_object_dofs, object, sel, out, velocities);
+}
 cudaError_t launchSetTarget(const Launch& L, int object, const float* v) { LAUNCH(k_set_target, object, v); }
 cudaError_t launchStep(const Launch& L, int object, const float* targets, int nTargets, int stepsPerTarget, int execCtrl,
                        int allowSleep) {
@@ -495,6 +550,9 @@ cudaError_t launchStepGuarded(const Launch& L, int steps, int execCtrl, int allo
 cudaError_t launchGetBodies(const Launch& L, float* out) { LAUNCH(k_get_bodies, out); }
 cudaError_t launchGetFat(const Launch& L, float* out) { LAUNCH(k_get_fat, out); }
 cudaError_t launchGetJoints(const Launch& L, int* iout, float* fout) { LAUNCH(k_get_joints, iout, fout); }
+cudaError_t launchGetBalls(const Launch& L, const float* balls, int first, int count, float* out) {
+    LAUNCH(k_get_balls, balls, first, count, out);
+}
 cudaError_t launchGetContacts(const Launch& L, int* counts, int* iout, float* fout, int maxPer) {
     LAUNCH(k_get_contacts, counts, iout, fout, maxPer);
 }

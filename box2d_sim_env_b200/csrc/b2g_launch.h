@@ -18,6 +18,12 @@ struct Launch {
     int stepLanes;         // worlds per warp of the stepping kernel: 32, or a smaller power of two for small batches
 };
 
+// a selection of object-local DOF indices (ascending) passed to the per-object DOF kernels by value
+struct DofSel {
+    int n;
+    int idx[kMaxDofsPerObject];
+};
+
 unsigned long long launchCount();
 cudaError_t launchInit(const Launch& L);
 cudaError_t launchBroadcast(const Launch& L, const float* tmpl);
@@ -26,6 +32,8 @@ cudaError_t launchSetState(const Launch& L, const float* q, const float* qd);
 cudaError_t launchGetState(const Launch& L, float* q, float* qd);
 cudaError_t launchSetPose(const Launch& L, int object, const float* pose);
 cudaError_t launchGetPose(const Launch& L, int object, float* pose);
+cudaError_t launchSetObjectDofs(const Launch& L, int object, const DofSel& sel, const float* values, int velocities);
+cudaError_t launchGetObjectDofs(const Launch& L, int object, const DofSel& sel, float* out, int velocities);
 cudaError_t launchSetTarget(const Launch& L, int object, const float* v);
 cudaError_t launchStep(const Launch& L, int object, const float* targets, int nTargets, int stepsPerTarget, int execCtrl,
                        int allowSleep);
@@ -39,6 +47,7 @@ cudaError_t launchStepGuarded(const Launch& L, int steps, int execCtrl, int allo
 cudaError_t launchGetBodies(const Launch& L, float* out);
 cudaError_t launchGetFat(const Launch& L, float* out);
 cudaError_t launchGetJoints(const Launch& L, int* iout, float* fout);
+cudaError_t launchGetBalls(const Launch& L, const float* balls, int first, int count, float* out);
 cudaError_t launchGetContacts(const Launch& L, int* counts, int* iout, float* fout, int maxPer);
 cudaError_t launchCheckCollision(const Launch& L, int* counts, int* iout, float* fout, int maxPer);
 cudaError_t launchStatus(const Launch& L, int* out);

@@ -192,6 +192,52 @@ DEVN void objectSetDofVelocities(Ctx c, int o, const float* v) {
     updateBodyVelocities(c, o, qd);
 }
 
+// Box2DObject::setDOFPositions(values, indices) (:1585-1626) for a subset of the object's DOFs: idx holds n object-local DOF
+// indices in ascending order (the reference assumes sorted indices, :1611)
+DEVN void objectSetDofPositionsIdx(Ctx c, int o, const float* values, const int* idx, int n) {
+    float qd[kMaxDofsPerObject];
+    getDofVelocities(c, o, qd);
+    const int nBase = mI(c, mobj(c, o, MO_STATIC)) ? 0 : 3;
+    int dofOffset = 0;
+    float pose[3];
+    basePose(c, o, pose);
+    for (int i = 0; i < (nBase < n ? nBase : n); ++i) {
+        const int d = idx[i];
+        if (d < nBase) {
+            ++dofOffset;
+            pose[d] = values[i];
+        } else {
+            break;
+        }
+    }
+    if (dofOffset > 0) placeSubtree(c, o, 0, pose, false);
+    for (int i = dofOffset; i < n; ++i) {
+        // Box2DJoint::resetPosition(values[i], false)
+        const int ji = idx[i] - nBase;
+        int j = objJoint(c, o, ji);
+        int bA = mI(c, mjoint(c, j, MJ_BODYA));
+        int dof = mI(c, mjoint(c, j, MJ_DOF));
+        float clamped = clampStd(values[i], dofLimit(c, dof, 0), dofLimit(c, dof, 1));
+        float jp[3];
+        V2 axisWorld = jointAnchorA(c, j);
+        jp[0] = H().invScale * axisWorld.x;
+        jp[1] = H().invScale * axisWorld.y;
+        jp[2] = ldF(c, bslot(c, bA, SB_A)) + clamped + mF(c, mjoint(c, j, MJ_REF));
+        placeSubtree(c, o, objJointChildPos(c, o, ji), jp, false);
+    }
+    updateBodyVelocities(c, o, qd);
+}
+
+// Box2DObject::setDOFVelocities(values, indices) (:1691-1715) for a subset of the object's DOFs
+DEVN void objectSetDofVelocitiesIdx(Ctx c, int o, const float* values, const int* idx, int n) {
+    float qd[kMaxDofsPerObject];
+    getDofVelocities(c, o, qd);
+    int dofOffset = mI(c, mobj(c, o, MO_DOF_OFFSET));
+    for (int i = 0; i < n; ++i)
+        qd[idx[i]] = clampStd(values[i], dofLimit(c, dofOffset + idx[i], 2), dofLimit(c, dofOffset + idx[i], 3));
+    updateBodyVelocities(c, o, qd);
+}
+
 // Box2DObject::setState (:1980-1989) for object o; q/qd are the object's slices of the world state vector
 DEV void objectSetState(Ctx c, int o, const float* q, const float* qd) {
     if (!mI(c, mobj(c, o, MO_STATIC))) objectSetPose(c, o, q[0], q[1], q[2]);

@@ -2,6 +2,7 @@
 // Mirrors the reference's description structs (include/sim_env/Box2DIOUtils.h:18-70): link / joint /
 // object / robot / state / environment.  Eigen is not available; plain arrays are used.
 #pragma once
+#include <array>
 #include <map>
 #include <string>
 #include <vector>
@@ -16,6 +17,8 @@ struct LinkDescription {
     float ground_torque_integral = 0.0f;
     float contact_friction = 0.0f;
     float restitution = 0.0f;
+    // ball approximation: centre (x, y, z) in the link frame and radius, user units (Box2DIOUtils.h:21, 139-142)
+    std::vector<std::array<float, 4>> balls;
 };
 
 struct JointDescription {

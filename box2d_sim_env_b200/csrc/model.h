@@ -95,6 +95,7 @@ struct StepParams {
     int* recI;                // [N][recMax][4] bodyA bodyB fixtureA fixtureB
     float* recF;              // [N][recMax][6] contact_point(3) contact_normal(3), both times 1/scale
     const unsigned char* allowed;  // [nb][nb]: 0 = a BeginContact between these bodies aborts the world's stepping
+    long long worldOffset;    // per-world calls on a sub-range (b2g_batch_select_worlds): thread w owns world w + worldOffset
     const char* stateBase;    // start of the state array (world index of a thread = f(its state pointer), see worldIndex)
 };
 

@@ -713,6 +713,7 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
 
     // ---- introspection
     out.objects.clear();
+    out.balls.clear();
     for (int oi = 0; oi < no; ++oi) {
         HostObjectInfo info;
         info.name = objects[oi].d->name;
@@ -723,6 +724,17 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
         info.firstBody = objects[oi].firstBody;
         info.nLinks = objects[oi].nLinks;
         info.nJoints = (int)objects[oi].jointList.size();
+        info.ballStart = (int)out.balls.size() / 8;
+        for (int b : objects[oi].nameOrder) {
+            const LinkDescription& ld = objects[oi].d->links[b - objects[oi].firstBody];
+            const bool base = b == objects[oi].baseBody;  // only the base link has a _local_origin_offset (:53, 653-671)
+            for (auto& ball : ld.balls) {
+                const float row[8] = {(float)b, base ? objects[oi].originX : 0.0f, base ? objects[oi].originY : 0.0f,
+                                      ball[0], ball[1], ball[2], ball[3], 0.0f};
+                out.balls.insert(out.balls.end(), row, row + 8);
+            }
+        }
+        info.nBalls = (int)out.balls.size() / 8 - info.ballStart;
         out.objects.push_back(info);
     }
     out.bodyNames.clear();

@@ -12,6 +12,7 @@ struct HostObjectInfo {
     std::string name;
     bool isRobot = false, isStatic = false;
     int nDofs = 0, dofOffset = 0, firstBody = 0, nLinks = 0, nJoints = 0;
+    int ballStart = 0, nBalls = 0;  // rows of HostModel::balls
 };
 
 struct HostModel {
@@ -26,6 +27,9 @@ struct HostModel {
     std::vector<int32_t> jointInts;   // nj x 6
     std::vector<float> jointFloats;   // nj x 15
     std::vector<float> dofLimits;     // nq x 6
+    // ball approximation (Box2DLink::_balls), object by object, links in name order (Box2DObject::getBallApproximation
+    // walks its std::map of links, Box2DWorld.cpp:1754-1763): rows of 8 = body, origin offset x y (scaled), centre x y z, radius
+    std::vector<float> balls;
     std::vector<std::string> warnings;
 };
 

@@ -246,6 +246,17 @@ LinkDescription decodeLink(const Node& node, EnvironmentDescription& ed, const s
             throw std::runtime_error(ctx + ": a polygon needs an even number (>= 6) of floats");
         ld.polygons.push_back(p);
     }
+    // optional ball approximation (Box2DIOUtils.h:139-142): a sequence of yaml-cpp pairs [[x, y, z], radius]
+    if (const Node* balls = node.find("balls")) {
+        if (balls->kind != Node::Seq && balls->kind != Node::Null)
+            throw std::runtime_error(ctx + ": balls must be a sequence of [[x, y, z], radius] pairs");
+        for (auto& b : balls->seq) {
+            if (b.kind != Node::Seq || b.seq.size() != 2)
+                throw std::runtime_error(ctx + ": a ball is a pair [[x, y, z], radius]");
+            std::vector<float> c = asFloats(b.seq[0], ctx + " ball centre", 3);
+            ld.balls.push_back({c[0], c[1], c[2], asFloat(b.seq[1], ctx + " ball radius")});
+        }
+    }
     return ld;
 }
 

@@ -61,6 +61,9 @@ b2g_status b2g_env_add_link(b2g_env* env, int is_robot, int object, const char* 
                             float ground_friction, float ground_torque_integral, float contact_friction,
                             float restitution, int* out_index);
 b2g_status b2g_env_add_polygon(b2g_env* env, int is_robot, int object, int link, const float* xy, int n_floats);
+/* one ball of the link's ball approximation: centre in the link frame (user units) and radius
+ * (Box2DLinkDescription::balls, Box2DIOUtils.h:21, 139-142; kept by the Box2DLink ctor, Box2DWorld.cpp:54-57) */
+b2g_status b2g_env_add_ball(b2g_env* env, int is_robot, int object, int link, const float center[3], float radius);
 /* params9 = axis(2), position_limits(2), velocity_limits(2), acceleration_limits(2), axis_orientation */
 b2g_status b2g_env_add_joint(b2g_env* env, int is_robot, int object, const char* name, const char* link_a,
                              const char* link_b, const float* params9, int actuated, const char* joint_type);
@@ -92,6 +95,7 @@ typedef struct b2g_object_info {
     int32_t n_dofs;      /* 3 base DOFs unless static + one per joint (Box2DWorld.cpp:1314-1331) */
     int32_t dof_offset;  /* first index in the world state vector */
     int32_t first_body, n_links, n_joints;
+    int32_t n_balls;     /* Box2DObject::_num_balls (Box2DWorld.cpp:1305) */
 } b2g_object_info;
 b2g_status b2g_model_get_object(const b2g_model* model, int object, b2g_object_info* out);
 /* DOF limits in world-state order: out[nq][6] = position lo/hi, velocity lo/hi, acceleration lo/hi
@@ -105,6 +109,9 @@ b2g_status b2g_model_get_fixtures(const b2g_model* model, int32_t* iout, float* 
 /* per joint: iout[6] = kind(0 friction,1 revolute) bodyA bodyB 0 enableMotor enableLimit;
  * fout[15] = 0 0 0 0 0 0 maxForce maxTorque anchorA(2) anchorB(2) referenceAngle lower upper */
 b2g_status b2g_model_get_joints(const b2g_model* model, int32_t* iout, float* fout);
+/* Box2DLink::getLocalBallApproximation (Box2DWorld.cpp:727-731) for every link of the object, links in name order:
+ * bodies[n_balls] = body index of the ball's link, xyzr[n_balls][4] = centre in the link frame and radius */
+b2g_status b2g_model_get_balls(const b2g_model* model, int object, int32_t* bodies, float* xyzr);
 
 /* ---------------------------------------------------------------------------------------------------
  * Batch of worlds.  b2g_batch_create == N x Box2DWorld::loadWorld (Box2DWorld.cpp:3040-3054): every world
@@ -114,6 +121,12 @@ b2g_status b2g_model_get_joints(const b2g_model* model, int32_t* iout, float* fo
 b2g_status b2g_batch_create(const b2g_model* model, int64_t n_worlds, int device, int max_contacts, b2g_batch** out);
 void b2g_batch_destroy(b2g_batch* batch);
 /* setPhysicsTimeStep / setVelocitySteps / setPositionSteps (Box2DWorld.cpp:3340-3353); defaults 0.01, 15, 15 */
+/* Restrict the per-world calls below (state / pose / target get and set, collision and region queries, ball
+ * approximation, probes, status) to worlds [first, first + count): their arrays then have `count` rows.  This is what a
+ * single-world view (BatchBox2DWorld::world(i) in b2g_world.hpp, the reference's one-world Box2DWorld signatures) is built
+ * on.  count <= 0 selects the whole batch again.  Stepping and the save/restore stack always act on the whole batch and
+ * fail with B2G_ERR_INVALID while a sub-range is selected. */
+b2g_status b2g_batch_select_worlds(b2g_batch* batch, int64_t first, int64_t count);
 b2g_status b2g_batch_set_params(b2g_batch* batch, float dt, int velocity_steps, int position_steps);
 /* per-world status after the last call: 0 ok, bit0 contact capacity exceeded, bit1 non-finite state */
 b2g_status b2g_batch_status(b2g_batch* batch, int32_t* out);
@@ -131,6 +144,15 @@ b2g_status b2g_batch_set_state_dev(b2g_batch* batch, const float* q, const float
 b2g_status b2g_batch_get_state(b2g_batch* batch, float* q, float* qd);
 b2g_status b2g_batch_get_state_dev(b2g_batch* batch, float* q, float* qd);
 /* Box2DObject::setPose(x, y, theta) (:1940-1947) for one object in every world; pose: [n_worlds][3] */
+/* Box2DObject::setDOFPositions / setDOFVelocities(values, indices) (Box2DWorld.cpp:1585-1626, 1691-1715) and
+ * getDOFPositions / getDOFVelocities(indices) (:1507-1528, 1628-1649) of one object in every selected world.
+ * indices: n_indices object-local DOF indices in ascending order (base x, y, theta = 0, 1, 2 unless the object is
+ * static; joints in YAML order after); null / 0 = all DOFs.  values / out: [n_worlds][n_indices].  velocities != 0
+ * selects the velocity variant (values are clamped to the DOF velocity limits like the reference). */
+b2g_status b2g_batch_set_object_dofs(b2g_batch* batch, int object, int velocities, const int32_t* indices, int n_indices,
+                                     const float* values);
+b2g_status b2g_batch_get_object_dofs(b2g_batch* batch, int object, int velocities, const int32_t* indices, int n_indices,
+                                     float* out);
 b2g_status b2g_batch_set_object_pose(b2g_batch* batch, int object, const float* pose);
 b2g_status b2g_batch_get_object_pose(b2g_batch* batch, int object, float* pose);
 
@@ -177,6 +199,10 @@ b2g_status b2g_batch_step_guarded(b2g_batch* batch, int steps, int execute_contr
  * targets[t]) on robot `object`, stepPhysics(steps_per_target).  targets: [n_targets][n_worlds][n_dofs]
  * on the device. One kernel launch. */
 b2g_status b2g_batch_rollout_dev(b2g_batch* batch, int object, const float* targets, int n_targets, int steps_per_target);
+
+/* Box2DObject::getBallApproximation (Box2DWorld.cpp:1754-1763, Box2DLink::updateBallApproximation :733-747) of one
+ * object in every world: out[n_worlds][n_balls][4] = centre (world frame, user units) and radius, links in name order */
+b2g_status b2g_batch_get_ball_approximation(b2g_batch* batch, int object, float* out);
 
 /* Parity probes (b2Body / b2Joint / b2Contact state).  bodies: [n_worlds][n_bodies][16] =
  * xf.p(2) xf.q.s xf.q.c c(2) a c0(2) a0 v(2) w sleepTime awake type */

@@ -15,6 +15,8 @@
 #define B2G_WORLD_HPP_
 
 #include <cstdint>
+#include <limits>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -36,7 +38,140 @@ struct Contact {
 struct ObjectInfo {
     std::string name;
     bool is_robot = false, is_static = false;
-    int n_dofs = 0, dof_offset = 0, first_body = 0, n_links = 0, n_joints = 0;
+    int n_dofs = 0, dof_offset = 0, first_body = 0, n_links = 0, n_joints = 0, n_balls = 0;
+};
+
+// sim_env types the single-world views speak (restated; Eigen is replaced by std::vector / plain arrays):
+// DOFInformation (Box2DWorld.cpp:1338-1361), ObjectState (:1962-1970), WorldState (:3462-3473), Ball (:709-720)
+struct DOFInformation {
+    int dof_index = 0;
+    float position_limits[2], velocity_limits[2], acceleration_limits[2];
+    bool cyclic = false;
+};
+struct ObjectState {
+    std::vector<int> active_dofs;
+    std::vector<float> dof_positions, dof_velocities;  // all DOFs of the object (getDOFIndices order)
+    float pose[3] = {0.0f, 0.0f, 0.0f};                // base link pose x, y, theta (the reference stores an Affine3f)
+};
+typedef std::map<std::string, ObjectState> WorldState;
+struct Ball {
+    float center[3];
+    float radius;
+};
+enum class EntityType { Link, Joint, Object, Robot };
+
+class BatchBox2DWorld;
+class World;
+
+// One object (or robot) of ONE world of the batch with the method names of Box2DObject / Box2DRobot
+// (/root/reference/include/sim_env/Box2DWorld.h:350-590).  Obtained from World::getObject / getRobot.
+class Object {
+public:
+    const std::string& getName() const;
+    EntityType getType() const;
+    bool isStatic() const;
+    int index() const { return _object; }
+    // DOF bookkeeping (:1435-1505): active DOFs are kept per object name in the batch (one set for all worlds)
+    unsigned int getNumDOFs() const;
+    unsigned int getNumBaseDOFs() const { return isStatic() ? 0u : 3u; }
+    std::vector<int> getDOFIndices() const;
+    std::vector<int> getActiveDOFs() const;
+    unsigned int getNumActiveDOFs() const { return (unsigned int)getActiveDOFs().size(); }
+    void setActiveDOFs(const std::vector<int>& indices);
+    DOFInformation getDOFInformation(unsigned int dof_index) const;
+    // getDOFPositions / getDOFVelocities / setDOFPositions / setDOFVelocities (:1507-1528, 1628-1649, 1585-1626, 1691-1715):
+    // an empty index list means the active DOFs; indices must be ascending
+    std::vector<float> getDOFPositions(const std::vector<int>& indices = std::vector<int>()) const;
+    std::vector<float> getDOFVelocities(const std::vector<int>& indices = std::vector<int>()) const;
+    void setDOFPositions(const std::vector<float>& values, const std::vector<int>& indices = std::vector<int>());
+    void setDOFVelocities(const std::vector<float>& values, const std::vector<int>& indices = std::vector<int>());
+    // base link pose (Box2DLink::getPose :215-224, Box2DObject::setPose :1940-1947)
+    void getPose(float pose[3]) const;
+    void setPose(const float pose[3]);
+    // getState / setState (:1962-1989)
+    void getState(ObjectState& state) const;
+    ObjectState getState() const {
+        ObjectState s;
+        getState(s);
+        return s;
+    }
+    void setState(const ObjectState& state);
+    void setToRest() { setDOFVelocities(std::vector<float>(getNumDOFs(), 0.0f), getDOFIndices()); }  // (:1717-1722)
+    // checkCollision overloads (Box2DWorld.h:372-377)
+    bool checkCollision();
+    bool checkCollision(std::vector<Contact>& contacts);
+    bool checkCollision(const Object& other);
+    bool checkCollision(const Object& other, std::vector<Contact>& contacts);
+    bool checkCollision(const std::vector<Object>& others);
+    bool checkCollision(const std::vector<Object>& others, std::vector<Contact>& contacts);
+    // getBallApproximation (:1754-1763)
+    void getBallApproximation(std::vector<Ball>& balls) const;
+    // Box2DRobotVelocityController::setTargetVelocity (Box2DController.cpp:42-63); one value per DOF of the robot
+    void setTargetVelocity(const std::vector<float>& target);
+
+private:
+    friend class World;
+    Object(BatchBox2DWorld* batch, int64_t world, int object) : _batch(batch), _world(world), _object(object) {}
+    BatchBox2DWorld* _batch;
+    int64_t _world;
+    int _object;
+};
+
+// ONE world of the batch with the single-world signatures of sim_env::Box2DWorld (Box2DWorld.h:748-844): what a planner
+// written against sim_env::World calls.  Every call touches only this world (b2g_batch_select_worlds); stepping is a
+// batch operation and is only forwarded when the batch holds a single world.
+class World {
+public:
+    int64_t index() const { return _world; }
+    Object getRobot(const std::string& name) const;
+    Object getObject(const std::string& name, bool exclude_robots = true) const;
+    void getObjects(std::vector<Object>& objects, bool exclude_robots = true) const;
+    void getRobots(std::vector<Object>& robots) const;
+    // stepPhysics overloads (:3256-3333): only for a batch of one world (use BatchBox2DWorld::stepPhysics otherwise)
+    void stepPhysics(int steps = 1, bool execute_controllers = true, bool allow_sleeping = true);
+    bool stepPhysics(std::vector<Contact>& contacts, int steps = 1, bool execute_controllers = true, bool allow_sleeping = true);
+    float getPhysicsTimeStep() const;
+    int getVelocitySteps() const;
+    int getPositionSteps() const;
+    // getWorldState / setWorldState (:3462-3513); setWorldState returns false for unknown object names like the reference
+    void getWorldState(WorldState& state) const;
+    WorldState getWorldState() const {
+        WorldState s;
+        getWorldState(s);
+        return s;
+    }
+    bool setWorldState(const WorldState& state);
+    // checkCollision overloads (Box2DWorld.h:797-815); links are given by body index (Contact::body_a / body_b)
+    bool checkCollision(std::vector<Contact>& contacts);
+    bool checkCollision(const Object& object_a, const Object& object_b);
+    bool checkCollision(const Object& object_a, const Object& object_b, std::vector<Contact>& contacts);
+    bool checkCollision(const Object& object);
+    bool checkCollision(const Object& object, std::vector<Contact>& contacts);
+    bool checkCollision(const Object& object, std::vector<Object>& collidors);
+    bool checkCollision(const Object& object_a, const std::vector<Object>& other_objects);
+    bool checkCollision(const Object& object_a, const std::vector<Object>& other_objects, std::vector<Contact>& contacts);
+    bool checkCollisionLink(int link_body);
+    bool checkCollisionLink(int link_body, std::vector<Contact>& contacts);
+    bool checkCollisionLink(int link_body, const std::vector<int>& other_link_bodies, std::vector<Contact>* contacts = nullptr);
+    bool checkCollisionLink(int link_body, const std::vector<Object>& other_objects, std::vector<Contact>* contacts = nullptr);
+    bool checkCollision(const Object& object_a, int link_body_b, std::vector<Contact>* contacts = nullptr);
+    // atRest (:3435-3452), isPhysicallyFeasible (:3370-3400), getObjects(aabb, ...) (:3207-3254), setToRest (:3550-3558)
+    bool atRest(float threshold = 0.0001f) const;
+    bool isPhysicallyFeasible() const;
+    void getObjects(const float aabb[4], std::vector<Object>& objects, bool exclude_robots = true) const;
+
+private:
+    friend class BatchBox2DWorld;
+    friend class Object;
+    World(BatchBox2DWorld* batch, int64_t world) : _batch(batch), _world(world) {}
+    // Box2DCollisionChecker (:2551-2741) on top of the world's touching-contact list: a contact is reported for a body set A
+    // when one of its bodies is in A; with `others` the other body must be in it too.  link_a of a reported contact is the
+    // body that belongs to A (the checker fills link_a from the queried collidable, :2596-2609).
+    bool filterContacts(const std::vector<char>& in_a, const std::vector<char>* in_b, std::vector<Contact>* out,
+                        std::vector<char>* hit_bodies = nullptr);
+    std::vector<char> bodiesOf(const Object& o) const;
+    BatchBox2DWorld* _batch;
+    int64_t _world;
 };
 
 class BatchBox2DWorld {
@@ -66,8 +201,14 @@ public:
             o.first_body = oi.first_body;
             o.n_links = oi.n_links;
             o.n_joints = oi.n_joints;
+            o.n_balls = oi.n_balls;
             _objects.push_back(o);
         }
+        _active.assign(_objects.size(), std::vector<int>());
+        for (size_t i = 0; i < _objects.size(); ++i)  // all DOFs are active after construction (:1333)
+            for (int d = 0; d < _objects[i].n_dofs; ++d) _active[i].push_back(d);
+        _limits.assign((size_t)_info.nq * 6, 0.0f);
+        if (_info.nq > 0) check(b2g_model_get_dof_limits(_model, _limits.data()));
         check(b2g_batch_create(_model, _n, _device, _max_contacts, &_batch));
     }
 
@@ -192,6 +333,44 @@ public:
     void setToRest() { check(b2g_batch_set_to_rest(_batch)); }
     void setLinkEnabled(int body, bool enabled) { check(b2g_batch_set_link_enabled(_batch, body, nullptr, enabled)); }
 
+    // Box2DObject::getBallApproximation (:1754-1763) of one object in every world: out[w * n_balls + k]
+    std::vector<Ball> getBallApproximation(const std::string& object) {
+        const int o = objectIndex(object);
+        std::vector<float> raw((size_t)_n * _objects[o].n_balls * 4);
+        check(b2g_batch_get_ball_approximation(_batch, o, raw.data()));
+        std::vector<Ball> balls(raw.size() / 4);
+        for (size_t i = 0; i < balls.size(); ++i) {
+            for (int d = 0; d < 3; ++d) balls[i].center[d] = raw[i * 4 + d];
+            balls[i].radius = raw[i * 4 + 3];
+        }
+        return balls;
+    }
+    // per-object DOF access for every world: values / result [n_worlds][indices.size()], empty indices = all DOFs
+    std::vector<float> getDOFPositions(const std::string& object, const std::vector<int>& indices = std::vector<int>(),
+                                       bool velocities = false) {
+        const int o = objectIndex(object);
+        const size_t n = indices.empty() ? (size_t)_objects[o].n_dofs : indices.size();
+        std::vector<float> out((size_t)_n * n);
+        std::vector<int32_t> ix(indices.begin(), indices.end());
+        check(b2g_batch_get_object_dofs(_batch, o, velocities, ix.data(), (int)ix.size(), out.data()));
+        return out;
+    }
+    void setDOFPositions(const std::string& object, const std::vector<float>& values,
+                         const std::vector<int>& indices = std::vector<int>(), bool velocities = false) {
+        const int o = objectIndex(object);
+        const size_t n = indices.empty() ? (size_t)_objects[o].n_dofs : indices.size();
+        if (values.size() != (size_t)_n * n)
+            throw std::runtime_error("[sim_env::b2g::BatchBox2DWorld::setDOFPositions] values must be [n_worlds][n_indices]");
+        std::vector<int32_t> ix(indices.begin(), indices.end());
+        check(b2g_batch_set_object_dofs(_batch, o, velocities, ix.data(), (int)ix.size(), values.data()));
+    }
+
+    // single-world view with the reference's one-world signatures
+    World world(int64_t i) {
+        if (i < 0 || i >= _n) throw std::runtime_error("[sim_env::b2g::BatchBox2DWorld::world] world index out of range");
+        return World(this, i);
+    }
+
     // per-world status after the last call (contact capacity exceeded -> std::runtime_error)
     std::vector<int32_t> status() {
         std::vector<int32_t> s(_n);
@@ -201,6 +380,14 @@ public:
     b2g_batch* handle() { return _batch; }
 
 private:
+    friend class World;
+    friend class Object;
+    // scope guard: per-world calls act on world i only while it lives
+    struct Select {
+        Select(const BatchBox2DWorld* b, int64_t i) : _b(b) { check(b2g_batch_select_worlds(_b->_batch, i, 1)); }
+        ~Select() { b2g_batch_select_worlds(_b->_batch, 0, 0); }
+        const BatchBox2DWorld* _b;
+    };
     static void check(b2g_status s) {
         if (s == B2G_OK) return;
         std::string msg = b2g_last_error();
@@ -245,7 +432,319 @@ private:
     b2g_batch* _batch = nullptr;
     b2g_model_info _info{};
     std::vector<ObjectInfo> _objects;
+    std::vector<std::vector<int> > _active;  // active DOFs per object (Box2DObject::_active_dof_indices)
+    std::vector<float> _limits;              // nq x 6 (b2g_model_get_dof_limits)
 };
+
+// ------------------------------------------------------------------------------------------------ Object (one world)
+inline const std::string& Object::getName() const { return _batch->_objects[_object].name; }
+inline EntityType Object::getType() const { return _batch->_objects[_object].is_robot ? EntityType::Robot : EntityType::Object; }
+inline bool Object::isStatic() const { return _batch->_objects[_object].is_static; }
+inline unsigned int Object::getNumDOFs() const { return (unsigned int)_batch->_objects[_object].n_dofs; }
+inline std::vector<int> Object::getDOFIndices() const {
+    std::vector<int> v(getNumDOFs());
+    for (size_t i = 0; i < v.size(); ++i) v[i] = (int)i;
+    return v;
+}
+inline std::vector<int> Object::getActiveDOFs() const { return _batch->_active[_object]; }
+inline void Object::setActiveDOFs(const std::vector<int>& indices) {
+    for (size_t i = 0; i < indices.size(); ++i)
+        if (indices[i] < 0 || indices[i] >= (int)getNumDOFs() || (i > 0 && indices[i] <= indices[i - 1]))
+            throw std::runtime_error("[sim_env::b2g::Object::setActiveDOFs] indices must be ascending DOF indices of the object");
+    _batch->_active[_object] = indices;
+}
+inline DOFInformation Object::getDOFInformation(unsigned int dof_index) const {
+    if (dof_index >= getNumDOFs()) throw std::runtime_error("[sim_env::b2g::Object::getDOFInformation] invalid DOF index");
+    DOFInformation d;
+    const float* l = &_batch->_limits[(size_t)(_batch->_objects[_object].dof_offset + (int)dof_index) * 6];
+    d.dof_index = (int)dof_index;
+    for (int k = 0; k < 2; ++k) {
+        d.position_limits[k] = l[k];
+        d.velocity_limits[k] = l[2 + k];
+        d.acceleration_limits[k] = l[4 + k];
+    }
+    d.cyclic = !isStatic() && dof_index == 2;  // base rotation (:1355)
+    return d;
+}
+inline std::vector<float> Object::getDOFPositions(const std::vector<int>& indices) const {
+    const std::vector<int>& ix = indices.empty() ? _batch->_active[_object] : indices;
+    std::vector<float> out(ix.size());
+    if (ix.empty()) return out;
+    BatchBox2DWorld::Select sel(_batch, _world);
+    std::vector<int32_t> i32(ix.begin(), ix.end());
+    BatchBox2DWorld::check(b2g_batch_get_object_dofs(_batch->_batch, _object, 0, i32.data(), (int)i32.size(), out.data()));
+    return out;
+}
+inline std::vector<float> Object::getDOFVelocities(const std::vector<int>& indices) const {
+    const std::vector<int>& ix = indices.empty() ? _batch->_active[_object] : indices;
+    std::vector<float> out(ix.size());
+    if (ix.empty()) return out;
+    BatchBox2DWorld::Select sel(_batch, _world);
+    std::vector<int32_t> i32(ix.begin(), ix.end());
+    BatchBox2DWorld::check(b2g_batch_get_object_dofs(_batch->_batch, _object, 1, i32.data(), (int)i32.size(), out.data()));
+    return out;
+}
+inline void Object::setDOFPositions(const std::vector<float>& values, const std::vector<int>& indices) {
+    const std::vector<int>& ix = indices.empty() ? _batch->_active[_object] : indices;
+    if (ix.size() != values.size())
+        throw std::runtime_error("[sim_env::Box2DObject::setDOFPositions] Could not set DOF positions."
+                                 " Number of indices to set and number of provided values do not match.");
+    if (ix.empty()) return;
+    BatchBox2DWorld::Select sel(_batch, _world);
+    std::vector<int32_t> i32(ix.begin(), ix.end());
+    BatchBox2DWorld::check(b2g_batch_set_object_dofs(_batch->_batch, _object, 0, i32.data(), (int)i32.size(), values.data()));
+}
+inline void Object::setDOFVelocities(const std::vector<float>& values, const std::vector<int>& indices) {
+    const std::vector<int>& ix = indices.empty() ? _batch->_active[_object] : indices;
+    if (ix.size() != values.size())  // (:1700-1704)
+        throw std::runtime_error("[sim_env::Box2DObject::setDOFVelocities] Could not set DOF velocities."
+                                 " Number of indices to set and number of provided values do not match.");
+    if (ix.empty()) return;
+    BatchBox2DWorld::Select sel(_batch, _world);
+    std::vector<int32_t> i32(ix.begin(), ix.end());
+    BatchBox2DWorld::check(b2g_batch_set_object_dofs(_batch->_batch, _object, 1, i32.data(), (int)i32.size(), values.data()));
+}
+inline void Object::getPose(float pose[3]) const {
+    BatchBox2DWorld::Select sel(_batch, _world);
+    BatchBox2DWorld::check(b2g_batch_get_object_pose(_batch->_batch, _object, pose));
+}
+inline void Object::setPose(const float pose[3]) {
+    BatchBox2DWorld::Select sel(_batch, _world);
+    BatchBox2DWorld::check(b2g_batch_set_object_pose(_batch->_batch, _object, pose));
+}
+inline void Object::getState(ObjectState& state) const {
+    state.active_dofs = _batch->_active[_object];
+    state.dof_positions = getNumDOFs() ? getDOFPositions(getDOFIndices()) : std::vector<float>();
+    state.dof_velocities = getNumDOFs() ? getDOFVelocities(getDOFIndices()) : std::vector<float>();
+    getPose(state.pose);
+}
+inline void Object::setState(const ObjectState& state) {
+    if (state.dof_positions.size() != getNumDOFs() || state.dof_velocities.size() != getNumDOFs())
+        throw std::runtime_error("[sim_env::b2g::Object::setState] the state must hold every DOF of the object");
+    setActiveDOFs(state.active_dofs);
+    setPose(state.pose);  // setTransform(object_state.pose) (:1984)
+    if (getNumDOFs()) {
+        setDOFPositions(state.dof_positions, getDOFIndices());
+        setDOFVelocities(state.dof_velocities, getDOFIndices());
+    }
+}
+inline void Object::getBallApproximation(std::vector<Ball>& balls) const {
+    const int n = _batch->_objects[_object].n_balls;
+    balls.resize((size_t)n);
+    if (n == 0) return;
+    std::vector<float> raw((size_t)n * 4);
+    BatchBox2DWorld::Select sel(_batch, _world);
+    BatchBox2DWorld::check(b2g_batch_get_ball_approximation(_batch->_batch, _object, raw.data()));
+    for (int i = 0; i < n; ++i) {
+        for (int d = 0; d < 3; ++d) balls[(size_t)i].center[d] = raw[(size_t)i * 4 + d];
+        balls[(size_t)i].radius = raw[(size_t)i * 4 + 3];
+    }
+}
+inline void Object::setTargetVelocity(const std::vector<float>& target) {
+    if (!_batch->_objects[_object].is_robot) throw std::logic_error("[sim_env::b2g::Object::setTargetVelocity] not a robot");
+    if (target.size() != getNumDOFs())
+        throw std::runtime_error("[sim_env::b2g::Object::setTargetVelocity] one target value per DOF of the robot is needed");
+    BatchBox2DWorld::Select sel(_batch, _world);
+    BatchBox2DWorld::check(b2g_batch_set_target_velocity(_batch->_batch, _object, target.data()));
+}
+inline bool Object::checkCollision() { return World(_batch, _world).checkCollision(*this); }
+inline bool Object::checkCollision(std::vector<Contact>& contacts) { return World(_batch, _world).checkCollision(*this, contacts); }
+inline bool Object::checkCollision(const Object& other) { return World(_batch, _world).checkCollision(*this, other); }
+inline bool Object::checkCollision(const Object& other, std::vector<Contact>& contacts) {
+    return World(_batch, _world).checkCollision(*this, other, contacts);
+}
+inline bool Object::checkCollision(const std::vector<Object>& others) { return World(_batch, _world).checkCollision(*this, others); }
+inline bool Object::checkCollision(const std::vector<Object>& others, std::vector<Contact>& contacts) {
+    return World(_batch, _world).checkCollision(*this, others, contacts);
+}
+
+// ------------------------------------------------------------------------------------------------- World (one world)
+inline Object World::getRobot(const std::string& name) const {
+    const int o = _batch->objectIndex(name);
+    if (!_batch->_objects[(size_t)o].is_robot) throw std::runtime_error("[sim_env::b2g::World::getRobot] '" + name + "' is not a robot");
+    return Object(_batch, _world, o);
+}
+inline Object World::getObject(const std::string& name, bool exclude_robots) const {
+    const int o = _batch->objectIndex(name);
+    if (exclude_robots && _batch->_objects[(size_t)o].is_robot)
+        throw std::runtime_error("[sim_env::b2g::World::getObject] '" + name + "' is a robot");
+    return Object(_batch, _world, o);
+}
+inline void World::getObjects(std::vector<Object>& objects, bool exclude_robots) const {
+    for (size_t o = 0; o < _batch->_objects.size(); ++o)
+        if (!exclude_robots || !_batch->_objects[o].is_robot) objects.push_back(Object(_batch, _world, (int)o));
+}
+inline void World::getRobots(std::vector<Object>& robots) const {
+    for (size_t o = 0; o < _batch->_objects.size(); ++o)
+        if (_batch->_objects[o].is_robot) robots.push_back(Object(_batch, _world, (int)o));
+}
+inline void World::stepPhysics(int steps, bool execute_controllers, bool allow_sleeping) {
+    if (_batch->_n != 1)
+        throw std::logic_error("[sim_env::b2g::World::stepPhysics] stepping advances every world of the batch: call "
+                               "BatchBox2DWorld::stepPhysics (a view steps only when the batch holds one world)");
+    _batch->stepPhysics(steps, execute_controllers, allow_sleeping);
+}
+inline bool World::stepPhysics(std::vector<Contact>& contacts, int steps, bool execute_controllers, bool allow_sleeping) {
+    if (_batch->_n != 1)
+        throw std::logic_error("[sim_env::b2g::World::stepPhysics] stepping advances every world of the batch: call "
+                               "BatchBox2DWorld::stepPhysics (a view steps only when the batch holds one world)");
+    std::vector<int64_t> offsets;
+    _batch->stepPhysics(contacts, offsets, steps, execute_controllers, allow_sleeping);
+    return true;
+}
+inline float World::getPhysicsTimeStep() const { return _batch->getPhysicsTimeStep(); }
+inline int World::getVelocitySteps() const { return _batch->getVelocitySteps(); }
+inline int World::getPositionSteps() const { return _batch->getPositionSteps(); }
+inline void World::getWorldState(WorldState& state) const {
+    for (size_t o = 0; o < _batch->_objects.size(); ++o) state[_batch->_objects[o].name] = Object(_batch, _world, (int)o).getState();
+}
+inline bool World::setWorldState(const WorldState& state) {
+    bool ok = true;
+    for (WorldState::const_iterator it = state.begin(); it != state.end(); ++it) {
+        int o = -1;
+        for (size_t i = 0; i < _batch->_objects.size(); ++i)
+            if (_batch->_objects[i].name == it->first) o = (int)i;
+        if (o < 0) {  // "Unknown object encountered!" (:3505-3508): warn and report failure
+            ok = false;
+            continue;
+        }
+        Object(_batch, _world, o).setState(it->second);
+    }
+    return ok;
+}
+inline std::vector<char> World::bodiesOf(const Object& o) const {
+    std::vector<char> in((size_t)_batch->_info.n_bodies, 0);
+    const ObjectInfo& oi = _batch->_objects[(size_t)o.index()];
+    for (int b = oi.first_body; b < oi.first_body + oi.n_links; ++b) in[(size_t)b] = 1;
+    return in;
+}
+inline bool World::checkCollision(std::vector<Contact>& contacts) {
+    const int cap = 128;  // kMaxContacts
+    std::vector<int32_t> io((size_t)cap * 4);
+    std::vector<float> fo((size_t)cap * 6);
+    int32_t count = 0;
+    {
+        BatchBox2DWorld::Select sel(_batch, _world);
+        BatchBox2DWorld::check(b2g_batch_check_collision(_batch->_batch, &count, io.data(), fo.data(), cap));
+    }
+    const int n = count < cap ? count : cap;
+    for (int k = 0; k < n; ++k) {
+        Contact c;
+        for (int d = 0; d < 3; ++d) { c.contact_point[d] = fo[(size_t)k * 6 + d]; c.contact_normal[d] = fo[(size_t)k * 6 + 3 + d]; }
+        c.body_a = io[(size_t)k * 4]; c.body_b = io[(size_t)k * 4 + 1];
+        c.fixture_a = io[(size_t)k * 4 + 2]; c.fixture_b = io[(size_t)k * 4 + 3];
+        contacts.push_back(c);
+    }
+    return n > 0;
+}
+inline bool World::filterContacts(const std::vector<char>& in_a, const std::vector<char>* in_b, std::vector<Contact>* out,
+                                  std::vector<char>* hit_bodies) {
+    std::vector<Contact> all;
+    checkCollision(all);
+    bool hit = false;
+    for (size_t k = 0; k < all.size(); ++k) {
+        for (int flip = 0; flip < 2; ++flip) {  // the cache holds every contact under both of its bodies (:2904-2905)
+            Contact c = all[k];
+            if (flip) { int t = c.body_a; c.body_a = c.body_b; c.body_b = t; t = c.fixture_a; c.fixture_a = c.fixture_b; c.fixture_b = t; }
+            if (!in_a[(size_t)c.body_a]) continue;
+            if (in_b && !(*in_b)[(size_t)c.body_b]) continue;
+            hit = true;
+            if (out) out->push_back(c);
+            if (hit_bodies) (*hit_bodies)[(size_t)c.body_b] = 1;
+        }
+    }
+    return hit;
+}
+inline bool World::checkCollision(const Object& a, const Object& b) {
+    std::vector<char> ia = bodiesOf(a), ib = bodiesOf(b);
+    return filterContacts(ia, &ib, nullptr);
+}
+inline bool World::checkCollision(const Object& a, const Object& b, std::vector<Contact>& contacts) {
+    std::vector<char> ia = bodiesOf(a), ib = bodiesOf(b);
+    return filterContacts(ia, &ib, &contacts);
+}
+inline bool World::checkCollision(const Object& object) { return filterContacts(bodiesOf(object), nullptr, nullptr); }
+inline bool World::checkCollision(const Object& object, std::vector<Contact>& contacts) {
+    return filterContacts(bodiesOf(object), nullptr, &contacts);
+}
+inline bool World::checkCollision(const Object& object, std::vector<Object>& collidors) {
+    std::vector<char> hitBodies((size_t)_batch->_info.n_bodies, 0);
+    const bool hit = filterContacts(bodiesOf(object), nullptr, nullptr, &hitBodies);
+    for (size_t o = 0; o < _batch->_objects.size(); ++o) {
+        const ObjectInfo& oi = _batch->_objects[o];
+        bool any = false;
+        for (int b = oi.first_body; b < oi.first_body + oi.n_links; ++b) any = any || hitBodies[(size_t)b];
+        if (any) collidors.push_back(Object(_batch, _world, (int)o));
+    }
+    return hit;
+}
+inline bool World::checkCollision(const Object& a, const std::vector<Object>& others) {
+    std::vector<char> ib((size_t)_batch->_info.n_bodies, 0);
+    for (size_t i = 0; i < others.size(); ++i) {
+        std::vector<char> t = bodiesOf(others[i]);
+        for (size_t b = 0; b < t.size(); ++b) ib[b] = ib[b] || t[b];
+    }
+    return filterContacts(bodiesOf(a), &ib, nullptr);
+}
+inline bool World::checkCollision(const Object& a, const std::vector<Object>& others, std::vector<Contact>& contacts) {
+    std::vector<char> ib((size_t)_batch->_info.n_bodies, 0);
+    for (size_t i = 0; i < others.size(); ++i) {
+        std::vector<char> t = bodiesOf(others[i]);
+        for (size_t b = 0; b < t.size(); ++b) ib[b] = ib[b] || t[b];
+    }
+    return filterContacts(bodiesOf(a), &ib, &contacts);
+}
+inline bool World::checkCollisionLink(int link_body) {
+    std::vector<char> ia((size_t)_batch->_info.n_bodies, 0);
+    ia.at((size_t)link_body) = 1;
+    return filterContacts(ia, nullptr, nullptr);
+}
+inline bool World::checkCollisionLink(int link_body, std::vector<Contact>& contacts) {
+    std::vector<char> ia((size_t)_batch->_info.n_bodies, 0);
+    ia.at((size_t)link_body) = 1;
+    return filterContacts(ia, nullptr, &contacts);
+}
+inline bool World::checkCollisionLink(int link_body, const std::vector<int>& other_link_bodies, std::vector<Contact>* contacts) {
+    std::vector<char> ia((size_t)_batch->_info.n_bodies, 0), ib((size_t)_batch->_info.n_bodies, 0);
+    ia.at((size_t)link_body) = 1;
+    for (size_t i = 0; i < other_link_bodies.size(); ++i) ib.at((size_t)other_link_bodies[i]) = 1;
+    return filterContacts(ia, &ib, contacts);
+}
+inline bool World::checkCollisionLink(int link_body, const std::vector<Object>& other_objects, std::vector<Contact>* contacts) {
+    std::vector<char> ia((size_t)_batch->_info.n_bodies, 0), ib((size_t)_batch->_info.n_bodies, 0);
+    ia.at((size_t)link_body) = 1;
+    for (size_t i = 0; i < other_objects.size(); ++i) {
+        std::vector<char> t = bodiesOf(other_objects[i]);
+        for (size_t b = 0; b < t.size(); ++b) ib[b] = ib[b] || t[b];
+    }
+    return filterContacts(ia, &ib, contacts);
+}
+inline bool World::checkCollision(const Object& a, int link_body_b, std::vector<Contact>* contacts) {
+    std::vector<char> ib((size_t)_batch->_info.n_bodies, 0);
+    ib.at((size_t)link_body_b) = 1;
+    return filterContacts(bodiesOf(a), &ib, contacts);
+}
+inline bool World::atRest(float threshold) const {
+    int32_t out = 0;
+    BatchBox2DWorld::Select sel(_batch, _world);
+    BatchBox2DWorld::check(b2g_batch_at_rest(_batch->_batch, threshold, &out));
+    return out != 0;
+}
+inline bool World::isPhysicallyFeasible() const {
+    int32_t out = 0;
+    BatchBox2DWorld::Select sel(_batch, _world);
+    BatchBox2DWorld::check(b2g_batch_is_physically_feasible(_batch->_batch, &out));
+    return out != 0;
+}
+inline void World::getObjects(const float aabb[4], std::vector<Object>& objects, bool exclude_robots) const {
+    std::vector<uint8_t> hits(_batch->_objects.size());
+    {
+        BatchBox2DWorld::Select sel(_batch, _world);
+        BatchBox2DWorld::check(b2g_batch_objects_in_aabb(_batch->_batch, aabb, exclude_robots, hits.data()));
+    }
+    for (size_t o = 0; o < hits.size(); ++o)
+        if (hits[o]) objects.push_back(Object(_batch, _world, (int)o));
+}
 
 }  // namespace b2g
 }  // namespace sim_env

@@ -39,6 +39,10 @@ def lib():
         L.b2o_env_add_object.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.b2o_env_add_link.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p] + [C.c_float] * 5
         L.b2o_env_add_polygon.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.b2o_env_add_ball.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float]
+        L.b2o_world_set_object_dofs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.b2o_world_get_object_dofs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.b2o_world_ball_approximation.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.b2o_env_add_joint.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p,
                                         C.c_void_p, C.c_int, C.c_char_p]
         L.b2o_env_add_state.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -98,7 +102,9 @@ def _decode_link(node):
     gti = node["ground_torque_integral"] if "ground_torque_integral" in node else node["rot_friction"]
     return dict(name=str(node["name"]), geometry=[[float(v) for v in poly] for poly in node["geometry"]],
                 mass=float(node["mass"]), ground_friction=float(gf), ground_torque_integral=float(gti),
-                contact_friction=float(node["contact_friction"]), restitution=float(node["restitution"]))
+                contact_friction=float(node["contact_friction"]), restitution=float(node["restitution"]),
+                # yaml-cpp pairs [[x, y, z], radius] (Box2DIOUtils.h:139-142)
+                balls=[[float(c[0]), float(c[1]), float(c[2]), float(r)] for c, r in (node.get("balls") or [])])
 
 
 def _decode_joint(node):
@@ -174,6 +180,9 @@ class OracleEnv:
                     for poly in link["geometry"]:
                         p = _f32(poly)
                         L.b2o_env_add_polygon(self.h, is_robot, oi, li, _ptr(p), len(p))
+                    for ball in link.get("balls") or []:
+                        c = _f32(ball[:3])
+                        L.b2o_env_add_ball(self.h, is_robot, oi, li, _ptr(c), float(ball[3]))
                 for j in obj["joints"]:
                     params = _f32(list(j["axis"]) + list(j["position_limits"]) + list(j["velocity_limits"]) +
                                   list(j["acceleration_limits"]) + [j["axis_orientation"]])
@@ -254,6 +263,27 @@ class OracleWorld:
         p = np.zeros(3, np.float32)
         lib().b2o_world_get_object_pose(self.h, obj, _ptr(p))
         return p
+
+    def set_object_dofs(self, obj, values, indices=None, velocities=False):
+        """Box2DObject::setDOFPositions / setDOFVelocities(values, indices); indices None = all DOFs."""
+        v = _f32(values)
+        ix = np.ascontiguousarray(indices, np.int32) if indices is not None else None
+        if lib().b2o_world_set_object_dofs(self.h, obj, int(velocities), _ptr(ix), 0 if ix is None else len(ix), _ptr(v)):
+            raise RuntimeError(lib().b2o_last_error().decode())
+
+    def get_object_dofs(self, obj, indices=None, velocities=False):
+        ix = np.ascontiguousarray(indices, np.int32) if indices is not None else None
+        out = np.zeros(self.objects[obj]["n_dofs"] if ix is None else len(ix), np.float32)
+        lib().b2o_world_get_object_dofs(self.h, obj, int(velocities), _ptr(ix), 0 if ix is None else len(ix), _ptr(out))
+        return out
+
+    def ball_approximation(self, obj):
+        """Box2DObject::getBallApproximation: [n_balls, 4] = centre (world frame, user units), radius."""
+        n = lib().b2o_world_ball_approximation(self.h, obj, None)
+        out = np.zeros((n, 4), np.float32)
+        if n:
+            lib().b2o_world_ball_approximation(self.h, obj, _ptr(out))
+        return out
 
     def set_target_velocity(self, obj, v):
         v = _f32(v)

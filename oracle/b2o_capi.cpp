@@ -82,6 +82,11 @@ void b2o_env_add_polygon(void* env, int isRobot, int obj, int link, const float*
     o.links.at(link).polygons.emplace_back(xy, xy + nFloats);
 }
 
+void b2o_env_add_ball(void* env, int isRobot, int obj, int link, const float* center3, float radius) {
+    ObjectDesc& o = pick((EnvDesc*)env, isRobot, obj);
+    o.links.at(link).balls.push_back({center3[0], center3[1], center3[2], radius});
+}
+
 // params: axis(2), position_limits(2), velocity_limits(2), acceleration_limits(2), axis_orientation
 void b2o_env_add_joint(void* env, int isRobot, int obj, const char* name, const char* linkA, const char* linkB,
                        const float* params9, int actuated, const char* type) {
@@ -171,6 +176,31 @@ int b2o_world_set_object_pose(void* wp, int objIdx, float x, float y, float thet
 
 void b2o_world_get_object_pose(void* wp, int objIdx, float* pose3) {
     ((OWorld*)wp)->creationOrder.at(objIdx)->baseLink->getPose(pose3);
+}
+
+// Box2DObject::setDOFPositions / setDOFVelocities(values, indices); n == 0: all DOFs
+int b2o_world_set_object_dofs(void* wp, int objIdx, int velocities, const int* idx, int n, const float* values) {
+    OObject* o = ((OWorld*)wp)->creationOrder.at(objIdx);
+    try {
+        std::vector<int> ix = n > 0 ? std::vector<int>(idx, idx + n) : o->allDofs();
+        std::vector<float> v(values, values + ix.size());
+        if (velocities) o->setDOFVelocities(v, ix); else o->setDOFPositions(v, ix);
+        return 0;
+    } catch (const std::exception& ex) { g_err = ex.what(); return 1; }
+}
+void b2o_world_get_object_dofs(void* wp, int objIdx, int velocities, const int* idx, int n, float* out) {
+    OObject* o = ((OWorld*)wp)->creationOrder.at(objIdx);
+    std::vector<int> ix = n > 0 ? std::vector<int>(idx, idx + n) : o->allDofs();
+    std::vector<float> v = velocities ? o->getDOFVelocities(ix) : o->getDOFPositions(ix);
+    memcpy(out, v.data(), v.size() * sizeof(float));
+}
+
+// Box2DObject::getBallApproximation: returns the number of balls; out (may be null) receives [n][4]
+int b2o_world_ball_approximation(void* wp, int objIdx, float* out) {
+    std::vector<float> v;
+    ((OWorld*)wp)->creationOrder.at(objIdx)->ballApproximation(v);
+    if (out) memcpy(out, v.data(), v.size() * sizeof(float));
+    return (int)v.size() / 4;
 }
 
 int b2o_world_set_target_velocity(void* wp, int objIdx, const float* v, int n) {

@@ -35,6 +35,23 @@ void OLink::getPose(float pose[3]) const {  // Box2DWorld.cpp:215-224
     pose[2] = body->GetAngle();
 }
 
+void OLink::ballApproximation(std::vector<float>& out) const {  // :733-747 with getTransform() :193-213
+    // getTransform(): matrix(0,0) = cos(a), (0,1) = -sin(a), (1,0) = -(0,1), (1,1) = (0,0), translation = invScale *
+    // GetWorldPoint(_local_origin_offset).  cos / sin of the body angle are the engine's own (Rot), as everywhere else.
+    Vec2 pos = body->GetWorldPoint(localOriginOffset);
+    float inv = world->invScale();
+    Rot r(body->GetAngle());
+    const float m00 = r.c, m01 = -r.s, m10 = -m01, m11 = m00;
+    const float tx = inv * pos.x, ty = inv * pos.y;
+    for (const std::vector<float>& b : balls) {
+        // Eigen: Affine3f * Vector3f = linear * v + translation, coefficient sums left to right
+        out.push_back(((m00 * b[0] + m01 * b[1]) + 0.0f * b[2]) + tx);
+        out.push_back(((m10 * b[0] + m11 * b[1]) + 0.0f * b[2]) + ty);
+        out.push_back(((0.0f * b[0] + 0.0f * b[1]) + 1.0f * b[2]) + 0.0f);
+        out.push_back(b[3]);
+    }
+}
+
 void OLink::getVelocityVector(float v[3]) const {  // :233-241
     float inv = world->invScale();
     v[0] = inv * body->linearVelocity.x;
@@ -164,6 +181,10 @@ std::vector<int> OObject::allDofs() const {
     std::vector<int> v(numDofs);
     for (unsigned i = 0; i < numDofs; ++i) v[i] = (int)i;
     return v;
+}
+
+void OObject::ballApproximation(std::vector<float>& out) const {  // :1754-1763
+    for (const auto& kv : links) kv.second->ballApproximation(out);
 }
 
 std::vector<float> OObject::getDOFPositions(const std::vector<int>& idxIn) const {  // :1507-1528
@@ -386,6 +407,7 @@ OObject* OWorld::createObject(const ObjectDesc& d) {  // Box2DObject ctor :1292-
         link->world = this;
         link->object = obj;
         link->localOriginOffset = Vec2(0.0f, 0.0f);
+        link->balls = ld.balls;  // :54-57
         link->body = b2->CreateBody(d.is_static ? kStaticBody : kDynamicBody, Vec2(0.0f, 0.0f), 0.0f);
         link->body->userData = link;
         float area = 0.0f;

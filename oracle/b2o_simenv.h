@@ -23,6 +23,7 @@ struct LinkDesc {
     float ground_torque_integral = 0.0f;
     float contact_friction = 0.0f;
     float restitution = 0.0f;
+    std::vector<std::vector<float>> balls;  // [x, y, z, radius] in the link frame (Box2DIOUtils.h:21, 139-142)
 };
 struct JointDesc {
     std::string name, link_a, link_b;
@@ -73,8 +74,11 @@ struct OLink {
     std::vector<OJoint*> childJoints;
     OJoint* parentJoint = nullptr;
     bool enabled = true;
+    std::vector<std::vector<float>> balls;  // Box2DLink::_balls (:54-57): [x, y, z, radius]
 
     void getPose(float pose[3]) const;
+    // Box2DLink::updateBallApproximation (:733-747): appends [x, y, z, radius] with centre = getTransform() * centre
+    void ballApproximation(std::vector<float>& out) const;
     void setPose(const float pose[3], bool updateChildren = true, bool jointOverride = false);
     void getVelocityVector(float v[3]) const;
     float getMass() const { return body->GetMass(); }
@@ -134,6 +138,8 @@ struct OObject {
     void setDOFPositions(const std::vector<float>& values, const std::vector<int>& idx);
     void setDOFVelocities(const std::vector<float>& values, const std::vector<int>& idx);
     void setPose(float x, float y, float theta);
+    // Box2DObject::getBallApproximation (:1754-1763): links in std::map (name) order
+    void ballApproximation(std::vector<float>& out) const;
     void updateBodyVelocities(const std::vector<float>& allDofVel);
     float getInertia() const;
     // controller

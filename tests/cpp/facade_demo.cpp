@@ -1,6 +1,7 @@
 // Exercises include/b2g_world.hpp the way a planner built on sim_env::Box2DWorld would (C++11, no CUDA headers needed).
 //   facade_demo <env.yaml> host   -> model introspection works, creating the batch fails loudly without a GPU
 //   facade_demo <env.yaml> gpu    -> steps 64 worlds and prints world 0's state as hex floats for the Python-side check
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -62,5 +63,63 @@ int main(int argc, char** argv) {
     } catch (const std::runtime_error&) {
         threw = true;
     }
-    return threw ? 0 : 1;
+    // ---- single-world views: the one-world signatures of Box2DWorld / Box2DObject on world 3
+    using namespace sim_env::b2g;
+    int bad = 0;
+    World w3 = batch.world(3);
+    Object robot = w3.getRobot("my_robot"), obj1 = w3.getObject("obj1"), obj2 = w3.getObject("obj2");
+    bad += robot.getNumDOFs() != 7 || obj1.getNumDOFs() != 3 || obj2.getNumDOFs() != 1 || !obj2.isStatic();
+    bad += robot.getType() != EntityType::Robot || obj1.getType() != EntityType::Object;
+    bad += !robot.getDOFInformation(2).cyclic || robot.getDOFInformation(3).cyclic;
+    std::vector<float> p = obj1.getDOFPositions();  // active DOFs = all DOFs
+    for (int i = 0; i < 3; ++i) bad += p[i] != q[(size_t)3 * nq + 7 + i];
+    std::vector<float> rv = robot.getDOFVelocities(std::vector<int>{0, 2, 5});
+    bad += rv[0] != qd[(size_t)3 * nq + 0] || rv[1] != qd[(size_t)3 * nq + 2] || rv[2] != qd[(size_t)3 * nq + 5];
+    obj1.setDOFPositions(std::vector<float>{0.55f}, std::vector<int>{0});  // x only, world 3 only
+    std::vector<float> q2, qd2;
+    batch.getWorldState(q2, qd2);
+    bad += std::fabs(q2[(size_t)3 * nq + 7] - 0.55f) > 1e-5f || std::fabs(q2[(size_t)3 * nq + 8] - q[(size_t)3 * nq + 8]) > 1e-5f;
+    for (int i = 0; i < nq; ++i) bad += q2[(size_t)4 * nq + i] != q[(size_t)4 * nq + i] || q2[(size_t)2 * nq + i] != q[(size_t)2 * nq + i];
+    WorldState ws = w3.getWorldState();
+    bad += ws.size() != 3 || std::fabs(ws["obj1"].dof_positions[0] - 0.55f) > 1e-5f;
+    ws["obj1"].dof_positions[1] = -0.25f;
+    ws["obj1"].pose[1] = -0.25f;
+    bad += !w3.setWorldState(ws);
+    bad += std::fabs(obj1.getDOFPositions(std::vector<int>{1})[0] + 0.25f) > 1e-5f;
+    WorldState unknown;
+    unknown["nobody"] = ws["obj1"];
+    bad += w3.setWorldState(unknown);  // unknown names: false, like the reference (:3505-3510)
+    // collision overloads agree with the world's contact list
+    int viewHits = 0;
+    for (int w = 0; w < n; ++w) {
+        World vw = batch.world(w);
+        std::vector<Contact> all, ro;
+        bool any = vw.checkCollision(all);
+        Object r = vw.getRobot("my_robot"), o1 = vw.getObject("obj1");
+        bool pair = vw.checkCollision(r, o1, ro);
+        bool expect = false;
+        size_t cnt = 0;
+        const int rb0 = batch.getObjects()[0].first_body, rn = batch.getObjects()[0].n_links;
+        const int ob0 = batch.getObjects()[1].first_body, on = batch.getObjects()[1].n_links;
+        for (size_t k = 0; k < all.size(); ++k) {
+            bool aR = all[k].body_a >= rb0 && all[k].body_a < rb0 + rn, bR = all[k].body_b >= rb0 && all[k].body_b < rb0 + rn;
+            bool aO = all[k].body_a >= ob0 && all[k].body_a < ob0 + on, bO = all[k].body_b >= ob0 && all[k].body_b < ob0 + on;
+            if ((aR && bO) || (aO && bR)) { expect = true; ++cnt; }
+        }
+        bad += pair != expect || ro.size() != cnt || (any != !all.empty());
+        for (size_t k = 0; k < ro.size(); ++k) bad += !(ro[k].body_a >= rb0 && ro[k].body_a < rb0 + rn);  // link_a is the queried one
+        bad += r.checkCollision(o1) != pair || o1.checkCollision(r) != pair;
+        std::vector<Object> collidors;
+        bool rc = vw.checkCollision(r, collidors);
+        bad += rc != r.checkCollision();
+        viewHits += pair ? 1 : 0;
+    }
+    bool viewThrew = false;
+    try {
+        w3.stepPhysics(1);
+    } catch (const std::logic_error&) {
+        viewThrew = true;
+    }
+    std::printf("VIEW bad=%d hits=%d threw=%d\n", bad, viewHits, (int)viewThrew);
+    return threw && viewThrew && bad == 0 ? 0 : 1;
 }

@@ -52,3 +52,5 @@ def test_facade_matches_python_mirror(tmp_path, b2g):
     q1, _ = batch.getWorldState()
     assert np.array_equal(q1[0], q0_cpp)
     assert "recorded=%d " % int(np.minimum(counts, 32).sum()) in line and "restored=1" in line
+    view = [l for l in out.stdout.splitlines() if l.startswith("VIEW")][0]
+    assert "bad=0" in view and "threw=1" in view, view

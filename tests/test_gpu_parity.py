@@ -419,3 +419,70 @@ def test_large_batch_full_warp_path(b2g, env_name, n):
     counts, cio, _ = batch.contacts(max_per_world=4)
     assert int(cio[..., 2].sum()) > 50
     assert np.all(batch.status() == 0)
+
+
+@pytest.mark.parametrize("env_name", [ENV_A, ENV_B])
+def test_object_dof_subsets_parity(b2g, env_name):
+    """Box2DObject::setDOFPositions / setDOFVelocities / getDOF*(values, indices) on index subsets (:1585-1626, 1691-1715):
+    every object, several ascending subsets, interleaved with stepping; bit-exact vs the oracle."""
+    n = 32
+    batch = make_batch(b2g, env_name, n)
+    worlds = oracle_worlds(load_env_dict(env_name), n)
+    model = batch.model
+    rng = np.random.default_rng(31)
+    q, qd = random_states(model, n, seed=32)
+    batch.setWorldState(q, qd, reset_caches=True)
+    for w, ow in enumerate(worlds):
+        ow.set_state(q[w], qd[w])
+    lim = model.dof_limits()
+    for rnd in range(3):
+        for o, info in enumerate(model.objects):
+            nd = info["n_dofs"]
+            if nd == 0:
+                continue
+            k = int(rng.integers(1, nd + 1))
+            idx = np.sort(rng.choice(nd, size=k, replace=False)).astype(np.int32)
+            lo = np.maximum(lim[info["dof_offset"] + idx, 0], -2.0)
+            hi = np.minimum(lim[info["dof_offset"] + idx, 1], 2.0)
+            vals = rng.uniform(lo, hi, (n, k)).astype(np.float32)
+            vels = rng.uniform(-3.0, 3.0, (n, k)).astype(np.float32)   # partly outside the velocity limits: clamped
+            use_idx = None if k == nd and rnd == 0 else idx
+            batch.setDOFPositions(o, vals, use_idx)
+            batch.setDOFVelocities(o, vels, use_idx)
+            for w, ow in enumerate(worlds):
+                ow.set_object_dofs(o, vals[w], use_idx)
+                ow.set_object_dofs(o, vels[w], use_idx, velocities=True)
+            gp, gv = batch.getDOFPositions(o, use_idx), batch.getDOFVelocities(o, use_idx)
+            for w, ow in enumerate(worlds):
+                assert np.array_equal(gp[w], ow.get_object_dofs(o, use_idx))
+                assert np.array_equal(gv[w], ow.get_object_dofs(o, use_idx, velocities=True))
+        assert_same(batch, worlds, "DOF subsets round %d" % rnd)
+        batch.stepPhysics(3)
+        for ow in worlds:
+            ow.step(3)
+        assert_same(batch, worlds, "DOF subsets + steps round %d" % rnd)
+
+
+def test_select_worlds(b2g):
+    """b2g_batch_select_worlds: per-world calls on a sub-range touch only that range; stepping refuses a partial selection."""
+    n = 40
+    batch = make_batch(b2g, ENV_A, n)
+    q, qd = random_states(batch.model, n, seed=5)
+    batch.setWorldState(q, qd, reset_caches=True)
+    before = batch.bodies()
+    batch.selectWorlds(33, 4)
+    sq, sqd = batch.getWorldState()
+    assert sq.shape == (4, batch.nq)
+    full_q, _ = (q, qd)
+    pose = np.tile(np.float32([0.3, -0.4, 0.5]), (4, 1))
+    batch.setObjectPose("obj1", pose)
+    assert np.array_equal(batch.getObjectPose("obj1")[:, :2], pose[:, :2])
+    with pytest.raises(RuntimeError):
+        batch.stepPhysics(1)
+    batch.selectWorlds()
+    after = batch.bodies()
+    same = [np.array_equal(before[w], after[w]) for w in range(n)]
+    assert all(same[:33]) and all(same[37:]) and not any(same[33:37])
+    got_q, _ = batch.getWorldState()
+    assert np.array_equal(got_q[33:37], np.concatenate([sq[:, :7], batch.getObjectPose("obj1")[33:37], sq[:, 10:]], 1))
+    batch.stepPhysics(2)
