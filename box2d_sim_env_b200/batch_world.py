@@ -62,12 +62,15 @@ def lib():
     if _LIB is not None:
         return _LIB
     so = os.path.join(_HERE, "libb2g.so")
-    try:
-        from . import build as _build
-        so = _build.build()
-    except Exception:
-        if not os.path.exists(so):
-            raise
+    if os.environ.get("B2G_LIB"):  # tuning experiments only: a prebuilt variant of the library
+        so = os.environ["B2G_LIB"]
+    else:
+        try:
+            from . import build as _build
+            so = _build.build()
+        except Exception:
+            if not os.path.exists(so):
+                raise
     L = C.CDLL(so)
     vp, ip, fp = C.c_void_p, C.c_void_p, C.c_void_p
     L.b2g_last_error.restype = C.c_char_p

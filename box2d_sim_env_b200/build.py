@@ -34,7 +34,10 @@ def needs_build():
     return False
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None):
+    global LIB
+    if out:  # tuning experiments: build a variant next to the product library
+        LIB = out
     if not force and not needs_build():
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "--fmad=false", "-lineinfo", "-std=c++17",

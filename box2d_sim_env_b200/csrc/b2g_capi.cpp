@@ -341,12 +341,21 @@ b2g_status b2g_batch_create(const b2g_model* model, int64_t n_worlds, int device
     const char* envStep = getenv("B2G_STEP_BLOCK");
     if (envStep) b->stepBlock = atoi(envStep);
     else if (envBlock) b->stepBlock = b->block;
-    else {  // about two CTAs per SM once the batch is large enough (measured optimum on B200, tools/block_sweep.sh)
-        long long want = (n_worlds + 295) / 296;
-        b->stepBlock = 32;
-        while (b->stepBlock < want && b->stepBlock < 256) b->stepBlock *= 2;
+    else {
+        // Two CTAs per SM, sized so that the grid fills all 148 SMs evenly: with 110 registers per thread an SM holds 16
+        // warps of k_step, so the batch runs in `waves` rounds of at most 148 x 16 warps; the warps of one round are
+        // split evenly over the SMs (CTA size = any multiple of 32) instead of leaving a partly filled last round or SMs
+        // with one CTA next to SMs with two.  Fewer resident warps per SM also keep the velocity-iteration working set
+        // closer to the L1 capacity.  65536 worlds: 293 CTAs of 224 threads instead of 256 of 256.
+        const long long warps = (n_worlds + 31) / 32;
+        const long long waves = (warps + 148 * 16 - 1) / (148 * 16);
+        const long long perSM = (warps + waves * 148 - 1) / (waves * 148);
+        long long w = (perSM + 1) / 2;
+        if (w < 1) w = 1;
+        if (w > 8) w = 8;
+        b->stepBlock = (int)(32 * w);
     }
-    if (b->stepBlock < 32 || b->stepBlock > kWorldPad || (b->stepBlock & (b->stepBlock - 1))) b->stepBlock = 32;
+    if (b->stepBlock < 32 || b->stepBlock > kWorldPad || (b->stepBlock % 32)) b->stepBlock = 32;
     // worlds per warp: a B200 has 148 x 4 warp schedulers; a batch with fewer than 592 full warps is spread over narrower
     // warps (k_step_narrow) so that rare per-world events serialise fewer neighbours
     const char* envLanes = getenv("B2G_LANES");
@@ -367,7 +376,7 @@ b2g_status b2g_batch_create(const b2g_model* model, int64_t n_worlds, int device
     // state[tile][chunk][lane]: tiles of 32 worlds, 16-byte chunks (model.h)
     // padded to a multiple of kWorldPad worlds: the padding worlds are idle copies that let every thread of a k_step CTA
     // take part in the phase barriers
-    size_t tiles = ((size_t)n_worlds + kWorldPad - 1) / kWorldPad * (kWorldPad / kTileWorlds);
+    size_t tiles = (size_t)paddedTiles(n_worlds);
     size_t stateBytes = tiles * (size_t)b->m.h.stateChunks * kChunkBytes;
     if ((e = cudaMalloc((void**)&b->S, stateBytes)) != cudaSuccess) return cleanup(e, "cudaMalloc(state)");
     if ((e = cudaMalloc((void**)&b->tmpl, (size_t)b->m.h.stateChunks * 16)) != cudaSuccess) return cleanup(e, "cudaMalloc(template)");
@@ -377,7 +386,14 @@ b2g_status b2g_batch_create(const b2g_model* model, int64_t n_worlds, int device
         l.N = 1;
         if ((e = launchInit(l)) != cudaSuccess) return cleanup(e, "init kernel");
         if ((e = launchExtractWorld(b->L(), b->tmpl, 0)) != cudaSuccess) return cleanup(e, "extract kernel");
-        if ((e = launchBroadcast(b->L(), b->tmpl)) != cudaSuccess) return cleanup(e, "broadcast kernel");
+        {   // every world, padding included, starts as a copy of the loaded world; the padding worlds are then parked
+            Launch p = b->L();
+            p.N = paddedTiles(n_worlds) * kTileWorlds;
+            if ((e = launchBroadcast(p, b->tmpl)) != cudaSuccess) return cleanup(e, "broadcast kernel");
+            p.prm.worldOffset = n_worlds;
+            p.N = paddedTiles(n_worlds) * kTileWorlds - n_worlds;
+            if ((e = launchPark(p)) != cudaSuccess) return cleanup(e, "park kernel");
+        }
         if ((e = cudaStreamSynchronize(b->stream)) != cudaSuccess) return cleanup(e, "init sync");
     }
     *out = b;

@@ -50,12 +50,26 @@ __global__ void k_init(const __grid_constant__ ModelHeader hdr, const uint32_t* 
     initWorld(c);
 }
 
-// broadcast the state of a template world (stored [chunk]) to every world: state[tile][chunk][lane] = tmpl[chunk]
-__global__ void k_broadcast(float4* S, const float4* __restrict__ tmpl, long long tiles, int chunks) {
-    long long total = tiles * chunks * kTileWorlds;
+// broadcast the state of a template world (stored [chunk]) to worlds [first, first + count):
+// state[tile][chunk][lane] = tmpl[chunk]; walks whole tiles so that every store instruction is a coalesced 512-byte row
+__global__ void k_broadcast(float4* S, const float4* __restrict__ tmpl, long long first, long long count, int chunks) {
+    const long long tile0 = first >> 5, tile1 = (first + count + 31) >> 5;
+    const long long total = (tile1 - tile0) * chunks * kTileWorlds;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        S[i] = tmpl[(i >> 5) % chunks];
+        const long long world = ((tile0 + i / ((long long)chunks * kTileWorlds)) << 5) + (i & 31);
+        if (world >= first && world < first + count) S[tile0 * chunks * kTileWorlds + i] = tmpl[(i >> 5) % chunks];
     }
+}
+
+// Padding worlds (behind the batch, model.h: paddedTiles) exist so that every thread of a k_step CTA owns real memory.  They
+// are parked: every body asleep, nothing buffered for the broad phase, no new-fixture flag -- a step of a parked world finds
+// no island, no pair and no contact, whatever the loaded scene looks like.
+__global__ void k_park(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
+                       StepParams prm) {
+    B2G_PROLOGUE();
+    for (int b = 0; b < H().nb; ++b) sleepBody(c, b);
+    stI(c, sslot(c, SS_FLAGS), ldI(c, sslot(c, SS_FLAGS)) & ~1);
+    stMoved(c, 0ull);
 }
 
 __global__ void k_extract_world(const float4* S, float4* tmpl, int chunks, long long world) {
@@ -491,6 +505,7 @@ static cudaError_t prepare(const void* fn, const ModelHeader& h) {
     } while (0)
 
 cudaError_t launchInit(const Launch& L) { LAUNCH(k_init); }
+cudaError_t launchPark(const Launch& L) { LAUNCH(k_park); }
 cudaError_t launchSetState(const Launch& L, const float* q, const float* qd) { LAUNCH(k_set_state, q, qd); }
 cudaError_t launchGetState(const Launch& L, float* q, float* qd) { LAUNCH(k_get_state, q, qd); }
 cudaError_t launchSetPose(const Launch& L, int object, const float* pose) { LAUNCH(k_set_pose, object, pose); }
@@ -559,13 +574,13 @@ cudaError_t launchGetContacts(const Launch& L, int* counts, int* iout, float* fo
 cudaError_t launchCheckCollision(const Launch& L, int* counts, int* iout, float* fout, int maxPer) {
     LAUNCH(k_check_collision, counts, iout, fout, maxPer);
 }
-cudaError_t launchBroadcast(const Launch& L, const float* tmpl) {
-    long long tiles = (L.N + kWorldPad - 1) / kWorldPad * (kWorldPad / kTileWorlds);  // padding worlds included
-    long long total = tiles * L.h.stateChunks * kTileWorlds;
+cudaError_t launchBroadcast(const Launch& L, const float* tmpl) {  // worlds [prm.worldOffset, prm.worldOffset + N)
+    const long long first = L.prm.worldOffset, count = L.N;
+    long long total = (((first + count + 31) >> 5) - (first >> 5)) * L.h.stateChunks * kTileWorlds;
     int threads = 256;
     long long want = (total + threads - 1) / threads;
     unsigned blocks = (unsigned)(want < 148 * 16 ? want : 148 * 16);
-    k_broadcast<<<blocks, threads, 0, L.stream>>>(reinterpret_cast<float4*>(L.S), reinterpret_cast<const float4*>(tmpl), tiles,
+    k_broadcast<<<blocks, threads, 0, L.stream>>>(reinterpret_cast<float4*>(L.S), reinterpret_cast<const float4*>(tmpl), first, count,
                                                  L.h.stateChunks);
     ++g_launches;
     return cudaGetLastError();

@@ -26,6 +26,7 @@ struct DofSel {
 
 unsigned long long launchCount();
 cudaError_t launchInit(const Launch& L);
+cudaError_t launchPark(const Launch& L);  // parks worlds [prm.worldOffset, prm.worldOffset + N): the padding worlds
 cudaError_t launchBroadcast(const Launch& L, const float* tmpl);
 cudaError_t launchExtractWorld(const Launch& L, float* tmpl, long long world);
 cudaError_t launchSetState(const Launch& L, const float* q, const float* qd);

@@ -96,25 +96,22 @@ DEVN void jointInit(Ctx c, int j, float dtRatio) {
     V2 rB = mul(qB, mk(arm.z, arm.w));
     float mA = im.x, mB = im.z;
     float iA = im.y, iB = im.w;
-    st4(c, jw + WJ_R4, mk4(rA.x, rA.y, rB.x, rB.y));
 
     if (type == 0) {
         float kxx = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
         float kxy = -iA * rA.x * rA.y - iB * rB.x * rB.y;
         float kyx = kxy;
         float kyy = mA + mB + iA * rA.x * rA.x + iB * rB.x * rB.x;
-        // b2Mat22::GetInverse
+        // b2Mat22::GetInverse; the inverse of a symmetric matrix is symmetric bit for bit (ex.y = -det * c, ey.x = -det * b, b == c)
         float a = kxx, b = kyx, cc = kxy, d = kyy;
         float det = a * d - b * cc;
         if (det != 0.0f) det = 1.0f / det;
-        st4(c, jw + WJ_M0, mk4(det * d, -det * cc, -det * b, det * a));  // ex.x ex.y ey.x ey.y
-        float angularMass = iA + iB;
-        if (angularMass > 0.0f) angularMass = 1.0f / angularMass;
+        st4(c, jw + WJ_R4, mk4(rB.y, det * d, -det * cc, det * a));  // rB.y  M.xx  M.xy  M.yy
         // warm start
         float4 imp = ld4(c, js + SJ_IMPULSE4);
         V2 P = mk(imp.x * dtRatio, imp.y * dtRatio);
         float ang = imp.z * dtRatio;
-        st4(c, js + SJ_IMPULSE4, mk4(P.x, P.y, ang, angularMass));
+        st4(c, js + SJ_IMPULSE4, mk4(P.x, P.y, ang, rB.x));
         A.v = A.v - mA * P;
         A.w -= iA * (cross(rA, P) + ang);
         B.v = B.v + mB * P;
@@ -127,12 +124,10 @@ DEVN void jointInit(Ctx c, int j, float dtRatio) {
         float eyy = mA + mB + rA.x * rA.x * iA + rB.x * rB.x * iB;
         float ezy = rA.x * iA + rB.x * iB;
         // symmetric: ex.y = ey.x, ex.z = ez.x, ey.z = ez.y; ez.z = iA + iB is recomputed by the solver
-        st4(c, jw + WJ_M0, mk4(exx, eyx, eyy, 0.0f));
-        st4(c, jw + WJ_M1, mk4(ezx, ezy, 0.0f, 0.0f));
-        float motorMass = iA + iB;
-        if (motorMass > 0.0f) motorMass = 1.0f / motorMass;
+        st4(c, jw + WJ_R4, mk4(rA.x, rA.y, rB.x, rB.y));
+        st4(c, jw + WJ_M0, mk4(exx, eyx, eyy, ezx));
 
-        float4 mot = ld4(c, js + SJ_MOTOR4);  // flags maxMotorTorque motorSpeed motorMass
+        float4 mot = ld4(c, js + SJ_MOTOR4);  // flags maxMotorTorque motorSpeed | K.zy
         int flags = __float_as_int(mot.x);
         bool enableMotor = (flags & 4) != 0;
         int limitState = flags & 3;
@@ -162,7 +157,7 @@ DEVN void jointInit(Ctx c, int j, float dtRatio) {
             limitState = 0;
         }
         mot.x = __int_as_float((flags & ~3) | limitState);
-        mot.w = motorMass;
+        mot.w = ezy;
         st4(c, js + SJ_MOTOR4, mot);
         imp.x *= dtRatio; imp.y *= dtRatio; imp.z *= dtRatio;
         motorImpulse *= dtRatio;
@@ -177,42 +172,37 @@ DEVN void jointInit(Ctx c, int j, float dtRatio) {
     if (!staticB) stVelAt(c, off.w, B);
 }
 
-// b2FrictionJoint::SolveVelocityConstraints.  STATIC_A: bodyA is static (the ground for every link's friction
-// joint, Box2DWorld.cpp:134-147) -- its velocity is the constant +0 and all of its updates are dead code.
-template <bool STATIC_A>
+// b2FrictionJoint::SolveVelocityConstraints.  bodyA is the static ground (every link's friction joint,
+// Box2DWorld.cpp:134-147; enforced by the model builder): its velocity is the constant +0 and all of its updates are
+// dead code, so neither its velocity nor its anchor arm is loaded.  Two joint chunks + one body chunk per solve.
 DEV void frictionSolveVel(Ctx c, int jr) {
-    const int4 off = mi4(c, jr + MJ_SOFF);     // js jw bodyA bodyB
-    const float4 im = m4(c, jr + MJ_MA);       // mA iA mB iB
-    const float2 hmax = m2(c, jr + MJ_HMAXFORCE);  // dt * maxForce, dt * maxTorque
+    const int4 off = mi4(c, jr + MJ_SOFF);         // js jw bodyA bodyB
+    const float4 im = m4(c, jr + MJ_MA);           // mA iA mB iB
+    const float4 hm = m4(c, jr + MJ_HMAXFORCE);    // dt * maxForce, dt * maxTorque, angularMass, -
     const int js = off.x, jw = off.y;
-    Vel A = STATIC_A ? zeroVel() : ldVelAt(c, off.z);
     Vel B = ldVelAt(c, off.w);
-    float mA = im.x, mB = im.z;
-    float iA = im.y, iB = im.w;
-    const float4 r = ld4(c, jw + WJ_R4);
-    const float4 lm = ld4(c, jw + WJ_M0);
-    float4 acc4 = ld4(c, js + SJ_IMPULSE4);  // linearImpulse.xy angularImpulse angularMass
-    V2 rA = mk(r.x, r.y);
-    V2 rB = mk(r.z, r.w);
+    const float mB = im.z, iB = im.w;
+    const float4 wk = ld4(c, jw + WJ_R4);          // rB.y  M.xx  M.xy  M.yy
+    float4 acc4 = ld4(c, js + SJ_IMPULSE4);        // linearImpulse.xy angularImpulse rB.x
+    const V2 rB = mk(acc4.w, wk.x);
     {
-        float Cdot = B.w - A.w;
-        float impulse = -acc4.w * Cdot;
+        float Cdot = B.w - 0.0f;
+        float impulse = -hm.z * Cdot;
         float oldImpulse = acc4.z;
-        float maxImpulse = hmax.y;
+        float maxImpulse = hm.y;
         float acc = clampT(oldImpulse + impulse, -maxImpulse, maxImpulse);
         acc4.z = acc;
         impulse = acc - oldImpulse;
-        A.w -= iA * impulse;
         B.w += iB * impulse;
     }
     {
-        V2 Cdot = B.v + cross(B.w, rB) - A.v - cross(A.w, rA);
-        float exx = lm.x, exy = lm.y;
-        float eyx = lm.z, eyy = lm.w;
+        V2 Cdot = B.v + cross(B.w, rB) - mk(0.0f, 0.0f) - mk(-0.0f, 0.0f);  // - vA - cross(wA, rA) with vA = wA = +0
+        float exx = wk.y, exy = wk.z;
+        float eyx = wk.z, eyy = wk.w;
         V2 impulse = -mk(exx * Cdot.x + eyx * Cdot.y, exy * Cdot.x + eyy * Cdot.y);
         V2 oldImpulse = mk(acc4.x, acc4.y);
         V2 acc = oldImpulse + impulse;
-        float maxImpulse = hmax.x;
+        float maxImpulse = hm.x;
         if (dot(acc, acc) > maxImpulse * maxImpulse) {
             normalize(acc);
             acc = mk(acc.x * maxImpulse, acc.y * maxImpulse);
@@ -220,13 +210,10 @@ DEV void frictionSolveVel(Ctx c, int jr) {
         acc4.x = acc.x;
         acc4.y = acc.y;
         impulse = acc - oldImpulse;
-        A.v = A.v - mA * impulse;
-        A.w -= iA * cross(rA, impulse);
         B.v = B.v + mB * impulse;
         B.w += iB * cross(rB, impulse);
     }
     st4(c, js + SJ_IMPULSE4, acc4);
-    if (!STATIC_A) stVelAt(c, off.z, A);
     stVelAt(c, off.w, B);
 }
 
@@ -255,9 +242,10 @@ DEV void revoluteSolveVel(Ctx c, int jr, int modelFlags) {
     float mA = im.x, mB = im.z;
     float iA = im.y, iB = im.w;
     const float4 r = ld4(c, jw + WJ_R4);
-    const float4 k0 = ld4(c, jw + WJ_M0);     // ex.x ex.y(=ey.x) ey.y -
-    const float4 mot = ld4(c, js + SJ_MOTOR4);  // flags maxMotorTorque motorSpeed motorMass
+    const float4 k0 = ld4(c, jw + WJ_M0);       // K.xx K.xy(=K.yx) K.yy K.zx(=K.xz)
+    const float4 mot = ld4(c, js + SJ_MOTOR4);  // flags maxMotorTorque motorSpeed K.zy(=K.yz)
     float4 imp4 = ld4(c, js + SJ_IMPULSE4);     // impulse.xyz motorImpulse
+    const float motorMass = mF(c, jr + MJ_ROTMASS);
     V2 rA = mk(r.x, r.y);
     V2 rB = mk(r.z, r.w);
     int flags = __float_as_int(mot.x);
@@ -268,7 +256,7 @@ DEV void revoluteSolveVel(Ctx c, int jr, int modelFlags) {
 
     if (enableMotor && limitState != 3 && fixedRotation == false) {
         float Cdot = B.w - A.w - mot.z;
-        float impulse = -mot.w * Cdot;
+        float impulse = -motorMass * Cdot;
         float oldImpulse = imp4.w;
         float maxImpulse = PRM().dt * mot.y;
         float acc = clampT(oldImpulse + impulse, -maxImpulse, maxImpulse);
@@ -278,8 +266,7 @@ DEV void revoluteSolveVel(Ctx c, int jr, int modelFlags) {
         B.w += iB * impulse;
     }
     if (enableLimit && limitState != 0 && fixedRotation == false) {
-        const float4 k1 = ld4(c, jw + WJ_M1);  // ez.x(=ex.z) ez.y(=ey.z)
-        float m[9] = {k0.x, k0.y, k1.x, k0.y, k0.z, k1.y, k1.x, k1.y, iA + iB};
+        float m[9] = {k0.x, k0.y, k0.w, k0.y, k0.z, mot.w, k0.w, mot.w, iA + iB};
         V2 Cdot1 = B.v + cross(B.w, rB) - A.v - cross(A.w, rA);
         float Cdot2 = B.w - A.w;
         V3 Cdot = {Cdot1.x, Cdot1.y, Cdot2};
@@ -418,7 +405,7 @@ DEV bool revoluteSolvePos(Ctx c, int jr, int modelFlags) {
     float positionError = 0.0f;
     bool fixedRotation = (iA + iB == 0.0f);
     if (enableLimit && limitState != 0 && fixedRotation == false) {
-        float motorMass = mot.w;
+        float motorMass = mF(c, jr + MJ_ROTMASS);
         const float4 lim = m4(c, jr + MJ_REF);
         float lower = lim.y, upper = lim.z;
         float angle = B.a - A.a - lim.x;
@@ -835,9 +822,12 @@ DEV void integratePosition(Ctx c, int b, float h) {
 // SASS); 16 resident warps that drift through different phases thrash the SM's instruction cache ("no_instructions"
 // was the top stall).  With SYNC every warp of the CTA walks the phases together, so the cache holds one phase.
 // All threads of the CTA must reach every phaseSync: they sit outside data-dependent control flow only.
-template <bool SYNC>
+#ifndef B2G_SYNC_MASK
+#define B2G_SYNC_MASK 0x3ff  /* tuning experiments: bit ID keeps phase barrier ID */
+#endif
+template <bool SYNC, int ID>
 DEV void phaseSync() {
-    if (SYNC) __syncthreads();
+    if (SYNC && ((B2G_SYNC_MASK >> ID) & 1)) __syncthreads();
 }
 
 
@@ -918,7 +908,7 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
     // first, which puts the free objects before the robot; emitting them in the opposite order keeps the lanes of
     // a warp aligned on the robot's joints (same model, same DFS) and leaves the part that differs from world to
     // world (which objects are awake) at the tail, where every entry has the same type.
-    phaseSync<SYNC>();
+    phaseSync<SYNC, 2>();
     //
     // "Simple" islands -- one dynamic body held by its ground-friction joint, no contacts: a free object, or a rigid
     // robot that touches nothing -- leave the lists altogether: their 15 velocity iterations only ever touch one body
@@ -974,13 +964,13 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
         V.w *= ld;
         stVelAt(c, bo, V);
     }
-    phaseSync<SYNC>();
+    phaseSync<SYNC, 3>();
     for (int i = 0; i < L.nc; ++i) contactInit(c, L.contacts[i], dtRatio, true);
     for (int i = 0; i < L.nc; ++i) contactWarmStart(c, L.contacts[i]);
     for (int i = 0; i < L.nj; ++i) jointInit(c, L.joints[i], dtRatio);
 
     const int velIters = PRM().velIters, posIters = PRM().posIters;
-    phaseSync<SYNC>();
+    phaseSync<SYNC, 4>();
     for (int it = 0; it < velIters; ++it) {
         for (int i = 0; i < L.nj; ++i) {
             const int jr = mjoint(c, L.joints[i], 0);
@@ -989,24 +979,23 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
             {   // pull the next joint's scratch, impulses and body velocities towards L1 while this one is solved
                 const int jn = mjoint(c, L.joints[i + 1 < L.nj ? i + 1 : 0], 0);
                 const int4 on = mi4(c, jn + MJ_SOFF);
-                pf(c, on.y + WJ_R4); pf(c, on.y + WJ_M0); pf(c, on.x + SJ_IMPULSE4); pf(c, on.x + SJ_MOTOR4);
+                pf(c, on.y + WJ_R4); pf(c, on.x + SJ_IMPULSE4);
                 pf(c, on.z + SB_VEL4); pf(c, on.w + SB_VEL4);
             }
 #endif
             if (jh.x == 0) {
-                if (jh.w & 4) frictionSolveVel<true>(c, jr);
-                else frictionSolveVel<false>(c, jr);
+                frictionSolveVel(c, jr);
             } else {
                 revoluteSolveVel(c, jr, jh.w);
             }
         }
         for (int i = 0; i < L.nc; ++i) contactSolveVel(c, L.contacts[i]);
     }
-    phaseSync<SYNC>();
+    phaseSync<SYNC, 5>();
     for (int i = 0; i < L.nc; ++i) contactStoreImpulses(c, L.contacts[i]);
     for (int i = 0; i < nSimple; ++i) frictionIslandSolve(c, L.joints[L.nj + i], dtRatio, velIters);
 
-    phaseSync<SYNC>();
+    phaseSync<SYNC, 6>();
     for (int i = 0; i < L.ndyn; ++i) integratePosition(c, L.dyn[i], h);
 
     // position iterations: every island leaves the loop on its own (b2Island::Solve breaks when contactsOkay &&
@@ -1037,7 +1026,7 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
         solved |= open & ~bad;
         open &= bad;
     }
-    phaseSync<SYNC>();
+    phaseSync<SYNC, 7>();
     for (int i = 0; i < L.ndyn; ++i) syncTransform(c, L.dyn[i]);
     for (uint64_t m = staticSeen; m; m &= m - 1ull) syncTransform(c, __ffsll((long long)m) - 1);
 
@@ -1072,7 +1061,7 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
         if ((asleep >> L.bodyIsl[b]) & 1ull) sleepBody(c, b); else wakeBody(c, b);
     }
 
-    phaseSync<SYNC>();
+    phaseSync<SYNC, 8>();
     uint64_t moved = 0ull;
     for (int b = nb - 1; b >= 0; --b) {
         if (((bodyFlag >> b) & 1ull) == 0ull) continue;

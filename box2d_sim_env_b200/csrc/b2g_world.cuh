@@ -416,11 +416,11 @@ DEVN void stepWorld(Ctx c, bool executeControllers, bool allowSleeping) {
         stI(c, sslot(c, SS_FLAGS), flags & ~1);
     }
     float dtRatio = ldF(c, sslot(c, SS_INV_DT0)) * PRM().dt;
-    phaseSync<SYNC>();
+    phaseSync<SYNC, 0>();
     collide(c);
-    phaseSync<SYNC>();
+    phaseSync<SYNC, 1>();
     solveIslands<SYNC>(c, dtRatio, allowSleeping);
-    phaseSync<SYNC>();
+    phaseSync<SYNC, 9>();
 #ifndef B2G_EXPERIMENT_NO_TOI  /* tuning experiment only: wrong physics, shows the register cost of the TOI call chain */
     solveTOI(c);
 #endif

@@ -56,7 +56,8 @@ enum JointField {
     MJ_SOFF, MJ_WOFF, MJ_BAOFF, MJ_BBOFF,  // byte offsets into the per-world state: joint state, joint scratch, bodyA, bodyB
     MJ_RA0X, MJ_RA0Y, MJ_RB0X, MJ_RB0Y,    // localAnchorA - localCenterA, localAnchorB - localCenterB
     MJ_HMAXFORCE, MJ_HMAXTORQUE,           // dt * maxForce, dt * maxTorque: written by the kernel prologue (depends on dt)
-    MJ_SPARE2, MJ_SPARE3,
+    MJ_ROTMASS,                            // m = iA + iB; if (m > 0) m = 1 / m: b2FrictionJoint::m_angularMass / b2RevoluteJoint::m_motorMass
+    MJ_SPARE3,
     MJ_MA, MJ_IA, MJ_MB, MJ_IB,            // invMass / invI of bodyA and bodyB
     MJ_STRIDE
 };
@@ -118,7 +119,11 @@ struct ModelHeader {
 //     base(tile, lane) + chunk * 512 + word * 4
 // Field enumerators below are such byte offsets relative to the first chunk of their record.
 constexpr int kTileWorlds = 32;
-constexpr int kWorldPad = 1024;  // the state array holds a multiple of this many worlds (= the largest CTA of k_step)
+constexpr int kWorldPad = 1024;  // the largest CTA of k_step
+// Tiles of the state array of an n-world batch: n rounded up to a multiple of kWorldPad plus one more kWorldPad worlds.
+// The padding worlds are valid idle copies of the loaded world: every thread of every k_step CTA (any CTA size that is a
+// multiple of 32 up to kWorldPad) owns a world that exists in memory and can take part in the phase barriers.
+inline long long paddedTiles(long long n) { return ((n + kWorldPad - 1) / kWorldPad + 1) * (kWorldPad / 32); }
 constexpr int kChunkBytes = 16 * kTileWorlds;  // 512
 #define B2G_F(chunk, word) ((chunk) * 512 + (word) * 4)
 
@@ -133,23 +138,26 @@ enum BodyState {
     SB_XF4 = B2G_F(0, 0), SB_POS4 = B2G_F(1, 0), SB_POS04 = B2G_F(2, 0), SB_VEL4 = B2G_F(3, 0), SB_FORCE4 = B2G_F(4, 0),
     SB_CHUNKS = 5
 };
+// Joint chunks are packed so that the velocity iterations -- the part of the step that sweeps the same chunks 15 times and
+// whose footprint decides whether a resident warp set fits in L1 -- touch as few chunks as possible (friction joint 2,
+// revolute joint 4, plus the bodies); constants of a joint (angular / motor mass, dt * limits) live in the model record.
+//   friction (bodyA is the static ground, model_build.cpp):
+//     SJ chunk 0  linearImpulse.xy angularImpulse | rB.x (scratch)        WJ chunk 0  rB.y  M.xx  M.xy(=M.yx)  M.yy   (M = K^-1)
+//   revolute:
+//     SJ chunk 0  impulse.xyz motorImpulse                                WJ chunk 0  rA.xy rB.xy
+//     SJ chunk 1  flags maxMotorTorque motorSpeed | K.zy (scratch)        WJ chunk 1  K.xx K.xy(=K.yx) K.yy K.zx   (K.zz = iA + iB)
 enum JointState {
     SJ_IX = B2G_F(0, 0), SJ_IY = B2G_F(0, 1), SJ_IZ = B2G_F(0, 2),  // friction: linearImpulse.xy, angularImpulse; revolute: m_impulse
-    SJ_MOTOR_IMPULSE = B2G_F(0, 3),                                 // revolute only
-    SJ_ANGULAR_MASS = B2G_F(0, 3),                                  // friction only (solver scratch kept next to the impulses)
+    SJ_MOTOR_IMPULSE = B2G_F(0, 3),                                 // revolute only (friction: scratch)
     SJ_FLAGS = B2G_F(1, 0),                                         // bits0-1 limitState, bit2 enableMotor
     SJ_MAX_MOTOR_TORQUE = B2G_F(1, 1), SJ_MOTOR_SPEED = B2G_F(1, 2),
-    SJ_MOTOR_MASS = B2G_F(1, 3),                                    // revolute solver scratch
     SJ_IMPULSE4 = B2G_F(0, 0), SJ_MOTOR4 = B2G_F(1, 0),
     SJ_CHUNKS = 2
 };
 enum JointWork {  // solver scratch, valid inside one island solve
-    WJ_RAX = B2G_F(0, 0), WJ_RAY = B2G_F(0, 1), WJ_RBX = B2G_F(0, 2), WJ_RBY = B2G_F(0, 3),
-    // friction: linearMass = [ex.x ex.y ey.x ey.y];  revolute: the symmetric 3x3 K is stored as
-    // [ex.x ex.y(=ey.x) ey.y -] [ez.x(=ex.z) ez.y(=ey.z) - -]; ez.z = iA + iB is recomputed
-    WJ_M0 = B2G_F(1, 0), WJ_M1 = B2G_F(2, 0),
     WJ_R4 = B2G_F(0, 0),
-    WJ_CHUNKS = 3
+    WJ_M0 = B2G_F(1, 0),
+    WJ_CHUNKS = 2
 };
 enum ContactState {
     SC_FIX = B2G_F(0, 0),       // fixtureA | fixtureB << 8

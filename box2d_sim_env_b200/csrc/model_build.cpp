@@ -607,6 +607,13 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
         w[MJ_RA0X] = fbits(jt.lax - A.lcx); w[MJ_RA0Y] = fbits(jt.lay - A.lcy);
         w[MJ_RB0X] = fbits(jt.lbx - Bd.lcx); w[MJ_RB0Y] = fbits(jt.lby - Bd.lcy);
         w[MJ_MA] = fbits(A.invMass); w[MJ_IA] = fbits(A.invI); w[MJ_MB] = fbits(Bd.invMass); w[MJ_IB] = fbits(Bd.invI);
+        {   // b2FrictionJoint::m_angularMass / b2RevoluteJoint::m_motorMass: constant for the joint
+            float m = A.invI + Bd.invI;
+            if (m > 0.0f) m = 1.0f / m;
+            w[MJ_ROTMASS] = fbits(m);
+        }
+        // the compact friction-joint layout (model.h) relies on what Box2DLink's ctor always builds: ground -> link
+        if (jt.type == 0 && A.type != 0) throw std::runtime_error("friction joints must hang off the static ground body");
     }
     // links / chains / object joints / name order / init
     h.oLink = allocWords(0);

@@ -398,11 +398,14 @@ def test_region_query_and_feasibility(b2g):
     assert_same(batch, worlds, "after isPhysicallyFeasible (runs UpdateContacts)")
 
 
-@pytest.mark.parametrize("env_name,n", [(ENV_A, 20000), (ENV_B, 12345)])
-def test_large_batch_full_warp_path(b2g, env_name, n):
-    """Batches large enough for the full-warp, CTA-synchronised stepping kernel (phase barriers, padding worlds in the
-    last CTA; small batches use the narrow-warp kernel): final states of a 60-step rollout, all worlds, bit-exact."""
+@pytest.mark.parametrize("env_name,n,step_block", [(ENV_A, 20000, None), (ENV_B, 12345, None), (ENV_A, 19999, 224), (ENV_B, 20001, 96)])
+def test_large_batch_full_warp_path(b2g, env_name, n, step_block, monkeypatch):
+    """Batches large enough for the full-warp, CTA-synchronised stepping kernel (phase barriers, parked padding worlds in
+    the last CTA; small batches use the narrow-warp kernel), with the CTA size of the heuristic and with explicit
+    non-power-of-two CTA sizes: final states of a 60-step rollout, all worlds, bit-exact."""
     from oracle import b2o
+    if step_block:
+        monkeypatch.setenv("B2G_STEP_BLOCK", str(step_block))
     batch = make_batch(b2g, env_name, n)
     nd = batch.model.objects[0]["n_dofs"]
     q, qd = random_states(batch.model, n, seed=97, spread=0.6)
@@ -483,6 +486,12 @@ def test_select_worlds(b2g):
     after = batch.bodies()
     same = [np.array_equal(before[w], after[w]) for w in range(n)]
     assert all(same[:33]) and all(same[37:]) and not any(same[33:37])
+    # a fresh-cache set_state on a sub-range (broadcast of the loaded world + set_state) leaves the other worlds alone
+    batch.selectWorlds(5, 3)
+    batch.setWorldState(q[5:8], qd[5:8], reset_caches=True)
+    batch.selectWorlds()
+    again = batch.bodies()
+    assert all(np.array_equal(after[w], again[w]) for w in range(n) if not 5 <= w < 8)
     got_q, _ = batch.getWorldState()
     assert np.array_equal(got_q[33:37], np.concatenate([sq[:, :7], batch.getObjectPose("obj1")[33:37], sq[:, 10:]], 1))
     batch.stepPhysics(2)
