@@ -389,11 +389,17 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch from `ncu --set full` (profiles/), bytes per launch
+# dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch (k_step / k_step_narrow) from `ncu --set full`, bytes per
+# launch of the config's default world count (profiles/r1c_<config>_<worlds>_k_step_ncu_full.txt)
 MEASURED_TRAFFIC = {
-    # profiles/r1_final_k_step_cfg2_4096_ncu_full.txt: 5.03 MB read + 0.24 MB written; the 21 MB state of 4096 worlds
-    # stays L2-resident across the 100 steps of a launch, so DRAM sees far less than the algorithmic bytes
-    "cfg2": 5031680 + 240896,
+    # 4096 worlds: the 21 MB state stays L2-resident across the 100 steps of a launch, DRAM sees far less than the
+    # algorithmic bytes (5.82 MB read + 0.39 MB written)
+    "cfg2": 5821952 + 391424,
+    # 65536 rigid-robot worlds (4.9 KB state each, 320 MB): 31.8 MB read + 82.4 MB written -- also mostly L2 hits
+    "cfg3": 31752448 + 82375680,
+    # 65536 clutter worlds: the ~9 KB a step touches per world (590 MB for the batch) does not fit the 126 MB L2, every
+    # step streams it: 81.8 GB read + 49.1 GB written per 6.55 M world-steps = 20 KB per world-step (algorithmic: 5.0 KB)
+    "cfg4": 81779440000 + 49093333000,
 }
 
 
