@@ -48,7 +48,8 @@ ABI_SYMBOLS = [
     "b2g_batch_get_state", "b2g_batch_get_state_dev", "b2g_batch_set_object_pose", "b2g_batch_set_object_dofs", "b2g_batch_get_object_dofs", "b2g_batch_select_worlds", "b2g_batch_get_object_pose",
     "b2g_batch_set_to_rest", "b2g_batch_at_rest", "b2g_batch_set_link_enabled", "b2g_batch_objects_in_aabb",
     "b2g_batch_is_physically_feasible",
-    "b2g_batch_set_target_velocity", "b2g_batch_set_target_velocity_dev", "b2g_batch_step", "b2g_batch_step_record",
+    "b2g_batch_set_target_velocity", "b2g_batch_set_target_velocity_dev", "b2g_batch_set_control_efforts",
+    "b2g_batch_set_control_efforts_dev", "b2g_batch_step", "b2g_batch_step_record",
     "b2g_batch_step_guarded", "b2g_batch_rollout_dev",
     "b2g_batch_get_bodies", "b2g_batch_get_fat_aabbs", "b2g_batch_get_joints", "b2g_batch_get_contacts",
     "b2g_batch_check_collision", "b2g_batch_check_collision_dev", "b2g_batch_save_state", "b2g_batch_restore_state", "b2g_batch_drop_state",
@@ -119,6 +120,8 @@ def lib():
     L.b2g_batch_is_physically_feasible.argtypes = [vp, ip]
     L.b2g_batch_set_target_velocity.argtypes = [vp, C.c_int, fp]
     L.b2g_batch_set_target_velocity_dev.argtypes = [vp, C.c_int, fp]
+    L.b2g_batch_set_control_efforts.argtypes = [vp, C.c_int, fp]
+    L.b2g_batch_set_control_efforts_dev.argtypes = [vp, C.c_int, fp]
     L.b2g_batch_step.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.b2g_batch_rollout_dev.argtypes = [vp, C.c_int, fp, C.c_int, C.c_int]
     L.b2g_batch_step_record.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, ip, fp, C.c_int]
@@ -497,6 +500,14 @@ class BatchBox2DWorld:
             raise B2GError(1, "[sim_env::Box2DRobotVelocityController::setTargetVelocity]"
                               "Provided target velocity has invalid dimension.")
         _check(lib().b2g_batch_set_target_velocity(self.h, robot, _ptr(v)))
+
+    def setControlEfforts(self, robot, efforts):
+        """Box2DRobot::setController (:2312-2317) with a callback that returns `efforts` ([n_worlds, n_dofs]) on every step:
+        they go to commandEfforts (:2319-2379).  The hook for user control laws."""
+        robot = self.model.object_index(robot) if isinstance(robot, str) else robot
+        nd = self.model.objects[robot]["n_dofs"]
+        e = _f32(np.broadcast_to(_f32(efforts), (self._rows(), nd)))
+        _check(lib().b2g_batch_set_control_efforts(self.h, robot, _ptr(e)))
 
     # -- collision (:3846-3859 through Box2DCollisionChecker::updateContactCache :2880-2911)
     def checkCollision(self, max_per_world=32):

@@ -605,6 +605,28 @@ b2g_status b2g_batch_set_target_velocity(b2g_batch* b, int object, const float* 
     return B2G_OK;
 }
 
+b2g_status b2g_batch_set_control_efforts_dev(b2g_batch* b, int object, const float* efforts) {
+    b2g_status s = checkRobot(b, object);
+    if (s) return s;
+    if (!efforts) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    CU(launchSetEfforts(b->L(), object, efforts));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_set_control_efforts(b2g_batch* b, int object, const float* efforts) {
+    b2g_status s = checkRobot(b, object);
+    if (s) return s;
+    if (!efforts) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    size_t bytes = (size_t)b->n() * b->m.objects[object].nDofs * 4;
+    CU(b->stageA.reserve(bytes));
+    CU(cudaMemcpyAsync(b->stageA.p, efforts, bytes, cudaMemcpyHostToDevice, b->stream));
+    CU(launchSetEfforts(b->L(), object, (const float*)b->stageA.p));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
 static b2g_status timedStep(b2g_batch* b, int object, const float* targets, int nTargets, int stepsPerTarget, int execCtrl,
                             int allowSleep) {
     cudaEvent_t e0 = getEvent(b), e1 = getEvent(b);

@@ -169,7 +169,19 @@ DEV void setTarget(const Ctx& c, int object, const float* v) {
     int slot = 0;
     for (int r = 0; r < H().nrobots; ++r)
         if (mI(c, H().oRobotOrder + r) == object) slot = r;
-    stI(c, sslot(c, SS_TARGET_AVAIL), ldI(c, sslot(c, SS_TARGET_AVAIL)) | (1 << slot));
+    stI(c, sslot(c, SS_TARGET_AVAIL), (ldI(c, sslot(c, SS_TARGET_AVAIL)) | (1 << slot)) & ~(1 << (16 + slot)));
+}
+
+// Box2DRobot::setController (:2312-2317) with a callback that returns the given efforts on every control(dt) call
+// (:2284-2310): they go straight to commandEfforts (:2319-2379).  Shares the target slots with the velocity controller.
+DEV void setEfforts(const Ctx& c, int object, const float* e) {
+    int n = mI(c, mobj(c, object, MO_NDOFS));
+    int tOff = mI(c, mobj(c, object, MO_TARGET_OFFSET));
+    for (int i = 0; i < n; ++i) stF(c, tslot(c, tOff + i), e[i]);
+    int slot = 0;
+    for (int r = 0; r < H().nrobots; ++r)
+        if (mI(c, H().oRobotOrder + r) == object) slot = r;
+    stI(c, sslot(c, SS_TARGET_AVAIL), ldI(c, sslot(c, SS_TARGET_AVAIL)) | (1 << slot) | (1 << (16 + slot)));
 }
 
 __global__ void k_set_target(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
@@ -179,6 +191,15 @@ __global__ void k_set_target(const __grid_constant__ ModelHeader hdr, const uint
     float lv[kMaxDofsPerObject];
     for (int i = 0; i < n; ++i) lv[i] = v[w * n + i];
     setTarget(c, object, lv);
+}
+
+__global__ void k_set_efforts(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
+                              StepParams prm, int object, const float* __restrict__ v) {
+    B2G_PROLOGUE();
+    int n = mI(c, mobj(c, object, MO_NDOFS));
+    float lv[kMaxDofsPerObject];
+    for (int i = 0; i < n; ++i) lv[i] = v[w * n + i];
+    setEfforts(c, object, lv);
 }
 
 // stepPhysics / rollout: nTargets segments of stepsPerTarget steps; targets == nullptr keeps the stored target
@@ -516,6 +537,7 @@ cudaError_t launchSetObjectDofs(const Launch& L, int object, const DofSel& sel, 
 cudaError_t launchGetObjectDofs(const Launch& L, int object, const DofSel& sel, float* out, int velocities) {
     LAUNCH(k_get_object_dofs, object, sel, out, velocities);
 }
+cudaError_t launchSetEfforts(const Launch& L, int object, const float* v) { LAUNCH(k_set_efforts, object, v); }
 cudaError_t launchSetTarget(const Launch& L, int object, const float* v) { LAUNCH(k_set_target, object, v); }
 cudaError_t launchStep(const Launch& L, int object, const float* targets, int nTargets, int stepsPerTarget, int execCtrl,
                        int allowSleep) {

@@ -35,6 +35,7 @@ cudaError_t launchSetPose(const Launch& L, int object, const float* pose);
 cudaError_t launchGetPose(const Launch& L, int object, float* pose);
 cudaError_t launchSetObjectDofs(const Launch& L, int object, const DofSel& sel, const float* values, int velocities);
 cudaError_t launchGetObjectDofs(const Launch& L, int object, const DofSel& sel, float* out, int velocities);
+cudaError_t launchSetEfforts(const Launch& L, int object, const float* v);
 cudaError_t launchSetTarget(const Launch& L, int object, const float* v);
 cudaError_t launchStep(const Launch& L, int object, const float* targets, int nTargets, int stepsPerTarget, int execCtrl,
                        int allowSleep);

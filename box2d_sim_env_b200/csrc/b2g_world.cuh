@@ -316,7 +316,10 @@ DEVN void initWorld(Ctx c) {
 // Box2DRobot::control (:2284-2310) = Box2DRobotVelocityController::control (Box2DController.cpp:65-117)
 // followed by Box2DRobot::commandEfforts (:2319-2379) and Box2DJoint::setControlTorque (:1198-1222).
 DEVN void robotControl(Ctx c, int o, int robotSlot) {
-    if (((ldI(c, sslot(c, SS_TARGET_AVAIL)) >> robotSlot) & 1) == 0) return;  // "No target available."
+    const int avail = ldI(c, sslot(c, SS_TARGET_AVAIL));
+    if (((avail >> robotSlot) & 1) == 0) return;  // "No target available."
+    // bit 16 + slot: the robot's controller is a ControlCallback that returns fixed efforts (b2g_batch_set_control_efforts)
+    const bool effortMode = ((avail >> (16 + robotSlot)) & 1) != 0;
     int n = mI(c, mobj(c, o, MO_NDOFS));
     int isStatic = mI(c, mobj(c, o, MO_STATIC));
     int baseDofs = isStatic ? 0 : 3;
@@ -327,6 +330,10 @@ DEVN void robotControl(Ctx c, int o, int robotSlot) {
     float inv = H().invScale, s = H().scale;
     int baseBody = mI(c, mobj(c, o, MO_BASE_BODY));
     for (int i = 0; i < n; ++i) {
+        if (effortMode) {
+            effort[i] = ldF(c, tslot(c, tOff + i));
+            continue;
+        }
         float massInertia;
         if (i < baseDofs) {
             if (i < 2) {

@@ -177,6 +177,13 @@ b2g_status b2g_batch_set_link_enabled(b2g_batch* batch, int body, const uint8_t*
  * in-kernel before every step (Box2DRobot::control, Box2DWorld.cpp:2284-2310). */
 b2g_status b2g_batch_set_target_velocity(b2g_batch* batch, int object, const float* v);
 b2g_status b2g_batch_set_target_velocity_dev(b2g_batch* batch, int object, const float* v);
+/* Box2DRobot::setController (Box2DWorld.cpp:2312-2317) with a ControlCallback that returns these efforts on every
+ * control(dt) call (:2284-2310): each step they go to Box2DRobot::commandEfforts (:2319-2379) -- force on the base
+ * centre (x scale), torque (x scale^2), joint motors through Box2DJoint::setControlTorque (:1198-1222).  This is the
+ * hook for user control laws: compute efforts outside, install them, step.  efforts: [n_worlds][n_dofs of the robot].
+ * Replaces the robot's velocity-controller target until b2g_batch_set_target_velocity is called again. */
+b2g_status b2g_batch_set_control_efforts(b2g_batch* batch, int object, const float* efforts);
+b2g_status b2g_batch_set_control_efforts_dev(b2g_batch* batch, int object, const float* efforts);
 
 /* Box2DWorld::stepPhysics(steps, execute_controllers, allow_sleeping) (:3266-3283). */
 b2g_status b2g_batch_step(b2g_batch* batch, int steps, int execute_controllers, int allow_sleeping);

@@ -296,6 +296,12 @@ public:
         check(b2g_batch_set_target_velocity(_batch, objectIndex(robot), v));
     }
 
+    // Box2DRobot::setController (:2312-2317) with a ControlCallback that returns these efforts on every step (they reach
+    // Box2DRobot::commandEfforts :2319-2379): the hook for user control laws; efforts: [n_worlds][n_dofs of the robot]
+    void setControlEfforts(const std::string& robot, const float* efforts) {
+        check(b2g_batch_set_control_efforts(_batch, objectIndex(robot), efforts));
+    }
+
     // checkCollision(std::vector<Contact>&) (:3846-3859 -> updateContactCache :2880-2911) for every world
     void checkCollision(std::vector<Contact>& contacts, std::vector<int64_t>& offsets, int max_per_world = 32) {
         std::vector<int32_t> counts(_n), io((size_t)_n * max_per_world * 4);

@@ -56,6 +56,7 @@ def lib():
         L.b2o_world_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2o_world_set_object_pose.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float]
         L.b2o_world_get_object_pose.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.b2o_world_set_control_efforts.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.b2o_world_set_target_velocity.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.b2o_world_object_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_char_p, C.c_int]
         for name in ("b2o_world_get_bodies", "b2o_world_get_body_model", "b2o_world_get_fat_aabbs"):
@@ -288,6 +289,12 @@ class OracleWorld:
     def set_target_velocity(self, obj, v):
         v = _f32(v)
         if lib().b2o_world_set_target_velocity(self.h, obj, _ptr(v), len(v)):
+            raise RuntimeError(lib().b2o_last_error().decode())
+
+    def set_control_efforts(self, obj, efforts):
+        """Install a controller that returns these efforts every step (Box2DRobot::setController + commandEfforts)."""
+        e = _f32(efforts)
+        if lib().b2o_world_set_control_efforts(self.h, obj, _ptr(e), len(e)):
             raise RuntimeError(lib().b2o_last_error().decode())
 
     def controller_efforts(self, obj):

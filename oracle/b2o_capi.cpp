@@ -203,9 +203,18 @@ int b2o_world_ball_approximation(void* wp, int objIdx, float* out) {
     return (int)v.size() / 4;
 }
 
+int b2o_world_set_control_efforts(void* wp, int objIdx, const float* e, int n) {
+    OObject* o = ((OWorld*)wp)->creationOrder.at(objIdx);
+    if (!o->isRobot || (size_t)n != o->activeDofs.size()) { g_err = "set_control_efforts: not a robot / wrong size"; return 1; }
+    o->controlEfforts.assign(e, e + n);
+    o->effortController = true;
+    return 0;
+}
+
 int b2o_world_set_target_velocity(void* wp, int objIdx, const float* v, int n) {
     OWorld* w = (OWorld*)wp;
     try {
+        w->creationOrder.at(objIdx)->effortController = false;
         w->creationOrder.at(objIdx)->setTargetVelocity(std::vector<float>(v, v + n));
         return 0;
     } catch (const std::exception& ex) { g_err = ex.what(); return 1; }

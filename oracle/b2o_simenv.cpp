@@ -369,6 +369,10 @@ bool OObject::controllerCompute(const std::vector<float>& velocities, float dt, 
 
 void OObject::control(float dt) {  // Box2DWorld.cpp:2284-2310
     if (!isRobot) return;
+    if (effortController) {  // callback success with these efforts
+        commandEfforts(controlEfforts);
+        return;
+    }
     std::vector<float> velocities = getDOFVelocities({});
     std::vector<float> efforts;
     if (controllerCompute(velocities, dt, efforts)) commandEfforts(efforts);

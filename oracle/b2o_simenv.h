@@ -129,6 +129,10 @@ struct OObject {
     // velocity controller state (Box2DRobotVelocityController)
     std::vector<float> targetVelocity;
     bool targetAvailable = false;
+    // a ControlCallback that returns fixed efforts (Box2DRobot::setController :2312-2317): control() hands them to
+    // commandEfforts every step
+    bool effortController = false;
+    std::vector<float> controlEfforts;
 
     unsigned numBaseDofs() const { return isStatic ? 0 : 3; }
     std::vector<int> allDofs() const;

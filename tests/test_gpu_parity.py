@@ -495,3 +495,30 @@ def test_select_worlds(b2g):
     got_q, _ = batch.getWorldState()
     assert np.array_equal(got_q[33:37], np.concatenate([sq[:, :7], batch.getObjectPose("obj1")[33:37], sq[:, 10:]], 1))
     batch.stepPhysics(2)
+
+
+def test_control_efforts_parity(b2g):
+    """Box2DRobot::setController with a callback returning fixed efforts -> commandEfforts (:2284-2379) on every step;
+    switching back to the velocity controller afterwards."""
+    n = 48
+    batch = make_batch(b2g, ENV_A, n)
+    worlds = oracle_worlds(load_env_dict(ENV_A), n)
+    q, qd = random_states(batch.model, n, seed=61, spread=0.7)
+    rng = np.random.default_rng(62)
+    eff = np.concatenate([rng.uniform(-3, 3, (n, 2)), rng.uniform(-0.5, 0.5, (n, 1)), rng.uniform(-0.05, 0.05, (n, 4))], 1).astype(np.float32)
+    eff[:, 4][::3] = 0.0     # tau == 0: negative motor speed, zero max torque (:1198-1222)
+    batch.setWorldState(q, qd, reset_caches=True)
+    batch.setControlEfforts(0, eff)
+    batch.stepPhysics(12)
+    tg = random_targets(batch.model, 0, n, seed=63)[0]
+    for w, ow in enumerate(worlds):
+        ow.set_state(q[w], qd[w])
+        ow.set_control_efforts(0, eff[w])
+        ow.step(12)
+    assert_same(batch, worlds, "fixed control efforts, 12 steps")
+    batch.setTargetVelocity(0, tg)
+    batch.stepPhysics(8)
+    for w, ow in enumerate(worlds):
+        ow.set_target_velocity(0, tg[w])
+        ow.step(8)
+    assert_same(batch, worlds, "back to the velocity controller")
