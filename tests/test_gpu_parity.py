@@ -18,7 +18,7 @@ def make_batch(b2g, env_name, n, max_contacts=0):
 
 def assert_same(batch, worlds, what, atol=0.0):
     bodies = batch.bodies()
-    contacts = batch.contacts()
+    contacts = batch.contacts(max_per_world=128)
     fat = batch.fat_aabbs()
     jio, jfo = batch.joints()
     bad = []
@@ -242,6 +242,44 @@ def test_clutter_shape_c_parity(b2g):
     for w, ow in enumerate(worlds):
         oio, ofo = ow.check_collision()
         assert counts[w] == len(oio) and np.array_equal(io[w, :len(oio)], oio) and np.array_equal(fo[w, :len(oio)], ofo)
+
+
+def test_maximum_size_world_parity(b2g):
+    """A world at the capacity limit (63 bodies, 64 proxies, 66 joints: robot + 57 clutter objects), narrow-warp and
+    full-warp kernels: bit-exact vs the oracle over a contact-rich rollout."""
+    from box2d_sim_env_b200 import envgen
+    env = envgen.clutter_env(n_objects=57)
+    model = b2g.Model(env)
+    assert model.n_fixtures == 64
+    n = 12
+    batch = b2g.BatchBox2DWorld(n, max_contacts=128).loadWorld(model)
+    worlds = oracle_worlds(env, n)
+    # robot at the origin, objects on a 0.4 m grid around it (none closer than 0.7 m), sliding fast at random
+    rng = np.random.default_rng(9)
+    cells = [(x, y) for x in np.arange(-1.8, 1.81, 0.4) for y in np.arange(-1.8, 1.81, 0.4) if x * x + y * y > 0.7 ** 2][:57]
+    assert len(cells) == 57
+    q = np.zeros((n, model.nq), np.float32)
+    qd = np.zeros_like(q)
+    for k, (x, y) in enumerate(cells):
+        q[:, 7 + 3 * k] = x + rng.uniform(-0.05, 0.05, n)
+        q[:, 8 + 3 * k] = y + rng.uniform(-0.05, 0.05, n)
+        q[:, 9 + 3 * k] = rng.uniform(-3, 3, n)
+        qd[:, 7 + 3 * k:9 + 3 * k] = rng.uniform(-3, 3, (n, 2))
+        qd[:, 9 + 3 * k] = rng.uniform(-3, 3, n)
+    tg = random_targets(model, 0, n, seed=10, segments=3)
+    batch.setWorldState(q, qd, reset_caches=True)
+    for w, ow in enumerate(worlds):
+        ow.set_state(q[w], qd[w])
+    for seg in range(3):
+        batch.setTargetVelocity(0, tg[seg])
+        batch.stepPhysics(10)
+        for w, ow in enumerate(worlds):
+            ow.set_target_velocity(0, tg[seg][w])
+            ow.step(10)
+        assert_same(batch, worlds, "max-size world, segment %d" % seg)
+    assert np.all(batch.status() == 0)
+    counts, cio, _ = batch.contacts(max_per_world=128)
+    assert int(cio[..., 2].sum()) > 20
 
 
 @pytest.mark.parametrize("n", [1, 31, 33, 95])

@@ -94,6 +94,17 @@ def test_prismatic_is_rejected(b2g):
     assert e.value.code == 4
 
 
+def test_maximum_model_sizes(b2g):
+    """Capacity limits of a world (64 bodies / 64 broad-phase proxies, model.h): the largest model builds, one more object
+    fails loudly at model creation, never at step time."""
+    from box2d_sim_env_b200 import envgen
+    m = b2g.Model(envgen.clutter_env(n_objects=57))       # ground + 5 robot links + 57 = 63 bodies, 1 + 6 + 57 = 64 proxies
+    assert (m.n_bodies, m.n_fixtures) == (63, 64)
+    with pytest.raises(b2g.B2GError) as e:
+        b2g.Model(envgen.clutter_env(n_objects=58))
+    assert "too many" in str(e.value)
+
+
 def test_kinematic_structure_is_validated(b2g):
     env = load_env_dict(ENV_A)
     env["robots"][0]["joints"][0]["link_b"] = "nonexistent"
