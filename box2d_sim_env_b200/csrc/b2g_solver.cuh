@@ -356,8 +356,11 @@ DEVN void frictionIslandSolve(Ctx c, int j, float dtRatio, int velIters) {
     }
     // a static bodyA is written back unchanged by the reference (x -= 0 * impulse); here it stays the constant +0
     A = zeroVel();
-    // ---- velocity iterations
+    // ---- velocity iterations.  One iteration maps (B.v, B.w, accumulated impulses) to new values and reads nothing else
+    // that changes, so once an iteration returns its input bit for bit every later one does too: stop there.  A free body
+    // on its friction joint gets there in a few iterations (impulses saturate or the velocity reaches zero).
     for (int it = 0; it < velIters; ++it) {
+        const float pvx = B.v.x, pvy = B.v.y, pw = B.w, pax = acc4.x, pay = acc4.y, paz = acc4.z;
         {
             float Cdot = B.w - A.w;
             float impulse = -acc4.w * Cdot;
@@ -384,6 +387,10 @@ DEVN void frictionIslandSolve(Ctx c, int j, float dtRatio, int velIters) {
             B.v = B.v + mB * impulse;
             B.w += iB * cross(rB, impulse);
         }
+        const int diff = (__float_as_int(B.v.x) ^ __float_as_int(pvx)) | (__float_as_int(B.v.y) ^ __float_as_int(pvy)) |
+                         (__float_as_int(B.w) ^ __float_as_int(pw)) | (__float_as_int(acc4.x) ^ __float_as_int(pax)) |
+                         (__float_as_int(acc4.y) ^ __float_as_int(pay)) | (__float_as_int(acc4.z) ^ __float_as_int(paz));
+        if (diff == 0) break;
     }
     st4(c, js + SJ_IMPULSE4, acc4);
     stVelAt(c, off.w, B);
