@@ -12,6 +12,47 @@ def load_env_dict(name):
     return b2o.load_env_yaml(b2g.data_path(name))
 
 
+ENV_2 = "variant:env2"   # the reference's test_data/test_env2.yaml: base-only robot, obj2 (two hinged bars) DYNAMIC
+ENV_3 = "variant:env3"   # the reference's test_data/test_env3.yaml: one-link frictionless fingers, obj2 dynamic
+
+
+def env_variant(name):
+    """The reference ships two more environments (test_data/test_env2.yaml + robots/test_robot2.yaml, test_env3.yaml +
+    robots/test_robot3.yaml).  They are the shipped shape-A files with parts removed / parameters changed, so they are
+    rebuilt here from this repo's shape-A description; tests/test_host.py checks the result against the reference's own
+    files where /root/reference exists."""
+    env = load_env_dict(ENV_A)
+    robot = env["robots"][0]
+    ba = robot["base_actuation"]
+    ba["translational_velocity_limits"] = [-10.0, 10.0]
+    ba["rotational_velocity_limits"] = [-3.14, 3.14]
+    if name == ENV_2:
+        ba["translational_acceleration_limits"] = [-1.8, 1.8]
+        robot["links"] = robot["links"][:1]
+        robot["links"][0]["ground_torque_integral"] = 0.0
+        robot["joints"] = []
+        ndof = 3
+    elif name == ENV_3:
+        keep = ("test_robot_base", "test_robot_finger_l_1", "test_robot_finger_r_1")
+        robot["links"] = [l for l in robot["links"] if l["name"] in keep]
+        for l in robot["links"][1:]:
+            l["ground_friction"] = 0.0
+            l["ground_torque_integral"] = 0.0
+        robot["joints"] = [j for j in robot["joints"] if j["name"] in ("finger_l_joint_1", "finger_r_joint_1")]
+        ndof = 5
+    else:
+        raise KeyError(name)
+    env["world_bounds"] = [0.0, 0.0, 0.0, 0.0]          # no world_bounds key: defaults (Box2DIOUtils.cpp:79-84)
+    env["objects"][1]["static"] = False                  # obj2 dynamic: 3 base DOFs + its hinge
+    env["states"]["my_robot"] = dict(configuration=[0.0] * ndof, velocity=[0.0] * ndof)
+    env["states"]["obj2"] = dict(configuration=[2.9, 1.2, -6.12, 0.0], velocity=[0.0, 0.0, 0.0, -0.5])
+    return env
+
+
+def env_dict(name):
+    return env_variant(name) if name.startswith("variant:") else load_env_dict(name)
+
+
 def random_states(model, n, seed, spread=1.2, vel=1.0):
     """Random world states inside the DOF limits: objects scattered around the origin so contacts happen."""
     rng = np.random.default_rng(seed)

@@ -7,7 +7,7 @@ import re
 import numpy as np
 import pytest
 
-from parity_utils import ENV_A, ENV_B, load_env_dict
+from parity_utils import ENV_2, ENV_3, ENV_A, ENV_B, env_variant, load_env_dict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -38,6 +38,32 @@ def test_model_matches_oracle_builder(b2g, oracle, env_name):
     assert np.array_equal(jf[:, 6:], ojf[:, 6:])
     assert [o["name"] for o in m.objects] == [o["name"] for o in w.objects]
     assert [o["n_dofs"] for o in m.objects] == [o["n_dofs"] for o in w.objects]
+
+
+@pytest.mark.parametrize("variant,ref_file", [(ENV_2, "test_env2.yaml"), (ENV_3, "test_env3.yaml")])
+def test_reference_env2_env3(b2g, oracle, variant, ref_file):
+    """The reference's other two environments (dynamic hinged obj2, frictionless fingers, no world_bounds key): the variants
+    the parity tests use build the same model as the reference's own files read by the product's C++ loader (stale
+    trans_friction / rot_friction keys, ignored max_torque key) and by the oracle's PyYAML loader."""
+    env = env_variant(variant)
+    m = b2g.Model(env)
+    w = oracle.OracleWorld(env)
+    assert np.array_equal(m.body_model(), w.body_model())
+    assert np.array_equal(m.fixture_model()[1], w.fixture_model()[1])
+    assert [(o["name"], o["n_dofs"], o["is_static"]) for o in m.objects][1:] == [("obj1", 3, False), ("obj2", 4, False)]
+    ref = os.path.join("/root/reference/test_data", ref_file)
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not present on this machine")
+    r = b2g.Model(ref)                                    # product loader on the reference's own file
+    assert (r.n_bodies, r.n_fixtures, r.n_joints, r.nq) == (m.n_bodies, m.n_fixtures, m.n_joints, m.nq)
+    assert np.array_equal(r.body_model(), m.body_model())
+    assert np.array_equal(r.fixture_model()[1], m.fixture_model()[1])
+    assert np.array_equal(r.joint_model()[0], m.joint_model()[0]) and np.array_equal(r.joint_model()[1], m.joint_model()[1])
+    assert np.array_equal(r.dof_limits(), m.dof_limits())
+    ow = oracle.OracleWorld(oracle.load_env_yaml(ref))    # oracle loader on the reference's own file
+    q0, qd0 = ow.get_state()
+    q1, qd1 = w.get_state()
+    assert np.array_equal(q0, q1) and np.array_equal(qd0, qd1)
 
 
 def test_programmatic_env_equals_yaml(b2g):

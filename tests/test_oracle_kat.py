@@ -209,3 +209,20 @@ def test_feasibility_known_answers(oracle):
     assert not w.is_physically_feasible()
     w.set_object_pose(1, 3.0, -3.0, 0.0)     # far away again
     assert w.is_physically_feasible()
+
+
+# configurations / velocities the reference's own test hands to the sim_env suite (tests/test_Box2DWorld.cpp:11-20, 46-51,
+# 67-72): a set followed by a get has to return them
+REF_OBJECT = (1, [1.0, 2.0, 3.0], [0.0, 1.0, 0.2])
+REF_ROBOT = (0, [0.0, 6.0, 2.0, 0.1, 0.1, 0.1, 0.1], [0.0, 1.0, 0.2, 0.1, 0.2, 0.0, 0.1])
+
+
+@pytest.mark.parametrize("obj,conf,vel", [REF_OBJECT, REF_ROBOT])
+def test_reference_test_configurations_round_trip(oracle, obj, conf, vel):
+    w = oracle.OracleWorld(load_env_dict(ENV_A))
+    w.set_object_dofs(obj, conf)
+    w.set_object_dofs(obj, vel, velocities=True)
+    assert w.get_object_dofs(obj).tolist() == pytest.approx(conf, abs=2e-6)
+    assert w.get_object_dofs(obj, velocities=True).tolist() == pytest.approx(vel, abs=2e-6)
+    pose = w.get_object_pose(obj)
+    assert pose.tolist() == pytest.approx(conf[:3], abs=2e-6)
