@@ -9,8 +9,9 @@ With --gpus N every rank owns its own batch (weak scaling; cfg5: a slice of the 
 final [n, 2, nq] states are all-gathered over NCCL, which is the only collective the path has.
 
     value     device-timed throughput with inputs resident in HBM (CUDA events on the batch's stream)
-    e2e       same metric through the host-pointer path: pinned host buffers, H2D of the step's inputs and D2H of
-              its results inside the timed region
+    e2e       same metric through the host-pointer C-ABI call a planner makes (b2g_batch_rollout: pinned host buffers in,
+              pinned host buffers out; H2D of the step's inputs and D2H of its results inside the timed region; with
+              --gpus N > 1 the device path plus explicit copies, because the NCCL gather needs the states on the device)
     roofline  algorithmic bytes of the rollout kernel / its CUDA-event duration, against the measured HBM peak
     cpu_baseline   the CPU oracle ("port" of the reference's arithmetic; the reference itself cannot be built
               here) on the box's host cores, one world per thread, bounded sample
@@ -261,6 +262,8 @@ def run_ours(args):
     h_qd = torch.empty_like(h_q).pin_memory()
     h_tg = torch.empty((N_TARGETS, n, nd), dtype=torch.float32).pin_memory()
     h_out = torch.empty((n, 2, nq), dtype=torch.float32).pin_memory()
+    h_oq = torch.empty((n, nq), dtype=torch.float32).pin_memory()
+    h_oqd = torch.empty((n, nq), dtype=torch.float32).pin_memory()
     d_oq = torch.empty((n, nq), dtype=torch.float32, device=dev)
     d_oqd = torch.empty_like(d_oq)
 
@@ -306,15 +309,21 @@ def run_ours(args):
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            if e2e:
-                with torch.cuda.stream(stream):
-                    d_q.copy_(h_q, non_blocking=True)
-                    d_qd.copy_(h_qd, non_blocking=True)
-                    d_tg.copy_(h_tg, non_blocking=True)
-            rollout_device()
-            if e2e:
-                with torch.cuda.stream(stream):
-                    h_out.copy_(d_out, non_blocking=True)
+            if e2e and world == 1:
+                # the call a planner makes: ONE host-pointer C-ABI call (b2g_batch_rollout) on pinned host buffers --
+                # H2D of states and targets, fresh-clone set_state, the rollout kernel, get_state, D2H of the results
+                batch.rollout_host(0, h_q.data_ptr(), h_qd.data_ptr(), h_tg.data_ptr(), N_TARGETS, STEPS_PER_TARGET,
+                                   h_oq.data_ptr(), h_oqd.data_ptr())
+            else:
+                if e2e:
+                    with torch.cuda.stream(stream):
+                        d_q.copy_(h_q, non_blocking=True)
+                        d_qd.copy_(h_qd, non_blocking=True)
+                        d_tg.copy_(h_tg, non_blocking=True)
+                rollout_device()
+                if e2e:
+                    with torch.cuda.stream(stream):
+                        h_out.copy_(d_out, non_blocking=True)
             e1.record(stream)
             barrier()
             total_ms += e0.elapsed_time(e1)

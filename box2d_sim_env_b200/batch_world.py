@@ -50,7 +50,7 @@ ABI_SYMBOLS = [
     "b2g_batch_is_physically_feasible",
     "b2g_batch_set_target_velocity", "b2g_batch_set_target_velocity_dev", "b2g_batch_set_control_efforts",
     "b2g_batch_set_control_efforts_dev", "b2g_batch_step", "b2g_batch_step_record",
-    "b2g_batch_step_guarded", "b2g_batch_rollout_dev",
+    "b2g_batch_step_guarded", "b2g_batch_rollout_dev", "b2g_batch_rollout",
     "b2g_batch_get_bodies", "b2g_batch_get_fat_aabbs", "b2g_batch_get_joints", "b2g_batch_get_contacts",
     "b2g_batch_check_collision", "b2g_batch_check_collision_dev", "b2g_batch_save_state", "b2g_batch_restore_state", "b2g_batch_drop_state",
     "b2g_host_alloc", "b2g_host_free", "b2g_launch_count", "b2g_batch_take_kernel_ms",
@@ -124,6 +124,7 @@ def lib():
     L.b2g_batch_set_control_efforts_dev.argtypes = [vp, C.c_int, fp]
     L.b2g_batch_step.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.b2g_batch_rollout_dev.argtypes = [vp, C.c_int, fp, C.c_int, C.c_int]
+    L.b2g_batch_rollout.argtypes = [vp, C.c_int, fp, fp, C.c_int, fp, C.c_int, C.c_int, fp, fp]
     L.b2g_batch_step_record.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, ip, fp, C.c_int]
     L.b2g_batch_step_guarded.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, ip, ip]
     L.b2g_batch_get_bodies.argtypes = [vp, fp]
@@ -558,6 +559,30 @@ class BatchBox2DWorld:
 
     def get_state_dev(self, q_ptr, qd_ptr):
         _check(lib().b2g_batch_get_state_dev(self.h, C.c_void_p(q_ptr), C.c_void_p(qd_ptr)))
+
+    def rollout(self, robot, targets, steps_per_target, q=None, qd=None, reset_caches=True, q_out=None, qd_out=None):
+        """Planner "propagate" as one host-pointer call: optional setWorldState(q, qd), then for every targets[t]
+        ([n_targets, n_worlds, n_dofs]) setTargetVelocity + stepPhysics(steps_per_target), then getWorldState."""
+        robot = self.model.object_index(robot) if isinstance(robot, str) else robot
+        tg = _f32(targets)
+        nd = self.model.objects[robot]["n_dofs"]
+        if tg.ndim != 3 or tg.shape[1:] != (self.n_worlds, nd):
+            raise B2GError(1, "targets must be [n_targets][n_worlds][n_dofs]")
+        if q is not None:
+            q, qd = _f32(q), _f32(qd)
+            if q.shape != (self.n_worlds, self.nq) or qd.shape != q.shape:
+                raise B2GError(1, "state arrays must be [n_worlds][nq]")
+        q_out = np.empty((self.n_worlds, self.nq), np.float32) if q_out is None else q_out
+        qd_out = np.empty((self.n_worlds, self.nq), np.float32) if qd_out is None else qd_out
+        _check(lib().b2g_batch_rollout(self.h, robot, _ptr(q), _ptr(qd), int(reset_caches), _ptr(tg), tg.shape[0],
+                                       int(steps_per_target), _ptr(q_out), _ptr(qd_out)))
+        return q_out, qd_out
+
+    def rollout_host(self, robot, q_ptr, qd_ptr, targets_ptr, n_targets, steps_per_target, q_out_ptr, qd_out_ptr, reset_caches=True):
+        """b2g_batch_rollout on raw host addresses (pinned buffers of the caller)."""
+        robot = self.model.object_index(robot) if isinstance(robot, str) else robot
+        _check(lib().b2g_batch_rollout(self.h, robot, C.c_void_p(q_ptr), C.c_void_p(qd_ptr), int(reset_caches), C.c_void_p(targets_ptr),
+                                       int(n_targets), int(steps_per_target), C.c_void_p(q_out_ptr), C.c_void_p(qd_out_ptr)))
 
     def rollout_dev(self, robot, targets_ptr, n_targets, steps_per_target):
         robot = self.model.object_index(robot) if isinstance(robot, str) else robot

@@ -658,6 +658,37 @@ b2g_status b2g_batch_rollout_dev(b2g_batch* b, int object, const float* targets,
     return timedStep(b, object, targets, n_targets, steps_per_target, 1, 1);
 }
 
+b2g_status b2g_batch_rollout(b2g_batch* b, int object, const float* q, const float* qd, int reset_caches, const float* targets,
+                             int n_targets, int steps_per_target, float* q_out, float* qd_out) {
+    b2g_status s = checkRobot(b, object);
+    if (s) return s;
+    if (!targets || n_targets < 0 || steps_per_target < 0 || !q_out || !qd_out || (q == nullptr) != (qd == nullptr))
+        return fail(B2G_ERR_INVALID, "bad rollout arguments");
+    if (!b->allSelected()) return fail(B2G_ERR_INVALID, "stepping and the state stack act on the whole batch: call b2g_batch_select_worlds(batch, 0, 0) first");
+    CU(cudaSetDevice(b->device));
+    const size_t sb = (size_t)b->N * b->m.h.nq * 4;
+    const size_t tb = (size_t)n_targets * b->N * b->m.objects[object].nDofs * 4;
+    CU(b->stageA.reserve(sb));
+    CU(b->stageB.reserve(sb));
+    CU(b->stageC.reserve(tb > 0 ? tb : 4));
+    if (q) {
+        CU(cudaMemcpyAsync(b->stageA.p, q, sb, cudaMemcpyHostToDevice, b->stream));
+        CU(cudaMemcpyAsync(b->stageB.p, qd, sb, cudaMemcpyHostToDevice, b->stream));
+        if (reset_caches) CU(launchBroadcast(b->L(), b->tmpl));
+        CU(launchSetState(b->L(), (const float*)b->stageA.p, (const float*)b->stageB.p));
+    }
+    if (n_targets > 0) {
+        CU(cudaMemcpyAsync(b->stageC.p, targets, tb, cudaMemcpyHostToDevice, b->stream));
+        s = timedStep(b, object, (const float*)b->stageC.p, n_targets, steps_per_target, 1, 1);
+        if (s) return s;
+    }
+    CU(launchGetState(b->L(), (float*)b->stageA.p, (float*)b->stageB.p));
+    CU(cudaMemcpyAsync(q_out, b->stageA.p, sb, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(qd_out, b->stageB.p, sb, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
 b2g_status b2g_batch_set_to_rest(b2g_batch* b) {
     if (!b) return fail(B2G_ERR_INVALID, "null batch");
     CU(cudaSetDevice(b->device));

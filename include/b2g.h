@@ -206,6 +206,13 @@ b2g_status b2g_batch_step_guarded(b2g_batch* batch, int steps, int execute_contr
  * targets[t]) on robot `object`, stepPhysics(steps_per_target).  targets: [n_targets][n_worlds][n_dofs]
  * on the device. One kernel launch. */
 b2g_status b2g_batch_rollout_dev(b2g_batch* batch, int object, const float* targets, int n_targets, int steps_per_target);
+/* The same propagate as ONE host-pointer call, the way a planner evaluates a batch of candidate controls: (optionally)
+ * setWorldState(q, qd) on every world -- fresh clones when reset_caches != 0; q == qd == NULL keeps the current state --,
+ * the n_targets x steps_per_target rollout, getWorldState into q_out / qd_out.  All buffers are host memory
+ * ([n_worlds][nq], targets [n_targets][n_worlds][n_dofs]); copies run on the batch's stream (asynchronously when the
+ * buffers are pinned, see b2g_host_alloc) and the call returns after one synchronisation. */
+b2g_status b2g_batch_rollout(b2g_batch* batch, int object, const float* q, const float* qd, int reset_caches, const float* targets,
+                             int n_targets, int steps_per_target, float* q_out, float* qd_out);
 
 /* Box2DObject::getBallApproximation (Box2DWorld.cpp:1754-1763, Box2DLink::updateBallApproximation :733-747) of one
  * object in every world: out[n_worlds][n_balls][4] = centre (world frame, user units) and radius, links in name order */

@@ -263,6 +263,13 @@ public:
         return ok;
     }
 
+    // planner "propagate" in one call: setWorldState(q, qd) (fresh clones), then for every targets[t] ([n_targets][n_worlds]
+    // [n_dofs]) setTargetVelocity + stepPhysics(steps_per_target), then getWorldState into q_out / qd_out
+    void propagate(const std::string& robot, const float* q, const float* qd, const float* targets, int n_targets,
+                   int steps_per_target, float* q_out, float* qd_out, bool reset_caches = true) {
+        check(b2g_batch_rollout(_batch, objectIndex(robot), q, qd, reset_caches, targets, n_targets, steps_per_target, q_out, qd_out));
+    }
+
     // getWorldState / setWorldState (:3462-3513); q, qd: [n_worlds][nq]
     void getWorldState(float* q, float* qd) { check(b2g_batch_get_state(_batch, q, qd)); }
     void setWorldState(const float* q, const float* qd, bool reset_caches = false) {

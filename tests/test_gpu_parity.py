@@ -583,3 +583,25 @@ def test_reference_test_configurations(b2g):
         for w, ow in enumerate(worlds):
             assert np.array_equal(gp[w], ow.get_object_dofs(obj)) and np.array_equal(gv[w], ow.get_object_dofs(obj, velocities=True))
     assert_same(batch, worlds, "reference test configurations")
+
+
+def test_one_call_rollout_matches_stepwise(b2g):
+    """b2g_batch_rollout (host buffers in / out, one call) == setWorldState + per-segment setTargetVelocity + stepPhysics +
+    getWorldState, bit for bit; q = None continues from the current state."""
+    n = 300
+    batch = make_batch(b2g, ENV_A, n)
+    other = make_batch(b2g, ENV_A, n)
+    q, qd = random_states(batch.model, n, seed=71, spread=0.6)
+    tg = random_targets(batch.model, 0, n, seed=72, segments=4)
+    oq, oqd = batch.rollout(0, tg[:2], 5, q, qd)
+    oq2, oqd2 = batch.rollout(0, tg[2:], 5)                       # continues
+    other.setWorldState(q, qd, reset_caches=True)
+    for seg in range(4):
+        other.setTargetVelocity(0, tg[seg])
+        other.stepPhysics(5)
+        if seg == 1:
+            mq, mqd = other.getWorldState()
+            assert np.array_equal(oq, mq) and np.array_equal(oqd, mqd)
+    mq, mqd = other.getWorldState()
+    assert np.array_equal(oq2, mq) and np.array_equal(oqd2, mqd)
+    assert np.array_equal(batch.bodies(), other.bodies())
