@@ -180,6 +180,43 @@ def cpu_oracle_throughput(cfg, limits, n_worlds, repeats, threads, seed0=9000):
     return n_worlds * ROLLOUT_STEPS, times
 
 
+def parity_gate(cfg, batch, limits, n, seed, threads, sample=1024):
+    """Correctness gate that accompanies the measurement: the first `sample` worlds of one bench step's
+    inputs go through the CUDA path and through the CPU oracle (here as the checker); compared after ONE step from the
+    identical fresh-cache state and after the whole 100-step rollout: DOF positions / velocities (max |diff|, worlds that
+    are bit-identical) and the touching-pair sets with their manifold point counts."""
+    from oracle import b2o
+    m = min(sample, n)
+    q, qd, tg = synth_inputs(limits, n, seed, cfg)
+    out = {"worlds": m, "physics_steps": ROLLOUT_STEPS}
+    env = b2o.OracleEnv(oracle_env(cfg))
+    for label, n_tg, spt in (("single_step", 1, 1), ("rollout", N_TARGETS, STEPS_PER_TARGET)):
+        ob = b2o.OracleBatch(env, m)   # freshly loaded worlds: the CUDA side starts from fresh clones (reset_caches) too
+        gq, gqd = batch.rollout(0, tg[:n_tg], spt, q, qd, reset_caches=True)
+        counts, cio, _ = batch.contacts(max_per_world=64)
+        oq, oqd = ob.rollout(q[:m], qd[:m], 0, np.ascontiguousarray(tg[:n_tg, :m]), spt, threads)
+        dq = np.abs(gq[:m].astype(np.float64) - oq)
+        dv = np.abs(gqd[:m].astype(np.float64) - oqd)
+        same = np.all(gq[:m] == oq, axis=1) & np.all(gqd[:m] == oqd, axis=1)
+        pairs_ok, touching = 0, 0
+        for w in range(m):
+            oio, _ = ob.world(w).contacts()
+            k = int(counts[w])
+            g = sorted((int(r[0]), int(r[1]), int(r[4])) for r in cio[w, :k] if r[2])      # fixtureA, fixtureB, pointCount
+            o = sorted((int(r[0]), int(r[1]), int(r[4])) for r in oio if r[2])
+            pairs_ok += int(g == o)
+            touching += len(o)
+        out[label] = {"max_abs_dq": float(dq.max()), "max_abs_dqd": float(dv.max()), "mean_abs_dq": float(dq.mean()),
+                      "bit_identical_worlds": int(same.sum()), "touching_pair_sets_identical": pairs_ok,
+                      "touching_contacts": touching}
+    # BASELINE.json: single-step state error <= 1e-5 and bit-exact contact-pair sets / manifold point counts; multi-step
+    # trajectories are reported with their divergence statistics (here they are bit-identical as well)
+    out["pass"] = bool(out["single_step"]["max_abs_dq"] <= 1e-5 and out["single_step"]["max_abs_dqd"] <= 1e-5 and
+                       out["single_step"]["touching_pair_sets_identical"] == m and
+                       out["rollout"]["touching_pair_sets_identical"] == m)
+    return out
+
+
 def workload_text(cfg, n):
     return cfg["text"] % n
 
@@ -393,6 +430,8 @@ def run_ours(args):
                                     "kind": "port",
                                     "sample": "%d worlds x %d steps x %d repeats of the same workload, one world per thread"
                                               % (nref, ROLLOUT_STEPS, len(timed))}
+            # correctness gate run with the measurement (outside every timed region; the oracle is the checker)
+            line["parity"] = parity_gate(cfg, batch, limits, n, 1234 + 100 + args.steps - 1, threads)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
