@@ -356,15 +356,17 @@ b2g_status b2g_batch_create(const b2g_model* model, int64_t n_worlds, int device
         b->stepBlock = (int)(32 * w);
     }
     if (b->stepBlock < 32 || b->stepBlock > kWorldPad || (b->stepBlock % 32)) b->stepBlock = 32;
-    // worlds per warp: a B200 has 148 x 4 warp schedulers; a batch with fewer than 592 full warps is spread over narrower
-    // warps (k_step_narrow) so that rare per-world events serialise fewer neighbours
+    // worlds per warp: a B200 has 148 x 4 warp schedulers; a batch with fewer than 592 x 16 worlds is spread over narrower
+    // warps (k_step_narrow), one warp per scheduler at most, so that rare per-world events serialise fewer neighbours
     const char* envLanes = getenv("B2G_LANES");
     if (envLanes) b->stepLanes = atoi(envLanes);
     else {
-        b->stepLanes = 1;
-        while (b->stepLanes < 32 && n_worlds > 592LL * b->stepLanes) b->stepLanes *= 2;
+        // as few worlds per warp as one-warp-per-scheduler allows; above 8 lanes a power of two (measured: 11 or 14 lanes
+        // lose more to row segments that straddle 128-byte lines than they gain over 16)
+        long long l = (n_worlds + 591) / 592;
+        b->stepLanes = l <= 8 ? (int)l : (l <= 16 ? 16 : 32);
     }
-    if (b->stepLanes < 1 || b->stepLanes > 32 || (b->stepLanes & (b->stepLanes - 1))) b->stepLanes = 32;
+    if (b->stepLanes < 1 || b->stepLanes > 32) b->stepLanes = 32;
     auto cleanup = [&](cudaError_t err, const char* what) {
         b2g_batch_destroy(b);
         return cudaFail(err, what);

@@ -224,19 +224,18 @@ __global__ void k_step(const __grid_constant__ ModelHeader hdr, const uint32_t* 
     }
 }
 
-// Small batches: stepping with only `lanes` (a power of two < 32) worlds per warp.  A batch that cannot fill the GPU's
-// 592 warp schedulers gains nothing from full warps, but every rare event (a contact, a TOI sub-step, a sleeping body)
-// in one lane makes the whole warp walk that path: spreading the worlds over more, narrower warps cuts that
-// serialisation.  Warp g owns worlds [tile * 32 + sub * lanes, + lanes) of tile = g / (32 / lanes): the state layout
-// is unchanged, a narrow warp reads `lanes` x 16 contiguous bytes of each chunk.
+// Small batches: stepping with only `lanes` (1..31) worlds per warp.  A batch that cannot fill the GPU's 592 warp schedulers
+// gains nothing from full warps, but every rare event (a contact, a TOI sub-step, a sleeping body) in one lane makes the
+// whole warp walk that path: spreading the worlds over more, narrower warps -- at most one per scheduler -- cuts that
+// serialisation.  Warp g owns worlds [g * lanes, (g + 1) * lanes): the state layout is unchanged, a narrow warp reads
+// `lanes` x 16 contiguous bytes of each chunk (two pieces when its worlds straddle a tile boundary).
 __global__ void k_step_narrow(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
                               StepParams prm, int object, const float* __restrict__ targets, int nTargets, int stepsPerTarget,
                               int executeControllers, int allowSleeping, int lanes) {
     B2G_STAGE();
     const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const int groups = 32 / lanes;
-    const long long w = (g / groups) * 32 + (g % groups) * lanes + lane;
+    const long long w = g * lanes + lane;
     if (lane >= lanes || w >= N) return;
     Ctx c;
     c.P = worldBase(S, hdr.stateChunks, w);
@@ -544,8 +543,7 @@ cudaError_t launchStep(const Launch& L, int object, const float* targets, int nT
     if (L.stepLanes < 32) {  // small batch: narrow warps, one warp per CTA
         cudaError_t e = prepare((const void*)k_step_narrow, L.h);
         if (e != cudaSuccess) return e;
-        long long tiles = (L.N + kTileWorlds - 1) / kTileWorlds;
-        unsigned blocks = (unsigned)(tiles * (32 / L.stepLanes));
+        unsigned blocks = (unsigned)((L.N + L.stepLanes - 1) / L.stepLanes);
         k_step_narrow<<<blocks, 32, smemBytes(L.h), L.stream>>>(L.h, L.blob, L.S, L.N, L.prm, object, targets, nTargets,
                                                               stepsPerTarget, execCtrl, allowSleep, L.stepLanes);
         ++g_launches;
