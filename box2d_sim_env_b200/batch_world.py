@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "b2g_env_add_polygon", "b2g_env_add_ball", "b2g_env_add_joint", "b2g_env_add_state", "b2g_model_create", "b2g_model_destroy",
     "b2g_model_get_info", "b2g_model_get_object", "b2g_model_get_dof_limits", "b2g_model_get_bodies",
     "b2g_model_get_fixtures", "b2g_model_get_joints", "b2g_model_get_balls", "b2g_batch_get_ball_approximation",
-    "b2g_batch_create", "b2g_batch_destroy", "b2g_batch_set_params",
+    "b2g_batch_create", "b2g_batch_clone", "b2g_batch_destroy", "b2g_batch_set_params",
     "b2g_batch_status", "b2g_batch_stream", "b2g_batch_sync", "b2g_batch_set_state", "b2g_batch_set_state_dev",
     "b2g_batch_get_state", "b2g_batch_get_state_dev", "b2g_batch_set_object_pose", "b2g_batch_set_object_dofs", "b2g_batch_get_object_dofs", "b2g_batch_select_worlds", "b2g_batch_get_object_pose",
     "b2g_batch_set_to_rest", "b2g_batch_at_rest", "b2g_batch_set_link_enabled", "b2g_batch_objects_in_aabb",
@@ -97,6 +97,7 @@ def lib():
     L.b2g_model_get_fixtures.argtypes = [vp, ip, fp]
     L.b2g_model_get_joints.argtypes = [vp, ip, fp]
     L.b2g_batch_create.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.POINTER(vp)]
+    L.b2g_batch_clone.argtypes = [vp, C.POINTER(vp)]
     L.b2g_batch_destroy.argtypes = [vp]
     L.b2g_batch_destroy.restype = None
     L.b2g_batch_set_params.argtypes = [vp, C.c_float, C.c_int, C.c_int]
@@ -317,10 +318,14 @@ class BatchBox2DWorld:
         return self
 
     def clone(self):
-        """Box2DWorld::clone (:3021-3038): same model, state copied through get/setWorldState."""
-        other = BatchBox2DWorld(self.n_worlds, self.device, self.max_contacts).loadWorld(self.model)
-        q, qd = self.getWorldState()
-        other.setWorldState(q, qd, reset_caches=True)
+        """Box2DWorld::clone (:3021-3038): same environment and step parameters, setWorldState(getWorldState()) incl. the
+        poses of static objects, fresh caches."""
+        other = BatchBox2DWorld(self.n_worlds, self.device, self.max_contacts)
+        other.model = self.model
+        other.nq = self.nq
+        other._dt, other._vs, other._ps = self.getPhysicsTimeStep(), self.getVelocitySteps(), self.getPositionSteps()
+        other.h = C.c_void_p()
+        _check(lib().b2g_batch_clone(self.h, C.byref(other.h)))
         return other
 
     def _destroy(self):

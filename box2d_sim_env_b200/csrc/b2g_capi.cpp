@@ -316,8 +316,51 @@ b2g_status b2g_model_get_joints(const b2g_model* model, int32_t* iout, float* fo
 }
 
 // ------------------------------------------------------------------------------------------------------ batch
+static b2g_status createBatch(const HostModel& hostModel, int64_t n_worlds, int device, int max_contacts, b2g_batch** out);
+
 b2g_status b2g_batch_create(const b2g_model* model, int64_t n_worlds, int device, int max_contacts, b2g_batch** out) {
     if (!model || !out || n_worlds <= 0) return fail(B2G_ERR_INVALID, "bad batch arguments");
+    return createBatch(model->m, n_worlds, device, max_contacts, out);
+}
+
+// Box2DWorld::clone (Box2DWorld.cpp:3021-3038): a new world from the same environment description, same step parameters,
+// then setWorldState(getWorldState()) -- DOF positions / velocities of every object plus the poses of static objects; the
+// clone starts with fresh caches (no contacts, zero warm-start impulses), exactly like the reference's.
+b2g_status b2g_batch_clone(b2g_batch* src, b2g_batch** out) {
+    if (!src || !out) return fail(B2G_ERR_INVALID, "null argument");
+    if (!src->allSelected()) return fail(B2G_ERR_INVALID, "stepping and the state stack act on the whole batch: call b2g_batch_select_worlds(batch, 0, 0) first");
+    b2g_batch* dst = nullptr;
+    b2g_status st = createBatch(src->m, src->N, src->device, src->m.h.maxc, &dst);
+    if (st) return st;
+    dst->prm.dt = src->prm.dt;
+    dst->prm.inv_dt = src->prm.inv_dt;
+    dst->prm.velIters = src->prm.velIters;
+    dst->prm.posIters = src->prm.posIters;
+    auto bail = [&](cudaError_t e, const char* what) {
+        b2g_batch_destroy(dst);
+        return cudaFail(e, what);
+    };
+    cudaError_t e;
+    const size_t bytes = (size_t)src->N * src->m.h.nq * 4;
+    if ((e = src->stageA.reserve(bytes)) != cudaSuccess) return bail(e, "cudaMalloc(stage)");
+    if ((e = src->stageB.reserve(bytes)) != cudaSuccess) return bail(e, "cudaMalloc(stage)");
+    if ((e = src->stageC.reserve((size_t)src->N * 3 * 4)) != cudaSuccess) return bail(e, "cudaMalloc(stage)");
+    // everything runs on the source's stream, in order; the clone's own stream starts after the final synchronisation
+    Launch ld = dst->L();
+    ld.stream = src->stream;
+    for (int o = 0; o < src->m.h.no; ++o) {
+        if (!src->m.objects[o].isStatic) continue;
+        if ((e = launchGetPose(src->L(), o, (float*)src->stageC.p)) != cudaSuccess) return bail(e, "get pose kernel");
+        if ((e = launchSetPose(ld, o, (const float*)src->stageC.p)) != cudaSuccess) return bail(e, "set pose kernel");
+    }
+    if ((e = launchGetState(src->L(), (float*)src->stageA.p, (float*)src->stageB.p)) != cudaSuccess) return bail(e, "get state kernel");
+    if ((e = launchSetState(ld, (const float*)src->stageA.p, (const float*)src->stageB.p)) != cudaSuccess) return bail(e, "set state kernel");
+    if ((e = cudaStreamSynchronize(src->stream)) != cudaSuccess) return bail(e, "clone sync");
+    *out = dst;
+    return B2G_OK;
+}
+
+static b2g_status createBatch(const HostModel& hostModel, int64_t n_worlds, int device, int max_contacts, b2g_batch** out) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
@@ -326,7 +369,7 @@ b2g_status b2g_batch_create(const b2g_model* model, int64_t n_worlds, int device
     if (device < 0 || device >= count) return fail(B2G_ERR_INVALID, "unknown device");
     CU(cudaSetDevice(device));
     b2g_batch* b = new b2g_batch();
-    b->m = model->m;
+    b->m = hostModel;
     if (max_contacts > 0) layoutState(b->m.h, max_contacts > kMaxContacts ? kMaxContacts : max_contacts);
     b->device = device;
     b->N = n_worlds;

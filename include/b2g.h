@@ -120,6 +120,9 @@ b2g_status b2g_model_get_balls(const b2g_model* model, int object, int32_t* bodi
  * ------------------------------------------------------------------------------------------------- */
 b2g_status b2g_batch_create(const b2g_model* model, int64_t n_worlds, int device, int max_contacts, b2g_batch** out);
 void b2g_batch_destroy(b2g_batch* batch);
+/* Box2DWorld::clone (Box2DWorld.cpp:3021-3038) for the whole batch: same environment, same time step / iteration counts,
+ * setWorldState(getWorldState()) incl. the poses of static objects; fresh caches like a freshly loaded world. */
+b2g_status b2g_batch_clone(b2g_batch* batch, b2g_batch** out);
 /* setPhysicsTimeStep / setVelocitySteps / setPositionSteps (Box2DWorld.cpp:3340-3353); defaults 0.01, 15, 15 */
 /* Restrict the per-world calls below (state / pose / target get and set, collision and region queries, ball
  * approximation, probes, status) to worlds [first, first + count): their arrays then have `count` rows.  This is what a

@@ -185,6 +185,7 @@ public:
     // Box2DWorld::loadWorld(path) (Box2DWorld.cpp:3040-3054)
     void loadWorld(const std::string& path) {
         destroy();
+        _path = path;
         check(b2g_env_load_yaml(path.c_str(), &_env));
         check(b2g_model_create(_env, &_model));
         check(b2g_model_get_info(_model, &_info));
@@ -210,6 +211,28 @@ public:
         _limits.assign((size_t)_info.nq * 6, 0.0f);
         if (_info.nq > 0) check(b2g_model_get_dof_limits(_model, _limits.data()));
         check(b2g_batch_create(_model, _n, _device, _max_contacts, &_batch));
+    }
+
+    // Box2DWorld::clone (:3021-3038): same environment and step parameters, setWorldState(getWorldState()) incl. the poses of
+    // static objects, fresh caches.  The clone re-reads the environment file the original was loaded from.
+    BatchBox2DWorld* clone() {
+        if (!_batch) throw std::logic_error("[sim_env::b2g::BatchBox2DWorld::clone] no world loaded");
+        BatchBox2DWorld* other = new BatchBox2DWorld(_n, _device, _max_contacts);
+        try {
+            check(b2g_env_load_yaml(_path.c_str(), &other->_env));
+            check(b2g_model_create(other->_env, &other->_model));
+            other->_info = _info;
+            other->_objects = _objects;
+            other->_active = _active;
+            other->_limits = _limits;
+            other->_path = _path;
+            other->_dt = _dt; other->_vs = _vs; other->_ps = _ps;
+            check(b2g_batch_clone(_batch, &other->_batch));
+        } catch (...) {
+            delete other;
+            throw;
+        }
+        return other;
     }
 
     // model introspection (host only; valid after loadWorld's model stage even when batch creation failed)
@@ -444,6 +467,7 @@ private:
     b2g_model* _model = nullptr;
     b2g_batch* _batch = nullptr;
     b2g_model_info _info{};
+    std::string _path;
     std::vector<ObjectInfo> _objects;
     std::vector<std::vector<int> > _active;  // active DOFs per object (Box2DObject::_active_dof_indices)
     std::vector<float> _limits;              // nq x 6 (b2g_model_get_dof_limits)

@@ -114,6 +114,19 @@ int main(int argc, char** argv) {
         bad += rc != r.checkCollision();
         viewHits += pair ? 1 : 0;
     }
+    // clone(): same parameters and state, independent afterwards
+    {
+        BatchBox2DWorld* twin = batch.clone();
+        std::vector<float> tq, tqd, bq, bqd;
+        twin->getWorldState(tq, tqd);
+        batch.getWorldState(bq, bqd);
+        for (size_t i = 0; i < tq.size(); ++i) bad += std::fabs(tq[i] - bq[i]) > 1e-5f;
+        bad += twin->getPhysicsTimeStep() != batch.getPhysicsTimeStep();
+        twin->stepPhysics(3);
+        batch.getWorldState(tq, tqd);
+        for (size_t i = 0; i < tq.size(); ++i) bad += tq[i] != bq[i];  // stepping the clone leaves the original alone
+        delete twin;
+    }
     bool viewThrew = false;
     try {
         w3.stepPhysics(1);

@@ -605,3 +605,40 @@ def test_one_call_rollout_matches_stepwise(b2g):
     mq, mqd = other.getWorldState()
     assert np.array_equal(oq2, mq) and np.array_equal(oqd2, mqd)
     assert np.array_equal(batch.bodies(), other.bodies())
+
+
+def test_clone(b2g):
+    """Box2DWorld::clone (:3021-3038): same step parameters, DOF state and static object poses, fresh caches: the clone
+    continues like an oracle world that went through getWorldState -> fresh world -> setWorldState."""
+    n = 40
+    batch = make_batch(b2g, ENV_A, n)
+    batch.setPhysicsTimeStep(0.005)
+    batch.setVelocitySteps(9)
+    worlds = oracle_worlds(load_env_dict(ENV_A), n)
+    q, qd = random_states(batch.model, n, seed=81, spread=0.6)
+    tg = random_targets(batch.model, 0, n, seed=82, segments=2)
+    batch.setWorldState(q, qd, reset_caches=True)
+    scatter_obstacle(batch, worlds, seed=83)          # moves the static obstacle in both
+    batch.setTargetVelocity(0, tg[0])
+    batch.stepPhysics(15)
+    twin = batch.clone()
+    assert (twin.getPhysicsTimeStep(), twin.getVelocitySteps(), twin.getPositionSteps()) == (0.005, 9, 15)
+    assert np.array_equal(twin.getObjectPose("obj2"), batch.getObjectPose("obj2"))
+    cq, cqd = twin.getWorldState()
+    bq, bqd = batch.getWorldState()
+    assert np.allclose(cq, bq, atol=2e-6) and np.allclose(cqd, bqd, atol=2e-5)
+    assert int(twin.contacts()[0].sum()) == 0         # fresh caches
+    # oracle: fresh worlds with the same parameters that receive the clone's state
+    fresh = oracle_worlds(load_env_dict(ENV_A), n)
+    poses = batch.getObjectPose("obj2")
+    for w, ow in enumerate(fresh):
+        ow.set_params(0.005, 9, 15)
+        ow.set_object_pose(2, *[float(x) for x in poses[w]])
+        ow.set_state(bq[w], bqd[w])
+    assert_same(twin, fresh, "clone == fresh world + setWorldState")
+    twin.setTargetVelocity(0, tg[1])
+    twin.stepPhysics(10)
+    for w, ow in enumerate(fresh):
+        ow.set_target_velocity(0, tg[1][w])
+        ow.step(10)
+    assert_same(twin, fresh, "clone after 10 steps")

@@ -226,3 +226,60 @@ def test_reference_test_configurations_round_trip(oracle, obj, conf, vel):
     assert w.get_object_dofs(obj, velocities=True).tolist() == pytest.approx(vel, abs=2e-6)
     pose = w.get_object_pose(obj)
     assert pose.tolist() == pytest.approx(conf[:3], abs=2e-6)
+
+
+def test_collide_polygons_box_face_known_answers(oracle):
+    """b2CollidePolygons on two axis-aligned unit boxes, derived by hand from the published algorithm (Box2D 2.3.1
+    b2CollidePolygon.cpp) -- A at the origin, B shifted along +x:
+
+    hull order of a box after b2PolygonShape::Set (KAT above): v0 = (h,-h), v1 = (h,h), v2 = (-h,h), v3 = (-h,-h), normals
+    (1,0) (0,1) (-1,0) (0,-1).  b2FindMaxSeparation(A, B) = x_B - 2h on A's edge 0, b2FindMaxSeparation(B, A) the same on B's
+    edge 2; equal separations -> no flip (k_tol = 0.1 * linearSlop), reference face = A's edge 0, manifold type e_faceA with
+    localNormal (1,0), localPoint (h,0).  Incident edge on B = the edge whose normal is most anti-parallel: edge 2, vertices
+    v2, v3 -> clip points (x_B - h, +h) and (x_B - h, -h), both inside the side planes (|y| <= h + totalRadius), kept while
+    separation = x_B - 2h <= totalRadius = 2 * polygonRadius = 0.02; manifold points are stored in B's frame: (-h, +h),
+    (-h, -h); contact ids {indexA = 0 (reference edge), indexB = 2 / 3 (incident vertex), typeA = face (1), typeB = vertex
+    (0)} = 0x010200, 0x010300."""
+    h = 0.5
+    box = [-h, -h, h, -h, h, h, -h, h]
+    for xb, expect_points in ((0.9, 2), (1.015, 2), (1.03, 0)):     # overlapping / inside the 0.02 skin / separated
+        m = oracle.collide_polygons(box, [0, 0, 0], box, [xb, 0, 0])
+        assert m["point_count"] == expect_points
+        if expect_points == 0:
+            continue
+        assert m["type"] == 1                                            # b2Manifold::e_faceA
+        assert m["local_normal"].tolist() == [1.0, 0.0]
+        assert m["local_point"].tolist() == [0.5, 0.0]
+        assert np.allclose(m["points"], [[-0.5, 0.5], [-0.5, -0.5]], atol=1e-6)
+        assert m["ids"] == [0x010200, 0x010300]
+    # the mirrored configuration makes A's edge 2 the reference face and B's vertices v0, v1 the incident ones
+    m = oracle.collide_polygons(box, [0, 0, 0], box, [-0.9, 0, 0])
+    assert (m["point_count"], m["type"]) == (2, 1)
+    assert m["local_normal"].tolist() == [-1.0, 0.0] and m["local_point"].tolist() == [-0.5, 0.0]
+    assert np.allclose(m["points"], [[0.5, -0.5], [0.5, 0.5]], atol=1e-6)
+    assert m["ids"] == [0x010002, 0x010102]
+
+
+def _two_box_env(restitution):
+    def box(name):
+        link = dict(name="link", geometry=[[-0.1, -0.1, 0.1, -0.1, 0.1, 0.1, -0.1, 0.1]], mass=0.5, ground_friction=0.0,
+                    ground_torque_integral=0.0, contact_friction=0.0, restitution=restitution, balls=[])
+        return dict(name=name, static=False, links=[link], joints=[], base_actuation=None)
+    return dict(scale=10.0, world_bounds=[-5, -5, 5, 5], robots=[], objects=[box("a"), box("b")],
+                states={"a": dict(configuration=[0.0, 0.0, 0.0], velocity=[1.0, 0.0, 0.0]),
+                        "b": dict(configuration=[0.5, 0.0, 0.0], velocity=[0.0, 0.0, 0.0])})
+
+
+@pytest.mark.parametrize("restitution,va,vb", [(1.0, 0.0, 1.0), (0.0, 0.5, 0.5)])
+def test_head_on_collision_known_answers(oracle, restitution, va, vb):
+    """Two equal frictionless boxes, a at 1 m/s onto b at rest (no ground friction, no gravity): conservation of momentum
+    plus Newton's restitution law give the textbook answers -- velocities swap for e = 1 (b2MixRestitution = max, relative
+    normal speed 10 > b2_velocityThreshold 1 in Box2D units), both move at 0.5 m/s for e = 0."""
+    w = oracle.OracleWorld(_two_box_env(restitution))
+    w.step(60)
+    q, qd = w.get_state()
+    assert qd[0] + qd[3] == pytest.approx(1.0, abs=1e-5)              # momentum (equal masses)
+    assert qd[0] == pytest.approx(va, abs=2e-3) and qd[3] == pytest.approx(vb, abs=2e-3)
+    assert abs(qd[1]) < 1e-6 and abs(qd[4]) < 1e-6 and abs(qd[2]) < 1e-5 and abs(qd[5]) < 1e-5   # stays one-dimensional
+    if restitution == 0.0:
+        assert q[3] - q[0] >= 0.2 - 0.011                             # boxes rest against each other, within the slop
