@@ -201,7 +201,7 @@ DEV void sleepBody(Ctx c, int b) {
     int f = ldI(c, bslot(c, b, SB_FLAGS));
     st4(c, bslot(c, b, SB_VEL4), mk4(0.0f, 0.0f, 0.0f, __int_as_float(f & ~1)));
     stF(c, bslot(c, b, SB_SLEEP), 0.0f);
-    st4(c, bslot(c, b, SB_FORCE4), mk4(0.0f, 0.0f, 0.0f, 0.0f));
+    if (mI(c, mbody(c, b, MB_FORCED))) st4(c, bslot(c, b, SB_FORCE4), mk4(0.0f, 0.0f, 0.0f, 0.0f));
 }
 
 // ---- broad phase: fat AABBs, move buffer as a 64-bit mask ---------------------------------------------------

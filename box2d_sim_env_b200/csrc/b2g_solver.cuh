@@ -958,7 +958,8 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
         stV2(c, bo + SB_C0X, P.c);
         stF(c, bo + SB_A0, P.a);
         Vel V = ldVelAt(c, bo);
-        const float4 ft = ld4(c, bo + SB_FORCE4);
+        // only a robot's base link ever receives forces; for every other body the chunk is the constant +0
+        const float4 ft = mI(c, mbody(c, L.dyn[i], MB_FORCED)) ? ld4(c, bo + SB_FORCE4) : mk4(0.0f, 0.0f, 0.0f, 0.0f);
         V2 f = mk(ft.x, ft.y);
         float tq = ft.z;
         float im = bm.x, ii = bm.y;

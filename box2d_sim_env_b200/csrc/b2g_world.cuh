@@ -433,7 +433,7 @@ DEVN void stepWorld(Ctx c, bool executeControllers, bool allowSleeping) {
 #endif
     stF(c, sslot(c, SS_INV_DT0), PRM().inv_dt);
     for (int b = 0; b < h.nb; ++b) {  // ClearForces
-        st4(c, bslot(c, b, SB_FORCE4), mk4(0.0f, 0.0f, 0.0f, 0.0f));
+        if (mI(c, mbody(c, b, MB_FORCED))) st4(c, bslot(c, b, SB_FORCE4), mk4(0.0f, 0.0f, 0.0f, 0.0f));
     }
 }
 

@@ -30,7 +30,9 @@ enum BodyField {  // per body; 16-byte groups are read with one LDS.128
     MB_COLLIDE_LO, MB_COLLIDE_HI,  // bit b: b2Body::ShouldCollide(this, b)
     MB_PX, MB_PY,  // creation position (non-zero for the ground body only)
     MB_SOFF,       // byte offset of this body's first state chunk (see the per-world state below)
-    MB_SPARE1, MB_SPARE2, MB_SPARE3,
+    MB_FORCED,     // 1: forces / torques can reach this body (the base link of a robot, Box2DRobot::commandEfforts :2319-2379);
+                   // every other body's force chunk stays +0 for ever and is neither read nor cleared
+    MB_SPARE2, MB_SPARE3,
     MB_STRIDE
 };
 enum FixtureField {  // per fixture / broad-phase proxy (creation order == proxy id order)

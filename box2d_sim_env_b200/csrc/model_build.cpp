@@ -553,6 +553,9 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
         w[MB_COLLIDE_LO] = (uint32_t)(collide[b] & 0xffffffffull); w[MB_COLLIDE_HI] = (uint32_t)(collide[b] >> 32);
         w[MB_PX] = fbits(bd.px); w[MB_PY] = fbits(bd.py);
         w[MB_SOFF] = (uint32_t)(b * SB_CHUNKS * kChunkBytes);  // layoutState puts the bodies first (cBody == 0)
+        w[MB_FORCED] = 0u;
+        for (const BObject& ob : objects)
+            if (ob.d->is_robot && ob.baseBody == b) w[MB_FORCED] = 1u;
     }
     align4();
     h.oFix = allocWords(nf * MF_STRIDE);
