@@ -67,6 +67,17 @@ DEV Pos ldPosAt(Ctx c, int boff) {
     return r;
 }
 DEV void stPosAt(Ctx c, int boff, const Pos& r) { st4(c, boff + SB_POS4, mk4(r.c.x, r.c.y, r.a, r.keep)); }
+// Rotation of a body at the start of an island solve.  b2Island reads it as b2Rot(position.a) with position.a = m_sweep.a;
+// every path that writes m_sweep.a (SynchronizeTransform, SetTransform, b2Body::Advance) also sets m_xf.q = b2Rot(a) with
+// the same deterministic sin / cos, so the stored m_xf.q IS b2Rot(a), bit for bit, and the sin / cos is not recomputed.
+DEV Rot ldRotAt(Ctx c, int boff) {
+    float2 q = ld2(c, boff + SB_QS);
+    Rot r;
+    r.s = q.x;
+    r.c = q.y;
+    return r;
+}
+
 // A static body never moves: b2Island copies v = w = +0 for it and every solver update is x -= 0 * impulse, which
 // leaves +0 for any finite impulse.  Its velocity is therefore neither loaded nor stored.
 DEV Vel zeroVel() {
@@ -87,11 +98,9 @@ DEVN void jointInit(Ctx c, int j, float dtRatio) {
     const int type = jh.x;
     const bool staticA = (jh.w & 4) != 0, staticB = (jh.w & 8) != 0;
     const int js = off.x, jw = off.y;
-    float aA = ldF(c, off.z + SB_A);
-    float aB = ldF(c, off.w + SB_A);
     Vel A = staticA ? zeroVel() : ldVelAt(c, off.z);
     Vel B = staticB ? zeroVel() : ldVelAt(c, off.w);
-    Rot qA = rotOf(aA), qB = rotOf(aB);
+    Rot qA = ldRotAt(c, off.z), qB = ldRotAt(c, off.w);
     V2 rA = mul(qA, mk(arm.x, arm.y));
     V2 rB = mul(qB, mk(arm.z, arm.w));
     float mA = im.x, mB = im.z;
@@ -140,7 +149,7 @@ DEVN void jointInit(Ctx c, int j, float dtRatio) {
         if (enableLimit && fixedRotation == false) {
             const float4 lim = m4(c, jr + MJ_REF);  // ref lower upper maxForce
             float lower = lim.y, upper = lim.z;
-            float jointAngle = aB - aA - lim.x;
+            float jointAngle = ldF(c, off.w + SB_A) - ldF(c, off.z + SB_A) - lim.x;
             if (absT(upper - lower) < 2.0f * B2G_ANGULAR_SLOP) {
                 limitState = 3;
             } else if (jointAngle <= lower) {
@@ -324,12 +333,10 @@ DEVN void frictionIslandSolve(Ctx c, int j, float dtRatio, int velIters) {
     const float4 im = m4(c, jr + MJ_MA);      // mA iA mB iB
     const float2 hmax = m2(c, jr + MJ_HMAXFORCE);
     const int js = off.x;
-    float aA = ldF(c, off.z + SB_A);
-    float aB = ldF(c, off.w + SB_A);
     Vel A = zeroVel();
     Vel B = ldVelAt(c, off.w);
     float4 acc4 = ld4(c, js + SJ_IMPULSE4);
-    Rot qA = rotOf(aA), qB = rotOf(aB);
+    Rot qA = ldRotAt(c, off.z), qB = ldRotAt(c, off.w);
     V2 rA = mul(qA, mk(arm.x, arm.y));
     V2 rB = mul(qB, mk(arm.z, arm.w));
     float mA = im.x, mB = im.z;
@@ -481,9 +488,13 @@ DEVN void contactInit(Ctx c, int k, float dtRatio, bool warmStarting) {
     float iA = bmA.y, iB = bmB.y;
     Pos PA = ldPos(c, bA), PB = ldPos(c, bB);
     Vel A = ldVel(c, bA), B = ldVel(c, bB);
+    // b2Island::Solve (warmStarting): positions are the bodies' sweeps, so xf.q = b2Rot(a) is the stored m_xf.q (ldRotAt).
+    // b2Island::SolveTOI: the TOI position solver has moved the positions away from the bodies' transforms -> recompute.
+    // xf.p = c - q * localCenter is always recomputed: after a SetTransform the stored m_xf.p is the caller's position,
+    // which differs from c - q * localCenter in the last bit.
     XF xfA, xfB;
-    xfA.q = rotOf(PA.a);
-    xfB.q = rotOf(PB.a);
+    xfA.q = warmStarting ? ldRotAt(c, bslot(c, bA, 0)) : rotOf(PA.a);
+    xfB.q = warmStarting ? ldRotAt(c, bslot(c, bB, 0)) : rotOf(PB.a);
     xfA.p = PA.c - mul(xfA.q, mk(bmA.z, bmA.w));
     xfB.p = PB.c - mul(xfB.q, mk(bmB.z, bmB.w));
     float restitution = fmA.w > fmB.w ? fmA.w : fmB.w;        // b2MixRestitution
@@ -955,8 +966,7 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
         const int bo = bslot(c, L.dyn[i], 0);
         const float4 bm = m4(c, mbody(c, L.dyn[i], MB_INVMASS));
         Pos P = ldPosAt(c, bo);
-        stV2(c, bo + SB_C0X, P.c);
-        stF(c, bo + SB_A0, P.a);
+        st4(c, bo + SB_POS04, mk4(P.c.x, P.c.y, P.a, 0.0f));  // c0 = c, a0 = a, alpha0 = 0
         Vel V = ldVelAt(c, bo);
         // only a robot's base link ever receives forces; for every other body the chunk is the constant +0
         const float4 ft = mI(c, mbody(c, L.dyn[i], MB_FORCED)) ? ld4(c, bo + SB_FORCE4) : mk4(0.0f, 0.0f, 0.0f, 0.0f);

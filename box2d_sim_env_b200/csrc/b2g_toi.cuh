@@ -10,6 +10,7 @@ namespace b2g {
 struct Sweep {
     V2 lc, c0, c;
     float a0, a, alpha0;
+    float keep;  // 4th word of the {c, a} chunk (the body's sleep time): rides along untouched
 };
 
 DEV Sweep ldSweep(Ctx c, int b) {
@@ -20,13 +21,13 @@ DEV Sweep ldSweep(Ctx c, int b) {
     s.c = mk(p.x, p.y);
     s.a0 = p0.z;
     s.a = p.z;
-    s.alpha0 = p.w;
+    s.alpha0 = p0.w;
+    s.keep = p.w;
     return s;
 }
 DEV void stSweep(Ctx c, int b, const Sweep& s) {
-    st4(c, bslot(c, b, SB_POS4), mk4(s.c.x, s.c.y, s.a, s.alpha0));
-    stV2(c, bslot(c, b, SB_C0X), s.c0);
-    stF(c, bslot(c, b, SB_A0), s.a0);
+    st4(c, bslot(c, b, SB_POS4), mk4(s.c.x, s.c.y, s.a, s.keep));
+    st4(c, bslot(c, b, SB_POS04), mk4(s.c0.x, s.c0.y, s.a0, s.alpha0));
 }
 DEV void sweepAdvance(Sweep& s, float alpha) {  // b2Sweep::Advance
     float beta = (alpha - s.alpha0) / (1.0f - s.alpha0);
@@ -367,14 +368,22 @@ DEVN void solveTOI(Ctx c) {
     bool candidates = false;
     for (int k = contactCount(c) - 1; k >= 0; --k) {
         int fl = ldI(c, cslot(c, k, SC_FLAGS));
-        stI(c, cslot(c, k, SC_FLAGS), fl & (CF_TOUCHING | CF_ENABLED | CF_FILTER));  // clears toi flag and toiCount
-        stF(c, cslot(c, k, SC_TOI), 1.0f);
+        // clears toi flag and toiCount; m_toi = 1 is dead (the value is only read under the toi flag, which is set together
+        // with a freshly computed m_toi)
+        if (fl & ~(CF_TOUCHING | CF_ENABLED | CF_FILTER)) stI(c, cslot(c, k, SC_FLAGS), fl & (CF_TOUCHING | CF_ENABLED | CF_FILTER));
         int fA, fB;
         contactFixtures(c, k, fA, fB);
         if (bodyType(c, mI(c, mfix(c, fA, MF_BODY))) != 2 || bodyType(c, mI(c, mfix(c, fB, MF_BODY))) != 2) candidates = true;
     }
-    for (int b = 0; b < nb; ++b) stF(c, bslot(c, b, SB_ALPHA0), 0.0f);
+    // sweeps' alpha0 = 0: island bodies got it with their c0 / a0 when the step began (solveIslands); the others (static,
+    // sleeping) can only hold a non-zero alpha0 if a TOI loop ran since the last reset (bit1 of the world flags)
+    const int wf = ldI(c, sslot(c, SS_FLAGS));
+    if (wf & 2) {
+        for (int b = 0; b < nb; ++b) stF(c, bslot(c, b, SB_ALPHA0), 0.0f);
+        if (!candidates) stI(c, sslot(c, SS_FLAGS), wf & ~2);
+    }
     if (!candidates) return;  // only contacts with a non-dynamic body are ever swept (no bullets in the reference)
+    if ((wf & 2) == 0) stI(c, sslot(c, SS_FLAGS), wf | 2);
 
     for (;;) {
         int minContact = -1;

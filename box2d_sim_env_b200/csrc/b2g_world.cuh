@@ -381,27 +381,29 @@ DEVN void robotControl(Ctx c, int o, int robotSlot) {
         accel = fminf(dofLimit(c, dofOffset + i, 5), fmaxf(accel, dofLimit(c, dofOffset + i, 4)));
         effort[i] = massInertia * accel;
     }
-    // commandEfforts
-    for (int i = 0; i < n; ++i) {
-        if (i < baseDofs) {
-            if (i < 2) {  // b2Body::ApplyForceToCenter(force, wake = true)
-                wakeBody(c, baseBody);
-                V2 f = ldV2(c, bslot(c, baseBody, SB_FX));
-                V2 add = i == 0 ? mk(s * effort[i], 0.0f) : mk(0.0f, s * effort[i]);
-                stV2(c, bslot(c, baseBody, SB_FX), f + add);
-            } else {      // b2Body::ApplyTorque
-                wakeBody(c, baseBody);
-                stF(c, bslot(c, baseBody, SB_TORQUE), ldF(c, bslot(c, baseBody, SB_TORQUE)) + s * s * effort[i]);
-            }
-        } else {
-            int j = objJoint(c, o, i - baseDofs);
-            wakeBody(c, mI(c, mjoint(c, j, MJ_BODYA)));
-            wakeBody(c, mI(c, mjoint(c, j, MJ_BODYB)));
-            stI(c, jslot(c, j, SJ_FLAGS), ldI(c, jslot(c, j, SJ_FLAGS)) | 4);  // EnableMotor(true)
-            stF(c, jslot(c, j, SJ_MAX_MOTOR_TORQUE), s * s * fabsf(effort[i]));
-            float sgn = effort[i] > 0.0f ? 1.0f : -1.0f;
-            stF(c, jslot(c, j, SJ_MOTOR_SPEED), sgn * FLT_MAX);
-        }
+    // commandEfforts (:2319-2379).  The base link's force / torque accumulate in registers in the reference's order (x force,
+    // y force, torque; each ApplyForceToCenter adds a full (fx, fy) vector) and go back with one store; a joint's motor
+    // settings are one chunk.
+    if (baseDofs > 0) {
+        wakeBody(c, baseBody);  // ApplyForceToCenter / ApplyTorque(…, wake = true)
+        float4 ft = ld4(c, bslot(c, baseBody, SB_FORCE4));
+        ft.x = ft.x + s * effort[0];
+        ft.y = ft.y + 0.0f;
+        ft.x = ft.x + 0.0f;
+        ft.y = ft.y + s * effort[1];
+        ft.z = ft.z + s * s * effort[2];
+        st4(c, bslot(c, baseBody, SB_FORCE4), ft);
+    }
+    for (int i = baseDofs; i < n; ++i) {
+        int j = objJoint(c, o, i - baseDofs);
+        wakeBody(c, mI(c, mjoint(c, j, MJ_BODYA)));
+        wakeBody(c, mI(c, mjoint(c, j, MJ_BODYB)));
+        // Box2DJoint::setControlTorque (:1198-1222): EnableMotor(true), maxMotorTorque = scale^2 |tau|, speed = sign(tau) FLT_MAX
+        float4 mot = ld4(c, jslot(c, j, SJ_MOTOR4));
+        mot.x = __int_as_float(__float_as_int(mot.x) | 4);
+        mot.y = s * s * fabsf(effort[i]);
+        mot.z = (effort[i] > 0.0f ? 1.0f : -1.0f) * FLT_MAX;
+        st4(c, jslot(c, j, SJ_MOTOR4), mot);
     }
 }
 

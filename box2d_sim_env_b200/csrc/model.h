@@ -131,9 +131,10 @@ constexpr int kChunkBytes = 16 * kTileWorlds;  // 512
 
 enum BodyState {
     SB_PX = B2G_F(0, 0), SB_PY = B2G_F(0, 1), SB_QS = B2G_F(0, 2), SB_QC = B2G_F(0, 3),    // b2Body::m_xf
-    SB_CX = B2G_F(1, 0), SB_CY = B2G_F(1, 1), SB_A = B2G_F(1, 2), SB_ALPHA0 = B2G_F(1, 3),  // m_sweep.c, a, alpha0
-    SB_C0X = B2G_F(2, 0), SB_C0Y = B2G_F(2, 1), SB_A0 = B2G_F(2, 2),                        // m_sweep.c0, a0
-    SB_SLEEP = B2G_F(2, 3),                                                                // m_sleepTime
+    SB_CX = B2G_F(1, 0), SB_CY = B2G_F(1, 1), SB_A = B2G_F(1, 2),                           // m_sweep.c, a
+    SB_SLEEP = B2G_F(1, 3),                                                                // m_sleepTime
+    // m_sweep.c0, a0, alpha0: all three only live inside one step, one STG.128 writes them when the step begins
+    SB_C0X = B2G_F(2, 0), SB_C0Y = B2G_F(2, 1), SB_A0 = B2G_F(2, 2), SB_ALPHA0 = B2G_F(2, 3),
     SB_VX = B2G_F(3, 0), SB_VY = B2G_F(3, 1), SB_W = B2G_F(3, 2),
     SB_FLAGS = B2G_F(3, 3),                                                                // bit0 awake
     SB_FX = B2G_F(4, 0), SB_FY = B2G_F(4, 1), SB_TORQUE = B2G_F(4, 2),
@@ -189,7 +190,7 @@ enum ContactWork {  // b2ContactVelocityConstraint, valid inside one island / TO
 };
 enum ScalarState {
     SS_INV_DT0 = B2G_F(0, 0),
-    SS_FLAGS = B2G_F(0, 1),      // bit0 newFixture
+    SS_FLAGS = B2G_F(0, 1),      // bit0 newFixture, bit1 the TOI loop ran since the sweeps' alpha0 were last reset
     SS_NCONTACTS = B2G_F(0, 2),
     SS_STATUS = B2G_F(0, 3),     // bit0 contact capacity exceeded, bit1 non-finite
     SS_MOVED_LO = B2G_F(1, 0), SS_MOVED_HI = B2G_F(1, 1),
