@@ -816,7 +816,10 @@ struct WorldLists {
 };
 
 // integrate positions with the translation / rotation caps (b2Island::Solve step 6, also SolveTOI)
-DEV void integratePosition(Ctx c, int b, float h) {
+// updateSleep: b2Island::Solve's sleep-time bookkeeping (m_sleepTime = 0 if the body moves faster than the sleep tolerances,
+// += h otherwise) is folded in here: it reads exactly the velocity this function leaves (the position iterations that
+// follow do not touch velocities) and the sleep time lives in the 4th word of the position chunk that is stored anyway.
+DEV void integratePosition(Ctx c, int b, float h, bool updateSleep) {
     Pos P = ldPos(c, b);
     Vel V = ldVel(c, b);
     V2 translation = h * V.v;
@@ -831,6 +834,11 @@ DEV void integratePosition(Ctx c, int b, float h) {
     }
     P.c = P.c + h * V.v;
     P.a += h * V.w;
+    if (updateSleep) {
+        const float linTolSqr = B2G_LINEAR_SLEEP_TOL * B2G_LINEAR_SLEEP_TOL;
+        const float angTolSqr = B2G_ANGULAR_SLEEP_TOL * B2G_ANGULAR_SLEEP_TOL;
+        P.keep = (V.w * V.w > angTolSqr || dot(V.v, V.v) > linTolSqr) ? 0.0f : P.keep + h;
+    }
     stPos(c, b, P);
     stVel(c, b, V);
 }
@@ -1014,7 +1022,7 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
     for (int i = 0; i < nSimple; ++i) frictionIslandSolve(c, L.joints[L.nj + i], dtRatio, velIters);
 
     phaseSync<SYNC, 6>();
-    for (int i = 0; i < L.ndyn; ++i) integratePosition(c, L.dyn[i], h);
+    for (int i = 0; i < L.ndyn; ++i) integratePosition(c, L.dyn[i], h, allowSleep);
 
     // position iterations: every island leaves the loop on its own (b2Island::Solve breaks when contactsOkay &&
     // jointsOkay); `open` = islands still iterating, `solved` = islands that reported positionSolved
@@ -1045,29 +1053,34 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
         open &= bad;
     }
     phaseSync<SYNC, 7>();
-    for (int i = 0; i < L.ndyn; ++i) syncTransform(c, L.dyn[i]);
+    // SynchronizeTransform of every island body, fused with its SynchronizeFixtures (upstream runs that in a second pass
+    // over the body list; the order is free here: the move buffer is a bit mask and nothing in between touches transforms
+    // or fat AABBs).  xf1 = the transform at the start of the step: its rotation b2Rot(a0) is the m_xf.q still stored at
+    // this point, xf1.p = c0 - q * localCenter is recomputed (see contactInit).
+    uint64_t moved = 0ull;
+    float minSleep[kMaxBodies];  // per island: the smallest sleep time of its bodies (updated in integratePosition)
+    for (int i = 0; i < L.nIslands; ++i) minSleep[i] = FLT_MAX;
+    for (int i = 0; i < L.ndyn; ++i) {
+        const int b = L.dyn[i];
+        const int bo = bslot(c, b, 0);
+        const V2 lc = localCenter(c, b);
+        XF xf1, xf2;
+        xf1.q = ldRotAt(c, bo);
+        xf1.p = ldV2(c, bo + SB_C0X) - mul(xf1.q, lc);
+        const float4 p = ld4(c, bo + SB_POS4);  // c, a, sleep time
+        xf2.q = rotOf(p.z);                     // b2Body::SynchronizeTransform
+        xf2.p = mk(p.x, p.y) - mul(xf2.q, lc);
+        stXF(c, b, xf2);
+        const int isl = L.bodyIsl[b];
+        minSleep[isl] = fminT(minSleep[isl], p.w);
+        moved |= syncBodyFixtures(c, b, xf1, xf2);
+    }
     for (uint64_t m = staticSeen; m; m &= m - 1ull) syncTransform(c, __ffsll((long long)m) - 1);
 
     // sleep decision per island; static bodies take the state their last island leaves them in (the DFS wakes
     // every body it reaches, a sleeping island then puts all of its bodies to sleep, static ones included)
     uint64_t asleep = 0ull;
     if (allowSleep) {
-        float minSleep[kMaxBodies];
-        for (int i = 0; i < L.nIslands; ++i) minSleep[i] = FLT_MAX;
-        const float linTolSqr = B2G_LINEAR_SLEEP_TOL * B2G_LINEAR_SLEEP_TOL;
-        const float angTolSqr = B2G_ANGULAR_SLEEP_TOL * B2G_ANGULAR_SLEEP_TOL;
-        for (int i = 0; i < L.ndyn; ++i) {
-            const int b = L.dyn[i], isl = L.bodyIsl[b];
-            Vel V = ldVel(c, b);
-            if (V.w * V.w > angTolSqr || dot(V.v, V.v) > linTolSqr) {
-                stF(c, bslot(c, b, SB_SLEEP), 0.0f);
-                minSleep[isl] = 0.0f;
-            } else {
-                float st = ldF(c, bslot(c, b, SB_SLEEP)) + h;
-                stF(c, bslot(c, b, SB_SLEEP), st);
-                minSleep[isl] = fminT(minSleep[isl], st);
-            }
-        }
         for (int i = 0; i < L.nIslands; ++i)
             if (minSleep[i] >= B2G_TIME_TO_SLEEP && ((solved >> i) & 1ull)) asleep |= 1ull << i;
         if (asleep)
@@ -1080,15 +1093,6 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
     }
 
     phaseSync<SYNC, 8>();
-    uint64_t moved = 0ull;
-    for (int b = nb - 1; b >= 0; --b) {
-        if (((bodyFlag >> b) & 1ull) == 0ull) continue;
-        XF xf1;
-        xf1.q = rotOf(ldF(c, bslot(c, b, SB_A0)));
-        xf1.p = ldV2(c, bslot(c, b, SB_C0X)) - mul(xf1.q, localCenter(c, b));
-        XF xf2 = ldXF(c, b);
-        moved |= syncBodyFixtures(c, b, xf1, xf2);
-    }
     if (moved) stMoved(c, ldMoved(c) | moved);
     findNewContacts(c);
 }

@@ -514,7 +514,7 @@ DEVN void solveTOI(Ctx c) {
         for (int it = 0, nv = PRM().velIters; it < nv; ++it)
             for (int i = 0; i < nic; ++i) contactSolveVel(c, icontacts[i]);
         for (int i = 0; i < nib; ++i) {
-            integratePosition(c, ibodies[i], h);
+            integratePosition(c, ibodies[i], h, false);
             syncTransform(c, ibodies[i]);
         }
 
