@@ -71,8 +71,13 @@ DEV void stPosAt(Ctx c, int boff, const Pos& r) { st4(c, boff + SB_POS4, mk4(r.c
 // every path that writes m_sweep.a (SynchronizeTransform, SetTransform, b2Body::Advance) also sets m_xf.q = b2Rot(a) with
 // the same deterministic sin / cos, so the stored m_xf.q IS b2Rot(a), bit for bit, and the sin / cos is not recomputed.
 DEV Rot ldRotAt(Ctx c, int boff) {
-    float2 q = ld2(c, boff + SB_QS);
     Rot r;
+    if (boff == 0) {  // body 0 is the ground: never moved, m_xf.q = b2Rot(0) = (0, 1) -- nothing to load
+        r.s = 0.0f;
+        r.c = 1.0f;
+        return r;
+    }
+    float2 q = ld2(c, boff + SB_QS);
     r.s = q.x;
     r.c = q.y;
     return r;
