@@ -173,6 +173,14 @@ DEVN void jointInit(Ctx c, int j, float dtRatio) {
         mot.x = __int_as_float((flags & ~3) | limitState);
         mot.w = ezy;
         st4(c, js + SJ_MOTOR4, mot);
+        if (enableLimit && limitState != 0 && fixedRotation == false) {
+            // b2Mat33::Solve33's right-hand-side independent part for the velocity iterations: cross(ey, ez), 1 / det
+            const float ezz = iA + iB;
+            const float cx = eyy * ezz - ezy * ezy, cy = ezy * ezx - eyx * ezz, cz = eyx * ezy - eyy * ezx;
+            float det = exx * cx + eyx * cy + ezx * cz;
+            if (det != 0.0f) det = 1.0f / det;
+            st4(c, jw + WJ_M1, mk4(cx, cy, cz, det));
+        }
         imp.x *= dtRatio; imp.y *= dtRatio; imp.z *= dtRatio;
         motorImpulse *= dtRatio;
         st4(c, js + SJ_IMPULSE4, mk4(imp.x, imp.y, imp.z, motorImpulse));
@@ -245,6 +253,19 @@ DEV V3 solve33(const float* m, V3 b) {  // m = ex.xyz ey.xyz ez.xyz ; b2Mat33::S
     return x;
 }
 
+// b2Mat33::Solve33 with cross(ey, ez) and 1 / det taken from jointInit (same operations on the same values)
+DEV V3 solve33pre(const float* m, float4 pre, V3 b) {
+    V3 ex = {m[0], m[1], m[2]}, ey = {m[3], m[4], m[5]}, ez = {m[6], m[7], m[8]};
+    const float det = pre.w;
+    V3 x;
+    x.x = det * (b.x * pre.x + b.y * pre.y + b.z * pre.z);
+    V3 cbz = {b.y * ez.z - b.z * ez.y, b.z * ez.x - b.x * ez.z, b.x * ez.y - b.y * ez.x};
+    x.y = det * (ex.x * cbz.x + ex.y * cbz.y + ex.z * cbz.z);
+    V3 cyb = {ey.y * b.z - ey.z * b.y, ey.z * b.x - ey.x * b.z, ey.x * b.y - ey.y * b.x};
+    x.z = det * (ex.x * cyb.x + ex.y * cyb.y + ex.z * cyb.z);
+    return x;
+}
+
 // b2RevoluteJoint::SolveVelocityConstraints
 DEV void revoluteSolveVel(Ctx c, int jr, int modelFlags) {
     const int4 off = mi4(c, jr + MJ_SOFF);  // js jw bodyA bodyB
@@ -281,10 +302,11 @@ DEV void revoluteSolveVel(Ctx c, int jr, int modelFlags) {
     }
     if (enableLimit && limitState != 0 && fixedRotation == false) {
         float m[9] = {k0.x, k0.y, k0.w, k0.y, k0.z, mot.w, k0.w, mot.w, iA + iB};
+        const float4 pre = ld4(c, jw + WJ_M1);  // cross(ey, ez), 1 / det (jointInit)
         V2 Cdot1 = B.v + cross(B.w, rB) - A.v - cross(A.w, rA);
         float Cdot2 = B.w - A.w;
         V3 Cdot = {Cdot1.x, Cdot1.y, Cdot2};
-        V3 s = solve33(m, Cdot);
+        V3 s = solve33pre(m, pre, Cdot);
         V3 impulse = {-s.x, -s.y, -s.z};
         V3 acc;
         acc.x = imp4.x; acc.y = imp4.y; acc.z = imp4.z;

@@ -149,6 +149,8 @@ enum BodyState {
 //   revolute:
 //     SJ chunk 0  impulse.xyz motorImpulse                                WJ chunk 0  rA.xy rB.xy
 //     SJ chunk 1  flags maxMotorTorque motorSpeed | K.zy (scratch)        WJ chunk 1  K.xx K.xy(=K.yx) K.yy K.zx   (K.zz = iA + iB)
+//     WJ chunk 2 (only written / read while the joint limit is active): the part of b2Mat33::Solve33 that does not depend
+//     on the right-hand side -- cross(K.ey, K.ez) and 1 / det(K) -- computed once per step instead of once per iteration
 enum JointState {
     SJ_IX = B2G_F(0, 0), SJ_IY = B2G_F(0, 1), SJ_IZ = B2G_F(0, 2),  // friction: linearImpulse.xy, angularImpulse; revolute: m_impulse
     SJ_MOTOR_IMPULSE = B2G_F(0, 3),                                 // revolute only (friction: scratch)
@@ -160,7 +162,8 @@ enum JointState {
 enum JointWork {  // solver scratch, valid inside one island solve
     WJ_R4 = B2G_F(0, 0),
     WJ_M0 = B2G_F(1, 0),
-    WJ_CHUNKS = 2
+    WJ_M1 = B2G_F(2, 0),
+    WJ_CHUNKS = 3
 };
 enum ContactState {
     SC_FIX = B2G_F(0, 0),       // fixtureA | fixtureB << 8
