@@ -438,16 +438,16 @@ def run_ours(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch (k_step / k_step_narrow) from `ncu --set full`, bytes per
-# launch of the config's default world count (profiles/r1c_<config>_<worlds>_k_step_ncu_full.txt)
+# launch of the config's default world count (profiles/r1d_<config>_<worlds>_k_step_ncu_full.txt)
 MEASURED_TRAFFIC = {
-    # 4096 worlds: the 21 MB state stays L2-resident across the 100 steps of a launch, DRAM sees far less than the
-    # algorithmic bytes (5.82 MB read + 0.39 MB written)
-    "cfg2": 5821952 + 391424,
-    # 65536 rigid-robot worlds (4.9 KB state each, 320 MB): 31.8 MB read + 82.4 MB written -- also mostly L2 hits
-    "cfg3": 31752448 + 82375680,
+    # 4096 worlds: the 32 MB state stays L2-resident across the 100 steps of a launch, DRAM sees far less than the
+    # algorithmic bytes (6.40 MB read + 0.48 MB written)
+    "cfg2": 6396160 + 484096,
+    # 65536 rigid-robot worlds: 31.6 MB read + 24.8 MB written -- the touched part of the state stays in L2 as well
+    "cfg3": 31598080 + 24777728,
     # 65536 clutter worlds: the ~9 KB a step touches per world (590 MB for the batch) does not fit the 126 MB L2, every
-    # step streams it: 81.8 GB read + 49.1 GB written per 6.55 M world-steps = 20 KB per world-step (algorithmic: 5.0 KB)
-    "cfg4": 81779440000 + 49093333000,
+    # step streams it: 69.8 GB read + 36.2 GB written per 6.55 M world-steps = 16 KB per world-step (algorithmic: 5.0 KB)
+    "cfg4": 69778133000 + 36249869000,
 }
 
 
