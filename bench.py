@@ -416,6 +416,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": MEASURED_TRAFFIC.get(args.config), "kernel": "k_step", "peak_kind": peak_kind,
+                         "sm_issue_active_pct": MEASURED_ISSUE_ACTIVE_PCT.get(args.config),
                          "kernel_ms_per_launch": kernel_ms / max(kernel_launches, 1),
                          "algorithmic_bytes_per_world_step": algorithmic_bytes_per_world_step(mean_contacts, cfg),
                          "note": "FP32 issue / dependent-latency bound, not bandwidth bound: DESIGN.md §3, profiles/"},
@@ -439,6 +440,10 @@ def run_ours(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch (k_step / k_step_narrow) from `ncu --set full`, bytes per
 # launch of the config's default world count (profiles/r1d_<config>_<worlds>_k_step_ncu_full.txt)
+# smsp__issue_active.avg.pct_of_peak_sustained_active of the same captures: the path is bound by issue slots / dependent
+# latency, not by HBM, so the SM issue utilisation is reported next to the HBM fraction
+MEASURED_ISSUE_ACTIVE_PCT = {"cfg2": 21.6, "cfg3": 38.1, "cfg4": 26.4}
+
 MEASURED_TRAFFIC = {
     # 4096 worlds: the 32 MB state stays L2-resident across the 100 steps of a launch, DRAM sees far less than the
     # algorithmic bytes (6.40 MB read + 0.48 MB written)

@@ -644,3 +644,25 @@ def test_clone(b2g):
         ow.set_target_velocity(0, tg[1][w])
         ow.step(10)
     assert_same(twin, fresh, "clone after 10 steps")
+
+
+def test_cfg1_single_world_thousand_steps(b2g):
+    """BASELINE.json configs[0]: test_env.yaml, ONE world, 1000 steps of robot velocity control with a fixed target
+    ([0.5, 0, 0.3, 0.5, -0.5, -0.5, 0.5]) from the YAML's initial state -- the longest trajectory in the
+    suite; compared with the oracle every 100 steps, bit for bit (plus three neighbours with perturbed targets)."""
+    n = 4
+    batch = make_batch(b2g, ENV_A, n)
+    worlds = oracle_worlds(load_env_dict(ENV_A), n)
+    tg = np.tile(np.float32([0.5, 0.0, 0.3, 0.5, -0.5, -0.5, 0.5]), (n, 1))
+    tg[1:, :3] += np.float32([[0.3, 0.2, -0.4], [-0.6, 0.1, 0.2], [0.0, -0.5, 0.6]])
+    batch.setTargetVelocity(0, tg)
+    for w, ow in enumerate(worlds):
+        ow.set_target_velocity(0, tg[w])
+    for block in range(10):
+        batch.stepPhysics(100)
+        for ow in worlds:
+            ow.step(100)
+        assert_same(batch, worlds, "after %d steps" % (100 * (block + 1)))
+    q, _ = batch.getWorldState()
+    assert abs(q[0, 0] - 5.0) < 0.6 and abs(q[0, 2] - 3.0) < 0.5      # the robot has travelled ~ v * 10 s
+    assert np.all(batch.status() == 0)
