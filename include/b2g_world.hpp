@@ -15,6 +15,7 @@
 #define B2G_WORLD_HPP_
 
 #include <cstdint>
+#include <cstdio>
 #include <limits>
 #include <map>
 #include <stdexcept>
@@ -187,36 +188,14 @@ public:
         destroy();
         _path = path;
         check(b2g_env_load_yaml(path.c_str(), &_env));
-        check(b2g_model_create(_env, &_model));
-        check(b2g_model_get_info(_model, &_info));
-        _objects.clear();
-        for (int i = 0; i < _info.n_objects; ++i) {
-            b2g_object_info oi;
-            check(b2g_model_get_object(_model, i, &oi));
-            ObjectInfo o;
-            o.name = oi.name;
-            o.is_robot = oi.is_robot != 0;
-            o.is_static = oi.is_static != 0;
-            o.n_dofs = oi.n_dofs;
-            o.dof_offset = oi.dof_offset;
-            o.first_body = oi.first_body;
-            o.n_links = oi.n_links;
-            o.n_joints = oi.n_joints;
-            o.n_balls = oi.n_balls;
-            _objects.push_back(o);
-        }
-        _active.assign(_objects.size(), std::vector<int>());
-        for (size_t i = 0; i < _objects.size(); ++i)  // all DOFs are active after construction (:1333)
-            for (int d = 0; d < _objects[i].n_dofs; ++d) _active[i].push_back(d);
-        _limits.assign((size_t)_info.nq * 6, 0.0f);
-        if (_info.nq > 0) check(b2g_model_get_dof_limits(_model, _limits.data()));
-        check(b2g_batch_create(_model, _n, _device, _max_contacts, &_batch));
+        finishLoad();
     }
 
     // Box2DWorld::clone (:3021-3038): same environment and step parameters, setWorldState(getWorldState()) incl. the poses of
     // static objects, fresh caches.  The clone re-reads the environment file the original was loaded from.
     BatchBox2DWorld* clone() {
         if (!_batch) throw std::logic_error("[sim_env::b2g::BatchBox2DWorld::clone] no world loaded");
+        if (_path.empty()) throw std::logic_error("[sim_env::b2g::BatchBox2DWorld::clone] the world was not loaded from a file");
         BatchBox2DWorld* other = new BatchBox2DWorld(_n, _device, _max_contacts);
         try {
             check(b2g_env_load_yaml(_path.c_str(), &other->_env));
@@ -234,6 +213,24 @@ public:
         }
         return other;
     }
+
+    // Box2DWorld::loadWorld(const Box2DEnvironmentDescription&) (:3049-3054): a description built with b2g_env_create /
+    // b2g_env_add_* (the batch takes ownership of `env`).  clone() is not available for such a world (no file to re-read).
+    void loadWorld(b2g_env* env) {
+        destroy();
+        _path.clear();
+        _env = env;
+        finishLoad();
+    }
+    bool supportsPhysics() const { return true; }                      // (:3335-3338)
+    bool isRobot(const std::string& name) const {                      // (:3202-3205)
+        for (size_t i = 0; i < _objects.size(); ++i)
+            if (_objects[i].name == name) return _objects[i].is_robot;
+        return false;
+    }
+    float getGravity() const { return 9.81f * _info.scale; }           // GRAVITY * getScale() (Box2DWorld.h:865-869)
+    // printWorldState (:3475-3488) of one world, to a stdio stream instead of the sim_env logger
+    void printWorldState(int64_t world_index, std::FILE* out = stdout);
 
     // model introspection (host only; valid after loadWorld's model stage even when batch creation failed)
     int64_t numWorlds() const { return _n; }
@@ -418,6 +415,32 @@ public:
 private:
     friend class World;
     friend class Object;
+    void finishLoad() {
+        check(b2g_model_create(_env, &_model));
+        check(b2g_model_get_info(_model, &_info));
+        _objects.clear();
+        for (int i = 0; i < _info.n_objects; ++i) {
+            b2g_object_info oi;
+            check(b2g_model_get_object(_model, i, &oi));
+            ObjectInfo o;
+            o.name = oi.name;
+            o.is_robot = oi.is_robot != 0;
+            o.is_static = oi.is_static != 0;
+            o.n_dofs = oi.n_dofs;
+            o.dof_offset = oi.dof_offset;
+            o.first_body = oi.first_body;
+            o.n_links = oi.n_links;
+            o.n_joints = oi.n_joints;
+            o.n_balls = oi.n_balls;
+            _objects.push_back(o);
+        }
+        _active.assign(_objects.size(), std::vector<int>());
+        for (size_t i = 0; i < _objects.size(); ++i)  // all DOFs are active after construction (:1333)
+            for (int d = 0; d < _objects[i].n_dofs; ++d) _active[i].push_back(d);
+        _limits.assign((size_t)_info.nq * 6, 0.0f);
+        if (_info.nq > 0) check(b2g_model_get_dof_limits(_model, _limits.data()));
+        check(b2g_batch_create(_model, _n, _device, _max_contacts, &_batch));
+    }
     // scope guard: per-world calls act on world i only while it lives
     struct Select {
         Select(const BatchBox2DWorld* b, int64_t i) : _b(b) { check(b2g_batch_select_worlds(_b->_batch, i, 1)); }
@@ -593,6 +616,20 @@ inline bool Object::checkCollision(const Object& other, std::vector<Contact>& co
 inline bool Object::checkCollision(const std::vector<Object>& others) { return World(_batch, _world).checkCollision(*this, others); }
 inline bool Object::checkCollision(const std::vector<Object>& others, std::vector<Contact>& contacts) {
     return World(_batch, _world).checkCollision(*this, others, contacts);
+}
+
+inline void BatchBox2DWorld::printWorldState(int64_t world_index, std::FILE* out) {
+    WorldState state = world(world_index).getWorldState();
+    std::fprintf(out, "World state: \n");
+    for (WorldState::const_iterator it = state.begin(); it != state.end(); ++it) {
+        std::fprintf(out, "%s positions:", it->first.c_str());
+        for (size_t i = 0; i < it->second.dof_positions.size(); ++i) std::fprintf(out, " %g", it->second.dof_positions[i]);
+        std::fprintf(out, " velocities:");
+        for (size_t i = 0; i < it->second.dof_velocities.size(); ++i) std::fprintf(out, " %g", it->second.dof_velocities[i]);
+        std::fprintf(out, " active_dofs:");
+        for (size_t i = 0; i < it->second.active_dofs.size(); ++i) std::fprintf(out, " %d", it->second.active_dofs[i]);
+        std::fprintf(out, "\n");
+    }
 }
 
 // ------------------------------------------------------------------------------------------------- World (one world)

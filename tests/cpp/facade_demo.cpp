@@ -68,6 +68,8 @@ int main(int argc, char** argv) {
     int bad = 0;
     World w3 = batch.world(3);
     Object robot = w3.getRobot("my_robot"), obj1 = w3.getObject("obj1"), obj2 = w3.getObject("obj2");
+    bad += !batch.isRobot("my_robot") || batch.isRobot("obj1") || batch.isRobot("nobody") || !batch.supportsPhysics();
+    bad += std::fabs(batch.getGravity() - 98.1f) > 1e-4f;
     bad += robot.getNumDOFs() != 7 || obj1.getNumDOFs() != 3 || obj2.getNumDOFs() != 1 || !obj2.isStatic();
     bad += robot.getType() != EntityType::Robot || obj1.getType() != EntityType::Object;
     bad += !robot.getDOFInformation(2).cyclic || robot.getDOFInformation(3).cyclic;
