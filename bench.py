@@ -439,20 +439,20 @@ def run_ours(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch (k_step / k_step_narrow) from `ncu --set full`, bytes per
-# launch of the config's default world count (profiles/r1d_<config>_<worlds>_k_step_ncu_full.txt)
+# launch of the config's default world count (profiles/r1e_<config>_<worlds>_k_step_ncu_full.txt)
 # smsp__issue_active.avg.pct_of_peak_sustained_active of the same captures: the path is bound by issue slots / dependent
 # latency, not by HBM, so the SM issue utilisation is reported next to the HBM fraction
-MEASURED_ISSUE_ACTIVE_PCT = {"cfg2": 21.6, "cfg3": 38.1, "cfg4": 26.4}
+MEASURED_ISSUE_ACTIVE_PCT = {"cfg2": 21.7, "cfg3": 38.9, "cfg4": 26.7}
 
 MEASURED_TRAFFIC = {
     # 4096 worlds: the 32 MB state stays L2-resident across the 100 steps of a launch, DRAM sees far less than the
-    # algorithmic bytes (6.40 MB read + 0.48 MB written)
-    "cfg2": 6396160 + 484096,
-    # 65536 rigid-robot worlds: 31.6 MB read + 24.8 MB written -- the touched part of the state stays in L2 as well
-    "cfg3": 31598080 + 24777728,
+    # algorithmic bytes (6.44 MB read + 0.51 MB written)
+    "cfg2": 6435840 + 507392,
+    # 65536 rigid-robot worlds: 31.6 MB read + 24.5 MB written -- the touched part of the state stays in L2 as well
+    "cfg3": 31556352 + 24489728,
     # 65536 clutter worlds: the ~9 KB a step touches per world (590 MB for the batch) does not fit the 126 MB L2, every
-    # step streams it: 69.8 GB read + 36.2 GB written per 6.55 M world-steps = 16 KB per world-step (algorithmic: 5.0 KB)
-    "cfg4": 69778133000 + 36249869000,
+    # step streams it: 69.1 GB read + 36.1 GB written per 6.55 M world-steps = 16 KB per world-step (algorithmic: 5.0 KB)
+    "cfg4": 69142817000 + 36054000000,
 }
 
 
