@@ -153,7 +153,6 @@ DEV void st4(Ctx c, int off, float4 v) { *reinterpret_cast<float4*>(sp(c, off)) 
 DEV float2 ld2(Ctx c, int off) { return *reinterpret_cast<const float2*>(sp(c, off)); }
 DEV void st2(Ctx c, int off, float2 v) { *reinterpret_cast<float2*>(sp(c, off)) = v; }
 DEV float4 mk4(float x, float y, float z, float w) { return make_float4(x, y, z, w); }
-DEV void pf(Ctx c, int off) { asm volatile("prefetch.global.L1 [%0];" ::"l"(sp(c, off))); }
 
 // model blob access (shared memory, warp-uniform addresses: broadcast reads)
 DEV float mF(Ctx, int off) { return __uint_as_float(g_sm[kHdrWords + off]); }

@@ -897,8 +897,8 @@ DEV void integratePosition(Ctx c, int b, float h, bool updateSleep) {
 }
 
 
-// Phase barrier of the CTA-synchronised stepping kernel.  The step is ~8k distinct instructions (k_step is 270 KB of
-// SASS); 16 resident warps that drift through different phases thrash the SM's instruction cache ("no_instructions"
+// Phase barrier of the CTA-synchronised stepping kernel.  The step is ~17.6 k distinct instructions (k_step is 280 KB of
+// SASS); resident warps that drift through different phases thrash the SM's instruction cache ("no_instructions"
 // was the top stall).  With SYNC every warp of the CTA walks the phases together, so the cache holds one phase.
 // All threads of the CTA must reach every phaseSync: they sit outside data-dependent control flow only.
 // Which of the ten candidate barriers are kept (bit ID).  Measured on B200, 65536 worlds of test_env.yaml, ms per 100 steps:
