@@ -372,6 +372,7 @@ def run_ours(args):
     # warm-up (nothing is JIT-compiled: the library is prebuilt), then the timed region
     warm = max(args.warmup, 3)
     timed_pass(warm, False, 0)
+    timed_pass(1, True, 50)   # the end-to-end path once, untimed: first use allocates its staging buffers
     batch.take_kernel_ms()
     launches0 = L.b2g_launch_count()
     with ClockSampler(local) as clocks:
