@@ -77,6 +77,9 @@ def lib():
         L.b2o_polygon_set.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p]
         L.b2o_collide_polygons.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                            C.c_void_p, C.c_void_p]
+        L.b2o_distance.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.b2o_time_of_impact.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]
         L.b2o_batch_new.argtypes = [C.c_void_p, C.c_int]
         L.b2o_batch_free.argtypes = [C.c_void_p]
         L.b2o_batch_world.argtypes = [C.c_void_p, C.c_int]
@@ -438,6 +441,25 @@ def polygon_set(points, density=1.0):
     n = lib().b2o_polygon_set(_ptr(p), len(p) // 2, density, _ptr(out))
     return dict(count=n, vertices=out[:16].reshape(8, 2)[:n].copy(), normals=out[16:32].reshape(8, 2)[:n].copy(),
                 centroid=out[32:34].copy(), mass=float(out[34]), center=out[35:37].copy(), I=float(out[37]))
+
+
+def distance(polyA, poseA, polyB, poseB, use_radii=False):
+    """b2Distance between two polygons: dict(distance, iterations, point_a, point_b)."""
+    a, b = _f32(polyA).reshape(-1), _f32(polyB).reshape(-1)
+    pa, pb = _f32(poseA), _f32(poseB)
+    out = np.zeros(6, np.float32)
+    lib().b2o_distance(_ptr(a), len(a) // 2, _ptr(pa), _ptr(b), len(b) // 2, _ptr(pb), int(use_radii), _ptr(out))
+    return dict(distance=float(out[0]), iterations=int(out[1]), point_a=out[2:4].copy(), point_b=out[4:6].copy())
+
+
+def time_of_impact(polyA, poseA0, poseA1, polyB, poseB0, poseB1):
+    """b2TimeOfImpact over [0, 1] for two polygons sweeping between two poses: (state, t); state 3 = touching,
+    4 = separated, 2 = overlapped, 1 = failed."""
+    a, b = _f32(polyA).reshape(-1), _f32(polyB).reshape(-1)
+    out = np.zeros(2, np.float32)
+    lib().b2o_time_of_impact(_ptr(a), len(a) // 2, _ptr(_f32(poseA0)), _ptr(_f32(poseA1)), _ptr(b), len(b) // 2,
+                             _ptr(_f32(poseB0)), _ptr(_f32(poseB1)), _ptr(out))
+    return int(out[0]), float(out[1])
 
 
 def collide_polygons(polyA, poseA, polyB, poseB):

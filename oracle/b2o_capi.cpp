@@ -425,6 +425,56 @@ int b2o_polygon_set(const float* xy, int n, float density, float* out38) {
     return s.count;
 }
 
+// b2Distance probe: two polygons + transforms (x, y, angle) -> out4 = distance, iterations, |pointA - pointB| check, useRadii
+void b2o_distance(const float* xyA, int nA, const float* poseA, const float* xyB, int nB, const float* poseB, int useRadii,
+                  float* out6) {
+    std::vector<Vec2> a, b;
+    for (int i = 0; i < nA; ++i) a.emplace_back(xyA[2 * i], xyA[2 * i + 1]);
+    for (int i = 0; i < nB; ++i) b.emplace_back(xyB[2 * i], xyB[2 * i + 1]);
+    PolygonShape sa, sb;
+    sa.Set(a.data(), nA);
+    sb.Set(b.data(), nB);
+    DistanceInput in;
+    in.proxyA = &sa;
+    in.proxyB = &sb;
+    in.transformA.Set(Vec2(poseA[0], poseA[1]), poseA[2]);
+    in.transformB.Set(Vec2(poseB[0], poseB[1]), poseB[2]);
+    in.useRadii = useRadii != 0;
+    SimplexCache cache;
+    DistanceOutput out;
+    DistanceGJK(&out, &cache, &in);
+    out6[0] = out.distance; out6[1] = (float)out.iterations;
+    out6[2] = out.pointA.x; out6[3] = out.pointA.y; out6[4] = out.pointB.x; out6[5] = out.pointB.y;
+}
+
+// b2TimeOfImpact probe: polygon A sweeps from poseA0 to poseA1 (local centre at the origin), B likewise, tMax = 1
+// out2 = state (b2TOIOutput::State), t
+void b2o_time_of_impact(const float* xyA, int nA, const float* poseA0, const float* poseA1, const float* xyB, int nB,
+                        const float* poseB0, const float* poseB1, float* out2) {
+    std::vector<Vec2> a, b;
+    for (int i = 0; i < nA; ++i) a.emplace_back(xyA[2 * i], xyA[2 * i + 1]);
+    for (int i = 0; i < nB; ++i) b.emplace_back(xyB[2 * i], xyB[2 * i + 1]);
+    PolygonShape sa, sb;
+    sa.Set(a.data(), nA);
+    sb.Set(b.data(), nB);
+    TOIInput in;
+    in.proxyA = &sa;
+    in.proxyB = &sb;
+    in.sweepA.localCenter = Vec2(0.0f, 0.0f);
+    in.sweepA.c0 = Vec2(poseA0[0], poseA0[1]); in.sweepA.a0 = poseA0[2];
+    in.sweepA.c = Vec2(poseA1[0], poseA1[1]); in.sweepA.a = poseA1[2];
+    in.sweepA.alpha0 = 0.0f;
+    in.sweepB.localCenter = Vec2(0.0f, 0.0f);
+    in.sweepB.c0 = Vec2(poseB0[0], poseB0[1]); in.sweepB.a0 = poseB0[2];
+    in.sweepB.c = Vec2(poseB1[0], poseB1[1]); in.sweepB.a = poseB1[2];
+    in.sweepB.alpha0 = 0.0f;
+    in.tMax = 1.0f;
+    TOIOutput out;
+    TimeOfImpact(&out, &in);
+    out2[0] = (float)out.state;
+    out2[1] = out.t;
+}
+
 // narrowphase probe: two polygons + transforms (x, y, angle) -> manifold
 // out ints [pointCount, type, id0, id1], floats [localNormal(2) localPoint(2) p0(2) p1(2)]
 void b2o_collide_polygons(const float* xyA, int nA, const float* poseA, const float* xyB, int nB, const float* poseB,

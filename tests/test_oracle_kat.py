@@ -283,3 +283,37 @@ def test_head_on_collision_known_answers(oracle, restitution, va, vb):
     assert abs(qd[1]) < 1e-6 and abs(qd[4]) < 1e-6 and abs(qd[2]) < 1e-5 and abs(qd[5]) < 1e-5   # stays one-dimensional
     if restitution == 0.0:
         assert q[3] - q[0] >= 0.2 - 0.011                             # boxes rest against each other, within the slop
+
+
+def test_distance_known_answers(oracle):
+    """b2Distance (GJK) between boxes, from plane geometry: face to face -> the gap; corner to corner -> the diagonal of the
+    gap; a box rotated by 45 degrees -> centre distance minus the half diagonal minus the half width; with radii the
+    two polygon radii (0.01 each) come off; overlapping shapes -> 0."""
+    h = 0.5
+    box = [-h, -h, h, -h, h, h, -h, h]
+    d = oracle.distance(box, [0, 0, 0], box, [3.0, 0.2, 0])
+    assert d["distance"] == pytest.approx(2.0, abs=1e-6) and d["point_a"][0] == pytest.approx(0.5, abs=1e-6)
+    assert oracle.distance(box, [0, 0, 0], box, [3.0, 0.2, 0], use_radii=True)["distance"] == pytest.approx(1.98, abs=1e-6)
+    d = oracle.distance(box, [0, 0, 0], box, [2.0, 3.0, 0])
+    assert d["distance"] == pytest.approx(np.hypot(1.0, 2.0), abs=1e-6)
+    assert np.allclose(d["point_a"], [0.5, 0.5], atol=1e-6) and np.allclose(d["point_b"], [1.5, 2.5], atol=1e-6)
+    d = oracle.distance(box, [0, 0, 0], box, [3.0, 0.0, np.pi / 4])
+    assert d["distance"] == pytest.approx(3.0 - 0.5 - np.sqrt(0.5), abs=2e-6)
+    assert oracle.distance(box, [0, 0, 0], box, [0.7, 0.1, 0.3])["distance"] == pytest.approx(0.0, abs=1e-6)
+
+
+def test_time_of_impact_known_answers(oracle):
+    """b2TimeOfImpact for a box translating onto a resting box: contact is declared when the separation reaches the target
+    = max(linearSlop, totalRadius - 3 linearSlop) = 0.005 (totalRadius = 2 * 0.01), within a tolerance of 0.25 * linearSlop
+    -> t = (gap - target) / travelled distance.  A sweep that stops short -> separated at t = 1."""
+    h = 0.5
+    box = [-h, -h, h, -h, h, h, -h, h]
+    # gap 2.0, B travels 4.0 towards A: t = (2.0 - 0.005) / 4.0
+    state, t = oracle.time_of_impact(box, [0, 0, 0], [0, 0, 0], box, [3.0, 0.1, 0], [-1.0, 0.1, 0])
+    assert state == 3 and t == pytest.approx((2.0 - 0.005) / 4.0, abs=0.25 * 0.005 / 4.0 + 1e-6)
+    # both moving: closing distance 1.5 + 2.5
+    state, t = oracle.time_of_impact(box, [0, 0, 0], [1.5, 0, 0], box, [3.0, 0.1, 0], [0.5, 0.1, 0])
+    assert state == 3 and t == pytest.approx((2.0 - 0.005) / 4.0, abs=0.25 * 0.005 / 4.0 + 1e-6)
+    # stops one unit short
+    state, t = oracle.time_of_impact(box, [0, 0, 0], [0, 0, 0], box, [3.0, 0.1, 0], [2.0, 0.1, 0])
+    assert state == 4 and t == 1.0
