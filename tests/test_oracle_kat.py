@@ -317,3 +317,43 @@ def test_time_of_impact_known_answers(oracle):
     # stops one unit short
     state, t = oracle.time_of_impact(box, [0, 0, 0], [0, 0, 0], box, [3.0, 0.1, 0], [2.0, 0.1, 0])
     assert state == 4 and t == 1.0
+
+
+def test_hinged_pair_conserves_momentum(oracle):
+    """Two bars joined by a free hinge, no ground friction, no contacts, no gravity: the revolute joint exchanges equal and
+    opposite impulses at one point, so total linear momentum and total angular momentum (about the origin) are conserved
+    while the relative angle changes and the anchors stay together."""
+    def link(name, poly, mass):
+        return dict(name=name, geometry=[poly], mass=mass, ground_friction=0.0, ground_torque_integral=0.0, contact_friction=0.0,
+                    restitution=0.0, balls=[])
+    obj = dict(name="pair", static=False, base_actuation=None,
+               links=[link("a", [-0.2, -0.05, 0.2, -0.05, 0.2, 0.05, -0.2, 0.05], 0.7), link("b", [0.0, -0.04, 0.3, -0.04, 0.3, 0.04, 0.0, 0.04], 0.4)],
+               joints=[dict(name="hinge", link_a="a", link_b="b", axis=[0.2, 0.0], axis_orientation=0.0, position_limits=[0.0, 0.0],
+                            velocity_limits=[-100.0, 100.0], acceleration_limits=[-100.0, 100.0], joint_type="revolute", actuated=False)])
+    env = dict(scale=10.0, world_bounds=[-5, -5, 5, 5], robots=[], objects=[obj],
+               states={"pair": dict(configuration=[0.1, -0.2, 0.3, 0.4], velocity=[0.3, -0.2, 0.8, -1.5])})
+    w = oracle.OracleWorld(env)
+    bm = w.body_model()            # mass invMass I (about the centre of mass, b2Body::m_I) invI lcx lcy type nfix (Box2D units)
+
+    def momenta():
+        b = w.bodies()
+        p = np.zeros(2)
+        L = 0.0
+        for i in (1, 2):
+            m, I_c = float(bm[i, 0]), float(bm[i, 2])
+            c, v, om = b[i, 4:6].astype(np.float64), b[i, 10:12].astype(np.float64), float(b[i, 12])
+            p += m * v
+            L += I_c * om + m * (c[0] * v[1] - c[1] * v[0])
+        return p, L
+    p0, L0 = momenta()
+    q0, _ = w.get_state()
+    w.step(200, allow_sleeping=False)
+    p1, L1 = momenta()
+    q1, _ = w.get_state()
+    assert np.allclose(p1, p0, rtol=0, atol=1e-4 * np.abs(p0).max())
+    assert L1 == pytest.approx(L0, rel=2e-3)
+    assert abs(q1[3] - q0[3]) > 0.5                           # the hinge really turned
+    b = w.bodies()                                            # anchors coincide within the linear slop (Box2D units)
+    ca, sa = np.cos(b[1, 6]), np.sin(b[1, 6])
+    anchor_a = b[1, 0:2] + np.array([ca * 2.0, sa * 2.0])     # body a origin + R * (scale * axis)
+    assert np.linalg.norm(anchor_a - b[2, 0:2]) < 0.02
