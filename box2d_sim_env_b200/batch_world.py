@@ -41,7 +41,7 @@ class _ObjectInfo(C.Structure):
 ABI_SYMBOLS = [
     "b2g_last_error", "b2g_env_create", "b2g_env_load_yaml", "b2g_env_destroy", "b2g_env_add_object", "b2g_env_add_link",
     "b2g_env_add_polygon", "b2g_env_add_ball", "b2g_env_add_joint", "b2g_env_add_state", "b2g_model_create", "b2g_model_destroy",
-    "b2g_model_get_info", "b2g_model_get_object", "b2g_model_get_dof_limits", "b2g_model_get_bodies",
+    "b2g_model_get_info", "b2g_model_get_warnings", "b2g_model_get_object", "b2g_model_get_dof_limits", "b2g_model_get_bodies",
     "b2g_model_get_fixtures", "b2g_model_get_joints", "b2g_model_get_balls", "b2g_batch_get_ball_approximation",
     "b2g_batch_create", "b2g_batch_clone", "b2g_batch_destroy", "b2g_batch_set_params",
     "b2g_batch_status", "b2g_batch_stream", "b2g_batch_sync", "b2g_batch_set_state", "b2g_batch_set_state_dev",
@@ -92,6 +92,7 @@ def lib():
     L.b2g_model_destroy.restype = None
     L.b2g_model_get_info.argtypes = [vp, C.POINTER(_ModelInfo)]
     L.b2g_model_get_object.argtypes = [vp, C.c_int, C.POINTER(_ObjectInfo)]
+    L.b2g_model_get_warnings.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(C.c_int32)]
     L.b2g_model_get_dof_limits.argtypes = [vp, fp]
     L.b2g_model_get_bodies.argtypes = [vp, fp]
     L.b2g_model_get_fixtures.argtypes = [vp, ip, fp]
@@ -250,6 +251,13 @@ class Model:
             self.objects.append(dict(name=oi.name.decode(), is_robot=bool(oi.is_robot), is_static=bool(oi.is_static),
                                      n_dofs=oi.n_dofs, dof_offset=oi.dof_offset, first_body=oi.first_body,
                                      n_links=oi.n_links, n_joints=oi.n_joints, n_balls=oi.n_balls))
+
+    def warnings(self):
+        """Loader diagnostics (what the reference sends to its logger while loading + accepted stale key names)."""
+        buf = C.create_string_buffer(16384)
+        n = C.c_int32()
+        _check(lib().b2g_model_get_warnings(self.h, buf, len(buf), C.byref(n)))
+        return [l for l in buf.value.decode().split("\n") if l]
 
     def object_index(self, name):
         for i, o in enumerate(self.objects):

@@ -269,6 +269,21 @@ b2g_status b2g_model_get_info(const b2g_model* model, b2g_model_info* out) {
     return B2G_OK;
 }
 
+b2g_status b2g_model_get_warnings(const b2g_model* model, char* buf, int cap, int32_t* n_out) {
+    if (!model || !n_out || (cap > 0 && !buf)) return fail(B2G_ERR_INVALID, "null argument");
+    std::string all;
+    for (const std::string& w : model->m.warnings) {
+        all += w;
+        all += '\n';
+    }
+    *n_out = (int32_t)model->m.warnings.size();
+    if (cap > 0) {
+        strncpy(buf, all.c_str(), (size_t)cap - 1);
+        buf[cap - 1] = 0;
+    }
+    return B2G_OK;
+}
+
 b2g_status b2g_model_get_object(const b2g_model* model, int object, b2g_object_info* out) {
     if (!model || !out || object < 0 || object >= (int)model->m.objects.size()) return fail(B2G_ERR_INVALID, "unknown object");
     const HostObjectInfo& o = model->m.objects[object];

@@ -88,6 +88,10 @@ typedef struct b2g_model_info {
     float scale;
 } b2g_model_info;
 b2g_status b2g_model_get_info(const b2g_model* model, b2g_model_info* out);
+/* What the reference reports through its logger while loading (logWarn in parseYAML / createWorld, e.g. "No scale
+ * specified", Box2DIOUtils.cpp:70-84) plus this loader's own notes (stale key names accepted as aliases): the messages,
+ * one per line, copied into buf (NUL-terminated, truncated to cap); *n_out = number of messages. */
+b2g_status b2g_model_get_warnings(const b2g_model* model, char* buf, int cap, int32_t* n_out);
 
 typedef struct b2g_object_info {
     char name[64];

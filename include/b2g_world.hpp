@@ -222,6 +222,20 @@ public:
         _env = env;
         finishLoad();
     }
+    // loader diagnostics: what the reference sends to its logger while loading (getLogger()->logWarn), one per entry
+    std::vector<std::string> getLoadWarnings() const {
+        std::vector<std::string> out;
+        if (!_model) return out;
+        std::vector<char> buf(16384);
+        int32_t n = 0;
+        check(b2g_model_get_warnings(_model, buf.data(), (int)buf.size(), &n));
+        std::string all(buf.data()), line;
+        for (size_t i = 0; i < all.size(); ++i) {
+            if (all[i] == '\n') { if (!line.empty()) out.push_back(line); line.clear(); }
+            else line.push_back(all[i]);
+        }
+        return out;
+    }
     bool supportsPhysics() const { return true; }                      // (:3335-3338)
     bool isRobot(const std::string& name) const {                      // (:3202-3205)
         for (size_t i = 0; i < _objects.size(); ++i)

@@ -102,6 +102,18 @@ def test_yaml_stale_keys_are_aliased(b2g, tmp_path):
     assert np.array_equal(a.joint_model()[1], b.joint_model()[1])
 
 
+def test_loader_warnings_are_reported(b2g):
+    """The reference's own test_data still uses trans_friction / rot_friction and test_env2.yaml has no world_bounds: the
+    loader accepts them and says so (the reference would log through sim_env::Logger)."""
+    assert b2g.Model(b2g.data_path(ENV_A)).warnings() == []
+    ref = "/root/reference/test_data/test_env2.yaml"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not present on this machine")
+    w = b2g.Model(ref).warnings()
+    assert any("world bounds" in x.lower() for x in w)
+    assert any("trans_friction" in x for x in w) and any("rot_friction" in x for x in w)
+
+
 def test_yaml_errors_are_loud(b2g, tmp_path):
     with pytest.raises(b2g.B2GError) as e:
         b2g.Model(str(tmp_path / "missing.yaml"))
