@@ -163,10 +163,31 @@ Node loadFile(const std::string& path) {
     Parser p;
     std::string raw;
     int number = 0;
+    auto flowDepth = [](const std::string& t) {  // unbalanced '[' of a line (quotes respected)
+        int depth = 0;
+        bool inS = false, inD = false;
+        for (char ch : t) {
+            if (ch == '\'' && !inD) inS = !inS;
+            else if (ch == '"' && !inS) inD = !inD;
+            else if (!inS && !inD && ch == '[') ++depth;
+            else if (!inS && !inD && ch == ']') --depth;
+        }
+        return depth;
+    };
     while (std::getline(in, raw)) {
         ++number;
         if (!raw.empty() && raw.back() == '\r') raw.pop_back();
         std::string s = stripComment(raw);
+        // a flow sequence may run over several lines ("- [0.0, 0.0,\n   0.8, 0.0]"): join them
+        for (int depth = flowDepth(s); depth > 0;) {
+            std::string more;
+            if (!std::getline(in, more)) throw std::runtime_error(path + ":" + std::to_string(number) + ": unterminated flow sequence");
+            ++number;
+            if (!more.empty() && more.back() == '\r') more.pop_back();
+            more = stripComment(more);
+            depth += flowDepth(more);
+            s += " " + trim(more);
+        }
         size_t ind = 0;
         while (ind < s.size() && s[ind] == ' ') ++ind;
         std::string t = trim(s);

@@ -169,3 +169,32 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(root, f), errors="ignore").read()
                 assert "libb2o" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_yaml_formatting_variants_match_pyyaml(b2g, oracle, tmp_path):
+    """The product's own YAML-subset reader against PyYAML (the oracle's loader) on the formatting hand-written environment
+    files use: comments, quoted names, CRLF line ends, flow sequences that run over several lines, odd indentation."""
+    data = os.path.dirname(b2g.data_path(ENV_A))
+    import shutil
+    shutil.copytree(data, tmp_path / "data")
+    obj = tmp_path / "data" / "objects" / "test_object.yaml"
+    text = obj.read_text()
+    first_poly = re.search(r"- \[[^\]]*\]", text).group(0)
+    inner = first_poly[3:-1].split(",")
+    multi = "- [" + ",".join(inner[:3]) + ",   # a comment inside the sequence\n          " + ",".join(inner[3:]) + "\n        ]"
+    text = text.replace(first_poly, multi, 1)
+    text = re.sub(r"name: (\S+)", r'name: "\1"', text, count=1)
+    obj.write_text(text.replace("\n", "\r\n"))
+    env_file = tmp_path / "data" / ENV_A
+    env_file.write_text("# leading comment\n---\n" + env_file.read_text().replace("scale: 10.0", "scale:    10.0   # trailing comment"))
+    path = str(env_file)
+    m = b2g.Model(path)
+    w = oracle.OracleWorld(oracle.load_env_yaml(path))
+    ref = b2g.Model(b2g.data_path(ENV_A))
+    assert np.array_equal(m.body_model(), w.body_model()) and np.array_equal(m.body_model(), ref.body_model())
+    assert np.array_equal(m.fixture_model()[1], w.fixture_model()[1])
+    assert [o["name"] for o in m.objects] == [o["name"] for o in ref.objects]
+    bad = tmp_path / "data" / "objects" / "test_object2.yaml"
+    bad.write_text(bad.read_text().replace("]", "", 1))           # a sequence that never closes
+    with pytest.raises(b2g.B2GError):
+        b2g.Model(path)
