@@ -198,3 +198,14 @@ def test_yaml_formatting_variants_match_pyyaml(b2g, oracle, tmp_path):
     bad.write_text(bad.read_text().replace("]", "", 1))           # a sequence that never closes
     with pytest.raises(b2g.B2GError):
         b2g.Model(path)
+
+
+def test_c_header_is_plain_c(tmp_path):
+    """include/b2g.h is the C ABI: it has to compile as C99 (no C++-isms, no CUDA / torch types)."""
+    import subprocess
+    src = tmp_path / "cabi.c"
+    src.write_text('#include "b2g.h"\nint main(void) { return b2g_last_error == 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-fsyntax-only", str(src)])
+    header = open(os.path.join(ROOT, "include", "b2g.h")).read()
+    assert "torch" not in header and "cuda_runtime" not in header and "at::" not in header
