@@ -204,7 +204,7 @@ def test_c_header_is_plain_c(tmp_path):
     """include/b2g.h is the C ABI: it has to compile as C99 (no C++-isms, no CUDA / torch types)."""
     import subprocess
     src = tmp_path / "cabi.c"
-    src.write_text('#include "b2g.h"\nint main(void) { return b2g_last_error == 0; }\n')
+    src.write_text('#include "b2g.h"\nint main(void) { return b2g_last_error() == 0; }\n')
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
                            "-fsyntax-only", str(src)])
     header = open(os.path.join(ROOT, "include", "b2g.h")).read()
