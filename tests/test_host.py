@@ -208,4 +208,4 @@ def test_c_header_is_plain_c(tmp_path):
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
                            "-fsyntax-only", str(src)])
     header = open(os.path.join(ROOT, "include", "b2g.h")).read()
-    assert "torch" not in header and "cuda_runtime" not in header and "at::" not in header
+    assert "#include <torch" not in header and "cuda_runtime" not in header and "at::" not in header
