@@ -666,3 +666,85 @@ def test_cfg1_single_world_thousand_steps(b2g):
     q, _ = batch.getWorldState()
     assert abs(q[0, 0] - 5.0) < 0.6 and abs(q[0, 2] - 3.0) < 0.5      # the robot has travelled ~ v * 10 s
     assert np.all(batch.status() == 0)
+
+
+def _random_env(seed):
+    """A random environment within the loader's rules: a robot (base + 0-2 finger chains of 1-2 links, actuated revolute
+    joints with limits), 2-4 objects of 1-3 chained links (free hinges, with and without limits), one of them possibly
+    static; random convex polygons (boxes, triangles, up to two per link), masses, frictions, restitutions."""
+    rng = np.random.default_rng(seed)
+
+    def poly():
+        if rng.random() < 0.7:
+            hx, hy = rng.uniform(0.05, 0.25), rng.uniform(0.03, 0.12)
+            ox, oy = rng.uniform(-0.05, 0.05, 2)
+            return [float(v) for v in (ox - hx, oy - hy, ox + hx, oy - hy, ox + hx, oy + hy, ox - hx, oy + hy)]
+        r = rng.uniform(0.08, 0.2)
+        a = np.sort(rng.uniform(0, 2 * np.pi, 3)) + np.array([0.0, 0.4, 0.8])
+        return [float(v) for p in a for v in (r * np.cos(p), r * np.sin(p))]
+
+    def link(name):
+        return dict(name=name, geometry=[poly() for _ in range(1 + int(rng.random() < 0.3))], mass=float(rng.uniform(0.1, 3.0)),
+                    ground_friction=float(rng.choice([0.0, rng.uniform(0.01, 0.4)])), ground_torque_integral=float(rng.uniform(0.0, 0.2)),
+                    contact_friction=float(rng.uniform(0.0, 1.5)), restitution=float(rng.choice([0.0, 0.5, 1.0])), balls=[])
+
+    def joint(name, a, b, actuated):
+        lim = [0.0, 0.0] if rng.random() < 0.3 else [float(-rng.uniform(0.3, 1.5)), float(rng.uniform(0.3, 1.5))]
+        return dict(name=name, link_a=a, link_b=b, axis=[float(rng.uniform(-0.2, 0.2)), float(rng.uniform(0.05, 0.3))],
+                    axis_orientation=float(rng.uniform(-0.5, 0.5)), position_limits=lim, velocity_limits=[-10.0, 10.0],
+                    acceleration_limits=[-30.0, 30.0], joint_type="revolute", actuated=actuated)
+
+    def chain_object(name, n_chains, max_len, actuated):
+        links, joints = [link("base")], []
+        for ch in range(n_chains):
+            parent = "base"
+            for k in range(int(rng.integers(1, max_len + 1))):
+                nm = "l%d_%d" % (ch, k)
+                links.append(link(nm))
+                joints.append(joint("j%d_%d" % (ch, k), parent, nm, actuated))
+                parent = nm
+        return dict(name=name, static=False, links=links, joints=joints, base_actuation=None)
+
+    robot = chain_object("robot", int(rng.integers(0, 3)), 2, True)
+    robot["base_actuation"] = dict(translational_velocity_limits=[-2.0, 2.0], translational_acceleration_limits=[-3.0, 3.0],
+                                   rotational_velocity_limits=[-2.0, 2.0], rotational_acceleration_limits=[-2.0, 2.0], use_center_of_mass=True)
+    objects = [chain_object("obj%d" % i, int(rng.random() < 0.4), 2, False) for i in range(int(rng.integers(2, 5)))]
+    if rng.random() < 0.6:
+        objects[-1]["static"] = True
+    return dict(scale=10.0, world_bounds=[-10, -10, 10, 10], robots=[robot], objects=objects, states={})
+
+
+@pytest.mark.parametrize("seed", [101, 102, 103, 104, 105, 106])
+def test_random_models_parity(b2g, seed):
+    """The engine is generic over the model: random robots / articulated objects / static obstacles built through the
+    programmatic environment API, scattered so that they collide, stepped with random targets -- bit-exact vs the oracle."""
+    env = _random_env(seed)
+    n = 24
+    model = b2g.Model(env)
+    batch = b2g.BatchBox2DWorld(n, max_contacts=96).loadWorld(model)
+    worlds = oracle_worlds(env, n)
+    assert_same(batch, worlds, "fresh random world %d" % seed)
+    q, qd = random_states(model, n, seed=seed + 1000, spread=0.8, vel=1.5)
+    batch.setWorldState(q, qd, reset_caches=True)
+    for w, ow in enumerate(worlds):
+        ow.set_state(q[w], qd[w])
+    rng = np.random.default_rng(seed + 2000)
+    for o, info in enumerate(model.objects):          # static objects are placed by pose
+        if info["is_static"]:
+            poses = np.concatenate([rng.uniform(-0.8, 0.8, (n, 2)), rng.uniform(-3, 3, (n, 1))], 1).astype(np.float32)
+            batch.setObjectPose(o, poses)
+            for w, ow in enumerate(worlds):
+                ow.set_object_pose(o, *[float(x) for x in poses[w]])
+    assert_same(batch, worlds, "random world %d after set_state" % seed)
+    tg = random_targets(model, 0, n, seed=seed + 3000, segments=4)
+    touching = 0
+    for seg in range(4):
+        batch.setTargetVelocity(0, tg[seg])
+        batch.stepPhysics(10)
+        for w, ow in enumerate(worlds):
+            ow.set_target_velocity(0, tg[seg][w])
+            ow.step(10)
+        assert_same(batch, worlds, "random world %d, segment %d" % (seed, seg))
+        touching += int(batch.contacts(max_per_world=96)[1][..., 2].sum())
+    assert touching > 10, "random scenario %d produced too few touching contacts" % seed
+    assert np.all(batch.status() == 0)
