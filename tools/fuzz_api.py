@@ -21,7 +21,7 @@ def run(seed, env_name, n=12, n_ops=40):
         ow.set_state(q[w], qd[w])
     log = []
     for k in range(n_ops):
-        op = int(rng.integers(0, 8))
+        op = int(rng.integers(0, 11))
         if op == 0:
             s = int(rng.integers(1, 12)); sleep = bool(rng.integers(0, 2))
             batch.stepPhysics(s, True, sleep)
@@ -61,6 +61,27 @@ def run(seed, env_name, n=12, n_ops=40):
             batch.setLinkEnabled(body, en)
             for w, ow in enumerate(worlds): ow.set_link_enabled(body, bool(en[w]))
             log.append("enable body %d" % body)
+        elif op == 8:
+            s = int(rng.integers(1, 10))
+            counts, io, fo = batch.stepPhysicsRecord(s, max_per_world=64)
+            for w, ow in enumerate(worlds):
+                oio, ofo = ow.step_record(s)
+                assert counts[w] == len(oio) and np.array_equal(io[w, :len(oio)], oio) and np.array_equal(fo[w, :len(oio)], ofo), \
+                    "recorded contacts differ, world %d after %s" % (w, log[-6:])
+            log.append("stepRecord %d" % s)
+        elif op == 9:
+            box = np.sort(rng.uniform(-1.5, 1.5, (2, 2)), axis=0).astype(np.float32)
+            aabb = [float(box[0, 0]), float(box[0, 1]), float(box[1, 0]), float(box[1, 1])]
+            excl = bool(rng.integers(0, 2))
+            hits = batch.getObjects(aabb, exclude_robots=excl)
+            for w, ow in enumerate(worlds):
+                assert np.array_equal(hits[w], ow.objects_in_aabb(aabb, excl, model.n_objects)), "getObjects(aabb) differs, world %d" % w
+            log.append("getObjects")
+        elif op == 10:
+            feas = batch.isPhysicallyFeasible()
+            for w, ow in enumerate(worlds):
+                assert bool(feas[w]) == bool(ow.is_physically_feasible()), "isPhysicallyFeasible differs, world %d" % w
+            log.append("feasible")
         else:
             counts, io, fo = batch.checkCollision(max_per_world=64)
             for w, ow in enumerate(worlds):
