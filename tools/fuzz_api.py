@@ -101,6 +101,8 @@ for seed in range(lo, hi):
     env_name = [ENV_A, ENV_B, ENV_2, ENV_3][seed % 4]
     try:
         run(seed, env_name)
+    except b2g.B2GError as e:
+        print('seed', seed, 'B2GError:', str(e)[:120])
     except AssertionError as e:
         bad.append((seed, env_name, str(e)[:600]))
 print("API fuzz seeds %d..%d: %d failures" % (lo, hi, len(bad)))

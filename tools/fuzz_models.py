@@ -9,6 +9,8 @@ bad = []
 for seed in range(lo, hi):
     try:
         t.test_random_models_parity(b2g, seed)
+    except b2g.B2GError as e:
+        print('seed', seed, 'B2GError:', str(e)[:120])
     except AssertionError as e:
         if "too few touching" not in str(e):
             bad.append((seed, str(e)[:300]))
