@@ -357,3 +357,50 @@ def test_hinged_pair_conserves_momentum(oracle):
     ca, sa = np.cos(b[1, 6]), np.sin(b[1, 6])
     anchor_a = b[1, 0:2] + np.array([ca * 2.0, sa * 2.0])     # body a origin + R * (scale * axis)
     assert np.linalg.norm(anchor_a - b[2, 0:2]) < 0.02
+
+
+def test_step_translation_and_rotation_clamps(oracle):
+    """b2Island::Solve clamps the motion of one step to b2_maxTranslation = 2 and b2_maxRotation = pi/2 (Box2D units) by
+    scaling the velocity: with scale 10 and dt 0.01 a box thrown at 50 m/s covers 0.2 m in the step and leaves it at
+    20 m/s; one spun at 400 rad/s turns a quarter turn and leaves at 50 pi rad/s."""
+    env = _two_box_env(0.0)
+    env["states"]["a"] = dict(configuration=[0.0, 0.0, 0.0], velocity=[50.0, 0.0, 0.0])
+    env["states"]["b"] = dict(configuration=[0.0, 3.0, 0.0], velocity=[0.0, 0.0, 400.0])
+    w = oracle.OracleWorld(env)
+    w.step(1)
+    q, qd = w.get_state()
+    assert q[0] == pytest.approx(0.2, rel=1e-6) and qd[0] == pytest.approx(20.0, rel=1e-6)
+    assert q[5] == pytest.approx(np.pi / 2, rel=1e-6) and qd[5] == pytest.approx(50.0 * np.pi, rel=1e-6)
+    assert q[1] == 0.0 and q[3] == pytest.approx(0.0, abs=1e-6) and q[4] == pytest.approx(3.0, abs=1e-6)
+
+
+def test_restitution_needs_the_velocity_threshold(oracle):
+    """b2ContactSolver only applies restitution when the approach speed exceeds b2_velocityThreshold = 1 (Box2D units):
+    at 0.05 m/s (0.5 units) two fully elastic boxes still collide inelastically and share the momentum."""
+    env = _two_box_env(1.0)
+    env["states"]["a"] = dict(configuration=[0.0, 0.0, 0.0], velocity=[0.05, 0.0, 0.0])
+    env["states"]["b"] = dict(configuration=[0.25, 0.0, 0.0], velocity=[0.0, 0.0, 0.0])
+    w = oracle.OracleWorld(env)
+    w.step(200)
+    q, qd = w.get_state()
+    assert qd[0] + qd[3] == pytest.approx(0.05, abs=1e-6)
+    assert qd[0] == pytest.approx(0.025, abs=5e-4) and qd[3] == pytest.approx(0.025, abs=5e-4)
+
+
+def test_overlap_recovers_to_the_linear_slop(oracle):
+    """Two boxes created 1 cm inside each other: the position solver (pseudo impulses, Baumgarte 0.2, no velocity added)
+    pushes them apart until the separation of the skinned polygons is -b2_linearSlop, i.e. the faces end
+    2 * b2_polygonRadius - b2_linearSlop = 0.015 Box2D units = 1.5 mm apart, symmetrically and at rest."""
+    env = _two_box_env(0.0)
+    env["states"]["a"] = dict(configuration=[0.0, 0.0, 0.0], velocity=[0.0, 0.0, 0.0])
+    env["states"]["b"] = dict(configuration=[0.19, 0.0, 0.0], velocity=[0.0, 0.0, 0.0])
+    w = oracle.OracleWorld(env)
+    w.step(1)
+    q, _ = w.get_state()
+    assert -0.01 < q[3] - q[0] - 0.2 < 0.0015          # on its way after one step, never past the target
+    w.step(150)
+    q, qd = w.get_state()
+    assert q[3] - q[0] - 0.2 == pytest.approx(0.0015, abs=2e-6)
+    assert q[0] + q[3] == pytest.approx(0.19, abs=1e-6) and np.all(qd == 0.0)
+    # the two manifold points are corrected one after the other, which breaks the mirror symmetry by a few microns
+    assert abs(q[1]) < 5e-5 and abs(q[2]) < 5e-4 and abs(q[4]) < 5e-5 and abs(q[5]) < 5e-4
