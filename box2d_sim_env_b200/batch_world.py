@@ -42,11 +42,13 @@ ABI_SYMBOLS = [
     "b2g_last_error", "b2g_env_create", "b2g_env_load_yaml", "b2g_env_destroy", "b2g_env_add_object", "b2g_env_add_link",
     "b2g_env_add_polygon", "b2g_env_add_ball", "b2g_env_add_joint", "b2g_env_add_state", "b2g_model_create", "b2g_model_destroy",
     "b2g_model_get_info", "b2g_model_get_warnings", "b2g_model_get_object", "b2g_model_get_dof_limits", "b2g_model_get_bodies",
-    "b2g_model_get_fixtures", "b2g_model_get_joints", "b2g_model_get_balls", "b2g_batch_get_ball_approximation",
+    "b2g_model_get_fixtures", "b2g_model_get_joints", "b2g_model_get_balls", "b2g_model_set_link_property",
+    "b2g_model_get_link_property", "b2g_batch_get_ball_approximation",
     "b2g_batch_create", "b2g_batch_clone", "b2g_batch_destroy", "b2g_batch_set_params",
     "b2g_batch_status", "b2g_batch_stream", "b2g_batch_sync", "b2g_batch_set_state", "b2g_batch_set_state_dev",
     "b2g_batch_get_state", "b2g_batch_get_state_dev", "b2g_batch_set_object_pose", "b2g_batch_set_object_dofs", "b2g_batch_get_object_dofs", "b2g_batch_select_worlds", "b2g_batch_get_object_pose",
-    "b2g_batch_set_to_rest", "b2g_batch_at_rest", "b2g_batch_set_link_enabled", "b2g_batch_objects_in_aabb",
+    "b2g_batch_set_to_rest", "b2g_batch_at_rest", "b2g_batch_set_link_enabled", "b2g_batch_set_link_property",
+    "b2g_batch_get_link_property", "b2g_batch_objects_in_aabb",
     "b2g_batch_is_physically_feasible",
     "b2g_batch_set_target_velocity", "b2g_batch_set_target_velocity_dev", "b2g_batch_set_control_efforts",
     "b2g_batch_set_control_efforts_dev", "b2g_batch_step", "b2g_batch_step_record",
@@ -84,6 +86,8 @@ def lib():
     L.b2g_env_add_polygon.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, C.c_int]
     L.b2g_env_add_ball.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, C.c_float]
     L.b2g_model_get_balls.argtypes = [vp, C.c_int, ip, fp]
+    L.b2g_model_set_link_property.argtypes = [vp, C.c_int, C.c_int, C.c_float]
+    L.b2g_model_get_link_property.argtypes = [vp, C.c_int, C.c_int, fp]
     L.b2g_batch_get_ball_approximation.argtypes = [vp, C.c_int, fp]
     L.b2g_env_add_joint.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, fp, C.c_int, C.c_char_p]
     L.b2g_env_add_state.argtypes = [vp, C.c_char_p, fp, fp, C.c_int]
@@ -118,6 +122,8 @@ def lib():
     L.b2g_batch_set_to_rest.argtypes = [vp]
     L.b2g_batch_at_rest.argtypes = [vp, C.c_float, ip]
     L.b2g_batch_set_link_enabled.argtypes = [vp, C.c_int, vp, C.c_int]
+    L.b2g_batch_set_link_property.argtypes = [vp, C.c_int, C.c_int, C.c_float]
+    L.b2g_batch_get_link_property.argtypes = [vp, C.c_int, C.c_int, fp]
     L.b2g_batch_objects_in_aabb.argtypes = [vp, fp, C.c_int, vp]
     L.b2g_batch_is_physically_feasible.argtypes = [vp, ip]
     L.b2g_batch_set_target_velocity.argtypes = [vp, C.c_int, fp]
@@ -229,6 +235,11 @@ class Environment:
             self.h = None
 
 
+# Box2DLink's dynamics parameters (Box2DWorld.cpp:471-566), numbered as b2g_link_property in include/b2g.h
+LINK_PROPERTIES = dict(mass=0, ground_friction=1, ground_torque_integral=2, contact_friction=3, inertia=4,
+                       com_inertia=5, ground_friction_limit_force=6, ground_friction_limit_torque=7)
+
+
 class Model:
     """Immutable flattened model shared by the worlds of a batch (host only; no GPU needed)."""
 
@@ -296,6 +307,15 @@ class Model:
         fo = np.zeros((self.n_joints, 15), np.float32)
         _check(lib().b2g_model_get_joints(self.h, _ptr(io), _ptr(fo)))
         return io, fo
+
+    def set_link_property(self, body, prop, value):
+        """Box2DLink's setters (:478-547) applied to the model: batches created afterwards start with the new value."""
+        _check(lib().b2g_model_set_link_property(self.h, int(body), LINK_PROPERTIES[prop], float(value)))
+
+    def get_link_property(self, body, prop):
+        out = np.zeros(1, np.float32)
+        _check(lib().b2g_model_get_link_property(self.h, int(body), LINK_PROPERTIES[prop], _ptr(out)))
+        return float(out[0])
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -504,6 +524,18 @@ class BatchBox2DWorld:
             if e.shape != (self._rows(),):
                 raise B2GError(1, "enabled must be a bool or an [n_worlds] array")
             _check(lib().b2g_batch_set_link_enabled(self.h, int(body), _ptr(e), 0))
+
+    LINK_PROPERTIES = LINK_PROPERTIES
+
+    def setLinkProperty(self, body, prop, value):
+        """Box2DLink::setMass / setGroundFrictionCoefficient / setGroundFrictionTorqueIntegral / setContactFriction
+        (:478-547) for the link with body index `body` in every world (the worlds of a batch share their model)."""
+        _check(lib().b2g_batch_set_link_property(self.h, int(body), self.LINK_PROPERTIES[prop], float(value)))
+
+    def getLinkProperty(self, body, prop):
+        out = np.zeros(1, np.float32)
+        _check(lib().b2g_batch_get_link_property(self.h, int(body), self.LINK_PROPERTIES[prop], _ptr(out)))
+        return float(out[0])
 
     # -- controller (Box2DController.h:23)
     def setTargetVelocity(self, robot, velocity):

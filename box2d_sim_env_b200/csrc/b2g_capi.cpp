@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -68,6 +69,9 @@ struct SavedState {
 
 struct b2g_batch {
     HostModel m;
+    // the model as loaded: Box2DWorld::clone reloads the environment description (Box2DWorld.cpp:3030), so link parameters
+    // changed afterwards (b2g_batch_set_link_property) are not inherited by a clone
+    std::shared_ptr<const HostModel> loaded;
     int device = 0;
     long long N = 0;
     long long selFirst = 0, selCount = 0;  // b2g_batch_select_worlds: per-world calls act on [selFirst, selFirst + selCount)
@@ -345,7 +349,7 @@ b2g_status b2g_batch_clone(b2g_batch* src, b2g_batch** out) {
     if (!src || !out) return fail(B2G_ERR_INVALID, "null argument");
     if (!src->allSelected()) return fail(B2G_ERR_INVALID, "stepping and the state stack act on the whole batch: call b2g_batch_select_worlds(batch, 0, 0) first");
     b2g_batch* dst = nullptr;
-    b2g_status st = createBatch(src->m, src->N, src->device, src->m.h.maxc, &dst);
+    b2g_status st = createBatch(src->loaded ? *src->loaded : src->m, src->N, src->device, src->m.h.maxc, &dst);
     if (st) return st;
     dst->prm.dt = src->prm.dt;
     dst->prm.inv_dt = src->prm.inv_dt;
@@ -386,6 +390,7 @@ static b2g_status createBatch(const HostModel& hostModel, int64_t n_worlds, int 
     b2g_batch* b = new b2g_batch();
     b->m = hostModel;
     if (max_contacts > 0) layoutState(b->m.h, max_contacts > kMaxContacts ? kMaxContacts : max_contacts);
+    b->loaded = std::make_shared<const HostModel>(b->m);
     b->device = device;
     b->N = n_worlds;
     b->selFirst = 0;
@@ -806,6 +811,62 @@ b2g_status b2g_batch_set_link_enabled(b2g_batch* b, int body, const uint8_t* ena
     }
     CU(launchSetLinkEnabled(b->L(), body, dev, enabled_all));
     CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
+// Box2DLink::setMass / setGroundFrictionCoefficient / setGroundFrictionTorqueIntegral / setContactFriction (:478-547) for
+// link `body` of every world: the model is shared by the worlds of a batch, so the records of the batch's own model copy
+// are re-derived on the host and uploaded; setMass also runs b2Body::SetMassData's sweep-centre update on every world.
+b2g_status b2g_batch_set_link_property(b2g_batch* b, int body, int property, float value) {
+    if (!b) return fail(B2G_ERR_INVALID, "null batch");
+    if (!isLinkBody(b->m, body)) return fail(B2G_ERR_INVALID, "unknown link (body 0 is the ground)");
+    if (property < 0 || property > B2G_LINK_CONTACT_FRICTION)
+        return fail(B2G_ERR_INVALID, "this link property is derived (read-only) or unknown");
+    if (!b->allSelected())
+        return fail(B2G_ERR_INVALID, "link parameters belong to the model all worlds of the batch share: call b2g_batch_select_worlds(batch, 0, 0) first");
+    CU(cudaSetDevice(b->device));
+    bool massCenter = false;
+    try {
+        massCenter = setLinkProperty(b->m, body, property, value);
+    } catch (const std::exception& ex) {
+        return fail(B2G_ERR_INVALID, ex.what());
+    }
+    CU(cudaStreamSynchronize(b->stream));  // the blob is read by whatever was launched before
+    CU(cudaMemcpy(b->blob, b->m.blob.data(), b->m.blob.size() * 4, cudaMemcpyHostToDevice));
+    if (massCenter) {
+        CU(launchMassCenter(b->L(), body));
+        CU(cudaStreamSynchronize(b->stream));
+    }
+    return B2G_OK;
+}
+
+// the same on a model: batches created from it afterwards start with the changed parameters
+b2g_status b2g_model_set_link_property(b2g_model* m, int body, int property, float value) {
+    if (!m) return fail(B2G_ERR_INVALID, "null model");
+    if (!isLinkBody(m->m, body)) return fail(B2G_ERR_INVALID, "unknown link (body 0 is the ground)");
+    if (property < 0 || property > B2G_LINK_CONTACT_FRICTION)
+        return fail(B2G_ERR_INVALID, "this link property is derived (read-only) or unknown");
+    try {
+        setLinkProperty(m->m, body, property, value);
+    } catch (const std::exception& ex) {
+        return fail(B2G_ERR_INVALID, ex.what());
+    }
+    return B2G_OK;
+}
+
+b2g_status b2g_model_get_link_property(const b2g_model* m, int body, int property, float* out) {
+    if (!m || !out) return fail(B2G_ERR_INVALID, "null argument");
+    if (!isLinkBody(m->m, body)) return fail(B2G_ERR_INVALID, "unknown link (body 0 is the ground)");
+    if (property < 0 || property >= LP_COUNT) return fail(B2G_ERR_INVALID, "unknown link property");
+    *out = getLinkProperty(m->m, body, property);
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_get_link_property(const b2g_batch* b, int body, int property, float* out) {
+    if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
+    if (!isLinkBody(b->m, body)) return fail(B2G_ERR_INVALID, "unknown link (body 0 is the ground)");
+    if (property < 0 || property >= LP_COUNT) return fail(B2G_ERR_INVALID, "unknown link property");
+    *out = getLinkProperty(b->m, body, property);
     return B2G_OK;
 }
 

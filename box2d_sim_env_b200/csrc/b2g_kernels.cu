@@ -294,6 +294,21 @@ __global__ void k_set_link_enabled(const __grid_constant__ ModelHeader hdr, cons
     stMoved(c, ldMoved(c) | bits);
 }
 
+// Tail of b2Body::SetMassData for dynamic body `body` (Box2DLink::setMass :478-489; the mass data themselves live in the
+// model): the sweep centre is re-derived from the body transform, c0 = c, and the linear velocity follows the (round-off
+// sized) shift of the centre.
+__global__ void k_mass_center(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
+                              StepParams prm, int body) {
+    B2G_PROLOGUE();
+    const V2 oldCenter = ldV2(c, bslot(c, body, SB_CX));
+    const V2 cc = mul(ldXF(c, body), localCenter(c, body));
+    stV2(c, bslot(c, body, SB_CX), cc);
+    stV2(c, bslot(c, body, SB_C0X), cc);
+    const float wz = ldF(c, bslot(c, body, SB_W));
+    const V2 v = ldV2(c, bslot(c, body, SB_VX));
+    stV2(c, bslot(c, body, SB_VX), v + cross(wz, cc - oldCenter));
+}
+
 // Box2DWorld::atRest(threshold) (:3435-3452): every object's DOF velocities are within the threshold (infinity norm)
 __global__ void k_at_rest(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
                           StepParams prm, float threshold, int* __restrict__ out) {
@@ -562,6 +577,7 @@ cudaError_t launchSetToRest(const Launch& L) { LAUNCH(k_set_to_rest); }
 cudaError_t launchSetLinkEnabled(const Launch& L, int body, const unsigned char* enabled, int all) {
     LAUNCH(k_set_link_enabled, body, enabled, all);
 }
+cudaError_t launchMassCenter(const Launch& L, int body) { LAUNCH(k_mass_center, body); }
 cudaError_t launchAtRest(const Launch& L, float threshold, int* out) { LAUNCH(k_at_rest, threshold, out); }
 cudaError_t launchPhysicallyFeasible(const Launch& L, int* out) { LAUNCH(k_physically_feasible, out); }
 cudaError_t launchObjectsInAABB(const Launch& L, float lx, float ly, float ux, float uy, unsigned char* hits) {

@@ -219,6 +219,7 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
     const float scale = env.scale;
     if (!(scale > 0.0f)) throw std::runtime_error("scale must be positive");
     std::vector<BBody> bodies;
+    std::vector<float> linkParams;  // per body: ground_friction, ground_torque_integral, contact_friction, friction joint
     std::vector<BFix> fixtures;
     std::vector<BJoint> joints;
 
@@ -368,6 +369,11 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
             fj.maxForce = ld.ground_friction * gravity * bodyMass;
             fj.maxTorque = ld.ground_friction * ld.ground_torque_integral * scale * scale;
             fj.object = (int)oi;
+            linkParams.resize(4 * bodies.size(), 0.0f);  // rows of bodies without a link (the ground) stay zero / -1
+            linkParams.push_back(ld.ground_friction);
+            linkParams.push_back(ld.ground_torque_integral);
+            linkParams.push_back(ld.contact_friction);
+            linkParams.push_back((float)joints.size());
             joints.push_back(fj);
             bodies.push_back(b);
         }
@@ -779,6 +785,134 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
         fo[12] = joints[j].ref; fo[13] = joints[j].lower; fo[14] = joints[j].upper;
     }
     out.warnings = env.warnings;
+    linkParams.resize(4 * nb, 0.0f);
+    out.linkParams = linkParams;
+    for (int b = 0; b < nb; ++b) {
+        bool isLink = false;
+        for (int j = 0; j < nj; ++j) isLink = isLink || (joints[j].type == 0 && joints[j].bodyB == b);
+        if (!isLink) out.linkParams[4 * b + 3] = -1.0f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Box2DLink's dynamics parameters on a built model (Box2DWorld.cpp:471-566).  Every quantity the kernels read that
+// depends on them is re-derived in place: the body record (mass data), the records of the joints that touch the body
+// (inverse masses, angular / motor mass) and the link's ground-friction joint (maxForce / maxTorque).
+namespace {
+float wordF(const HostModel& m, int word) {
+    float f;
+    std::memcpy(&f, &m.blob[word], 4);
+    return f;
+}
+void setWordF(HostModel& m, int word, float f) { std::memcpy(&m.blob[word], &f, 4); }
+
+void refreshJointsOfBody(HostModel& m, int body) {
+    const ModelHeader& h = m.h;
+    for (int j = 0; j < h.nj; ++j) {
+        const int jr = h.oJoint + j * MJ_STRIDE;
+        const int a = (int)m.blob[jr + MJ_BODYA], b = (int)m.blob[jr + MJ_BODYB];
+        if (a != body && b != body) continue;
+        const float mA = wordF(m, h.oBody + a * MB_STRIDE + MB_INVMASS), iA = wordF(m, h.oBody + a * MB_STRIDE + MB_INVI);
+        const float mB = wordF(m, h.oBody + b * MB_STRIDE + MB_INVMASS), iB = wordF(m, h.oBody + b * MB_STRIDE + MB_INVI);
+        setWordF(m, jr + MJ_MA, mA); setWordF(m, jr + MJ_IA, iA); setWordF(m, jr + MJ_MB, mB); setWordF(m, jr + MJ_IB, iB);
+        float rot = iA + iB;
+        if (rot > 0.0f) rot = 1.0f / rot;
+        setWordF(m, jr + MJ_ROTMASS, rot);
+    }
+}
+
+// Box2DLink::updateFrictionJoint (:523-531): mu * mass * gravity (the ctor multiplies in the order mu * gravity * mass, :141)
+void updateFrictionJoint(HostModel& m, int body) {
+    const ModelHeader& h = m.h;
+    const int j = (int)m.linkParams[4 * body + 3];
+    const float mu = m.linkParams[4 * body], integral = m.linkParams[4 * body + 1];
+    const float gravity = 9.81f * h.scale;
+    const float mass = wordF(m, h.oBody + body * MB_STRIDE + MB_MASS);  // b2Body::GetMass(): 0 for a static body
+    const float maxForce = mu * mass * gravity;
+    const float maxTorque = mu * integral * h.scale * h.scale;
+    setWordF(m, h.oJoint + j * MJ_STRIDE + MJ_MAXFORCE, maxForce);
+    setWordF(m, h.oJoint + j * MJ_STRIDE + MJ_MAXTORQUE, maxTorque);
+    m.jointFloats[j * 15 + 6] = maxForce;
+    m.jointFloats[j * 15 + 7] = maxTorque;
+}
+}  // namespace
+
+bool isLinkBody(const HostModel& m, int body) {
+    return body >= 0 && body < m.h.nb && 4 * (size_t)body + 3 < m.linkParams.size() && m.linkParams[4 * body + 3] >= 0.0f;
+}
+
+bool setLinkProperty(HostModel& m, int body, int prop, float value) {
+    const ModelHeader& h = m.h;
+    const int br = h.oBody + body * MB_STRIDE;
+    switch (prop) {
+        case LP_MASS: {  // Box2DLink::setMass (:478-489) = b2Body::GetMassData, scale mass and I, b2Body::SetMassData
+            const bool dynamic = m.blob[br + MB_TYPE] == 2u;
+            if (dynamic) {
+                const float lcx = wordF(m, br + MB_LCX), lcy = wordF(m, br + MB_LCY);
+                const float oldMass = wordF(m, br + MB_MASS);
+                float dataI = wordF(m, br + MB_I) + oldMass * (lcx * lcx + lcy * lcy);
+                const float ratio = value / oldMass;
+                dataI = dataI * ratio;
+                float mass = value;
+                if (mass <= 0.0f) mass = 1.0f;
+                const float invMass = 1.0f / mass;
+                float I = 0.0f, invI = 0.0f;
+                if (dataI > 0.0f) {
+                    I = dataI - mass * (lcx * lcx + lcy * lcy);
+                    invI = 1.0f / I;
+                }
+                setWordF(m, br + MB_MASS, mass); setWordF(m, br + MB_INVMASS, invMass);
+                setWordF(m, br + MB_I, I); setWordF(m, br + MB_INVI, invI);
+                float* o = &m.bodyModel[body * 8];
+                o[0] = mass; o[1] = invMass; o[2] = I; o[3] = invI;
+                refreshJointsOfBody(m, body);
+            }
+            updateFrictionJoint(m, body);
+            return dynamic;  // the caller re-derives the sweep centre of dynamic bodies (b2Body::SetMassData's tail)
+        }
+        case LP_GROUND_FRICTION:
+            m.linkParams[4 * body] = value;
+            updateFrictionJoint(m, body);
+            return false;
+        case LP_GROUND_TORQUE_INTEGRAL:
+            m.linkParams[4 * body + 1] = value;
+            updateFrictionJoint(m, body);
+            return false;
+        case LP_CONTACT_FRICTION: {  // Box2DLink::setContactFriction (:538-547): b2Fixture::SetFriction on every fixture
+            m.linkParams[4 * body + 2] = value;
+            const int f0 = (int)m.blob[br + MB_FIX_START], nfix = (int)m.blob[br + MB_FIX_COUNT];
+            for (int f = f0; f < f0 + nfix; ++f) {
+                setWordF(m, h.oFix + f * MF_STRIDE + MF_FRICTION, value);
+                m.fixFloats[f * 38 + 34] = value;
+            }
+            return false;
+        }
+        default:
+            throw std::runtime_error("link property is read-only or unknown");
+    }
+}
+
+float getLinkProperty(const HostModel& m, int body, int prop) {
+    const ModelHeader& h = m.h;
+    const int br = h.oBody + body * MB_STRIDE;
+    const float mass = wordF(m, br + MB_MASS);
+    const float lcx = wordF(m, br + MB_LCX), lcy = wordF(m, br + MB_LCY);
+    const float inertia = wordF(m, br + MB_I) + mass * (lcx * lcx + lcy * lcy);  // b2Body::GetInertia
+    switch (prop) {
+        case LP_MASS: return mass;
+        case LP_GROUND_FRICTION: return m.linkParams[4 * body];
+        case LP_GROUND_TORQUE_INTEGRAL: return m.linkParams[4 * body + 1];
+        case LP_CONTACT_FRICTION: return m.linkParams[4 * body + 2];
+        case LP_INERTIA: return h.invScale * h.invScale * inertia;  // Box2DLink::getInertia (:549-555)
+        case LP_COM_INERTIA: {                                        // Box2DLink::getCOMInertia (:557-566)
+            const float comDist = std::sqrt(lcx * lcx + lcy * lcy);
+            const float comInertia = inertia - mass * comDist * comDist;
+            return h.invScale * h.invScale * comInertia;
+        }
+        case LP_LIMIT_FORCE: return m.linkParams[4 * body] * mass * 9.81f;                 // :507-510
+        case LP_LIMIT_TORQUE: return m.linkParams[4 * body] * m.linkParams[4 * body + 1];  // :502-505
+        default: throw std::runtime_error("unknown link property");
+    }
 }
 
 }  // namespace b2g

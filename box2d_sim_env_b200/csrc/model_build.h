@@ -31,7 +31,23 @@ struct HostModel {
     // walks its std::map of links, Box2DWorld.cpp:1754-1763): rows of 8 = body, origin offset x y (scaled), centre x y z, radius
     std::vector<float> balls;
     std::vector<std::string> warnings;
+    // Box2DLink's tunable dynamics parameters per body: _ground_friction, _ground_torque_integral, _contact_friction, index
+    // of the link's ground-friction joint (-1: the body is not a link, i.e. the ground)
+    std::vector<float> linkParams;    // nb x 4
 };
+
+// Box2DLink::setMass / setGroundFrictionCoefficient / setGroundFrictionTorqueIntegral / setContactFriction and the
+// matching getters (Box2DWorld.cpp:471-566), numbered as in include/b2g.h (b2g_link_property)
+enum LinkProperty {
+    LP_MASS = 0, LP_GROUND_FRICTION, LP_GROUND_TORQUE_INTEGRAL, LP_CONTACT_FRICTION,  // settable
+    LP_INERTIA, LP_COM_INERTIA, LP_LIMIT_FORCE, LP_LIMIT_TORQUE,                      // derived, read-only
+    LP_COUNT
+};
+bool isLinkBody(const HostModel& m, int body);
+// patches blob + introspection copies in place; returns true when the per-world sweep centres of `body` have to be
+// re-derived (b2Body::SetMassData on a dynamic body); throws std::runtime_error for a read-only property
+bool setLinkProperty(HostModel& m, int body, int prop, float value);
+float getLinkProperty(const HostModel& m, int body, int prop);
 
 // throws std::runtime_error (unsupported joint type, capacity, malformed description)
 void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& out);

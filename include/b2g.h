@@ -179,6 +179,36 @@ b2g_status b2g_batch_is_physically_feasible(b2g_batch* batch, int32_t* out);
  * enabled_all to every world. */
 b2g_status b2g_batch_set_link_enabled(b2g_batch* batch, int body, const uint8_t* enabled, int enabled_all);
 
+/* Box2DLink's dynamics parameters (src/sim_env/Box2DWorld.cpp:471-566).  The worlds of a batch share one model, so a
+ * setter acts on link `body` (body index, 0 = ground is not a link) of EVERY world, like calling the reference's setter on
+ * each of N worlds; the whole batch must be selected.
+ *   MASS                    setMass :478-489 (b2Body mass and inertia scaled by mass / old mass, sweep centre re-derived,
+ *                           ground-friction joint updated); no effect on the mass data of a static link, as upstream
+ *   GROUND_FRICTION         setGroundFrictionCoefficient :496-500; both this and the next run updateFrictionJoint
+ *   GROUND_TORQUE_INTEGRAL  setGroundFrictionTorqueIntegral :512-516 (:523-531: maxForce = mu m g scale, maxTorque = mu integral scale^2)
+ *   CONTACT_FRICTION        setContactFriction :538-547 (b2Fixture::SetFriction on every fixture of the link).  Contacts that
+ *                           exist at the time of the call adopt the new coefficient with their next solve; upstream they keep
+ *                           the old mixed value until they are destroyed (the reference's own TODO at :541 asks for the former)
+ * Read-only: INERTIA getInertia :549-555 (about the link origin), COM_INERTIA getCOMInertia :557-566,
+ * GROUND_FRICTION_LIMIT_FORCE :507-510 (mu m 9.81, unscaled), GROUND_FRICTION_LIMIT_TORQUE :502-505 (mu integral).
+ * Like the reference's clone (it reloads the environment description, :3030), b2g_batch_clone does not inherit changes. */
+typedef enum b2g_link_property {
+    B2G_LINK_MASS = 0,
+    B2G_LINK_GROUND_FRICTION = 1,
+    B2G_LINK_GROUND_TORQUE_INTEGRAL = 2,
+    B2G_LINK_CONTACT_FRICTION = 3,
+    B2G_LINK_INERTIA = 4,
+    B2G_LINK_COM_INERTIA = 5,
+    B2G_LINK_GROUND_FRICTION_LIMIT_FORCE = 6,
+    B2G_LINK_GROUND_FRICTION_LIMIT_TORQUE = 7
+} b2g_link_property;
+b2g_status b2g_batch_set_link_property(b2g_batch* batch, int body, int property, float value);
+b2g_status b2g_batch_get_link_property(const b2g_batch* batch, int body, int property, float* out);
+/* The same on a model (no per-world state involved): batches created from it afterwards start with the changed parameters,
+ * as if the setter had been called on every freshly loaded world. */
+b2g_status b2g_model_set_link_property(b2g_model* model, int body, int property, float value);
+b2g_status b2g_model_get_link_property(const b2g_model* model, int body, int property, float* out);
+
 /* Box2DRobotVelocityController::setTargetVelocity (src/sim_env/Box2DController.cpp:42-63) for robot
  * `object` in every world; v: [n_worlds][n_dofs of that robot].  The controller is then evaluated
  * in-kernel before every step (Box2DRobot::control, Box2DWorld.cpp:2284-2310). */

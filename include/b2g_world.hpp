@@ -380,6 +380,29 @@ public:
     void setToRest() { check(b2g_batch_set_to_rest(_batch)); }
     void setLinkEnabled(int body, bool enabled) { check(b2g_batch_set_link_enabled(_batch, body, nullptr, enabled)); }
 
+    // Box2DLink's dynamics parameters (Box2DWorld.cpp:471-566) for the link with body index `body`; the worlds of a batch
+    // share their model, so a setter reaches that link in every world (and needs the whole batch selected)
+    void setMass(int body, float mass) { check(b2g_batch_set_link_property(_batch, body, B2G_LINK_MASS, mass)); }
+    void setGroundFrictionCoefficient(int body, float mu) {
+        check(b2g_batch_set_link_property(_batch, body, B2G_LINK_GROUND_FRICTION, mu));
+    }
+    void setGroundFrictionTorqueIntegral(int body, float val) {
+        check(b2g_batch_set_link_property(_batch, body, B2G_LINK_GROUND_TORQUE_INTEGRAL, val));
+    }
+    void setContactFriction(int body, float mu) { check(b2g_batch_set_link_property(_batch, body, B2G_LINK_CONTACT_FRICTION, mu)); }
+    float getLinkProperty(int body, b2g_link_property property) const {
+        float v = 0.0f;
+        check(b2g_batch_get_link_property(_batch, body, property, &v));
+        return v;
+    }
+    float getMass(int body) const { return getLinkProperty(body, B2G_LINK_MASS); }
+    float getInertia(int body) const { return getLinkProperty(body, B2G_LINK_INERTIA); }
+    float getGroundFrictionCoefficient(int body) const { return getLinkProperty(body, B2G_LINK_GROUND_FRICTION); }
+    float getGroundFrictionTorqueIntegral(int body) const { return getLinkProperty(body, B2G_LINK_GROUND_TORQUE_INTEGRAL); }
+    float getGroundFrictionLimitForce(int body) const { return getLinkProperty(body, B2G_LINK_GROUND_FRICTION_LIMIT_FORCE); }
+    float getGroundFrictionLimitTorque(int body) const { return getLinkProperty(body, B2G_LINK_GROUND_FRICTION_LIMIT_TORQUE); }
+    float getContactFriction(int body) const { return getLinkProperty(body, B2G_LINK_CONTACT_FRICTION); }
+
     // Box2DObject::getBallApproximation (:1754-1763) of one object in every world: out[w * n_balls + k]
     std::vector<Ball> getBallApproximation(const std::string& object) {
         const int o = objectIndex(object);

@@ -69,6 +69,9 @@ def lib():
         L.b2o_world_is_physically_feasible.argtypes = [C.c_void_p]
         L.b2o_world_step_record.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.b2o_world_set_link_enabled.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.b2o_world_set_link_property.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float]
+        L.b2o_world_get_link_property.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.b2o_world_get_link_property.restype = C.c_float
         L.b2o_world_trace_islands.argtypes = [C.c_void_p, C.c_int]
         L.b2o_world_get_island_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.b2o_world_stats.argtypes = [C.c_void_p, C.c_void_p]
@@ -364,6 +367,16 @@ class OracleWorld:
 
     def set_link_enabled(self, body_index, enabled):
         lib().b2o_world_set_link_enabled(self.h, body_index, int(enabled))
+
+    # Box2DLink::setMass / setGroundFrictionCoefficient / setGroundFrictionTorqueIntegral / setContactFriction and getters
+    LINK_PROPERTIES = dict(mass=0, ground_friction=1, ground_torque_integral=2, contact_friction=3, inertia=4,
+                           com_inertia=5, ground_friction_limit_force=6, ground_friction_limit_torque=7)
+
+    def set_link_property(self, body_index, prop, value):
+        lib().b2o_world_set_link_property(self.h, body_index, self.LINK_PROPERTIES[prop], float(value))
+
+    def get_link_property(self, body_index, prop):
+        return float(lib().b2o_world_get_link_property(self.h, body_index, self.LINK_PROPERTIES[prop]))
 
     def trace_islands(self, flag=True):
         lib().b2o_world_trace_islands(self.h, int(flag))

@@ -366,6 +366,38 @@ void b2o_world_set_link_enabled(void* wp, int bodyIndex, int enabled) {
     if (l) l->setEnabled(enabled != 0);
 }
 
+// Box2DLink dynamics parameters (Box2DWorld.cpp:471-566): 0 mass, 1 ground friction coefficient, 2 ground friction torque
+// integral, 3 contact friction (settable); 4 getInertia, 5 getCOMInertia, 6 ground friction limit force, 7 limit torque
+void b2o_world_set_link_property(void* wp, int bodyIndex, int prop, float value) {
+    OWorld* w = (OWorld*)wp;
+    OLink* l = (OLink*)w->b2->bodies.at(bodyIndex)->userData;
+    if (!l) return;
+    switch (prop) {
+        case 0: l->setMass(value); break;
+        case 1: l->setGroundFrictionCoefficient(value); break;
+        case 2: l->setGroundFrictionTorqueIntegral(value); break;
+        case 3: l->setContactFriction(value); break;
+        default: break;
+    }
+}
+
+float b2o_world_get_link_property(void* wp, int bodyIndex, int prop) {
+    OWorld* w = (OWorld*)wp;
+    OLink* l = (OLink*)w->b2->bodies.at(bodyIndex)->userData;
+    if (!l) return 0.0f;
+    switch (prop) {
+        case 0: return l->getMass();
+        case 1: return l->groundFriction;
+        case 2: return l->groundTorqueIntegral;
+        case 3: return l->contactFriction;
+        case 4: return l->getInertia();
+        case 5: return l->getCOMInertia();
+        case 6: return l->getGroundFrictionLimitForce();
+        case 7: return l->getGroundFrictionLimitTorque();
+        default: return 0.0f;
+    }
+}
+
 void b2o_world_trace_islands(void* wp, int flag) { ((OWorld*)wp)->b2->traceIslands = flag != 0; }
 
 // flattened island trace of the last step: [nIslands, then per island: nb, bodies..., nj, joints..., nc, (fa,fb)...]

@@ -134,6 +134,27 @@ void OLink::updateBodyVelocities(const std::vector<float>& qd, std::vector<std::
     }
 }
 
+void OLink::setMass(float mass) {  // :478-489
+    MassData data;
+    body->GetMassData(&data);
+    float massRatio = mass / data.mass;
+    data.mass = mass;
+    data.I = data.I * massRatio;
+    body->SetMassData(&data);
+    updateFrictionJoint();
+}
+
+void OLink::updateFrictionJoint() {  // :523-531 (note the operand order: mu * mass * gravity, the ctor has mu * gravity * mass)
+    float gravity = 9.81f * world->scale;
+    frictionJoint->maxForce = groundFriction * getMass() * gravity;
+    frictionJoint->maxTorque = groundFriction * groundTorqueIntegral * world->scale * world->scale;
+}
+
+void OLink::setContactFriction(float mu) {  // :538-547; b2Fixture::SetFriction: live contacts keep their mixed value
+    contactFriction = mu;
+    for (Fixture* f : body->fixtures) f->friction = mu;
+}
+
 void OLink::setEnabled(bool e) {  // :802-822
     if (e == enabled) return;
     enabled = e;

@@ -89,6 +89,14 @@ struct OLink {
     void updateBodyVelocities(const std::vector<float>& allDofVel, std::vector<std::pair<Vec2, unsigned>>& parentJoints,
                               unsigned indexOffset);
     void setEnabled(bool e);
+    // dynamics parameters (Box2DWorld.cpp:478-547)
+    void setMass(float mass);
+    void setGroundFrictionCoefficient(float mu) { groundFriction = mu; updateFrictionJoint(); }
+    void setGroundFrictionTorqueIntegral(float v) { groundTorqueIntegral = v; updateFrictionJoint(); }
+    void setContactFriction(float mu);
+    void updateFrictionJoint();
+    float getGroundFrictionLimitTorque() const { return groundFriction * groundTorqueIntegral; }  // :502-505
+    float getGroundFrictionLimitForce() const { return groundFriction * getMass() * 9.81f; }      // :507-510
 };
 
 struct OJoint {

@@ -129,6 +129,29 @@ int main(int argc, char** argv) {
         for (size_t i = 0; i < tq.size(); ++i) bad += tq[i] != bq[i];  // stepping the clone leaves the original alone
         delete twin;
     }
+    // Box2DLink's dynamics parameters on the shared model: getters follow, the clone keeps the loaded values
+    {
+        const int body = 6;  // obj1's only link
+        const float m0 = batch.getMass(body), i0 = batch.getInertia(body);
+        batch.setMass(body, 2.0f * m0);
+        batch.setGroundFrictionCoefficient(body, 0.5f);
+        batch.setGroundFrictionTorqueIntegral(body, 0.04f);
+        batch.setContactFriction(body, 0.7f);
+        bad += std::fabs(batch.getMass(body) - 2.0f * m0) > 1e-6f || std::fabs(batch.getInertia(body) - 2.0f * i0) > 1e-6f;
+        bad += std::fabs(batch.getGroundFrictionLimitForce(body) - 0.5f * 2.0f * m0 * 9.81f) > 1e-5f;
+        bad += std::fabs(batch.getGroundFrictionLimitTorque(body) - 0.5f * 0.04f) > 1e-7f || batch.getContactFriction(body) != 0.7f;
+        BatchBox2DWorld* twin = batch.clone();
+        bad += twin->getMass(body) != m0;
+        delete twin;
+        batch.stepPhysics(2);
+        bool groundThrew = false;
+        try {
+            batch.setMass(0, 1.0f);
+        } catch (const std::exception&) {
+            groundThrew = true;
+        }
+        bad += !groundThrew;
+    }
     bool viewThrew = false;
     try {
         w3.stepPhysics(1);

@@ -764,3 +764,55 @@ def test_random_api_sequences(b2g, seed):
     except SystemExit:
         pass
     mod.run(seed, [ENV_A, ENV_B, ENV_2, ENV_3][seed % 4])
+
+
+@pytest.mark.parametrize("env_name", [ENV_A, ENV_2])
+def test_link_properties_parity(b2g, env_name):
+    """Box2DLink::setMass / setGroundFrictionCoefficient / setGroundFrictionTorqueIntegral / setContactFriction
+    (reference :478-547) on every world of a batch: the model records the kernels read (mass data, joint inverse masses,
+    motor / angular masses, ground-friction limits, fixture friction) and b2Body::SetMassData's sweep-centre update leave
+    the worlds bit-identical to oracle worlds that received the same setter calls, right away and after stepping on."""
+    n = 48
+    batch, worlds = scattered_start(b2g, env_name, n, seed=141)
+    robot_base = batch.model.objects[0]["first_body"]
+    obj1 = batch.model.objects[1]["first_body"]
+    obj2 = batch.model.objects[2]["first_body"]
+
+    def both(body, prop, value):
+        batch.setLinkProperty(body, prop, value)
+        for ow in worlds:
+            ow.set_link_property(body, prop, value)
+        assert batch.getLinkProperty(body, prop) == worlds[0].get_link_property(body, prop)
+
+    # contact friction before any contact exists (live contacts keep their mixed value upstream, see include/b2g.h)
+    both(obj1, "contact_friction", 1.3)
+    both(robot_base + 3, "contact_friction", 0.02)
+    batch.stepPhysics(12)
+    for ow in worlds:
+        ow.step(12)
+    assert_same(batch, worlds, "contact friction set before stepping")
+    both(obj1, "mass", 0.21)
+    both(robot_base, "mass", 1.7)
+    both(robot_base + 2, "mass", 0.05)
+    both(obj2, "mass", 2.0)                       # static in test_env.yaml (no-op on the body), dynamic in env2
+    both(obj1, "ground_friction", 0.45)
+    both(obj1, "ground_torque_integral", 0.03)
+    both(robot_base + 1, "ground_friction", 0.0)
+    assert_same(batch, worlds, "right after the setters (sweep centres, velocities)")
+    tg = random_targets(batch.model, 0, n, seed=143)[0]
+    batch.setTargetVelocity(0, tg)
+    for w, ow in enumerate(worlds):
+        ow.set_target_velocity(0, tg[w])
+    batch.stepPhysics(30)
+    for ow in worlds:
+        ow.step(30)
+    assert_same(batch, worlds, "30 steps after the setters")
+    assert int(batch.contacts()[0].sum()) > 10, "scenario has too few contacts"
+    # the clone reloads the environment description (reference :3030): it does not inherit the changed parameters
+    twin = batch.clone()
+    assert twin.getLinkProperty(obj1, "mass") == batch.model.get_link_property(obj1, "mass") != batch.getLinkProperty(obj1, "mass")
+    # per-world selection cannot address a parameter of the shared model
+    batch.selectWorlds(3, 5)
+    with pytest.raises(b2g.B2GError):
+        batch.setLinkProperty(obj1, "mass", 1.0)
+    batch.selectWorlds(0, 0)

@@ -209,3 +209,55 @@ def test_c_header_is_plain_c(tmp_path):
                            "-fsyntax-only", str(src)])
     header = open(os.path.join(ROOT, "include", "b2g.h")).read()
     assert "#include <torch" not in header and "cuda_runtime" not in header and "at::" not in header
+
+
+LINK_PROPS = ["mass", "ground_friction", "ground_torque_integral", "contact_friction", "inertia", "com_inertia",
+              "ground_friction_limit_force", "ground_friction_limit_torque"]
+
+
+def test_link_properties_match_oracle(b2g, oracle):
+    """Box2DLink::setMass / setGroundFrictionCoefficient / setGroundFrictionTorqueIntegral / setContactFriction
+    (Box2DWorld.cpp:478-547) applied to the model: mass data, ground-friction joint limits, fixture friction and every getter
+    agree bit for bit with the oracle's restatement (b2Body::Get/SetMassData, updateFrictionJoint), incl. static links."""
+    m = b2g.Model(b2g.data_path(ENV_A))
+    w = oracle.OracleWorld(load_env_dict(ENV_A))
+    names = {o["name"]: o for o in m.objects}
+    robot_base, obj1, obj2 = m.objects[0]["first_body"], names["obj1"]["first_body"], names["obj2"]["first_body"]
+    assert m.objects[0]["is_robot"] and names["obj2"]["is_static"]
+    edits = [(obj1, "mass", 0.37), (robot_base, "mass", 2.5), (robot_base + 2, "mass", 0.011), (obj2, "mass", 3.0),
+             (obj1, "ground_friction", 0.31), (robot_base + 1, "ground_friction", 0.0), (obj1, "ground_torque_integral", 0.07),
+             (obj2, "ground_friction", 0.9), (obj1, "contact_friction", 1.25), (robot_base, "contact_friction", 0.05),
+             (obj1, "mass", 0.5)]
+    for body, prop, value in edits:
+        m.set_link_property(body, prop, value)
+        w.set_link_property(body, prop, value)
+        assert np.array_equal(m.body_model(), w.body_model()), (body, prop)
+        assert np.array_equal(m.fixture_model()[1], w.fixture_model()[1]), (body, prop)
+        assert np.array_equal(m.joint_model()[1][:, 6:], w.joints()[1][:, 6:]), (body, prop)
+        for b in range(1, m.n_bodies):
+            for p in LINK_PROPS:
+                assert m.get_link_property(b, p) == w.get_link_property(b, p), (b, p)
+    with pytest.raises(b2g.B2GError):
+        m.set_link_property(0, "mass", 1.0)               # the ground is not a link
+    with pytest.raises(b2g.B2GError):
+        m.set_link_property(obj1, "inertia", 1.0)         # derived, read-only
+
+
+def test_link_property_known_answers(b2g):
+    """setMass scales mass and inertia by the same ratio (Box2DWorld.cpp:483-487); the ground-friction joint follows with
+    maxForce = mu m g scale, maxTorque = mu integral scale^2 (:529-530); the limit getters are unscaled (:502-510)."""
+    m = b2g.Model(b2g.data_path(ENV_A))
+    obj1 = {o["name"]: o for o in m.objects}["obj1"]["first_body"]
+    mass0, inertia0 = m.get_link_property(obj1, "mass"), m.get_link_property(obj1, "inertia")
+    m.set_link_property(obj1, "mass", 3.0 * mass0)
+    m.set_link_property(obj1, "ground_friction", 0.25)
+    m.set_link_property(obj1, "ground_torque_integral", 0.02)
+    assert m.get_link_property(obj1, "mass") == pytest.approx(3.0 * mass0, rel=1e-6)
+    assert m.get_link_property(obj1, "inertia") == pytest.approx(3.0 * inertia0, rel=1e-5)
+    assert m.body_model()[obj1, 1] == pytest.approx(1.0 / (3.0 * mass0), rel=1e-6)
+    ji, jf = m.joint_model()
+    fj = [j for j in range(m.n_joints) if ji[j, 0] == 0 and ji[j, 2] == obj1][0]
+    assert jf[fj, 6] == pytest.approx(0.25 * 3.0 * mass0 * 9.81 * m.scale, rel=1e-6)
+    assert jf[fj, 7] == pytest.approx(0.25 * 0.02 * m.scale ** 2, rel=1e-6)
+    assert m.get_link_property(obj1, "ground_friction_limit_force") == pytest.approx(0.25 * 3.0 * mass0 * 9.81, rel=1e-6)
+    assert m.get_link_property(obj1, "ground_friction_limit_torque") == pytest.approx(0.25 * 0.02, rel=1e-6)
