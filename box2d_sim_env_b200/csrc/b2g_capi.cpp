@@ -831,12 +831,10 @@ b2g_status b2g_batch_set_link_property(b2g_batch* b, int body, int property, flo
     } catch (const std::exception& ex) {
         return fail(B2G_ERR_INVALID, ex.what());
     }
-    CU(cudaStreamSynchronize(b->stream));  // the blob is read by whatever was launched before
-    CU(cudaMemcpy(b->blob, b->m.blob.data(), b->m.blob.size() * 4, cudaMemcpyHostToDevice));
-    if (massCenter) {
-        CU(launchMassCenter(b->L(), body));
-        CU(cudaStreamSynchronize(b->stream));
-    }
+    // stream order: behind whatever still reads the old blob, ahead of the sweep-centre kernel and everything after
+    CU(cudaMemcpyAsync(b->blob, b->m.blob.data(), b->m.blob.size() * 4, cudaMemcpyHostToDevice, b->stream));
+    if (massCenter) CU(launchMassCenter(b->L(), body));
+    CU(cudaStreamSynchronize(b->stream));
     return B2G_OK;
 }
 
