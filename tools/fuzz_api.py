@@ -1,5 +1,5 @@
-"""Exploration: random sequences of API calls (step, targets, efforts, DOF subsets, poses, link enable/disable, collision
-checks) on a batch, mirrored on oracle worlds, full state compared after every call.  Usage: fuzz_api.py <first_seed> <last_seed>"""
+"""Exploration: random sequences of API calls (step, targets, efforts, DOF subsets, poses, link enable/disable, link
+mass / ground friction, collision checks) on a batch, mirrored on oracle worlds, full state compared after every call.  Usage: fuzz_api.py <first_seed> <last_seed>"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -21,7 +21,7 @@ def run(seed, env_name, n=12, n_ops=40):
         ow.set_state(q[w], qd[w])
     log = []
     for k in range(n_ops):
-        op = int(rng.integers(0, 11))
+        op = int(rng.integers(0, 12))
         if op == 0:
             s = int(rng.integers(1, 12)); sleep = bool(rng.integers(0, 2))
             batch.stepPhysics(s, True, sleep)
@@ -61,6 +61,13 @@ def run(seed, env_name, n=12, n_ops=40):
             batch.setLinkEnabled(body, en)
             for w, ow in enumerate(worlds): ow.set_link_enabled(body, bool(en[w]))
             log.append("enable body %d" % body)
+        elif op == 11:
+            body = int(rng.integers(1, model.n_bodies))
+            prop = ["mass", "ground_friction", "ground_torque_integral"][int(rng.integers(0, 3))]
+            value = float(np.float32(rng.uniform(0.02, 1.5) if prop == "mass" else rng.uniform(0.0, 0.6)))
+            batch.setLinkProperty(body, prop, value)
+            for ow in worlds: ow.set_link_property(body, prop, value)
+            log.append("link %d %s = %g" % (body, prop, value))
         elif op == 8:
             s = int(rng.integers(1, 10))
             counts, io, fo = batch.stepPhysicsRecord(s, max_per_world=64)
