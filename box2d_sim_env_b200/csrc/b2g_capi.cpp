@@ -3,6 +3,7 @@
 // device every one of them fails with B2G_ERR_CUDA.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -814,6 +815,14 @@ b2g_status b2g_batch_set_link_enabled(b2g_batch* b, int body, const uint8_t* ena
     return B2G_OK;
 }
 
+// upstream asserts on these (b2IsValid, b2FrictionJoint::SetMaxForce / SetMaxTorque: force >= 0, b2Fixture friction is used
+// under a square root): refused here instead of poisoning every world of the batch with NaNs
+static const char* badLinkValue(int property, float value) {
+    if (!std::isfinite(value)) return "link parameter is not finite";
+    if (property != B2G_LINK_MASS && value < 0.0f) return "friction parameters must not be negative";
+    return nullptr;
+}
+
 // Box2DLink::setMass / setGroundFrictionCoefficient / setGroundFrictionTorqueIntegral / setContactFriction (:478-547) for
 // link `body` of every world: the model is shared by the worlds of a batch, so the records of the batch's own model copy
 // are re-derived on the host and uploaded; setMass also runs b2Body::SetMassData's sweep-centre update on every world.
@@ -824,6 +833,7 @@ b2g_status b2g_batch_set_link_property(b2g_batch* b, int body, int property, flo
         return fail(B2G_ERR_INVALID, "this link property is derived (read-only) or unknown");
     if (!b->allSelected())
         return fail(B2G_ERR_INVALID, "link parameters belong to the model all worlds of the batch share: call b2g_batch_select_worlds(batch, 0, 0) first");
+    if (const char* why = badLinkValue(property, value)) return fail(B2G_ERR_INVALID, why);
     CU(cudaSetDevice(b->device));
     bool massCenter = false;
     try {
@@ -844,6 +854,7 @@ b2g_status b2g_model_set_link_property(b2g_model* m, int body, int property, flo
     if (!isLinkBody(m->m, body)) return fail(B2G_ERR_INVALID, "unknown link (body 0 is the ground)");
     if (property < 0 || property > B2G_LINK_CONTACT_FRICTION)
         return fail(B2G_ERR_INVALID, "this link property is derived (read-only) or unknown");
+    if (const char* why = badLinkValue(property, value)) return fail(B2G_ERR_INVALID, why);
     try {
         setLinkProperty(m->m, body, property, value);
     } catch (const std::exception& ex) {

@@ -241,6 +241,10 @@ def test_link_properties_match_oracle(b2g, oracle):
         m.set_link_property(0, "mass", 1.0)               # the ground is not a link
     with pytest.raises(b2g.B2GError):
         m.set_link_property(obj1, "inertia", 1.0)         # derived, read-only
+    for prop, value in [("mass", float("nan")), ("ground_friction", -0.1), ("contact_friction", float("inf"))]:
+        with pytest.raises(b2g.B2GError):
+            m.set_link_property(obj1, prop, value)        # upstream asserts on these
+    assert np.array_equal(m.body_model(), w.body_model())   # refused calls leave the model alone
 
 
 def test_link_property_known_answers(b2g):
