@@ -37,13 +37,24 @@ class _ObjectInfo(C.Structure):
                 ("n_balls", C.c_int32)]
 
 
+class _LinkInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("object", C.c_int32), ("is_base_link", C.c_int32), ("is_static", C.c_int32),
+                ("parent_joint", C.c_int32), ("n_fixtures", C.c_int32)]
+
+
+class _JointInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("kind", C.c_int32), ("object", C.c_int32), ("body_a", C.c_int32),
+                ("body_b", C.c_int32), ("dof_index", C.c_int32), ("actuated", C.c_int32), ("limited", C.c_int32)]
+
+
 # every symbol include/b2g.h declares (tests/test_abi.py checks the library exports them all)
 ABI_SYMBOLS = [
     "b2g_last_error", "b2g_env_create", "b2g_env_load_yaml", "b2g_env_destroy", "b2g_env_add_object", "b2g_env_add_link",
     "b2g_env_add_polygon", "b2g_env_add_ball", "b2g_env_add_joint", "b2g_env_add_state", "b2g_model_create", "b2g_model_destroy",
     "b2g_model_get_info", "b2g_model_get_warnings", "b2g_model_get_object", "b2g_model_get_dof_limits", "b2g_model_get_bodies",
     "b2g_model_get_fixtures", "b2g_model_get_joints", "b2g_model_get_balls", "b2g_model_set_link_property",
-    "b2g_model_get_link_property", "b2g_batch_get_ball_approximation",
+    "b2g_model_get_link_property", "b2g_model_get_link", "b2g_model_find_link", "b2g_model_get_joint", "b2g_model_find_joint",
+    "b2g_batch_get_ball_approximation",
     "b2g_batch_create", "b2g_batch_clone", "b2g_batch_destroy", "b2g_batch_set_params",
     "b2g_batch_status", "b2g_batch_stream", "b2g_batch_sync", "b2g_batch_set_state", "b2g_batch_set_state_dev",
     "b2g_batch_get_state", "b2g_batch_get_state_dev", "b2g_batch_set_object_pose", "b2g_batch_set_object_dofs", "b2g_batch_get_object_dofs", "b2g_batch_select_worlds", "b2g_batch_get_object_pose",
@@ -96,6 +107,10 @@ def lib():
     L.b2g_model_destroy.restype = None
     L.b2g_model_get_info.argtypes = [vp, C.POINTER(_ModelInfo)]
     L.b2g_model_get_object.argtypes = [vp, C.c_int, C.POINTER(_ObjectInfo)]
+    L.b2g_model_get_link.argtypes = [vp, C.c_int, C.POINTER(_LinkInfo)]
+    L.b2g_model_find_link.argtypes = [vp, C.c_int, C.c_char_p, ip]
+    L.b2g_model_get_joint.argtypes = [vp, C.c_int, C.POINTER(_JointInfo)]
+    L.b2g_model_find_joint.argtypes = [vp, C.c_int, C.c_char_p, ip]
     L.b2g_model_get_warnings.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(C.c_int32)]
     L.b2g_model_get_dof_limits.argtypes = [vp, fp]
     L.b2g_model_get_bodies.argtypes = [vp, fp]
@@ -307,6 +322,33 @@ class Model:
         fo = np.zeros((self.n_joints, 15), np.float32)
         _check(lib().b2g_model_get_joints(self.h, _ptr(io), _ptr(fo)))
         return io, fo
+
+    def link(self, body):
+        """Name and place of the link with body index `body` (what contacts report as link_a / link_b)."""
+        li = _LinkInfo()
+        _check(lib().b2g_model_get_link(self.h, int(body), C.byref(li)))
+        return dict(name=li.name.decode(), object=li.object, is_base_link=bool(li.is_base_link), is_static=bool(li.is_static),
+                    parent_joint=li.parent_joint, n_fixtures=li.n_fixtures)
+
+    def find_link(self, obj, name):
+        """Box2DObject::getLink(name): body index of the link."""
+        obj = self.object_index(obj) if isinstance(obj, str) else obj
+        out = np.zeros(1, np.int32)
+        _check(lib().b2g_model_find_link(self.h, obj, name.encode(), _ptr(out)))
+        return int(out[0])
+
+    def joint(self, joint):
+        ji = _JointInfo()
+        _check(lib().b2g_model_get_joint(self.h, int(joint), C.byref(ji)))
+        return dict(name=ji.name.decode(), kind=ji.kind, object=ji.object, body_a=ji.body_a, body_b=ji.body_b,
+                    dof_index=ji.dof_index, actuated=bool(ji.actuated), limited=bool(ji.limited))
+
+    def find_joint(self, obj, name):
+        """Box2DObject::getJoint(name): model joint index of the revolute joint."""
+        obj = self.object_index(obj) if isinstance(obj, str) else obj
+        out = np.zeros(1, np.int32)
+        _check(lib().b2g_model_find_joint(self.h, obj, name.encode(), _ptr(out)))
+        return int(out[0])
 
     def set_link_property(self, body, prop, value):
         """Box2DLink's setters (:478-547) applied to the model: batches created afterwards start with the new value."""

@@ -3,7 +3,9 @@
 // device every one of them fails with B2G_ERR_CUDA.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -846,6 +848,71 @@ b2g_status b2g_batch_set_link_property(b2g_batch* b, int body, int property, flo
     if (massCenter) CU(launchMassCenter(b->L(), body));
     CU(cudaStreamSynchronize(b->stream));
     return B2G_OK;
+}
+
+// Names <-> indices: Box2DObject::getLink(name) / getJoint(name) / getLinks / getJoints (Box2DWorld.cpp:1411-1505) hand out
+// entities by name; here links are body indices and joints are model joint indices, these calls translate.
+b2g_status b2g_model_get_link(const b2g_model* m, int body, b2g_link_info* out) {
+    if (!m || !out) return fail(B2G_ERR_INVALID, "null argument");
+    if (!isLinkBody(m->m, body)) return fail(B2G_ERR_INVALID, "unknown link (body 0 is the ground)");
+    const HostModel& hm = m->m;
+    std::memset(out, 0, sizeof(*out));
+    const std::string& full = hm.bodyNames[body];  // "<object>/<link>"
+    const int object = (int)hm.blob[hm.h.oBody + body * MB_STRIDE + MB_OBJECT];
+    const std::string link = full.substr(std::min(full.size(), hm.objects[object].name.size() + 1));
+    std::snprintf(out->name, sizeof(out->name), "%s", link.c_str());
+    out->object = object;
+    out->is_base_link = (int)hm.blob[hm.h.oObj + object * MO_STRIDE + MO_BASE_BODY] == body;
+    out->parent_joint = -1;
+    for (int j = 0; j < hm.h.nj; ++j)
+        if (hm.jointInts[j * 6] == 1 && hm.jointInts[j * 6 + 2] == body) out->parent_joint = j;
+    out->n_fixtures = (int)hm.blob[hm.h.oBody + body * MB_STRIDE + MB_FIX_COUNT];
+    out->is_static = hm.blob[hm.h.oBody + body * MB_STRIDE + MB_TYPE] != 2u;
+    return B2G_OK;
+}
+
+b2g_status b2g_model_find_link(const b2g_model* m, int object, const char* name, int32_t* body) {
+    if (!m || !name || !body) return fail(B2G_ERR_INVALID, "null argument");
+    const HostModel& hm = m->m;
+    if (object < 0 || object >= (int)hm.objects.size()) return fail(B2G_ERR_INVALID, "unknown object");
+    const std::string full = hm.objects[object].name + "/" + name;
+    for (int b = 1; b < hm.h.nb; ++b)
+        if (hm.bodyNames[b] == full && (int)hm.blob[hm.h.oBody + b * MB_STRIDE + MB_OBJECT] == object) {
+            *body = b;
+            return B2G_OK;
+        }
+    return fail(B2G_ERR_INVALID, "object '" + hm.objects[object].name + "' has no link '" + name + "'");
+}
+
+b2g_status b2g_model_get_joint(const b2g_model* m, int joint, b2g_joint_info* out) {
+    if (!m || !out) return fail(B2G_ERR_INVALID, "null argument");
+    const HostModel& hm = m->m;
+    if (joint < 0 || joint >= hm.h.nj) return fail(B2G_ERR_INVALID, "unknown joint");
+    std::memset(out, 0, sizeof(*out));
+    std::snprintf(out->name, sizeof(out->name), "%s", hm.jointNames[joint].c_str());
+    const uint32_t* jr = &hm.blob[hm.h.oJoint + joint * MJ_STRIDE];
+    out->kind = (int32_t)jr[MJ_TYPE];
+    out->object = (int32_t)jr[MJ_OBJECT];
+    out->body_a = (int32_t)jr[MJ_BODYA];
+    out->body_b = (int32_t)jr[MJ_BODYB];
+    out->dof_index = (int32_t)jr[MJ_DOF];
+    out->actuated = (hm.jointInts[joint * 6 + 4] != 0);
+    out->limited = (hm.jointInts[joint * 6 + 5] != 0);
+    return B2G_OK;
+}
+
+b2g_status b2g_model_find_joint(const b2g_model* m, int object, const char* name, int32_t* joint) {
+    if (!m || !name || !joint) return fail(B2G_ERR_INVALID, "null argument");
+    const HostModel& hm = m->m;
+    if (object < 0 || object >= (int)hm.objects.size()) return fail(B2G_ERR_INVALID, "unknown object");
+    for (int j = 0; j < hm.h.nj; ++j) {
+        const uint32_t* jr = &hm.blob[hm.h.oJoint + j * MJ_STRIDE];
+        if (jr[MJ_TYPE] == 1u && (int)jr[MJ_OBJECT] == object && hm.jointNames[j] == name) {
+            *joint = j;
+            return B2G_OK;
+        }
+    }
+    return fail(B2G_ERR_INVALID, "object '" + hm.objects[object].name + "' has no joint '" + name + "'");
 }
 
 // the same on a model: batches created from it afterwards start with the changed parameters

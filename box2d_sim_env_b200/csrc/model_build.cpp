@@ -184,6 +184,7 @@ struct BJoint {
     int type, bodyA, bodyB, flags;
     float lax, lay, lbx, lby, ref, lower, upper, maxForce, maxTorque;
     int dof = -1, object = -1;
+    std::string name;  // revolute joints: the YAML name; ground-friction joints have none
 };
 struct BLink {
     int body;
@@ -434,6 +435,7 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
             j.maxTorque = 0.0f;
             j.dof = nq + baseDofs + (int)ob.jointList.size();
             j.object = (int)oi;
+            j.name = jd.name;
             children[j.bodyA].push_back({(int)joints.size(), j.bodyB});
             parentJointOf[j.bodyB] = (int)joints.size();
             ob.jointList.push_back((int)joints.size());
@@ -785,6 +787,8 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
         fo[12] = joints[j].ref; fo[13] = joints[j].lower; fo[14] = joints[j].upper;
     }
     out.warnings = env.warnings;
+    out.jointNames.clear();
+    for (int j = 0; j < nj; ++j) out.jointNames.push_back(joints[j].name);
     linkParams.resize(4 * nb, 0.0f);
     out.linkParams = linkParams;
     for (int b = 0; b < nb; ++b) {

@@ -19,7 +19,8 @@ struct HostModel {
     ModelHeader h;
     std::vector<uint32_t> blob;
     std::vector<HostObjectInfo> objects;
-    std::vector<std::string> bodyNames;
+    std::vector<std::string> bodyNames;   // "<object>/<link>"; body 0 is the ground
+    std::vector<std::string> jointNames;  // revolute joints: YAML name; ground-friction joints: ""
     // introspection copies (parity probes)
     std::vector<float> bodyModel;     // nb x 8
     std::vector<int32_t> fixInts;     // nf x 3

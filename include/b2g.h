@@ -117,6 +117,30 @@ b2g_status b2g_model_get_joints(const b2g_model* model, int32_t* iout, float* fo
  * bodies[n_balls] = body index of the ball's link, xyzr[n_balls][4] = centre in the link frame and radius */
 b2g_status b2g_model_get_balls(const b2g_model* model, int object, int32_t* bodies, float* xyzr);
 
+/* Names <-> indices.  The reference hands out links and joints by name (Box2DObject::getLink / getJoint / getLinks /
+ * getJoints, Box2DWorld.cpp:1411-1505; Contact::link_a / link_b are LinkPtrs); here a link is its body index (what contacts
+ * report) and a joint its model joint index (b2g_model_get_joints order). */
+typedef struct b2g_link_info {
+    char name[64];         /* the link's own name (YAML `name`) */
+    int32_t object;        /* owning object (b2g_model_get_object index) */
+    int32_t is_base_link;
+    int32_t is_static;
+    int32_t parent_joint;  /* model joint index of the revolute joint whose child link this is; -1 for the base link */
+    int32_t n_fixtures;
+} b2g_link_info;
+b2g_status b2g_model_get_link(const b2g_model* model, int body, b2g_link_info* out);
+b2g_status b2g_model_find_link(const b2g_model* model, int object, const char* name, int32_t* body);
+typedef struct b2g_joint_info {
+    char name[64];         /* YAML name; empty for the ground-friction joint of a link */
+    int32_t kind;          /* 0 ground friction, 1 revolute */
+    int32_t object;
+    int32_t body_a, body_b;  /* parent / child link (ground friction: 0 / the link) */
+    int32_t dof_index;     /* index in the world state vector, -1 for ground-friction joints */
+    int32_t actuated, limited;
+} b2g_joint_info;
+b2g_status b2g_model_get_joint(const b2g_model* model, int joint, b2g_joint_info* out);
+b2g_status b2g_model_find_joint(const b2g_model* model, int object, const char* name, int32_t* joint);
+
 /* ---------------------------------------------------------------------------------------------------
  * Batch of worlds.  b2g_batch_create == N x Box2DWorld::loadWorld (Box2DWorld.cpp:3040-3054): every world
  * starts in the state createWorld leaves (bodies placed, YAML `states` applied, nothing stepped).

@@ -380,6 +380,42 @@ public:
     void setToRest() { check(b2g_batch_set_to_rest(_batch)); }
     void setLinkEnabled(int body, bool enabled) { check(b2g_batch_set_link_enabled(_batch, body, nullptr, enabled)); }
 
+    // Box2DObject::getLink(name) / getJoint(name) / getBaseLink (Box2DWorld.cpp:1411-1505): a link is its body index (what
+    // Contact::body_a / body_b report), a joint its model joint index
+    int getLink(const std::string& object, const std::string& link) const {
+        int32_t body = -1;
+        check(b2g_model_find_link(_model, objectIndex(object), link.c_str(), &body));
+        return body;
+    }
+    int getJoint(const std::string& object, const std::string& joint) const {
+        int32_t j = -1;
+        check(b2g_model_find_joint(_model, objectIndex(object), joint.c_str(), &j));
+        return j;
+    }
+    b2g_link_info getLinkInfo(int body) const {
+        b2g_link_info info;
+        check(b2g_model_get_link(_model, body, &info));
+        return info;
+    }
+    b2g_joint_info getJointInfo(int joint) const {
+        b2g_joint_info info;
+        check(b2g_model_get_joint(_model, joint, &info));
+        return info;
+    }
+    std::string getLinkName(int body) const { return getLinkInfo(body).name; }
+    int getBaseLink(const std::string& object) const {
+        const ObjectInfo& o = _objects[objectIndex(object)];
+        for (int b = o.first_body; b < o.first_body + o.n_links; ++b)
+            if (getLinkInfo(b).is_base_link) return b;
+        throw std::logic_error("[sim_env::b2g::BatchBox2DWorld::getBaseLink] object without a base link");
+    }
+    std::vector<int> getLinks(const std::string& object) const {
+        const ObjectInfo& o = _objects[objectIndex(object)];
+        std::vector<int> links;
+        for (int b = o.first_body; b < o.first_body + o.n_links; ++b) links.push_back(b);
+        return links;
+    }
+
     // Box2DLink's dynamics parameters (Box2DWorld.cpp:471-566) for the link with body index `body`; the worlds of a batch
     // share their model, so a setter reaches that link in every world (and needs the whole batch selected)
     void setMass(int body, float mass) { check(b2g_batch_set_link_property(_batch, body, B2G_LINK_MASS, mass)); }

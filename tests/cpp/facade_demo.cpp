@@ -23,9 +23,23 @@ int main(int argc, char** argv) {
         }
         // no CUDA device: the model stage must still have succeeded and the failure must name CUDA
         bool named = std::string(e.what()).find("cuda") != std::string::npos || std::string(e.what()).find("CUDA") != std::string::npos;
-        std::printf("HOST nq=%d bodies=%d objects=%zu first=%s cuda_named=%d\n", batch.nq(), batch.numBodies(), batch.getObjects().size(),
-                    batch.getObjects().empty() ? "-" : batch.getObjects()[0].name.c_str(), (int)named);
-        return named ? 0 : 1;
+        // name lookups are model-only: Box2DObject::getLink / getJoint / getBaseLink
+        int lookup = 0;
+        try {
+            lookup = batch.getLink("obj1", "test_object_link") == 6 && batch.getBaseLink("my_robot") == 1 &&
+                     batch.getLinkName(3) == "test_robot_finger_l_2" && batch.getLinks("obj2").size() == 2 &&
+                     batch.getJointInfo(batch.getJoint("my_robot", "finger_r_joint_2")).dof_index == 6;
+            try {
+                batch.getLink("obj1", "no_such_link");
+                lookup = 0;
+            } catch (const std::runtime_error&) {
+            }
+        } catch (const std::exception&) {
+            lookup = 0;
+        }
+        std::printf("HOST nq=%d bodies=%d objects=%zu first=%s cuda_named=%d lookup=%d\n", batch.nq(), batch.numBodies(),
+                    batch.getObjects().size(), batch.getObjects().empty() ? "-" : batch.getObjects()[0].name.c_str(), (int)named, lookup);
+        return named && lookup ? 0 : 1;
     }
     if (!gpu) {
         std::printf("HOST nq=%d bodies=%d objects=%zu first=%s cuda_named=-1\n", batch.nq(), batch.numBodies(), batch.getObjects().size(),
@@ -131,7 +145,11 @@ int main(int argc, char** argv) {
     }
     // Box2DLink's dynamics parameters on the shared model: getters follow, the clone keeps the loaded values
     {
-        const int body = 6;  // obj1's only link
+        const int body = batch.getLink("obj1", "test_object_link");  // obj1's only link
+        bad += body != 6 || batch.getBaseLink("obj1") != body || batch.getLinkName(body) != "test_object_link";
+        bad += batch.getLinks("my_robot").size() != 5 || batch.getBaseLink("my_robot") != batch.getLink("my_robot", "test_robot_base");
+        const b2g_joint_info ji = batch.getJointInfo(batch.getJoint("my_robot", "finger_r_joint_2"));
+        bad += ji.dof_index != 6 || ji.body_b != batch.getLink("my_robot", "test_robot_finger_r_2") || !ji.actuated;
         const float m0 = batch.getMass(body), i0 = batch.getInertia(body);
         batch.setMass(body, 2.0f * m0);
         batch.setGroundFrictionCoefficient(body, 0.5f);

@@ -26,7 +26,7 @@ def test_facade_compiles_and_fails_loudly_without_gpu(tmp_path, b2g):
     assert out.returncode == 0, out.stdout + out.stderr
     assert "nq=11 bodies=9 objects=3 first=my_robot" in out.stdout
     if not torch.cuda.is_available():
-        assert "cuda_named=1" in out.stdout
+        assert "cuda_named=1 lookup=1" in out.stdout
 
 
 @pytest.mark.gpu

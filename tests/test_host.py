@@ -265,3 +265,33 @@ def test_link_property_known_answers(b2g):
     assert jf[fj, 7] == pytest.approx(0.25 * 0.02 * m.scale ** 2, rel=1e-6)
     assert m.get_link_property(obj1, "ground_friction_limit_force") == pytest.approx(0.25 * 3.0 * mass0 * 9.81, rel=1e-6)
     assert m.get_link_property(obj1, "ground_friction_limit_torque") == pytest.approx(0.25 * 0.02, rel=1e-6)
+
+
+def test_link_and_joint_lookup_by_name(b2g):
+    """Box2DObject::getLink(name) / getJoint(name) (Box2DWorld.cpp:1411-1505): names <-> body / joint indices, checked
+    against the YAML (test_robot.yaml: base + 2 x 2 finger links, 4 actuated limited joints in DOF order 3..6)."""
+    m = b2g.Model(b2g.data_path(ENV_A))
+    env = load_env_dict(ENV_A)
+    robot = env["robots"][0]
+    for k, ld in enumerate(robot["links"]):
+        body = m.find_link(0, ld["name"])
+        info = m.link(body)
+        assert info["name"] == ld["name"] and info["object"] == 0 and not info["is_static"]
+        assert info["is_base_link"] == (ld["name"] == robot.get("base_link", robot["links"][0]["name"]))
+        assert info["n_fixtures"] == len(ld["geometry"])
+    for k, jd in enumerate(robot["joints"]):
+        j = m.find_joint(0, jd["name"])
+        info = m.joint(j)
+        assert info["name"] == jd["name"] and info["kind"] == 1 and info["dof_index"] == 3 + k
+        assert info["body_a"] == m.find_link(0, jd["link_a"]) and info["body_b"] == m.find_link(0, jd["link_b"])
+        assert info["actuated"] == bool(jd["actuated"]) and info["limited"]
+        assert m.link(info["body_b"])["parent_joint"] == j
+    obj2 = m.object_index("obj2")
+    assert m.link(m.find_link("obj2", "test_object_link_2"))["is_static"]
+    assert m.joint(m.find_joint(obj2, "object_joint"))["dof_index"] == m.objects[obj2]["dof_offset"]
+    friction = [m.joint(j) for j in range(m.n_joints) if m.joint(j)["kind"] == 0]
+    assert len(friction) == m.n_bodies - 1 and all(f["name"] == "" and f["body_a"] == 0 and f["dof_index"] == -1 for f in friction)
+    for bad in [lambda: m.find_link(0, "nope"), lambda: m.find_joint(0, "object_joint"), lambda: m.link(0), lambda: m.joint(99),
+                lambda: m.find_link(7, "x")]:
+        with pytest.raises(b2g.B2GError):
+            bad()
