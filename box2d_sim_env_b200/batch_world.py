@@ -64,7 +64,7 @@ ABI_SYMBOLS = [
     "b2g_batch_set_target_velocity", "b2g_batch_set_target_velocity_dev", "b2g_batch_set_control_efforts",
     "b2g_batch_set_control_efforts_dev", "b2g_batch_step", "b2g_batch_step_record",
     "b2g_batch_step_guarded", "b2g_batch_rollout_dev", "b2g_batch_rollout",
-    "b2g_batch_get_bodies", "b2g_batch_get_fat_aabbs", "b2g_batch_get_joints", "b2g_batch_get_contacts",
+    "b2g_batch_get_link_states", "b2g_batch_get_bodies", "b2g_batch_get_fat_aabbs", "b2g_batch_get_joints", "b2g_batch_get_contacts",
     "b2g_batch_check_collision", "b2g_batch_check_collision_dev", "b2g_batch_save_state", "b2g_batch_restore_state", "b2g_batch_drop_state",
     "b2g_host_alloc", "b2g_host_free", "b2g_launch_count", "b2g_batch_take_kernel_ms",
 ]
@@ -151,6 +151,7 @@ def lib():
     L.b2g_batch_step_record.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, ip, fp, C.c_int]
     L.b2g_batch_step_guarded.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, ip, ip]
     L.b2g_batch_get_bodies.argtypes = [vp, fp]
+    L.b2g_batch_get_link_states.argtypes = [vp, fp]
     L.b2g_batch_get_fat_aabbs.argtypes = [vp, fp]
     L.b2g_batch_get_joints.argtypes = [vp, ip, fp]
     L.b2g_batch_get_contacts.argtypes = [vp, ip, ip, fp, C.c_int]
@@ -606,6 +607,13 @@ class BatchBox2DWorld:
         return counts, io, fo
 
     # -- parity probes
+    def getLinkStates(self):
+        """Box2DLink::getPose / getVelocityVector / getCenterOfMass of every link: [n_worlds, n_bodies, 8] =
+        pose x y theta, velocity x y omega, centre of mass x y (user units; row 0 is the ground)."""
+        out = np.zeros((self._rows(), self.model.n_bodies, 8), np.float32)
+        _check(lib().b2g_batch_get_link_states(self.h, _ptr(out)))
+        return out
+
     def bodies(self):
         out = np.zeros((self._rows(), self.model.n_bodies, 16), np.float32)
         _check(lib().b2g_batch_get_bodies(self.h, _ptr(out)))

@@ -1046,6 +1046,19 @@ b2g_status b2g_batch_get_bodies(b2g_batch* b, float* out) {
     return B2G_OK;
 }
 
+// Box2DLink::getPose / getVelocityVector / getCenterOfMass of every link of every (selected) world
+b2g_status b2g_batch_get_link_states(b2g_batch* b, float* out) {
+    if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(b->device));
+    size_t bytes = (size_t)b->n() * b->m.h.nb * 8 * 4;
+    CU(b->stageA.reserve(bytes));
+    CU(cudaMemsetAsync(b->stageA.p, 0, bytes, b->stream));  // the ground's rows
+    CU(launchGetLinks(b->L(), (float*)b->stageA.p));
+    CU(cudaMemcpyAsync(out, b->stageA.p, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
 b2g_status b2g_batch_get_fat_aabbs(b2g_batch* b, float* out) {
     if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
     CU(cudaSetDevice(b->device));

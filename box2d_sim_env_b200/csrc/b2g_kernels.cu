@@ -431,6 +431,26 @@ __global__ void k_get_balls(const __grid_constant__ ModelHeader hdr, const uint3
     }
 }
 
+// Box2DLink::getPose (:215-224), getVelocityVector (:233-241) and getCenterOfMass (:595-603) of every link:
+// out[w][body][8] = pose x y theta, velocity x y omega, centre of mass x y (user units); the ground's row is left alone
+__global__ void k_get_links(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
+                            StepParams prm, float* __restrict__ out) {
+    B2G_PROLOGUE();
+    const int nb = H().nb;
+    const float inv = H().invScale;
+    for (int b = 1; b < nb; ++b) {
+        const int o = mI(c, mbody(c, b, MB_OBJECT));
+        const bool base = mI(c, mobj(c, o, MO_BASE_BODY)) == b;  // only base links carry a _local_origin_offset (:653-671)
+        const V2 off = base ? mk(mF(c, mobj(c, o, MO_ORIGIN_X)), mF(c, mobj(c, o, MO_ORIGIN_Y))) : mk(0.0f, 0.0f);
+        const V2 pos = mul(ldXF(c, b), off);
+        const V2 v = ldV2(c, bslot(c, b, SB_VX));
+        const V2 cc = ldV2(c, bslot(c, b, SB_CX));
+        float4* r = reinterpret_cast<float4*>(out + ((size_t)w * nb + b) * 8);
+        r[0] = make_float4(inv * pos.x, inv * pos.y, ldF(c, bslot(c, b, SB_A)), inv * v.x);
+        r[1] = make_float4(inv * v.y, ldF(c, bslot(c, b, SB_W)), inv * cc.x, inv * cc.y);
+    }
+}
+
 __global__ void k_get_joints(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
                              long long N, StepParams prm, int* __restrict__ iout, float* __restrict__ fout) {
     B2G_PROLOGUE();
@@ -604,6 +624,7 @@ cudaError_t launchGetJoints(const Launch& L, int* iout, float* fout) { LAUNCH(k_
 cudaError_t launchGetBalls(const Launch& L, const float* balls, int first, int count, float* out) {
     LAUNCH(k_get_balls, balls, first, count, out);
 }
+cudaError_t launchGetLinks(const Launch& L, float* out) { LAUNCH(k_get_links, out); }
 cudaError_t launchGetContacts(const Launch& L, int* counts, int* iout, float* fout, int maxPer) {
     LAUNCH(k_get_contacts, counts, iout, fout, maxPer);
 }

@@ -40,6 +40,7 @@ cudaError_t launchSetTarget(const Launch& L, int object, const float* v);
 cudaError_t launchStep(const Launch& L, int object, const float* targets, int nTargets, int stepsPerTarget, int execCtrl,
                        int allowSleep);
 cudaError_t launchSetToRest(const Launch& L);
+cudaError_t launchGetLinks(const Launch& L, float* out);  // [N][nb][8] link pose / velocity / centre of mass
 cudaError_t launchMassCenter(const Launch& L, int body);  // b2Body::SetMassData's sweep-centre update (setMass)
 cudaError_t launchSetLinkEnabled(const Launch& L, int body, const unsigned char* enabled, int all);
 cudaError_t launchAtRest(const Launch& L, float threshold, int* out);

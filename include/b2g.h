@@ -279,6 +279,10 @@ b2g_status b2g_batch_rollout(b2g_batch* batch, int object, const float* q, const
  * object in every world: out[n_worlds][n_balls][4] = centre (world frame, user units) and radius, links in name order */
 b2g_status b2g_batch_get_ball_approximation(b2g_batch* batch, int object, float* out);
 
+/* Box2DLink::getPose (Box2DWorld.cpp:215-224), getVelocityVector (:233-241) and getCenterOfMass (:595-603) of every link:
+ * out[n_worlds][n_bodies][8] = pose x y theta, velocity x y omega, centre of mass x y (user units; row 0, the ground, is 0) */
+b2g_status b2g_batch_get_link_states(b2g_batch* batch, float* out);
+
 /* Parity probes (b2Body / b2Joint / b2Contact state).  bodies: [n_worlds][n_bodies][16] =
  * xf.p(2) xf.q.s xf.q.c c(2) a c0(2) a0 v(2) w sleepTime awake type */
 b2g_status b2g_batch_get_bodies(b2g_batch* batch, float* out);

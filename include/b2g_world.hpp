@@ -416,6 +416,13 @@ public:
         return links;
     }
 
+    // Box2DLink::getPose (:215-224), getVelocityVector (:233-241), getCenterOfMass (:595-603) of every link of every world:
+    // out[(w * numBodies() + body) * 8 + k], k = pose x y theta, velocity x y omega, centre of mass x y
+    void getLinkStates(std::vector<float>& out) {
+        out.resize((size_t)_n * _info.n_bodies * 8);
+        check(b2g_batch_get_link_states(_batch, out.data()));
+    }
+
     // Box2DLink's dynamics parameters (Box2DWorld.cpp:471-566) for the link with body index `body`; the worlds of a batch
     // share their model, so a setter reaches that link in every world (and needs the whole batch selected)
     void setMass(int body, float mass) { check(b2g_batch_set_link_property(_batch, body, B2G_LINK_MASS, mass)); }

@@ -69,6 +69,7 @@ def lib():
         L.b2o_world_is_physically_feasible.argtypes = [C.c_void_p]
         L.b2o_world_step_record.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.b2o_world_set_link_enabled.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.b2o_world_get_link_states.argtypes = [C.c_void_p, C.c_void_p]
         L.b2o_world_set_link_property.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float]
         L.b2o_world_get_link_property.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.b2o_world_get_link_property.restype = C.c_float
@@ -307,6 +308,12 @@ class OracleWorld:
         out = np.zeros(64, np.float32)
         n = lib().b2o_world_controller_efforts(self.h, obj, _ptr(out))
         return out[:n].copy()
+
+    def link_states(self):
+        """[n_bodies, 8]: Box2DLink::getPose(3), getVelocityVector(3), getCenterOfMass(2); row 0 (ground) is 0"""
+        out = np.zeros((self.n_bodies, 8), np.float32)
+        lib().b2o_world_get_link_states(self.h, _ptr(out))
+        return out
 
     def bodies(self):
         """[n_bodies, 16]: xf.p(2) xf.q.s xf.q.c c(2) a c0(2) a0 v(2) w sleepTime awake type"""

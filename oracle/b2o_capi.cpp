@@ -233,6 +233,20 @@ void b2o_world_object_info(void* wp, int objIdx, int* info6, char* nameOut, int 
 }
 
 // 16 floats per body: xf.p(2) xf.q.s xf.q.c c(2) a c0(2) a0 v(2) w sleepTime awake type
+// Box2DLink::getPose / getVelocityVector / getCenterOfMass per link: out[n_bodies][8], the ground's row stays 0
+void b2o_world_get_link_states(void* wp, float* out) {
+    OWorld* w = (OWorld*)wp;
+    for (Body* b : w->b2->bodies) {
+        OLink* l = (OLink*)b->userData;
+        float* o = out + 8 * b->index;
+        for (int i = 0; i < 8; ++i) o[i] = 0.0f;
+        if (!l) continue;
+        l->getPose(o);
+        l->getVelocityVector(o + 3);
+        l->getCenterOfMass(o + 6);
+    }
+}
+
 void b2o_world_get_bodies(void* wp, float* out) {
     OWorld* w = (OWorld*)wp;
     for (Body* b : w->b2->bodies) {

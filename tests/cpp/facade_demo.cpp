@@ -158,6 +158,12 @@ int main(int argc, char** argv) {
         bad += std::fabs(batch.getMass(body) - 2.0f * m0) > 1e-6f || std::fabs(batch.getInertia(body) - 2.0f * i0) > 1e-6f;
         bad += std::fabs(batch.getGroundFrictionLimitForce(body) - 0.5f * 2.0f * m0 * 9.81f) > 1e-5f;
         bad += std::fabs(batch.getGroundFrictionLimitTorque(body) - 0.5f * 0.04f) > 1e-7f || batch.getContactFriction(body) != 0.7f;
+        std::vector<float> links;
+        batch.getLinkStates(links);
+        float pose[3];
+        batch.world(5).getObject("obj1").getPose(pose);
+        const float* row = &links[((size_t)5 * batch.numBodies() + body) * 8];
+        bad += links.size() != (size_t)n * batch.numBodies() * 8 || row[0] != pose[0] || row[1] != pose[1] || row[2] != pose[2];
         BatchBox2DWorld* twin = batch.clone();
         bad += twin->getMass(body) != m0;
         delete twin;

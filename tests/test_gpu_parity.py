@@ -817,3 +817,28 @@ def test_link_properties_parity(b2g, env_name):
     with pytest.raises(b2g.B2GError):
         batch.setLinkProperty(obj1, "mass", 1.0)
     batch.selectWorlds(0, 0)
+
+
+@pytest.mark.parametrize("env_name", [ENV_A, ENV_B, ENV_2])
+def test_link_states_parity(b2g, env_name):
+    """Box2DLink::getPose / getVelocityVector / getCenterOfMass (reference :215-241, 595-603) of every link of every world,
+    bit-identical to the oracle's links after a contact-rich rollout; also on a selected sub-range of worlds."""
+    n = 40
+    batch, worlds = scattered_start(b2g, env_name, n, seed=151)
+    batch.stepPhysics(30)
+    for ow in worlds:
+        ow.step(30)
+    ls = batch.getLinkStates()
+    assert ls.shape == (n, batch.model.n_bodies, 8)
+    for w, ow in enumerate(worlds):
+        assert np.array_equal(ls[w], ow.link_states()), "world %d" % w
+    assert np.abs(ls[:, 1:, 3:6]).max() > 0.01                 # something moves
+    batch.selectWorlds(7, 5)
+    assert np.array_equal(batch.getLinkStates(), ls[7:12])
+    batch.selectWorlds(0, 0)
+    # base link pose == the object's pose DOFs (what getWorldState reports)
+    q, _ = batch.getWorldState()
+    for o in batch.model.objects:
+        if not o["is_static"]:
+            base = [b for b in range(o["first_body"], o["first_body"] + o["n_links"]) if batch.model.link(b)["is_base_link"]][0]
+            assert np.array_equal(ls[:, base, :3], q[:, o["dof_offset"]:o["dof_offset"] + 3])

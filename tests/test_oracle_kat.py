@@ -404,3 +404,22 @@ def test_overlap_recovers_to_the_linear_slop(oracle):
     assert q[0] + q[3] == pytest.approx(0.19, abs=1e-6) and np.all(qd == 0.0)
     # the two manifold points are corrected one after the other, which breaks the mirror symmetry by a few microns
     assert abs(q[1]) < 5e-5 and abs(q[2]) < 5e-4 and abs(q[4]) < 5e-5 and abs(q[5]) < 5e-4
+
+
+def test_link_states_known_answers(oracle):
+    """Box2DLink::getPose / getVelocityVector / getCenterOfMass: a dynamic object's base link has its origin at the centre of
+    mass (setOriginToCenterOfMass), so pose == centre of mass == the object's base DOFs; a finger link sits at its parent's
+    joint anchor (test_robot.yaml axis [-0.3, 0.2] relative to the base link origin before the origin moved to the COM)."""
+    w = oracle.OracleWorld(load_env_dict(ENV_A))
+    q, qd = w.get_state()
+    ls = w.link_states()
+    assert not ls[0].any()                                                    # the ground is not a link
+    assert np.allclose(ls[1, :3], q[0:3], atol=1e-6) and np.allclose(ls[1, 6:8], q[0:2], atol=1e-6)
+    assert np.allclose(ls[6, :3], q[7:10], atol=1e-6) and np.allclose(ls[6, 6:8], q[7:9], atol=1e-6)
+    assert np.allclose(ls[6, 3:6], qd[7:10], atol=1e-6)
+    assert np.allclose(ls[2, 0], -0.3, atol=1e-6) and np.allclose(ls[4, 0], 0.3, atol=1e-6)   # finger roots mirror each other
+    assert ls[2, 1] == pytest.approx(ls[4, 1], abs=1e-6)
+    assert np.allclose(ls[3, :2] - ls[2, :2], [0.0, 0.35], atol=1e-5)          # second finger joint 0.35 m up the first link
+    # YAML initial velocity of finger_l_joint_2 (index 4): the outer link turns about its joint, its COM 0.1 m further out
+    assert ls[3, 5] == pytest.approx(qd[4] + qd[3] + qd[2], abs=1e-5)
+    assert ls[3, 3] == pytest.approx(-ls[3, 5] * (ls[3, 7] - ls[3, 1]), abs=1e-5)
