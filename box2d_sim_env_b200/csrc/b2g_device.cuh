@@ -597,7 +597,13 @@ DEV void addPair(Ctx c, int a, int b) {
     st4(c, cn + SC_HEAD4, mk4(__int_as_float(key), __int_as_float(CF_ENABLED), 0.0f, 1.0f));
     const float4 zero = mk4(0.0f, 0.0f, 0.0f, 0.0f);
     st4(c, cn + SC_ID4, zero);
-    st4(c, cn + SC_LP4, zero);
+    {   // b2Contact::b2Contact: the mixed coefficients are fixed when the contact is created (b2Fixture::SetFriction does
+        // not reach live contacts; Box2DLink::setContactFriction, Box2DWorld.cpp:538-547)
+        const float2 frA = m2(c, mfix(c, a, MF_FRICTION)), frB = m2(c, mfix(c, b, MF_FRICTION));  // friction, restitution
+        const float friction = sqrtf(frA.x * frB.x);                  // b2MixFriction
+        const float restitution = frA.y > frB.y ? frA.y : frB.y;      // b2MixRestitution
+        st4(c, cn + SC_LP4, mk4(0.0f, 0.0f, friction, restitution));
+    }
     st4(c, cn + SC_P04, zero);
     st4(c, cn + SC_P14, zero);
     stI(c, sslot(c, SS_NCONTACTS), n + 1);

@@ -529,7 +529,7 @@ DEVN void contactInit(Ctx c, int k, float dtRatio, bool warmStarting) {
     const float4 head = ld4(c, ck + SC_HEAD4);
     const float4 idn = ld4(c, ck + SC_ID4);
     const int fA = __float_as_int(head.x) & 0xff, fB = (__float_as_int(head.x) >> 8) & 0xff;
-    const float4 fmA = m4(c, mfix(c, fA, MF_BODY));  // body count friction restitution
+    const float4 fmA = m4(c, mfix(c, fA, MF_BODY));  // body count - -
     const float4 fmB = m4(c, mfix(c, fB, MF_BODY));
     const int bA = __float_as_int(fmA.x), bB = __float_as_int(fmB.x);
     int man = __float_as_int(head.z);
@@ -550,11 +550,12 @@ DEVN void contactInit(Ctx c, int k, float dtRatio, bool warmStarting) {
     xfB.q = warmStarting ? ldRotAt(c, bslot(c, bB, 0)) : rotOf(PB.a);
     xfA.p = PA.c - mul(xfA.q, mk(bmA.z, bmA.w));
     xfB.p = PB.c - mul(xfB.q, mk(bmB.z, bmB.w));
-    float restitution = fmA.w > fmB.w ? fmA.w : fmB.w;        // b2MixRestitution
-    float friction = sqrtf(fmA.z * fmB.z);                     // b2MixFriction
+    const float4 lpf = ld4(c, ck + SC_LP4);  // localPoint, b2Contact::m_friction, m_restitution (mixed at creation, addPair)
+    float restitution = lpf.w;
+    float friction = lpf.z;
     // b2WorldManifold::Initialize
     V2 localNormal = mk(idn.z, idn.w);
-    V2 localPoint = ldV2(c, ck + SC_LPX);
+    V2 localPoint = mk(lpf.x, lpf.y);
     float4 pts[2];
     pts[0] = ld4(c, ck + SC_P04);
     pts[1] = ld4(c, ck + SC_P14);

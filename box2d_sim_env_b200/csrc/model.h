@@ -172,6 +172,7 @@ enum ContactState {
     SC_TOI = B2G_F(0, 3),
     SC_ID0 = B2G_F(1, 0), SC_ID1 = B2G_F(1, 1), SC_LNX = B2G_F(1, 2), SC_LNY = B2G_F(1, 3),
     SC_LPX = B2G_F(2, 0), SC_LPY = B2G_F(2, 1),
+    SC_FRICTION = B2G_F(2, 2), SC_RESTITUTION = B2G_F(2, 3),  // b2Contact::m_friction / m_restitution, mixed at creation
     SC_P0X = B2G_F(3, 0), SC_P0Y = B2G_F(3, 1), SC_N0 = B2G_F(3, 2), SC_T0 = B2G_F(3, 3),
     SC_P1X = B2G_F(4, 0), SC_P1Y = B2G_F(4, 1), SC_N1 = B2G_F(4, 2), SC_T1 = B2G_F(4, 3),
     SC_HEAD4 = B2G_F(0, 0), SC_ID4 = B2G_F(1, 0), SC_LP4 = B2G_F(2, 0), SC_P04 = B2G_F(3, 0), SC_P14 = B2G_F(4, 0),

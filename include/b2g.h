@@ -210,9 +210,9 @@ b2g_status b2g_batch_set_link_enabled(b2g_batch* batch, int body, const uint8_t*
  *                           ground-friction joint updated); no effect on the mass data of a static link, as upstream
  *   GROUND_FRICTION         setGroundFrictionCoefficient :496-500; both this and the next run updateFrictionJoint
  *   GROUND_TORQUE_INTEGRAL  setGroundFrictionTorqueIntegral :512-516 (:523-531: maxForce = mu m g scale, maxTorque = mu integral scale^2)
- *   CONTACT_FRICTION        setContactFriction :538-547 (b2Fixture::SetFriction on every fixture of the link).  Contacts that
- *                           exist at the time of the call adopt the new coefficient with their next solve; upstream they keep
- *                           the old mixed value until they are destroyed (the reference's own TODO at :541 asks for the former)
+ *   CONTACT_FRICTION        setContactFriction :538-547 (b2Fixture::SetFriction on every fixture of the link).  As upstream,
+ *                           contacts that exist at the time of the call keep the coefficient they were created with
+ *                           (b2Contact mixes friction and restitution in its constructor); later contacts use the new one
  * Read-only: INERTIA getInertia :549-555 (about the link origin), COM_INERTIA getCOMInertia :557-566,
  * GROUND_FRICTION_LIMIT_FORCE :507-510 (mu m 9.81, unscaled), GROUND_FRICTION_LIMIT_TORQUE :502-505 (mu integral).
  * Like the reference's clone (it reloads the environment description, :3030), b2g_batch_clone does not inherit changes. */

@@ -785,7 +785,7 @@ def test_link_properties_parity(b2g, env_name):
             ow.set_link_property(body, prop, value)
         assert batch.getLinkProperty(body, prop) == worlds[0].get_link_property(body, prop)
 
-    # contact friction before any contact exists (live contacts keep their mixed value upstream, see include/b2g.h)
+    # contact friction before any contact exists
     both(obj1, "contact_friction", 1.3)
     both(robot_base + 3, "contact_friction", 0.02)
     batch.stepPhysics(12)
@@ -809,6 +809,17 @@ def test_link_properties_parity(b2g, env_name):
         ow.step(30)
     assert_same(batch, worlds, "30 steps after the setters")
     assert int(batch.contacts()[0].sum()) > 10, "scenario has too few contacts"
+    # contact friction with contacts alive: like upstream (b2Contact mixes the coefficients when it is created) they keep
+    # the old value until they end, contacts that begin later use the new one
+    touching_before = int(batch.contacts()[1][..., 2].sum())
+    both(obj1, "contact_friction", 0.01)
+    both(batch.model.n_bodies - 1, "contact_friction", 1.9)   # the last link (env2's robot is one rigid link)
+    both(robot_base, "contact_friction", 0.6)
+    batch.stepPhysics(25)
+    for ow in worlds:
+        ow.step(25)
+    assert_same(batch, worlds, "25 steps after changing contact friction under live contacts")
+    assert touching_before > 0
     # the clone reloads the environment description (reference :3030): it does not inherit the changed parameters
     twin = batch.clone()
     assert twin.getLinkProperty(obj1, "mass") == batch.model.get_link_property(obj1, "mass") != batch.getLinkProperty(obj1, "mass")
