@@ -443,12 +443,12 @@ def run_ours(args):
 # launch of the config's default world count (profiles/r1e_<config>_<worlds>_k_step_ncu_full.txt)
 # smsp__issue_active.avg.pct_of_peak_sustained_active of the same captures: the path is bound by issue slots / dependent
 # latency, not by HBM, so the SM issue utilisation is reported next to the HBM fraction
-MEASURED_ISSUE_ACTIVE_PCT = {"cfg2": 21.7, "cfg3": 38.9, "cfg4": 26.7}
+MEASURED_ISSUE_ACTIVE_PCT = {"cfg2": 21.6, "cfg3": 38.9, "cfg4": 26.7}
 
 MEASURED_TRAFFIC = {
     # 4096 worlds: the 32 MB state stays L2-resident across the 100 steps of a launch, DRAM sees far less than the
-    # algorithmic bytes (6.44 MB read + 0.51 MB written)
-    "cfg2": 6435840 + 507392,
+    # algorithmic bytes (6.44 MB read + 0.46 MB written; profiles/r1f_cfg2_4096_k_step_ncu_full.txt)
+    "cfg2": 6444800 + 456960,
     # 65536 rigid-robot worlds: 31.6 MB read + 24.5 MB written -- the touched part of the state stays in L2 as well
     "cfg3": 31556352 + 24489728,
     # 65536 clutter worlds: the ~9 KB a step touches per world (590 MB for the batch) does not fit the 126 MB L2, every
