@@ -6,6 +6,7 @@
 // (/root/reference/CMakeLists.txt:54-59: -O3, no -march, no fast-math).
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdlib>
 
 #include "b2g_launch.h"
@@ -529,8 +530,9 @@ __global__ void k_status(float* S, long long N, int stateChunks, int statusOff, 
 // ---------------------------------------------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------------------------------------------
-static unsigned long long g_launches = 0;
-unsigned long long launchCount() { return g_launches; }
+// batches may be driven from different host threads (one stream per batch): the launch counter is shared
+static std::atomic<unsigned long long> g_launches{0};
+unsigned long long launchCount() { return g_launches.load(std::memory_order_relaxed); }
 
 static size_t smemPad() {  // tuning knob: extra dynamic shared memory per CTA throttles occupancy (B2G_SMEM_PAD bytes)
     static long pad = -1;
