@@ -423,3 +423,89 @@ def test_link_states_known_answers(oracle):
     # YAML initial velocity of finger_l_joint_2 (index 4): the outer link turns about its joint, its COM 0.1 m further out
     assert ls[3, 5] == pytest.approx(qd[4] + qd[3] + qd[2], abs=1e-5)
     assert ls[3, 3] == pytest.approx(-ls[3, 5] * (ls[3, 7] - ls[3, 1]), abs=1e-5)
+
+
+def test_ground_friction_torque_decelerates_spin(oracle):
+    """The angular row of b2FrictionJoint: a spinning box loses mu * torque_integral / I per second (maxTorque =
+    mu * integral * scale^2 in Box2D units, Box2DWorld.cpp:145; inertia scales with scale^2 as well), and setMass /
+    setGroundFrictionTorqueIntegral (:478-531) change that rate the way the formula says."""
+    env = _two_box_env(0.0)
+    link = env["objects"][0]["links"][0]
+    link["ground_friction"], link["ground_torque_integral"] = 0.2, 0.004
+    env["states"]["a"] = dict(configuration=[0.0, 0.0, 0.0], velocity=[0.0, 0.0, 3.0])
+    env["states"]["b"] = dict(configuration=[0.0, 3.0, 0.0], velocity=[0.0, 0.0, 0.0])
+    w = oracle.OracleWorld(env)
+    inertia = w.get_link_property(1, "com_inertia")                     # 0.5 kg, 0.2 m square: m (w^2 + h^2) / 12
+    assert inertia == pytest.approx(0.5 * (0.2 ** 2 + 0.2 ** 2) / 12.0, rel=1e-5)
+    w.step(50)
+    _, qd = w.get_state()
+    rate = 0.2 * 0.004 / inertia
+    assert qd[2] == pytest.approx(3.0 - rate * 0.5, rel=1e-3) and qd[0] == 0.0 and qd[1] == 0.0
+    w.set_link_property(1, "mass", 1.0)                                 # twice the mass -> twice the inertia -> half the rate
+    w.set_link_property(1, "ground_torque_integral", 0.002)             # and half the torque
+    w0 = qd[2]
+    w.step(50)
+    _, qd = w.get_state()
+    assert qd[2] == pytest.approx(w0 - 0.25 * rate * 0.5, rel=1e-3)
+
+
+def test_joint_effort_is_a_constant_torque(oracle):
+    """Box2DJoint::setControlTorque (Box2DWorld.cpp:1198-1222): motor speed +-FLT_MAX with maxMotorTorque = scale^2 |tau|
+    makes the revolute motor saturate every step, i.e. it applies the constant torque tau.  With a base 10^4 times heavier
+    than the arm, no ground friction and no limits, the arm spins up at tau / I_anchor (inertia of the arm about the hinge:
+    m (w^2 + h^2) / 12 + m d^2, hinge at the arm's end) and the base takes the opposite angular momentum."""
+    def link(name, poly, mass):
+        return dict(name=name, geometry=[poly], mass=mass, ground_friction=0.0, ground_torque_integral=0.0, contact_friction=0.0,
+                    restitution=0.0, balls=[])
+    arm_m, arm_w, arm_h = 0.3, 0.1, 0.4
+    robot = dict(name="r", static=False,
+                 links=[link("base", [-0.5, -0.5, 0.5, -0.5, 0.5, 0.5, -0.5, 0.5], 3000.0),
+                        link("arm", [-arm_w / 2, 0.0, arm_w / 2, 0.0, arm_w / 2, arm_h, -arm_w / 2, arm_h], arm_m)],
+                 joints=[dict(name="hinge", link_a="base", link_b="arm", axis=[0.0, 0.6], axis_orientation=0.0, position_limits=[0.0, 0.0],
+                              velocity_limits=[-100.0, 100.0], acceleration_limits=[-1000.0, 1000.0], joint_type="revolute",
+                              actuated=True)],
+                 base_actuation=dict(translational_velocity_limits=[-2.0, 2.0], translational_acceleration_limits=[-2.0, 2.0],
+                                     rotational_velocity_limits=[-2.0, 2.0], rotational_acceleration_limits=[-2.0, 2.0],
+                                     use_center_of_mass=True))
+    env = dict(scale=10.0, world_bounds=[-5, -5, 5, 5], robots=[robot], objects=[],
+               states={"r": dict(configuration=[0.0, 0.0, 0.0, 0.0], velocity=[0.0, 0.0, 0.0, 0.0])})
+    w = oracle.OracleWorld(env)
+    tau = 0.02
+    w.set_control_efforts(0, np.array([0.0, 0.0, 0.0, tau], np.float32))
+    w.step(40)
+    q, qd = w.get_state()
+    i_anchor = arm_m * (arm_w ** 2 + arm_h ** 2) / 12.0 + arm_m * (arm_h / 2) ** 2
+    assert qd[3] == pytest.approx(tau / i_anchor * 0.4, rel=5e-3)                  # joint speed after 0.4 s
+    assert q[3] == pytest.approx(0.5 * tau / i_anchor * 0.4 ** 2, rel=3e-2)        # semi-implicit Euler: within a step's worth
+    assert abs(qd[2]) < 1e-3 * abs(qd[3])                                          # the heavy base hardly turns
+
+
+def test_base_effort_is_a_force_on_the_robot(oracle):
+    """Box2DRobot::commandEfforts (Box2DWorld.cpp:2319-2379): base efforts are a force scale * f at the base link's centre
+    of mass and a torque scale^2 * tau.  Whatever the hinge does, Newton's second law for the whole robot holds: the total
+    linear momentum after t seconds is f t (user units), and with a force through the base COM alone the free arm lags."""
+    def link(name, poly, mass):
+        return dict(name=name, geometry=[poly], mass=mass, ground_friction=0.0, ground_torque_integral=0.0, contact_friction=0.0,
+                    restitution=0.0, balls=[])
+    robot = dict(name="r", static=False,
+                 links=[link("base", [-0.2, -0.2, 0.2, -0.2, 0.2, 0.2, -0.2, 0.2], 2.0),
+                        link("arm", [-0.05, 0.0, 0.05, 0.0, 0.05, 0.4, -0.05, 0.4], 0.5)],
+                 joints=[dict(name="hinge", link_a="base", link_b="arm", axis=[0.0, 0.3], axis_orientation=0.0, position_limits=[0.0, 0.0],
+                              velocity_limits=[-100.0, 100.0], acceleration_limits=[-1000.0, 1000.0], joint_type="revolute",
+                              actuated=True)],
+                 base_actuation=dict(translational_velocity_limits=[-20.0, 20.0], translational_acceleration_limits=[-20.0, 20.0],
+                                     rotational_velocity_limits=[-20.0, 20.0], rotational_acceleration_limits=[-20.0, 20.0],
+                                     use_center_of_mass=True))
+    env = dict(scale=10.0, world_bounds=[-5, -5, 5, 5], robots=[robot], objects=[],
+               states={"r": dict(configuration=[0.0, 0.0, 0.0, 0.0], velocity=[0.0, 0.0, 0.0, 0.0])})
+    w = oracle.OracleWorld(env)
+    f = np.array([1.5, -0.5], np.float64)
+    w.set_control_efforts(0, np.array([f[0], f[1], 0.0, 0.0], np.float32))
+    w.step(30)
+    bm, b = w.body_model(), w.bodies()
+    p = sum(float(bm[i, 0]) * b[i, 10:12].astype(np.float64) for i in (1, 2)) / 10.0        # Box2D units -> user units
+    assert np.allclose(p, f * 0.3, rtol=2e-4)
+    ls = w.link_states()
+    assert ls[1, 3] > ls[2, 3] > 0.0                       # pulled along through the hinge, the arm's COM lags behind the base
+    assert np.allclose(ls[2, :2] - ls[1, :2], np.array([0.0, 0.3]) @ np.array([[np.cos(ls[1, 2]), np.sin(ls[1, 2])],
+                                                                               [-np.sin(ls[1, 2]), np.cos(ls[1, 2])]]), atol=2e-3)
