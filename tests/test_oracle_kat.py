@@ -509,3 +509,26 @@ def test_base_effort_is_a_force_on_the_robot(oracle):
     assert ls[1, 3] > ls[2, 3] > 0.0                       # pulled along through the hinge, the arm's COM lags behind the base
     assert np.allclose(ls[2, :2] - ls[1, :2], np.array([0.0, 0.3]) @ np.array([[np.cos(ls[1, 2]), np.sin(ls[1, 2])],
                                                                                [-np.sin(ls[1, 2]), np.cos(ls[1, 2])]]), atol=2e-3)
+
+
+def test_velocity_controller_ramps_at_the_acceleration_limit(oracle):
+    """Box2DRobotVelocityController::control (Box2DController.cpp:65-117): effort = mass * clamp((v* - v) / dt, accel limits)
+    with mass = the robot's total mass (Box2DObject::_mass), applied as a force on the base link.  Far from the target the
+    clamp is active, so without ground friction the robot's centre of mass accelerates at exactly the limit
+    (test_robot.yaml: 2 m/s^2): total momentum = M a t."""
+    env = load_env_dict(ENV_A)
+    for l in env["robots"][0]["links"]:
+        l["ground_friction"] = 0.0
+    env["states"]["my_robot"]["velocity"] = [0.0] * 7
+    env["states"]["obj1"] = dict(configuration=[3.0, 3.0, 0.0], velocity=[0.0, 0.0, 0.0])       # out of the way
+    w = oracle.OracleWorld(env)
+    w.set_target_velocity(0, np.array([2.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0], np.float32))
+    w.step(40)
+    bm, b = w.body_model(), w.bodies()
+    links = range(1, 6)
+    mass = sum(float(bm[i, 0]) for i in links)
+    p = sum(float(bm[i, 0]) * b[i, 10:12].astype(np.float64) for i in links) / 10.0
+    assert p[0] / mass == pytest.approx(2.0 * 0.4, rel=1e-3) and abs(p[1] / mass) < 1e-3
+    w.step(100)                                                                                   # then it settles at the target
+    _, qd = w.get_state()
+    assert qd[0] == pytest.approx(2.0, abs=2e-2)
