@@ -532,3 +532,32 @@ def test_velocity_controller_ramps_at_the_acceleration_limit(oracle):
     w.step(100)                                                                                   # then it settles at the target
     _, qd = w.get_state()
     assert qd[0] == pytest.approx(2.0, abs=2e-2)
+
+
+def test_off_centre_elastic_collision_conserves_everything(oracle):
+    """A box hits a rotated box off-centre (corner against face: one manifold point), frictionless, restitution 1: both
+    start to spin, and linear momentum, angular momentum about the origin and kinetic energy all survive the impact —
+    normal-impulse-only contact with Newton restitution is exactly that."""
+    env = _two_box_env(1.0)
+    env["states"]["a"] = dict(configuration=[0.0, 0.0, 0.0], velocity=[1.0, 0.0, 0.0])
+    env["states"]["b"] = dict(configuration=[0.5, 0.13, 0.6], velocity=[0.0, 0.0, 0.0])
+    w = oracle.OracleWorld(env)
+    bm = w.body_model()
+
+    def invariants():
+        b = w.bodies()
+        p, ang, energy = np.zeros(2), 0.0, 0.0
+        for i in (1, 2):
+            m, inertia = float(bm[i, 0]), float(bm[i, 2])
+            c, v, om = b[i, 4:6].astype(np.float64), b[i, 10:12].astype(np.float64), float(b[i, 12])
+            p += m * v
+            ang += m * (c[0] * v[1] - c[1] * v[0]) + inertia * om
+            energy += 0.5 * m * (v @ v) + 0.5 * inertia * om * om
+        return p, ang, energy
+
+    p0, l0, e0 = invariants()
+    w.step(60)
+    p1, l1, e1 = invariants()
+    _, qd = w.get_state()
+    assert abs(qd[2]) > 1.0 and abs(qd[5]) > 1.0 and abs(qd[1]) > 0.1           # the impact really was oblique
+    assert np.allclose(p1, p0, atol=1e-5) and abs(l1 - l0) < 1e-5 and e1 == pytest.approx(e0, rel=1e-6)
