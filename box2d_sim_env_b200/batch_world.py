@@ -53,7 +53,7 @@ ABI_SYMBOLS = [
     "b2g_env_add_polygon", "b2g_env_add_ball", "b2g_env_add_joint", "b2g_env_add_state", "b2g_model_create", "b2g_model_destroy",
     "b2g_model_get_info", "b2g_model_get_warnings", "b2g_model_get_object", "b2g_model_get_dof_limits", "b2g_model_get_bodies",
     "b2g_model_get_fixtures", "b2g_model_get_joints", "b2g_model_get_balls", "b2g_model_set_link_property",
-    "b2g_model_get_link_property", "b2g_model_get_link", "b2g_model_find_link", "b2g_model_get_joint", "b2g_model_find_joint",
+    "b2g_model_get_link_property", "b2g_model_get_link", "b2g_model_find_link", "b2g_model_get_link_aabb", "b2g_model_get_object_aabb", "b2g_model_get_joint", "b2g_model_find_joint",
     "b2g_batch_get_ball_approximation",
     "b2g_batch_create", "b2g_batch_clone", "b2g_batch_destroy", "b2g_batch_set_params",
     "b2g_batch_status", "b2g_batch_stream", "b2g_batch_sync", "b2g_batch_set_state", "b2g_batch_set_state_dev",
@@ -109,6 +109,8 @@ def lib():
     L.b2g_model_get_object.argtypes = [vp, C.c_int, C.POINTER(_ObjectInfo)]
     L.b2g_model_get_link.argtypes = [vp, C.c_int, C.POINTER(_LinkInfo)]
     L.b2g_model_find_link.argtypes = [vp, C.c_int, C.c_char_p, ip]
+    L.b2g_model_get_link_aabb.argtypes = [vp, C.c_int, fp]
+    L.b2g_model_get_object_aabb.argtypes = [vp, C.c_int, fp]
     L.b2g_model_get_joint.argtypes = [vp, C.c_int, C.POINTER(_JointInfo)]
     L.b2g_model_find_joint.argtypes = [vp, C.c_int, C.c_char_p, ip]
     L.b2g_model_get_warnings.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(C.c_int32)]
@@ -337,6 +339,19 @@ class Model:
         out = np.zeros(1, np.int32)
         _check(lib().b2g_model_find_link(self.h, obj, name.encode(), _ptr(out)))
         return int(out[0])
+
+    def link_aabb(self, body):
+        """Box2DLink::getLocalBoundingBox: min x, min y, max x, max y of the link's polygons (user units)."""
+        out = np.zeros(4, np.float32)
+        _check(lib().b2g_model_get_link_aabb(self.h, int(body), _ptr(out)))
+        return out
+
+    def object_aabb(self, obj):
+        """Box2DObject::getLocalAABB."""
+        obj = self.object_index(obj) if isinstance(obj, str) else obj
+        out = np.zeros(4, np.float32)
+        _check(lib().b2g_model_get_object_aabb(self.h, obj, _ptr(out)))
+        return out
 
     def joint(self, joint):
         ji = _JointInfo()

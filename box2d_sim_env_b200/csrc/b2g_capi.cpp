@@ -871,6 +871,20 @@ b2g_status b2g_model_get_link(const b2g_model* m, int body, b2g_link_info* out) 
     return B2G_OK;
 }
 
+b2g_status b2g_model_get_link_aabb(const b2g_model* m, int body, float out[4]) {
+    if (!m || !out) return fail(B2G_ERR_INVALID, "null argument");
+    if (!isLinkBody(m->m, body)) return fail(B2G_ERR_INVALID, "unknown link (body 0 is the ground)");
+    for (int i = 0; i < 4; ++i) out[i] = m->m.linkAabb[4 * body + i];
+    return B2G_OK;
+}
+
+b2g_status b2g_model_get_object_aabb(const b2g_model* m, int object, float out[4]) {
+    if (!m || !out) return fail(B2G_ERR_INVALID, "null argument");
+    if (object < 0 || object >= (int)m->m.objects.size()) return fail(B2G_ERR_INVALID, "unknown object");
+    objectLocalAabb(m->m, object, out);
+    return B2G_OK;
+}
+
 b2g_status b2g_model_find_link(const b2g_model* m, int object, const char* name, int32_t* body) {
     if (!m || !name || !body) return fail(B2G_ERR_INVALID, "null argument");
     const HostModel& hm = m->m;

@@ -220,6 +220,7 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
     const float scale = env.scale;
     if (!(scale > 0.0f)) throw std::runtime_error("scale must be positive");
     std::vector<BBody> bodies;
+    std::vector<float> linkAabb;    // per body: Box2DLink::_local_aabb (min x, min y, max x, max y; user units)
     std::vector<float> linkParams;  // per body: ground_friction, ground_torque_integral, contact_friction, friction joint
     std::vector<BFix> fixtures;
     std::vector<BJoint> joints;
@@ -355,6 +356,8 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
             linkBody[ld.name] = (int)bodies.size();
             aabbMin[ld.name] = {mnx, mny};
             aabbMax[ld.name] = {mxx, mxy};
+            linkAabb.resize(4 * bodies.size(), 0.0f);
+            linkAabb.push_back(mnx); linkAabb.push_back(mny); linkAabb.push_back(mxx); linkAabb.push_back(mxy);
             ob.mass += b.mass * (b.type == 2 ? 1.0f : 0.0f);  // b2Body::GetMass() of a static body is 0
             // friction joint to the ground (:131-147)
             BJoint fj;
@@ -789,6 +792,8 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
     out.warnings = env.warnings;
     out.jointNames.clear();
     for (int j = 0; j < nj; ++j) out.jointNames.push_back(joints[j].name);
+    linkAabb.resize(4 * nb, 0.0f);
+    out.linkAabb = linkAabb;
     linkParams.resize(4 * nb, 0.0f);
     out.linkParams = linkParams;
     for (int b = 0; b < nb; ++b) {
@@ -840,6 +845,25 @@ void updateFrictionJoint(HostModel& m, int body) {
     m.jointFloats[j * 15 + 7] = maxTorque;
 }
 }  // namespace
+
+// Box2DObject::getLocalAABB (Box2DWorld.cpp:1928-1931): the link boxes merged as they are, each in its own link frame
+// (:1304), shifted by the base link's local centre of mass as it was before setOriginToCenterOfMass (:1308-1312; a static
+// body has none, b2Body::GetLocalCenter() is zero).  BoundingBox::merge belongs to the absent sim_env package: assumed to
+// be the component-wise min / max starting from an empty box.
+void objectLocalAabb(const HostModel& m, int object, float out[4]) {
+    const HostObjectInfo& o = m.objects[object];
+    out[0] = out[1] = std::numeric_limits<float>::max();
+    out[2] = out[3] = std::numeric_limits<float>::lowest();
+    for (int b = o.firstBody; b < o.firstBody + o.nLinks; ++b) {
+        out[0] = std::min(out[0], m.linkAabb[4 * b]); out[1] = std::min(out[1], m.linkAabb[4 * b + 1]);
+        out[2] = std::max(out[2], m.linkAabb[4 * b + 2]); out[3] = std::max(out[3], m.linkAabb[4 * b + 3]);
+    }
+    const int base = (int)m.blob[m.h.oObj + object * MO_STRIDE + MO_BASE_BODY];
+    const bool dynamic = m.blob[m.h.oBody + base * MB_STRIDE + MB_TYPE] == 2u;
+    const float cx = dynamic ? m.h.invScale * wordF(m, m.h.oBody + base * MB_STRIDE + MB_LCX) : 0.0f;
+    const float cy = dynamic ? m.h.invScale * wordF(m, m.h.oBody + base * MB_STRIDE + MB_LCY) : 0.0f;
+    out[0] -= cx; out[1] -= cy; out[2] -= cx; out[3] -= cy;
+}
 
 bool isLinkBody(const HostModel& m, int body) {
     return body >= 0 && body < m.h.nb && 4 * (size_t)body + 3 < m.linkParams.size() && m.linkParams[4 * body + 3] >= 0.0f;

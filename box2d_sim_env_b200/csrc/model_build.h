@@ -35,7 +35,9 @@ struct HostModel {
     // Box2DLink's tunable dynamics parameters per body: _ground_friction, _ground_torque_integral, _contact_friction, index
     // of the link's ground-friction joint (-1: the body is not a link, i.e. the ground)
     std::vector<float> linkParams;    // nb x 4
+    std::vector<float> linkAabb;      // nb x 4: Box2DLink::_local_aabb (Box2DWorld.cpp:69-90), user units
 };
+void objectLocalAabb(const HostModel& m, int object, float out[4]);
 
 // Box2DLink::setMass / setGroundFrictionCoefficient / setGroundFrictionTorqueIntegral / setContactFriction and the
 // matching getters (Box2DWorld.cpp:471-566), numbered as in include/b2g.h (b2g_link_property)

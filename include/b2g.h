@@ -130,6 +130,11 @@ typedef struct b2g_link_info {
 } b2g_link_info;
 b2g_status b2g_model_get_link(const b2g_model* model, int body, b2g_link_info* out);
 b2g_status b2g_model_find_link(const b2g_model* model, int object, const char* name, int32_t* body);
+/* Box2DLink::getLocalBoundingBox (Box2DWorld.cpp:258-261; the box of the link's polygons as given in the description) and
+ * Box2DObject::getLocalAABB (:1928-1931; the link boxes merged, shifted by the base link's local centre of mass, :1304-1312):
+ * out = min x, min y, max x, max y in user units */
+b2g_status b2g_model_get_link_aabb(const b2g_model* model, int body, float out[4]);
+b2g_status b2g_model_get_object_aabb(const b2g_model* model, int object, float out[4]);
 typedef struct b2g_joint_info {
     char name[64];         /* YAML name; empty for the ground-friction joint of a link */
     int32_t kind;          /* 0 ground friction, 1 revolute */

@@ -403,6 +403,11 @@ public:
         return info;
     }
     std::string getLinkName(int body) const { return getLinkInfo(body).name; }
+    // Box2DObject::getLocalAABB (:1928-1931) / Box2DLink::getLocalBoundingBox (:258-261): min x, min y, max x, max y
+    void getLocalAABB(const std::string& object, float aabb[4]) const {
+        check(b2g_model_get_object_aabb(_model, objectIndex(object), aabb));
+    }
+    void getLocalBoundingBox(int body, float aabb[4]) const { check(b2g_model_get_link_aabb(_model, body, aabb)); }
     int getBaseLink(const std::string& object) const {
         const ObjectInfo& o = _objects[objectIndex(object)];
         for (int b = o.first_body; b < o.first_body + o.n_links; ++b)

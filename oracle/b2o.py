@@ -70,6 +70,8 @@ def lib():
         L.b2o_world_step_record.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.b2o_world_set_link_enabled.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.b2o_world_get_link_states.argtypes = [C.c_void_p, C.c_void_p]
+        L.b2o_world_get_link_aabb.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.b2o_world_get_object_aabb.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.b2o_world_set_link_property.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float]
         L.b2o_world_get_link_property.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.b2o_world_get_link_property.restype = C.c_float
@@ -308,6 +310,16 @@ class OracleWorld:
         out = np.zeros(64, np.float32)
         n = lib().b2o_world_controller_efforts(self.h, obj, _ptr(out))
         return out[:n].copy()
+
+    def link_aabb(self, body_index):
+        out = np.zeros(4, np.float32)
+        lib().b2o_world_get_link_aabb(self.h, body_index, _ptr(out))
+        return out
+
+    def object_aabb(self, obj):
+        out = np.zeros(4, np.float32)
+        lib().b2o_world_get_object_aabb(self.h, obj, _ptr(out))
+        return out
 
     def link_states(self):
         """[n_bodies, 8]: Box2DLink::getPose(3), getVelocityVector(3), getCenterOfMass(2); row 0 (ground) is 0"""

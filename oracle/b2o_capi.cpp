@@ -233,6 +233,21 @@ void b2o_world_object_info(void* wp, int objIdx, int* info6, char* nameOut, int 
 }
 
 // 16 floats per body: xf.p(2) xf.q.s xf.q.c c(2) a c0(2) a0 v(2) w sleepTime awake type
+// Box2DLink::getLocalBoundingBox (:258-261) and Box2DObject::getLocalAABB (:1928-1931, built at :1304-1312): min x, min y, max x, max y
+void b2o_world_get_link_aabb(void* wp, int bodyIndex, float* out) {
+    OWorld* w = (OWorld*)wp;
+    OLink* l = (OLink*)w->b2->bodies.at(bodyIndex)->userData;
+    for (int i = 0; i < 4; ++i) out[i] = 0.0f;
+    if (!l) return;
+    out[0] = l->localAabbMin[0]; out[1] = l->localAabbMin[1]; out[2] = l->localAabbMax[0]; out[3] = l->localAabbMax[1];
+}
+
+void b2o_world_get_object_aabb(void* wp, int object, float* out) {
+    OWorld* w = (OWorld*)wp;
+    OObject* o = w->creationOrder.at(object);
+    for (int i = 0; i < 4; ++i) out[i] = o->localAabb[i];
+}
+
 // Box2DLink::getPose / getVelocityVector / getCenterOfMass per link: out[n_bodies][8], the ground's row stays 0
 void b2o_world_get_link_states(void* wp, float* out) {
     OWorld* w = (OWorld*)wp;

@@ -468,6 +468,21 @@ OObject* OWorld::createObject(const ObjectDesc& d) {  // Box2DObject ctor :1292-
         obj->mass += link->getMass();
     }
     obj->baseLink = obj->links.at(d.base_link);
+    {   // :1304-1312: merge the link boxes (BoundingBox::merge of the absent sim_env: assumed component-wise min / max from an
+        // empty box), then shift by the base link's local centre of mass as it is before the origin moves there
+        obj->localAabb[0] = obj->localAabb[1] = std::numeric_limits<float>::max();
+        obj->localAabb[2] = obj->localAabb[3] = std::numeric_limits<float>::lowest();
+        for (OLink* l : obj->linksCreation) {
+            obj->localAabb[0] = std::min(obj->localAabb[0], l->localAabbMin[0]);
+            obj->localAabb[1] = std::min(obj->localAabb[1], l->localAabbMin[1]);
+            obj->localAabb[2] = std::max(obj->localAabb[2], l->localAabbMax[0]);
+            obj->localAabb[3] = std::max(obj->localAabb[3], l->localAabbMax[1]);
+        }
+        Vec2 b2center = obj->baseLink->body->GetLocalCenter() - obj->baseLink->localOriginOffset;  // getLocalCenterOfMass :577-586
+        float oldCenter[2] = {b2center.x * invScale(), b2center.y * invScale()};
+        obj->localAabb[0] -= oldCenter[0]; obj->localAabb[1] -= oldCenter[1];
+        obj->localAabb[2] -= oldCenter[0]; obj->localAabb[3] -= oldCenter[1];
+    }
     obj->baseLink->setOriginToCenterOfMass();
     unsigned baseDofs = obj->isStatic ? 0 : 3;
     for (const JointDesc& jd : d.joints) {  // Box2DJoint ctor :872-948

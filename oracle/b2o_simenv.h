@@ -127,6 +127,7 @@ struct OObject {
     bool isStatic = false;
     bool isRobot = false;
     float mass = 0.0f;
+    float localAabb[4] = {0, 0, 0, 0};     // Box2DObject::_local_bounding_box (:1304-1312): min x, min y, max x, max y
     std::map<std::string, OLink*> links;   // name order, as the reference's std::map
     std::vector<OLink*> linksCreation;     // YAML order
     std::vector<OJoint*> sortedJoints;     // YAML order

@@ -295,3 +295,30 @@ def test_link_and_joint_lookup_by_name(b2g):
                 lambda: m.find_link(7, "x")]:
         with pytest.raises(b2g.B2GError):
             bad()
+
+
+@pytest.mark.parametrize("env_name", [ENV_A, ENV_B])
+def test_local_bounding_boxes(b2g, oracle, env_name):
+    """Box2DLink::getLocalBoundingBox (Box2DWorld.cpp:69-90, 258-261) and Box2DObject::getLocalAABB (:1304-1312, 1928-1931)
+    against the oracle's restatement and the YAML: obj1 is a 0.1 m square about its centre of mass; obj2's two links merge to
+    [-0.05, 0.4] x [-0.05, 0.1] (a static object keeps the box as given: no centre of mass to shift by)."""
+    m = b2g.Model(b2g.data_path(env_name))
+    w = oracle.OracleWorld(load_env_dict(env_name))
+    for b in range(1, m.n_bodies):
+        assert np.array_equal(m.link_aabb(b), w.link_aabb(b))
+    for o in range(m.n_objects):
+        assert np.array_equal(m.object_aabb(o), w.object_aabb(o))
+    assert np.allclose(m.object_aabb("obj1"), [-0.05, -0.05, 0.05, 0.05], atol=1e-6)
+    assert np.allclose(m.object_aabb("obj2"), [-0.05, -0.05, 0.4, 0.1], atol=1e-6)
+    robot = m.object_aabb(0)
+    base = m.objects[0]["first_body"]
+    lc = m.body_model()[base, 4:6] / m.scale                      # the robot's box is shifted by the base link's centre of mass
+    merged = np.array([min(m.link_aabb(b)[0] for b in range(base, base + m.objects[0]["n_links"])),
+                       min(m.link_aabb(b)[1] for b in range(base, base + m.objects[0]["n_links"])),
+                       max(m.link_aabb(b)[2] for b in range(base, base + m.objects[0]["n_links"])),
+                       max(m.link_aabb(b)[3] for b in range(base, base + m.objects[0]["n_links"]))], np.float32)
+    assert np.allclose(robot, merged - np.array([lc[0], lc[1], lc[0], lc[1]], np.float32), atol=1e-6)
+    with pytest.raises(b2g.B2GError):
+        m.link_aabb(0)
+    with pytest.raises(b2g.B2GError):
+        m.object_aabb(17)
