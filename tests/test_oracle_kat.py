@@ -561,3 +561,24 @@ def test_off_centre_elastic_collision_conserves_everything(oracle):
     _, qd = w.get_state()
     assert abs(qd[2]) > 1.0 and abs(qd[5]) > 1.0 and abs(qd[1]) > 0.1           # the impact really was oblique
     assert np.allclose(p1, p0, atol=1e-5) and abs(l1 - l0) < 1e-5 and e1 == pytest.approx(e0, rel=1e-6)
+
+
+@pytest.mark.parametrize("mu_a,mu_b", [(0.3, 0.3), (0.5, 0.2)])
+def test_oblique_impact_obeys_coulomb_friction(oracle, mu_a, mu_b):
+    """A box strikes the face of a resting box while sliding along it much faster than the impact can stop: the contact
+    slides throughout, so the tangential impulse is the Coulomb limit, |J_t| = mu |J_n| with b2MixFriction's
+    mu = sqrt(mu_a mu_b), for both bodies (equal and opposite impulses)."""
+    env = _two_box_env(0.0)
+    env["objects"][0]["links"][0]["contact_friction"] = mu_a
+    env["objects"][1]["links"][0]["contact_friction"] = mu_b
+    env["states"]["a"] = dict(configuration=[0.0, 0.0, 0.0], velocity=[1.0, 2.0, 0.0])
+    env["states"]["b"] = dict(configuration=[0.3, 0.05, 0.0], velocity=[0.0, 0.0, 0.0])
+    w = oracle.OracleWorld(env)
+    w.step(40)
+    _, qd = w.get_state()
+    mu = np.sqrt(mu_a * mu_b)
+    jn_a, jt_a = 0.5 * (qd[0] - 1.0), 0.5 * (qd[1] - 2.0)
+    jn_b, jt_b = 0.5 * qd[3], 0.5 * qd[4]
+    assert jn_a < -0.05 and jn_b > 0.05                                  # a real impact
+    assert jt_a / jn_a == pytest.approx(mu, rel=1e-4) and jt_b / jn_b == pytest.approx(mu, rel=1e-4)
+    assert jn_a + jn_b == pytest.approx(0.0, abs=1e-6) and jt_a + jt_b == pytest.approx(0.0, abs=1e-6)
