@@ -582,3 +582,24 @@ def test_oblique_impact_obeys_coulomb_friction(oracle, mu_a, mu_b):
     assert jn_a < -0.05 and jn_b > 0.05                                  # a real impact
     assert jt_a / jn_a == pytest.approx(mu, rel=1e-4) and jt_b / jn_b == pytest.approx(mu, rel=1e-4)
     assert jn_a + jn_b == pytest.approx(0.0, abs=1e-6) and jt_a + jt_b == pytest.approx(0.0, abs=1e-6)
+
+
+def test_fat_aabb_follows_the_move_proxy_rule(oracle):
+    """b2Body::SynchronizeFixtures + b2DynamicTree::MoveProxy: a proxy keeps its fat box while the swept tight box (polygon
+    +- b2_polygonRadius at the old and the new transform) stays inside; otherwise the new fat box is the swept box
+    +- b2_aabbExtension (0.1) stretched by b2_aabbMultiplier (2) x displacement on the leading side.  A 2 x 2 box (Box2D
+    units) moving at 0.3 units per step: refits at step 1 to [-1.11, 1.01 + 0.3 + 0.1 + 0.6] and again at step 4."""
+    env = _two_box_env(0.0)
+    env["states"]["a"] = dict(configuration=[0.0, 0.0, 0.0], velocity=[3.0, 0.0, 0.0])
+    env["states"]["b"] = dict(configuration=[0.0, 3.0, 0.0], velocity=[0.0, 0.0, 0.0])
+    w = oracle.OracleWorld(env)
+    fat = w.fat_aabbs()
+    assert np.allclose(fat[1], [-1.11, -1.11, 1.11, 1.11], atol=1e-6)          # creation: tight box +- 0.1
+    assert np.allclose(fat[2], [-1.11, 28.89, 1.11, 31.11], atol=1e-5)
+    expect = {1: [-1.11, 2.01], 2: [-1.11, 2.01], 3: [-1.11, 2.01], 4: [-0.21, 2.91], 5: [-0.21, 2.91]}
+    for step in range(1, 6):
+        w.step(1)
+        f = w.fat_aabbs()[1]
+        assert np.allclose(f[[0, 2]], expect[step], atol=1e-5), step
+        assert np.allclose(f[[1, 3]], [-1.11, 1.11], atol=1e-6)
+    assert np.array_equal(w.fat_aabbs()[2], fat[2])                            # the resting box never refits
