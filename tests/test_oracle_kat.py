@@ -603,3 +603,25 @@ def test_fat_aabb_follows_the_move_proxy_rule(oracle):
         assert np.allclose(f[[0, 2]], expect[step], atol=1e-5), step
         assert np.allclose(f[[1, 3]], [-1.11, 1.11], atol=1e-6)
     assert np.array_equal(w.fat_aabbs()[2], fat[2])                            # the resting box never refits
+
+
+def test_sleep_thresholds(oracle):
+    """b2Island::Solve's sleep rule: a body slower than b2_linearSleepTolerance (0.01 Box2D units/s) and
+    b2_angularSleepTolerance accumulates sleep time; the island is put to sleep (velocity zeroed) once the minimum reaches
+    b2_timeToSleep = 0.5 s -- in float arithmetic 50 x 0.01 is 0.4999998, so that is step 51.  A body at twice the tolerance
+    never sleeps; stepping with allow_sleeping = false keeps the slow one awake too."""
+    env = _two_box_env(0.0)
+    env["states"]["a"] = dict(configuration=[0.0, 0.0, 0.0], velocity=[0.0005, 0.0, 0.0])
+    env["states"]["b"] = dict(configuration=[0.0, 3.0, 0.0], velocity=[0.002, 0.0, 0.0])
+    w = oracle.OracleWorld(env)
+    w.step(50)
+    b = w.bodies()
+    assert b[1, 14] == 1.0 and b[1, 10] == pytest.approx(0.005, rel=1e-6) and b[1, 13] == pytest.approx(0.5, abs=1e-6) and b[1, 13] < 0.5
+    w.step(1)
+    b = w.bodies()
+    assert b[1, 14] == 0.0 and b[1, 10] == 0.0 and b[1, 13] == 0.0            # asleep, velocity and sleep time reset
+    assert b[2, 14] == 1.0 and b[2, 10] == pytest.approx(0.02, rel=1e-6)      # the faster box stays awake
+    w2 = oracle.OracleWorld(env)
+    w2.step(80, True, False)
+    b = w2.bodies()
+    assert b[1, 14] == 1.0 and b[1, 10] == pytest.approx(0.005, rel=1e-6)
