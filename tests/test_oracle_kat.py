@@ -625,3 +625,35 @@ def test_sleep_thresholds(oracle):
     w2.step(80, True, False)
     b = w2.bodies()
     assert b[1, 14] == 1.0 and b[1, 10] == pytest.approx(0.005, rel=1e-6)
+
+
+def test_revolute_limit_is_an_inelastic_stop(oracle):
+    """b2RevoluteJoint with enableLimit: the limit only acts once the angle has reached it (so the arm overshoots by at most
+    one step of travel), then the velocity constraint removes the whole relative speed (no restitution on joint limits) and
+    the position constraint tolerates b2_angularSlop (2 degrees) beyond the limit: the arm parks within
+    [upper, upper + angularSlop]."""
+    def link(name, poly, mass):
+        return dict(name=name, geometry=[poly], mass=mass, ground_friction=0.0, ground_torque_integral=0.0, contact_friction=0.0,
+                    restitution=0.0, balls=[])
+    robot = dict(name="r", static=False,
+                 links=[link("base", [-0.5, -0.5, 0.5, -0.5, 0.5, 0.5, -0.5, 0.5], 3000.0),
+                        link("arm", [-0.05, 0.0, 0.05, 0.0, 0.05, 0.4, -0.05, 0.4], 0.3)],
+                 joints=[dict(name="hinge", link_a="base", link_b="arm", axis=[0.0, 0.6], axis_orientation=0.0, position_limits=[-0.5, 0.5],
+                              velocity_limits=[-100.0, 100.0], acceleration_limits=[-1000.0, 1000.0], joint_type="revolute",
+                              actuated=False)],
+                 base_actuation=dict(translational_velocity_limits=[-2.0, 2.0], translational_acceleration_limits=[-2.0, 2.0],
+                                     rotational_velocity_limits=[-2.0, 2.0], rotational_acceleration_limits=[-2.0, 2.0],
+                                     use_center_of_mass=True))
+    env = dict(scale=10.0, world_bounds=[-5, -5, 5, 5], robots=[robot], objects=[],
+               states={"r": dict(configuration=[0.0, 0.0, 0.0, 0.0], velocity=[0.0, 0.0, 0.0, 2.0])})
+    w = oracle.OracleWorld(env)
+    w.step(24)
+    q, qd = w.get_state()
+    assert q[3] == pytest.approx(24 * 0.02, rel=2e-3) and qd[3] == pytest.approx(2.0, rel=5e-3)   # free swing below the limit
+    w.step(16)
+    q, qd = w.get_state()
+    slop = 2.0 / 180.0 * np.pi
+    assert 0.5 <= q[3] <= 0.5 + min(slop, 0.02 + 1e-4) and abs(qd[3]) < 1e-6
+    w.step(50)
+    q2, _ = w.get_state()
+    assert q2[3] == pytest.approx(q[3], abs=1e-5)                                                  # and stays there
