@@ -216,7 +216,49 @@ void layoutState(ModelHeader& h, int maxContacts) {
     h.stateChunks = s;
 }
 
+namespace {
+// A non-finite number anywhere in the description (`.inf`, `.nan`, an overflowing literal) would end up in the mass data or
+// the world bounds and turn every world of every batch into NaNs after one step: refused with the place it was found.
+void requireFinite(float v, const std::string& where) {
+    if (!std::isfinite(v)) throw std::runtime_error("non-finite number in " + where);
+}
+void requireFinite(const EnvironmentDescription& env) {
+    requireFinite(env.scale, "scale");
+    for (float v : env.world_bounds) requireFinite(v, "world_bounds");
+    auto object = [](const ObjectDescription& d) {
+        for (const LinkDescription& l : d.links) {
+            const std::string where = "link '" + l.name + "' of '" + d.name + "'";
+            requireFinite(l.mass, where); requireFinite(l.ground_friction, where); requireFinite(l.ground_torque_integral, where);
+            requireFinite(l.contact_friction, where); requireFinite(l.restitution, where);
+            for (const auto& poly : l.polygons) for (float v : poly) requireFinite(v, "geometry of " + where);
+            for (const auto& ball : l.balls) for (float v : ball) requireFinite(v, "balls of " + where);
+        }
+        for (const JointDescription& j : d.joints) {
+            const std::string where = "joint '" + j.name + "' of '" + d.name + "'";
+            for (int k = 0; k < 2; ++k) {
+                requireFinite(j.axis[k], where); requireFinite(j.position_limits[k], where);
+                requireFinite(j.velocity_limits[k], where); requireFinite(j.acceleration_limits[k], where);
+            }
+            requireFinite(j.axis_orientation, where);
+        }
+        for (int k = 0; k < 2; ++k) {
+            requireFinite(d.translational_velocity_limits[k], "base_actuation of '" + d.name + "'");
+            requireFinite(d.translational_acceleration_limits[k], "base_actuation of '" + d.name + "'");
+            requireFinite(d.rotational_velocity_limits[k], "base_actuation of '" + d.name + "'");
+            requireFinite(d.rotational_acceleration_limits[k], "base_actuation of '" + d.name + "'");
+        }
+    };
+    for (const ObjectDescription& d : env.robots) object(d);
+    for (const ObjectDescription& d : env.objects) object(d);
+    for (const auto& kv : env.states) {
+        for (float v : kv.second.configuration) requireFinite(v, "state of '" + kv.first + "'");
+        for (float v : kv.second.velocity) requireFinite(v, "state of '" + kv.first + "'");
+    }
+}
+}  // namespace
+
 void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& out) {
+    requireFinite(env);
     const float scale = env.scale;
     if (!(scale > 0.0f)) throw std::runtime_error("scale must be positive");
     std::vector<BBody> bodies;
