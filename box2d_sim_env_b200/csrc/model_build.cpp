@@ -230,6 +230,11 @@ void requireFinite(const EnvironmentDescription& env) {
             const std::string where = "link '" + l.name + "' of '" + d.name + "'";
             requireFinite(l.mass, where); requireFinite(l.ground_friction, where); requireFinite(l.ground_torque_integral, where);
             requireFinite(l.contact_friction, where); requireFinite(l.restitution, where);
+            // upstream asserts density >= 0 (b2Body::CreateFixture) and force / torque limits >= 0 (b2FrictionJoint); a negative
+            // contact friction makes b2MixFriction's square root a NaN
+            if (l.mass < 0.0f || l.ground_friction < 0.0f || l.ground_torque_integral < 0.0f || l.contact_friction < 0.0f ||
+                l.restitution < 0.0f)
+                throw std::runtime_error("negative mass / friction / restitution in " + where);
             for (const auto& poly : l.polygons) for (float v : poly) requireFinite(v, "geometry of " + where);
             for (const auto& ball : l.balls) for (float v : ball) requireFinite(v, "balls of " + where);
         }

@@ -339,6 +339,12 @@ def test_non_finite_numbers_are_refused(b2g, tmp_path):
         with pytest.raises(b2g.B2GError) as ei:
             b2g.Model(bad)
         assert "non-finite" in str(ei.value) and where in str(ei.value)
+    for key in ["mass", "ground_friction", "ground_torque_integral", "contact_friction", "restitution"]:
+        bad = copy.deepcopy(env)
+        bad["objects"][0]["links"][0][key] = -0.1
+        with pytest.raises(b2g.B2GError) as ei:
+            b2g.Model(bad)                                     # upstream asserts on these
+        assert "negative" in str(ei.value)
     text = open(b2g.data_path(ENV_A)).read().replace("world_bounds: [-20.0,", "world_bounds: [-20.1e9990,")
     assert "1e9990" in text
     import shutil
