@@ -657,3 +657,33 @@ def test_revolute_limit_is_an_inelastic_stop(oracle):
     w.step(50)
     q2, _ = w.get_state()
     assert q2[3] == pytest.approx(q[3], abs=1e-5)                                                  # and stays there
+
+
+def test_toi_lands_the_box_at_the_wall(oracle):
+    """Continuous collision against a static body: a box flying 1.5 Box2D units per step at a wall 0.5 units away is
+    advanced to the time of impact (core shapes b2_linearSlop = 0.005 apart, tolerance a quarter of it), b2Island::SolveTOI
+    pushes the two manifold points out to -1.5 linearSlop of skinned separation (b2_toiBaugarte 0.75: +0.0075, then
+    +0.0019 for the second point) and removes the approach speed; the rest of the step is spent at rest.  It never
+    penetrates, lands between 0.0125 and 0.016 units from the wall and creeps to the resting gap
+    2 polygonRadius - linearSlop = 0.015 afterwards."""
+    env = _two_box_env(0.0)
+    env["objects"][1]["static"] = True
+    env["states"]["a"] = dict(configuration=[0.0, 0.0, 0.0], velocity=[15.0, 0.0, 0.0])
+    env["states"]["b"] = dict(configuration=[1.0, 0.02, 0.0], velocity=[])
+    w = oracle.OracleWorld(env)
+
+    def gap():
+        b = w.bodies()
+        return float((b[2, 4] - 1.0) - (b[1, 4] + 1.0))      # between the facing sides, Box2D units (half width 1)
+
+    for step in range(1, 6):
+        w.step(1)
+        assert w.stats()["toi_events"] == 0 and gap() == pytest.approx(8.0 - 1.5 * step, abs=1e-4)
+    w.step(1)
+    _, qd = w.get_state()
+    # the approach speed is gone; the frictionless two-point impact leaves a sideways drift of under a millimetre per second
+    assert w.stats()["toi_events"] == 1 and abs(qd[0]) < 1e-5 and abs(qd[1]) < 5e-3
+    assert 0.005 + 0.0075 - 0.00125 <= gap() <= 0.016
+    landed = gap()
+    w.step(200)
+    assert landed <= gap() <= 0.015 + 1e-5 and gap() == pytest.approx(0.015, abs=2e-4)
