@@ -687,3 +687,67 @@ def test_toi_lands_the_box_at_the_wall(oracle):
     landed = gap()
     w.step(200)
     assert landed <= gap() <= 0.015 + 1e-5 and gap() == pytest.approx(0.015, abs=2e-4)
+
+
+def test_forward_kinematics_known_answers(oracle):
+    """setDOFPositions -> link poses (Box2DJoint::resetPosition :992-1019, Box2DLink::setPose :405-438): a child link's origin
+    sits at its joint's axis point in the parent frame and is turned by the joint angle plus axis_orientation; the robot's
+    pose DOFs are the base link's centre of mass (its origin was moved there, :653-671)."""
+    env = load_env_dict(ENV_A)
+    w = oracle.OracleWorld(env)
+    q, qd = w.get_state()
+    q[:7] = [0.4, -0.3, 0.7, 0.5, -0.4, -0.6, 0.3]
+    w.set_state(q, np.zeros_like(qd))
+    ls = w.link_states().astype(np.float64)
+    bm = w.body_model().astype(np.float64)
+    joints = {j["name"]: j for j in env["robots"][0]["joints"]}
+
+    def rot(a):
+        return np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+
+    base_angle = 0.7
+    base_origin = np.array([0.4, -0.3]) - rot(base_angle) @ (bm[1, 4:6] / 10.0)      # body origin = COM - R * local COM
+    assert ls[1, 2] == pytest.approx(base_angle, abs=1e-6) and np.allclose(ls[1, :2], [0.4, -0.3], atol=1e-6)
+    chain = [("finger_l_joint_1", 2, 1, 0.5), ("finger_l_joint_2", 3, 2, -0.4), ("finger_r_joint_1", 4, 1, -0.6),
+             ("finger_r_joint_2", 5, 4, 0.3)]
+    origin, angle = {1: base_origin}, {1: base_angle}
+    for name, child, parent, value in chain:
+        jd = joints[name]
+        origin[child] = origin[parent] + rot(angle[parent]) @ np.array(jd["axis"], np.float64)
+        angle[child] = angle[parent] + value + jd["axis_orientation"]
+        assert np.allclose(ls[child, :2], origin[child], atol=2e-6), name
+        assert ls[child, 2] == pytest.approx(angle[child], abs=2e-6), name
+    q1, _ = w.get_state()
+    assert np.allclose(q1[:7], q[:7], atol=2e-6)                                     # and the DOFs read back
+
+
+def test_velocity_kinematics_known_answers(oracle):
+    """setDOFVelocities -> body velocities (Box2DObject::updateBodyVelocities :2018-2044, Box2DLink::updateBodyVelocities
+    :759-800): every link moves with the base (translation plus rotation about the base link's centre of mass) and turns
+    about each joint above it: v_com = v_base + w_base x (com - com_base) + sum_i qd_i x (com - anchor_i), w = w_base + sum_i qd_i."""
+    env = load_env_dict(ENV_A)
+    w = oracle.OracleWorld(env)
+    q, qd = w.get_state()
+    q[:7] = [0.1, 0.2, -0.5, 0.3, 0.2, -0.2, -0.3]
+    qd[:7] = [0.3, -0.1, 0.8, 1.5, -2.0, 0.7, 1.1]
+    w.set_state(q, qd)
+    ls = w.link_states().astype(np.float64)
+
+    def cross(omega, r):
+        return omega * np.array([-r[1], r[0]])
+
+    v_base, w_base, com_base = np.array([0.3, -0.1]), 0.8, ls[1, 6:8]
+    assert np.allclose(ls[1, 3:6], [0.3, -0.1, 0.8], atol=1e-6)
+    # the joint anchors are the child links' origins (pose), the chains are base -> l1 -> l2 and base -> r1 -> r2
+    chains = {2: [(2, 1.5)], 3: [(2, 1.5), (3, -2.0)], 4: [(4, 0.7)], 5: [(4, 0.7), (5, 1.1)]}
+    for link, joints in chains.items():
+        com = ls[link, 6:8]
+        v = v_base + cross(w_base, com - com_base)
+        omega = w_base
+        for anchor_link, rate in joints:
+            v = v + cross(rate, com - ls[anchor_link, :2])
+            omega += rate
+        assert np.allclose(ls[link, 3:5], v, atol=5e-6), link
+        assert ls[link, 5] == pytest.approx(omega, abs=1e-6), link
+    _, qd1 = w.get_state()
+    assert np.allclose(qd1[:7], qd[:7], atol=5e-6)
