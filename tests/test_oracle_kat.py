@@ -751,3 +751,19 @@ def test_velocity_kinematics_known_answers(oracle):
         assert ls[link, 5] == pytest.approx(omega, abs=1e-6), link
     _, qd1 = w.get_state()
     assert np.allclose(qd1[:7], qd[:7], atol=5e-6)
+
+
+def test_check_collision_known_answers(oracle):
+    """Box2DCollisionChecker (Box2DWorld.cpp:2832-2911): polygons touch when their cores are closer than the two polygon
+    radii (0.02 Box2D units = 2 mm); the reported point is b2WorldManifold::points[0] -- midway between the skinned surfaces,
+    at the first incident vertex -- and the reference multiplies point AND unit normal by 1 / scale (:2857-2862)."""
+    env = _two_box_env(0.0)
+    env["states"]["a"] = dict(configuration=[0.0, 0.0, 0.0], velocity=[0.0, 0.0, 0.0])
+    env["states"]["b"] = dict(configuration=[0.201, 0.05, 0.0], velocity=[0.0, 0.0, 0.0])      # faces 1 mm apart
+    io, fo = oracle.OracleWorld(env).check_collision()
+    assert io.tolist() == [[1, 2, 1, 2]]                                                      # bodies a, b; their fixtures
+    assert np.allclose(fo[0, :3], [0.1005, -0.05, 0.0], atol=1e-6)                            # mid-gap, B's lower corner
+    assert np.allclose(fo[0, 3:], [0.1, 0.0, 0.0], atol=1e-7)                                 # unit normal / scale
+    env["states"]["b"] = dict(configuration=[0.2021, 0.05, 0.0], velocity=[0.0, 0.0, 0.0])     # 2.1 mm: beyond the radii
+    io, fo = oracle.OracleWorld(env).check_collision()
+    assert len(io) == 0
