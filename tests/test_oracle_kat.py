@@ -767,3 +767,16 @@ def test_check_collision_known_answers(oracle):
     env["states"]["b"] = dict(configuration=[0.2021, 0.05, 0.0], velocity=[0.0, 0.0, 0.0])     # 2.1 mm: beyond the radii
     io, fo = oracle.OracleWorld(env).check_collision()
     assert len(io) == 0
+
+
+def test_recorded_contacts_known_answers(oracle):
+    """stepPhysics(std::vector<Contact>&, steps) (Box2DWorld.cpp:3290-3310, BeginContact :2792-2810): one record per
+    BeginContact.  Box a (1 m/s) meets resting box b whose near face is at x = 0.4 m: exactly one event, at that face,
+    with the unit normal from a to b divided by the scale; after the elastic bounce they separate and nothing else begins."""
+    w = oracle.OracleWorld(_two_box_env(1.0))
+    io, fo = w.step_record(60)
+    assert io.tolist() == [[1, 2, 1, 2]]
+    assert fo[0, 0] == pytest.approx(0.4, abs=2e-3) and abs(fo[0, 1]) == pytest.approx(0.1, abs=1e-6) and fo[0, 2] == 0.0
+    assert np.allclose(fo[0, 3:], [0.1, 0.0, 0.0], atol=1e-7)
+    io, fo = w.step_record(20)
+    assert len(io) == 0
