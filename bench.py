@@ -34,7 +34,6 @@ sys.path.insert(0, ROOT)
 STEPS_PER_TARGET = 10
 N_TARGETS = 10
 ROLLOUT_STEPS = STEPS_PER_TARGET * N_TARGETS
-BASE_Q = np.array([0, 0, 0, 0, 0, 0, 0, 0.9, 1.0, -1.0, 0.0], np.float32)
 
 # BASELINE.json configs -> concrete workloads.  `bytes` = algorithmic bytes per world-step
 # (fixed part, per live contact), DESIGN.md §2.
@@ -70,29 +69,61 @@ def oracle_env(cfg):
     return b2o.load_env_yaml(os.path.join(ROOT, "box2d_sim_env_b200", "data", cfg["env"]))
 
 
-def synth_inputs(limits, n, seed, cfg=None, lo=0, hi=None):
-    """Inputs of one bench step for worlds lo:hi of an n-world batch: jittered initial states and robot
-    targets ~ U(velocity limits) resampled every 10 steps.  Counter-based (Philox) and indexed by world, so the CPU
-    and GPU arms — and any GPU count — draw identical controls for the same world."""
+# Top edge of the robot base's rectangle in the robot frame (the robot pose is the base link's centre of mass,
+# `use_center_of_mass: true`): the 0.8 m x 0.2 m rectangle's upper side, y = 0.2 m - com_y
+BASE_TOP_Y = {"test_env.yaml": 0.2 + 0.016667, "test_env_rigid_robot.yaml": 0.2 - 0.046667}
+OBJ_HALF = 0.05   # obj1 is a 0.1 m x 0.1 m box whose pose is its lower-left corner
+
+
+def robot_velocity_limits(env):
+    """[robot_dofs, 2] velocity limits of the first robot of an environment description (plain dicts): base x, y, theta,
+    then the joints in file order -- the same rows as Model.dof_limits()[:, 2:4], without touching the CUDA library."""
+    r = env["robots"][0]
+    ba = r["base_actuation"]
+    rows = [ba["translational_velocity_limits"], ba["translational_velocity_limits"], ba["rotational_velocity_limits"]]
+    rows += [j["velocity_limits"] for j in r["joints"]]
+    return np.array(rows, np.float32)
+
+
+def synth_inputs(vel_limits, n, seed, cfg=None, lo=0, hi=None):
+    """Inputs of one bench step for worlds lo:hi of an n-world batch.  Counter-based (Philox) and indexed
+    by world, so the CPU and GPU arms -- and any GPU count -- draw identical inputs for the same world.
+
+    cfg2 / cfg3 / cfg5 (robot + free box obj1 + hinged obstacle): the box starts in the robot's palm, between the fingers
+    and in front of the base -- a quarter of the worlds with the box resting against the base's front edge (within the
+    2 mm polygon skin: touching from the first step), the rest up to 0.3 m ahead with a random heading -- and the robot
+    pushes: targets ~ U(velocity limits), resampled every 10 steps, with the base's forward component folded to >= 0.
+    The rollout therefore runs the narrow phase, the contact solver and restitution on most worlds (the round-1
+    placement left the box 1.3 m away: 0 touching contacts in 1024 worlds)."""
     cfg = cfg or CONFIGS["cfg2"]
     hi = n if hi is None else hi
     nd = cfg["robot_dofs"]
+    vel_limits = np.asarray(vel_limits, np.float32)
+    if vel_limits.shape[1] == 6:          # Model.dof_limits() rows: position, velocity, acceleration (lo, hi)
+        vel_limits = vel_limits[:, 2:4]
     rng = np.random.Generator(np.random.Philox(key=seed))
-    if cfg["env"] == "test_env.yaml":
-        q = np.tile(BASE_Q, (n, 1))
-        q[:, 7:9] += rng.uniform(-0.2, 0.2, (n, 2)).astype(np.float32)
-        q[:, 9] = rng.uniform(-np.pi, np.pi, n).astype(np.float32)
-        qd = np.zeros_like(q)
-    elif cfg["env"] == "test_env_rigid_robot.yaml":
-        # robot(3) obj1(3) obj2(1, static hinge): obj1 in front of the pusher, jittered
-        q = np.tile(np.array([0, 0, 0, 0.9, 1.0, -1.0, 0.0], np.float32), (n, 1))
-        q[:, 3:5] += rng.uniform(-0.3, 0.3, (n, 2)).astype(np.float32)
-        q[:, 5] = rng.uniform(-np.pi, np.pi, n).astype(np.float32)
+    if cfg["env"] in BASE_TOP_Y:
+        ytop = BASE_TOP_Y[cfg["env"]]
+        resting = rng.uniform(0.0, 1.0, n) < 0.25
+        cx = rng.uniform(-0.17, 0.17, n)
+        cy = rng.uniform(ytop + 0.08, ytop + 0.30, n)
+        th = rng.uniform(-np.pi, np.pi, n)
+        gap = rng.uniform(0.0002, 0.0015, n)
+        cy = np.where(resting, ytop + gap + OBJ_HALF, cy)
+        th = np.where(resting, 0.0, th)
+        c, s = np.cos(th), np.sin(th)
+        first = 7 if nd == 7 else 3      # robot DOFs come first, then obj1 (x, y, theta), then obj2's hinge
+        q = np.zeros((n, first + 4), np.float32)
+        q[:, first] = cx - (c * OBJ_HALF - s * OBJ_HALF)
+        q[:, first + 1] = cy - (s * OBJ_HALF + c * OBJ_HALF)
+        q[:, first + 2] = th
         qd = np.zeros_like(q)
     else:
         from box2d_sim_env_b200 import envgen
         q, qd = envgen.clutter_states(n, seed=seed)
-    tg = rng.uniform(limits[:nd, 2], limits[:nd, 3], (N_TARGETS, n, nd)).astype(np.float32)
+    tg = rng.uniform(vel_limits[:nd, 0], vel_limits[:nd, 1], (N_TARGETS, n, nd)).astype(np.float32)
+    if cfg["env"] in BASE_TOP_Y:
+        tg[:, :, 1] = np.abs(tg[:, :, 1])   # the robot pushes forward
     return q[lo:hi], qd[lo:hi], np.ascontiguousarray(tg[:, lo:hi])
 
 
@@ -180,45 +211,122 @@ def cpu_oracle_throughput(cfg, limits, n_worlds, repeats, threads, seed0=9000):
     return n_worlds * ROLLOUT_STEPS, times
 
 
+def _touching_sets(gcounts, gio, oracle_batch, m):
+    """Per world: the sorted (fixtureA, fixtureB, manifold point count) tuples of the touching contacts, CUDA vs oracle."""
+    same, touching = 0, 0
+    for w in range(m):
+        oio, _ = oracle_batch.world(w).contacts()
+        k = int(gcounts[w])
+        g = sorted((int(r[0]), int(r[1]), int(r[4])) for r in gio[w, :k] if r[2])
+        o = sorted((int(r[0]), int(r[1]), int(r[4])) for r in oio if r[2])
+        same += int(g == o)
+        touching += len(o)
+    return same, touching
+
+
 def parity_gate(cfg, batch, limits, n, seed, threads, sample=1024):
-    """Correctness gate that accompanies the measurement: the first `sample` worlds of one bench step's
-    inputs go through the CUDA path and through the CPU oracle (here as the checker); compared after ONE step from the
-    identical fresh-cache state and after the whole 100-step rollout: DOF positions / velocities (max |diff|, worlds that
-    are bit-identical) and the touching-pair sets with their manifold point counts."""
+    """Correctness gate that accompanies the measurement (BASELINE.json).  The first `sample` worlds of one
+    bench step's inputs go through the CUDA path and through the CPU oracle (here as the checker):
+
+      single_step  one step from the identical fresh-cache state: DOF positions / velocities (max |diff|, worlds that are
+                   bit-identical) and the touching-pair sets with their manifold point counts;
+      rollout      the same comparison at every checkpoint of the 100-step rollout (after each 10-step target segment);
+      vs_libm      the divergence statistics the north star asks for: the same rollout on the oracle built with libm
+                   sinf / cosf in b2Rot (what upstream Box2D calls; the CUDA path and the oracle proper share one fixed
+                   sin / cos sequence, so their difference is 0 by construction) -- per checkpoint max / mean |dq|, |dqd|
+                   and the number of worlds whose touching-pair sets still agree.
+
+    The gate FAILS when it is vacuous: no touching contact after the single step, or fewer than one touching contact per
+    8 worlds summed over the rollout's checkpoints."""
     from oracle import b2o
     m = min(sample, n)
     q, qd, tg = synth_inputs(limits, n, seed, cfg)
+    env_desc = oracle_env(cfg)
+    env = b2o.OracleEnv(env_desc)
     out = {"worlds": m, "physics_steps": ROLLOUT_STEPS}
-    env = b2o.OracleEnv(oracle_env(cfg))
-    for label, n_tg, spt in (("single_step", 1, 1), ("rollout", N_TARGETS, STEPS_PER_TARGET)):
-        ob = b2o.OracleBatch(env, m)   # freshly loaded worlds: the CUDA side starts from fresh clones (reset_caches) too
-        gq, gqd = batch.rollout(0, tg[:n_tg], spt, q, qd, reset_caches=True)
-        counts, cio, _ = batch.contacts(max_per_world=64)
-        oq, oqd = ob.rollout(q[:m], qd[:m], 0, np.ascontiguousarray(tg[:n_tg, :m]), spt, threads)
+
+    def compare(gq, gqd, oq, oqd):
         dq = np.abs(gq[:m].astype(np.float64) - oq)
         dv = np.abs(gqd[:m].astype(np.float64) - oqd)
         same = np.all(gq[:m] == oq, axis=1) & np.all(gqd[:m] == oqd, axis=1)
-        pairs_ok, touching = 0, 0
-        for w in range(m):
-            oio, _ = ob.world(w).contacts()
-            k = int(counts[w])
-            g = sorted((int(r[0]), int(r[1]), int(r[4])) for r in cio[w, :k] if r[2])      # fixtureA, fixtureB, pointCount
-            o = sorted((int(r[0]), int(r[1]), int(r[4])) for r in oio if r[2])
-            pairs_ok += int(g == o)
-            touching += len(o)
-        out[label] = {"max_abs_dq": float(dq.max()), "max_abs_dqd": float(dv.max()), "mean_abs_dq": float(dq.mean()),
-                      "bit_identical_worlds": int(same.sum()), "touching_pair_sets_identical": pairs_ok,
-                      "touching_contacts": touching}
-    # BASELINE.json: single-step state error <= 1e-5 and bit-exact contact-pair sets / manifold point counts; multi-step
-    # trajectories are reported with their divergence statistics (here they are bit-identical as well)
-    out["pass"] = bool(out["single_step"]["max_abs_dq"] <= 1e-5 and out["single_step"]["max_abs_dqd"] <= 1e-5 and
-                       out["single_step"]["touching_pair_sets_identical"] == m and
-                       out["rollout"]["touching_pair_sets_identical"] == m)
+        return {"max_abs_dq": float(dq.max()), "max_abs_dqd": float(dv.max()), "mean_abs_dq": float(dq.mean()),
+                "mean_abs_dqd": float(dv.mean()), "bit_identical_worlds": int(same.sum())}
+
+    # ---- one step from the fresh-cache state
+    ob = b2o.OracleBatch(env, m)   # freshly loaded worlds: the CUDA side starts from fresh clones (reset_caches) too
+    gq, gqd = batch.rollout(0, tg[:1], 1, q, qd, reset_caches=True)
+    counts, cio, _ = batch.contacts(max_per_world=64)
+    oq, oqd = ob.rollout(q[:m], qd[:m], 0, np.ascontiguousarray(tg[:1, :m]), 1, threads)
+    single = compare(gq, gqd, oq, oqd)
+    single["touching_pair_sets_identical"], single["touching_contacts"] = _touching_sets(counts, cio, ob, m)
+    out["single_step"] = single
+
+    # ---- the rollout, compared at every checkpoint; the libm-trig oracle runs alongside
+    lm = b2o.load_variant("_libm")
+    ob = b2o.OracleBatch(env, m)
+    ol = lm.OracleBatch(lm.OracleEnv(env_desc), m)
+    roll = {"checkpoint_steps": [], "touching_contacts_at_checkpoint": [], "touching_pair_sets_identical_at_checkpoint": [],
+            "max_abs_dq": 0.0, "max_abs_dqd": 0.0, "bit_identical_worlds": m}
+    libm = {"checkpoint_steps": [], "max_abs_dq": [], "mean_abs_dq": [], "max_abs_dqd": [], "mean_abs_dqd": [],
+            "touching_pair_sets_identical": []}
+    for t in range(N_TARGETS):
+        first = t == 0
+        gq, gqd = batch.rollout(0, tg[t:t + 1], STEPS_PER_TARGET, q if first else None, qd if first else None,
+                                reset_caches=first)
+        counts, cio, _ = batch.contacts(max_per_world=64)
+        seg = np.ascontiguousarray(tg[t:t + 1, :m])
+        oq, oqd = ob.rollout(q[:m] if first else None, qd[:m] if first else None, 0, seg, STEPS_PER_TARGET, threads)
+        lq, lqd = ol.rollout(q[:m] if first else None, qd[:m] if first else None, 0, seg, STEPS_PER_TARGET, threads)
+        c = compare(gq, gqd, oq, oqd)
+        same, touching = _touching_sets(counts, cio, ob, m)
+        roll["checkpoint_steps"].append((t + 1) * STEPS_PER_TARGET)
+        roll["touching_contacts_at_checkpoint"].append(touching)
+        roll["touching_pair_sets_identical_at_checkpoint"].append(same)
+        roll["max_abs_dq"] = max(roll["max_abs_dq"], c["max_abs_dq"])
+        roll["max_abs_dqd"] = max(roll["max_abs_dqd"], c["max_abs_dqd"])
+        roll["bit_identical_worlds"] = min(roll["bit_identical_worlds"], c["bit_identical_worlds"])
+        d = compare(gq, gqd, lq, lqd)
+        libm["checkpoint_steps"].append((t + 1) * STEPS_PER_TARGET)
+        for k in ("max_abs_dq", "mean_abs_dq", "max_abs_dqd", "mean_abs_dqd"):
+            libm[k].append(d[k])
+        libm["touching_pair_sets_identical"].append(_touching_sets(counts, cio, ol, m)[0])
+    roll["touching_contacts"] = int(sum(roll["touching_contacts_at_checkpoint"]))
+    roll["touching_pair_sets_identical"] = int(min(roll["touching_pair_sets_identical_at_checkpoint"]))
+    stats = [ob.world(w).stats() for w in range(m)]
+    roll["toi_events"] = int(sum(x["toi_events"] for x in stats))
+    roll["toi_calls"] = int(sum(x["toi_calls"] for x in stats))
+    out["rollout"] = roll
+
+    # single step against the libm-trig oracle: the north star's 1e-5 bound against reference-like trigonometry
+    ol1 = lm.OracleBatch(lm.OracleEnv(env_desc), m)
+    gq, gqd = batch.rollout(0, tg[:1], 1, q, qd, reset_caches=True)
+    counts, cio, _ = batch.contacts(max_per_world=64)
+    lq, lqd = ol1.rollout(q[:m], qd[:m], 0, np.ascontiguousarray(tg[:1, :m]), 1, threads)
+    l1 = compare(gq, gqd, lq, lqd)
+    l1["touching_pair_sets_identical"] = _touching_sets(counts, cio, ol1, m)[0]
+    libm["single_step"] = l1
+    libm["what"] = "CUDA path vs the oracle rebuilt with libm sinf/cosf in b2Rot (upstream Box2D's calls)"
+    out["rollout_vs_libm"] = libm
+
+    nonvacuous = single["touching_contacts"] > 0 and roll["touching_contacts"] * 8 >= m
+    out["nonvacuous"] = bool(nonvacuous)
+    # BASELINE.json: single-step state error <= 1e-5 and bit-exact contact-pair sets / manifold point counts
+    out["pass"] = bool(nonvacuous and single["max_abs_dq"] <= 1e-5 and single["max_abs_dqd"] <= 1e-5 and
+                       single["touching_pair_sets_identical"] == m and roll["touching_pair_sets_identical"] == m and
+                       l1["max_abs_dq"] <= 1e-5 and l1["max_abs_dqd"] <= 1e-5)
     return out
 
 
 def workload_text(cfg, n):
     return cfg["text"] % n
+
+
+def config_dict(cfg, name, worlds_per_gpu_cfg, worlds_total):
+    """The `config` object both arms print (identical keys and values for the same command line)."""
+    return {"workload": workload_text(cfg, worlds_per_gpu_cfg), "name": name, "worlds_total": worlds_total,
+            "physics_steps_per_step": ROLLOUT_STEPS, "dt": 0.01, "velocity_iterations": 15, "position_iterations": 15,
+            "l2": "flushed between timed iterations (384 MB write)",
+            "inputs": "box in the robot's palm (1/4 resting against the base), forward-pushing random velocity targets"}
 
 
 def run_reference(args):
@@ -230,9 +338,10 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = CONFIGS[args.config]
-    limits = load_model(cfg).dof_limits()
+    limits = robot_velocity_limits(oracle_env(cfg))   # from the environment description: the CUDA library is never loaded here
     threads = host_threads()
     full = args.worlds or cfg["worlds"]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     n = min(full, args.ref_worlds)
     units, times = cpu_oracle_throughput(cfg, limits, n, args.warmup + args.steps, threads)
     timed = times[args.warmup:]
@@ -244,11 +353,10 @@ def run_reference(args):
         "impl": "reference", "metric": "world-steps/sec", "value": value, "unit": "world-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True,
         "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_text(cfg, full), "name": args.config, "worlds_per_step_sampled": n,
-                   "physics_steps_per_step": ROLLOUT_STEPS, "dt": 0.01, "velocity_iterations": 15, "position_iterations": 15},
+        "config": config_dict(cfg, args.config, full, full if cfg["scaling"] == "strong" else full * world),
         "cpu_baseline": {"value": value, "unit": "world-steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "sampled": {"worlds_per_step_sampled": n},
     }
     print(json.dumps(line))
 
@@ -379,7 +487,8 @@ def run_ours(args):
         dev_ms = timed_pass(args.steps, False, 100)
         kernel_ms, kernel_launches = batch.take_kernel_ms()
         launches = int(L.b2g_launch_count() - launches0)
-        counts, _, _ = batch.contacts(max_per_world=8)
+        counts, cio_end, _ = batch.contacts(max_per_world=16)
+        touching_per_world = float(cio_end[..., 2].sum()) / max(n, 1)
         e2e_ms = timed_pass(args.steps, True, 100)
     status = batch.status()
     extras = {}
@@ -403,26 +512,40 @@ def run_ours(args):
     achieved = bytes_per_launch * kernel_launches / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
 
     if rank == 0:
-        config = {"workload": workload_text(cfg, n_cfg), "name": args.config, "worlds_per_gpu": n, "worlds_total": n_total,
-                  "physics_steps_per_step": ROLLOUT_STEPS, "dt": 0.01, "velocity_iterations": 15, "position_iterations": 15,
-                  "l2": "flushed between timed iterations (384 MB write)",
-                  "status_nonzero_worlds": int((status != 0).sum()), "mean_live_contacts": mean_contacts}
-        config.update(extras)
+        prof = profile_metrics(args.config, n)
+        clock_summary = clocks.summary()
+        config = config_dict(cfg, args.config, n_cfg, n_total)
+        run_info = {"worlds_per_gpu": n, "status_nonzero_worlds": int((status != 0).sum()), "mean_live_contacts": mean_contacts,
+                    "touching_contacts_per_world": touching_per_world}
+        run_info.update(extras)
         line = {
             "metric": "world-steps/sec", "value": value, "unit": "world-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": cfg["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "world-steps/s",
                     "h2d_bytes_per_step": int(h_q.numel() * 4 * 2 + h_tg.numel() * 4), "d2h_bytes_per_step": int(h_out.numel() * 4)},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "run": run_info,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": MEASURED_TRAFFIC.get(args.config), "kernel": "k_step", "peak_kind": peak_kind,
-                         "sm_issue_active_pct": MEASURED_ISSUE_ACTIVE_PCT.get(args.config),
+                         "traffic": prof["traffic"] if prof else None, "kernel": "k_step", "peak_kind": peak_kind,
+                         "source": prof["source"] if prof else None,
+                         "sm_issue_active_pct": prof["sm_issue_active_pct"] if prof else None,
                          "kernel_ms_per_launch": kernel_ms / max(kernel_launches, 1),
                          "algorithmic_bytes_per_world_step": algorithmic_bytes_per_world_step(mean_contacts, cfg),
                          "note": "FP32 issue / dependent-latency bound, not bandwidth bound: DESIGN.md §3, profiles/"},
-            "clocks": clocks.summary(),
+            "clocks": clock_summary,
         }
+        if prof:
+            # the roof this path actually sits under: FP32 lane-issue slots.  thread instructions per world-step (ncu capture
+            # named in `source`) x measured world-steps/s of the kernel, against 148 SMs x 128 lanes x SM clock under load
+            mhz = clock_summary.get("sm_mhz") or clock_summary.get("sm_max_mhz") or 1965.0
+            lane_peak = 148 * 128 * mhz * 1e6
+            kernel_rate = n * ROLLOUT_STEPS * kernel_launches / (kernel_ms * 1e-3) if kernel_ms > 0 else 0.0
+            line["instruction_roofline"] = {
+                "thread_instructions_per_world_step": prof["thread_instructions_per_world_step"],
+                "lanes_active_per_instruction": prof["lanes_active_per_instruction"],
+                "achieved_thread_instructions_per_s": prof["thread_instructions_per_world_step"] * kernel_rate,
+                "peak_thread_instructions_per_s": lane_peak, "sm_mhz": mhz,
+                "frac": prof["thread_instructions_per_world_step"] * kernel_rate / lane_peak, "source": prof["source"]}
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
             nref = min(n, args.ref_worlds)
@@ -439,22 +562,46 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch (k_step / k_step_narrow) from `ncu --set full`, bytes per
-# launch of the config's default world count (profiles/r1e_<config>_<worlds>_k_step_ncu_full.txt)
-# smsp__issue_active.avg.pct_of_peak_sustained_active of the same captures: the path is bound by issue slots / dependent
-# latency, not by HBM, so the SM issue utilisation is reported next to the HBM fraction
-MEASURED_ISSUE_ACTIVE_PCT = {"cfg2": 21.6, "cfg3": 38.9, "cfg4": 26.7}
+_UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
-MEASURED_TRAFFIC = {
-    # 4096 worlds: the 32 MB state stays L2-resident across the 100 steps of a launch, DRAM sees far less than the
-    # algorithmic bytes (6.44 MB read + 0.46 MB written; profiles/r1f_cfg2_4096_k_step_ncu_full.txt)
-    "cfg2": 6444800 + 456960,
-    # 65536 rigid-robot worlds: 31.6 MB read + 24.5 MB written -- the touched part of the state stays in L2 as well
-    "cfg3": 31556352 + 24489728,
-    # 65536 clutter worlds: the ~9 KB a step touches per world (590 MB for the batch) does not fit the 126 MB L2, every
-    # step streams it: 69.1 GB read + 36.1 GB written per 6.55 M world-steps = 16 KB per world-step (algorithmic: 5.0 KB)
-    "cfg4": 69142817000 + 36054000000,
-}
+
+def profile_metrics(config_name, worlds):
+    """Counters of the stepping kernel from the newest committed `ncu --set full` summary of this config and world count
+    (profiles/r<round><letter>_<config>_<worlds>_k_step_ncu_full.txt, written by tools/ncu_profile_summary.py from ONE rollout
+    launch = 100 physics steps per world).  Returns None when no capture matches -- the bench line then prints null instead
+    of a stale constant."""
+    import glob
+    import re
+    pat = os.path.join(ROOT, "profiles", "r*_%s_%d_k_step_ncu_full.txt" % (config_name, worlds))
+
+    def order(path):  # r1e < r1f < r2a < r10a: (round number, letters)
+        m = re.match(r"r(\d+)([a-z]*)_", os.path.basename(path))
+        return (int(m.group(1)), m.group(2)) if m else (0, "")
+
+    files = sorted(glob.glob(pat), key=order)
+    if not files:
+        return None
+    vals = {}
+    for line in open(files[-1]):
+        f = line.split()
+        if len(f) >= 2 and ("__" in f[0]):
+            try:
+                v = float(f[-1])
+            except ValueError:
+                continue
+            vals[f[0]] = v * _UNIT.get(f[1], 1.0) if len(f) == 3 else v
+    need = ("dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum",
+            "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active")
+    if any(k not in vals for k in need):
+        return None
+    world_steps = float(worlds) * ROLLOUT_STEPS
+    return {"source": os.path.relpath(files[-1], ROOT),
+            "traffic": vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"],
+            "sm_issue_active_pct": vals["smsp__issue_active.avg.pct_of_peak_sustained_active"],
+            "lanes_active_per_instruction": vals["smsp__thread_inst_executed_per_inst_executed.ratio"],
+            "thread_instructions_per_world_step": vals["smsp__inst_executed.sum"] *
+                                                  vals["smsp__thread_inst_executed_per_inst_executed.ratio"] / world_steps,
+            "warp_instructions_per_launch": vals["smsp__inst_executed.sum"]}
 
 
 def main():

@@ -16,14 +16,29 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+# "" = the oracle proper (deterministic sin/cos shared with the CUDA path); "_libm" = the sensitivity variant whose b2Rot
+# calls libm sinf / cosf the way upstream Box2D does (oracle/Makefile: libb2o_libm.so, -DB2O_LIBM_TRIG)
+_VARIANT = ""
 
 
 def build(force=False):
-    so = os.path.join(_HERE, "libb2o.so")
+    target = "libb2o%s.so" % _VARIANT
+    so = os.path.join(_HERE, target)
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h"))]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["make", "-C", _HERE, "libb2o.so"], stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-C", _HERE, target], stdout=subprocess.DEVNULL)
     return so
+
+
+def load_variant(suffix):
+    """A second, independent copy of this module bound to libb2o<suffix>.so (e.g. "_libm"): every class of the copy
+    calls its own lib(), so both oracles can live in one process."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("oracle.b2o" + suffix, os.path.abspath(__file__))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod._VARIANT = suffix
+    return mod
 
 
 def lib():
