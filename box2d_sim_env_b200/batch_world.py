@@ -8,6 +8,7 @@ Reference interface mirrored (file:line in /root/reference):
   Box2DRobotVelocityController::setTargetVelocity  include/sim_env/Box2DController.h:23
 """
 import ctypes as C
+import weakref
 import os
 
 import numpy as np
@@ -189,9 +190,10 @@ def pinned_empty(shape, dtype=np.float32):
     p = C.c_void_p()
     _check(lib().b2g_host_alloc(C.byref(p), max(n, 1)))
     buf = (C.c_char * max(n, 1)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    arr._b2g_pinned = p  # keep the handle; memory is released with b2g_host_free(arr._b2g_pinned) by the caller
-    return arr
+    # the ctypes buffer is the base object of every view of the array: the page-locked block is released when the last
+    # view is gone (the finalizer holds the address, not the array)
+    weakref.finalize(buf, lib().b2g_host_free, C.c_void_p(p.value))
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 class Environment:

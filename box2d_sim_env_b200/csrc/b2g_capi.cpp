@@ -44,6 +44,26 @@ b2g_status cudaFail(cudaError_t e, const char* what) {
         if (e__ != cudaSuccess) return cudaFail(e__, #call); \
     } while (0)
 
+// Every entry point works on its batch's device and leaves the calling thread's current device as it found it (callers
+// that share the process -- torch tensors handed to the *_dev entry points -- keep allocating where they were).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err != cudaSuccess) { prev = -1; return; }
+        if (prev != device) err = cudaSetDevice(device); else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define ON_DEVICE(dev)                                                        \
+    DeviceGuard deviceGuard__(dev);                                           \
+    if (deviceGuard__.err != cudaSuccess) return cudaFail(deviceGuard__.err, "cudaSetDevice")
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -117,15 +137,16 @@ ObjectDescription* pickObject(b2g_env* env, int isRobot, int idx) {
     if (idx < 0 || idx >= (int)v.size()) return nullptr;
     return &v[idx];
 }
-cudaEvent_t getEvent(b2g_batch* b) {
+// Timing events of the stepping launches (b2g_batch_take_kernel_ms).  A planner that never asks for the timings must not
+// accumulate events: at most kMaxTimed launches are remembered, the oldest pair is recycled beyond that.
+constexpr size_t kMaxTimed = 64;
+cudaError_t getEvent(b2g_batch* b, cudaEvent_t* out) {
     if (!b->eventPool.empty()) {
-        cudaEvent_t e = b->eventPool.back();
+        *out = b->eventPool.back();
         b->eventPool.pop_back();
-        return e;
+        return cudaSuccess;
     }
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    return e;
+    return cudaEventCreate(out);
 }
 }  // namespace
 
@@ -389,7 +410,7 @@ static b2g_status createBatch(const HostModel& hostModel, int64_t n_worlds, int 
         return fail(B2G_ERR_CUDA, std::string("no CUDA device available (the batched backend has no CPU fallback): ") +
                                       cudaGetErrorString(e));
     if (device < 0 || device >= count) return fail(B2G_ERR_INVALID, "unknown device");
-    CU(cudaSetDevice(device));
+    ON_DEVICE(device);
     b2g_batch* b = new b2g_batch();
     b->m = hostModel;
     if (max_contacts > 0) layoutState(b->m.h, max_contacts > kMaxContacts ? kMaxContacts : max_contacts);
@@ -470,7 +491,7 @@ static b2g_status createBatch(const HostModel& hostModel, int64_t n_worlds, int 
 
 void b2g_batch_destroy(b2g_batch* b) {
     if (!b) return;
-    cudaSetDevice(b->device);
+    DeviceGuard guard(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (auto& s : b->stack) {
         cudaFree(s.q);
@@ -510,14 +531,14 @@ void* b2g_batch_stream(b2g_batch* b) { return b ? (void*)b->stream : nullptr; }
 
 b2g_status b2g_batch_sync(b2g_batch* b) {
     if (!b) return fail(B2G_ERR_INVALID, "null batch");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     CU(cudaStreamSynchronize(b->stream));
     return B2G_OK;
 }
 
 b2g_status b2g_batch_status(b2g_batch* b, int32_t* out) {
     if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     CU(b->stageA.reserve((size_t)b->n() * 4));
     CU(launchStatus(b->L(), (int*)b->stageA.p));
     CU(cudaMemcpyAsync(out, b->stageA.p, (size_t)b->n() * 4, cudaMemcpyDeviceToHost, b->stream));
@@ -529,7 +550,7 @@ b2g_status b2g_batch_status(b2g_batch* b, int32_t* out) {
 
 b2g_status b2g_batch_set_state_dev(b2g_batch* b, const float* q, const float* qd, int reset_caches) {
     if (!b || !q || !qd) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     if (reset_caches) CU(launchBroadcast(b->L(), b->tmpl));
     CU(launchSetState(b->L(), q, qd));
     return B2G_OK;
@@ -537,7 +558,7 @@ b2g_status b2g_batch_set_state_dev(b2g_batch* b, const float* q, const float* qd
 
 b2g_status b2g_batch_set_state(b2g_batch* b, const float* q, const float* qd, int reset_caches) {
     if (!b || !q || !qd) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     size_t bytes = (size_t)b->n() * b->m.h.nq * 4;
     CU(b->stageA.reserve(bytes));
     CU(b->stageB.reserve(bytes));
@@ -551,14 +572,14 @@ b2g_status b2g_batch_set_state(b2g_batch* b, const float* q, const float* qd, in
 
 b2g_status b2g_batch_get_state_dev(b2g_batch* b, float* q, float* qd) {
     if (!b || !q || !qd) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     CU(launchGetState(b->L(), q, qd));
     return B2G_OK;
 }
 
 b2g_status b2g_batch_get_state(b2g_batch* b, float* q, float* qd) {
     if (!b || !q || !qd) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     size_t bytes = (size_t)b->n() * b->m.h.nq * 4;
     CU(b->stageA.reserve(bytes));
     CU(b->stageB.reserve(bytes));
@@ -598,7 +619,7 @@ b2g_status b2g_batch_set_object_dofs(b2g_batch* b, int object, int velocities, c
     if (st) return st;
     if (sel.n == 0) return B2G_OK;
     if (!values) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     size_t bytes = (size_t)b->n() * sel.n * 4;
     CU(b->stageA.reserve(bytes));
     CU(cudaMemcpyAsync(b->stageA.p, values, bytes, cudaMemcpyHostToDevice, b->stream));
@@ -613,7 +634,7 @@ b2g_status b2g_batch_get_object_dofs(b2g_batch* b, int object, int velocities, c
     if (st) return st;
     if (sel.n == 0) return B2G_OK;
     if (!out) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     size_t bytes = (size_t)b->n() * sel.n * 4;
     CU(b->stageA.reserve(bytes));
     CU(launchGetObjectDofs(b->L(), object, sel, (float*)b->stageA.p, velocities));
@@ -624,7 +645,7 @@ b2g_status b2g_batch_get_object_dofs(b2g_batch* b, int object, int velocities, c
 
 b2g_status b2g_batch_set_object_pose(b2g_batch* b, int object, const float* pose) {
     if (!b || !pose || object < 0 || object >= b->m.h.no) return fail(B2G_ERR_INVALID, "unknown object");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     size_t bytes = (size_t)b->n() * 3 * 4;
     CU(b->stageA.reserve(bytes));
     CU(cudaMemcpyAsync(b->stageA.p, pose, bytes, cudaMemcpyHostToDevice, b->stream));
@@ -635,7 +656,7 @@ b2g_status b2g_batch_set_object_pose(b2g_batch* b, int object, const float* pose
 
 b2g_status b2g_batch_get_object_pose(b2g_batch* b, int object, float* pose) {
     if (!b || !pose || object < 0 || object >= b->m.h.no) return fail(B2G_ERR_INVALID, "unknown object");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     size_t bytes = (size_t)b->n() * 3 * 4;
     CU(b->stageA.reserve(bytes));
     CU(launchGetPose(b->L(), object, (float*)b->stageA.p));
@@ -655,7 +676,7 @@ b2g_status b2g_batch_set_target_velocity_dev(b2g_batch* b, int object, const flo
     b2g_status s = checkRobot(b, object);
     if (s) return s;
     if (!v) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     CU(launchSetTarget(b->L(), object, v));
     return B2G_OK;
 }
@@ -664,7 +685,7 @@ b2g_status b2g_batch_set_target_velocity(b2g_batch* b, int object, const float* 
     b2g_status s = checkRobot(b, object);
     if (s) return s;
     if (!v) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     size_t bytes = (size_t)b->n() * b->m.objects[object].nDofs * 4;
     CU(b->stageA.reserve(bytes));
     CU(cudaMemcpyAsync(b->stageA.p, v, bytes, cudaMemcpyHostToDevice, b->stream));
@@ -677,7 +698,7 @@ b2g_status b2g_batch_set_control_efforts_dev(b2g_batch* b, int object, const flo
     b2g_status s = checkRobot(b, object);
     if (s) return s;
     if (!efforts) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     CU(launchSetEfforts(b->L(), object, efforts));
     return B2G_OK;
 }
@@ -686,7 +707,7 @@ b2g_status b2g_batch_set_control_efforts(b2g_batch* b, int object, const float* 
     b2g_status s = checkRobot(b, object);
     if (s) return s;
     if (!efforts) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     size_t bytes = (size_t)b->n() * b->m.objects[object].nDofs * 4;
     CU(b->stageA.reserve(bytes));
     CU(cudaMemcpyAsync(b->stageA.p, efforts, bytes, cudaMemcpyHostToDevice, b->stream));
@@ -697,10 +718,22 @@ b2g_status b2g_batch_set_control_efforts(b2g_batch* b, int object, const float* 
 
 static b2g_status timedStep(b2g_batch* b, int object, const float* targets, int nTargets, int stepsPerTarget, int execCtrl,
                             int allowSleep) {
-    cudaEvent_t e0 = getEvent(b), e1 = getEvent(b);
-    CU(cudaEventRecord(e0, b->stream));
-    CU(launchStep(b->L(), object, targets, nTargets, stepsPerTarget, execCtrl, allowSleep));
-    CU(cudaEventRecord(e1, b->stream));
+    if (b->timed.size() >= kMaxTimed) {  // nobody collected the timings: forget the oldest launch, reuse its events
+        b->eventPool.push_back(b->timed.front().first);
+        b->eventPool.push_back(b->timed.front().second);
+        b->timed.erase(b->timed.begin());
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = getEvent(b, &e0);
+    if (e == cudaSuccess) e = getEvent(b, &e1);
+    if (e == cudaSuccess) e = cudaEventRecord(e0, b->stream);
+    if (e == cudaSuccess) e = launchStep(b->L(), object, targets, nTargets, stepsPerTarget, execCtrl, allowSleep);
+    if (e == cudaSuccess) e = cudaEventRecord(e1, b->stream);
+    if (e != cudaSuccess) {  // the events go back to the pool, nothing is leaked on the error path
+        if (e0) b->eventPool.push_back(e0);
+        if (e1) b->eventPool.push_back(e1);
+        return cudaFail(e, "stepping launch");
+    }
     b->timed.emplace_back(e0, e1);
     return B2G_OK;
 }
@@ -708,7 +741,7 @@ static b2g_status timedStep(b2g_batch* b, int object, const float* targets, int 
 b2g_status b2g_batch_step(b2g_batch* b, int steps, int execute_controllers, int allow_sleeping) {
     if (!b || steps < 0) return fail(B2G_ERR_INVALID, "bad step arguments");
     if (!b->allSelected()) return fail(B2G_ERR_INVALID, "stepping and the state stack act on the whole batch: call b2g_batch_select_worlds(batch, 0, 0) first");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     if (steps == 0) return B2G_OK;
     b2g_status s = timedStep(b, 0, nullptr, 1, steps, execute_controllers, allow_sleeping);
     if (s) return s;
@@ -721,7 +754,7 @@ b2g_status b2g_batch_rollout_dev(b2g_batch* b, int object, const float* targets,
     if (s) return s;
     if (!targets || n_targets < 0 || steps_per_target < 0) return fail(B2G_ERR_INVALID, "bad rollout arguments");
     if (!b->allSelected()) return fail(B2G_ERR_INVALID, "stepping and the state stack act on the whole batch: call b2g_batch_select_worlds(batch, 0, 0) first");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     if (n_targets == 0) return B2G_OK;
     return timedStep(b, object, targets, n_targets, steps_per_target, 1, 1);
 }
@@ -733,7 +766,7 @@ b2g_status b2g_batch_rollout(b2g_batch* b, int object, const float* q, const flo
     if (!targets || n_targets < 0 || steps_per_target < 0 || !q_out || !qd_out || (q == nullptr) != (qd == nullptr))
         return fail(B2G_ERR_INVALID, "bad rollout arguments");
     if (!b->allSelected()) return fail(B2G_ERR_INVALID, "stepping and the state stack act on the whole batch: call b2g_batch_select_worlds(batch, 0, 0) first");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     const size_t sb = (size_t)b->N * b->m.h.nq * 4;
     const size_t tb = (size_t)n_targets * b->N * b->m.objects[object].nDofs * 4;
     CU(b->stageA.reserve(sb));
@@ -759,7 +792,7 @@ b2g_status b2g_batch_rollout(b2g_batch* b, int object, const float* q, const flo
 
 b2g_status b2g_batch_set_to_rest(b2g_batch* b) {
     if (!b) return fail(B2G_ERR_INVALID, "null batch");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     CU(launchSetToRest(b->L()));
     CU(cudaStreamSynchronize(b->stream));
     return B2G_OK;
@@ -767,7 +800,7 @@ b2g_status b2g_batch_set_to_rest(b2g_batch* b) {
 
 b2g_status b2g_batch_at_rest(b2g_batch* b, float threshold, int32_t* out) {
     if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     CU(b->stageC.reserve((size_t)b->n() * 4));
     CU(launchAtRest(b->L(), threshold, (int*)b->stageC.p));
     CU(cudaMemcpyAsync(out, b->stageC.p, (size_t)b->n() * 4, cudaMemcpyDeviceToHost, b->stream));
@@ -778,7 +811,7 @@ b2g_status b2g_batch_at_rest(b2g_batch* b, float threshold, int32_t* out) {
 // getObjects(aabb, objects, exclude_robots) (:3207-3254): the box is scaled like the reference does (:3210-3214)
 b2g_status b2g_batch_objects_in_aabb(b2g_batch* b, const float aabb[4], int exclude_robots, uint8_t* hits) {
     if (!b || !aabb || !hits) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     const float s = b->m.h.scale;
     const int no = b->m.h.no;
     size_t bytes = (size_t)b->n() * no;
@@ -795,7 +828,7 @@ b2g_status b2g_batch_objects_in_aabb(b2g_batch* b, const float aabb[4], int excl
 
 b2g_status b2g_batch_is_physically_feasible(b2g_batch* b, int32_t* out) {
     if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     CU(b->stageC.reserve((size_t)b->n() * 4));
     CU(launchPhysicallyFeasible(b->L(), (int*)b->stageC.p));
     CU(cudaMemcpyAsync(out, b->stageC.p, (size_t)b->n() * 4, cudaMemcpyDeviceToHost, b->stream));
@@ -805,7 +838,7 @@ b2g_status b2g_batch_is_physically_feasible(b2g_batch* b, int32_t* out) {
 
 b2g_status b2g_batch_set_link_enabled(b2g_batch* b, int body, const uint8_t* enabled, int enabled_all) {
     if (!b || body <= 0 || body >= b->m.h.nb) return fail(B2G_ERR_INVALID, "unknown link (body 0 is the ground)");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     const unsigned char* dev = nullptr;
     if (enabled) {
         CU(b->stageC.reserve((size_t)b->n()));
@@ -836,7 +869,7 @@ b2g_status b2g_batch_set_link_property(b2g_batch* b, int body, int property, flo
     if (!b->allSelected())
         return fail(B2G_ERR_INVALID, "link parameters belong to the model all worlds of the batch share: call b2g_batch_select_worlds(batch, 0, 0) first");
     if (const char* why = badLinkValue(property, value)) return fail(B2G_ERR_INVALID, why);
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     bool massCenter = false;
     try {
         massCenter = setLinkProperty(b->m, body, property, value);
@@ -965,7 +998,7 @@ b2g_status b2g_batch_step_record(b2g_batch* b, int steps, int execute_controller
                                  int32_t* iout, float* fout, int max_per_world) {
     if (!b || steps < 0 || !counts || !iout || !fout || max_per_world <= 0) return fail(B2G_ERR_INVALID, "bad arguments");
     if (!b->allSelected()) return fail(B2G_ERR_INVALID, "stepping and the state stack act on the whole batch: call b2g_batch_select_worlds(batch, 0, 0) first");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     size_t cb = (size_t)b->n() * 4, ib = (size_t)b->n() * max_per_world * 4 * 4, fb = (size_t)b->n() * max_per_world * 6 * 4;
     size_t sb = (size_t)b->n() * b->m.h.nq * 4;
     CU(b->stageA.reserve(ib));
@@ -1005,7 +1038,7 @@ b2g_status b2g_batch_step_guarded(b2g_batch* b, int steps, int execute_controlle
                                   const uint8_t* allowed_pairs, int32_t* completed, int32_t* steps_done) {
     if (!b || steps < 0 || !allowed_pairs || !completed) return fail(B2G_ERR_INVALID, "bad arguments");
     if (!b->allSelected()) return fail(B2G_ERR_INVALID, "stepping and the state stack act on the whole batch: call b2g_batch_select_worlds(batch, 0, 0) first");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     const int nb = b->m.h.nb;
     size_t tb = (size_t)nb * nb, cb = (size_t)b->n() * 4;
     CU(b->stageA.reserve(tb));
@@ -1033,7 +1066,7 @@ b2g_status b2g_batch_step_guarded(b2g_batch* b, int steps, int execute_controlle
 
 b2g_status b2g_batch_take_kernel_ms(b2g_batch* b, float* out_ms, int32_t* out_launches) {
     if (!b || !out_ms) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     CU(cudaStreamSynchronize(b->stream));
     float total = 0.0f;
     for (auto& p : b->timed) {
@@ -1051,7 +1084,7 @@ b2g_status b2g_batch_take_kernel_ms(b2g_batch* b, float* out_ms, int32_t* out_la
 
 b2g_status b2g_batch_get_bodies(b2g_batch* b, float* out) {
     if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     size_t bytes = (size_t)b->n() * b->m.h.nb * 16 * 4;
     CU(b->stageA.reserve(bytes));
     CU(launchGetBodies(b->L(), (float*)b->stageA.p));
@@ -1063,7 +1096,7 @@ b2g_status b2g_batch_get_bodies(b2g_batch* b, float* out) {
 // Box2DLink::getPose / getVelocityVector / getCenterOfMass of every link of every (selected) world
 b2g_status b2g_batch_get_link_states(b2g_batch* b, float* out) {
     if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     size_t bytes = (size_t)b->n() * b->m.h.nb * 8 * 4;
     CU(b->stageA.reserve(bytes));
     CU(cudaMemsetAsync(b->stageA.p, 0, bytes, b->stream));  // the ground's rows
@@ -1075,7 +1108,7 @@ b2g_status b2g_batch_get_link_states(b2g_batch* b, float* out) {
 
 b2g_status b2g_batch_get_fat_aabbs(b2g_batch* b, float* out) {
     if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     size_t bytes = (size_t)b->n() * b->m.h.nf * 4 * 4;
     CU(b->stageA.reserve(bytes));
     CU(launchGetFat(b->L(), (float*)b->stageA.p));
@@ -1089,7 +1122,7 @@ b2g_status b2g_batch_get_ball_approximation(b2g_batch* b, int object, float* out
     const HostObjectInfo& o = b->m.objects[object];
     if (o.nBalls == 0) return B2G_OK;
     if (!out) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     if (!b->balls) {  // the ball table of the model, uploaded on first use
         CU(cudaMalloc((void**)&b->balls, b->m.balls.size() * sizeof(float)));
         CU(cudaMemcpyAsync(b->balls, b->m.balls.data(), b->m.balls.size() * sizeof(float), cudaMemcpyHostToDevice, b->stream));
@@ -1104,7 +1137,7 @@ b2g_status b2g_batch_get_ball_approximation(b2g_batch* b, int object, float* out
 
 b2g_status b2g_batch_get_joints(b2g_batch* b, int32_t* iout, float* fout) {
     if (!b || !iout || !fout) return fail(B2G_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     size_t ib = (size_t)b->n() * b->m.h.nj * 6 * 4, fb = (size_t)b->n() * b->m.h.nj * 15 * 4;
     CU(b->stageA.reserve(ib));
     CU(b->stageB.reserve(fb));
@@ -1117,7 +1150,7 @@ b2g_status b2g_batch_get_joints(b2g_batch* b, int32_t* iout, float* fout) {
 
 b2g_status b2g_batch_get_contacts(b2g_batch* b, int32_t* counts, int32_t* iout, float* fout, int max_per_world) {
     if (!b || !counts || !iout || !fout || max_per_world <= 0) return fail(B2G_ERR_INVALID, "bad arguments");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     size_t cb = (size_t)b->n() * 4, ib = (size_t)b->n() * max_per_world * 8 * 4, fb = (size_t)b->n() * max_per_world * 12 * 4;
     CU(b->stageA.reserve(ib));
     CU(b->stageB.reserve(fb));
@@ -1135,14 +1168,14 @@ b2g_status b2g_batch_get_contacts(b2g_batch* b, int32_t* counts, int32_t* iout, 
 b2g_status b2g_batch_check_collision_dev(b2g_batch* b, int32_t* counts, int32_t* iout, float* fout, int max_per_world) {
     if (!b || !counts || max_per_world < 0) return fail(B2G_ERR_INVALID, "bad arguments");
     if (!iout || !fout) max_per_world = 0;
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     CU(launchCheckCollision(b->L(), counts, iout, fout, max_per_world));
     return B2G_OK;
 }
 
 b2g_status b2g_batch_check_collision(b2g_batch* b, int32_t* counts, int32_t* iout, float* fout, int max_per_world) {
     if (!b || !counts || !iout || !fout || max_per_world <= 0) return fail(B2G_ERR_INVALID, "bad arguments");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     size_t cb = (size_t)b->n() * 4, ib = (size_t)b->n() * max_per_world * 4 * 4, fb = (size_t)b->n() * max_per_world * 6 * 4;
     CU(b->stageA.reserve(ib));
     CU(b->stageB.reserve(fb));
@@ -1161,7 +1194,7 @@ b2g_status b2g_batch_check_collision(b2g_batch* b, int32_t* counts, int32_t* iou
 b2g_status b2g_batch_save_state(b2g_batch* b) {
     if (!b) return fail(B2G_ERR_INVALID, "null batch");
     if (!b->allSelected()) return fail(B2G_ERR_INVALID, "stepping and the state stack act on the whole batch: call b2g_batch_select_worlds(batch, 0, 0) first");
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     SavedState s;
     size_t bytes = (size_t)b->n() * b->m.h.nq * 4;
     CU(cudaMalloc((void**)&s.q, bytes));
@@ -1182,7 +1215,7 @@ b2g_status b2g_batch_save_state(b2g_batch* b) {
 b2g_status b2g_batch_drop_state(b2g_batch* b) {
     if (!b) return fail(B2G_ERR_INVALID, "null batch");
     if (b->stack.empty()) return B2G_OK;
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     SavedState s = b->stack.back();
     b->stack.pop_back();
     cudaFree(s.q);
@@ -1195,7 +1228,7 @@ b2g_status b2g_batch_restore_state(b2g_batch* b) {
     if (!b) return fail(B2G_ERR_INVALID, "null batch");
     if (!b->allSelected()) return fail(B2G_ERR_INVALID, "stepping and the state stack act on the whole batch: call b2g_batch_select_worlds(batch, 0, 0) first");
     if (b->stack.empty()) return fail(B2G_ERR_INVALID, "state stack is empty");  // reference returns false (:3526-3528)
-    CU(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     SavedState& s = b->stack.back();
     for (auto& p : s.staticPoses) CU(launchSetPose(b->L(), p.first, p.second));
     CU(launchSetState(b->L(), s.q, s.qd));

@@ -321,7 +321,8 @@ void b2g_host_free(void* p);
 /* counters: kernels launched by this library since load (bench evidence) */
 uint64_t b2g_launch_count(void);
 /* device-side timing of the launches made since the last call (CUDA events on the batch stream):
- * returns the accumulated milliseconds of step/rollout kernels and resets the accumulator */
+ * returns the accumulated milliseconds of step/rollout kernels and resets the accumulator.  At most the 64 most recent
+ * stepping launches are remembered (callers that never collect timings do not accumulate events). */
 b2g_status b2g_batch_take_kernel_ms(b2g_batch* batch, float* out_ms, int32_t* out_launches);
 
 #ifdef __cplusplus
