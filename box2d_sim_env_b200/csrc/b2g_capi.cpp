@@ -109,6 +109,7 @@ struct b2g_batch {
     int block = 32;
     int stepBlock = 32;
     int stepLanes = 32;
+    int stepLpw = 1;
     DevBuf stageA, stageB, stageC, stageD, stageE;
     std::vector<SavedState> stack;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
@@ -127,6 +128,7 @@ struct b2g_batch {
         l.block = block;
         l.stepBlock = stepBlock;
         l.stepLanes = stepLanes;
+        l.stepLpw = stepLpw;
         return l;
     }
 };
@@ -454,6 +456,14 @@ static b2g_status createBatch(const HostModel& hostModel, int64_t n_worlds, int 
         b->stepLanes = l <= 8 ? (int)l : (l <= 16 ? 16 : 32);
     }
     if (b->stepLanes < 1 || b->stepLanes > 32) b->stepLanes = 32;
+    // lanes per world (b2g_multi.cuh): experiments / tests choose with B2G_LPW
+    const char* envLpw = getenv("B2G_LPW");
+    b->stepLpw = envLpw ? atoi(envLpw) : 1;
+    if (b->stepLpw != 1 && b->stepLpw != 2 && b->stepLpw != 4 && b->stepLpw != 8 && b->stepLpw != 16 && b->stepLpw != 32) b->stepLpw = 1;
+    if (b->stepLpw > 1) {
+        const int maxWorlds = 32 / b->stepLpw;
+        if (!envLanes || b->stepLanes > maxWorlds) b->stepLanes = maxWorlds;
+    }
     auto cleanup = [&](cudaError_t err, const char* what) {
         b2g_batch_destroy(b);
         return cudaFail(err, what);

@@ -12,6 +12,7 @@
 #include "b2g_launch.h"
 #include "b2g_query.cuh"
 #include "b2g_world.cuh"
+#include "b2g_multi.cuh"
 
 namespace b2g {
 
@@ -248,6 +249,44 @@ __global__ void k_step_narrow(const __grid_constant__ ModelHeader hdr, const uin
             setTarget(c, object, lv);
         }
         for (int s = 0; s < stepsPerTarget; ++s) stepWorld<false>(c, executeControllers != 0, allowSleeping != 0);
+    }
+}
+
+// Small and medium batches: a world is owned by LPW lanes of a warp (b2g_multi.cuh); `wpw` <= 32 / LPW worlds per warp, one
+// warp per CTA.  Warp g owns worlds [g * wpw, (g + 1) * wpw); the lists of each world live in shared memory behind the model.
+DEV WorldShared* worldShared(const ModelHeader& hdr, int slot) {
+    return reinterpret_cast<WorldShared*>(g_sm + kHdrWords + ((hdr.words + 3) & ~3)) + slot;
+}
+template <int LPW>
+__global__ void __launch_bounds__(32) k_step_multi(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
+                                                   long long N, StepParams prm, int object, const float* __restrict__ targets,
+                                                   int nTargets, int stepsPerTarget, int executeControllers, int allowSleeping, int wpw) {
+    B2G_STAGE();
+    const int lane = threadIdx.x & 31;
+    const int slot = lane / LPW;
+    const long long w = (long long)blockIdx.x * wpw + slot;
+    const bool live = slot < wpw && w < N;
+    const unsigned warpMask = __ballot_sync(0xffffffffu, live);
+    if (!live) return;  // whole groups leave: the group barriers only name lanes of one group
+    Grp<LPW> g;
+    g.warp = warpMask;
+    g.s = lane % LPW;
+    g.mask = (LPW == 32 ? 0xffffffffu : ((1u << LPW) - 1u)) << (lane - g.s);
+    WorldShared& W = *worldShared(hdr, slot);
+    if (g.s == 0) W.keyNj = -1;  // no schedule cached yet
+    Ctx c;
+    c.P = worldBase(S, hdr.stateChunks, w);
+    for (int t = 0; t < nTargets; ++t) {
+        if (targets != nullptr) {
+            if (g.s == 0) {
+                int n = mI(c, mobj(c, object, MO_NDOFS));
+                float lv[kMaxDofsPerObject];
+                for (int i = 0; i < n; ++i) lv[i] = targets[((size_t)t * N + w) * n + i];
+                setTarget(c, object, lv);
+            }
+            gsync(g);
+        }
+        for (int s = 0; s < stepsPerTarget; ++s) stepWorldMulti<LPW>(c, g, W, executeControllers != 0, allowSleeping != 0);
     }
 }
 
@@ -577,6 +616,27 @@ cudaError_t launchSetEfforts(const Launch& L, int object, const float* v) { LAUN
 cudaError_t launchSetTarget(const Launch& L, int object, const float* v) { LAUNCH(k_set_target, object, v); }
 cudaError_t launchStep(const Launch& L, int object, const float* targets, int nTargets, int stepsPerTarget, int execCtrl,
                        int allowSleep) {
+    if (L.stepLpw > 1) {  // small / medium batch: LPW lanes per world, stepLanes worlds per warp, one warp per CTA
+        const size_t bytes = (((size_t)kHdrWords + ((L.h.words + 3) & ~3)) * 4) + (size_t)L.stepLanes * sizeof(WorldShared) + smemPad();
+        const unsigned blocks = (unsigned)((L.N + L.stepLanes - 1) / L.stepLanes);
+#define B2G_MULTI(LPW)                                                                                                          \
+    {                                                                                                                            \
+        if (bytes > 48 * 1024) {                                                                                                 \
+            cudaError_t e = cudaFuncSetAttribute((const void*)k_step_multi<LPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); \
+            if (e != cudaSuccess) return e;                                                                                      \
+        }                                                                                                                        \
+        k_step_multi<LPW><<<blocks, 32, bytes, L.stream>>>(L.h, L.blob, L.S, L.N, L.prm, object, targets, nTargets, stepsPerTarget, \
+                                                           execCtrl, allowSleep, L.stepLanes);                                  \
+    }
+        if (L.stepLpw == 2) B2G_MULTI(2)
+        else if (L.stepLpw == 4) B2G_MULTI(4)
+        else if (L.stepLpw == 8) B2G_MULTI(8)
+        else if (L.stepLpw == 16) B2G_MULTI(16)
+        else B2G_MULTI(32)
+#undef B2G_MULTI
+        ++g_launches;
+        return cudaGetLastError();
+    }
     if (L.stepLanes < 32) {  // small batch: narrow warps, one warp per CTA
         cudaError_t e = prepare((const void*)k_step_narrow, L.h);
         if (e != cudaSuccess) return e;

@@ -15,7 +15,8 @@ struct Launch {
     cudaStream_t stream;
     int block;             // threads per CTA
     int stepBlock;         // threads per CTA of k_step (power of two <= kWorldPad)
-    int stepLanes;         // worlds per warp of the stepping kernel: 32, or a smaller power of two for small batches
+    int stepLanes;         // worlds per warp of the stepping kernel: 32, or fewer for small batches
+    int stepLpw;           // lanes per world: 1 = one thread per world (k_step / k_step_narrow); 2, 4, 8 = k_step_multi
 };
 
 // a selection of object-local DOF indices (ascending) passed to the per-object DOF kernels by value

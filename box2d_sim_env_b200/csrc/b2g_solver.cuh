@@ -915,12 +915,15 @@ DEV void phaseSync() {
 }
 
 
-// b2World::Solve + b2Island::Solve for every island of the world, then SynchronizeFixtures + FindNewContacts
-template <bool SYNC>
-DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
+// ---- island lists ------------------------------------------------------------------------------------------------------
+// Shared by the one-thread-per-world solver (lists in local memory, WorldLists) and the sub-warp-per-world solver (lists in
+// shared memory, b2g_multi.cuh): `Lists` only needs WorldLists' members.
+//
+// Islands by DFS in upstream order (b2World::Solve: body list newest first, contact edges before joint edges, both newest
+// first); returns the mask of static bodies that joined at least one island.
+template <class Lists>
+DEV uint64_t buildIslands(Ctx c, Lists& L) {
     const int nb = H().nb;
-    const float h = PRM().dt;
-    WorldLists L;
     L.ndyn = 0; L.nj = 0; L.nc = 0; L.nIslands = 0;
     uint64_t bodyFlag = 0ull;      // dynamic bodies that are in some island
     uint64_t staticSeen = 0ull;    // static bodies that joined at least one island
@@ -936,7 +939,6 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
         if ((fl & CF_ENABLED) != 0 && (fl & CF_TOUCHING) != 0) contactLive[k >> 6] |= 1ull << (k & 63);
     }
 
-    // ---- islands by DFS in upstream order (body list: newest first)
     unsigned char stack[kMaxBodies];
     for (int seed = nb - 1; seed >= 0; --seed) {
         if ((bodyFlag >> seed) & 1ull) continue;
@@ -987,67 +989,101 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
             }
         }
     }
+    return staticSeen;
+}
 
-    // The order of islands inside the flat lists is free (they are independent).  Upstream finds them newest body
-    // first, which puts the free objects before the robot; emitting them in the opposite order keeps the lanes of
-    // a warp aligned on the robot's joints (same model, same DFS) and leaves the part that differs from world to
-    // world (which objects are awake) at the tail, where every entry has the same type.
-    phaseSync<SYNC, 2>();
-    //
-    // "Simple" islands -- one dynamic body held by its ground-friction joint, no contacts: a free object, or a rigid
-    // robot that touches nothing -- leave the lists altogether: their 15 velocity iterations only ever touch one body
-    // and one joint, so they run in registers (frictionIslandSolve) instead of streaming the same chunks through
-    // L1/L2 fifteen times.  `simple` = mask of those islands, their joints go to the tail of L.joints.
+// The order of islands inside the flat lists is free (they are independent).  Upstream finds them newest body
+// first, which puts the free objects before the robot; emitting them in the opposite order keeps the lanes of
+// a warp aligned on the robot's joints (same model, same DFS) and leaves the part that differs from world to
+// world (which objects are awake) at the tail, where every entry has the same type.
+//
+// "Simple" islands -- one dynamic body held by its ground-friction joint, no contacts: a free object, or a rigid
+// robot that touches nothing -- leave the lists altogether: their 15 velocity iterations only ever touch one body
+// and one joint, so they run in registers (frictionIslandSolve) instead of streaming the same chunks through
+// L1/L2 fifteen times.  Returns the mask of those islands; their joints go to the tail of L.joints (nSimple entries
+// behind L.nj).
+template <class Lists>
+DEV uint64_t reorderIslands(Ctx c, Lists& L, int& nSimple) {
     uint64_t simple = 0ull;
-    int nSimple = 0;
-    {
-        unsigned char tmp[kMaxJoints];
-        unsigned char tail[kMaxBodies];
-        L.jStart[L.nIslands] = (unsigned char)L.nj;
-        L.cStart[L.nIslands] = (unsigned char)L.nc;
-        int n = 0;
-        for (int isl = L.nIslands - 1; isl >= 0; --isl) {
-            const int j0 = L.jStart[isl], nj = L.jStart[isl + 1] - j0, nc = L.cStart[isl + 1] - L.cStart[isl];
-            if (nj == 1 && nc == 0) {
-                const int4 jh = mi4(c, mjoint(c, L.joints[j0], MJ_TYPE));
-                if (jh.x == 0 && (jh.w & 12) == 4) {  // friction joint, bodyA static, bodyB dynamic
-                    simple |= 1ull << isl;
-                    tail[nSimple++] = L.joints[j0];
-                    continue;
-                }
+    nSimple = 0;
+    unsigned char tmp[kMaxJoints];
+    unsigned char tail[kMaxBodies];
+    L.jStart[L.nIslands] = (unsigned char)L.nj;
+    L.cStart[L.nIslands] = (unsigned char)L.nc;
+    int n = 0;
+    for (int isl = L.nIslands - 1; isl >= 0; --isl) {
+        const int j0 = L.jStart[isl], nj = L.jStart[isl + 1] - j0, nc = L.cStart[isl + 1] - L.cStart[isl];
+        if (nj == 1 && nc == 0) {
+            const int4 jh = mi4(c, mjoint(c, L.joints[j0], MJ_TYPE));
+            if (jh.x == 0 && (jh.w & 12) == 4) {  // friction joint, bodyA static, bodyB dynamic
+                simple |= 1ull << isl;
+                tail[nSimple++] = L.joints[j0];
+                continue;
             }
-            for (int i = j0; i < j0 + nj; ++i) tmp[n++] = L.joints[i];
         }
-        for (int i = 0; i < n; ++i) L.joints[i] = tmp[i];
-        for (int i = 0; i < nSimple; ++i) L.joints[n + i] = tail[i];
-        L.nj = n;
-        n = 0;
-        for (int isl = L.nIslands - 1; isl >= 0; --isl)
-            for (int i = L.cStart[isl]; i < L.cStart[isl + 1]; ++i) tmp[n++] = L.contacts[i];
-        for (int i = 0; i < n; ++i) L.contacts[i] = tmp[i];
+        for (int i = j0; i < j0 + nj; ++i) tmp[n++] = L.joints[i];
     }
+    for (int i = 0; i < n; ++i) L.joints[i] = tmp[i];
+    for (int i = 0; i < nSimple; ++i) L.joints[n + i] = tail[i];
+    L.nj = n;
+    n = 0;
+    for (int isl = L.nIslands - 1; isl >= 0; --isl)
+        for (int i = L.cStart[isl]; i < L.cStart[isl + 1]; ++i) tmp[n++] = L.contacts[i];
+    for (int i = 0; i < n; ++i) L.contacts[i] = tmp[i];
+    return simple;
+}
+
+// b2Island::Solve "integrate velocities" for one island body (c0 = c, a0 = a, alpha0 = 0 ride along)
+DEV void integrateVelocity(Ctx c, int b, float h) {
+    const int bo = bslot(c, b, 0);
+    const float4 bm = m4(c, mbody(c, b, MB_INVMASS));
+    Pos P = ldPosAt(c, bo);
+    st4(c, bo + SB_POS04, mk4(P.c.x, P.c.y, P.a, 0.0f));  // c0 = c, a0 = a, alpha0 = 0
+    Vel V = ldVelAt(c, bo);
+    // only a robot's base link ever receives forces; for every other body the chunk is the constant +0
+    const float4 ft = mI(c, mbody(c, b, MB_FORCED)) ? ld4(c, bo + SB_FORCE4) : mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    V2 f = mk(ft.x, ft.y);
+    float tq = ft.z;
+    float im = bm.x, ii = bm.y;
+    // gravity is (0,0), gravityScale 1, damping 0 (Box2DWorld.cpp:3668; b2BodyDef defaults)
+    V2 acc = 1.0f * mk(0.0f, 0.0f) + im * f;
+    V.v = V.v + h * acc;
+    V.w += h * ii * tq;
+    float ld = 1.0f / (1.0f + h * 0.0f);
+    V.v = mk(V.v.x * ld, V.v.y * ld);
+    V.w *= ld;
+    stVelAt(c, bo, V);
+}
+
+// SynchronizeTransform of an island body fused with its SynchronizeFixtures; returns the bits for the move buffer and the
+// body's sleep time.  xf1 = the transform at the start of the step: its rotation b2Rot(a0) is the m_xf.q still stored at this
+// point, xf1.p = c0 - q * localCenter is recomputed (see contactInit).
+DEV uint64_t syncIslandBody(Ctx c, int b, float& sleepTime) {
+    const int bo = bslot(c, b, 0);
+    const V2 lc = localCenter(c, b);
+    XF xf1, xf2;
+    xf1.q = ldRotAt(c, bo);
+    xf1.p = ldV2(c, bo + SB_C0X) - mul(xf1.q, lc);
+    const float4 p = ld4(c, bo + SB_POS4);  // c, a, sleep time
+    xf2.q = rotOf(p.z);                     // b2Body::SynchronizeTransform
+    xf2.p = mk(p.x, p.y) - mul(xf2.q, lc);
+    stXF(c, b, xf2);
+    sleepTime = p.w;
+    return syncBodyFixtures(c, b, xf1, xf2);
+}
+
+// b2World::Solve + b2Island::Solve for every island of the world, then SynchronizeFixtures + FindNewContacts
+template <bool SYNC>
+DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
+    const float h = PRM().dt;
+    WorldLists L;
+    const uint64_t staticSeen = buildIslands(c, L);
+    phaseSync<SYNC, 2>();
+    int nSimple = 0;
+    const uint64_t simple = reorderIslands(c, L, nSimple);
 
     // ---- b2Island::Solve, all islands together
-    for (int i = 0; i < L.ndyn; ++i) {  // c0 = c, integrate velocities
-        const int bo = bslot(c, L.dyn[i], 0);
-        const float4 bm = m4(c, mbody(c, L.dyn[i], MB_INVMASS));
-        Pos P = ldPosAt(c, bo);
-        st4(c, bo + SB_POS04, mk4(P.c.x, P.c.y, P.a, 0.0f));  // c0 = c, a0 = a, alpha0 = 0
-        Vel V = ldVelAt(c, bo);
-        // only a robot's base link ever receives forces; for every other body the chunk is the constant +0
-        const float4 ft = mI(c, mbody(c, L.dyn[i], MB_FORCED)) ? ld4(c, bo + SB_FORCE4) : mk4(0.0f, 0.0f, 0.0f, 0.0f);
-        V2 f = mk(ft.x, ft.y);
-        float tq = ft.z;
-        float im = bm.x, ii = bm.y;
-        // gravity is (0,0), gravityScale 1, damping 0 (Box2DWorld.cpp:3668; b2BodyDef defaults)
-        V2 acc = 1.0f * mk(0.0f, 0.0f) + im * f;
-        V.v = V.v + h * acc;
-        V.w += h * ii * tq;
-        float ld = 1.0f / (1.0f + h * 0.0f);
-        V.v = mk(V.v.x * ld, V.v.y * ld);
-        V.w *= ld;
-        stVelAt(c, bo, V);
-    }
+    for (int i = 0; i < L.ndyn; ++i) integrateVelocity(c, L.dyn[i], h);  // c0 = c, integrate velocities
     phaseSync<SYNC, 3>();
     for (int i = 0; i < L.nc; ++i) contactInit(c, L.contacts[i], dtRatio, true);
     for (int i = 0; i < L.nc; ++i) contactWarmStart(c, L.contacts[i]);
@@ -1112,18 +1148,10 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
     for (int i = 0; i < L.nIslands; ++i) minSleep[i] = FLT_MAX;
     for (int i = 0; i < L.ndyn; ++i) {
         const int b = L.dyn[i];
-        const int bo = bslot(c, b, 0);
-        const V2 lc = localCenter(c, b);
-        XF xf1, xf2;
-        xf1.q = ldRotAt(c, bo);
-        xf1.p = ldV2(c, bo + SB_C0X) - mul(xf1.q, lc);
-        const float4 p = ld4(c, bo + SB_POS4);  // c, a, sleep time
-        xf2.q = rotOf(p.z);                     // b2Body::SynchronizeTransform
-        xf2.p = mk(p.x, p.y) - mul(xf2.q, lc);
-        stXF(c, b, xf2);
+        float sleepTime;
+        moved |= syncIslandBody(c, b, sleepTime);
         const int isl = L.bodyIsl[b];
-        minSleep[isl] = fminT(minSleep[isl], p.w);
-        moved |= syncBodyFixtures(c, b, xf1, xf2);
+        minSleep[isl] = fminT(minSleep[isl], sleepTime);
     }
     for (uint64_t m = staticSeen; m; m &= m - 1ull) syncTransform(c, __ffsll((long long)m) - 1);
 
