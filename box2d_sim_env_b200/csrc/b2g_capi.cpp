@@ -110,6 +110,7 @@ struct b2g_batch {
     int stepBlock = 32;
     int stepLanes = 32;
     int stepLpw = 1;
+    int sms = 148;
     DevBuf stageA, stageB, stageC, stageD, stageE;
     std::vector<SavedState> stack;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
@@ -421,9 +422,12 @@ static b2g_status createBatch(const HostModel& hostModel, int64_t n_worlds, int 
     b->N = n_worlds;
     b->selFirst = 0;
     b->selCount = n_worlds;
+    int sms = 148;  // SM count of the batch's device (B200: 148; 4 warp schedulers each)
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms < 1) sms = 148;
+    b->sms = sms;
     const char* envBlock = getenv("B2G_BLOCK");
     if (envBlock) b->block = atoi(envBlock);
-    else b->block = n_worlds <= 148 * 32 * 8 ? 32 : 64;
+    else b->block = n_worlds <= (long long)sms * 32 * 8 ? 32 : 64;
     if (b->block < 32 || b->block > 1024 || (b->block & (b->block - 1))) b->block = 32;
     // CTA size of the stepping kernel: its warps walk the solver phases together (phase barriers), which keeps the
     // instruction cache on one phase; one warp per CTA while the batch does not fill the GPU anyway
@@ -437,8 +441,8 @@ static b2g_status createBatch(const HostModel& hostModel, int64_t n_worlds, int 
         // with one CTA next to SMs with two.  Fewer resident warps per SM also keep the velocity-iteration working set
         // closer to the L1 capacity.  65536 worlds: 293 CTAs of 224 threads instead of 256 of 256.
         const long long warps = (n_worlds + 31) / 32;
-        const long long waves = (warps + 148 * 16 - 1) / (148 * 16);
-        const long long perSM = (warps + waves * 148 - 1) / (waves * 148);
+        const long long waves = (warps + sms * 16 - 1) / (sms * 16);
+        const long long perSM = (warps + waves * sms - 1) / (waves * sms);
         long long w = (perSM + 1) / 2;
         if (w < 1) w = 1;
         if (w > 8) w = 8;
@@ -450,9 +454,12 @@ static b2g_status createBatch(const HostModel& hostModel, int64_t n_worlds, int 
     const char* envLanes = getenv("B2G_LANES");
     if (envLanes) b->stepLanes = atoi(envLanes);
     else {
-        // as few worlds per warp as one-warp-per-scheduler allows; above 8 lanes a power of two (measured: 11 or 14 lanes
-        // lose more to row segments that straddle 128-byte lines than they gain over 16)
-        long long l = (n_worlds + 591) / 592;
+        // As few worlds per warp as keeps the batch on at most 512 warps (a B200 has 592 warp schedulers); above 8 lanes a
+        // power of two (11 or 14 lanes lose more to row segments that straddle 128-byte lines than they gain over 16).
+        // Measured on the contact-rich cfg 2 workload, 4096 worlds, ms per 100 steps: 4 -> 24.3, 5 -> 21.0, 6 -> 17.5,
+        // 7 -> 15.6, 8 -> 14.6, 16 -> 14.3 (profiles/r2_mode_sweep.txt).
+        const long long warpsTarget = (long long)sms * 4 * 7 / 8;  // 518 on a 148-SM B200
+        long long l = (n_worlds + warpsTarget - 1) / warpsTarget;
         b->stepLanes = l <= 8 ? (int)l : (l <= 16 ? 16 : 32);
     }
     if (b->stepLanes < 1 || b->stepLanes > 32) b->stepLanes = 32;

@@ -10,6 +10,7 @@
 // reference calls through b2World::Step (src/sim_env/Box2DWorld.cpp:3279).
 #pragma once
 #include <cfloat>
+#include <cstdio>
 #include <cstdint>
 
 #include "model.h"
@@ -140,25 +141,46 @@ struct Ctx {
 
 // per-world state access: `off` is a byte offset (chunk * 512 + word * 4, see model.h); signed so that constant
 // field offsets fold into the instruction's immediate
-DEV char* sp(Ctx c, int off) {
+// B2G_CHECK (tools/checked_build.sh): the stand-in for compute-sanitizer's memcheck on pools where the tool is closed.  Every
+// state access is checked against the world's chunk range (and its alignment), every model read against the blob size, every
+// list append against its capacity; a violation prints what and where and traps the kernel.
+#ifdef B2G_CHECK
+#define B2G_ASSERT(cond, what, a, b)                                                                                    \
+    do {                                                                                                                 \
+        if (!(cond)) {                                                                                                   \
+            printf("B2G_CHECK failed: %s (%d, %d) block %d thread %d\n", what, (int)(a), (int)(b), blockIdx.x, threadIdx.x); \
+            __trap();                                                                                                    \
+        }                                                                                                                \
+    } while (0)
+#else
+#define B2G_ASSERT(cond, what, a, b) ((void)0)
+#endif
+
+template <int BYTES>
+DEV char* spn(Ctx c, int off) {
     __builtin_assume(__isGlobal(c.P));
+    B2G_ASSERT(off >= 0 && (off & 511) + BYTES <= 16 && (off >> 9) < H().stateChunks && (off & (BYTES - 1)) == 0,
+               "state access outside the world's chunks / misaligned", off, BYTES);
     return c.P + off;
 }
-DEV float ldF(Ctx c, int off) { return *reinterpret_cast<const float*>(sp(c, off)); }
-DEV void stF(Ctx c, int off, float v) { *reinterpret_cast<float*>(sp(c, off)) = v; }
-DEV int ldI(Ctx c, int off) { return *reinterpret_cast<const int*>(sp(c, off)); }
-DEV void stI(Ctx c, int off, int v) { *reinterpret_cast<int*>(sp(c, off)) = v; }
-DEV float4 ld4(Ctx c, int off) { return *reinterpret_cast<const float4*>(sp(c, off)); }
-DEV void st4(Ctx c, int off, float4 v) { *reinterpret_cast<float4*>(sp(c, off)) = v; }
-DEV float2 ld2(Ctx c, int off) { return *reinterpret_cast<const float2*>(sp(c, off)); }
-DEV void st2(Ctx c, int off, float2 v) { *reinterpret_cast<float2*>(sp(c, off)) = v; }
+DEV char* sp(Ctx c, int off) { return spn<4>(c, off); }
+DEV float ldF(Ctx c, int off) { return *reinterpret_cast<const float*>(spn<4>(c, off)); }
+DEV void stF(Ctx c, int off, float v) { *reinterpret_cast<float*>(spn<4>(c, off)) = v; }
+DEV int ldI(Ctx c, int off) { return *reinterpret_cast<const int*>(spn<4>(c, off)); }
+DEV void stI(Ctx c, int off, int v) { *reinterpret_cast<int*>(spn<4>(c, off)) = v; }
+DEV float4 ld4(Ctx c, int off) { return *reinterpret_cast<const float4*>(spn<16>(c, off)); }
+DEV void st4(Ctx c, int off, float4 v) { *reinterpret_cast<float4*>(spn<16>(c, off)) = v; }
+DEV float2 ld2(Ctx c, int off) { return *reinterpret_cast<const float2*>(spn<8>(c, off)); }
+DEV void st2(Ctx c, int off, float2 v) { *reinterpret_cast<float2*>(spn<8>(c, off)) = v; }
 DEV float4 mk4(float x, float y, float z, float w) { return make_float4(x, y, z, w); }
 
 // model blob access (shared memory, warp-uniform addresses: broadcast reads)
-DEV float mF(Ctx, int off) { return __uint_as_float(g_sm[kHdrWords + off]); }
-DEV int mI(Ctx, int off) { return (int)g_sm[kHdrWords + off]; }
-DEV float4 m4(Ctx, int off) { return *reinterpret_cast<const float4*>(g_sm + kHdrWords + off); }  // off % 4 == 0
-DEV float2 m2(Ctx, int off) { return *reinterpret_cast<const float2*>(g_sm + kHdrWords + off); }  // off % 2 == 0
+// (the region query reads one scratch fixture record behind the blob, b2g_kernels.cu: launchObjectsInAABB)
+#define B2G_MODEL_OK(off, n) B2G_ASSERT((off) >= 0 && (off) + (n) <= H().words + 2 * MF_STRIDE && ((off) & ((n) - 1)) == 0, "model read outside the blob / misaligned", off, n)
+DEV float mF(Ctx, int off) { B2G_MODEL_OK(off, 1); return __uint_as_float(g_sm[kHdrWords + off]); }
+DEV int mI(Ctx, int off) { B2G_MODEL_OK(off, 1); return (int)g_sm[kHdrWords + off]; }
+DEV float4 m4(Ctx, int off) { B2G_MODEL_OK(off, 4); return *reinterpret_cast<const float4*>(g_sm + kHdrWords + off); }  // off % 4 == 0
+DEV float2 m2(Ctx, int off) { B2G_MODEL_OK(off, 2); return *reinterpret_cast<const float2*>(g_sm + kHdrWords + off); }  // off % 2 == 0
 
 DEV int bslot(Ctx c, int b, int f) { return (H().cBody + b * SB_CHUNKS) * kChunkBytes + f; }
 DEV int fslot(Ctx c, int f) { return (H().cFix + f) * kChunkBytes; }

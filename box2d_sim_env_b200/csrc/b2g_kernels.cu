@@ -698,7 +698,7 @@ cudaError_t launchBroadcast(const Launch& L, const float* tmpl) {  // worlds [pr
     long long total = (((first + count + 31) >> 5) - (first >> 5)) * L.h.stateChunks * kTileWorlds;
     int threads = 256;
     long long want = (total + threads - 1) / threads;
-    unsigned blocks = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+    unsigned blocks = (unsigned)(want < 4096 ? want : 4096);  // grid-stride copy: a few CTAs per SM saturate HBM
     k_broadcast<<<blocks, threads, 0, L.stream>>>(reinterpret_cast<float4*>(L.S), reinterpret_cast<const float4*>(tmpl), first, count,
                                                  L.h.stateChunks);
     ++g_launches;

@@ -48,7 +48,7 @@ struct JointRec {
     int base;  // word offset of the record in the blob
 };
 DEV JointRec jrec(Ctx c, int j) { JointRec r; r.base = mjoint(c, j, 0); return r; }
-DEV int4 mi4(Ctx, int off) { return *reinterpret_cast<const int4*>(g_sm + kHdrWords + off); }
+DEV int4 mi4(Ctx, int off) { B2G_MODEL_OK(off, 4); return *reinterpret_cast<const int4*>(g_sm + kHdrWords + off); }
 DEV Vel ldVelAt(Ctx c, int boff) {
     float4 q = ld4(c, boff + SB_VEL4);
     Vel r;
@@ -958,6 +958,7 @@ DEV uint64_t buildIslands(Ctx c, Lists& L) {
                 staticSeen |= 1ull << b;  // its awake flag is settled after the sleep decisions (see below)
                 continue;
             }
+            B2G_ASSERT(L.ndyn < kMaxBodies && sp <= kMaxBodies, "island body list / DFS stack overflow", L.ndyn, sp);
             L.dyn[L.ndyn++] = (unsigned char)b;
             wakeBody(c, b);
             // contact edges of b, newest first
@@ -966,6 +967,7 @@ DEV uint64_t buildIslands(Ctx c, Lists& L) {
                 if (cA != b && cB != b) continue;
                 if ((contactFlag[k >> 6] >> (k & 63)) & 1ull) continue;
                 if (((contactLive[k >> 6] >> (k & 63)) & 1ull) == 0ull) continue;
+                B2G_ASSERT(L.nc < kMaxContacts, "island contact list overflow", L.nc, k);
                 L.contacts[L.nc++] = (unsigned char)k;
                 contactFlag[k >> 6] |= 1ull << (k & 63);
                 int other = cA == b ? cB : cA;
@@ -981,6 +983,7 @@ DEV uint64_t buildIslands(Ctx c, Lists& L) {
                 int j = packed & 0xffff;
                 int other = packed >> 16;
                 if ((jointFlag[j >> 6] >> (j & 63)) & 1ull) continue;
+                B2G_ASSERT(L.nj < kMaxJoints, "island joint list overflow", L.nj, j);
                 L.joints[L.nj++] = (unsigned char)j;
                 jointFlag[j >> 6] |= 1ull << (j & 63);
                 if (((bodyFlag | staticFlag) >> other) & 1ull) continue;

@@ -74,6 +74,36 @@ def random_states(model, n, seed, spread=1.2, vel=1.0):
     return q, qd
 
 
+def base_front_edge(fat_aabbs_world0, scale=10.0):
+    """y of the robot base rectangle's front (upper) edge in the robot frame, read off the fat AABB of fixture 1 of a freshly
+    loaded world (robot at the origin): fat = tight + polygon radius (0.01) + aabb extension (0.1), Box2D units."""
+    return (float(fat_aabbs_world0[1][3]) - 0.11) / scale
+
+
+def feasible_states(model, n, seed, ytop):
+    """Physically feasible (no initial interpenetration) contact-rich states for the shipped env shapes and their variants:
+    the robot at the origin at rest, obj1 in the robot's palm -- a quarter of the worlds with the box resting against the
+    base's front edge inside the polygon skin (touching from the first step) --, obj2 where its YAML puts it.  The same
+    placement bench.py uses for BASELINE.json configs[1] / [2]."""
+    rng = np.random.default_rng(seed)
+    q = np.zeros((n, model.nq), np.float32)
+    qd = np.zeros((n, model.nq), np.float32)
+    for o in model.objects:
+        off = o["dof_offset"]
+        if o["name"] == "obj1":
+            resting = rng.uniform(0, 1, n) < 0.25
+            cx = rng.uniform(-0.17, 0.17, n)
+            cy = np.where(resting, ytop + rng.uniform(0.0002, 0.0015, n) + 0.05, rng.uniform(ytop + 0.08, ytop + 0.30, n))
+            th = np.where(resting, 0.0, rng.uniform(-np.pi, np.pi, n))
+            c, s = np.cos(th), np.sin(th)
+            q[:, off] = cx - (c * 0.05 - s * 0.05)
+            q[:, off + 1] = cy - (s * 0.05 + c * 0.05)
+            q[:, off + 2] = th
+        elif o["name"] == "obj2" and not o["is_static"]:
+            q[:, off:off + 3] = [2.9, 1.2, -6.12]
+    return q, qd
+
+
 def random_targets(model, robot, n, seed, segments=1):
     rng = np.random.default_rng(seed)
     lim = model.dof_limits()

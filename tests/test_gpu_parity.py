@@ -7,8 +7,8 @@ import os
 import numpy as np
 import pytest
 
-from parity_utils import (ENV_2, ENV_3, ENV_A, ENV_B, compare_world, env_dict, load_env_dict, oracle_worlds, random_states,
-                          random_targets)
+from parity_utils import (ENV_2, ENV_3, ENV_A, ENV_B, base_front_edge, compare_world, env_dict, feasible_states, load_env_dict, oracle_worlds,
+                          random_states, random_targets)
 
 pytestmark = pytest.mark.gpu
 
@@ -853,3 +853,138 @@ def test_link_states_parity(b2g, env_name):
         if not o["is_static"]:
             base = [b for b in range(o["first_body"], o["first_body"] + o["n_links"]) if batch.model.link(b)["is_base_link"]][0]
             assert np.array_equal(ls[:, base, :3], q[:, o["dof_offset"]:o["dof_offset"] + 3])
+
+
+# ---- round 2 ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("env_name", [ENV_A, ENV_B, ENV_2, ENV_3, "clutter"])
+def test_single_step_vs_libm_trig_oracle(b2g, env_name):
+    """North-star tolerance against reference-like trigonometry: the oracle rebuilt with libm sinf / cosf in b2Rot (what
+    upstream Box2D calls; the CUDA path and the oracle proper share one fixed sin / cos sequence, so their difference is 0 by
+    construction).  One step from an identical, physically feasible fresh-cache state: |dq|, |dqd| <= 1e-5 (m, rad, m/s,
+    rad/s); the touching contact-pair sets with their manifold point counts identical.  (From interpenetrating random states
+    the same comparison stays within 7e-6 on positions but reaches 7e-5 rad/s on a few percent of the worlds: the dynamics
+    amplify a last-bit difference of sin / cos there)"""
+    from oracle import b2o
+    lm = b2o.load_variant("_libm")
+    n = 192
+    if env_name == "clutter":
+        from box2d_sim_env_b200 import envgen
+        desc = envgen.clutter_env()
+        batch = b2g.BatchBox2DWorld(n).loadWorld(b2g.Model(desc))
+        q, qd = envgen.clutter_states(n, seed=31, speed=2.0)
+        # a second step target: let the clutter slide into contact first (60 steps on both sides with the exact oracle), then
+        # compare ONE step of the libm variant from that state
+        warm = 60
+    else:
+        desc = env_dict(env_name)
+        batch = make_batch(b2g, env_name, n)
+        q, qd = feasible_states(batch.model, n, 31, base_front_edge(batch.fat_aabbs()[0]))
+        warm = 0
+    tgt = random_targets(batch.model, 0, n, seed=32)[0]
+    tgt[:, 1] = np.abs(tgt[:, 1])   # the robot pushes towards the box
+    if warm:
+        ob = b2o.OracleBatch(b2o.OracleEnv(desc), n)
+        q, qd = ob.rollout(q, qd, 0, tgt[None], warm, os.cpu_count() or 4)
+    gq, gqd = batch.rollout(0, tgt[None], 1, q, qd, reset_caches=True)
+    counts, cio, _ = batch.contacts(max_per_world=128)
+    ol = lm.OracleBatch(lm.OracleEnv(desc), n)
+    lq, lqd = ol.rollout(q, qd, 0, tgt[None], 1, os.cpu_count() or 4)
+    assert np.max(np.abs(gq.astype(np.float64) - lq)) <= 1e-5, np.max(np.abs(gq - lq))
+    assert np.max(np.abs(gqd.astype(np.float64) - lqd)) <= 1e-5, np.max(np.abs(gqd - lqd))
+    touching = 0
+    for w in range(n):
+        oio, _ = ol.world(w).contacts()
+        g = sorted((int(r[0]), int(r[1]), int(r[4])) for r in cio[w, :int(counts[w])] if r[2])
+        o = sorted((int(r[0]), int(r[1]), int(r[4])) for r in oio if r[2])
+        assert g == o, "world %d: touching pair sets differ between the CUDA path and the libm-trig oracle" % w
+        touching += len(o)
+    assert touching > 10, "scenario produced too few touching contacts"
+
+
+@pytest.mark.parametrize("lpw,lanes", [(4, None), (2, None), (8, 3), (16, None), (32, None)])
+@pytest.mark.parametrize("env_name", [ENV_A, ENV_B])
+def test_sub_warp_per_world_kernel_parity(b2g, env_name, lpw, lanes, monkeypatch):
+    """k_step_multi: a world owned by 2 .. 32 lanes (lane-strided body / joint / contact loops, dataflow-scheduled velocity
+    iterations from the cached slot table).  Contact-rich 120-step rollout, every segment bit-identical to the oracle; the
+    schedule cache is exercised by topologies that change as contacts begin and end."""
+    monkeypatch.setenv("B2G_LPW", str(lpw))
+    if lanes:
+        monkeypatch.setenv("B2G_LANES", str(lanes))
+    n = 77
+    batch = make_batch(b2g, env_name, n)
+    worlds = oracle_worlds(env_dict(env_name), n)
+    q, qd = random_states(batch.model, n, seed=41, spread=0.5)
+    tg = random_targets(batch.model, 0, n, seed=42, segments=12)
+    batch.setWorldState(q, qd, reset_caches=True)
+    for w, ow in enumerate(worlds):
+        ow.set_state(q[w], qd[w])
+    scatter_obstacle(batch, worlds, seed=43)
+    touching = 0
+    for seg in range(12):
+        batch.setTargetVelocity(0, tg[seg])
+        batch.stepPhysics(10, allow_sleeping=(seg % 4 != 3))
+        for w, ow in enumerate(worlds):
+            ow.set_target_velocity(0, tg[seg][w])
+            ow.step(10, True, seg % 4 != 3)
+        assert_same(batch, worlds, "lpw %d segment %d" % (lpw, seg))
+        touching += int(batch.contacts()[1][..., 2].sum())
+    assert touching > 50
+    assert np.all(batch.status() == 0)
+
+
+def test_sub_warp_per_world_clutter_and_serial_fallback(b2g, monkeypatch):
+    """Shape C on the sub-warp kernel: dozens of simple islands strided over the lanes, merged islands whose constraint count
+    exceeds the schedule's 32-node limit take the sequential fallback; 2 velocity iterations exercise short lap counts."""
+    from box2d_sim_env_b200 import envgen
+    monkeypatch.setenv("B2G_LPW", "4")
+    n = 20
+    env = envgen.clutter_env()
+    batch = b2g.BatchBox2DWorld(n).loadWorld(b2g.Model(env))
+    worlds = oracle_worlds(env, n)
+    q, qd = envgen.clutter_states(n, seed=8, speed=3.0)
+    tg = random_targets(batch.model, 0, n, seed=9, segments=5)
+    batch.setWorldState(q, qd, reset_caches=True)
+    for w, ow in enumerate(worlds):
+        ow.set_state(q[w], qd[w])
+    for seg in range(5):
+        if seg == 3:
+            batch.setVelocitySteps(2)
+            batch.setPositionSteps(3)
+            for ow in worlds:
+                ow.set_params(0.01, 2, 3)
+        batch.setTargetVelocity(0, tg[seg])
+        batch.stepPhysics(10)
+        for w, ow in enumerate(worlds):
+            ow.set_target_velocity(0, tg[seg][w])
+            ow.step(10)
+        assert_same(batch, worlds, "clutter on 4 lanes per world, segment %d" % seg)
+    assert np.all(batch.status() == 0)
+
+
+def test_pinned_empty_and_current_device(b2g):
+    """pinned_empty returns page-locked memory that the one-call rollout reads and writes directly and that is released with
+    the array; entry points leave the caller's current CUDA device alone."""
+    import gc
+    import torch
+    n = 64
+    batch = make_batch(b2g, ENV_A, n)
+    q = b2g.pinned_empty((n, batch.nq))
+    qd = b2g.pinned_empty((n, batch.nq))
+    q0, qd0 = random_states(batch.model, n, seed=51, spread=0.6)
+    q[:] = q0
+    qd[:] = qd0
+    tg = b2g.pinned_empty((2, n, 7))
+    tg[:] = random_targets(batch.model, 0, n, seed=52, segments=2)
+    oq, oqd = b2g.pinned_empty((n, batch.nq)), b2g.pinned_empty((n, batch.nq))
+    batch.rollout_host(0, q.ctypes.data, qd.ctypes.data, tg.ctypes.data, 2, 5, oq.ctypes.data, oqd.ctypes.data)
+    gq, gqd = batch.getWorldState()
+    assert np.array_equal(gq, oq) and np.array_equal(gqd, oqd)
+    view = oq[:4]
+    del oq
+    gc.collect()
+    assert np.array_equal(view, gq[:4])   # the block lives as long as any view of it
+    if torch.cuda.device_count() > 1:
+        other = b2g.BatchBox2DWorld(8, device=1).loadWorld(b2g.data_path(ENV_A))
+        torch.cuda.set_device(0)
+        other.stepPhysics(1)
+        assert torch.cuda.current_device() == 0
