@@ -361,25 +361,17 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def run_ours(args):
+def measure(args, cfg_name, n_cfg, steps, warmup, ctx, with_cpu):
+    """One benchmark record of config `cfg_name` on this rank's GPU (all ranks call it together).  Returns the JSON-line dict on
+    rank 0, None elsewhere."""
     import torch
     import torch.distributed as dist
     import box2d_sim_env_b200 as b2g
     from box2d_sim_env_b200 import sharding
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the batched backend has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    cfg = CONFIGS[args.config]
+    world, rank, local, dev = ctx["world"], ctx["rank"], ctx["local"], ctx["dev"]
+    cfg = CONFIGS[cfg_name]
     strong = cfg["scaling"] == "strong"
-    n_cfg = args.worlds or cfg["worlds"]
     if strong:   # total work fixed: rank r owns a contiguous slice of the n_cfg worlds
         n_total = n_cfg
         lo, hi = sharding.world_slice(n_total, rank, world)
@@ -401,23 +393,38 @@ def run_ours(args):
     d_tg = torch.empty((N_TARGETS, n, nd), dtype=torch.float32, device=dev)
     d_out = torch.empty((n, 2, nq), dtype=torch.float32, device=dev)     # row w = [q_w | qd_w]
     d_all = torch.empty((n_total, 2, nq), dtype=torch.float32, device=dev) if world > 1 else None
-    flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    flush = ctx["flush"]
     # pinned host staging for the end-to-end path
     h_q = torch.empty((n, nq), dtype=torch.float32).pin_memory()
     h_qd = torch.empty_like(h_q).pin_memory()
     h_tg = torch.empty((N_TARGETS, n, nd), dtype=torch.float32).pin_memory()
-    h_out = torch.empty((n, 2, nq), dtype=torch.float32).pin_memory()
     h_oq = torch.empty((n, nq), dtype=torch.float32).pin_memory()
     h_oqd = torch.empty((n, nq), dtype=torch.float32).pin_memory()
     d_oq = torch.empty((n, nq), dtype=torch.float32, device=dev)
     d_oqd = torch.empty_like(d_oq)
+    # several GPUs, end to end: the ONE call a C++ planner makes on a multi-GPU node, b2g_multi_rollout (include/b2g.h), issued
+    # by rank 0 for all `world` devices of the node -- host buffers for the whole job in, all-gathered states out; the other
+    # ranks wait at the barrier
+    multi = None
+    if world > 1 and rank == 0:
+        multi = b2g.MultiGpuBatch(model, n_total, list(range(world)))
+        m_q = torch.empty((n_total, nq), dtype=torch.float32).pin_memory()
+        m_qd = torch.empty_like(m_q).pin_memory()
+        m_tg = torch.empty((N_TARGETS, n_total, nd), dtype=torch.float32).pin_memory()
+        m_oq = torch.empty((n_total, nq), dtype=torch.float32).pin_memory()
+        m_oqd = torch.empty_like(m_oq).pin_memory()
+        m_stream = torch.cuda.ExternalStream(L.b2g_batch_stream(multi.shard(0)[0]), device=torch.device("cuda", 0))
+    gather_events = []
+
+    def rows(step_idx, first, last):
+        # weak scaling: every rank draws its own batch; strong scaling: rows of the one global batch
+        if strong:
+            return synth_inputs(limits, n_total, 1234 + step_idx, cfg, first, last)
+        parts = [synth_inputs(limits, n_cfg, 1234 + 1000 * r + step_idx, cfg) for r in range(first // n_cfg, (last + n_cfg - 1) // n_cfg)]
+        return (np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]), np.concatenate([p[2] for p in parts], axis=1))
 
     def load_inputs(step_idx, to_device):
-        # weak scaling: every rank draws its own batch; strong scaling: rows lo:hi of the one global batch
-        if strong:
-            q, qd, tg = synth_inputs(limits, n_total, 1234 + step_idx, cfg, lo, hi)
-        else:
-            q, qd, tg = synth_inputs(limits, n, 1234 + 1000 * rank + step_idx, cfg)
+        q, qd, tg = rows(step_idx, lo, hi)
         h_q.copy_(torch.from_numpy(q))
         h_qd.copy_(torch.from_numpy(qd))
         h_tg.copy_(torch.from_numpy(tg))
@@ -435,7 +442,11 @@ def run_ours(args):
             d_out[:, 0].copy_(d_oq)
             d_out[:, 1].copy_(d_oqd)
             if world > 1:   # the path's only collective: final gather of the rollout states over NCCL
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record(stream)
                 sharding.gather_states(d_out, n_total, out=d_all)
+                g1.record(stream)
+                gather_events.append((g0, g1))
 
     def barrier():
         stream.synchronize()
@@ -447,28 +458,40 @@ def run_ours(args):
     def timed_pass(n_steps, e2e, first_idx):
         total_ms = 0.0
         for s in range(n_steps):
-            load_inputs(first_idx + s, to_device=not e2e)
+            if e2e and world > 1:
+                if rank == 0:
+                    q, qd, tg = rows(first_idx + s, 0, n_total)
+                    m_q.copy_(torch.from_numpy(q))
+                    m_qd.copy_(torch.from_numpy(qd))
+                    m_tg.copy_(torch.from_numpy(tg))
+            else:
+                load_inputs(first_idx + s, to_device=not e2e)
             with torch.cuda.stream(stream):
                 flush.zero_()  # evict L2 between timed iterations
             barrier()
+            if e2e and world > 1:
+                ms = 0.0
+                if rank == 0:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(m_stream)
+                    multi.rollout_host(0, m_q.data_ptr(), m_qd.data_ptr(), m_tg.data_ptr(), N_TARGETS, STEPS_PER_TARGET,
+                                       m_oq.data_ptr(), m_oqd.data_ptr())
+                    e1.record(m_stream)
+                    m_stream.synchronize()
+                    ms = e0.elapsed_time(e1)
+                barrier()
+                total_ms += ms
+                continue
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            if e2e and world == 1:
+            if e2e:
                 # the call a planner makes: ONE host-pointer C-ABI call (b2g_batch_rollout) on pinned host buffers --
                 # H2D of states and targets, fresh-clone set_state, the rollout kernel, get_state, D2H of the results
                 batch.rollout_host(0, h_q.data_ptr(), h_qd.data_ptr(), h_tg.data_ptr(), N_TARGETS, STEPS_PER_TARGET,
                                    h_oq.data_ptr(), h_oqd.data_ptr())
             else:
-                if e2e:
-                    with torch.cuda.stream(stream):
-                        d_q.copy_(h_q, non_blocking=True)
-                        d_qd.copy_(h_qd, non_blocking=True)
-                        d_tg.copy_(h_tg, non_blocking=True)
                 rollout_device()
-                if e2e:
-                    with torch.cuda.stream(stream):
-                        h_out.copy_(d_out, non_blocking=True)
             e1.record(stream)
             barrier()
             total_ms += e0.elapsed_time(e1)
@@ -478,21 +501,39 @@ def run_ours(args):
         return float(t.item())
 
     # warm-up (nothing is JIT-compiled: the library is prebuilt), then the timed region
-    warm = max(args.warmup, 3)
+    warm = max(warmup, 3) if cfg_name != "cfg5" or args.config == "cfg5" else max(warmup, 1)
     timed_pass(warm, False, 0)
     timed_pass(1, True, 50)   # the end-to-end path once, untimed: first use allocates its staging buffers
     batch.take_kernel_ms()
+    del gather_events[:]
     launches0 = L.b2g_launch_count()
     with ClockSampler(local) as clocks:
-        dev_ms = timed_pass(args.steps, False, 100)
+        dev_ms = timed_pass(steps, False, 100)
         kernel_ms, kernel_launches = batch.take_kernel_ms()
         launches = int(L.b2g_launch_count() - launches0)
         counts, cio_end, _ = batch.contacts(max_per_world=16)
         touching_per_world = float(cio_end[..., 2].sum()) / max(n, 1)
-        e2e_ms = timed_pass(args.steps, True, 100)
+        gather_ms = sum(a.elapsed_time(b) for a, b in gather_events) / max(len(gather_events), 1) if gather_events else None
+        e2e_ms = timed_pass(steps, True, 100)
     status = batch.status()
+    multi_info = None
+    if world > 1:
+        # where the step's time goes on N GPUs: the rollout kernel of every rank (min / max over ranks) and the all-gather,
+        # which also waits for the slowest rank's kernel
+        k = torch.tensor([kernel_ms / max(kernel_launches, 1)], dtype=torch.float64, device=dev)
+        kmin, kmax, g = k.clone(), k.clone(), torch.tensor([gather_ms or 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(kmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(kmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(g, op=dist.ReduceOp.MAX)
+        multi_info = {"kernel_ms_per_launch_min_over_ranks": float(kmin.item()), "kernel_ms_per_launch_max_over_ranks": float(kmax.item()),
+                      "gather_ms_max_over_ranks": float(g.item()), "gather_bytes": int(n_total * 2 * nq * 4),
+                      "collective": "ncclAllGather of [worlds_total, 2, nq] f32 on the batch stream (torch.distributed, one process per GPU)",
+                      "e2e_path": "b2g_multi_rollout (C ABI, one process drives all GPUs: H2D of every slice, kernels, ncclAllGather, D2H)"}
+        if multi is not None:
+            multi_info["c_abi_last_timing"] = multi.last_timing()
+            multi.close()
     extras = {}
-    if args.config == "cfg4":   # batched checkCollision on the rolled-out worlds, device-timed
+    if cfg_name == "cfg4":   # batched checkCollision on the rolled-out worlds, device-timed
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         d_counts = torch.empty(n, dtype=torch.int32, device=dev)
         batch.check_collision_dev(d_counts.data_ptr())
@@ -504,26 +545,33 @@ def run_ours(args):
         extras["check_collision_worlds_per_s"] = n * 5 / (ev0.elapsed_time(ev1) * 1e-3)
 
     units_per_step = n_total * ROLLOUT_STEPS
-    value = units_per_step * args.steps / (dev_ms * 1e-3)
-    e2e_value = units_per_step * args.steps / (e2e_ms * 1e-3)
+    value = units_per_step * steps / (dev_ms * 1e-3)
+    e2e_value = units_per_step * steps / (e2e_ms * 1e-3)
     mean_contacts = float(counts.mean())
     peak, peak_kind = measured_peak()
     bytes_per_launch = algorithmic_bytes_per_world_step(mean_contacts, cfg) * n * ROLLOUT_STEPS
     achieved = bytes_per_launch * kernel_launches / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
 
+    line = None
     if rank == 0:
-        prof = profile_metrics(args.config, n)
+        prof = profile_metrics(cfg_name, n)
         clock_summary = clocks.summary()
-        config = config_dict(cfg, args.config, n_cfg, n_total)
+        config = config_dict(cfg, cfg_name, n_cfg, n_total)
         run_info = {"worlds_per_gpu": n, "status_nonzero_worlds": int((status != 0).sum()), "mean_live_contacts": mean_contacts,
                     "touching_contacts_per_world": touching_per_world}
         run_info.update(extras)
+        if world > 1:
+            h2d = int((2 * n_total * nq + N_TARGETS * n_total * nd) * 4)
+            d2h = int(2 * n_total * nq * 4)
+        else:
+            h2d = int(h_q.numel() * 4 * 2 + h_tg.numel() * 4)
+            d2h = int((h_oq.numel() + h_oqd.numel()) * 4)
         line = {
-            "metric": "world-steps/sec", "value": value, "unit": "world-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": warm, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": cfg["scaling"],
+            "metric": "world-steps/sec", "value": value, "unit": "world-steps/s", "n_gpus": world, "steps": steps,
+            "warmup": warm, "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": cfg["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-            "e2e": {"value": e2e_value, "unit": "world-steps/s",
-                    "h2d_bytes_per_step": int(h_q.numel() * 4 * 2 + h_tg.numel() * 4), "d2h_bytes_per_step": int(h_out.numel() * 4)},
+            "e2e": {"value": e2e_value, "unit": "world-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / steps},
             "gpu_launches": launches, "run": run_info,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": prof["traffic"] if prof else None, "kernel": "k_step", "peak_kind": peak_kind,
@@ -534,6 +582,8 @@ def run_ours(args):
                          "note": "FP32 issue / dependent-latency bound, not bandwidth bound: DESIGN.md §3, profiles/"},
             "clocks": clock_summary,
         }
+        if multi_info:
+            line["multi_gpu"] = multi_info
         if prof:
             # the roof this path actually sits under: FP32 lane-issue slots.  thread instructions per world-step (ncu capture
             # named in `source`) x measured world-steps/s of the kernel, against 148 SMs x 128 lanes x SM clock under load
@@ -546,7 +596,7 @@ def run_ours(args):
                 "achieved_thread_instructions_per_s": prof["thread_instructions_per_world_step"] * kernel_rate,
                 "peak_thread_instructions_per_s": lane_peak, "sm_mhz": mhz,
                 "frac": prof["thread_instructions_per_world_step"] * kernel_rate / lane_peak, "source": prof["source"]}
-        if world == 1 and not args.no_cpu_baseline:
+        if with_cpu and world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
             nref = min(n, args.ref_worlds)
             units, times = cpu_oracle_throughput(cfg, limits, nref, 1 + args.cpu_repeats, threads)
@@ -556,7 +606,37 @@ def run_ours(args):
                                     "sample": "%d worlds x %d steps x %d repeats of the same workload, one world per thread"
                                               % (nref, ROLLOUT_STEPS, len(timed))}
             # correctness gate run with the measurement (outside every timed region; the oracle is the checker)
-            line["parity"] = parity_gate(cfg, batch, limits, n, 1234 + 100 + args.steps - 1, threads)
+            line["parity"] = parity_gate(cfg, batch, limits, n, 1234 + 100 + steps - 1, threads)
+    # the batch (and its stream, which torch's allocator has seen) stays alive until the process ends
+    ctx.setdefault("keep", []).append((batch, stream))
+    return line
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the batched backend has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = {"world": world, "rank": rank, "local": local, "dev": dev,
+           "flush": torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=dev)}  # > 126 MB L2
+    cfg = CONFIGS[args.config]
+    line = measure(args, args.config, args.worlds or cfg["worlds"], args.steps, args.warmup, ctx, with_cpu=True)
+    if args.config == "cfg2" and not args.no_cfg5 and not args.worlds:
+        # BASELINE.json configs[4] rides along: the planner sweep (1 Mi worlds in total, strong scaling, states all-gathered),
+        # 2 timed steps, so that the driver's 1 / 2 / 4 / 8-GPU runs record it next to the weak-scaling headline
+        sub = measure(args, "cfg5", CONFIGS["cfg5"]["worlds"], 2, 1, ctx, with_cpu=False)
+        if rank == 0 and sub:
+            keep = ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "config", "e2e", "run", "roofline", "multi_gpu")
+            line["cfg5"] = {k: sub[k] for k in keep if k in sub}
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -616,6 +696,7 @@ def main():
     ap.add_argument("--ref-worlds", type=int, default=4096, help="worlds per step of the CPU oracle sample")
     ap.add_argument("--cpu-repeats", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the cfg5 (1 Mi-world sweep) sub-record of the default run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -4,4 +4,4 @@ Host-side Python mirror of the reference's Box2DWorld API (include/sim_env/Box2D
 JoshuaHaustein/box2d_sim_env) over the C ABI in include/b2g.h.  All compute runs in hand-written CUDA
 kernels (csrc/); there is no CPU fallback — creating a batch without a CUDA device raises.
 """
-from .batch_world import (B2GError, BatchBox2DWorld, Environment, Model, data_path, lib, pinned_empty)  # noqa: F401
+from .batch_world import (B2GError, BatchBox2DWorld, Environment, Model, MultiGpuBatch, data_path, lib, pinned_empty)  # noqa: F401

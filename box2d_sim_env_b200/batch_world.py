@@ -68,6 +68,8 @@ ABI_SYMBOLS = [
     "b2g_batch_get_link_states", "b2g_batch_get_bodies", "b2g_batch_get_fat_aabbs", "b2g_batch_get_joints", "b2g_batch_get_contacts",
     "b2g_batch_check_collision", "b2g_batch_check_collision_dev", "b2g_batch_save_state", "b2g_batch_restore_state", "b2g_batch_drop_state",
     "b2g_host_alloc", "b2g_host_free", "b2g_launch_count", "b2g_batch_take_kernel_ms",
+    "b2g_multi_create", "b2g_multi_destroy", "b2g_multi_device_count", "b2g_multi_get_shard", "b2g_multi_rollout",
+    "b2g_multi_gathered_dev", "b2g_multi_last_timing",
 ]
 
 
@@ -167,6 +169,14 @@ def lib():
     L.b2g_host_free.restype = None
     L.b2g_launch_count.restype = C.c_uint64
     L.b2g_batch_take_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    L.b2g_multi_create.argtypes = [vp, C.c_int64, ip, C.c_int, C.c_int, C.POINTER(vp)]
+    L.b2g_multi_destroy.argtypes = [vp]
+    L.b2g_multi_destroy.restype = None
+    L.b2g_multi_device_count.argtypes = [vp]
+    L.b2g_multi_get_shard.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.b2g_multi_rollout.argtypes = [vp, C.c_int, fp, fp, C.c_int, fp, C.c_int, C.c_int, fp, fp]
+    L.b2g_multi_gathered_dev.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64)]
+    L.b2g_multi_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     _LIB = L
     return L
 
@@ -709,3 +719,61 @@ class BatchBox2DWorld:
 
     def sync(self):
         _check(lib().b2g_batch_sync(self.h))
+
+
+class MultiGpuBatch:
+    """b2g_multi_*: one batch per GPU of this node inside ONE process (one host thread per device), contiguous world slices,
+    ncclAllGather of the final rollout states over NVLink.  Mirrors what a C++ planner gets from include/b2g.h."""
+
+    def __init__(self, model, n_worlds, devices, max_contacts=0):
+        self.model = model if isinstance(model, Model) else Model(model)
+        self.n_worlds = int(n_worlds)
+        self.devices = [int(d) for d in devices]
+        dev = np.asarray(self.devices, np.int32)
+        h = C.c_void_p()
+        _check(lib().b2g_multi_create(self.model.h, self.n_worlds, _ptr(dev), len(self.devices), int(max_contacts), C.byref(h)))
+        self.h = h
+        self.nq = self.model.nq
+
+    def shard(self, i):
+        """(batch handle, first world, world count) of device i."""
+        b, first, count = C.c_void_p(), C.c_int64(), C.c_int64()
+        _check(lib().b2g_multi_get_shard(self.h, int(i), C.byref(b), C.byref(first), C.byref(count)))
+        return b, first.value, count.value
+
+    def rollout(self, robot, targets, steps_per_target, q=None, qd=None, reset_caches=True, q_out=None, qd_out=None):
+        robot = self.model.object_index(robot) if isinstance(robot, str) else robot
+        tg = _f32(targets)
+        if q is not None:
+            q, qd = _f32(q), _f32(qd)
+        q_out = np.empty((self.n_worlds, self.nq), np.float32) if q_out is None else q_out
+        qd_out = np.empty((self.n_worlds, self.nq), np.float32) if qd_out is None else qd_out
+        _check(lib().b2g_multi_rollout(self.h, robot, _ptr(q), _ptr(qd), int(reset_caches), _ptr(tg), tg.shape[0],
+                                       int(steps_per_target), _ptr(q_out), _ptr(qd_out)))
+        return q_out, qd_out
+
+    def rollout_host(self, robot, q_ptr, qd_ptr, targets_ptr, n_targets, steps_per_target, q_out_ptr, qd_out_ptr, reset_caches=True):
+        _check(lib().b2g_multi_rollout(self.h, robot, C.c_void_p(q_ptr), C.c_void_p(qd_ptr), int(reset_caches), C.c_void_p(targets_ptr),
+                                       int(n_targets), int(steps_per_target), C.c_void_p(q_out_ptr), C.c_void_p(qd_out_ptr)))
+
+    def last_timing(self):
+        lo, hi, g = C.c_float(), C.c_float(), C.c_float()
+        _check(lib().b2g_multi_last_timing(self.h, C.byref(lo), C.byref(hi), C.byref(g)))
+        return {"kernel_ms_min": lo.value, "kernel_ms_max": hi.value, "gather_ms": g.value}
+
+    def gathered_dev(self, i):
+        """(q_all ptr, qd_all ptr, rows per device) of the gathered states on device i."""
+        qa, qda, rows = C.c_void_p(), C.c_void_p(), C.c_int64()
+        _check(lib().b2g_multi_gathered_dev(self.h, int(i), C.byref(qa), C.byref(qda), C.byref(rows)))
+        return qa.value, qda.value, rows.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b2g_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

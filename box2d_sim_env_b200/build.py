@@ -41,7 +41,7 @@ def build(force=False, verbose=False, out=None):
     if not force and not needs_build():
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "--fmad=false", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", "-o", LIB] + SOURCES
+           "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", "-o", LIB] + SOURCES + ["-ldl"]
     if os.environ.get("B2G_DEFINES"):  # tuning experiments only, e.g. B2G_DEFINES="-DB2G_SYNC_MASK=0x3ff"
         cmd[1:1] = os.environ["B2G_DEFINES"].split()
     if os.environ.get("B2G_MAXREG"):  # tuning experiments only; the product build uses the launch bounds in the source

@@ -2,6 +2,8 @@
 // kernel launches.  There is deliberately no CPU implementation of any compute entry point: without a CUDA
 // device every one of them fails with B2G_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -10,6 +12,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -1263,5 +1266,269 @@ void b2g_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 uint64_t b2g_launch_count(void) { return launchCount(); }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ several GPUs
+// One process, one host thread and one b2g_batch per device, contiguous world slices, ncclAllGather of the final states on
+// the batches' streams.  NCCL is loaded with dlopen on first use so that the library itself has no link-time
+// dependency on it (the single-GPU path and the CPU-side tests never touch it).
+namespace {
+struct Nccl {
+    void* lib = nullptr;
+    decltype(&ncclCommInitAll) commInitAll = nullptr;
+    decltype(&ncclCommDestroy) commDestroy = nullptr;
+    decltype(&ncclAllGather) allGather = nullptr;
+    decltype(&ncclGroupStart) groupStart = nullptr;
+    decltype(&ncclGroupEnd) groupEnd = nullptr;
+    decltype(&ncclGetErrorString) errorString = nullptr;
+    bool load(std::string& why) {
+        if (lib) return true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) {
+            why = std::string("cannot load libnccl.so.2: ") + dlerror();
+            return false;
+        }
+#define B2G_SYM(field, symbol)                                       \
+    field = reinterpret_cast<decltype(field)>(dlsym(lib, symbol));   \
+    if (!field) {                                                    \
+        why = std::string("libnccl has no symbol ") + symbol;        \
+        lib = nullptr;                                               \
+        return false;                                                \
+    }
+        B2G_SYM(commInitAll, "ncclCommInitAll")
+        B2G_SYM(commDestroy, "ncclCommDestroy")
+        B2G_SYM(allGather, "ncclAllGather")
+        B2G_SYM(groupStart, "ncclGroupStart")
+        B2G_SYM(groupEnd, "ncclGroupEnd")
+        B2G_SYM(errorString, "ncclGetErrorString")
+#undef B2G_SYM
+        return true;
+    }
+};
+Nccl g_nccl;
+
+struct Shard {
+    b2g_batch* batch = nullptr;
+    int device = 0;
+    long long first = 0, count = 0;
+    float *q = nullptr, *qd = nullptr, *tg = nullptr;  // this slice's inputs on the device
+    float *sendQ = nullptr, *sendQd = nullptr;        // [rowsPer][nq], padded
+    float *allQ = nullptr, *allQd = nullptr;          // [nDev][rowsPer][nq]
+    size_t tgCap = 0;
+    cudaEvent_t g0 = nullptr, g1 = nullptr;
+    float kernelMs = 0.0f, gatherMs = 0.0f;
+    b2g_status status = B2G_OK;
+    std::string error;
+};
+}  // namespace
+
+struct b2g_multi {
+    std::vector<Shard> shards;
+    std::vector<ncclComm_t> comms;
+    long long N = 0, rowsPer = 0;
+    int nq = 0;
+};
+
+extern "C" {
+
+void b2g_multi_destroy(b2g_multi* m) {
+    if (!m) return;
+    for (size_t i = 0; i < m->shards.size(); ++i) {
+        Shard& s = m->shards[i];
+        DeviceGuard guard(s.device);
+        if (s.batch) b2g_batch_sync(s.batch);
+        if (i < m->comms.size() && m->comms[i] && g_nccl.commDestroy) g_nccl.commDestroy(m->comms[i]);
+        for (float* p : {s.q, s.qd, s.tg, s.sendQ, s.sendQd, s.allQ, s.allQd}) cudaFree(p);
+        if (s.g0) cudaEventDestroy(s.g0);
+        if (s.g1) cudaEventDestroy(s.g1);
+        if (s.batch) b2g_batch_destroy(s.batch);
+    }
+    delete m;
+}
+
+b2g_status b2g_multi_create(const b2g_model* model, int64_t n_total, const int32_t* devices, int n_devices, int max_contacts,
+                            b2g_multi** out) {
+    if (!model || !out || !devices || n_devices < 1 || n_total < n_devices) return fail(B2G_ERR_INVALID, "bad multi-GPU batch arguments");
+    for (int i = 0; i < n_devices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return fail(B2G_ERR_INVALID, "every device may appear once (NCCL: one rank per GPU)");
+    std::string why;
+    if (!g_nccl.load(why)) return fail(B2G_ERR_UNSUPPORTED, why);
+    b2g_multi* m = new b2g_multi();
+    m->N = n_total;
+    m->shards.resize(n_devices);
+    m->rowsPer = (n_total + n_devices - 1) / n_devices;
+    // contiguous slices that differ by at most one world (the rule of box2d_sim_env_b200/sharding.py: world_slice)
+    const long long base = n_total / n_devices, rem = n_total % n_devices;
+    long long first = 0;
+    for (int i = 0; i < n_devices; ++i) {
+        Shard& s = m->shards[i];
+        s.device = devices[i];
+        s.first = first;
+        s.count = base + (i < rem ? 1 : 0);
+        first += s.count;
+        b2g_status st = b2g_batch_create(model, s.count, s.device, max_contacts, &s.batch);
+        if (st) {
+            const std::string msg = g_error;
+            b2g_multi_destroy(m);
+            return fail(st, msg);
+        }
+        m->nq = s.batch->m.h.nq;
+        DeviceGuard guard(s.device);
+        const size_t slice = (size_t)s.count * m->nq * 4, padded = (size_t)m->rowsPer * m->nq * 4;
+        cudaError_t e = cudaMalloc((void**)&s.q, slice);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s.qd, slice);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s.sendQ, padded);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s.sendQd, padded);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s.allQ, padded * n_devices);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s.allQd, padded * n_devices);
+        if (e == cudaSuccess) e = cudaMemset(s.sendQ, 0, padded);
+        if (e == cudaSuccess) e = cudaMemset(s.sendQd, 0, padded);
+        if (e == cudaSuccess) e = cudaEventCreate(&s.g0);
+        if (e == cudaSuccess) e = cudaEventCreate(&s.g1);
+        if (e != cudaSuccess) {
+            b2g_multi_destroy(m);
+            return cudaFail(e, "multi-GPU buffers");
+        }
+    }
+    m->comms.assign(n_devices, nullptr);
+    ncclResult_t r = g_nccl.commInitAll(m->comms.data(), n_devices, devices);
+    if (r != ncclSuccess) {
+        const std::string msg = std::string("ncclCommInitAll: ") + g_nccl.errorString(r);
+        b2g_multi_destroy(m);
+        return fail(B2G_ERR_CUDA, msg);
+    }
+    *out = m;
+    return B2G_OK;
+}
+
+int32_t b2g_multi_device_count(const b2g_multi* m) { return m ? (int32_t)m->shards.size() : 0; }
+
+b2g_status b2g_multi_get_shard(b2g_multi* m, int i, b2g_batch** batch, int64_t* first_world, int64_t* n_worlds) {
+    if (!m || i < 0 || i >= (int)m->shards.size()) return fail(B2G_ERR_INVALID, "unknown shard");
+    if (batch) *batch = m->shards[i].batch;
+    if (first_world) *first_world = m->shards[i].first;
+    if (n_worlds) *n_worlds = m->shards[i].count;
+    return B2G_OK;
+}
+
+b2g_status b2g_multi_rollout(b2g_multi* m, int object, const float* q, const float* qd, int reset_caches, const float* targets,
+                             int n_targets, int steps_per_target, float* q_out, float* qd_out) {
+    if (!m || !targets || n_targets < 1 || steps_per_target < 0 || !q_out || !qd_out || (q == nullptr) != (qd == nullptr))
+        return fail(B2G_ERR_INVALID, "bad rollout arguments");
+    const int nDev = (int)m->shards.size();
+    const int nq = m->nq;
+    {
+        b2g_status s = checkRobot(m->shards[0].batch, object);
+        if (s) return s;
+    }
+    const int nd = m->shards[0].batch->m.objects[object].nDofs;
+    auto work = [&](int i) {
+        Shard& s = m->shards[i];
+        b2g_batch* b = s.batch;
+        s.status = B2G_OK;
+        auto bad = [&](cudaError_t e, const char* what) {
+            s.status = B2G_ERR_CUDA;
+            s.error = std::string(what) + ": " + cudaGetErrorString(e);
+        };
+        cudaError_t e = cudaSetDevice(s.device);
+        if (e != cudaSuccess) return bad(e, "cudaSetDevice");
+        cudaStream_t st = b->stream;
+        const size_t slice = (size_t)s.count * nq * 4;
+        if (q) {
+            e = cudaMemcpyAsync(s.q, q + (size_t)s.first * nq, slice, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(s.qd, qd + (size_t)s.first * nq, slice, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return bad(e, "state H2D");
+            if ((s.status = b2g_batch_set_state_dev(b, s.q, s.qd, reset_caches)) != B2G_OK) {
+                s.error = g_error;
+                return;
+            }
+        }
+        const size_t tgBytes = (size_t)n_targets * s.count * nd * 4;
+        if (tgBytes > s.tgCap) {
+            cudaFree(s.tg);
+            s.tg = nullptr;
+            s.tgCap = 0;
+            if ((e = cudaMalloc((void**)&s.tg, tgBytes)) != cudaSuccess) return bad(e, "cudaMalloc(targets)");
+            s.tgCap = tgBytes;
+        }
+        // rows first .. first + count of every targets[t]: one strided copy
+        e = cudaMemcpy2DAsync(s.tg, (size_t)s.count * nd * 4, targets + (size_t)s.first * nd, (size_t)m->N * nd * 4,
+                              (size_t)s.count * nd * 4, (size_t)n_targets, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return bad(e, "targets H2D");
+        float ms = 0.0f;
+        int32_t launches = 0;
+        b2g_batch_take_kernel_ms(b, &ms, &launches);  // forget earlier launches
+        if ((s.status = b2g_batch_rollout_dev(b, object, s.tg, n_targets, steps_per_target)) != B2G_OK ||
+            (s.status = b2g_batch_get_state_dev(b, s.sendQ, s.sendQd)) != B2G_OK) {
+            s.error = g_error;
+            return;
+        }
+        // the path's only exchange: every device receives every slice
+        e = cudaEventRecord(s.g0, st);
+        if (e != cudaSuccess) return bad(e, "cudaEventRecord");
+        const size_t rowsBytes = (size_t)m->rowsPer * nq;
+        ncclResult_t r = g_nccl.groupStart();
+        if (r == ncclSuccess) r = g_nccl.allGather(s.sendQ, s.allQ, rowsBytes, ncclFloat, m->comms[i], st);
+        if (r == ncclSuccess) r = g_nccl.allGather(s.sendQd, s.allQd, rowsBytes, ncclFloat, m->comms[i], st);
+        if (r == ncclSuccess) r = g_nccl.groupEnd();
+        if (r != ncclSuccess) {
+            s.status = B2G_ERR_CUDA;
+            s.error = std::string("ncclAllGather: ") + g_nccl.errorString(r);
+            return;
+        }
+        e = cudaEventRecord(s.g1, st);
+        if (e == cudaSuccess && i == 0) {  // device 0 hands the gathered states to the caller, slice by slice (padding skipped)
+            for (int j = 0; j < nDev && e == cudaSuccess; ++j) {
+                const Shard& o = m->shards[j];
+                const size_t bytes = (size_t)o.count * nq * 4;
+                e = cudaMemcpyAsync(q_out + (size_t)o.first * nq, s.allQ + (size_t)j * rowsBytes, bytes, cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(qd_out + (size_t)o.first * nq, s.allQd + (size_t)j * rowsBytes, bytes, cudaMemcpyDeviceToHost, st);
+            }
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return bad(e, "gather / D2H");
+        cudaEventElapsedTime(&s.gatherMs, s.g0, s.g1);
+        b2g_batch_take_kernel_ms(b, &s.kernelMs, &launches);
+    };
+    if (nDev == 1) {
+        DeviceGuard guard(m->shards[0].device);
+        work(0);
+    } else {
+        std::vector<std::thread> threads;
+        for (int i = 0; i < nDev; ++i) threads.emplace_back(work, i);
+        for (auto& t : threads) t.join();
+    }
+    for (const Shard& s : m->shards)
+        if (s.status != B2G_OK) return fail(s.status, "device " + std::to_string(s.device) + ": " + s.error);
+    return B2G_OK;
+}
+
+b2g_status b2g_multi_gathered_dev(b2g_multi* m, int i, const float** q_all, const float** qd_all, int64_t* rows_per_device) {
+    if (!m || i < 0 || i >= (int)m->shards.size()) return fail(B2G_ERR_INVALID, "unknown shard");
+    if (q_all) *q_all = m->shards[i].allQ;
+    if (qd_all) *qd_all = m->shards[i].allQd;
+    if (rows_per_device) *rows_per_device = m->rowsPer;
+    return B2G_OK;
+}
+
+b2g_status b2g_multi_last_timing(b2g_multi* m, float* kernel_ms_min, float* kernel_ms_max, float* gather_ms) {
+    if (!m) return fail(B2G_ERR_INVALID, "null argument");
+    float lo = 1e30f, hi = 0.0f, g = 0.0f;
+    for (const Shard& s : m->shards) {
+        lo = std::min(lo, s.kernelMs);
+        hi = std::max(hi, s.kernelMs);
+        g = std::max(g, s.gatherMs);
+    }
+    if (kernel_ms_min) *kernel_ms_min = lo;
+    if (kernel_ms_max) *kernel_ms_max = hi;
+    if (gather_ms) *gather_ms = g;
+    return B2G_OK;
+}
 
 }  // extern "C"

@@ -325,6 +325,33 @@ uint64_t b2g_launch_count(void);
  * stepping launches are remembered (callers that never collect timings do not accumulate events). */
 b2g_status b2g_batch_take_kernel_ms(b2g_batch* batch, float* out_ms, int32_t* out_launches);
 
+/* ---- several GPUs of one node behind the same ABI ------------------------------------------------------
+ * The reference's planner steps one Box2DWorld per call (include/sim_env/Box2DWorld.h:748-844); worlds are independent, so a
+ * batch shards trivially: device i of `devices` owns the contiguous slice [first_i, first_i + count_i) of the n_worlds_total
+ * worlds (slices differ by at most one world), with its own b2g_batch, stream and host thread inside THIS process.  The
+ * only exchange is the final gather of the rollout states: ncclAllGather over NVLink on the batches' streams
+ * (ncclCommInitAll, one communicator per device; libnccl.so.2 is loaded on first use).  No data-path collective otherwise. */
+typedef struct b2g_multi b2g_multi;
+b2g_status b2g_multi_create(const b2g_model* model, int64_t n_worlds_total, const int32_t* devices, int n_devices, int max_contacts,
+                            b2g_multi** out);
+void b2g_multi_destroy(b2g_multi* multi);
+int32_t b2g_multi_device_count(const b2g_multi* multi);
+/* shard i: its batch (every b2g_batch_* call works on it; worlds are numbered from 0 inside the shard), the global index of
+ * its first world and its world count */
+b2g_status b2g_multi_get_shard(b2g_multi* multi, int i, b2g_batch** batch, int64_t* first_world, int64_t* n_worlds);
+/* b2g_batch_rollout over all devices at once.  Host buffers cover the whole job: q, qd, q_out, qd_out [n_worlds_total][nq],
+ * targets [n_targets][n_worlds_total][n_dofs].  Every device thread copies its slice in, runs the rollout kernel and
+ * getWorldState, then all devices all-gather the states (every device ends up with all n_worlds_total rows, see
+ * b2g_multi_gathered_dev) and device 0 copies them to q_out / qd_out. */
+b2g_status b2g_multi_rollout(b2g_multi* multi, int object, const float* q, const float* qd, int reset_caches, const float* targets,
+                             int n_targets, int steps_per_target, float* q_out, float* qd_out);
+/* the gathered states as device i holds them after b2g_multi_rollout: q_all / qd_all [n_devices][rows_per_device][nq]
+ * (device j's slice starts at row j * rows_per_device; its last rows_per_device - count_j rows are padding) */
+b2g_status b2g_multi_gathered_dev(b2g_multi* multi, int i, const float** q_all, const float** qd_all, int64_t* rows_per_device);
+/* timings of the last b2g_multi_rollout, CUDA events on the batches' streams: the rollout kernel per device (min / max over
+ * the devices) and the all-gather (max over the devices; it includes waiting for the slowest device's kernel) */
+b2g_status b2g_multi_last_timing(b2g_multi* multi, float* kernel_ms_min, float* kernel_ms_max, float* gather_ms);
+
 #ifdef __cplusplus
 }
 #endif

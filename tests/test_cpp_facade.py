@@ -54,3 +54,21 @@ def test_facade_matches_python_mirror(tmp_path, b2g):
     assert "recorded=%d " % int(np.minimum(counts, 32).sum()) in line and "restored=1" in line
     view = [l for l in out.stdout.splitlines() if l.startswith("VIEW")][0]
     assert "bad=0" in view and "threw=1" in view, view
+
+
+@pytest.mark.gpu
+def test_cpp_planner_on_several_gpus(tmp_path, b2g):
+    """tests/cpp/multi_demo.cpp: a C++ caller shards a batch over the node's GPUs through b2g_multi_* (one process, one host
+    thread per device, ncclAllGather of the states) and gets the single-batch result bit for bit."""
+    import torch
+    b2g.lib()
+    exe = os.path.join(str(tmp_path), "multi_demo")
+    libdir = os.path.join(ROOT, "box2d_sim_env_b200")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "multi_demo.cpp"), "-o", exe, "-L", libdir, "-lb2g",
+                           "-Wl,-rpath," + libdir])
+    ndev = min(torch.cuda.device_count(), 8)
+    for nd in sorted({1, ndev}):
+        out = subprocess.run([exe, b2g.data_path("test_env.yaml"), str(nd), "3001"], capture_output=True, text=True)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "devices=%d worlds=3001 covered=3001 identical=1" % nd in out.stdout, out.stdout

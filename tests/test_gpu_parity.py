@@ -988,3 +988,37 @@ def test_pinned_empty_and_current_device(b2g):
         torch.cuda.set_device(0)
         other.stepPhysics(1)
         assert torch.cuda.current_device() == 0
+
+
+def test_multi_gpu_c_abi_rollout(b2g):
+    """b2g_multi_*: the batch sharded over the GPUs of the node inside one process, ncclAllGather of the final states.  The
+    result must equal the single-batch rollout bit for bit, whatever the device count and however ragged the slices (runs
+    with one device on a single-GPU box, with two when the box has them)."""
+    import torch
+    ndev = min(2, torch.cuda.device_count())
+    n = 1001   # odd: slices of 501 + 500 worlds on two devices
+    model = b2g.Model(b2g.data_path(ENV_A))
+    multi = b2g.MultiGpuBatch(model, n, list(range(ndev)))
+    single = b2g.BatchBox2DWorld(n).loadWorld(model)
+    q, qd = random_states(model, n, seed=61, spread=0.6)
+    tg = random_targets(model, 0, n, seed=62, segments=3)
+    mq, mqd = multi.rollout(0, tg, 10, q, qd)
+    sq, sqd = single.rollout(0, tg, 10, q, qd)
+    assert np.array_equal(mq, sq) and np.array_equal(mqd, sqd)
+    sizes = [multi.shard(i)[2] for i in range(ndev)]
+    assert sum(sizes) == n and max(sizes) - min(sizes) <= 1 and multi.shard(0)[1] == 0
+    # the gathered copy every device holds: rows of device 0's slice on the last device
+    qa, qda, rows = multi.gathered_dev(ndev - 1)
+    t = torch.empty((ndev, rows, model.nq), dtype=torch.float32, device="cuda:%d" % (ndev - 1))
+    import ctypes
+    from box2d_sim_env_b200.batch_world import lib as _lib  # noqa: F401
+    torch.cuda.synchronize()
+    ctypes.CDLL("libcudart.so.12").cudaMemcpy(ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(qa), ctypes.c_size_t(t.numel() * 4), 3)
+    assert np.array_equal(t[0, :sizes[0]].cpu().numpy(), sq[:sizes[0]])
+    tm = multi.last_timing()
+    assert tm["kernel_ms_max"] >= tm["kernel_ms_min"] > 0.0 and tm["gather_ms"] > 0.0
+    # a second call reuses the communicators; continuing without set_state matches as well
+    mq2, _ = multi.rollout(0, tg[:1], 5)
+    sq2, _ = single.rollout(0, tg[:1], 5)
+    assert np.array_equal(mq2, sq2)
+    multi.close()

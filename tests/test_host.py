@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_abi_exports_every_declared_symbol(b2g):
     header = open(os.path.join(ROOT, "include", "b2g.h")).read()
-    declared = set(re.findall(r"^(?:b2g_status|void\*?|const char\*|uint64_t)\s+(b2g_[a-z0-9_]+)\s*\(", header, re.M))
+    declared = set(re.findall(r"^(?:b2g_status|void\*?|const char\*|uint64_t|int32_t)\s+(b2g_[a-z0-9_]+)\s*\(", header, re.M))
     assert declared, "no declarations found"
     L = b2g.lib()
     for name in sorted(declared):
