@@ -448,11 +448,13 @@ def measure(args, cfg_name, n_cfg, steps, warmup, ctx, with_cpu):
                 g1.record(stream)
                 gather_events.append((g0, g1))
 
-    def barrier():
+    def barrier(host_only=False):
         stream.synchronize()
         torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            # host_only: a gloo barrier.  While rank 0 drives every GPU of the node through b2g_multi_rollout the other ranks
+            # must not park an NCCL barrier kernel on their GPU (it would time-slice with rank 0's rollout kernel there)
+            dist.barrier(group=ctx["host_pg"]) if host_only else dist.barrier()
         torch.cuda.synchronize()
 
     def timed_pass(n_steps, e2e, first_idx):
@@ -468,7 +470,7 @@ def measure(args, cfg_name, n_cfg, steps, warmup, ctx, with_cpu):
                 load_inputs(first_idx + s, to_device=not e2e)
             with torch.cuda.stream(stream):
                 flush.zero_()  # evict L2 between timed iterations
-            barrier()
+            barrier(host_only=e2e and world > 1)
             if e2e and world > 1:
                 ms = 0.0
                 if rank == 0:
@@ -479,7 +481,7 @@ def measure(args, cfg_name, n_cfg, steps, warmup, ctx, with_cpu):
                     e1.record(m_stream)
                     m_stream.synchronize()
                     ms = e0.elapsed_time(e1)
-                barrier()
+                barrier(host_only=True)
                 total_ms += ms
                 continue
             e0 = torch.cuda.Event(enable_timing=True)
@@ -623,9 +625,11 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the batched backend has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_pg = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    ctx = {"world": world, "rank": rank, "local": local, "dev": dev,
+        host_pg = dist.new_group(backend="gloo")
+    ctx = {"world": world, "rank": rank, "local": local, "dev": dev, "host_pg": host_pg,
            "flush": torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=dev)}  # > 126 MB L2
     cfg = CONFIGS[args.config]
     line = measure(args, args.config, args.worlds or cfg["worlds"], args.steps, args.warmup, ctx, with_cpu=True)
