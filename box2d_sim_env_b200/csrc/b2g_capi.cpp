@@ -156,6 +156,17 @@ cudaError_t getEvent(b2g_batch* b, cudaEvent_t* out) {
 }
 }  // namespace
 
+// Objects with a prismatic joint can be loaded, stepped and read, but not placed: in the reference every DOF setter of such an
+// object ends in Box2DLink::updateBodyVelocities -> Box2DJoint::getGlobalAxisPosition, which throws std::logic_error for a
+// prismatic joint (Box2DWorld.cpp:789, 1282-1285), after Box2DJoint::resetPosition left the child link where it was (:1021-1026).
+static b2g_status refusePrismatic(const b2g_batch* b, int object) {
+    for (int o = 0; o < (int)b->m.objects.size(); ++o)
+        if ((object < 0 || o == object) && b->m.objects[o].hasPrismatic)
+            return fail(B2G_ERR_UNSUPPORTED, "object '" + b->m.objects[o].name + "' has a prismatic joint: its DOFs cannot be set (the "
+                        "reference throws in getGlobalAxisPosition, Box2DWorld.cpp:1282-1285)");
+    return B2G_OK;
+}
+
 extern "C" {
 
 const char* b2g_last_error(void) { return g_error.c_str(); }
@@ -286,7 +297,7 @@ b2g_status b2g_model_create(const b2g_env* env, b2g_model** out) {
     } catch (const std::exception& ex) {
         std::string what = ex.what();
         delete m;
-        bool unsupported = what.find("not supported") != std::string::npos;
+        bool unsupported = what.find("not supported") != std::string::npos || what.find("unsupported") != std::string::npos;
         return fail(unsupported ? B2G_ERR_UNSUPPORTED : B2G_ERR_INVALID, what);
     }
     *out = m;
@@ -570,6 +581,7 @@ b2g_status b2g_batch_status(b2g_batch* b, int32_t* out) {
 
 b2g_status b2g_batch_set_state_dev(b2g_batch* b, const float* q, const float* qd, int reset_caches) {
     if (!b || !q || !qd) return fail(B2G_ERR_INVALID, "null argument");
+    if (b2g_status st = refusePrismatic(b, -1)) return st;
     ON_DEVICE(b->device);
     if (reset_caches) CU(launchBroadcast(b->L(), b->tmpl));
     CU(launchSetState(b->L(), q, qd));
@@ -639,6 +651,7 @@ b2g_status b2g_batch_set_object_dofs(b2g_batch* b, int object, int velocities, c
     if (st) return st;
     if (sel.n == 0) return B2G_OK;
     if (!values) return fail(B2G_ERR_INVALID, "null argument");
+    if (b2g_status st2 = refusePrismatic(b, object)) return st2;
     ON_DEVICE(b->device);
     size_t bytes = (size_t)b->n() * sel.n * 4;
     CU(b->stageA.reserve(bytes));
@@ -665,6 +678,7 @@ b2g_status b2g_batch_get_object_dofs(b2g_batch* b, int object, int velocities, c
 
 b2g_status b2g_batch_set_object_pose(b2g_batch* b, int object, const float* pose) {
     if (!b || !pose || object < 0 || object >= b->m.h.no) return fail(B2G_ERR_INVALID, "unknown object");
+    if (b2g_status st = refusePrismatic(b, object)) return st;
     ON_DEVICE(b->device);
     size_t bytes = (size_t)b->n() * 3 * 4;
     CU(b->stageA.reserve(bytes));
@@ -786,6 +800,8 @@ b2g_status b2g_batch_rollout(b2g_batch* b, int object, const float* q, const flo
     if (!targets || n_targets < 0 || steps_per_target < 0 || !q_out || !qd_out || (q == nullptr) != (qd == nullptr))
         return fail(B2G_ERR_INVALID, "bad rollout arguments");
     if (!b->allSelected()) return fail(B2G_ERR_INVALID, "stepping and the state stack act on the whole batch: call b2g_batch_select_worlds(batch, 0, 0) first");
+    if (q)
+        if (b2g_status st = refusePrismatic(b, -1)) return st;
     ON_DEVICE(b->device);
     const size_t sb = (size_t)b->N * b->m.h.nq * 4;
     const size_t tb = (size_t)n_targets * b->N * b->m.objects[object].nDofs * 4;
@@ -812,6 +828,7 @@ b2g_status b2g_batch_rollout(b2g_batch* b, int object, const float* q, const flo
 
 b2g_status b2g_batch_set_to_rest(b2g_batch* b) {
     if (!b) return fail(B2G_ERR_INVALID, "null batch");
+    if (b2g_status st = refusePrismatic(b, -1)) return st;  // setToRest = setDOFVelocities(0) on every object
     ON_DEVICE(b->device);
     CU(launchSetToRest(b->L()));
     CU(cudaStreamSynchronize(b->stream));

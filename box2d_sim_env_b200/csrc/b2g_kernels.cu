@@ -505,7 +505,7 @@ __global__ void k_get_joints(const __grid_constant__ ModelHeader hdr, const uint
         fo[0] = ldF(c, jslot(c, j, SJ_IX)); fo[1] = ldF(c, jslot(c, j, SJ_IY)); fo[2] = ldF(c, jslot(c, j, SJ_IZ));
         fo[3] = type == 0 ? 0.0f : ldF(c, jslot(c, j, SJ_MOTOR_IMPULSE));
         fo[4] = ldF(c, jslot(c, j, SJ_MAX_MOTOR_TORQUE)); fo[5] = ldF(c, jslot(c, j, SJ_MOTOR_SPEED));
-        fo[6] = mF(c, mjoint(c, j, MJ_MAXFORCE)); fo[7] = mF(c, mjoint(c, j, MJ_MAXTORQUE));
+        fo[6] = type == 2 ? 0.0f : mF(c, mjoint(c, j, MJ_MAXFORCE)); fo[7] = mF(c, mjoint(c, j, MJ_MAXTORQUE));
         fo[8] = mF(c, mjoint(c, j, MJ_LAX)); fo[9] = mF(c, mjoint(c, j, MJ_LAY));
         fo[10] = mF(c, mjoint(c, j, MJ_LBX)); fo[11] = mF(c, mjoint(c, j, MJ_LBY));
         fo[12] = mF(c, mjoint(c, j, MJ_REF)); fo[13] = mF(c, mjoint(c, j, MJ_LOWER)); fo[14] = mF(c, mjoint(c, j, MJ_UPPER));

@@ -91,6 +91,7 @@ DEVN void jointInitPre(Ctx c, int j, float dtRatio) {
     const float4 arm = m4(c, jr + MJ_RA0X);   // localAnchorA - localCenterA, localAnchorB - localCenterB
     const float4 im = m4(c, jr + MJ_MA);      // mA iA mB iB
     const int type = jh.x;
+    if (type == 2) return;  // prismatic joints are initialised as a whole by jointWarmApply (sequential phase)
     const int js = off.x, jw = off.y;
     Rot qA = ldRotAt(c, off.z), qB = ldRotAt(c, off.w);
     V2 rA = mul(qA, mk(arm.x, arm.y));
@@ -165,9 +166,13 @@ DEVN void jointInitPre(Ctx c, int j, float dtRatio) {
 }
 
 // warm start of joint j: the (already scaled) accumulated impulses act on the body velocities
-DEV void jointWarmApply(Ctx c, int j) {
+DEV void jointWarmApply(Ctx c, int j, float dtRatio) {
     const int jr = mjoint(c, j, 0);
     const int4 jh = mi4(c, jr + MJ_TYPE);
+    if (jh.x == 2) {
+        prismaticInit(c, j, dtRatio);
+        return;
+    }
     const int4 off = mi4(c, jr + MJ_SOFF);
     const float4 im = m4(c, jr + MJ_MA);
     const bool staticA = (jh.w & 4) != 0, staticB = (jh.w & 8) != 0;
@@ -326,7 +331,9 @@ DEV void velocityIterations(Ctx c, const Grp<LPW>& g, const WorldShared& W, int 
                 for (int i = 0; i < nj; ++i) {
                     const int jr = mjoint(c, W.joints[i], 0);
                     const int4 jh = mi4(c, jr + MJ_TYPE);
-                    if (jh.x == 0) frictionSolveVel(c, jr); else revoluteSolveVel(c, jr, jh.w);
+                    if (jh.x == 0) frictionSolveVel(c, jr);
+                    else if (jh.x == 1) revoluteSolveVel(c, jr, jh.w);
+                    else prismaticSolveVel(c, jr, jh.w);
                 }
                 for (int i = 0; i < W.nc; ++i) contactSolveVel(c, W.contacts[i]);
             }
@@ -341,7 +348,9 @@ DEV void velocityIterations(Ctx c, const Grp<LPW>& g, const WorldShared& W, int 
             if (i < nj) {
                 const int jr = mjoint(c, W.joints[i], 0);
                 const int4 jh = mi4(c, jr + MJ_TYPE);
-                if (jh.x == 0) frictionSolveVel(c, jr); else revoluteSolveVel(c, jr, jh.w);
+                if (jh.x == 0) frictionSolveVel(c, jr);
+                else if (jh.x == 1) revoluteSolveVel(c, jr, jh.w);
+                else prismaticSolveVel(c, jr, jh.w);
             } else {
                 contactSolveVel(c, W.contacts[i - nj]);
             }
@@ -377,7 +386,7 @@ DEV void solveIslandsMulti(Ctx c, const Grp<LPW>& g, WorldShared& W, float dtRat
     gsync(g);
     if (g.s == 0) {  // warm starts add to body velocities: list order (contacts, then joints)
         for (int i = 0; i < nc; ++i) contactWarmStart(c, W.contacts[i]);
-        for (int i = 0; i < nj; ++i) jointWarmApply(c, W.joints[i]);
+        for (int i = 0; i < nj; ++i) jointWarmApply(c, W.joints[i], dtRatio);
     }
     gsync(g);
 
@@ -409,10 +418,10 @@ DEV void solveIslandsMulti(Ctx c, const Grp<LPW>& g, WorldShared& W, float dtRat
             for (int i = 0; i < nj; ++i) {
                 const int jr = mjoint(c, W.joints[i], 0);
                 const int4 jh = mi4(c, jr + MJ_TYPE);
-                if (jh.x != 1) continue;
+                if (jh.x == 0) continue;
                 const int isl = W.bodyIsl[(jh.w & 4) ? jh.z : jh.y];
                 if (((open >> isl) & 1ull) == 0ull) continue;
-                if (!revoluteSolvePos(c, jr, jh.w)) bad |= 1ull << isl;
+                if (!(jh.x == 1 ? revoluteSolvePos(c, jr, jh.w) : prismaticSolvePos(c, jr, jh.w))) bad |= 1ull << isl;
             }
             solved |= open & ~bad;
             open &= bad;

@@ -94,9 +94,14 @@ DEV Vel zeroVel() {
 }
 
 // b2FrictionJoint / b2RevoluteJoint::InitVelocityConstraints
+DEVN void prismaticInit(Ctx c, int j, float dtRatio);
 DEVN void jointInit(Ctx c, int j, float dtRatio) {
     const int jr = mjoint(c, j, 0);
     const int4 jh = mi4(c, jr + MJ_TYPE);     // type bodyA bodyB flags
+    if (jh.x == 2) {
+        prismaticInit(c, j, dtRatio);
+        return;
+    }
     const int4 off = mi4(c, jr + MJ_SOFF);    // js jw bodyA bodyB (state byte offsets)
     const float4 arm = m4(c, jr + MJ_RA0X);   // localAnchorA - localCenterA, localAnchorB - localCenterB
     const float4 im = m4(c, jr + MJ_MA);      // mA iA mB iB
@@ -373,6 +378,252 @@ DEV void revoluteSolveVel(Ctx c, int jr, int modelFlags) {
     st4(c, js + SJ_IMPULSE4, imp4);
     if (!staticA) stVelAt(c, off.z, A);
     if (!staticB) stVelAt(c, off.w, B);
+}
+
+// ---- b2PrismaticJoint (2.3.1; created by the reference at Box2DWorld.cpp:920-940) ---------------------------------------------
+// b2Mat33::Solve22 of the symmetric K = [k11 k12; k12 k22]
+DEV V2 solveSym22(float k11, float k12, float k22, V2 b) {
+    float a11 = k11, a12 = k12, a21 = k12, a22 = k22;
+    float det = a11 * a22 - a12 * a21;
+    if (det != 0.0f) det = 1.0f / det;
+    V2 x;
+    x.x = det * (a22 * b.x - a12 * b.y);
+    x.y = det * (a11 * b.y - a21 * b.x);
+    return x;
+}
+
+// b2PrismaticJoint::InitVelocityConstraints (warm start included)
+DEVN void prismaticInit(Ctx c, int j, float dtRatio) {
+    const int jr = mjoint(c, j, 0);
+    const int4 jh = mi4(c, jr + MJ_TYPE);     // type bodyA bodyB flags
+    const int4 off = mi4(c, jr + MJ_SOFF);    // js jw bodyA bodyB (state byte offsets)
+    const float4 arm = m4(c, jr + MJ_RA0X);   // localAnchorA - localCenterA, localAnchorB - localCenterB
+    const float4 im = m4(c, jr + MJ_MA);      // mA iA mB iB
+    const bool staticA = (jh.w & 4) != 0, staticB = (jh.w & 8) != 0;
+    const int js = off.x, jw = off.y;
+    Vel A = staticA ? zeroVel() : ldVelAt(c, off.z);
+    Vel B = staticB ? zeroVel() : ldVelAt(c, off.w);
+    const Pos PA = ldPosAt(c, off.z), PB = ldPosAt(c, off.w);
+    Rot qA = ldRotAt(c, off.z), qB = ldRotAt(c, off.w);
+    V2 rA = mul(qA, mk(arm.x, arm.y));
+    V2 rB = mul(qB, mk(arm.z, arm.w));
+    V2 d = (PB.c - PA.c) + rB - rA;
+    float mA = im.x, mB = im.z;
+    float iA = im.y, iB = im.w;
+    const V2 lx = mk(mF(c, jr + MJ_AXISX), mF(c, jr + MJ_AXISY));
+    const V2 ly = cross(1.0f, lx);
+    V2 axis = mul(qA, lx);
+    float a1 = cross(d + rA, axis);
+    float a2 = cross(rB, axis);
+    V2 perp = mul(qA, ly);
+    float s1 = cross(d + rA, perp);
+    float s2 = cross(rB, perp);
+    float k11 = mA + mB + iA * s1 * s1 + iB * s2 * s2;
+    float k12 = iA * s1 + iB * s2;
+    float k13 = iA * s1 * a1 + iB * s2 * a2;
+    float k23 = iA * a1 + iB * a2;
+    float k33 = mA + mB + iA * a1 * a1 + iB * a2 * a2;
+    st4(c, jw + WJ_R4, mk4(axis.x, axis.y, perp.x, perp.y));
+    st4(c, jw + WJ_M0, mk4(s1, s2, a1, a2));
+    st4(c, jw + WJ_M1, mk4(k11, k12, k13, k23));
+
+    float4 mot = ld4(c, js + SJ_MOTOR4);  // flags maxMotorForce motorSpeed | k33
+    int flags = __float_as_int(mot.x);
+    const bool enableMotor = (flags & 4) != 0;
+    int limitState = flags & 3;
+    const bool enableLimit = (jh.w & 1) != 0;
+    float4 imp = ld4(c, js + SJ_IMPULSE4);  // impulse.xyz motorImpulse
+    if (enableLimit) {
+        const float4 lim = m4(c, jr + MJ_REF);  // ref lower upper -
+        float jointTranslation = dot(axis, d);
+        if (absT(lim.z - lim.y) < 2.0f * B2G_LINEAR_SLOP) {
+            limitState = 3;
+        } else if (jointTranslation <= lim.y) {
+            if (limitState != 1) { limitState = 1; imp.z = 0.0f; }
+        } else if (jointTranslation >= lim.z) {
+            if (limitState != 2) { limitState = 2; imp.z = 0.0f; }
+        } else {
+            limitState = 0;
+            imp.z = 0.0f;
+        }
+    } else {
+        limitState = 0;
+        imp.z = 0.0f;
+    }
+    if (enableMotor == false) imp.w = 0.0f;
+    mot.x = __int_as_float((flags & ~3) | limitState);
+    mot.w = k33;
+    st4(c, js + SJ_MOTOR4, mot);
+    imp.x *= dtRatio; imp.y *= dtRatio; imp.z *= dtRatio;
+    imp.w *= dtRatio;
+    st4(c, js + SJ_IMPULSE4, imp);
+    V2 P = imp.x * perp + (imp.w + imp.z) * axis;
+    float LA = imp.x * s1 + imp.y + (imp.w + imp.z) * a1;
+    float LB = imp.x * s2 + imp.y + (imp.w + imp.z) * a2;
+    A.v = A.v - mA * P;
+    A.w -= iA * LA;
+    B.v = B.v + mB * P;
+    B.w += iB * LB;
+    if (!staticA) stVelAt(c, off.z, A);
+    if (!staticB) stVelAt(c, off.w, B);
+}
+
+// b2PrismaticJoint::SolveVelocityConstraints
+DEVN void prismaticSolveVel(Ctx c, int jr, int modelFlags) {
+    const int4 off = mi4(c, jr + MJ_SOFF);  // js jw bodyA bodyB
+    const float4 im = m4(c, jr + MJ_MA);    // mA iA mB iB
+    const int js = off.x, jw = off.y;
+    const bool staticA = (modelFlags & 4) != 0, staticB = (modelFlags & 8) != 0;
+    Vel A = staticA ? zeroVel() : ldVelAt(c, off.z);
+    Vel B = staticB ? zeroVel() : ldVelAt(c, off.w);
+    float mA = im.x, mB = im.z;
+    float iA = im.y, iB = im.w;
+    const float4 ap = ld4(c, jw + WJ_R4);    // axis.xy perp.xy
+    const float4 sa = ld4(c, jw + WJ_M0);    // s1 s2 a1 a2
+    const float4 kk = ld4(c, jw + WJ_M1);    // k11 k12 k13 k23
+    const float4 mot = ld4(c, js + SJ_MOTOR4);  // flags maxMotorForce motorSpeed k33
+    float4 imp = ld4(c, js + SJ_IMPULSE4);      // impulse.xyz motorImpulse
+    const V2 axis = mk(ap.x, ap.y), perp = mk(ap.z, ap.w);
+    const float s1 = sa.x, s2 = sa.y, a1 = sa.z, a2 = sa.w;
+    const int flags = __float_as_int(mot.x);
+    const bool enableMotor = (flags & 4) != 0;
+    const int limitState = flags & 3;
+    const bool enableLimit = (modelFlags & 1) != 0;
+    const float k33 = mot.w;
+    float k22 = iA + iB;
+    if (k22 == 0.0f) k22 = 1.0f;
+
+    if (enableMotor && limitState != 3) {
+        float motorMass = k33;  // m_motorMass is the same expression as k33, inverted when positive
+        if (motorMass > 0.0f) motorMass = 1.0f / motorMass;
+        float Cdot = dot(axis, B.v - A.v) + a2 * B.w - a1 * A.w;
+        float impulse = motorMass * (mot.z - Cdot);
+        float oldImpulse = imp.w;
+        float maxImpulse = PRM().dt * mot.y;
+        imp.w = clampT(imp.w + impulse, -maxImpulse, maxImpulse);
+        impulse = imp.w - oldImpulse;
+        V2 P = impulse * axis;
+        float LA = impulse * a1;
+        float LB = impulse * a2;
+        A.v = A.v - mA * P;
+        A.w -= iA * LA;
+        B.v = B.v + mB * P;
+        B.w += iB * LB;
+    }
+    V2 Cdot1;
+    Cdot1.x = dot(perp, B.v - A.v) + s2 * B.w - s1 * A.w;
+    Cdot1.y = B.w - A.w;
+    if (enableLimit && limitState != 0) {
+        float Cdot2 = dot(axis, B.v - A.v) + a2 * B.w - a1 * A.w;
+        V3 f1 = {imp.x, imp.y, imp.z};
+        const float m[9] = {kk.x, kk.y, kk.z, kk.y, k22, kk.w, kk.z, kk.w, k33};
+        V3 rhs = {-Cdot1.x, -Cdot1.y, -Cdot2};
+        V3 df = solve33(m, rhs);
+        imp.x += df.x; imp.y += df.y; imp.z += df.z;
+        if (limitState == 1) imp.z = fmaxT(imp.z, 0.0f);
+        else if (limitState == 2) imp.z = fminT(imp.z, 0.0f);
+        V2 b = -Cdot1 - (imp.z - f1.z) * mk(kk.z, kk.w);
+        V2 f2r = solveSym22(kk.x, kk.y, k22, b) + mk(f1.x, f1.y);
+        imp.x = f2r.x;
+        imp.y = f2r.y;
+        df.x = imp.x - f1.x; df.y = imp.y - f1.y; df.z = imp.z - f1.z;
+        V2 P = df.x * perp + df.z * axis;
+        float LA = df.x * s1 + df.y + df.z * a1;
+        float LB = df.x * s2 + df.y + df.z * a2;
+        A.v = A.v - mA * P;
+        A.w -= iA * LA;
+        B.v = B.v + mB * P;
+        B.w += iB * LB;
+    } else {
+        V2 df = solveSym22(kk.x, kk.y, k22, -Cdot1);
+        imp.x += df.x;
+        imp.y += df.y;
+        V2 P = df.x * perp;
+        float LA = df.x * s1 + df.y;
+        float LB = df.x * s2 + df.y;
+        A.v = A.v - mA * P;
+        A.w -= iA * LA;
+        B.v = B.v + mB * P;
+        B.w += iB * LB;
+    }
+    st4(c, js + SJ_IMPULSE4, imp);
+    if (!staticA) stVelAt(c, off.z, A);
+    if (!staticB) stVelAt(c, off.w, B);
+}
+
+// b2PrismaticJoint::SolvePositionConstraints
+DEVN bool prismaticSolvePos(Ctx c, int jr, int modelFlags) {
+    const int4 off = mi4(c, jr + MJ_SOFF);
+    const float4 im = m4(c, jr + MJ_MA);
+    const float4 arm = m4(c, jr + MJ_RA0X);
+    Pos A = ldPosAt(c, off.z);
+    Pos B = ldPosAt(c, off.w);
+    float mA = im.x, mB = im.z;
+    float iA = im.y, iB = im.w;
+    Rot qA = rotOf(A.a), qB = rotOf(B.a);
+    V2 rA = mul(qA, mk(arm.x, arm.y));
+    V2 rB = mul(qB, mk(arm.z, arm.w));
+    V2 d = B.c + rB - A.c - rA;
+    const V2 lx = mk(mF(c, jr + MJ_AXISX), mF(c, jr + MJ_AXISY));
+    V2 axis = mul(qA, lx);
+    float a1 = cross(d + rA, axis);
+    float a2 = cross(rB, axis);
+    V2 perp = mul(qA, cross(1.0f, lx));
+    float s1 = cross(d + rA, perp);
+    float s2 = cross(rB, perp);
+    const float4 lim = m4(c, jr + MJ_REF);  // ref lower upper -
+    V3 impulse;
+    V2 C1;
+    C1.x = dot(perp, d);
+    C1.y = B.a - A.a - lim.x;
+    float linearError = absT(C1.x);
+    float angularError = absT(C1.y);
+    bool active = false;
+    float C2 = 0.0f;
+    if ((modelFlags & 1) != 0) {
+        float translation = dot(axis, d);
+        if (absT(lim.z - lim.y) < 2.0f * B2G_LINEAR_SLOP) {
+            C2 = clampT(translation, -B2G_MAX_LINEAR_CORRECTION, B2G_MAX_LINEAR_CORRECTION);
+            linearError = fmaxT(linearError, absT(translation));
+            active = true;
+        } else if (translation <= lim.y) {
+            C2 = clampT(translation - lim.y + B2G_LINEAR_SLOP, -B2G_MAX_LINEAR_CORRECTION, 0.0f);
+            linearError = fmaxT(linearError, lim.y - translation);
+            active = true;
+        } else if (translation >= lim.z) {
+            C2 = clampT(translation - lim.z - B2G_LINEAR_SLOP, 0.0f, B2G_MAX_LINEAR_CORRECTION);
+            linearError = fmaxT(linearError, translation - lim.z);
+            active = true;
+        }
+    }
+    float k11 = mA + mB + iA * s1 * s1 + iB * s2 * s2;
+    float k12 = iA * s1 + iB * s2;
+    float k22 = iA + iB;
+    if (k22 == 0.0f) k22 = 1.0f;
+    if (active) {
+        float k13 = iA * s1 * a1 + iB * s2 * a2;
+        float k23 = iA * a1 + iB * a2;
+        float k33 = mA + mB + iA * a1 * a1 + iB * a2 * a2;
+        const float m[9] = {k11, k12, k13, k12, k22, k23, k13, k23, k33};
+        V3 rhs = {-C1.x, -C1.y, -C2};
+        impulse = solve33(m, rhs);
+    } else {
+        // b2Mat22::Solve: a11 = ex.x, a12 = ey.x, a21 = ex.y, a22 = ey.y
+        V2 i1 = solve22(k11, k12, k12, k22, -C1);
+        impulse.x = i1.x;
+        impulse.y = i1.y;
+        impulse.z = 0.0f;
+    }
+    V2 P = impulse.x * perp + impulse.z * axis;
+    float LA = impulse.x * s1 + impulse.y + impulse.z * a1;
+    float LB = impulse.x * s2 + impulse.y + impulse.z * a2;
+    A.c = A.c - mA * P;
+    A.a -= iA * LA;
+    B.c = B.c + mB * P;
+    B.a += iB * LB;
+    stPosAt(c, off.z, A);
+    stPosAt(c, off.w, B);
+    return linearError <= B2G_LINEAR_SLOP && angularError <= B2G_ANGULAR_SLOP;
 }
 
 // b2Island::Solve's joint work for an island that consists of one dynamic body and its ground-friction joint:
@@ -1100,8 +1351,10 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
             const int4 jh = mi4(c, jr + MJ_TYPE);  // type bodyA bodyB flags
             if (jh.x == 0) {
                 frictionSolveVel(c, jr);
-            } else {
+            } else if (jh.x == 1) {
                 revoluteSolveVel(c, jr, jh.w);
+            } else {
+                prismaticSolveVel(c, jr, jh.w);
             }
         }
         for (int i = 0; i < L.nc; ++i) contactSolveVel(c, L.contacts[i]);
@@ -1133,10 +1386,10 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
         for (int i = 0; i < L.nj; ++i) {
             const int jr = mjoint(c, L.joints[i], 0);
             const int4 jh = mi4(c, jr + MJ_TYPE);
-            if (jh.x != 1) continue;
+            if (jh.x == 0) continue;
             const int isl = L.bodyIsl[(jh.w & 4) ? jh.z : jh.y];
             if (((open >> isl) & 1ull) == 0ull) continue;
-            if (!revoluteSolvePos(c, jr, jh.w)) bad |= 1ull << isl;
+            if (!(jh.x == 1 ? revoluteSolvePos(c, jr, jh.w) : prismaticSolvePos(c, jr, jh.w))) bad |= 1ull << isl;
         }
         solved |= open & ~bad;
         open &= bad;

@@ -31,6 +31,34 @@ DEV float jointSpeed(Ctx c, int j) {
     int bA = mI(c, mjoint(c, j, MJ_BODYA)), bB = mI(c, mjoint(c, j, MJ_BODYB));
     return ldF(c, bslot(c, bB, SB_W)) - ldF(c, bslot(c, bA, SB_W));
 }
+// b2PrismaticJoint::GetJointTranslation / GetJointSpeed (:974-977, :1039-1042): reported in Box2D units, like the reference
+DEV float prismaticTranslation(Ctx c, int j) {
+    const int jr = mjoint(c, j, 0);
+    int bA = mI(c, jr + MJ_BODYA), bB = mI(c, jr + MJ_BODYB);
+    V2 pA = mul(ldXF(c, bA), mk(mF(c, jr + MJ_LAX), mF(c, jr + MJ_LAY)));
+    V2 pB = mul(ldXF(c, bB), mk(mF(c, jr + MJ_LBX), mF(c, jr + MJ_LBY)));
+    V2 d = pB - pA;
+    V2 axis = mul(ldXF(c, bA).q, mk(mF(c, jr + MJ_AXISX), mF(c, jr + MJ_AXISY)));
+    return dot(d, axis);
+}
+DEV float prismaticSpeed(Ctx c, int j) {
+    const int jr = mjoint(c, j, 0);
+    int bA = mI(c, jr + MJ_BODYA), bB = mI(c, jr + MJ_BODYB);
+    const float4 arm = m4(c, jr + MJ_RA0X);
+    const Rot qA = ldXF(c, bA).q, qB = ldXF(c, bB).q;
+    V2 rA = mul(qA, mk(arm.x, arm.y));
+    V2 rB = mul(qB, mk(arm.z, arm.w));
+    V2 p1 = ldV2(c, bslot(c, bA, SB_CX)) + rA;
+    V2 p2 = ldV2(c, bslot(c, bB, SB_CX)) + rB;
+    V2 d = p2 - p1;
+    V2 axis = mul(qA, mk(mF(c, jr + MJ_AXISX), mF(c, jr + MJ_AXISY)));
+    V2 vA = ldV2(c, bslot(c, bA, SB_VX)), vB = ldV2(c, bslot(c, bB, SB_VX));
+    float wA = ldF(c, bslot(c, bA, SB_W)), wB = ldF(c, bslot(c, bB, SB_W));
+    return dot(d, cross(wA, axis)) + dot(axis, vB + cross(wB, rB) - vA - cross(wA, rA));
+}
+// Box2DJoint::getPosition / getVelocity (:965-981, :1030-1046)
+DEV float jointPosition(Ctx c, int j) { return mI(c, mjoint(c, j, MJ_TYPE)) == 2 ? prismaticTranslation(c, j) : jointAngle(c, j); }
+DEV float jointVelocity(Ctx c, int j) { return mI(c, mjoint(c, j, MJ_TYPE)) == 2 ? prismaticSpeed(c, j) : jointSpeed(c, j); }
 DEV int objJoint(Ctx c, int o, int i) { return mI(c, H().oObjJoint + mI(c, mobj(c, o, MO_JOINT_START)) + i) & 0xffff; }
 DEV int objJointChildPos(Ctx c, int o, int i) { return mI(c, H().oObjJoint + mI(c, mobj(c, o, MO_JOINT_START)) + i) >> 16; }
 DEV V2 jointAnchorA(Ctx c, int j) {  // b2RevoluteJoint::GetAnchorA
@@ -49,7 +77,7 @@ DEV void getDofPositions(Ctx c, int o, float* q) {
         n = 3;
     }
     int nj = mI(c, mobj(c, o, MO_JOINT_COUNT));
-    for (int i = 0; i < nj; ++i) q[n + i] = jointAngle(c, objJoint(c, o, i));
+    for (int i = 0; i < nj; ++i) q[n + i] = jointPosition(c, objJoint(c, o, i));
 }
 DEV void getDofVelocities(Ctx c, int o, float* qd) {
     int isStatic = mI(c, mobj(c, o, MO_STATIC));
@@ -63,7 +91,7 @@ DEV void getDofVelocities(Ctx c, int o, float* qd) {
         n = 3;
     }
     int nj = mI(c, mobj(c, o, MO_JOINT_COUNT));
-    for (int i = 0; i < nj; ++i) qd[n + i] = jointSpeed(c, objJoint(c, o, i));
+    for (int i = 0; i < nj; ++i) qd[n + i] = jointVelocity(c, objJoint(c, o, i));
 }
 
 // Box2DLink::setPose(pose, update_children = true, joint_override) (:405-438) together with the
@@ -75,16 +103,22 @@ DEVN void placeSubtree(Ctx c, int o, int pos, const float pose[3], bool jointOve
     float jv[kMaxLinksPerObject];
     for (int i = 1; i < count; ++i) {
         int j = mI(c, olink(c, o, pos + i, ML_PARENT_JOINT));
-        jv[i] = jointOverride ? 0.0f : jointAngle(c, j);
+        jv[i] = jointOverride ? 0.0f : jointPosition(c, j);
     }
     float s = H().scale, inv = H().invScale;
+    int skipUntil = 0;  // links behind a prismatic joint stay where they are: Box2DJoint::resetPosition is a no-op there (:1021-1026)
     for (int i = 0; i < count; ++i) {
         int b = mI(c, olink(c, o, pos + i, ML_BODY));
         float px, py, th;
+        if (i < skipUntil) continue;
         if (i == 0) {
             px = pose[0]; py = pose[1]; th = pose[2];
         } else {
             int j = mI(c, olink(c, o, pos + i, ML_PARENT_JOINT));
+            if (mI(c, mjoint(c, j, MJ_TYPE)) == 2) {
+                skipUntil = i + mI(c, olink(c, o, pos + i, ML_SUBTREE));
+                continue;
+            }
             int bA = mI(c, mjoint(c, j, MJ_BODYA));
             int dof = mI(c, mjoint(c, j, MJ_DOF));
             float clamped = clampStd(jv[i], dofLimit(c, dof, 0), dofLimit(c, dof, 1));
@@ -272,6 +306,8 @@ DEVN void initWorld(Ctx c) {
         for (int k = 0; k < SJ_CHUNKS; ++k) st4(c, jslot(c, j, k * kChunkBytes), zero);
         int enableMotor = (mI(c, mjoint(c, j, MJ_FLAGS)) >> 1) & 1;
         stI(c, jslot(c, j, SJ_FLAGS), enableMotor << 2);
+        // b2PrismaticJointDef::maxMotorForce (:936-937); motorSpeed stays 0: an actuated prismatic joint brakes
+        if (mI(c, mjoint(c, j, MJ_TYPE)) == 2) stF(c, jslot(c, j, SJ_MAX_MOTOR_TORQUE), mF(c, mjoint(c, j, MJ_MAXFORCE)));
         for (int k = 0; k < WJ_CHUNKS; ++k) st4(c, jwslot(c, j, k * kChunkBytes), zero);
     }
     for (int k = 0; k < h.maxc; ++k) {

@@ -45,7 +45,7 @@ enum FixtureField {  // per fixture / broad-phase proxy (creation order == proxy
     MF_STRIDE = MF_NORMALS + 16
 };
 enum JointField {
-    MJ_TYPE = 0,  // 0 friction, 1 revolute
+    MJ_TYPE = 0,  // 0 friction, 1 revolute, 2 prismatic
     MJ_BODYA, MJ_BODYB,
     MJ_FLAGS,     // bit0 enableLimit, bit1 enableMotor at creation, bit2 bodyA is static, bit3 bodyB is static
     MJ_LAX, MJ_LAY, MJ_LBX, MJ_LBY,
@@ -53,13 +53,13 @@ enum JointField {
     MJ_MAXTORQUE,
     MJ_DOF,       // index in the world state vector (revolute joints of objects), -1 otherwise
     MJ_OBJECT,
-    MJ_SPARE,
+    MJ_AXISX,     // prismatic: b2PrismaticJoint::m_localXAxisA (normalised); .y is MJ_AXISY below
     // solver record: everything the velocity / position sweeps need, 16-byte groups, no dependent look-ups
     MJ_SOFF, MJ_WOFF, MJ_BAOFF, MJ_BBOFF,  // byte offsets into the per-world state: joint state, joint scratch, bodyA, bodyB
     MJ_RA0X, MJ_RA0Y, MJ_RB0X, MJ_RB0Y,    // localAnchorA - localCenterA, localAnchorB - localCenterB
     MJ_HMAXFORCE, MJ_HMAXTORQUE,           // dt * maxForce, dt * maxTorque: written by the kernel prologue (depends on dt)
     MJ_ROTMASS,                            // m = iA + iB; if (m > 0) m = 1 / m: b2FrictionJoint::m_angularMass / b2RevoluteJoint::m_motorMass
-    MJ_SPARE3,
+    MJ_AXISY,
     MJ_MA, MJ_IA, MJ_MB, MJ_IB,            // invMass / invI of bodyA and bodyB
     MJ_STRIDE
 };
@@ -151,6 +151,10 @@ enum BodyState {
 //     SJ chunk 1  flags maxMotorTorque motorSpeed | K.zy (scratch)        WJ chunk 1  K.xx K.xy(=K.yx) K.yy K.zx   (K.zz = iA + iB)
 //     WJ chunk 2 (only written / read while the joint limit is active): the part of b2Mat33::Solve33 that does not depend
 //     on the right-hand side -- cross(K.ey, K.ez) and 1 / det(K) -- computed once per step instead of once per iteration
+//   prismatic (b2PrismaticJoint):
+//     SJ chunk 0  impulse.xyz motorImpulse                                WJ chunk 0  axis.xy perp.xy
+//     SJ chunk 1  flags maxMotorForce motorSpeed | k33 (scratch)          WJ chunk 1  s1 s2 a1 a2
+//                                                                         WJ chunk 2  k11 k12 k13 k23   (k22 = iA + iB, or 1)
 enum JointState {
     SJ_IX = B2G_F(0, 0), SJ_IY = B2G_F(0, 1), SJ_IZ = B2G_F(0, 2),  // friction: linearImpulse.xy, angularImpulse; revolute: m_impulse
     SJ_MOTOR_IMPULSE = B2G_F(0, 3),                                 // revolute only (friction: scratch)

@@ -183,6 +183,7 @@ struct BFix {
 struct BJoint {
     int type, bodyA, bodyB, flags;
     float lax, lay, lbx, lby, ref, lower, upper, maxForce, maxTorque;
+    float axisX = 0.0f, axisY = 0.0f;  // prismatic joints: normalised local axis in bodyA
     int dof = -1, object = -1;
     std::string name;  // revolute joints: the YAML name; ground-friction joints have none
 };
@@ -307,8 +308,10 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
         std::vector<BLink> links;        // pre-order
         std::vector<int> nameOrder;      // bodies in link-name order
         int nDofs = 0, dofOffset = 0;
+        bool hasPrismatic = false;
     };
     std::vector<BObject> objects;
+    std::vector<std::string> extraWarnings;
     std::vector<const ObjectDescription*> descs;
     for (auto& r : env.robots) descs.push_back(&r);
     for (auto& o : env.objects) descs.push_back(&o);
@@ -462,14 +465,14 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
         std::map<int, std::vector<std::pair<int, int>>> children;  // parent body -> (joint, child body), registration order
         std::map<int, int> parentJointOf;
         for (const JointDescription& jd : d.joints) {
-            if (jd.joint_type != "revolute")
-                throw std::runtime_error("joint '" + jd.name + "': joint_type '" + jd.joint_type +
-                                         "' is not supported (the reference cannot drive prismatic joints either: "
-                                         "Box2DWorld.cpp:1204-1208)");
+            // Box2DJoint ctor (:888-898): "revolute" / "prismatic"; anything else is reported and treated as revolute
+            const bool prismatic = jd.joint_type == "prismatic";
+            if (!prismatic && jd.joint_type != "revolute")
+                extraWarnings.push_back("Unknown joint type " + jd.joint_type + ". Using revolute instead.");
             if (!linkBody.count(jd.link_a) || !linkBody.count(jd.link_b))
                 throw std::runtime_error("joint '" + jd.name + "' names an unknown link");
             BJoint j;
-            j.type = 1;
+            j.type = prismatic ? 2 : 1;
             j.bodyA = linkBody[jd.link_a];
             j.bodyB = linkBody[jd.link_b];
             j.lax = scale * jd.axis[0];
@@ -483,6 +486,29 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
             j.flags = (n2 > 0.0 ? 1 : 0) | (jd.actuated ? 2 : 0);
             j.maxForce = 0.0f;
             j.maxTorque = 0.0f;
+            if (prismatic) {
+                // b2PrismaticJointDef as the reference fills it (:920-940): localAnchorA is NOT scaled, the translation limits
+                // are; the axis is the unit vector at axis_orientation (libm cos / sin of a description constant), normalised
+                // by b2PrismaticJoint's constructor; maxMotorForce = min |acceleration limits| (kept in maxForce)
+                j.lax = jd.axis[0];
+                j.lay = jd.axis[1];
+                j.lower = scale * jd.position_limits[0];
+                j.upper = scale * jd.position_limits[1];
+                float ax = std::cos(jd.axis_orientation), ay = std::sin(jd.axis_orientation);
+                float len = sqrtf(ax * ax + ay * ay);
+                if (!(len < FLT_EPSILON)) {
+                    float inv = 1.0f / len;
+                    ax *= inv;
+                    ay *= inv;
+                }
+                j.axisX = ax;
+                j.axisY = ay;
+                j.maxForce = std::min(std::abs(jd.acceleration_limits[0]), std::abs(jd.acceleration_limits[1]));
+                ob.hasPrismatic = true;
+                if (d.is_robot)
+                    throw std::runtime_error("unsupported: robot '" + d.name + "' has the prismatic joint '" + jd.name + "': the reference "
+                                             "cannot control it (Box2DJoint::setControlTorque throws, Box2DWorld.cpp:1204-1208)");
+            }
             j.dof = nq + baseDofs + (int)ob.jointList.size();
             j.object = (int)oi;
             j.name = jd.name;
@@ -655,6 +681,7 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
         w[MJ_REF] = fbits(jt.ref); w[MJ_LOWER] = fbits(jt.lower); w[MJ_UPPER] = fbits(jt.upper);
         w[MJ_MAXFORCE] = fbits(jt.maxForce); w[MJ_MAXTORQUE] = fbits(jt.maxTorque);
         w[MJ_DOF] = (uint32_t)jt.dof; w[MJ_OBJECT] = (uint32_t)jt.object;
+        w[MJ_AXISX] = fbits(jt.axisX); w[MJ_AXISY] = fbits(jt.axisY);
         const BBody& A = bodies[jt.bodyA];
         const BBody& Bd = bodies[jt.bodyB];
         if (A.type == 0) w[MJ_FLAGS] |= 4u;
@@ -722,6 +749,10 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
             continue;
         }
         const StateDescription& sd = it->second;
+        if (ob.hasPrismatic)
+            throw std::runtime_error("unsupported: object '" + ob.d->name + "' has a prismatic joint and a `states` entry: the reference "
+                                     "throws while applying it (Box2DLink::updateBodyVelocities -> getGlobalAxisPosition, "
+                                     "Box2DWorld.cpp:789, 1282-1285)");
         int expect = ob.d->is_static ? ob.nDofs + 3 : ob.nDofs;
         if ((int)sd.configuration.size() != expect || (int)sd.velocity.size() != expect)
             throw std::runtime_error("state of '" + ob.d->name + "' needs " + std::to_string(expect) + " values");
@@ -792,6 +823,7 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
         info.firstBody = objects[oi].firstBody;
         info.nLinks = objects[oi].nLinks;
         info.nJoints = (int)objects[oi].jointList.size();
+        info.hasPrismatic = objects[oi].hasPrismatic;
         info.ballStart = (int)out.balls.size() / 8;
         for (int b : objects[oi].nameOrder) {
             const LinkDescription& ld = objects[oi].d->links[b - objects[oi].firstBody];
@@ -837,6 +869,7 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
         fo[12] = joints[j].ref; fo[13] = joints[j].lower; fo[14] = joints[j].upper;
     }
     out.warnings = env.warnings;
+    out.warnings.insert(out.warnings.end(), extraWarnings.begin(), extraWarnings.end());
     out.jointNames.clear();
     for (int j = 0; j < nj; ++j) out.jointNames.push_back(joints[j].name);
     linkAabb.resize(4 * nb, 0.0f);

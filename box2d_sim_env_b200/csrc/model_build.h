@@ -13,6 +13,9 @@ struct HostObjectInfo {
     bool isRobot = false, isStatic = false;
     int nDofs = 0, dofOffset = 0, firstBody = 0, nLinks = 0, nJoints = 0;
     int ballStart = 0, nBalls = 0;  // rows of HostModel::balls
+    // the object has a prismatic joint: the reference cannot place it or set its velocities (Box2DJoint::resetPosition is a
+    // no-op, getGlobalAxisPosition throws inside updateBodyVelocities; Box2DWorld.cpp:1021-1026, 1274-1287, 789)
+    bool hasPrismatic = false;
 };
 
 struct HostModel {

@@ -328,6 +328,9 @@ void b2o_world_get_joints(void* wp, int* iout, float* fout) {
         fo[4] = j->maxMotorTorque; fo[5] = j->motorSpeed; fo[6] = j->maxForce; fo[7] = j->maxTorque;
         fo[8] = j->localAnchorA.x; fo[9] = j->localAnchorA.y; fo[10] = j->localAnchorB.x; fo[11] = j->localAnchorB.y;
         fo[12] = j->referenceAngle; fo[13] = j->lowerAngle; fo[14] = j->upperAngle;
+        if (j->kind == kPrismaticJoint) {  // motor force and translation limits in the revolute joint's slots
+            fo[4] = j->maxMotorForce; fo[13] = j->lowerTranslation; fo[14] = j->upperTranslation;
+        }
     }
 }
 

@@ -275,6 +275,31 @@ Joint* World::CreateRevoluteJoint(Body* a, Body* b, const Vec2& anchorA, const V
     return j;
 }
 
+// b2PrismaticJoint::b2PrismaticJoint (2.3.1), created by the reference at Box2DWorld.cpp:920-940
+Joint* World::CreatePrismaticJoint(Body* a, Body* b, const Vec2& anchorA, const Vec2& anchorB, const Vec2& axisA, float refAngle,
+                                   float lower, float upper, bool enableLimit, float maxMotorForce_, bool enableMotor_) {
+    Joint* j = new Joint();
+    j->kind = kPrismaticJoint;
+    j->bodyA = a;
+    j->bodyB = b;
+    j->collideConnected = false;
+    j->localAnchorA = anchorA;
+    j->localAnchorB = anchorB;
+    j->localXAxisA = axisA;
+    j->localXAxisA.Normalize();
+    j->localYAxisA = Cross(1.0f, j->localXAxisA);
+    j->referenceAngle = refAngle;
+    j->lowerTranslation = lower;
+    j->upperTranslation = upper;
+    j->maxMotorForce = maxMotorForce_;
+    j->motorSpeed = 0.0f;
+    j->enableLimit = enableLimit;
+    j->enableMotor = enableMotor_;
+    j->limitState = kInactiveLimit;
+    LinkJoint(this, j);
+    return j;
+}
+
 // Solver data: positions/velocities live on the island; joints address them through
 // body->islandIndex exactly like upstream's b2SolverData.
 namespace {
@@ -284,7 +309,266 @@ thread_local Position* g_positions = nullptr;
 thread_local Velocity* g_velocities = nullptr;
 }  // namespace
 
+// ---- b2PrismaticJoint (2.3.1) -----------------------------------------------------------------------------------------
+// Linear constraint (point-to-line):   C = dot(perp, d),  Cdot = dot(perp, vB - vA) + s2 wB - s1 wA
+// Angular constraint:                  C = aB - aA - referenceAngle
+// Motor / limit along the axis:        Cdot = dot(axis, vB - vA) + a2 wB - a1 wA
+void Joint::PrismaticInit(const TimeStep& step) {
+    int indexA = bodyA->islandIndex, indexB = bodyB->islandIndex;
+    localCenterA = bodyA->sweep.localCenter;
+    localCenterB = bodyB->sweep.localCenter;
+    invMassA = bodyA->invMass;
+    invMassB = bodyB->invMass;
+    invIA = bodyA->invI;
+    invIB = bodyB->invI;
+    Vec2 cA = g_positions[indexA].c;
+    float aA = g_positions[indexA].a;
+    Vec2 vA = g_velocities[indexA].v;
+    float wA = g_velocities[indexA].w;
+    Vec2 cB = g_positions[indexB].c;
+    float aB = g_positions[indexB].a;
+    Vec2 vB = g_velocities[indexB].v;
+    float wB = g_velocities[indexB].w;
+    Rot qA(aA), qB(aB);
+    rA = Mul(qA, localAnchorA - localCenterA);
+    rB = Mul(qB, localAnchorB - localCenterB);
+    Vec2 d = (cB - cA) + rB - rA;
+    float mA = invMassA, mB = invMassB;
+    float iA = invIA, iB = invIB;
+    {
+        axis = Mul(qA, localXAxisA);
+        a1 = Cross(d + rA, axis);
+        a2 = Cross(rB, axis);
+        motorMass = mA + mB + iA * a1 * a1 + iB * a2 * a2;
+        if (motorMass > 0.0f) motorMass = 1.0f / motorMass;
+    }
+    {
+        perp = Mul(qA, localYAxisA);
+        s1 = Cross(d + rA, perp);
+        s2 = Cross(rB, perp);
+        float k11 = mA + mB + iA * s1 * s1 + iB * s2 * s2;
+        float k12 = iA * s1 + iB * s2;
+        float k13 = iA * s1 * a1 + iB * s2 * a2;
+        float k22 = iA + iB;
+        if (k22 == 0.0f) k22 = 1.0f;
+        float k23 = iA * a1 + iB * a2;
+        float k33 = mA + mB + iA * a1 * a1 + iB * a2 * a2;
+        massMat.ex = Vec3(k11, k12, k13);
+        massMat.ey = Vec3(k12, k22, k23);
+        massMat.ez = Vec3(k13, k23, k33);
+    }
+    if (enableLimit) {
+        float jointTranslation = Dot(axis, d);
+        if (Abs(upperTranslation - lowerTranslation) < 2.0f * kLinearSlop) {
+            limitState = kEqualLimits;
+        } else if (jointTranslation <= lowerTranslation) {
+            if (limitState != kAtLowerLimit) {
+                limitState = kAtLowerLimit;
+                impulse.z = 0.0f;
+            }
+        } else if (jointTranslation >= upperTranslation) {
+            if (limitState != kAtUpperLimit) {
+                limitState = kAtUpperLimit;
+                impulse.z = 0.0f;
+            }
+        } else {
+            limitState = kInactiveLimit;
+            impulse.z = 0.0f;
+        }
+    } else {
+        limitState = kInactiveLimit;
+        impulse.z = 0.0f;
+    }
+    if (enableMotor == false) motorImpulse = 0.0f;
+    if (step.warmStarting) {
+        impulse *= step.dtRatio;
+        motorImpulse *= step.dtRatio;
+        Vec2 P = impulse.x * perp + (motorImpulse + impulse.z) * axis;
+        float LA = impulse.x * s1 + impulse.y + (motorImpulse + impulse.z) * a1;
+        float LB = impulse.x * s2 + impulse.y + (motorImpulse + impulse.z) * a2;
+        vA -= mA * P;
+        wA -= iA * LA;
+        vB += mB * P;
+        wB += iB * LB;
+    } else {
+        impulse.SetZero();
+        motorImpulse = 0.0f;
+    }
+    g_velocities[indexA].v = vA;
+    g_velocities[indexA].w = wA;
+    g_velocities[indexB].v = vB;
+    g_velocities[indexB].w = wB;
+}
+
+void Joint::PrismaticSolveVelocity(const TimeStep& step) {
+    int indexA = bodyA->islandIndex, indexB = bodyB->islandIndex;
+    Vec2 vA = g_velocities[indexA].v;
+    float wA = g_velocities[indexA].w;
+    Vec2 vB = g_velocities[indexB].v;
+    float wB = g_velocities[indexB].w;
+    float mA = invMassA, mB = invMassB;
+    float iA = invIA, iB = invIB;
+    if (enableMotor && limitState != kEqualLimits) {
+        float Cdot = Dot(axis, vB - vA) + a2 * wB - a1 * wA;
+        float imp = motorMass * (motorSpeed - Cdot);
+        float oldImpulse = motorImpulse;
+        float maxImpulse = step.dt * maxMotorForce;
+        motorImpulse = Clamp(motorImpulse + imp, -maxImpulse, maxImpulse);
+        imp = motorImpulse - oldImpulse;
+        Vec2 P = imp * axis;
+        float LA = imp * a1;
+        float LB = imp * a2;
+        vA -= mA * P;
+        wA -= iA * LA;
+        vB += mB * P;
+        wB += iB * LB;
+    }
+    Vec2 Cdot1;
+    Cdot1.x = Dot(perp, vB - vA) + s2 * wB - s1 * wA;
+    Cdot1.y = wB - wA;
+    if (enableLimit && limitState != kInactiveLimit) {
+        float Cdot2 = Dot(axis, vB - vA) + a2 * wB - a1 * wA;
+        Vec3 Cdot(Cdot1.x, Cdot1.y, Cdot2);
+        Vec3 f1 = impulse;
+        Vec3 df = massMat.Solve33(-Cdot);
+        impulse += df;
+        if (limitState == kAtLowerLimit) impulse.z = Max(impulse.z, 0.0f);
+        else if (limitState == kAtUpperLimit) impulse.z = Min(impulse.z, 0.0f);
+        Vec2 b = -Cdot1 - (impulse.z - f1.z) * Vec2(massMat.ez.x, massMat.ez.y);
+        Vec2 f2r = massMat.Solve22(b) + Vec2(f1.x, f1.y);
+        impulse.x = f2r.x;
+        impulse.y = f2r.y;
+        df = Vec3(impulse.x - f1.x, impulse.y - f1.y, impulse.z - f1.z);
+        Vec2 P = df.x * perp + df.z * axis;
+        float LA = df.x * s1 + df.y + df.z * a1;
+        float LB = df.x * s2 + df.y + df.z * a2;
+        vA -= mA * P;
+        wA -= iA * LA;
+        vB += mB * P;
+        wB += iB * LB;
+    } else {
+        Vec2 df = massMat.Solve22(-Cdot1);
+        impulse.x += df.x;
+        impulse.y += df.y;
+        Vec2 P = df.x * perp;
+        float LA = df.x * s1 + df.y;
+        float LB = df.x * s2 + df.y;
+        vA -= mA * P;
+        wA -= iA * LA;
+        vB += mB * P;
+        wB += iB * LB;
+    }
+    g_velocities[indexA].v = vA;
+    g_velocities[indexA].w = wA;
+    g_velocities[indexB].v = vB;
+    g_velocities[indexB].w = wB;
+}
+
+bool Joint::PrismaticSolvePosition() {
+    int indexA = bodyA->islandIndex, indexB = bodyB->islandIndex;
+    Vec2 cA = g_positions[indexA].c;
+    float aA = g_positions[indexA].a;
+    Vec2 cB = g_positions[indexB].c;
+    float aB = g_positions[indexB].a;
+    Rot qA(aA), qB(aB);
+    float mA = invMassA, mB = invMassB;
+    float iA = invIA, iB = invIB;
+    Vec2 rA_ = Mul(qA, localAnchorA - localCenterA);
+    Vec2 rB_ = Mul(qB, localAnchorB - localCenterB);
+    Vec2 d = cB + rB_ - cA - rA_;
+    Vec2 ax = Mul(qA, localXAxisA);
+    float a1_ = Cross(d + rA_, ax);
+    float a2_ = Cross(rB_, ax);
+    Vec2 pp = Mul(qA, localYAxisA);
+    float s1_ = Cross(d + rA_, pp);
+    float s2_ = Cross(rB_, pp);
+    Vec3 imp;
+    Vec2 C1;
+    C1.x = Dot(pp, d);
+    C1.y = aB - aA - referenceAngle;
+    float linearError = Abs(C1.x);
+    float angularError = Abs(C1.y);
+    bool active = false;
+    float C2 = 0.0f;
+    if (enableLimit) {
+        float translation = Dot(ax, d);
+        if (Abs(upperTranslation - lowerTranslation) < 2.0f * kLinearSlop) {
+            C2 = Clamp(translation, -kMaxLinearCorrection, kMaxLinearCorrection);
+            linearError = Max(linearError, Abs(translation));
+            active = true;
+        } else if (translation <= lowerTranslation) {
+            C2 = Clamp(translation - lowerTranslation + kLinearSlop, -kMaxLinearCorrection, 0.0f);
+            linearError = Max(linearError, lowerTranslation - translation);
+            active = true;
+        } else if (translation >= upperTranslation) {
+            C2 = Clamp(translation - upperTranslation - kLinearSlop, 0.0f, kMaxLinearCorrection);
+            linearError = Max(linearError, translation - upperTranslation);
+            active = true;
+        }
+    }
+    if (active) {
+        float k11 = mA + mB + iA * s1_ * s1_ + iB * s2_ * s2_;
+        float k12 = iA * s1_ + iB * s2_;
+        float k13 = iA * s1_ * a1_ + iB * s2_ * a2_;
+        float k22 = iA + iB;
+        if (k22 == 0.0f) k22 = 1.0f;
+        float k23 = iA * a1_ + iB * a2_;
+        float k33 = mA + mB + iA * a1_ * a1_ + iB * a2_ * a2_;
+        Mat33 K;
+        K.ex = Vec3(k11, k12, k13);
+        K.ey = Vec3(k12, k22, k23);
+        K.ez = Vec3(k13, k23, k33);
+        Vec3 C(C1.x, C1.y, C2);
+        imp = K.Solve33(-C);
+    } else {
+        float k11 = mA + mB + iA * s1_ * s1_ + iB * s2_ * s2_;
+        float k12 = iA * s1_ + iB * s2_;
+        float k22 = iA + iB;
+        if (k22 == 0.0f) k22 = 1.0f;
+        Mat22 K;
+        K.ex = Vec2(k11, k12);
+        K.ey = Vec2(k12, k22);
+        Vec2 impulse1 = K.Solve(-C1);
+        imp.x = impulse1.x;
+        imp.y = impulse1.y;
+        imp.z = 0.0f;
+    }
+    Vec2 P = imp.x * pp + imp.z * ax;
+    float LA = imp.x * s1_ + imp.y + imp.z * a1_;
+    float LB = imp.x * s2_ + imp.y + imp.z * a2_;
+    cA -= mA * P;
+    aA -= iA * LA;
+    cB += mB * P;
+    aB += iB * LB;
+    g_positions[indexA].c = cA;
+    g_positions[indexA].a = aA;
+    g_positions[indexB].c = cB;
+    g_positions[indexB].a = aB;
+    return linearError <= kLinearSlop && angularError <= kAngularSlop;
+}
+
+float Joint::GetJointTranslation() const {
+    Vec2 pA = bodyA->GetWorldPoint(localAnchorA);
+    Vec2 pB = bodyB->GetWorldPoint(localAnchorB);
+    Vec2 d = pB - pA;
+    Vec2 ax = Mul(bodyA->xf.q, localXAxisA);
+    return Dot(d, ax);
+}
+
+float Joint::GetPrismaticJointSpeed() const {
+    Vec2 rA_ = Mul(bodyA->xf.q, localAnchorA - bodyA->sweep.localCenter);
+    Vec2 rB_ = Mul(bodyB->xf.q, localAnchorB - bodyB->sweep.localCenter);
+    Vec2 p1 = bodyA->sweep.c + rA_;
+    Vec2 p2 = bodyB->sweep.c + rB_;
+    Vec2 d = p2 - p1;
+    Vec2 ax = Mul(bodyA->xf.q, localXAxisA);
+    Vec2 vA = bodyA->linearVelocity, vB = bodyB->linearVelocity;
+    float wA = bodyA->angularVelocity, wB = bodyB->angularVelocity;
+    return Dot(d, Cross(wA, ax)) + Dot(ax, vB + Cross(wB, rB_) - vA - Cross(wA, rA_));
+}
+
 void Joint::InitVelocityConstraints(const TimeStep& step) {
+    if (kind == kPrismaticJoint) return PrismaticInit(step);
     int indexA = bodyA->islandIndex, indexB = bodyB->islandIndex;
     localCenterA = bodyA->sweep.localCenter;
     localCenterB = bodyB->sweep.localCenter;
@@ -378,6 +662,7 @@ void Joint::InitVelocityConstraints(const TimeStep& step) {
 }
 
 void Joint::SolveVelocityConstraints(const TimeStep& step) {
+    if (kind == kPrismaticJoint) return PrismaticSolveVelocity(step);
     int indexA = bodyA->islandIndex, indexB = bodyB->islandIndex;
     Vec2 vA = g_velocities[indexA].v;
     float wA = g_velocities[indexA].w;
@@ -486,6 +771,7 @@ void Joint::SolveVelocityConstraints(const TimeStep& step) {
 
 bool Joint::SolvePositionConstraints() {
     if (kind == kFrictionJoint) return true;
+    if (kind == kPrismaticJoint) return PrismaticSolvePosition();
     int indexA = bodyA->islandIndex, indexB = bodyB->islandIndex;
     Vec2 cA = g_positions[indexA].c;
     float aA = g_positions[indexA].a;

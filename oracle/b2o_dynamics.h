@@ -96,7 +96,7 @@ struct TimeStep {
     bool warmStarting;
 };
 
-enum JointKind { kFrictionJoint = 0, kRevoluteJoint = 1 };
+enum JointKind { kFrictionJoint = 0, kRevoluteJoint = 1, kPrismaticJoint = 2 };
 enum LimitState { kInactiveLimit = 0, kAtLowerLimit = 1, kAtUpperLimit = 2, kEqualLimits = 3 };
 
 struct Joint {
@@ -125,6 +125,13 @@ struct Joint {
     Mat33 massMat;
     float motorMass = 0.0f;
     int limitState = kInactiveLimit;
+    // prismatic (b2PrismaticJoint 2.3.1; shares impulse / motorImpulse / enableMotor / motorSpeed / enableLimit /
+    // referenceAngle / limitState / massMat / motorMass with the revolute joint's fields)
+    Vec2 localXAxisA, localYAxisA;
+    float lowerTranslation = 0.0f, upperTranslation = 0.0f;
+    float maxMotorForce = 0.0f;
+    Vec2 axis, perp;
+    float s1 = 0.0f, s2 = 0.0f, a1 = 0.0f, a2 = 0.0f;
     // solver temp
     Vec2 rA, rB, localCenterA, localCenterB;
     float invMassA = 0.0f, invMassB = 0.0f, invIA = 0.0f, invIB = 0.0f;
@@ -139,6 +146,12 @@ struct Joint {
     void EnableMotor(bool flag) { bodyA->SetAwake(true); bodyB->SetAwake(true); enableMotor = flag; }
     void SetMaxMotorTorque(float t) { bodyA->SetAwake(true); bodyB->SetAwake(true); maxMotorTorque = t; }
     void SetMotorSpeed(float s) { bodyA->SetAwake(true); bodyB->SetAwake(true); motorSpeed = s; }
+    // prismatic API used by the wrapper (Box2DWorld.cpp:974-977, 1039-1042)
+    float GetJointTranslation() const;
+    float GetPrismaticJointSpeed() const;
+    void PrismaticInit(const TimeStep& step);
+    void PrismaticSolveVelocity(const TimeStep& step);
+    bool PrismaticSolvePosition();
 };
 
 struct Contact {
@@ -199,6 +212,8 @@ struct World {
     Joint* CreateFrictionJoint(Body* a, Body* b, const Vec2& anchorA, const Vec2& anchorB, float maxForce, float maxTorque);
     Joint* CreateRevoluteJoint(Body* a, Body* b, const Vec2& anchorA, const Vec2& anchorB, float refAngle,
                                float lower, float upper, bool enableLimit, bool enableMotor);
+    Joint* CreatePrismaticJoint(Body* a, Body* b, const Vec2& anchorA, const Vec2& anchorB, const Vec2& axisA, float refAngle,
+                                float lower, float upper, bool enableLimit, float maxMotorForce, bool enableMotor);
     void SetAllowSleeping(bool flag);
     void Step(float dt, int velocityIterations, int positionIterations);
     void ClearForces();

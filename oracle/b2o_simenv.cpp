@@ -173,6 +173,7 @@ void OLink::setEnabled(bool e) {  // :802-822
 void OJoint::resetPosition(float value, bool childJointOverride) {  // :992-1028
     float clamped = clampf(value, positionLimits[0], positionLimits[1]);
     if (std::abs(clamped - value) > 0.0001f) world->warnings.push_back("joint position out of limits: " + name);
+    if (prismatic()) return;  // :1021-1026: "TODO" -- the child link is left where it is
     float newAngle = joint->bodyA->GetAngle() + clamped + joint->referenceAngle;
     Vec2 axisWorld = joint->GetAnchorA();
     float pose[3];
@@ -183,6 +184,7 @@ void OJoint::resetPosition(float value, bool childJointOverride) {  // :992-1028
 }
 
 void OJoint::setControlTorque(float value) {  // :1198-1222  (the "motor hack")
+    if (prismatic()) throw std::logic_error("setControlTorque for prismatic joints is not implemented yet");  // :1204-1208
     float s = world->scale;
     joint->EnableMotor(true);
     joint->SetMaxMotorTorque(s * s * std::abs(value));
@@ -486,7 +488,9 @@ OObject* OWorld::createObject(const ObjectDesc& d) {  // Box2DObject ctor :1292-
     obj->baseLink->setOriginToCenterOfMass();
     unsigned baseDofs = obj->isStatic ? 0 : 3;
     for (const JointDesc& jd : d.joints) {  // Box2DJoint ctor :872-948
-        if (jd.joint_type != "revolute") throw std::runtime_error("oracle: only revolute joints are supported: " + jd.name);
+        // unknown types fall back to revolute with an error message (:893-898)
+        const bool prismatic = jd.joint_type == "prismatic";
+        if (!prismatic && jd.joint_type != "revolute") warnings.push_back("Unknown joint type " + jd.joint_type + ". Using revolute instead.");
         ownedJoints.emplace_back(new OJoint());
         OJoint* j = ownedJoints.back().get();
         j->name = jd.name;
@@ -497,8 +501,19 @@ OObject* OWorld::createObject(const ObjectDesc& d) {  // Box2DObject ctor :1292-
         Vec2 axis(scale * jd.axis[0], scale * jd.axis[1]);
         float norm = sqrtf(jd.position_limits[0] * jd.position_limits[0] + jd.position_limits[1] * jd.position_limits[1]);
         bool enableLimit = norm > 0.0;
-        j->joint = b2->CreateRevoluteJoint(j->linkA->body, j->linkB->body, axis, Vec2(0.0f, 0.0f), jd.axis_orientation,
-                                           jd.position_limits[0], jd.position_limits[1], enableLimit, jd.actuated);
+        if (prismatic) {
+            // :920-940 -- localAnchorA is NOT scaled there, the translation limits are; the axis direction is the unit vector
+            // at axis_orientation (libm cos / sin of a description constant); maxMotorForce = min |acceleration limits|
+            Vec2 anchorA(jd.axis[0], jd.axis[1]);
+            Vec2 direction(std::cos(jd.axis_orientation), std::sin(jd.axis_orientation));
+            float maxMotorForce = std::min(std::abs(jd.acceleration_limits[0]), std::abs(jd.acceleration_limits[1]));
+            j->joint = b2->CreatePrismaticJoint(j->linkA->body, j->linkB->body, anchorA, Vec2(0.0f, 0.0f), direction, jd.axis_orientation,
+                                                scale * jd.position_limits[0], scale * jd.position_limits[1], enableLimit, maxMotorForce,
+                                                jd.actuated);
+        } else {
+            j->joint = b2->CreateRevoluteJoint(j->linkA->body, j->linkB->body, axis, Vec2(0.0f, 0.0f), jd.axis_orientation,
+                                               jd.position_limits[0], jd.position_limits[1], enableLimit, jd.actuated);
+        }
         for (int k = 0; k < 2; ++k) {
             j->positionLimits[k] = jd.position_limits[k];
             j->velocityLimits[k] = jd.velocity_limits[k];

@@ -6,6 +6,7 @@
 // 191-215), effort application (:1198-1222, 2284-2379), stepping (:3266-3333) and the collision
 // checker (:2743-2911).
 #pragma once
+#include <stdexcept>
 #include <map>
 #include <memory>
 #include <string>
@@ -109,12 +110,18 @@ struct OJoint {
     unsigned jointIndex = 0, dofIndex = 0;
     float positionLimits[2], velocityLimits[2], accelerationLimits[2];
 
-    float getPosition() const { return joint->GetJointAngle(); }
-    float getVelocity() const { return joint->GetJointSpeed(); }
+    bool prismatic() const { return joint->kind == kPrismaticJoint; }
+    // Box2DJoint::getPosition / getVelocity (:965-981, :1030-1046): a prismatic joint reports b2PrismaticJoint's translation /
+    // speed as they are, i.e. in Box2D units (the reference does not scale them back)
+    float getPosition() const { return prismatic() ? joint->GetJointTranslation() : joint->GetJointAngle(); }
+    float getVelocity() const { return prismatic() ? joint->GetPrismaticJointSpeed() : joint->GetJointSpeed(); }
     void resetPosition(float value, bool childJointOverride);
     void setControlTorque(float value);
     void getAxisPosition(float axis[2]) const;
-    Vec2 getGlobalAxisPosition() const { return joint->GetAnchorA(); }
+    Vec2 getGlobalAxisPosition() const {  // :1274-1287
+        if (prismatic()) throw std::logic_error("getLocalAxisPosition for prismatic joints is not implemented yet");
+        return joint->GetAnchorA();
+    }
 };
 
 struct DofInfo {

@@ -153,3 +153,25 @@ def compare_world(batch_bodies, batch_contacts, w, oracle_world, atol=0.0):
                 if not np.all((np.abs(a - b) <= atol) | (a == b)):
                     diffs.append("contact %d floats: oracle %s cuda %s" % (k, a.tolist(), b.tolist()))
     return diffs
+
+
+def env_prismatic(actuated=False, static_cabinet=False, limits=(-0.1, 0.2)):
+    """Shape A's robot in front of a drawer: a cabinet link and a slider link joined by a PRISMATIC joint along the cabinet's
+    x axis (the reference constructs a b2PrismaticJoint for `joint_type: prismatic`, Box2DWorld.cpp:920-940, and can step and
+    read it but not place it: no `states` entry for the drawer, it is created at the origin).  The robot starts turned by
+    -90 degrees behind the slider, which sits in its palm, so that driving the base along +x pushes the slider along its
+    axis into the upper limit and then pushes the whole drawer.  (`axis` is the joint anchor on the cabinet in BOX2D units: the
+    reference does not scale it for prismatic joints, :923; 3.5 puts the slider 0.05 m inside its travel when the world is
+    created.  Every link of a static object is a static body, so the drawer is dynamic.)"""
+    env = load_env_dict(ENV_A)
+    env["objects"] = [dict(
+        name="drawer", static=bool(static_cabinet), base_actuation=None,
+        links=[dict(name="cabinet", geometry=[[0.3, -0.2, 0.5, -0.2, 0.5, 0.2, 0.3, 0.2]], mass=5.0, ground_friction=0.3,
+                    ground_torque_integral=0.2, contact_friction=0.8, restitution=0.2, balls=[]),
+               dict(name="slider", geometry=[[-0.05, -0.05, 0.2, -0.05, 0.2, 0.05, -0.05, 0.05]], mass=0.2, ground_friction=0.05,
+                    ground_torque_integral=0.01, contact_friction=0.8, restitution=0.1, balls=[])],
+        joints=[dict(name="rail", link_a="cabinet", link_b="slider", axis=[3.5, 0.0], axis_orientation=0.0,
+                     position_limits=[float(limits[0]), float(limits[1])], velocity_limits=[-5.0, 5.0],
+                     acceleration_limits=[-0.6, 0.8], joint_type="prismatic", actuated=bool(actuated))])]
+    env["states"] = {"my_robot": dict(configuration=[-0.5, 0.0, -1.5707964, 0.0, 0.0, 0.0, 0.0], velocity=[0.0] * 7)}
+    return env

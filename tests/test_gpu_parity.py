@@ -1022,3 +1022,53 @@ def test_multi_gpu_c_abi_rollout(b2g):
     sq2, _ = single.rollout(0, tg[:1], 5)
     assert np.array_equal(mq2, sq2)
     multi.close()
+
+
+@pytest.mark.parametrize("variant", [dict(), dict(actuated=True), dict(limits=(0.1, 0.2)), dict(limits=(0.05, 0.0501))])
+@pytest.mark.parametrize("lpw", [1, 4])
+def test_prismatic_joint_parity(b2g, variant, lpw, monkeypatch):
+    """Row 8f-4: b2PrismaticJoint (init / velocity / position constraints, lower / upper / equal limits, the motor of an
+    actuated joint as a brake) on both stepping kernels.  The robot, placed per world through its own DOF setters, rams a
+    drawer whose slider runs on a prismatic rail; bodies, joints (impulses, limit states) and contacts bit-identical to the
+    oracle after every 10-step segment; getWorldState reports the rail's translation and speed in Box2D units like the
+    reference.  Setters on the drawer are refused (the reference throws there)."""
+    from parity_utils import env_prismatic
+    if lpw > 1:
+        monkeypatch.setenv("B2G_LPW", str(lpw))
+    n = 48
+    env = env_prismatic(**variant)
+    batch = b2g.BatchBox2DWorld(n).loadWorld(b2g.Model(env))
+    worlds = oracle_worlds(env, n)
+    assert_same(batch, worlds, "fresh prismatic world")
+    rng = np.random.default_rng(71)
+    rq = np.zeros((n, 7), np.float32)
+    rq[:, 0] = -0.5 + rng.uniform(-0.05, 0.05, n)
+    rq[:, 1] = rng.uniform(-0.08, 0.08, n)
+    rq[:, 2] = -1.5707964 + rng.uniform(-0.2, 0.2, n)
+    rq[:, 3:] = rng.uniform(-0.5, 0.5, (n, 4))
+    batch.setDOFPositions("my_robot", rq)
+    for w, ow in enumerate(worlds):
+        ow.set_object_dofs(0, rq[w])
+    tg = random_targets(batch.model, 0, n, seed=72, segments=12)
+    tg[:, :, 0] = np.abs(tg[:, :, 0])      # towards the drawer
+    states = set()
+    for seg in range(12):
+        batch.setTargetVelocity(0, tg[seg])
+        batch.stepPhysics(10)
+        for w, ow in enumerate(worlds):
+            ow.set_target_velocity(0, tg[seg][w])
+            ow.step(10)
+        assert_same(batch, worlds, "prismatic segment %d" % seg)
+        gq, gqd = batch.getWorldState()
+        oq = np.stack([ow.get_state()[0] for ow in worlds])
+        oqd = np.stack([ow.get_state()[1] for ow in worlds])
+        assert np.array_equal(gq, oq) and np.array_equal(gqd, oqd)
+        states |= set(int(x) for x in batch.joints()[0][:, -1, 3])
+    assert int(batch.contacts()[1][..., 2].sum()) > 0 or len(states) > 1
+    if "limits" in variant:
+        assert states & {1, 2, 3}, "no limit state was exercised: %s" % states
+    q, qd = batch.getWorldState()
+    for call in (lambda: batch.setWorldState(q, qd), lambda: batch.setDOFPositions("drawer", q[:, 7:]), lambda: batch.setToRest()):
+        with pytest.raises(b2g.B2GError) as e:
+            call()
+        assert e.value.code == 4

@@ -124,12 +124,36 @@ def test_yaml_errors_are_loud(b2g, tmp_path):
         b2g.Model(str(bad))
 
 
-def test_prismatic_is_rejected(b2g):
+def test_prismatic_joints_follow_the_reference(b2g, oracle):
+    """joint_type: prismatic builds a b2PrismaticJoint for an object (Box2DWorld.cpp:920-940: anchor not scaled, limits scaled,
+    maxMotorForce = min |acceleration limits|), with the model records the oracle builds; what the reference cannot do is
+    refused when the model is built: a robot with a prismatic joint (setControlTorque throws, :1204-1208) and a `states` entry
+    for an object that has one (updateBodyVelocities -> getGlobalAxisPosition throws, :789, :1282-1285)."""
+    from parity_utils import env_prismatic
+    env = env_prismatic(actuated=True)
+    m = b2g.Model(env)
+    w = oracle.OracleWorld(oracle.OracleEnv(env))
+    assert (m.n_bodies, m.n_joints, m.nq) == (w.n_bodies, w.n_joints, w.nq) == (8, 12, 11)
+    ji, jf = m.joint_model()
+    oji, ojf = w.joints()
+    assert ji[-1][0] == 2 and np.array_equal(ji[:, [0, 1, 2, 4, 5]], oji[:, [0, 1, 2, 4, 5]])
+    assert np.array_equal(jf[:, 8:], ojf[:, 8:])       # anchors (3.5, 0) unscaled, reference angle, translation limits -1 .. 2
+    assert list(jf[-1][8:10]) == [3.5, 0.0] and list(jf[-1][13:15]) == [-1.0, 2.0]
     env = load_env_dict(ENV_A)
     env["robots"][0]["joints"][0]["joint_type"] = "prismatic"
     with pytest.raises(b2g.B2GError) as e:
         b2g.Model(env)
+    assert e.value.code == 4 and "setControlTorque" in str(e.value)
+    env = env_prismatic()
+    env["states"]["drawer"] = dict(configuration=[1.0, 1.0, 0.0, 0.0], velocity=[0.0] * 4)
+    with pytest.raises(b2g.B2GError) as e:
+        b2g.Model(env)
     assert e.value.code == 4
+    # an unknown joint type is reported and treated as revolute (:893-898)
+    env = load_env_dict(ENV_A)
+    env["robots"][0]["joints"][1]["joint_type"] = "helical"
+    m = b2g.Model(env)
+    assert any("Unknown joint type helical" in x for x in m.warnings())
 
 
 def test_maximum_model_sizes(b2g):

@@ -780,3 +780,62 @@ def test_recorded_contacts_known_answers(oracle):
     assert np.allclose(fo[0, 3:], [0.1, 0.0, 0.0], atol=1e-7)
     io, fo = w.step_record(20)
     assert len(io) == 0
+
+
+# ---- b2PrismaticJoint (row 8f-4): known answers from the constraint definitions --------------------------------------------------
+def _rail(world):
+    """(translation, lateral offset, relative angle, limit state, motor impulse) of the drawer's prismatic joint from body states."""
+    b = world.bodies()
+    cab, sl = b[-2], b[-1]
+    ji, jf = world.joints()
+    ax = np.array([cab[3], cab[2]])                 # cabinet x axis in the world (cos, sin)
+    perp = np.array([-cab[2], cab[3]])
+    anchor = cab[0:2] + 3.5 * ax                    # localAnchorA = (3.5, 0) on the cabinet, Box2D units
+    d = sl[0:2] - anchor                            # localAnchorB = (0, 0) on the slider
+    return float(d @ ax), float(d @ perp), float(sl[6] - cab[6]), int(ji[-1][3]), float(jf[-1][3])
+
+
+def test_prismatic_joint_known_answers(oracle):
+    from parity_utils import env_prismatic
+    slop, ang_slop = 0.005, 2.0 / 180.0 * np.pi
+    # (a) free rail: the joint removes the lateral and the angular degree of freedom while the robot rams the drawer
+    w = oracle.OracleWorld(oracle.OracleEnv(env_prismatic()))
+    assert abs(w.get_state()[0][-1] - 0.5) < 1e-6       # created 0.5 units inside the travel; getPosition is in Box2D units
+    w.set_target_velocity(0, np.array([1.0, 0, 0, 0, 0, 0, 0], np.float32))
+    moved = 0.0
+    for _ in range(12):
+        w.step(10)
+        t, lat, ang, state, _ = _rail(w)
+        assert abs(lat) <= 3 * slop and abs(ang) <= 2 * ang_slop, (lat, ang)
+        assert -1.0 - 2 * slop <= t <= 2.0 + 2 * slop   # limits [-0.1, 0.2] m are scaled by 10
+        assert abs(t - w.get_state()[0][-1]) < 1e-4
+        moved = max(moved, abs(t - 0.5))
+    assert moved > 0.2, "the robot never moved the slider"
+    # (b) created below its lower limit: the position solver pushes the slider to lower - linearSlop and holds it there
+    w = oracle.OracleWorld(oracle.OracleEnv(env_prismatic(limits=(0.1, 0.2))))
+    w.step(10)
+    t, lat, ang, state, _ = _rail(w)
+    assert state == 1 and abs(t - (1.0 - slop)) < 1e-3, (t, state)
+    # (c) equal limits: b2PrismaticJoint pins the TRANSLATION to zero (C = translation), not to the limit value
+    w = oracle.OracleWorld(oracle.OracleEnv(env_prismatic(limits=(0.05, 0.0501))))
+    w.step(30)
+    t, lat, ang, state, _ = _rail(w)
+    assert state == 3 and abs(t) < 2 * slop, (t, state)
+    # (d) actuated: enableMotor with motorSpeed 0 and maxMotorForce = min |acceleration limits| = 0.6 -> a brake whose impulse
+    # saturates at dt * maxMotorForce while the slider is being pushed
+    w = oracle.OracleWorld(oracle.OracleEnv(env_prismatic(actuated=True)))
+    w.set_target_velocity(0, np.array([1.0, 0, 0, 0, 0, 0, 0], np.float32))
+    peak = 0.0
+    for _ in range(90):
+        w.step(1)
+        peak = max(peak, abs(_rail(w)[4]))
+    assert abs(peak - 0.01 * 0.6) < 1e-6, peak
+    # (e) what the reference cannot do, it refuses: placing the drawer, a `states` entry for it, a robot with a prismatic joint
+    w = oracle.OracleWorld(oracle.OracleEnv(env_prismatic()))
+    q, qd = w.get_state()
+    with pytest.raises(Exception):
+        w.set_state(q, qd)
+    bad = env_prismatic()
+    bad["states"]["drawer"] = dict(configuration=[1.0, 1.0, 0.0, 0.0], velocity=[0.0] * 4)
+    with pytest.raises(Exception):
+        oracle.OracleWorld(oracle.OracleEnv(bad))
