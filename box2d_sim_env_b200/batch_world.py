@@ -63,6 +63,7 @@ ABI_SYMBOLS = [
     "b2g_batch_get_link_property", "b2g_batch_objects_in_aabb",
     "b2g_batch_is_physically_feasible",
     "b2g_batch_set_target_velocity", "b2g_batch_set_target_velocity_dev", "b2g_batch_set_control_efforts",
+    "b2g_batch_set_target_position", "b2g_batch_set_target_position_dev",
     "b2g_batch_set_control_efforts_dev", "b2g_batch_step", "b2g_batch_step_record",
     "b2g_batch_step_guarded", "b2g_batch_rollout_dev", "b2g_batch_rollout",
     "b2g_batch_get_link_states", "b2g_batch_get_bodies", "b2g_batch_get_fat_aabbs", "b2g_batch_get_joints", "b2g_batch_get_contacts",
@@ -150,6 +151,8 @@ def lib():
     L.b2g_batch_set_target_velocity_dev.argtypes = [vp, C.c_int, fp]
     L.b2g_batch_set_control_efforts.argtypes = [vp, C.c_int, fp]
     L.b2g_batch_set_control_efforts_dev.argtypes = [vp, C.c_int, fp]
+    L.b2g_batch_set_target_position.argtypes = [vp, C.c_int, fp, C.c_float]
+    L.b2g_batch_set_target_position_dev.argtypes = [vp, C.c_int, fp, C.c_float]
     L.b2g_batch_step.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.b2g_batch_rollout_dev.argtypes = [vp, C.c_int, fp, C.c_int, C.c_int]
     L.b2g_batch_rollout.argtypes = [vp, C.c_int, fp, fp, C.c_int, fp, C.c_int, C.c_int, fp, fp]
@@ -616,6 +619,14 @@ class BatchBox2DWorld:
             raise B2GError(1, "[sim_env::Box2DRobotVelocityController::setTargetVelocity]"
                               "Provided target velocity has invalid dimension.")
         _check(lib().b2g_batch_set_target_velocity(self.h, robot, _ptr(v)))
+
+    def setTargetPosition(self, robot, position, kp=5.0):
+        """Position controller on top of the velocity controller (b2g_batch_set_target_position: v_target = kp * (q_target - q)
+        every control step, heading error wrapped; the reference's sim_env::RobotPositionController is not in the tree)."""
+        robot = self.model.object_index(robot) if isinstance(robot, str) else robot
+        nd = self.model.objects[robot]["n_dofs"]
+        q = _f32(np.broadcast_to(_f32(position), (self._rows(), nd)))
+        _check(lib().b2g_batch_set_target_position(self.h, robot, _ptr(q), C.c_float(kp)))
 
     def setControlEfforts(self, robot, efforts):
         """Box2DRobot::setController (:2312-2317) with a callback that returns `efforts` ([n_worlds, n_dofs]) on every step:

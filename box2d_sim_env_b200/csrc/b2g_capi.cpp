@@ -579,11 +579,32 @@ b2g_status b2g_batch_status(b2g_batch* b, int32_t* out) {
     return B2G_OK;
 }
 
+// reset_caches: every selected world becomes what Box2DWorld::clone() gives (Box2DWorld.cpp:3026-3037: a freshly loaded world
+// that then receives the world state) -- contact list, warm-start impulses, sleep timers, broad-phase move buffer, link
+// enable flags and controller targets as loaded -- EXCEPT the poses of static objects, which are part of the world state the
+// clone receives (and which b2g_batch_clone carries over the same way): they are read before the template is broadcast and set
+// again afterwards, as setPose calls on the fresh world.
+static b2g_status resetToFreshClones(b2g_batch* b) {
+    int nStatic = 0;
+    for (const auto& o : b->m.objects) nStatic += o.isStatic ? 1 : 0;
+    const size_t per = (size_t)b->n() * 3 * 4;
+    if (nStatic) CU(b->stageE.reserve(per * nStatic));
+    int k = 0;
+    for (int o = 0; o < b->m.h.no; ++o)
+        if (b->m.objects[o].isStatic) CU(launchGetPose(b->L(), o, (float*)((char*)b->stageE.p + per * k++)));
+    CU(launchBroadcast(b->L(), b->tmpl));
+    k = 0;
+    for (int o = 0; o < b->m.h.no; ++o)
+        if (b->m.objects[o].isStatic) CU(launchSetPose(b->L(), o, (const float*)((char*)b->stageE.p + per * k++)));
+    return B2G_OK;
+}
+
 b2g_status b2g_batch_set_state_dev(b2g_batch* b, const float* q, const float* qd, int reset_caches) {
     if (!b || !q || !qd) return fail(B2G_ERR_INVALID, "null argument");
     if (b2g_status st = refusePrismatic(b, -1)) return st;
     ON_DEVICE(b->device);
-    if (reset_caches) CU(launchBroadcast(b->L(), b->tmpl));
+    if (reset_caches)
+        if (b2g_status st = resetToFreshClones(b)) return st;
     CU(launchSetState(b->L(), q, qd));
     return B2G_OK;
 }
@@ -728,6 +749,28 @@ b2g_status b2g_batch_set_target_velocity(b2g_batch* b, int object, const float* 
     return B2G_OK;
 }
 
+b2g_status b2g_batch_set_target_position_dev(b2g_batch* b, int object, const float* q_target, float kp) {
+    b2g_status s = checkRobot(b, object);
+    if (s) return s;
+    if (!q_target || !(kp >= 0.0f)) return fail(B2G_ERR_INVALID, "bad position target");
+    ON_DEVICE(b->device);
+    CU(launchSetTargetPosition(b->L(), object, q_target, kp));
+    return B2G_OK;
+}
+
+b2g_status b2g_batch_set_target_position(b2g_batch* b, int object, const float* q_target, float kp) {
+    b2g_status s = checkRobot(b, object);
+    if (s) return s;
+    if (!q_target || !(kp >= 0.0f)) return fail(B2G_ERR_INVALID, "bad position target");
+    ON_DEVICE(b->device);
+    size_t bytes = (size_t)b->n() * b->m.objects[object].nDofs * 4;
+    CU(b->stageA.reserve(bytes));
+    CU(cudaMemcpyAsync(b->stageA.p, q_target, bytes, cudaMemcpyHostToDevice, b->stream));
+    CU(launchSetTargetPosition(b->L(), object, (const float*)b->stageA.p, kp));
+    CU(cudaStreamSynchronize(b->stream));
+    return B2G_OK;
+}
+
 b2g_status b2g_batch_set_control_efforts_dev(b2g_batch* b, int object, const float* efforts) {
     b2g_status s = checkRobot(b, object);
     if (s) return s;
@@ -811,7 +854,8 @@ b2g_status b2g_batch_rollout(b2g_batch* b, int object, const float* q, const flo
     if (q) {
         CU(cudaMemcpyAsync(b->stageA.p, q, sb, cudaMemcpyHostToDevice, b->stream));
         CU(cudaMemcpyAsync(b->stageB.p, qd, sb, cudaMemcpyHostToDevice, b->stream));
-        if (reset_caches) CU(launchBroadcast(b->L(), b->tmpl));
+        if (reset_caches)
+            if (b2g_status st = resetToFreshClones(b)) return st;
         CU(launchSetState(b->L(), (const float*)b->stageA.p, (const float*)b->stageB.p));
     }
     if (n_targets > 0) {

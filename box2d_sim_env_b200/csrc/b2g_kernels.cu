@@ -159,19 +159,27 @@ __global__ void k_get_pose(const __grid_constant__ ModelHeader hdr, const uint32
 // missing sim_env package; assumed: one uniform factor that brings every component inside its velocity limits.
 DEV void setTarget(const Ctx& c, int object, const float* v) {
     int n = mI(c, mobj(c, object, MO_NDOFS));
-    int off = mI(c, mobj(c, object, MO_DOF_OFFSET));
     int tOff = mI(c, mobj(c, object, MO_TARGET_OFFSET));
-    float factor = 1.0f;
-    for (int i = 0; i < n; ++i) {
-        float lo = dofLimit(c, off + i, 2), hi = dofLimit(c, off + i, 3);
-        if (v[i] > hi && v[i] > 0.0f) factor = fminf(factor, hi / v[i]);
-        if (v[i] < lo && v[i] < 0.0f) factor = fminf(factor, lo / v[i]);
-    }
+    const float factor = scaleToLimits(c, object, v);
     for (int i = 0; i < n; ++i) stF(c, tslot(c, tOff + i), factor < 1.0f ? factor * v[i] : v[i]);
     int slot = 0;
     for (int r = 0; r < H().nrobots; ++r)
         if (mI(c, H().oRobotOrder + r) == object) slot = r;
-    stI(c, sslot(c, SS_TARGET_AVAIL), (ldI(c, sslot(c, SS_TARGET_AVAIL)) | (1 << slot)) & ~(1 << (16 + slot)));
+    stI(c, sslot(c, SS_TARGET_AVAIL), (ldI(c, sslot(c, SS_TARGET_AVAIL)) | (1 << slot)) & ~((1 << (16 + slot)) | (1 << (8 + slot))));
+}
+
+// Position controller on top of the velocity controller (sim_env::RobotPositionController / SE2RobotPositionController,
+// instantiated at Box2DWorldViewer.cpp:1208-1216; the classes belong to the absent sim_env package -- assumed law, see
+// robotControl): stores the target positions and the gain and switches the robot's controller to position mode (bit 8 + slot).
+DEV void setTargetPosition(const Ctx& c, int object, const float* q, float kp) {
+    int n = mI(c, mobj(c, object, MO_NDOFS));
+    int tOff = mI(c, mobj(c, object, MO_TARGET_OFFSET));
+    for (int i = 0; i < n; ++i) stF(c, tslot(c, tOff + i), q[i]);
+    stF(c, tslot(c, tOff + n), kp);
+    int slot = 0;
+    for (int r = 0; r < H().nrobots; ++r)
+        if (mI(c, H().oRobotOrder + r) == object) slot = r;
+    stI(c, sslot(c, SS_TARGET_AVAIL), (ldI(c, sslot(c, SS_TARGET_AVAIL)) | (1 << slot) | (1 << (8 + slot))) & ~(1 << (16 + slot)));
 }
 
 // Box2DRobot::setController (:2312-2317) with a callback that returns the given efforts on every control(dt) call
@@ -183,7 +191,7 @@ DEV void setEfforts(const Ctx& c, int object, const float* e) {
     int slot = 0;
     for (int r = 0; r < H().nrobots; ++r)
         if (mI(c, H().oRobotOrder + r) == object) slot = r;
-    stI(c, sslot(c, SS_TARGET_AVAIL), ldI(c, sslot(c, SS_TARGET_AVAIL)) | (1 << slot) | (1 << (16 + slot)));
+    stI(c, sslot(c, SS_TARGET_AVAIL), (ldI(c, sslot(c, SS_TARGET_AVAIL)) | (1 << slot) | (1 << (16 + slot))) & ~(1 << (8 + slot)));
 }
 
 __global__ void k_set_target(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
@@ -193,6 +201,15 @@ __global__ void k_set_target(const __grid_constant__ ModelHeader hdr, const uint
     float lv[kMaxDofsPerObject];
     for (int i = 0; i < n; ++i) lv[i] = v[w * n + i];
     setTarget(c, object, lv);
+}
+
+__global__ void k_set_target_position(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
+                                      StepParams prm, int object, const float* __restrict__ q, float kp) {
+    B2G_PROLOGUE();
+    int n = mI(c, mobj(c, object, MO_NDOFS));
+    float lq[kMaxDofsPerObject];
+    for (int i = 0; i < n; ++i) lq[i] = q[w * n + i];
+    setTargetPosition(c, object, lq, kp);
 }
 
 __global__ void k_set_efforts(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
@@ -614,6 +631,7 @@ cudaError_t launchGetObjectDofs(const Launch& L, int object, const DofSel& sel, 
 }
 cudaError_t launchSetEfforts(const Launch& L, int object, const float* v) { LAUNCH(k_set_efforts, object, v); }
 cudaError_t launchSetTarget(const Launch& L, int object, const float* v) { LAUNCH(k_set_target, object, v); }
+cudaError_t launchSetTargetPosition(const Launch& L, int object, const float* q, float kp) { LAUNCH(k_set_target_position, object, q, kp); }
 cudaError_t launchStep(const Launch& L, int object, const float* targets, int nTargets, int stepsPerTarget, int execCtrl,
                        int allowSleep) {
     if (L.stepLpw > 1) {  // small / medium batch: LPW lanes per world, stepLanes worlds per warp, one warp per CTA

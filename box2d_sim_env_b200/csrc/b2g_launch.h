@@ -38,6 +38,7 @@ cudaError_t launchSetObjectDofs(const Launch& L, int object, const DofSel& sel, 
 cudaError_t launchGetObjectDofs(const Launch& L, int object, const DofSel& sel, float* out, int velocities);
 cudaError_t launchSetEfforts(const Launch& L, int object, const float* v);
 cudaError_t launchSetTarget(const Launch& L, int object, const float* v);
+cudaError_t launchSetTargetPosition(const Launch& L, int object, const float* q, float kp);
 cudaError_t launchStep(const Launch& L, int object, const float* targets, int nTargets, int stepsPerTarget, int execCtrl,
                        int allowSleep);
 cudaError_t launchSetToRest(const Launch& L);

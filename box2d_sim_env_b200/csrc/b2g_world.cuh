@@ -348,6 +348,20 @@ DEVN void initWorld(Ctx c) {
     }
 }
 
+// Box2DRobotVelocityController::setTargetVelocity's scaleToLimits (Box2DController.cpp:42-63).  scaleToLimits belongs to the
+// missing sim_env package; assumed: one uniform factor that brings every component inside its velocity limits.
+DEV float scaleToLimits(Ctx c, int object, const float* v) {
+    int n = mI(c, mobj(c, object, MO_NDOFS));
+    int off = mI(c, mobj(c, object, MO_DOF_OFFSET));
+    float factor = 1.0f;
+    for (int i = 0; i < n; ++i) {
+        float lo = dofLimit(c, off + i, 2), hi = dofLimit(c, off + i, 3);
+        if (v[i] > hi && v[i] > 0.0f) factor = fminf(factor, hi / v[i]);
+        if (v[i] < lo && v[i] < 0.0f) factor = fminf(factor, lo / v[i]);
+    }
+    return factor;
+}
+
 // ---- controller ------------------------------------------------------------------------------------------------
 // Box2DRobot::control (:2284-2310) = Box2DRobotVelocityController::control (Box2DController.cpp:65-117)
 // followed by Box2DRobot::commandEfforts (:2319-2379) and Box2DJoint::setControlTorque (:1198-1222).
@@ -361,7 +375,25 @@ DEVN void robotControl(Ctx c, int o, int robotSlot) {
     int baseDofs = isStatic ? 0 : 3;
     int dofOffset = mI(c, mobj(c, o, MO_DOF_OFFSET));
     int tOff = mI(c, mobj(c, o, MO_TARGET_OFFSET));
-    float vel[kMaxDofsPerObject], effort[kMaxDofsPerObject];
+    float vel[kMaxDofsPerObject], effort[kMaxDofsPerObject], target[kMaxDofsPerObject];
+    // bit 8 + slot: position controller (b2g_batch_set_target_position).  ASSUMED law (the reference's position controllers are
+    // sim_env classes that are not in the tree): every control step v_target = kp * (q_target - q), the heading error of a
+    // moving base wrapped to (-pi, pi], handed to setTargetVelocity (scaleToLimits included), then the velocity controller.
+    if (((avail >> (8 + robotSlot)) & 1) != 0) {
+        float q[kMaxDofsPerObject];
+        getDofPositions(c, o, q);
+        const float kp = ldF(c, tslot(c, tOff + n));
+        for (int i = 0; i < n; ++i) {
+            float err = ldF(c, tslot(c, tOff + i)) - q[i];
+            if (!isStatic && i == 2) err = err - 6.2831855f * rintf(err * 0.15915494f);
+            target[i] = kp * err;
+        }
+        const float factor = scaleToLimits(c, o, target);
+        if (factor < 1.0f)
+            for (int i = 0; i < n; ++i) target[i] = factor * target[i];
+    } else {
+        for (int i = 0; i < n; ++i) target[i] = ldF(c, tslot(c, tOff + i));
+    }
     getDofVelocities(c, o, vel);
     float inv = H().invScale, s = H().scale;
     int baseBody = mI(c, mobj(c, o, MO_BASE_BODY));
@@ -413,7 +445,7 @@ DEVN void robotControl(Ctx c, int o, int robotSlot) {
             float linkInertia = inv * inv * bodyInertia;  // Box2DLink::getInertia (:549-555)
             massInertia = 0.0f + (linkInertia + m * distance * distance);
         }
-        float accel = (ldF(c, tslot(c, tOff + i)) - vel[i]) / PRM().dt;
+        float accel = (target[i] - vel[i]) / PRM().dt;
         accel = fminf(dofLimit(c, dofOffset + i, 5), fmaxf(accel, dofLimit(c, dofOffset + i, 4)));
         effort[i] = massInertia * accel;
     }

@@ -604,12 +604,13 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
     for (int oi = 0; oi < no; ++oi)
         if (objects[oi].d->is_robot) {
             targetOffset[oi] = ntarget;
-            ntarget += objects[oi].nDofs;
+            ntarget += objects[oi].nDofs + 1;  // the controller targets of the robot's DOFs + the position controller's gain
         }
 
     // ---- flatten
     ModelHeader& h = out.h;
     memset(&h, 0, sizeof(h));
+    if (robotOrder.size() > 8) throw std::runtime_error("too many robots (max 8: controller mode bits per world)");
     h.nb = nb; h.nf = nf; h.nj = nj; h.no = no; h.nrobots = (int)robotOrder.size(); h.nq = nq; h.ntarget = ntarget;
     h.scale = scale;
     h.invScale = 1.0f / scale;

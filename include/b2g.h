@@ -171,9 +171,10 @@ b2g_status b2g_batch_sync(b2g_batch* batch);
 
 /* setWorldState (Box2DWorld.cpp:3492-3513 -> Box2DObject::setState :1980-1989): per object
  * setTransform(pose) [pose = first three DOFs; static objects keep their pose], setDOFPositions(all),
- * setDOFVelocities(all).  reset_caches != 0 first returns every world to the freshly loaded state
- * (what clone(), :3026-3038, gives a planner: no contacts, zero warm-start impulses, inv_dt0 = 0).
- * q, qd: [n_worlds][nq]. */
+ * setDOFVelocities(all).  reset_caches != 0 first turns every world into what clone() (:3026-3038) gives a planner: a
+ * freshly loaded world -- no contacts, zero warm-start impulses, inv_dt0 = 0, sleep timers, link enable flags and controller
+ * targets as loaded -- that keeps the poses of its static objects (b2g_batch_set_object_pose), which belong to the world
+ * state a clone receives.  q, qd: [n_worlds][nq]. */
 b2g_status b2g_batch_set_state(b2g_batch* batch, const float* q, const float* qd, int reset_caches);
 b2g_status b2g_batch_set_state_dev(b2g_batch* batch, const float* q, const float* qd, int reset_caches);
 /* getWorldState (:3462-3474): dof_positions / dof_velocities of every object */
@@ -243,6 +244,14 @@ b2g_status b2g_model_get_link_property(const b2g_model* model, int body, int pro
  * in-kernel before every step (Box2DRobot::control, Box2DWorld.cpp:2284-2310). */
 b2g_status b2g_batch_set_target_velocity(b2g_batch* batch, int object, const float* v);
 b2g_status b2g_batch_set_target_velocity_dev(b2g_batch* batch, int object, const float* v);
+/* Position control: sim_env::RobotPositionController / SE2RobotPositionController on top of the velocity controller
+ * (instantiated at Box2DWorldViewer.cpp:1208-1216).  The classes belong to the sim_env package, which is not in the tree, so the
+ * law is an ASSUMPTION stated here: at every control step v_target = kp * (q_target - q) over all DOFs of the robot (the heading
+ * error of a moving base wrapped to (-pi, pi]), passed through setTargetVelocity (scaleToLimits included) to the velocity
+ * controller.  q_target: [n_worlds][n_dofs of the robot]; kp in 1/s.  A later b2g_batch_set_target_velocity or
+ * b2g_batch_set_control_efforts switches the robot back. */
+b2g_status b2g_batch_set_target_position(b2g_batch* batch, int object, const float* q_target, float kp);
+b2g_status b2g_batch_set_target_position_dev(b2g_batch* batch, int object, const float* q_target, float kp);
 /* Box2DRobot::setController (Box2DWorld.cpp:2312-2317) with a ControlCallback that returns these efforts on every
  * control(dt) call (:2284-2310): each step they go to Box2DRobot::commandEfforts (:2319-2379) -- force on the base
  * centre (x scale), torque (x scale^2), joint motors through Box2DJoint::setControlTorque (:1198-1222).  This is the

@@ -337,6 +337,12 @@ public:
         check(b2g_batch_set_target_velocity(_batch, objectIndex(robot), v));
     }
 
+    // sim_env::RobotPositionController / SE2RobotPositionController on top of the velocity controller (instantiated by the
+    // reference's viewer, Box2DWorldViewer.cpp:1208-1216; assumed law, include/b2g.h): q_target: [n_worlds][n_dofs of the robot]
+    void setTargetPosition(const std::string& robot, const float* q_target, float kp = 5.0f) {
+        check(b2g_batch_set_target_position(_batch, objectIndex(robot), q_target, kp));
+    }
+
     // Box2DRobot::setController (:2312-2317) with a ControlCallback that returns these efforts on every step (they reach
     // Box2DRobot::commandEfforts :2319-2379): the hook for user control laws; efforts: [n_worlds][n_dofs of the robot]
     void setControlEfforts(const std::string& robot, const float* efforts) {

@@ -73,6 +73,7 @@ def lib():
         L.b2o_world_get_object_pose.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.b2o_world_set_control_efforts.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.b2o_world_set_target_velocity.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.b2o_world_set_target_position.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float]
         L.b2o_world_object_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_char_p, C.c_int]
         for name in ("b2o_world_get_bodies", "b2o_world_get_body_model", "b2o_world_get_fat_aabbs"):
             getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
@@ -313,6 +314,11 @@ class OracleWorld:
     def set_target_velocity(self, obj, v):
         v = _f32(v)
         if lib().b2o_world_set_target_velocity(self.h, obj, _ptr(v), len(v)):
+            raise RuntimeError(lib().b2o_last_error().decode())
+
+    def set_target_position(self, obj, q, kp):
+        q = _f32(q)
+        if lib().b2o_world_set_target_position(self.h, obj, _ptr(q), len(q), C.c_float(kp)):
             raise RuntimeError(lib().b2o_last_error().decode())
 
     def set_control_efforts(self, obj, efforts):

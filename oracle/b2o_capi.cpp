@@ -215,7 +215,22 @@ int b2o_world_set_target_velocity(void* wp, int objIdx, const float* v, int n) {
     OWorld* w = (OWorld*)wp;
     try {
         w->creationOrder.at(objIdx)->effortController = false;
+        w->creationOrder.at(objIdx)->positionController = false;
         w->creationOrder.at(objIdx)->setTargetVelocity(std::vector<float>(v, v + n));
+        return 0;
+    } catch (const std::exception& ex) { g_err = ex.what(); return 1; }
+}
+
+// position controller (assumed law, b2o_simenv.h): target positions for all DOFs of robot objIdx and the gain
+int b2o_world_set_target_position(void* wp, int objIdx, const float* q, int n, float kp) {
+    OWorld* w = (OWorld*)wp;
+    try {
+        OObject* o = w->creationOrder.at(objIdx);
+        if (!o->isRobot || (size_t)n != o->activeDofs.size()) throw std::runtime_error("bad position target");
+        o->effortController = false;
+        o->positionController = true;
+        o->targetPosition.assign(q, q + n);
+        o->positionGain = kp;
         return 0;
     } catch (const std::exception& ex) { g_err = ex.what(); return 1; }
 }

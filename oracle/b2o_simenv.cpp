@@ -396,6 +396,16 @@ void OObject::control(float dt) {  // Box2DWorld.cpp:2284-2310
         commandEfforts(controlEfforts);
         return;
     }
+    if (positionController) {
+        std::vector<float> q = getDOFPositions({});
+        std::vector<float> v(q.size());
+        for (size_t i = 0; i < q.size(); ++i) {
+            float err = targetPosition[i] - q[i];
+            if (!isStatic && activeDofs[i] == 2) err = err - 6.2831855f * rintf(err * 0.15915494f);
+            v[i] = positionGain * err;
+        }
+        setTargetVelocity(v);
+    }
     std::vector<float> velocities = getDOFVelocities({});
     std::vector<float> efforts;
     if (controllerCompute(velocities, dt, efforts)) commandEfforts(efforts);

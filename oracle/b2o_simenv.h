@@ -149,6 +149,13 @@ struct OObject {
     // commandEfforts every step
     bool effortController = false;
     std::vector<float> controlEfforts;
+    // position controller on top of the velocity controller (sim_env::RobotPositionController / SE2RobotPositionController,
+    // instantiated at Box2DWorldViewer.cpp:1208-1216; the classes live in the absent sim_env package).  ASSUMED law, the same
+    // on the CUDA side: every control step v_target = kp * (q_target - q), the heading error of a moving base wrapped to
+    // (-pi, pi], then setTargetVelocity (incl. its scaleToLimits) and the velocity controller.
+    bool positionController = false;
+    std::vector<float> targetPosition;
+    float positionGain = 0.0f;
 
     unsigned numBaseDofs() const { return isStatic ? 0 : 3; }
     std::vector<int> allDofs() const;

@@ -1072,3 +1072,86 @@ def test_prismatic_joint_parity(b2g, variant, lpw, monkeypatch):
         with pytest.raises(b2g.B2GError) as e:
             call()
         assert e.value.code == 4
+
+
+@pytest.mark.parametrize("env_name", [ENV_A, ENV_B])
+def test_position_controller_parity_and_convergence(b2g, env_name):
+    """Row 8f-4, second half: the position controller on top of the velocity controller (SE2 controller for the rigid robot of
+    shape B, all-DOF controller for shape A; Box2DWorldViewer.cpp:1208-1216 instantiates sim_env's classes, whose law is assumed:
+    v_target = kp * (q_target - q) with the heading error wrapped).  Bit-identical to the oracle's implementation of the same
+    law; first-principles check: worlds whose way is free reach their targets, the heading through the short way round."""
+    n = 96
+    batch = make_batch(b2g, env_name, n)
+    worlds = oracle_worlds(env_dict(env_name), n)
+    nd = batch.model.objects[0]["n_dofs"]
+    rng = np.random.default_rng(81)
+    q, qd = batch.getWorldState()
+    q[:, nd] = 5.0 + rng.uniform(-0.5, 0.5, n)       # obj1 out of the way in most worlds ...
+    q[: n // 4, nd:nd + 2] = [0.0, 0.45]              # ... in the robot's path in a quarter of them
+    q[:, 2] = rng.uniform(-3.0, 3.0, n)
+    batch.setWorldState(q, qd, reset_caches=True)
+    tgt = np.zeros((n, nd), np.float32)
+    tgt[:, 0:2] = rng.uniform(-0.6, 0.6, (n, 2))
+    tgt[:, 2] = rng.uniform(-3.0, 3.0, n)
+    tgt[:, 3:] = rng.uniform(-0.8, 0.8, (n, nd - 3))
+    batch.setTargetPosition(0, tgt, kp=4.0)
+    for w, ow in enumerate(worlds):
+        ow.set_state(q[w], qd[w])
+        ow.set_target_position(0, tgt[w], 4.0)
+    for seg in range(10):
+        batch.stepPhysics(30)
+        for ow in worlds:
+            ow.step(30)
+        assert_same(batch, worlds, "position control, segment %d" % seg)
+    gq, _ = batch.getWorldState()
+    err = gq[n // 4:, :nd] - tgt[n // 4:]
+    err[:, 2] = (err[:, 2] + np.pi) % (2 * np.pi) - np.pi
+    err0 = q[n // 4:, :nd] - tgt[n // 4:]
+    err0[:, 2] = (err0[:, 2] + np.pi) % (2 * np.pi) - np.pi
+    # the base reaches its x, y target; heading and fingers stop where the velocity controller's effort (inertia x the
+    # acceleration limit) no longer beats the ground friction -- closer than they started, through the short way round
+    assert np.abs(err[:, :2]).max() < 0.05, np.abs(err).max(axis=0)
+    assert np.all(np.abs(err[:, 2]) <= np.abs(err0[:, 2]) + 0.05) and np.abs(err[:, 2]).max() < 0.6, np.abs(err).max(axis=0)
+    # (finger targets that make the two fingers collide cannot be reached: no bound on the joint errors)
+    assert np.median(np.abs(err[:, 3:])) < 0.2 if nd > 3 else True
+    # switching back to velocity control leaves position mode
+    batch.setTargetVelocity(0, np.zeros((n, nd), np.float32))
+    for ow in worlds:
+        ow.set_target_velocity(0, np.zeros(nd, np.float32))
+    batch.stepPhysics(20)
+    for ow in worlds:
+        ow.step(20)
+    assert_same(batch, worlds, "back to velocity control")
+
+
+def test_reset_caches_keeps_static_object_poses(b2g):
+    """reset_caches = what Box2DWorld::clone() gives (:3026-3037: a freshly loaded world that receives the world state): the
+    poses given to static objects survive -- through the same getPose -> setPose hand-over a clone does --, contacts / impulses /
+    sleep timers / targets do not."""
+    from oracle import b2o
+    n = 64
+    batch = make_batch(b2g, ENV_A, n)
+    old = oracle_worlds(env_dict(ENV_A), n)
+    q, qd = random_states(batch.model, n, seed=91, spread=0.6)
+    tg = random_targets(batch.model, 0, n, seed=92)[0]
+    # dirty the worlds: contacts, impulses, a target, a moved obstacle
+    batch.setWorldState(q, qd, reset_caches=True)
+    scatter_obstacle(batch, old, seed=93)
+    batch.setTargetVelocity(0, tg)
+    batch.stepPhysics(25)
+    # a planner's next query: fresh caches, new state; the obstacle stays where it was put
+    q2, qd2 = random_states(batch.model, n, seed=94, spread=0.6)
+    batch.setWorldState(q2, qd2, reset_caches=True)
+    env = b2o.OracleEnv(env_dict(ENV_A))
+    worlds = []
+    for w, ow in enumerate(old):                      # the oracle's clone(): new world, static poses handed over, then the state
+        fresh = b2o.OracleWorld(env)
+        fresh.set_object_pose(2, *[float(x) for x in ow.get_object_pose(2)])
+        fresh.set_state(q2[w], qd2[w])
+        worlds.append(fresh)
+    assert_same(batch, worlds, "after reset_caches")
+    batch.stepPhysics(30)
+    for ow in worlds:
+        ow.step(30)
+    assert_same(batch, worlds, "30 steps after reset_caches")
+    assert int(batch.contacts()[1][..., 2].sum()) > 10
