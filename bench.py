@@ -38,16 +38,16 @@ ROLLOUT_STEPS = STEPS_PER_TARGET * N_TARGETS
 # BASELINE.json configs -> concrete workloads.  `bytes` = algorithmic bytes per world-step
 # (fixed part, per live contact), DESIGN.md §2.
 CONFIGS = {
-    "cfg2": dict(env="test_env.yaml", worlds=4096, robot_dofs=7, bytes=(940.0, 64.0), scaling="weak",
+    "cfg2": dict(env="test_env.yaml", worlds=4096, robot_dofs=7, bytes=(940.0, 64.0), scaling="weak", obstacle=(0.0, 1.2, 0.0),
                  text="test_env.yaml x %d worlds per GPU x 100 physics steps per step, random robot velocity targets "
                       "resampled every 10 steps (BASELINE.json configs[1])"),
-    "cfg3": dict(env="test_env_rigid_robot.yaml", worlds=65536, robot_dofs=3, bytes=(348.0, 64.0), scaling="weak",
+    "cfg3": dict(env="test_env_rigid_robot.yaml", worlds=65536, robot_dofs=3, bytes=(348.0, 64.0), scaling="weak", obstacle=(0.0, 1.1, 0.0),
                  text="test_env_rigid_robot.yaml x %d worlds per GPU x 100 physics steps per step, rigid robot pushing with "
                       "ground friction joints, random base velocity targets resampled every 10 steps (BASELINE.json configs[2])"),
     "cfg4": dict(env="clutter", worlds=65536, robot_dofs=7, bytes=(4660.0, 64.0), scaling="weak",
                  text="synthetic clutter (robot + 32 convex polygons, seed 42) x %d worlds per GPU x 100 physics steps per step "
                       "(propagate), batched checkCollision timed separately (BASELINE.json configs[3])"),
-    "cfg5": dict(env="test_env.yaml", worlds=1048576, robot_dofs=7, bytes=(940.0, 64.0), scaling="strong",
+    "cfg5": dict(env="test_env.yaml", worlds=1048576, robot_dofs=7, bytes=(940.0, 64.0), scaling="strong", obstacle=(0.0, 1.2, 0.0),
                  text="planner rollout sweep: test_env.yaml x %d worlds in total x 100 physics steps per step, sharded over "
                       "the GPUs, final NCCL all-gather of states (BASELINE.json configs[4])"),
 }
@@ -73,6 +73,23 @@ def oracle_env(cfg):
 # `use_center_of_mass: true`): the 0.8 m x 0.2 m rectangle's upper side, y = 0.2 m - com_y
 BASE_TOP_Y = {"test_env.yaml": 0.2 + 0.016667, "test_env_rigid_robot.yaml": 0.2 - 0.046667}
 OBJ_HALF = 0.05   # obj1 is a 0.1 m x 0.1 m box whose pose is its lower-left corner
+
+
+def place_obstacle(target, cfg, n):
+    """The static hinged obstacle obj2 goes half a metre in front of the finger tips (the YAML leaves it 3 m away), so that
+    the pushed box and the faster robots run into a STATIC body within the rollout: dynamic-vs-static contacts are what
+    Box2D's continuous step (TOI sub-stepping) works on.  About one world in twenty has a TOI event per rollout and 0.3
+    b2TimeOfImpact evaluations per world; DESIGN.md §3 lists how the throughput moves with the distance (the TOI path is the
+    most divergent part of the step on a GPU).  A static object's pose is part of the world state a clone keeps, so it is
+    set once per batch.  `target`: a BatchBox2DWorld, a MultiGpuBatch or an OracleBatch."""
+    pose = cfg.get("obstacle")
+    if pose is None:
+        return
+    if hasattr(target, "setObjectPose"):
+        target.setObjectPose("obj2", np.tile(np.asarray(pose, np.float32), (n, 1)))
+    else:   # OracleBatch: creation order robot, obj1, obj2
+        for w in range(n):
+            target.world(w).set_object_pose(2, *[float(x) for x in pose])
 
 
 def robot_velocity_limits(env):
@@ -200,6 +217,7 @@ def cpu_oracle_throughput(cfg, limits, n_worlds, repeats, threads, seed0=9000):
     """CPU oracle stepping the same workload, one world per thread-pool slot.  Returns (units per repeat, [seconds])."""
     from oracle import b2o
     batch = b2o.OracleBatch(oracle_env(cfg), n_worlds)
+    place_obstacle(batch, cfg, n_worlds)
     times = []
     for r in range(repeats):
         q, qd, tg = synth_inputs(limits, n_worlds, seed0 + r, cfg)
@@ -254,6 +272,7 @@ def parity_gate(cfg, batch, limits, n, seed, threads, sample=1024):
 
     # ---- one step from the fresh-cache state
     ob = b2o.OracleBatch(env, m)   # freshly loaded worlds: the CUDA side starts from fresh clones (reset_caches) too
+    place_obstacle(ob, cfg, m)
     gq, gqd = batch.rollout(0, tg[:1], 1, q, qd, reset_caches=True)
     counts, cio, _ = batch.contacts(max_per_world=64)
     oq, oqd = ob.rollout(q[:m], qd[:m], 0, np.ascontiguousarray(tg[:1, :m]), 1, threads)
@@ -265,6 +284,8 @@ def parity_gate(cfg, batch, limits, n, seed, threads, sample=1024):
     lm = b2o.load_variant("_libm")
     ob = b2o.OracleBatch(env, m)
     ol = lm.OracleBatch(lm.OracleEnv(env_desc), m)
+    place_obstacle(ob, cfg, m)
+    place_obstacle(ol, cfg, m)
     roll = {"checkpoint_steps": [], "touching_contacts_at_checkpoint": [], "touching_pair_sets_identical_at_checkpoint": [],
             "max_abs_dq": 0.0, "max_abs_dqd": 0.0, "bit_identical_worlds": m}
     libm = {"checkpoint_steps": [], "max_abs_dq": [], "mean_abs_dq": [], "max_abs_dqd": [], "mean_abs_dqd": [],
@@ -299,6 +320,7 @@ def parity_gate(cfg, batch, limits, n, seed, threads, sample=1024):
 
     # single step against the libm-trig oracle: the north star's 1e-5 bound against reference-like trigonometry
     ol1 = lm.OracleBatch(lm.OracleEnv(env_desc), m)
+    place_obstacle(ol1, cfg, m)
     gq, gqd = batch.rollout(0, tg[:1], 1, q, qd, reset_caches=True)
     counts, cio, _ = batch.contacts(max_per_world=64)
     lq, lqd = ol1.rollout(q[:m], qd[:m], 0, np.ascontiguousarray(tg[:1, :m]), 1, threads)
@@ -326,7 +348,7 @@ def config_dict(cfg, name, worlds_per_gpu_cfg, worlds_total):
     return {"workload": workload_text(cfg, worlds_per_gpu_cfg), "name": name, "worlds_total": worlds_total,
             "physics_steps_per_step": ROLLOUT_STEPS, "dt": 0.01, "velocity_iterations": 15, "position_iterations": 15,
             "l2": "flushed between timed iterations (384 MB write)",
-            "inputs": "box in the robot's palm (1/4 resting against the base), forward-pushing random velocity targets"}
+            "inputs": "box in the robot's palm (1/4 resting against the base), static obstacle ahead, forward-pushing random velocity targets"}
 
 
 def run_reference(args):
@@ -382,6 +404,7 @@ def measure(args, cfg_name, n_cfg, steps, warmup, ctx, with_cpu):
     L = b2g.lib()
     model = load_model(cfg)
     batch = b2g.BatchBox2DWorld(n, device=local).loadWorld(model)
+    place_obstacle(batch, cfg, n)
     limits = model.dof_limits()
     nq = model.nq
     nd = cfg["robot_dofs"]
@@ -408,6 +431,7 @@ def measure(args, cfg_name, n_cfg, steps, warmup, ctx, with_cpu):
     multi = None
     if world > 1 and rank == 0:
         multi = b2g.MultiGpuBatch(model, n_total, list(range(world)))
+        place_obstacle(multi, cfg, n_total)
         m_q = torch.empty((n_total, nq), dtype=torch.float32).pin_memory()
         m_qd = torch.empty_like(m_q).pin_memory()
         m_tg = torch.empty((N_TARGETS, n_total, nd), dtype=torch.float32).pin_memory()

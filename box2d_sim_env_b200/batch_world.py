@@ -752,6 +752,14 @@ class MultiGpuBatch:
         _check(lib().b2g_multi_get_shard(self.h, int(i), C.byref(b), C.byref(first), C.byref(count)))
         return b, first.value, count.value
 
+    def setObjectPose(self, obj, pose):
+        """b2g_batch_set_object_pose on every shard; pose: [n_worlds, 3] for the whole job."""
+        obj = self.model.object_index(obj) if isinstance(obj, str) else obj
+        pose = _f32(np.broadcast_to(_f32(pose), (self.n_worlds, 3)))
+        for i in range(len(self.devices)):
+            b, first, count = self.shard(i)
+            _check(lib().b2g_batch_set_object_pose(b, obj, _ptr(np.ascontiguousarray(pose[first:first + count]))))
+
     def rollout(self, robot, targets, steps_per_target, q=None, qd=None, reset_caches=True, q_out=None, qd_out=None):
         robot = self.model.object_index(robot) if isinstance(robot, str) else robot
         tg = _f32(targets)

@@ -137,7 +137,7 @@ b2g_status b2g_model_get_link_aabb(const b2g_model* model, int body, float out[4
 b2g_status b2g_model_get_object_aabb(const b2g_model* model, int object, float out[4]);
 typedef struct b2g_joint_info {
     char name[64];         /* YAML name; empty for the ground-friction joint of a link */
-    int32_t kind;          /* 0 ground friction, 1 revolute */
+    int32_t kind;          /* 0 ground friction, 1 revolute, 2 prismatic */
     int32_t object;
     int32_t body_a, body_b;  /* parent / child link (ground friction: 0 / the link) */
     int32_t dof_index;     /* index in the world state vector, -1 for ground-friction joints */

@@ -63,6 +63,107 @@ enum class EntityType { Link, Joint, Object, Robot };
 
 class BatchBox2DWorld;
 class World;
+class Object;
+class Joint;
+
+// sim_env::Logger as the reference uses it (Box2DWorld::getLogger, Box2DWorld.cpp:3011 / 3565-3568: DefaultLogger with a level
+// and a prefix per message).  Loader warnings (what the reference logs through logWarn while parsing, Box2DIOUtils.cpp:70-84) and
+// the facade's own notes go through it; the default sink is stderr, setSink redirects (or silences) it.
+class Logger {
+public:
+    enum class LogLevel { Debug = 0, Info = 1, Warn = 2, Error = 3 };
+    typedef void (*Sink)(LogLevel level, const std::string& message, const std::string& prefix);
+    void setLevel(LogLevel lvl) { _level = lvl; }
+    LogLevel getLevel() const { return _level; }
+    void setSink(Sink sink) { _sink = sink; }
+    void logDebug(const std::string& msg, const std::string& prefix = "") const { log(LogLevel::Debug, msg, prefix); }
+    void logInfo(const std::string& msg, const std::string& prefix = "") const { log(LogLevel::Info, msg, prefix); }
+    void logWarn(const std::string& msg, const std::string& prefix = "") const { log(LogLevel::Warn, msg, prefix); }
+    void logErr(const std::string& msg, const std::string& prefix = "") const { log(LogLevel::Error, msg, prefix); }
+    void log(LogLevel lvl, const std::string& msg, const std::string& prefix) const {
+        if ((int)lvl < (int)_level) return;
+        if (_sink) {
+            _sink(lvl, msg, prefix);
+            return;
+        }
+        static const char* names[] = {"[Debug]", "[Info]", "[Warning]", "[Error]"};
+        std::fprintf(stderr, "%s %s %s\n", names[(int)lvl], prefix.c_str(), msg.c_str());
+    }
+
+private:
+    LogLevel _level = LogLevel::Info;
+    Sink _sink = nullptr;
+};
+
+// One link of ONE world with the method names of Box2DLink (/root/reference/include/sim_env/Box2DWorld.h:100-220).  Obtained
+// from Object::getLink / getBaseLink / getLinks.  A link is identified by its body index (what contacts report).
+class Link {
+public:
+    std::string getName() const;
+    EntityType getType() const { return EntityType::Link; }
+    int body() const { return _body; }
+    int objectIndex() const;
+    // Box2DLink::getPose (:215-224), getVelocityVector (:233-241), getCenterOfMass (:595-603): x, y, theta / vx, vy, omega / x, y
+    void getPose(float pose[3]) const;
+    void getVelocityVector(float vel[3]) const;
+    void getCenterOfMass(float com[2]) const;
+    // link parameters (:463-603); the setters change the model the worlds of the batch share
+    float getMass() const;
+    float getInertia() const;
+    float getGroundFrictionCoefficient() const;
+    float getGroundFrictionTorqueIntegral() const;
+    float getGroundFrictionLimitForce() const;
+    float getGroundFrictionLimitTorque() const;
+    float getContactFriction() const;
+    // kinematic tree (:243-256): the joint this link is the child of (false for a base link), the joints it is the parent of
+    bool getParentJoint(Joint& joint) const;
+    std::vector<Joint> getChildJoints() const;
+    // Box2DLink::checkCollision overloads (Box2DWorld.h:124-129) on this world's contact list
+    bool checkCollision();
+    bool checkCollision(std::vector<Contact>& contacts);
+    bool checkCollision(const std::vector<Link>& other_links, std::vector<Contact>* contacts = nullptr);
+
+private:
+    friend class Object;
+    friend class Joint;
+    Link(BatchBox2DWorld* batch, int64_t world, int body) : _batch(batch), _world(world), _body(body) {}
+    void row(float out[8]) const;
+    BatchBox2DWorld* _batch;
+    int64_t _world;
+    int _body;
+};
+
+// One joint of ONE world with the method names of Box2DJoint (Box2DWorld.h:226-345).  Obtained from Object::getJoint / getJoints.
+class Joint {
+public:
+    enum class JointType { Revolute, Prismatic };
+    Joint() : _batch(nullptr), _world(0), _joint(-1) {}
+    std::string getName() const;
+    EntityType getType() const { return EntityType::Joint; }
+    JointType getJointType() const;
+    int index() const { return _joint; }          // model joint index
+    unsigned int getJointIndex() const;           // position among the object's joints (Box2DJoint::getJointIndex)
+    unsigned int getDOFIndex() const;             // object-local DOF index (Box2DJoint::getDOFIndex)
+    // getPosition / getVelocity (:965-981, :1030-1046) and their setters (:983-990, :1048-1055): one DOF of the owning object
+    float getPosition() const;
+    float getVelocity() const;
+    void setPosition(float v);
+    void setVelocity(float v);
+    void getPositionLimits(float limits[2]) const;
+    void getVelocityLimits(float limits[2]) const;
+    void getAccelerationLimits(float limits[2]) const;
+    DOFInformation getDOFInformation() const;
+    Link getChildLink() const;
+    Link getParentLink() const;
+
+private:
+    friend class Object;
+    friend class Link;
+    Joint(BatchBox2DWorld* batch, int64_t world, int joint) : _batch(batch), _world(world), _joint(joint) {}
+    BatchBox2DWorld* _batch;
+    int64_t _world;
+    int _joint;
+};
 
 // One object (or robot) of ONE world of the batch with the method names of Box2DObject / Box2DRobot
 // (/root/reference/include/sim_env/Box2DWorld.h:350-590).  Obtained from World::getObject / getRobot.
@@ -109,9 +210,17 @@ public:
     void getBallApproximation(std::vector<Ball>& balls) const;
     // Box2DRobotVelocityController::setTargetVelocity (Box2DController.cpp:42-63); one value per DOF of the robot
     void setTargetVelocity(const std::vector<float>& target);
+    // Box2DObject::getLink / getBaseLink / getLinks / getJoint / getJoints (:1411-1505)
+    Link getLink(const std::string& link_name) const;
+    Link getBaseLink() const;
+    std::vector<Link> getLinks() const;
+    Joint getJoint(const std::string& joint_name) const;
+    std::vector<Joint> getJoints() const;
 
 private:
     friend class World;
+    friend class Link;
+    friend class Joint;
     Object(BatchBox2DWorld* batch, int64_t world, int object) : _batch(batch), _world(world), _object(object) {}
     BatchBox2DWorld* _batch;
     int64_t _world;
@@ -124,6 +233,7 @@ private:
 class World {
 public:
     int64_t index() const { return _world; }
+    Logger& getLogger() const;   // Box2DWorld::getLogger (:3565-3568): the batch's logger
     Object getRobot(const std::string& name) const;
     Object getObject(const std::string& name, bool exclude_robots = true) const;
     void getObjects(std::vector<Object>& objects, bool exclude_robots = true) const;
@@ -164,6 +274,7 @@ public:
 private:
     friend class BatchBox2DWorld;
     friend class Object;
+    friend class Link;
     World(BatchBox2DWorld* batch, int64_t world) : _batch(batch), _world(world) {}
     // Box2DCollisionChecker (:2551-2741) on top of the world's touching-contact list: a contact is reported for a body set A
     // when one of its bodies is in A; with `others` the other body must be in it too.  link_a of a reported contact is the
@@ -236,6 +347,7 @@ public:
         }
         return out;
     }
+    Logger& getLogger() const { return _logger; }                      // Box2DWorld::getLogger (:3565-3568)
     bool supportsPhysics() const { return true; }                      // (:3335-3338)
     bool isRobot(const std::string& name) const {                      // (:3202-3205)
         for (size_t i = 0; i < _objects.size(); ++i)
@@ -506,6 +618,8 @@ public:
 private:
     friend class World;
     friend class Object;
+    friend class Link;
+    friend class Joint;
     void finishLoad() {
         check(b2g_model_create(_env, &_model));
         check(b2g_model_get_info(_model, &_info));
@@ -530,6 +644,9 @@ private:
             for (int d = 0; d < _objects[i].n_dofs; ++d) _active[i].push_back(d);
         _limits.assign((size_t)_info.nq * 6, 0.0f);
         if (_info.nq > 0) check(b2g_model_get_dof_limits(_model, _limits.data()));
+        // what the reference logs while it loads a world goes to the logger here too
+        const std::vector<std::string> warnings = getLoadWarnings();
+        for (size_t i = 0; i < warnings.size(); ++i) _logger.logWarn(warnings[i], "[sim_env::b2g::BatchBox2DWorld::loadWorld]");
         check(b2g_batch_create(_model, _n, _device, _max_contacts, &_batch));
     }
     // scope guard: per-world calls act on world i only while it lives
@@ -584,6 +701,7 @@ private:
     std::string _path;
     std::vector<ObjectInfo> _objects;
     std::vector<std::vector<int> > _active;  // active DOFs per object (Box2DObject::_active_dof_indices)
+    mutable Logger _logger;
     std::vector<float> _limits;              // nq x 6 (b2g_model_get_dof_limits)
 };
 
@@ -724,6 +842,123 @@ inline void BatchBox2DWorld::printWorldState(int64_t world_index, std::FILE* out
 }
 
 // ------------------------------------------------------------------------------------------------- World (one world)
+// ---- Link / Joint views ------------------------------------------------------------------------------------------------------
+inline Logger& World::getLogger() const { return _batch->getLogger(); }
+inline std::string Link::getName() const { return _batch->getLinkInfo(_body).name; }
+inline int Link::objectIndex() const { return _batch->getLinkInfo(_body).object; }
+inline void Link::row(float out[8]) const {
+    BatchBox2DWorld::Select sel(_batch, _world);
+    std::vector<float> all((size_t)_batch->numBodies() * 8);
+    BatchBox2DWorld::check(b2g_batch_get_link_states(_batch->_batch, all.data()));
+    for (int k = 0; k < 8; ++k) out[k] = all[(size_t)_body * 8 + k];
+}
+inline void Link::getPose(float pose[3]) const {
+    float r[8];
+    row(r);
+    pose[0] = r[0]; pose[1] = r[1]; pose[2] = r[2];
+}
+inline void Link::getVelocityVector(float vel[3]) const {
+    float r[8];
+    row(r);
+    vel[0] = r[3]; vel[1] = r[4]; vel[2] = r[5];
+}
+inline void Link::getCenterOfMass(float com[2]) const {
+    float r[8];
+    row(r);
+    com[0] = r[6]; com[1] = r[7];
+}
+inline float Link::getMass() const { return _batch->getMass(_body); }
+inline float Link::getInertia() const { return _batch->getInertia(_body); }
+inline float Link::getGroundFrictionCoefficient() const { return _batch->getGroundFrictionCoefficient(_body); }
+inline float Link::getGroundFrictionTorqueIntegral() const { return _batch->getGroundFrictionTorqueIntegral(_body); }
+inline float Link::getGroundFrictionLimitForce() const { return _batch->getGroundFrictionLimitForce(_body); }
+inline float Link::getGroundFrictionLimitTorque() const { return _batch->getGroundFrictionLimitTorque(_body); }
+inline float Link::getContactFriction() const { return _batch->getContactFriction(_body); }
+inline bool Link::getParentJoint(Joint& joint) const {
+    const int j = _batch->getLinkInfo(_body).parent_joint;
+    if (j < 0) return false;
+    joint = Joint(_batch, _world, j);
+    return true;
+}
+inline std::vector<Joint> Link::getChildJoints() const {
+    std::vector<Joint> out;
+    const b2g_link_info li = _batch->getLinkInfo(_body);
+    const ObjectInfo& o = _batch->_objects[(size_t)li.object];
+    for (int b = o.first_body; b < o.first_body + o.n_links; ++b) {
+        const int j = _batch->getLinkInfo(b).parent_joint;
+        if (j >= 0 && _batch->getJointInfo(j).body_a == _body) out.push_back(Joint(_batch, _world, j));
+    }
+    return out;
+}
+inline bool Link::checkCollision() { return World(_batch, _world).checkCollisionLink(_body); }
+inline bool Link::checkCollision(std::vector<Contact>& contacts) { return World(_batch, _world).checkCollisionLink(_body, contacts); }
+inline bool Link::checkCollision(const std::vector<Link>& other_links, std::vector<Contact>* contacts) {
+    std::vector<int> bodies;
+    for (size_t i = 0; i < other_links.size(); ++i) bodies.push_back(other_links[i]._body);
+    return World(_batch, _world).checkCollisionLink(_body, bodies, contacts);
+}
+
+inline std::string Joint::getName() const { return _batch->getJointInfo(_joint).name; }
+inline Joint::JointType Joint::getJointType() const { return _batch->getJointInfo(_joint).kind == 2 ? JointType::Prismatic : JointType::Revolute; }
+inline unsigned int Joint::getDOFIndex() const {
+    const b2g_joint_info ji = _batch->getJointInfo(_joint);
+    return (unsigned int)(ji.dof_index - _batch->_objects[(size_t)ji.object].dof_offset);
+}
+inline unsigned int Joint::getJointIndex() const {
+    const b2g_joint_info ji = _batch->getJointInfo(_joint);
+    return getDOFIndex() - (_batch->_objects[(size_t)ji.object].is_static ? 0u : 3u);
+}
+inline float Joint::getPosition() const {
+    const std::vector<int> ix(1, (int)getDOFIndex());
+    return Object(_batch, _world, _batch->getJointInfo(_joint).object).getDOFPositions(ix)[0];
+}
+inline float Joint::getVelocity() const {
+    const std::vector<int> ix(1, (int)getDOFIndex());
+    return Object(_batch, _world, _batch->getJointInfo(_joint).object).getDOFVelocities(ix)[0];
+}
+inline void Joint::setPosition(float v) {
+    Object(_batch, _world, _batch->getJointInfo(_joint).object).setDOFPositions(std::vector<float>(1, v), std::vector<int>(1, (int)getDOFIndex()));
+}
+inline void Joint::setVelocity(float v) {
+    Object(_batch, _world, _batch->getJointInfo(_joint).object).setDOFVelocities(std::vector<float>(1, v), std::vector<int>(1, (int)getDOFIndex()));
+}
+inline DOFInformation Joint::getDOFInformation() const {
+    return Object(_batch, _world, _batch->getJointInfo(_joint).object).getDOFInformation(getDOFIndex());
+}
+inline void Joint::getPositionLimits(float limits[2]) const {
+    const DOFInformation d = getDOFInformation();
+    limits[0] = d.position_limits[0]; limits[1] = d.position_limits[1];
+}
+inline void Joint::getVelocityLimits(float limits[2]) const {
+    const DOFInformation d = getDOFInformation();
+    limits[0] = d.velocity_limits[0]; limits[1] = d.velocity_limits[1];
+}
+inline void Joint::getAccelerationLimits(float limits[2]) const {
+    const DOFInformation d = getDOFInformation();
+    limits[0] = d.acceleration_limits[0]; limits[1] = d.acceleration_limits[1];
+}
+inline Link Joint::getChildLink() const { return Link(_batch, _world, _batch->getJointInfo(_joint).body_b); }
+inline Link Joint::getParentLink() const { return Link(_batch, _world, _batch->getJointInfo(_joint).body_a); }
+
+inline Link Object::getLink(const std::string& link_name) const { return Link(_batch, _world, _batch->getLink(getName(), link_name)); }
+inline Link Object::getBaseLink() const { return Link(_batch, _world, _batch->getBaseLink(getName())); }
+inline std::vector<Link> Object::getLinks() const {
+    std::vector<Link> out;
+    const std::vector<int> bodies = _batch->getLinks(getName());
+    for (size_t i = 0; i < bodies.size(); ++i) out.push_back(Link(_batch, _world, bodies[i]));
+    return out;
+}
+inline Joint Object::getJoint(const std::string& joint_name) const { return Joint(_batch, _world, _batch->getJoint(getName(), joint_name)); }
+inline std::vector<Joint> Object::getJoints() const {
+    std::vector<Joint> out;
+    const ObjectInfo& o = _batch->_objects[(size_t)_object];
+    for (int b = o.first_body; b < o.first_body + o.n_links; ++b) {
+        const int j = _batch->getLinkInfo(b).parent_joint;
+        if (j >= 0) out.push_back(Joint(_batch, _world, j));
+    }
+    return out;
+}
+
 inline Object World::getRobot(const std::string& name) const {
     const int o = _batch->objectIndex(name);
     if (!_batch->_objects[(size_t)o].is_robot) throw std::runtime_error("[sim_env::b2g::World::getRobot] '" + name + "' is not a robot");

@@ -176,6 +176,40 @@ int main(int argc, char** argv) {
         }
         bad += !groundThrew;
     }
+    // ---- Link / Joint views (Box2DLink / Box2DJoint) and the logger shim
+    {
+        Link base = robot.getBaseLink(), tip = robot.getLink("test_robot_finger_l_2");
+        Joint j = robot.getJoint("finger_l_joint_2"), parent;
+        bad += base.getName() != "test_robot_base" || tip.body() != 3 || robot.getLinks().size() != 5 || robot.getJoints().size() != 4;
+        bad += !tip.getParentJoint(parent) || parent.index() != j.index() || base.getParentJoint(parent) || base.getChildJoints().size() != 2;
+        bad += j.getJointType() != Joint::JointType::Revolute || j.getDOFIndex() != 4 || j.getJointIndex() != 1;
+        bad += j.getChildLink().body() != tip.body() || j.getParentLink().getName() != "test_robot_finger_l_1";
+        float lim[2];
+        j.getPositionLimits(lim);
+        bad += std::fabs(lim[0] + 1.05f) > 1e-6f || std::fabs(lim[1] - 1.05f) > 1e-6f;
+        // a joint's position / velocity are one DOF of its object, in this world only
+        const std::vector<float> before = robot.getDOFPositions();
+        j.setPosition(0.4f);
+        j.setVelocity(-0.2f);
+        const std::vector<float> after = robot.getDOFPositions(), w4q = batch.world(4).getRobot("my_robot").getDOFPositions();
+        bad += std::fabs(j.getPosition() - 0.4f) > 1e-5f || std::fabs(j.getVelocity() + 0.2f) > 1e-5f || std::fabs(after[4] - 0.4f) > 1e-5f;
+        bad += std::fabs(after[3] - before[3]) > 1e-6f || std::fabs(w4q[4] - 0.4f) < 1e-3f;
+        j.setPosition(before[4]);
+        // link pose: the base link's pose is the robot's first three DOFs; mass as in the description
+        float pose[3], com[2], vel[3];
+        base.getPose(pose);
+        base.getCenterOfMass(com);
+        base.getVelocityVector(vel);
+        bad += std::fabs(pose[0] - after[0]) > 1e-6f || std::fabs(pose[1] - after[1]) > 1e-6f || std::fabs(pose[2] - after[2]) > 1e-6f;
+        bad += std::fabs(base.getMass() - 10.1f) > 1e-5f || std::fabs(tip.getMass() - 0.1f) > 1e-6f || tip.getContactFriction() != 1.5f;
+        bad += (base.checkCollision() || tip.checkCollision()) != robot.checkCollision();
+        static int logged;
+        logged = 0;
+        w3.getLogger().setSink([](Logger::LogLevel lvl, const std::string&, const std::string&) { logged += lvl == Logger::LogLevel::Warn; });
+        w3.getLogger().logDebug("below the level", "[facade_demo]");
+        w3.getLogger().logWarn("a warning", "[facade_demo]");
+        bad += logged != 1;
+    }
     bool viewThrew = false;
     try {
         w3.stepPhysics(1);

@@ -81,8 +81,14 @@ class _OracleBackedBatch:
     def rollout(self, robot, tg, spt, q=None, qd=None, reset_caches=True):
         if reset_caches:
             self.ob = self.b2o.OracleBatch(self.env, self.n)
+            if getattr(self, "pose", None):   # reset_caches keeps the poses of static objects
+                for w in range(self.n):
+                    self.ob.world(w).set_object_pose(2, *self.pose)
         import numpy as np
         return self.ob.rollout(q, qd, robot, np.ascontiguousarray(tg), spt, 4)
+
+    def setObjectPose(self, obj, pose):
+        self.pose = [float(x) for x in pose[0]]
 
     def contacts(self, max_per_world=64):
         import numpy as np
@@ -104,7 +110,11 @@ def test_parity_gate_is_not_vacuous(oracle):
         cfg = bench.CONFIGS[name]
         n = 128
         desc = bench.oracle_env(cfg)
-        gate = bench.parity_gate(cfg, _OracleBackedBatch(oracle, desc, n), bench.robot_velocity_limits(desc), n, 1234, 4, sample=n)
+        stand_in = _OracleBackedBatch(oracle, desc, n)
+        bench.place_obstacle(stand_in, cfg, n)
+        gate = bench.parity_gate(cfg, stand_in, bench.robot_velocity_limits(desc), n, 1234, 4, sample=n)
+        if name == "cfg2":
+            assert gate["rollout"]["toi_events"] > 0, "the headline workload must exercise the TOI sub-steps"
         assert gate["pass"] and gate["nonvacuous"], gate
         assert gate["single_step"]["touching_contacts"] >= n // 8
         assert gate["rollout"]["touching_contacts"] * 8 >= n

@@ -11,6 +11,7 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 cfg = bench.CONFIGS[name]
 model = bench.load_model(cfg)
 batch = b2g.BatchBox2DWorld(n).loadWorld(model)
+bench.place_obstacle(batch, cfg, n)
 q, qd, tg = bench.synth_inputs(model.dof_limits(), n, 1, cfg)
 d_tg = torch.from_numpy(tg).cuda()
 for r in range(reps):
