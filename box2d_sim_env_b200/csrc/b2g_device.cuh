@@ -135,6 +135,25 @@ constexpr int kHdrWords = (int)((sizeof(ModelHeader) + sizeof(StepParams) + 15) 
 DEV const ModelHeader& H() { return *reinterpret_cast<const ModelHeader*>(g_sm); }
 DEV const StepParams& PRM() { return *reinterpret_cast<const StepParams*>(g_sm + sizeof(ModelHeader) / 4); }
 
+// B2G_PHASE_TIMING (tools/phase_timing.py; never in the product build): cycles per phase of the step, summed over warps.
+// tick(id) charges the cycles since the warp's previous tick to phase `id`; warps are converged at the phase boundaries.
+#ifdef B2G_PHASE_TIMING
+__device__ unsigned long long g_phaseCycles[32];
+DEV void tick(int id) {
+    __shared__ long long s_last[32];
+    const long long t = clock64();
+    const unsigned m = __activemask();
+    if ((int)(threadIdx.x & 31) == __ffs((int)m) - 1) {
+        const int wp = threadIdx.x >> 5;
+        if (id >= 0) atomicAdd(&g_phaseCycles[id], (unsigned long long)(t - s_last[wp]));
+        s_last[wp] = clock64();
+    }
+    __syncwarp(m);
+}
+#else
+DEV void tick(int) {}
+#endif
+
 struct Ctx {
     char* P;  // &state[tile][0][lane]: chunk k of this thread's world is the float4 at P + k * 512
 };
@@ -646,11 +665,28 @@ DEVN void findNewContacts(Ctx c) {
         if (((moved >> a) & 1ull) == 0ull) cand &= moved;
         if (cand == 0ull) continue;
         Box fa = ldFat(c, a);
+        // two passes: the overlap tests first (independent loads, nothing stored in between: they pipeline), then addPair for
+        // the hits in the same ascending order
+        uint64_t hit = 0ull;
         while (cand) {
-            int b = __ffsll((long long)cand) - 1;
+            const int b0 = __ffsll((long long)cand) - 1;
             cand &= cand - 1ull;
-            Box fb = ldFat(c, b);
-            if (boxOverlap(fb, fa)) addPair(c, a, b);
+            const int b1 = cand ? __ffsll((long long)cand) - 1 : b0;
+            cand &= cand - 1ull;   // 0 & (0 - 1) = 0
+            const int b2 = cand ? __ffsll((long long)cand) - 1 : b0;
+            cand &= cand - 1ull;
+            const int b3 = cand ? __ffsll((long long)cand) - 1 : b0;
+            cand &= cand - 1ull;
+            const Box f0 = ldFat(c, b0), f1 = ldFat(c, b1), f2 = ldFat(c, b2), f3 = ldFat(c, b3);
+            if (boxOverlap(f0, fa)) hit |= 1ull << b0;
+            if (boxOverlap(f1, fa)) hit |= 1ull << b1;
+            if (boxOverlap(f2, fa)) hit |= 1ull << b2;
+            if (boxOverlap(f3, fa)) hit |= 1ull << b3;
+        }
+        while (hit) {
+            const int b = __ffsll((long long)hit) - 1;
+            hit &= hit - 1ull;
+            addPair(c, a, b);
         }
     }
     stMoved(c, 0ull);

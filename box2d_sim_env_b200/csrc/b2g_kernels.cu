@@ -588,6 +588,16 @@ __global__ void k_status(float* S, long long N, int stateChunks, int statusOff, 
 // ---------------------------------------------------------------------------------------------------------------
 // batches may be driven from different host threads (one stream per batch): the launch counter is shared
 static std::atomic<unsigned long long> g_launches{0};
+#ifdef B2G_PHASE_TIMING
+extern "C" int b2g_debug_phase_cycles(unsigned long long* out32, int reset) {
+    if (out32 && cudaMemcpyFromSymbol(out32, g_phaseCycles, sizeof(unsigned long long) * 32) != cudaSuccess) return 1;
+    if (reset) {
+        unsigned long long zero[32] = {0};
+        if (cudaMemcpyToSymbol(g_phaseCycles, zero, sizeof(zero)) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+#endif
 unsigned long long launchCount() { return g_launches.load(std::memory_order_relaxed); }
 
 static size_t smemPad() {  // tuning knob: extra dynamic shared memory per CTA throttles occupancy (B2G_SMEM_PAD bytes)

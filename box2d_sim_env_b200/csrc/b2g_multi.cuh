@@ -215,7 +215,11 @@ DEV void jointWarmApply(Ctx c, int j, float dtRatio) {
 template <int LPW>
 DEV void updateSchedule(Ctx c, WorldShared& W, int velIters) {
     const int nj = W.nj, nc = W.nc, n = nj + nc;
+#ifdef B2G_MULTI_FORCE_SERIAL  /* tuning experiment: lane-strided phases only, the velocity iterations stay on lane 0 */
+    if (true) {
+#else
     if (n > kMaxNodes || velIters > kMaxLaps || velIters < 1) {
+#endif
         W.serial = 1;
         W.keyNj = -1;
         return;

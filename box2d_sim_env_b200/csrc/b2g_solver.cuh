@@ -1180,14 +1180,17 @@ DEV uint64_t buildIslands(Ctx c, Lists& L) {
     uint64_t staticSeen = 0ull;    // static bodies that joined at least one island
     uint64_t jointFlag[2] = {0ull, 0ull};
     uint64_t contactFlag[2] = {0ull, 0ull};
-    uint64_t contactLive[2] = {0ull, 0ull};  // enabled && touching
     const int ncAll = contactCount(c);
+    // contacts that can be island edges (enabled && touching), oldest first: the DFS walks this short list newest first for
+    // every body it pops instead of all ncAll slots (same visiting order: the slots it skips were skipped by the flag test)
+    unsigned char liveList[kMaxContacts];
+    int nLive = 0;
     for (int k = 0; k < ncAll; ++k) {
         const float4 head = ld4(c, cslot(c, k, SC_HEAD4));
         int fx = __float_as_int(head.x), fl = __float_as_int(head.y);
         L.cA[k] = (unsigned char)mI(c, mfix(c, fx & 0xff, MF_BODY));
         L.cB[k] = (unsigned char)mI(c, mfix(c, (fx >> 8) & 0xff, MF_BODY));
-        if ((fl & CF_ENABLED) != 0 && (fl & CF_TOUCHING) != 0) contactLive[k >> 6] |= 1ull << (k & 63);
+        if ((fl & CF_ENABLED) != 0 && (fl & CF_TOUCHING) != 0) liveList[nLive++] = (unsigned char)k;
     }
 
     unsigned char stack[kMaxBodies];
@@ -1213,11 +1216,11 @@ DEV uint64_t buildIslands(Ctx c, Lists& L) {
             L.dyn[L.ndyn++] = (unsigned char)b;
             wakeBody(c, b);
             // contact edges of b, newest first
-            for (int k = ncAll - 1; k >= 0; --k) {
+            for (int t = nLive - 1; t >= 0; --t) {
+                const int k = liveList[t];
                 int cA = L.cA[k], cB = L.cB[k];
                 if (cA != b && cB != b) continue;
                 if ((contactFlag[k >> 6] >> (k & 63)) & 1ull) continue;
-                if (((contactLive[k >> 6] >> (k & 63)) & 1ull) == 0ull) continue;
                 B2G_ASSERT(L.nc < kMaxContacts, "island contact list overflow", L.nc, k);
                 L.contacts[L.nc++] = (unsigned char)k;
                 contactFlag[k >> 6] |= 1ull << (k & 63);
@@ -1335,13 +1338,17 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
     phaseSync<SYNC, 2>();
     int nSimple = 0;
     const uint64_t simple = reorderIslands(c, L, nSimple);
+    tick(3);
 
     // ---- b2Island::Solve, all islands together
     for (int i = 0; i < L.ndyn; ++i) integrateVelocity(c, L.dyn[i], h);  // c0 = c, integrate velocities
     phaseSync<SYNC, 3>();
+    tick(4);
     for (int i = 0; i < L.nc; ++i) contactInit(c, L.contacts[i], dtRatio, true);
     for (int i = 0; i < L.nc; ++i) contactWarmStart(c, L.contacts[i]);
+    tick(5);
     for (int i = 0; i < L.nj; ++i) jointInit(c, L.joints[i], dtRatio);
+    tick(6);
 
     const int velIters = PRM().velIters, posIters = PRM().posIters;
     phaseSync<SYNC, 4>();
@@ -1360,11 +1367,14 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
         for (int i = 0; i < L.nc; ++i) contactSolveVel(c, L.contacts[i]);
     }
     phaseSync<SYNC, 5>();
+    tick(7);
     for (int i = 0; i < L.nc; ++i) contactStoreImpulses(c, L.contacts[i]);
     for (int i = 0; i < nSimple; ++i) frictionIslandSolve(c, L.joints[L.nj + i], dtRatio, velIters);
 
     phaseSync<SYNC, 6>();
+    tick(8);
     for (int i = 0; i < L.ndyn; ++i) integratePosition(c, L.dyn[i], h, allowSleep);
+    tick(9);
 
     // position iterations: every island leaves the loop on its own (b2Island::Solve breaks when contactsOkay &&
     // jointsOkay); `open` = islands still iterating, `solved` = islands that reported positionSolved
@@ -1395,6 +1405,7 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
         open &= bad;
     }
     phaseSync<SYNC, 7>();
+    tick(10);
     // SynchronizeTransform of every island body, fused with its SynchronizeFixtures (upstream runs that in a second pass
     // over the body list; the order is free here: the move buffer is a bit mask and nothing in between touches transforms
     // or fat AABBs).  xf1 = the transform at the start of the step: its rotation b2Rot(a0) is the m_xf.q still stored at
@@ -1427,6 +1438,7 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
     }
 
     phaseSync<SYNC, 8>();
+    tick(11);
     if (moved) stMoved(c, ldMoved(c) | moved);
     findNewContacts(c);
 }

@@ -480,12 +480,14 @@ template <bool SYNC>
 DEVN void stepWorld(Ctx c, bool executeControllers, bool allowSleeping) {
     const ModelHeader& h = H();
 
+    tick(-1);
     if (executeControllers) {
         for (int r = 0; r < h.nrobots; ++r) robotControl(c, mI(c, h.oRobotOrder + r), r);
     }
     if (!allowSleeping) {  // b2World::SetAllowSleeping(false) wakes every body
         for (int b = h.nb - 1; b >= 0; --b) wakeBody(c, b);
     }
+    tick(0);
     // b2World::Step
     int flags = ldI(c, sslot(c, SS_FLAGS));
     if (flags & 1) {
@@ -494,17 +496,22 @@ DEVN void stepWorld(Ctx c, bool executeControllers, bool allowSleeping) {
     }
     float dtRatio = ldF(c, sslot(c, SS_INV_DT0)) * PRM().dt;
     phaseSync<SYNC, 0>();
+    tick(1);
     collide(c);
     phaseSync<SYNC, 1>();
+    tick(2);
     solveIslands<SYNC>(c, dtRatio, allowSleeping);
     phaseSync<SYNC, 9>();
+    tick(12);
 #ifndef B2G_EXPERIMENT_NO_TOI  /* tuning experiment only: wrong physics, shows the register cost of the TOI call chain */
     solveTOI(c);
 #endif
+    tick(13);
     stF(c, sslot(c, SS_INV_DT0), PRM().inv_dt);
     for (int b = 0; b < h.nb; ++b) {  // ClearForces
         if (mI(c, mbody(c, b, MB_FORCED))) st4(c, bslot(c, b, SB_FORCE4), mk4(0.0f, 0.0f, 0.0f, 0.0f));
     }
+    tick(14);
 }
 
 // One step of stepPhysics(callback, ...) (:3312-3333): "for (i < steps and not abort_prematurely)".  Kept out of stepWorld
