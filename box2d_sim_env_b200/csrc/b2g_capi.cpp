@@ -468,13 +468,16 @@ static b2g_status createBatch(const HostModel& hostModel, int64_t n_worlds, int 
     const char* envLanes = getenv("B2G_LANES");
     if (envLanes) b->stepLanes = atoi(envLanes);
     else {
-        // As few worlds per warp as keeps the batch on at most 512 warps (a B200 has 592 warp schedulers); above 8 lanes a
-        // power of two (11 or 14 lanes lose more to row segments that straddle 128-byte lines than they gain over 16).
-        // Measured on the contact-rich cfg 2 workload, 4096 worlds, ms per 100 steps: 4 -> 24.3, 5 -> 21.0, 6 -> 17.5,
-        // 7 -> 15.6, 8 -> 14.6, 16 -> 14.3 (profiles/r2_mode_sweep.txt).
+        // Up to 4 worlds per warp while that keeps the batch on at most 518 warps (a B200 has 592 warp schedulers); beyond
+        // that 16, then full warps.  The stepping kernel streams ~400 KB of once-per-step code per warp and step through the
+        // GPC-level instruction caches, so FEWER, wider warps win as soon as the batch does not fit 4 lanes: measured on the
+        // contact-rich workloads, 4096 worlds, ms per 100 steps (profiles/r2_mode_sweep.txt):
+        //   cfg 2: 4 -> 27.2, 6 -> 20.4, 7 -> 17.2, 8 -> 16.8, 10 -> 15.6, 12 -> 15.8, 16 -> 15.9, 24 -> 16.7, 32 -> 17.3
+        //   cfg 3: 7 -> 7.8, 8 -> 7.3, 12 -> 6.0, 16 -> 5.7, 24 -> 5.7, 32 -> 5.7
+        // (10 or 12 lanes are within 2 % of 16 on cfg 2 and lose 5-12 % on cfg 3.)
         const long long warpsTarget = (long long)sms * 4 * 7 / 8;  // 518 on a 148-SM B200
         long long l = (n_worlds + warpsTarget - 1) / warpsTarget;
-        b->stepLanes = l <= 8 ? (int)l : (l <= 16 ? 16 : 32);
+        b->stepLanes = l <= 4 ? (int)l : (l <= 16 ? 16 : 32);
     }
     if (b->stepLanes < 1 || b->stepLanes > 32) b->stepLanes = 32;
     // lanes per world (b2g_multi.cuh): experiments / tests choose with B2G_LPW
