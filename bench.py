@@ -41,6 +41,11 @@ CONFIGS = {
     "cfg2": dict(env="test_env.yaml", worlds=4096, robot_dofs=7, bytes=(940.0, 64.0), scaling="weak", obstacle=(0.0, 1.2, 0.0),
                  text="test_env.yaml x %d worlds per GPU x 100 physics steps per step, random robot velocity targets "
                       "resampled every 10 steps (BASELINE.json configs[1])"),
+    # the round-1 inputs of cfg2 (box 1.3 m ahead of the robot, obstacle at its YAML pose: next to no contact within a rollout);
+    # rides along with the default run as the `r1_inputs` sub-record so that the two rounds' numbers stay comparable
+    "cfg2r1": dict(env="test_env.yaml", worlds=4096, robot_dofs=7, bytes=(940.0, 64.0), scaling="weak", placement="far",
+                   text="test_env.yaml x %d worlds per GPU x 100 physics steps per step, random robot velocity targets, round-1 "
+                        "inputs (box 1.3 m ahead of the robot: contact-free)"),
     "cfg3": dict(env="test_env_rigid_robot.yaml", worlds=65536, robot_dofs=3, bytes=(348.0, 64.0), scaling="weak", obstacle=(0.0, 1.1, 0.0),
                  text="test_env_rigid_robot.yaml x %d worlds per GPU x 100 physics steps per step, rigid robot pushing with "
                       "ground friction joints, random base velocity targets resampled every 10 steps (BASELINE.json configs[2])"),
@@ -128,6 +133,8 @@ def synth_inputs(vel_limits, n, seed, cfg=None, lo=0, hi=None):
         gap = rng.uniform(0.0002, 0.0015, n)
         cy = np.where(resting, ytop + gap + OBJ_HALF, cy)
         th = np.where(resting, 0.0, th)
+        if cfg.get("placement") == "far":
+            cy = np.full(n, ytop + 1.3)
         c, s = np.cos(th), np.sin(th)
         first = 7 if nd == 7 else 3      # robot DOFs come first, then obj1 (x, y, theta), then obj2's hinge
         q = np.zeros((n, first + 4), np.float32)
@@ -290,6 +297,7 @@ def parity_gate(cfg, batch, limits, n, seed, threads, sample=1024):
             "max_abs_dq": 0.0, "max_abs_dqd": 0.0, "bit_identical_worlds": m}
     libm = {"checkpoint_steps": [], "max_abs_dq": [], "mean_abs_dq": [], "max_abs_dqd": [], "mean_abs_dqd": [],
             "touching_pair_sets_identical": []}
+    mid = None
     for t in range(N_TARGETS):
         first = t == 0
         gq, gqd = batch.rollout(0, tg[t:t + 1], STEPS_PER_TARGET, q if first else None, qd if first else None,
@@ -299,6 +307,8 @@ def parity_gate(cfg, batch, limits, n, seed, threads, sample=1024):
         oq, oqd = ob.rollout(q[:m] if first else None, qd[:m] if first else None, 0, seg, STEPS_PER_TARGET, threads)
         lq, lqd = ol.rollout(q[:m] if first else None, qd[:m] if first else None, 0, seg, STEPS_PER_TARGET, threads)
         c = compare(gq, gqd, oq, oqd)
+        if first:
+            mid = (oq.copy(), oqd.copy())
         same, touching = _touching_sets(counts, cio, ob, m)
         roll["checkpoint_steps"].append((t + 1) * STEPS_PER_TARGET)
         roll["touching_contacts_at_checkpoint"].append(touching)
@@ -330,6 +340,21 @@ def parity_gate(cfg, batch, limits, n, seed, threads, sample=1024):
     libm["what"] = "CUDA path vs the oracle rebuilt with libm sinf/cosf in b2Rot (upstream Box2D's calls)"
     out["rollout_vs_libm"] = libm
 
+    # A config whose synthetic states start without overlaps (the clutter scene) has no touching contact after one step from
+    # the inputs: there the one-step comparison is repeated from the oracle's state after the first target segment (fresh
+    # caches on both sides, bodies already pressed together), so that the single-step bound is checked on live manifolds too.
+    if single["touching_contacts"] == 0 and mid is not None:
+        q1, qd1 = q.copy(), qd.copy()
+        q1[:m], qd1[:m] = mid
+        ob = b2o.OracleBatch(env, m)
+        place_obstacle(ob, cfg, m)
+        gq, gqd = batch.rollout(0, tg[1:2], 1, q1, qd1, reset_caches=True)
+        counts, cio, _ = batch.contacts(max_per_world=64)
+        oq, oqd = ob.rollout(q1[:m], qd1[:m], 0, np.ascontiguousarray(tg[1:2, :m]), 1, threads)
+        single = compare(gq, gqd, oq, oqd)
+        single["touching_pair_sets_identical"], single["touching_contacts"] = _touching_sets(counts, cio, ob, m)
+        single["from"] = "the oracle's state after the first %d steps (the input states have no overlaps)" % STEPS_PER_TARGET
+        out["single_step"] = single
     nonvacuous = single["touching_contacts"] > 0 and roll["touching_contacts"] * 8 >= m
     out["nonvacuous"] = bool(nonvacuous)
     # BASELINE.json: single-step state error <= 1e-5 and bit-exact contact-pair sets / manifold point counts
@@ -664,6 +689,11 @@ def run_ours(args):
         if rank == 0 and sub:
             keep = ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "config", "e2e", "run", "roofline", "multi_gpu")
             line["cfg5"] = {k: sub[k] for k in keep if k in sub}
+    if args.config == "cfg2" and world == 1 and not args.worlds and not args.no_cfg5:
+        sub = measure(args, "cfg2r1", CONFIGS["cfg2r1"]["worlds"], 3, 3, ctx, with_cpu=False)
+        if sub:
+            line["r1_inputs"] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "run", "e2e") if k in sub}
+            line["r1_inputs"]["inputs"] = "round-1 placement: box 1.3 m ahead of the robot, obstacle at its YAML pose (BENCH_r01: 5.06e7 world-steps/s)"
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -718,7 +748,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE.json config (default: the one the "
+    ap.add_argument("--config", default="cfg2", choices=sorted(k for k in CONFIGS if k != "cfg2r1"), help="BASELINE.json config (default: the one the "
                     "metric is quoted on, test_env.yaml x 4096 worlds)")
     ap.add_argument("--worlds", type=int, default=0, help="override the config's world count (per GPU; total for cfg5)")
     ap.add_argument("--ref-worlds", type=int, default=4096, help="worlds per step of the CPU oracle sample")

@@ -668,9 +668,11 @@ cudaError_t launchStep(const Launch& L, int object, const float* targets, int nT
     if (L.stepLanes < 32) {  // small batch: narrow warps, one warp per CTA
         cudaError_t e = prepare((const void*)k_step_narrow, L.h);
         if (e != cudaSuccess) return e;
-        unsigned blocks = (unsigned)((L.N + L.stepLanes - 1) / L.stepLanes);
-        k_step_narrow<<<blocks, 32, smemBytes(L.h), L.stream>>>(L.h, L.blob, L.S, L.N, L.prm, object, targets, nTargets,
-                                                              stepsPerTarget, execCtrl, allowSleep, L.stepLanes);
+        const unsigned warps = (unsigned)((L.N + L.stepLanes - 1) / L.stepLanes);
+        static const int wpc = [] { const char* e = getenv("B2G_NARROW_WARPS"); int v = e ? atoi(e) : 1; return v >= 1 && v <= 32 ? v : 1; }();
+        const unsigned blocks = (warps + wpc - 1) / wpc;  // warps per CTA: tuning experiments only (default one warp per CTA)
+        k_step_narrow<<<blocks, 32 * wpc, smemBytes(L.h), L.stream>>>(L.h, L.blob, L.S, L.N, L.prm, object, targets, nTargets,
+                                                                    stepsPerTarget, execCtrl, allowSleep, L.stepLanes);
         ++g_launches;
         return cudaGetLastError();
     }
