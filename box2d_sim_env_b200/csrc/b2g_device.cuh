@@ -226,19 +226,29 @@ DEV XF ldXF(Ctx c, int b) {
 }
 DEV void stXF(Ctx c, int b, const XF& x) { st4(c, bslot(c, b, SB_XF4), mk4(x.p.x, x.p.y, x.q.s, x.q.c)); }
 DEV V2 localCenter(Ctx c, int b) { float2 v = m2(c, mbody(c, b, MB_LCX)); return mk(v.x, v.y); }
-DEV bool isAwake(Ctx c, int b) { return (ldI(c, bslot(c, b, SB_FLAGS)) & 1) != 0; }
 DEV int bodyType(Ctx c, int b) { return mI(c, mbody(c, b, MB_TYPE)); }
+// awake bodies of the world as one mask (model.h: SS_AWAKE_LO): the same information as bit0 of every body's SB_FLAGS
+DEV uint64_t ldAwake(Ctx c) {
+    const float2 v = ld2(c, H().cScalar * kChunkBytes + SS_AWAKE_LO);
+    return (uint64_t)(uint32_t)__float_as_int(v.x) | ((uint64_t)(uint32_t)__float_as_int(v.y) << 32);
+}
+DEV void stAwake(Ctx c, uint64_t m) {
+    st2(c, H().cScalar * kChunkBytes + SS_AWAKE_LO, make_float2(__int_as_float((int)(uint32_t)m), __int_as_float((int)(uint32_t)(m >> 32))));
+}
+DEV bool isAwake(Ctx c, int b) { return ((ldAwake(c) >> b) & 1ull) != 0ull; }
 
 // b2Body::SetAwake
 DEV void wakeBody(Ctx c, int b) {
-    int f = ldI(c, bslot(c, b, SB_FLAGS));
-    if ((f & 1) == 0) {
-        stI(c, bslot(c, b, SB_FLAGS), f | 1);
+    const uint64_t m = ldAwake(c);
+    if (((m >> b) & 1ull) == 0ull) {
+        stAwake(c, m | (1ull << b));
+        stI(c, bslot(c, b, SB_FLAGS), ldI(c, bslot(c, b, SB_FLAGS)) | 1);
         stF(c, bslot(c, b, SB_SLEEP), 0.0f);
     }
 }
 DEV void sleepBody(Ctx c, int b) {
     int f = ldI(c, bslot(c, b, SB_FLAGS));
+    stAwake(c, ldAwake(c) & ~(1ull << b));
     st4(c, bslot(c, b, SB_VEL4), mk4(0.0f, 0.0f, 0.0f, __int_as_float(f & ~1)));
     stF(c, bslot(c, b, SB_SLEEP), 0.0f);
     if (mI(c, mbody(c, b, MB_FORCED))) st4(c, bslot(c, b, SB_FORCE4), mk4(0.0f, 0.0f, 0.0f, 0.0f));

@@ -1194,10 +1194,13 @@ DEV uint64_t buildIslands(Ctx c, Lists& L) {
     }
 
     unsigned char stack[kMaxBodies];
+    // seeds: awake dynamic bodies that no earlier island holds.  A body the DFS wakes is flagged in the same breath, so the mask
+    // read once is as good as the live flags.
+    const uint64_t awakeAtStart = ldAwake(c);
     for (int seed = nb - 1; seed >= 0; --seed) {
         if ((bodyFlag >> seed) & 1ull) continue;
+        if (((awakeAtStart >> seed) & 1ull) == 0ull) continue;
         if (bodyType(c, seed) == 0) continue;
-        if (!isAwake(c, seed)) continue;
         const int isl = L.nIslands++;
         L.jStart[isl] = (unsigned char)L.nj;
         L.cStart[isl] = (unsigned char)L.nc;

@@ -323,6 +323,7 @@ DEVN void initWorld(Ctx c) {
     stI(c, sslot(c, SS_TARGET_AVAIL), 0);
     stI(c, sslot(c, SS_ABORT), 0);
     st4(c, sslot(c, SS_DISABLED_LO), mk4(0.0f, 0.0f, 0.0f, 0.0f));
+    stAwake(c, h.nb >= 64 ? ~0ull : ((1ull << h.nb) - 1ull));  // every body is created awake (SB_FLAGS = 1 above)
     for (int t = 0; t < ((h.ntarget + 3) & ~3); ++t) stF(c, tslot(c, t), 0.0f);
 
     // Box2DObject ctor: _base_link->setPose((0,0,0), true, true) (:1335)

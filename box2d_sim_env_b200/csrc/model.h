@@ -205,6 +205,8 @@ enum ScalarState {
     SS_TARGET_AVAIL = B2G_F(1, 2),  // bit r: robot r has a controller target
     SS_ABORT = B2G_F(1, 3),      // guarded stepping: bit0 a forbidden BeginContact fired, bits 8.. steps executed
     SS_DISABLED_LO = B2G_F(2, 0), SS_DISABLED_HI = B2G_F(2, 1),  // bit f: fixture f has categoryBits = 0 (Box2DLink::setEnabled(false))
+    SS_AWAKE_LO = B2G_F(2, 2), SS_AWAKE_HI = B2G_F(2, 3),        // bit b: body b is awake -- mirrors bit0 of every body's SB_FLAGS (wakeBody / sleepBody keep
+                                                                 // both): finding the awake bodies costs one 8-byte load instead of one 512-byte row per body
     SS_CHUNKS = 3
 };
 
