@@ -396,6 +396,7 @@ b2g_status b2g_batch_clone(b2g_batch* src, b2g_batch** out) {
     dst->prm.inv_dt = src->prm.inv_dt;
     dst->prm.velIters = src->prm.velIters;
     dst->prm.posIters = src->prm.posIters;
+    dst->prm.syncMask = src->prm.syncMask;
     auto bail = [&](cudaError_t e, const char* what) {
         b2g_batch_destroy(dst);
         return cudaFail(e, what);
@@ -480,6 +481,11 @@ static b2g_status createBatch(const HostModel& hostModel, int64_t n_worlds, int 
         b->stepLanes = l <= 4 ? (int)l : (l <= 16 ? 16 : 32);
     }
     if (b->stepLanes < 1 || b->stepLanes > 32) b->stepLanes = 32;
+    // phase barriers of k_step (b2g_solver.cuh: phaseSync); B2G_SYNC_MASK overrides for experiments
+    {
+        const char* envMask = getenv("B2G_SYNC_MASK");
+        b->prm.syncMask = envMask ? (int)strtol(envMask, nullptr, 0) : (b->m.h.nb >= 16 ? 0x2aa : 0x7ff);
+    }
     // lanes per world (b2g_multi.cuh): experiments / tests choose with B2G_LPW
     const char* envLpw = getenv("B2G_LPW");
     b->stepLpw = envLpw ? atoi(envLpw) : 1;

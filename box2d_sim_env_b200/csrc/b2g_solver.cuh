@@ -1149,20 +1149,20 @@ DEV void integratePosition(Ctx c, int b, float h, bool updateSleep) {
 }
 
 
-// Phase barrier of the CTA-synchronised stepping kernel.  The step is ~17.6 k distinct instructions (k_step is 280 KB of
-// SASS); resident warps that drift through different phases thrash the SM's instruction cache ("no_instructions"
-// was the top stall).  With SYNC every warp of the CTA walks the phases together, so the cache holds one phase.
+// Phase barrier of the CTA-synchronised stepping kernel.  The step is ~17.6 k distinct instructions (k_step is 300 KB of
+// SASS); resident warps that drift through different phases thrash the SM's instruction caches ("no_instruction" was the top
+// stall).  With SYNC every warp of the CTA walks the phases together, so the caches hold one phase.
 // All threads of the CTA must reach every phaseSync: they sit outside data-dependent control flow only.
-// Which of the ten candidate barriers are kept (bit ID).  Measured on B200, 65536 worlds of test_env.yaml, ms per 100 steps:
-// none 32.7, only the two around the velocity iterations 24.6, every second one (0x2aa: after Collide, before the contact /
-// joint initialisation, after the velocity iterations, before the transform / fixture synchronisation, before TOI) 18.2,
-// all ten 18.5.  Dropping any single one of the ten changes the time by < 1 %.
-#ifndef B2G_SYNC_MASK
-#define B2G_SYNC_MASK 0x2aa
-#endif
+// Which of the thirteen candidate barriers are taken is a launch parameter (StepParams::syncMask, bit ID; warp-uniform
+// shared-memory read).  Measured on B200, 65536 worlds, ms per 100 steps (tools/sweep_sync.sh, profiles/r2_sync_sweep.txt):
+//   round-1 inputs (contact-free), cfg 2: none 32.7, the two around the velocity iterations 24.6, every second of the first
+//   ten (0x2aa) 18.2, all ten 18.5;
+//   round-2 inputs (contacts, TOI), cfg 2 / cfg 3 / cfg 4: none 102 / 28.0 / 271, 0x30 75.6 / 15.9 / 188, 0x2aa 44.5 / 10.95 /
+//   108.2, all ten (0x3ff) 42.3 / 10.4 / 110.4, ten + end of step (0x7ff) 41.4 / 10.35 / 110.5, all thirteen 41.8 / 10.3 / 110.4.
+// Default (b2g_capi.cpp): 0x7ff for small models, 0x2aa for scenes with 16 bodies or more (cfg 4).
 template <bool SYNC, int ID>
 DEV void phaseSync() {
-    if (SYNC && ((B2G_SYNC_MASK >> ID) & 1)) __syncthreads();
+    if (SYNC && ((PRM().syncMask >> ID) & 1)) __syncthreads();
 }
 
 
@@ -1349,6 +1349,7 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
     tick(4);
     for (int i = 0; i < L.nc; ++i) contactInit(c, L.contacts[i], dtRatio, true);
     for (int i = 0; i < L.nc; ++i) contactWarmStart(c, L.contacts[i]);
+    phaseSync<SYNC, 11>();
     tick(5);
     for (int i = 0; i < L.nj; ++i) jointInit(c, L.joints[i], dtRatio);
     tick(6);
@@ -1377,6 +1378,7 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
     phaseSync<SYNC, 6>();
     tick(8);
     for (int i = 0; i < L.ndyn; ++i) integratePosition(c, L.dyn[i], h, allowSleep);
+    phaseSync<SYNC, 12>();
     tick(9);
 
     // position iterations: every island leaves the loop on its own (b2Island::Solve breaks when contactsOkay &&

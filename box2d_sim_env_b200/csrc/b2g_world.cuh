@@ -507,6 +507,7 @@ DEVN void stepWorld(Ctx c, bool executeControllers, bool allowSleeping) {
 #ifndef B2G_EXPERIMENT_NO_TOI  /* tuning experiment only: wrong physics, shows the register cost of the TOI call chain */
     solveTOI(c);
 #endif
+    phaseSync<SYNC, 10>();
     tick(13);
     stF(c, sslot(c, SS_INV_DT0), PRM().inv_dt);
     for (int b = 0; b < h.nb; ++b) {  // ClearForces

@@ -100,6 +100,8 @@ struct StepParams {
     const unsigned char* allowed;  // [nb][nb]: 0 = a BeginContact between these bodies aborts the world's stepping
     long long worldOffset;    // per-world calls on a sub-range (b2g_batch_select_worlds): thread w owns world w + worldOffset
     const char* stateBase;    // start of the state array (world index of a thread = f(its state pointer), see worldIndex)
+    int syncMask;             // k_step: which of its candidate phase barriers are taken (bit ID, b2g_solver.cuh: phaseSync)
+    int pad0;
 };
 
 struct ModelHeader {
