@@ -93,6 +93,8 @@ struct SavedState {
 };
 }  // namespace
 
+constexpr int kStepWarpsPerSM = 20;  // k_step: __launch_bounds__(640), 96 registers per thread
+
 struct b2g_batch {
     HostModel m;
     // the model as loaded: Box2DWorld::clone reloads the environment description (Box2DWorld.cpp:3030), so link parameters
@@ -450,21 +452,21 @@ static b2g_status createBatch(const HostModel& hostModel, int64_t n_worlds, int 
     if (envStep) b->stepBlock = atoi(envStep);
     else if (envBlock) b->stepBlock = b->block;
     else {
-        // ONE CTA per SM, sized so that the grid fills all 148 SMs evenly: with 111 registers per thread an SM holds 16
-        // warps of k_step, so the batch runs in `waves` rounds of at most 148 x 16 warps; the warps of one round are split
+        // ONE CTA per SM, sized so that the grid fills all 148 SMs evenly: with 96 registers per thread (__launch_bounds__(640))
+        // an SM holds 20 warps of k_step, so the batch runs in `waves` rounds of at most 148 x 16 warps; the warps of one round are split
         // evenly over the SMs (CTA size = any multiple of 32) instead of leaving a partly filled last round.  All warps of an
         // SM then walk the phase barriers together and share one phase's code in the instruction caches; two CTAs per SM
         // (round 1) drift against each other.  Measured, 65536 worlds, ms per 100 steps, 2 x 224 -> 1 x 448 threads per SM:
         // cfg 2 41.5 -> 38.8, cfg 3 10.5 -> 9.6, cfg 4 109.6 -> 103.0; cfg 2 x 262144 162.5 -> 151.8 (1 x 512: 40.0 / 10.0 /
         // 106.2 / 155.7; profiles/r2_block_sweep.txt).
         const long long warps = (n_worlds + 31) / 32;
-        const long long waves = (warps + sms * 16 - 1) / (sms * 16);
+        const long long waves = (warps + sms * kStepWarpsPerSM - 1) / (sms * kStepWarpsPerSM);
         long long w = (warps + waves * sms - 1) / (waves * sms);
         if (w < 1) w = 1;
-        if (w > 16) w = 16;
+        if (w > kStepWarpsPerSM) w = kStepWarpsPerSM;
         b->stepBlock = (int)(32 * w);
     }
-    if (b->stepBlock < 32 || b->stepBlock > kWorldPad || (b->stepBlock % 32)) b->stepBlock = 32;
+    if (b->stepBlock < 32 || b->stepBlock > 32 * kStepWarpsPerSM || (b->stepBlock % 32)) b->stepBlock = 32;
     // worlds per warp: a B200 has 148 x 4 warp schedulers; a batch with fewer than 592 x 16 worlds is spread over narrower
     // warps (k_step_narrow), one warp per scheduler at most, so that rare per-world events serialise fewer neighbours
     const char* envLanes = getenv("B2G_LANES");

@@ -222,7 +222,10 @@ __global__ void k_set_efforts(const __grid_constant__ ModelHeader hdr, const uin
 }
 
 // stepPhysics / rollout: nTargets segments of stepsPerTarget steps; targets == nullptr keeps the stored target
-__global__ void k_step(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
+// __launch_bounds__(640): 96 registers instead of 113 (about 100 bytes of spills in cold code), so that an SM holds 20 warps
+// instead of 16.  The kernel is latency-bound; measured on 148 CTAs (one per SM) of cfg 2, world-steps/s: 16 warps 1.85e8
+// (either register count), 20 warps 2.09e8, 24 warps at 80 registers 2.2e8 but 3 % slower below that (profiles/r2_block_sweep.txt).
+__global__ void __launch_bounds__(640) k_step(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
                        StepParams prm, int object, const float* __restrict__ targets, int nTargets, int stepsPerTarget,
                        int executeControllers, int allowSleeping) {
     // CTA-synchronised stepping: every thread of the CTA owns a world that exists in memory (the state array is padded to
