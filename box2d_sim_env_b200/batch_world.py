@@ -602,7 +602,9 @@ class BatchBox2DWorld:
 
     def setLinkProperty(self, body, prop, value):
         """Box2DLink::setMass / setGroundFrictionCoefficient / setGroundFrictionTorqueIntegral / setContactFriction
-        (:478-547) for the link with body index `body` in every world (the worlds of a batch share their model)."""
+        (:478-547) for the link with body index `body` in every SELECTED world.  The whole batch, or -- for per-world
+        parameters (domain randomisation) -- a selection that covers whole 32-world tiles (selectWorlds(first, count) with
+        first % 32 == 0 and count % 32 == 0 or first + count == n_worlds): the worlds of a tile share one parameter set."""
         _check(lib().b2g_batch_set_link_property(self.h, int(body), self.LINK_PROPERTIES[prop], float(value)))
 
     def getLinkProperty(self, body, prop):

@@ -35,21 +35,33 @@ def needs_build():
 
 
 def build(force=False, verbose=False, out=None):
+    """The kernels (b2g_kernels.cu) are compiled twice -- -DB2G_SETS=0: one model per batch, the hot path; -DB2G_SETS=1: several
+    parameter sets per batch, every warp stages the model variant of its tile (b2g_launch.h) -- in parallel, then linked with
+    the host sources."""
     global LIB
     if out:  # tuning experiments: build a variant next to the product library
         LIB = out
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "--fmad=false", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", "-o", LIB] + SOURCES + ["-ldl"]
-    if os.environ.get("B2G_DEFINES"):  # tuning experiments only, e.g. B2G_DEFINES="-DB2G_SYNC_MASK=0x3ff"
-        cmd[1:1] = os.environ["B2G_DEFINES"].split()
+    common = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "--fmad=false", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-O2"]
+    if os.environ.get("B2G_DEFINES"):  # tuning experiments only, e.g. B2G_DEFINES="-DB2G_PHASE_TIMING"
+        common[1:1] = os.environ["B2G_DEFINES"].split()
     if os.environ.get("B2G_MAXREG"):  # tuning experiments only; the product build uses the launch bounds in the source
-        cmd[1:1] = ["-maxrregcount", os.environ["B2G_MAXREG"]]
+        common[1:1] = ["-maxrregcount", os.environ["B2G_MAXREG"]]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    subprocess.check_call(cmd, cwd=CSRC)
+        common[1:1] = ["-Xptxas", "-v"]
+    objdir = os.path.join(HERE, "..", "build", "obj_" + os.path.basename(LIB).replace(".", "_"))
+    os.makedirs(objdir, exist_ok=True)
+    objs, procs = [], []
+    for sets in (0, 1):
+        obj = os.path.join(objdir, "b2g_kernels_sets%d.o" % sets)
+        objs.append(obj)
+        procs.append(subprocess.Popen(common + ["-DB2G_SETS=%d" % sets, "-c", "b2g_kernels.cu", "-o", obj], cwd=CSRC))
+    codes = [p.wait() for p in procs]
+    if any(codes):
+        raise subprocess.CalledProcessError(max(codes), "nvcc -c b2g_kernels.cu")
+    subprocess.check_call(common + ["-shared", "-o", LIB] + objs + [x for x in SOURCES if x != "b2g_kernels.cu"] + ["-ldl"], cwd=CSRC)
     return LIB
 
 

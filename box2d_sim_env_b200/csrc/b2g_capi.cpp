@@ -105,7 +105,17 @@ struct b2g_batch {
     long long selFirst = 0, selCount = 0;  // b2g_batch_select_worlds: per-world calls act on [selFirst, selFirst + selCount)
     long long n() const { return selCount; }
     bool allSelected() const { return selFirst == 0 && selCount == N; }
-    uint32_t* blob = nullptr;
+    uint32_t* blob = nullptr;   // device: sets.size() blob variants, blobStride words apart
+    // Parameter sets (b2g_batch_set_link_property on a tile-aligned selection of worlds): sets[0] is `m`; sets[v > 0] are copies of
+    // the model whose link parameters differ.  tileSet[tile] names the set the 32 worlds of a tile use (all 0 while one set).
+    std::vector<std::shared_ptr<HostModel>> extraSets;   // sets 1 ..
+    std::vector<int> tileSet;                            // host copy, one entry per tile of the padded state array
+    int* dTileSet = nullptr;
+    int blobStride = 0;
+    size_t blobCapacitySets = 0;
+    size_t nSets() const { return 1 + extraSets.size(); }
+    HostModel& set(int v) { return v == 0 ? m : *extraSets[(size_t)v - 1]; }
+    const HostModel& set(int v) const { return v == 0 ? m : *extraSets[(size_t)v - 1]; }
     float* S = nullptr;
     float* tmpl = nullptr;
     float* balls = nullptr;  // device copy of HostModel::balls (ball approximation queries)
@@ -130,11 +140,14 @@ struct b2g_batch {
         l.prm = prm;
         l.prm.worldOffset = selFirst;
         l.prm.stateBase = (const char*)S;
+        l.prm.blobStride = blobStride;
+        l.prm.tileVariant = nSets() > 1 ? dTileSet : nullptr;
+        l.prm.lead = nSets() > 1 ? (int)(selFirst & 31) : 0;
         l.stream = stream;
         l.block = block;
         l.stepBlock = stepBlock;
-        l.stepLanes = stepLanes;
-        l.stepLpw = stepLpw;
+        l.stepLanes = nSets() > 1 && stepLanes == 3 ? 4 : stepLanes;  // parameter sets: the worlds of a warp share a tile
+        l.stepLpw = nSets() > 1 ? 1 : stepLpw;                        // the sub-warp kernel serves one-model batches only
         return l;
     }
 };
@@ -502,7 +515,9 @@ static b2g_status createBatch(const HostModel& hostModel, int64_t n_worlds, int 
         return cudaFail(err, what);
     };
     if ((e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(e, "cudaStreamCreate");
-    if ((e = cudaMalloc((void**)&b->blob, b->m.blob.size() * 4)) != cudaSuccess) return cleanup(e, "cudaMalloc(model)");
+    b->blobStride = (int)((b->m.blob.size() + 3) & ~(size_t)3);
+    b->blobCapacitySets = 1;
+    if ((e = cudaMalloc((void**)&b->blob, (size_t)b->blobStride * 4)) != cudaSuccess) return cleanup(e, "cudaMalloc(model)");
     if ((e = cudaMemcpy(b->blob, b->m.blob.data(), b->m.blob.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
         return cleanup(e, "cudaMemcpy(model)");
     // state[tile][chunk][lane]: tiles of 32 worlds, 16-byte chunks (model.h)
@@ -545,6 +560,7 @@ void b2g_batch_destroy(b2g_batch* b) {
     for (auto& ev : b->eventPool) cudaEventDestroy(ev);
     b->stageA.release(); b->stageB.release(); b->stageC.release(); b->stageD.release(); b->stageE.release();
     if (b->blob) cudaFree(b->blob);
+    if (b->dTileSet) cudaFree(b->dTileSet);
     if (b->S) cudaFree(b->S);
     if (b->tmpl) cudaFree(b->tmpl);
     if (b->balls) cudaFree(b->balls);
@@ -959,18 +975,71 @@ b2g_status b2g_batch_set_link_property(b2g_batch* b, int body, int property, flo
     if (!isLinkBody(b->m, body)) return fail(B2G_ERR_INVALID, "unknown link (body 0 is the ground)");
     if (property < 0 || property > B2G_LINK_CONTACT_FRICTION)
         return fail(B2G_ERR_INVALID, "this link property is derived (read-only) or unknown");
-    if (!b->allSelected())
-        return fail(B2G_ERR_INVALID, "link parameters belong to the model all worlds of the batch share: call b2g_batch_select_worlds(batch, 0, 0) first");
     if (const char* why = badLinkValue(property, value)) return fail(B2G_ERR_INVALID, why);
     ON_DEVICE(b->device);
+    if (b->allSelected() && b->nSets() == 1) {   // one model for the whole batch: patch it in place
+        bool massCenter = false;
+        try {
+            massCenter = setLinkProperty(b->m, body, property, value);
+        } catch (const std::exception& ex) {
+            return fail(B2G_ERR_INVALID, ex.what());
+        }
+        // stream order: behind whatever still reads the old blob, ahead of the sweep-centre kernel and everything after
+        CU(cudaMemcpyAsync(b->blob, b->m.blob.data(), b->m.blob.size() * 4, cudaMemcpyHostToDevice, b->stream));
+        if (massCenter) CU(launchMassCenter(b->L(), body));
+        CU(cudaStreamSynchronize(b->stream));
+        return B2G_OK;
+    }
+    // A selection of worlds gets its own parameter set.  The worlds of a 32-world tile share one set (every warp stages the
+    // blob of its tile), so the selection has to cover whole tiles.
+    if ((b->selFirst & 31) != 0 || ((b->selCount & 31) != 0 && b->selFirst + b->selCount != b->N))
+        return fail(B2G_ERR_INVALID, "link parameters are kept per tile of 32 worlds: select a range that starts at a multiple of 32 and "
+                    "ends at a multiple of 32 or at the last world (b2g_batch_select_worlds)");
+    const size_t tiles = (size_t)paddedTiles(b->N);
+    if (b->tileSet.size() != tiles) b->tileSet.assign(tiles, 0);
+    const size_t t0 = (size_t)(b->selFirst >> 5), t1 = (size_t)((b->selFirst + b->selCount + 31) >> 5);
+    const size_t lastRealTile = (size_t)((b->N + 31) >> 5);
+    std::vector<size_t> users(b->nSets(), 0), inside(b->nSets(), 0);
+    for (size_t t = 0; t < lastRealTile; ++t) users[(size_t)b->tileSet[t]]++;
+    for (size_t t = t0; t < t1; ++t) inside[(size_t)b->tileSet[t]]++;
     bool massCenter = false;
+    std::vector<int> remap(b->nSets(), -1);
+    const size_t setsBefore = b->nSets();
     try {
-        massCenter = setLinkProperty(b->m, body, property, value);
+        for (size_t v = 0; v < setsBefore; ++v) {
+            if (inside[v] == 0) continue;
+            if (inside[v] == users[v] && v != 0) {   // every tile that uses this set is selected: patch the set itself
+                massCenter = setLinkProperty(b->set((int)v), body, property, value) || massCenter;
+                remap[v] = (int)v;
+            } else {                                 // split: the selected tiles move to a patched copy (set 0 always stays the
+                if (b->nSets() >= 65536) return fail(B2G_ERR_CAPACITY, "too many parameter sets");  // loaded-model default)
+                auto copy = std::make_shared<HostModel>(b->set((int)v));
+                massCenter = setLinkProperty(*copy, body, property, value) || massCenter;
+                b->extraSets.push_back(copy);
+                remap[v] = (int)b->nSets() - 1;
+            }
+        }
     } catch (const std::exception& ex) {
+        b->extraSets.resize(setsBefore - 1);
         return fail(B2G_ERR_INVALID, ex.what());
     }
-    // stream order: behind whatever still reads the old blob, ahead of the sweep-centre kernel and everything after
-    CU(cudaMemcpyAsync(b->blob, b->m.blob.data(), b->m.blob.size() * 4, cudaMemcpyHostToDevice, b->stream));
+    for (size_t t = t0; t < t1; ++t) b->tileSet[t] = remap[(size_t)b->tileSet[t]];
+    // device copies: all blobs (the buffer grows geometrically), the tile table
+    CU(cudaStreamSynchronize(b->stream));
+    if (b->nSets() > b->blobCapacitySets) {
+        size_t cap = b->blobCapacitySets;
+        while (cap < b->nSets()) cap *= 2;
+        uint32_t* nb = nullptr;
+        CU(cudaMalloc((void**)&nb, cap * (size_t)b->blobStride * 4));
+        cudaFree(b->blob);
+        b->blob = nb;
+        b->blobCapacitySets = cap;
+    }
+    for (size_t v = 0; v < b->nSets(); ++v)
+        CU(cudaMemcpyAsync(b->blob + v * (size_t)b->blobStride, b->set((int)v).blob.data(), b->set((int)v).blob.size() * 4,
+                           cudaMemcpyHostToDevice, b->stream));
+    if (!b->dTileSet) CU(cudaMalloc((void**)&b->dTileSet, tiles * sizeof(int)));
+    CU(cudaMemcpyAsync(b->dTileSet, b->tileSet.data(), tiles * sizeof(int), cudaMemcpyHostToDevice, b->stream));
     if (massCenter) CU(launchMassCenter(b->L(), body));
     CU(cudaStreamSynchronize(b->stream));
     return B2G_OK;
@@ -1082,7 +1151,9 @@ b2g_status b2g_batch_get_link_property(const b2g_batch* b, int body, int propert
     if (!b || !out) return fail(B2G_ERR_INVALID, "null argument");
     if (!isLinkBody(b->m, body)) return fail(B2G_ERR_INVALID, "unknown link (body 0 is the ground)");
     if (property < 0 || property >= LP_COUNT) return fail(B2G_ERR_INVALID, "unknown link property");
-    *out = getLinkProperty(b->m, body, property);
+    // several parameter sets: the value the first selected world uses
+    const int v = b->nSets() > 1 && !b->tileSet.empty() ? b->tileSet[(size_t)(b->selFirst >> 5)] : 0;
+    *out = getLinkProperty(b->set(v), body, property);
     return B2G_OK;
 }
 

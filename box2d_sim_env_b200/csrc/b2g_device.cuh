@@ -38,7 +38,7 @@ namespace b2g {
 #define B2G_ANGULAR_SLEEP_TOL (2.0f / 180.0f * B2G_PI)
 
 #define DEV __device__ __forceinline__
-#define DEVN __device__ __noinline__
+#define DEVN static __device__ __noinline__  /* static: the kernels are compiled twice (B2G_SETS), host stubs must not clash */
 
 struct V2 {
     float x, y;
@@ -154,9 +154,25 @@ DEV void tick(int id) {
 DEV void tick(int) {}
 #endif
 
+// B2G_SETS: the kernels are compiled twice (build.py, b2g_launch.h).  0: all worlds of a batch share one model, staged once
+// per CTA.  1: the batch holds several parameter sets; every warp stages the blob variant of its tile behind the previous
+// warp's copy (b2g_kernels.cu: stageModel) and model reads carry the warp's offset.
+#ifndef B2G_SETS
+#define B2G_SETS 0
+#endif
 struct Ctx {
     char* P;  // &state[tile][0][lane]: chunk k of this thread's world is the float4 at P + k * 512
+#if B2G_SETS
+    int mo;   // word offset of this warp's copy of the model blob behind the first one
+#endif
 };
+#if B2G_SETS
+#define B2G_MO(c) ((c).mo)
+#define B2G_SET_MO(c, v) ((c).mo = (v))
+#else
+#define B2G_MO(c) 0
+#define B2G_SET_MO(c, v) ((void)(v))
+#endif
 
 // per-world state access: `off` is a byte offset (chunk * 512 + word * 4, see model.h); signed so that constant
 // field offsets fold into the instruction's immediate
@@ -196,10 +212,10 @@ DEV float4 mk4(float x, float y, float z, float w) { return make_float4(x, y, z,
 // model blob access (shared memory, warp-uniform addresses: broadcast reads)
 // (the region query reads one scratch fixture record behind the blob, b2g_kernels.cu: launchObjectsInAABB)
 #define B2G_MODEL_OK(off, n) B2G_ASSERT((off) >= 0 && (off) + (n) <= H().words + 2 * MF_STRIDE && ((off) & ((n) - 1)) == 0, "model read outside the blob / misaligned", off, n)
-DEV float mF(Ctx, int off) { B2G_MODEL_OK(off, 1); return __uint_as_float(g_sm[kHdrWords + off]); }
-DEV int mI(Ctx, int off) { B2G_MODEL_OK(off, 1); return (int)g_sm[kHdrWords + off]; }
-DEV float4 m4(Ctx, int off) { B2G_MODEL_OK(off, 4); return *reinterpret_cast<const float4*>(g_sm + kHdrWords + off); }  // off % 4 == 0
-DEV float2 m2(Ctx, int off) { B2G_MODEL_OK(off, 2); return *reinterpret_cast<const float2*>(g_sm + kHdrWords + off); }  // off % 2 == 0
+DEV float mF(Ctx c, int off) { B2G_MODEL_OK(off, 1); return __uint_as_float(g_sm[kHdrWords + B2G_MO(c) + off]); }
+DEV int mI(Ctx c, int off) { B2G_MODEL_OK(off, 1); return (int)g_sm[kHdrWords + B2G_MO(c) + off]; }
+DEV float4 m4(Ctx c, int off) { B2G_MODEL_OK(off, 4); return *reinterpret_cast<const float4*>(g_sm + kHdrWords + B2G_MO(c) + off); }  // off % 4 == 0
+DEV float2 m2(Ctx c, int off) { B2G_MODEL_OK(off, 2); return *reinterpret_cast<const float2*>(g_sm + kHdrWords + B2G_MO(c) + off); }  // off % 2 == 0
 
 DEV int bslot(Ctx c, int b, int f) { return (H().cBody + b * SB_CHUNKS) * kChunkBytes + f; }
 DEV int fslot(Ctx c, int f) { return (H().cFix + f) * kChunkBytes; }

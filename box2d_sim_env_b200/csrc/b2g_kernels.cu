@@ -14,32 +14,68 @@
 #include "b2g_world.cuh"
 #include "b2g_multi.cuh"
 
+#if B2G_SETS
+#define B2G_VNS sets
+#else
+#define B2G_VNS one
+#endif
+
 namespace b2g {
+namespace B2G_VNS {
 
-// Stage header + blob into shared memory and build the per-thread context.
-#define B2G_STAGE()                                                                             \
-    {                                                                                           \
-        const uint32_t* hsrc = reinterpret_cast<const uint32_t*>(&hdr);                         \
-        const uint32_t* psrc = reinterpret_cast<const uint32_t*>(&prm);                         \
-        const int hw = (int)(sizeof(ModelHeader) / 4), pw = (int)(sizeof(StepParams) / 4);      \
-        for (int i = threadIdx.x; i < hw; i += blockDim.x) g_sm[i] = hsrc[i];                   \
-        for (int i = threadIdx.x; i < pw; i += blockDim.x) g_sm[hw + i] = psrc[i];              \
-        for (int i = threadIdx.x; i < hdr.words; i += blockDim.x) g_sm[kHdrWords + i] = blob[i]; \
-    }                                                                                           \
-    __syncthreads();                                                                            \
-    for (int j = threadIdx.x; j < hdr.nj; j += blockDim.x) { /* dt-dependent joint constants */ \
-        uint32_t* jr = g_sm + kHdrWords + hdr.oJoint + j * MJ_STRIDE;                           \
-        jr[MJ_HMAXFORCE] = __float_as_uint(prm.dt * __uint_as_float(jr[MJ_MAXFORCE]));          \
-        jr[MJ_HMAXTORQUE] = __float_as_uint(prm.dt * __uint_as_float(jr[MJ_MAXTORQUE]));        \
-    }                                                                                           \
+// Stage header + step parameters + model blob into shared memory.  One model for the whole batch: one copy per CTA, every
+// thread reads it at offset 0.  Several parameter sets (StepParams::tileVariant): every warp stages the blob variant of ITS
+// tile behind the previous warp's copy and its threads read that one (Ctx::mo); `warpWorld` = the first world of the calling
+// thread's warp.  Returns the word offset of the copy this thread reads.
+DEV int stageModel(const ModelHeader& hdr, const StepParams& prm, const uint32_t* __restrict__ blob, long long warpWorld) {
+    const uint32_t* hsrc = reinterpret_cast<const uint32_t*>(&hdr);
+    const uint32_t* psrc = reinterpret_cast<const uint32_t*>(&prm);
+    const int hw = (int)(sizeof(ModelHeader) / 4), pw = (int)(sizeof(StepParams) / 4);
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) g_sm[i] = hsrc[i];
+    for (int i = threadIdx.x; i < pw; i += blockDim.x) g_sm[hw + i] = psrc[i];
+    int mo = 0;
+    if (!B2G_SETS || prm.tileVariant == nullptr) {
+        for (int i = threadIdx.x; i < hdr.words; i += blockDim.x) g_sm[kHdrWords + i] = blob[i];
+        __syncthreads();
+        for (int j = threadIdx.x; j < hdr.nj; j += blockDim.x) {  // dt-dependent joint constants
+            uint32_t* jr = g_sm + kHdrWords + hdr.oJoint + j * MJ_STRIDE;
+            jr[MJ_HMAXFORCE] = __float_as_uint(prm.dt * __uint_as_float(jr[MJ_MAXFORCE]));
+            jr[MJ_HMAXTORQUE] = __float_as_uint(prm.dt * __uint_as_float(jr[MJ_MAXTORQUE]));
+        }
+    } else {
+        const int lane = threadIdx.x & 31;
+        mo = (int)(threadIdx.x >> 5) * prm.blobStride;
+        const uint32_t* src = blob + (size_t)prm.tileVariant[warpWorld >> 5] * prm.blobStride;
+        for (int i = lane; i < hdr.words; i += 32) g_sm[kHdrWords + mo + i] = src[i];
+        __syncwarp();
+        for (int j = lane; j < hdr.nj; j += 32) {
+            uint32_t* jr = g_sm + kHdrWords + mo + hdr.oJoint + j * MJ_STRIDE;
+            jr[MJ_HMAXFORCE] = __float_as_uint(prm.dt * __uint_as_float(jr[MJ_MAXFORCE]));
+            jr[MJ_HMAXTORQUE] = __float_as_uint(prm.dt * __uint_as_float(jr[MJ_MAXTORQUE]));
+        }
+    }
     __syncthreads();
+    return mo;
+}
 
-#define B2G_PROLOGUE()                                                                          \
-    B2G_STAGE()                                                                                 \
-    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;                       \
-    if (w >= N) return;                                                                         \
-    Ctx c;                                                                                      \
+// per-world kernels: thread g of the grid owns world g - lead + worldOffset of the selection [worldOffset, worldOffset + N)
+#if B2G_SETS
+#define B2G_PROLOGUE()                                                                                          \
+    const long long b2g_g = (long long)blockIdx.x * blockDim.x + threadIdx.x;                                   \
+    const int b2g_mo = stageModel(hdr, prm, blob, (b2g_g & ~31ll) - prm.lead + prm.worldOffset);                \
+    const long long w = b2g_g - prm.lead;                                                                       \
+    if (w < 0 || w >= N) return;                                                                                \
+    Ctx c;                                                                                                      \
+    c.P = worldBase(S, hdr.stateChunks, w + prm.worldOffset);                                                   \
+    c.mo = b2g_mo;
+#else
+#define B2G_PROLOGUE()                                                                                          \
+    stageModel(hdr, prm, blob, 0);                                                                              \
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;                                       \
+    if (w >= N) return;                                                                                         \
+    Ctx c;                                                                                                      \
     c.P = worldBase(S, hdr.stateChunks, w + prm.worldOffset);
+#endif
 
 // &state[tile][0][lane] of world w
 DEV char* worldBase(float* S, int stateChunks, long long w) {
@@ -231,9 +267,9 @@ __global__ void __launch_bounds__(640) k_step(const __grid_constant__ ModelHeade
     // CTA-synchronised stepping: every thread of the CTA owns a world that exists in memory (the state array is padded to
     // a multiple of kWorldPad worlds, the padding worlds are valid idle copies of the loaded world), so all threads walk
     // the phase barriers of stepWorld<true> together.
-    B2G_STAGE();
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     Ctx c;
+    B2G_SET_MO(c, stageModel(hdr, prm, blob, w & ~31ll));
     c.P = worldBase(S, hdr.stateChunks, w);
     for (int t = 0; t < nTargets; ++t) {
         if (targets != nullptr && w < N) {
@@ -254,12 +290,14 @@ __global__ void __launch_bounds__(640) k_step(const __grid_constant__ ModelHeade
 __global__ void k_step_narrow(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
                               StepParams prm, int object, const float* __restrict__ targets, int nTargets, int stepsPerTarget,
                               int executeControllers, int allowSleeping, int lanes) {
-    B2G_STAGE();
     const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const long long w = g * lanes + lane;
+    // with parameter sets `lanes` divides 32 (b2g_capi.cpp), so the worlds of a warp share a tile; a warp behind the batch reads tile 0
+    const int mo = stageModel(hdr, prm, blob, g * lanes < N ? g * lanes : 0);
     if (lane >= lanes || w >= N) return;
     Ctx c;
+    B2G_SET_MO(c, mo);
     c.P = worldBase(S, hdr.stateChunks, w);
     for (int t = 0; t < nTargets; ++t) {
         if (targets != nullptr) {
@@ -281,7 +319,9 @@ template <int LPW>
 __global__ void __launch_bounds__(32) k_step_multi(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
                                                    long long N, StepParams prm, int object, const float* __restrict__ targets,
                                                    int nTargets, int stepsPerTarget, int executeControllers, int allowSleeping, int wpw) {
-    B2G_STAGE();
+    StepParams prm1 = prm;   // the sub-warp kernel serves one-model batches only (b2g_capi.cpp)
+    prm1.tileVariant = nullptr;
+    stageModel(hdr, prm1, blob, 0);
     const int lane = threadIdx.x & 31;
     const int slot = lane / LPW;
     const long long w = (long long)blockIdx.x * wpw + slot;
@@ -295,6 +335,7 @@ __global__ void __launch_bounds__(32) k_step_multi(const __grid_constant__ Model
     WorldShared& W = *worldShared(hdr, slot);
     if (g.s == 0) W.keyNj = -1;  // no schedule cached yet
     Ctx c;
+    B2G_SET_MO(c, 0);
     c.P = worldBase(S, hdr.stateChunks, w);
     for (int t = 0; t < nTargets; ++t) {
         if (targets != nullptr) {
@@ -388,7 +429,12 @@ __global__ void k_at_rest(const __grid_constant__ ModelHeader hdr, const uint32_
 __global__ void k_objects_in_aabb(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
                                   StepParams prm, float lx, float ly, float ux, float uy, int fQuery,
                                   unsigned char* __restrict__ hits) {
-    B2G_STAGE();
+    {   // geometry only: every parameter set shares it, so the first blob serves all worlds (one copy per CTA, the scratch
+        // record sits behind it)
+        StepParams one = prm;
+        one.tileVariant = nullptr;
+        stageModel(hdr, one, blob, 0);
+    }
     if (threadIdx.x == 0) {
         uint32_t* r = g_sm + kHdrWords + hdr.oFix + fQuery * MF_STRIDE;
         const float hx = 0.5f * (ux - lx), hy = 0.5f * (uy - ly);  // b2AABB::GetExtents -> SetAsBox(hx, hy)
@@ -401,9 +447,10 @@ __global__ void k_objects_in_aabb(const __grid_constant__ ModelHeader hdr, const
         }
     }
     __syncthreads();
-    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= N) return;
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x - prm.lead;
+    if (w < 0 || w >= N) return;
     Ctx c;
+    B2G_SET_MO(c, 0);
     c.P = worldBase(S, hdr.stateChunks, w + prm.worldOffset);
     unsigned char h8[kMaxBodies];
     objectsInAABB(c, lx, ly, ux, uy, fQuery, h8);
@@ -590,8 +637,14 @@ __global__ void k_status(float* S, long long N, int stateChunks, int statusOff, 
 // host-side launchers
 // ---------------------------------------------------------------------------------------------------------------
 // batches may be driven from different host threads (one stream per batch): the launch counter is shared
-static std::atomic<unsigned long long> g_launches{0};
-#ifdef B2G_PHASE_TIMING
+}  // namespace B2G_VNS
+#if B2G_SETS
+extern std::atomic<unsigned long long> g_launches;
+#else
+std::atomic<unsigned long long> g_launches{0};
+#endif
+namespace B2G_VNS {
+#if defined(B2G_PHASE_TIMING) && !B2G_SETS
 extern "C" int b2g_debug_phase_cycles(unsigned long long* out32, int reset) {
     if (out32 && cudaMemcpyFromSymbol(out32, g_phaseCycles, sizeof(unsigned long long) * 32) != cudaSuccess) return 1;
     if (reset) {
@@ -601,7 +654,11 @@ extern "C" int b2g_debug_phase_cycles(unsigned long long* out32, int reset) {
     return 0;
 }
 #endif
+}  // namespace B2G_VNS
+#if !B2G_SETS
 unsigned long long launchCount() { return g_launches.load(std::memory_order_relaxed); }
+#endif
+namespace B2G_VNS {
 
 static size_t smemPad() {  // tuning knob: extra dynamic shared memory per CTA throttles occupancy (B2G_SMEM_PAD bytes)
     static long pad = -1;
@@ -611,21 +668,30 @@ static size_t smemPad() {  // tuning knob: extra dynamic shared memory per CTA t
     }
     return (size_t)pad;
 }
+// dynamic shared memory of a CTA of `threads` threads: header + parameters + one blob, or one blob per warp when the batch holds
+// several parameter sets (stageModel)
+static inline size_t smemBytes(const Launch& L, int threads) {
+    const size_t copies = L.prm.tileVariant ? (size_t)((threads + 31) / 32) : 1;
+    const size_t blob = L.prm.tileVariant ? (size_t)L.prm.blobStride : (size_t)L.h.words;
+    return (size_t)kHdrWords * 4 + copies * blob * 4 + smemPad();
+}
 static inline size_t smemBytes(const ModelHeader& h) { return (size_t)kHdrWords * 4 + (size_t)h.words * 4 + smemPad(); }
 
-static cudaError_t prepare(const void* fn, const ModelHeader& h) {
-    size_t bytes = smemBytes(h);
+static cudaError_t prepare(const void* fn, size_t bytes) {
+    if (bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
     if (bytes > 48 * 1024) return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     return cudaSuccess;
 }
+static cudaError_t prepare(const void* fn, const ModelHeader& h) { return prepare(fn, smemBytes(h)); }
 
 #define LAUNCH(kernel, ...)                                                                         \
     do {                                                                                            \
-        cudaError_t e = prepare((const void*)kernel, L.h);                                          \
-        if (e != cudaSuccess) return e;                                                             \
         int threads = L.block;                                                                      \
-        unsigned blocks = (unsigned)((L.N + threads - 1) / threads);                                \
-        kernel<<<blocks, threads, smemBytes(L.h), L.stream>>>(L.h, L.blob, L.S, L.N, L.prm, ##__VA_ARGS__); \
+        const size_t bytes = smemBytes(L, threads);                                                 \
+        cudaError_t e = prepare((const void*)kernel, bytes);                                        \
+        if (e != cudaSuccess) return e;                                                             \
+        unsigned blocks = (unsigned)((L.N + L.prm.lead + threads - 1) / threads);                   \
+        kernel<<<blocks, threads, bytes, L.stream>>>(L.h, L.blob, L.S, L.N, L.prm, ##__VA_ARGS__);  \
         ++g_launches;                                                                               \
         return cudaGetLastError();                                                                  \
     } while (0)
@@ -669,22 +735,26 @@ cudaError_t launchStep(const Launch& L, int object, const float* targets, int nT
         return cudaGetLastError();
     }
     if (L.stepLanes < 32) {  // small batch: narrow warps, one warp per CTA
-        cudaError_t e = prepare((const void*)k_step_narrow, L.h);
-        if (e != cudaSuccess) return e;
         const unsigned warps = (unsigned)((L.N + L.stepLanes - 1) / L.stepLanes);
         static const int wpc = [] { const char* e = getenv("B2G_NARROW_WARPS"); int v = e ? atoi(e) : 1; return v >= 1 && v <= 32 ? v : 1; }();
         const unsigned blocks = (warps + wpc - 1) / wpc;  // warps per CTA: tuning experiments only (default one warp per CTA)
-        k_step_narrow<<<blocks, 32 * wpc, smemBytes(L.h), L.stream>>>(L.h, L.blob, L.S, L.N, L.prm, object, targets, nTargets,
-                                                                    stepsPerTarget, execCtrl, allowSleep, L.stepLanes);
+        const size_t bytes = smemBytes(L, 32 * wpc);
+        cudaError_t e = prepare((const void*)k_step_narrow, bytes);
+        if (e != cudaSuccess) return e;
+        k_step_narrow<<<blocks, 32 * wpc, bytes, L.stream>>>(L.h, L.blob, L.S, L.N, L.prm, object, targets, nTargets,
+                                                           stepsPerTarget, execCtrl, allowSleep, L.stepLanes);
         ++g_launches;
         return cudaGetLastError();
     }
-    cudaError_t e = prepare((const void*)k_step, L.h);
-    if (e != cudaSuccess) return e;
     int threads = L.stepBlock;
+    // several parameter sets: one blob copy per warp has to fit the SM's shared memory (large scenes get smaller CTAs)
+    while (threads > 32 && smemBytes(L, threads) > 200 * 1024) threads -= 32;
+    const size_t bytes = smemBytes(L, threads);
+    cudaError_t e = prepare((const void*)k_step, bytes);
+    if (e != cudaSuccess) return e;
     unsigned blocks = (unsigned)((L.N + threads - 1) / threads);  // every thread has a (possibly padding) world
-    k_step<<<blocks, threads, smemBytes(L.h), L.stream>>>(L.h, L.blob, L.S, L.N, L.prm, object, targets, nTargets, stepsPerTarget,
-                                                       execCtrl, allowSleep);
+    k_step<<<blocks, threads, bytes, L.stream>>>(L.h, L.blob, L.S, L.N, L.prm, object, targets, nTargets, stepsPerTarget,
+                                              execCtrl, allowSleep);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -704,7 +774,7 @@ cudaError_t launchObjectsInAABB(const Launch& L, float lx, float ly, float ux, f
         if (e != cudaSuccess) return e;
     }
     int threads = L.block;
-    unsigned blocks = (unsigned)((L.N + threads - 1) / threads);
+    unsigned blocks = (unsigned)((L.N + L.prm.lead + threads - 1) / threads);
     k_objects_in_aabb<<<blocks, threads, bytes, L.stream>>>(L.h, L.blob, L.S, L.N, L.prm, lx, ly, ux, uy, fQuery, hits);
     ++g_launches;
     return cudaGetLastError();
@@ -759,4 +829,5 @@ cudaError_t launchAbortFlags(const Launch& L, int* out) {
 }
 cudaError_t launchStatus(const Launch& L, int* out) { LAUNCH(k_world_status, out); }
 
+}  // namespace B2G_VNS
 }  // namespace b2g

@@ -48,7 +48,7 @@ struct JointRec {
     int base;  // word offset of the record in the blob
 };
 DEV JointRec jrec(Ctx c, int j) { JointRec r; r.base = mjoint(c, j, 0); return r; }
-DEV int4 mi4(Ctx, int off) { B2G_MODEL_OK(off, 4); return *reinterpret_cast<const int4*>(g_sm + kHdrWords + off); }
+DEV int4 mi4(Ctx c, int off) { B2G_MODEL_OK(off, 4); return *reinterpret_cast<const int4*>(g_sm + kHdrWords + B2G_MO(c) + off); }
 DEV Vel ldVelAt(Ctx c, int boff) {
     float4 q = ld4(c, boff + SB_VEL4);
     Vel r;

@@ -101,6 +101,12 @@ struct StepParams {
     long long worldOffset;    // per-world calls on a sub-range (b2g_batch_select_worlds): thread w owns world w + worldOffset
     const char* stateBase;    // start of the state array (world index of a thread = f(its state pointer), see worldIndex)
     int syncMask;             // k_step: which of its candidate phase barriers are taken (bit ID, b2g_solver.cuh: phaseSync)
+    // Parameter sets (b2g_batch_set_link_property on a selection of worlds): the worlds of one 32-world tile share one variant
+    // of the model blob; blob variants are blobStride words apart, tileVariant[tile] picks one.  nullptr: one model for all.
+    int blobStride;
+    const int* tileVariant;
+    int lead;                 // per-world kernels on a selection whose first world is not tile-aligned: thread g owns world
+                              // g - lead + worldOffset (lead = worldOffset % 32), so that a warp never straddles two tiles
     int pad0;
 };
 

@@ -209,9 +209,14 @@ b2g_status b2g_batch_is_physically_feasible(b2g_batch* batch, int32_t* out);
  * enabled_all to every world. */
 b2g_status b2g_batch_set_link_enabled(b2g_batch* batch, int body, const uint8_t* enabled, int enabled_all);
 
-/* Box2DLink's dynamics parameters (src/sim_env/Box2DWorld.cpp:471-566).  The worlds of a batch share one model, so a
- * setter acts on link `body` (body index, 0 = ground is not a link) of EVERY world, like calling the reference's setter on
- * each of N worlds; the whole batch must be selected.
+/* Box2DLink's dynamics parameters (src/sim_env/Box2DWorld.cpp:471-566).  A setter acts on link `body` (body index, 0 = ground
+ * is not a link) of every SELECTED world, like calling the reference's setter on each of them:
+ *   - the whole batch (the default selection): the one model all worlds share is patched;
+ *   - a selection that covers whole tiles of 32 worlds (b2g_batch_select_worlds(batch, first, count) with first % 32 == 0 and
+ *     count % 32 == 0 or first + count == n_worlds): those worlds get their own PARAMETER SET -- per-world dynamics for domain
+ *     randomisation at tile granularity; the stepping kernels then stage the model variant of each warp's tile (a second
+ *     build of the kernels, 1-3 % slower than the single-model path).  Any other selection is B2G_ERR_INVALID.
+ * b2g_batch_get_link_property answers for the first selected world.
  *   MASS                    setMass :478-489 (b2Body mass and inertia scaled by mass / old mass, sweep centre re-derived,
  *                           ground-friction joint updated); no effect on the mass data of a static link, as upstream
  *   GROUND_FRICTION         setGroundFrictionCoefficient :496-500; both this and the next run updateFrictionJoint

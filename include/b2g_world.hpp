@@ -546,8 +546,9 @@ public:
         check(b2g_batch_get_link_states(_batch, out.data()));
     }
 
-    // Box2DLink's dynamics parameters (Box2DWorld.cpp:471-566) for the link with body index `body`; the worlds of a batch
-    // share their model, so a setter reaches that link in every world (and needs the whole batch selected)
+    // Box2DLink's dynamics parameters (Box2DWorld.cpp:471-566) for the link with body index `body` in every selected world:
+    // the whole batch, or -- per-world parameters at tile granularity -- a selectWorlds(first, count) range that covers whole
+    // tiles of 32 worlds (include/b2g.h)
     void setMass(int body, float mass) { check(b2g_batch_set_link_property(_batch, body, B2G_LINK_MASS, mass)); }
     void setGroundFrictionCoefficient(int body, float mu) {
         check(b2g_batch_set_link_property(_batch, body, B2G_LINK_GROUND_FRICTION, mu));

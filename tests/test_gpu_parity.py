@@ -1155,3 +1155,74 @@ def test_reset_caches_keeps_static_object_poses(b2g):
         ow.step(30)
     assert_same(batch, worlds, "30 steps after reset_caches")
     assert int(batch.contacts()[1][..., 2].sum()) > 10
+
+
+@pytest.mark.parametrize("mode", ["narrow", "full-warps"])
+def test_link_parameter_sets_per_tile(b2g, mode, monkeypatch):
+    """Per-world link parameters (reference Box2DLink::setMass / setGroundFrictionCoefficient /
+    setContactFriction :478-547 called on the links of DIFFERENT worlds): a tile-aligned selection of worlds gets its own
+    parameter set, every warp stages the blob of its tile.  Worlds of four tiles with four different parameter histories
+    stay bit-identical to oracle worlds that received the same setter calls, on the narrow-warp and on the CTA-synchronised
+    stepping kernel, through stepping, checkCollision (contacts created there mix the tile's friction) and one-world views."""
+    if mode == "full-warps":
+        monkeypatch.setenv("B2G_LANES", "32")
+        monkeypatch.setenv("B2G_STEP_BLOCK", "64")
+    n = 100   # tiles: 32 + 32 + 32 + 4
+    batch, worlds = scattered_start(b2g, ENV_A, n, seed=311)
+    robot_base = batch.model.objects[0]["first_body"]
+    obj1 = batch.model.objects[1]["first_body"]
+
+    def on(first, count, body, prop, value):
+        batch.selectWorlds(first, count)
+        batch.setLinkProperty(body, prop, value)
+        batch.selectWorlds(0, 0)
+        for ow in worlds[first:first + count]:
+            ow.set_link_property(body, prop, value)
+
+    on(32, 32, obj1, "mass", 0.31)
+    on(64, 36, obj1, "ground_friction", 0.55)
+    on(0, 32, robot_base, "mass", 2.2)
+    on(32, 68, obj1, "contact_friction", 1.4)           # splits nothing new for tile 1, patches the sets of tiles 1-3
+    on(64, 32, robot_base + 2, "mass", 0.07)             # tile 2 leaves the set it shared with tile 3
+    assert_same(batch, worlds, "right after the per-tile setters")
+    batch.stepPhysics(25)
+    for ow in worlds:
+        ow.step(25)
+    assert_same(batch, worlds, "25 steps with four parameter sets")
+    # a setter on the whole batch reaches every set
+    batch.setLinkProperty(obj1, "ground_torque_integral", 0.02)
+    for ow in worlds:
+        ow.set_link_property(obj1, "ground_torque_integral", 0.02)
+    tg = random_targets(batch.model, 0, n, seed=313)[0]
+    batch.setTargetVelocity(0, tg)
+    for w, ow in enumerate(worlds):
+        ow.set_target_velocity(0, tg[w])
+    batch.stepPhysics(30)
+    for ow in worlds:
+        ow.step(30)
+    assert_same(batch, worlds, "30 more steps after a whole-batch setter")
+    assert int(batch.contacts()[1][..., 2].sum()) > 10, "scenario has too few touching contacts"
+    # the getters answer for the first selected world's tile
+    batch.selectWorlds(40, 1)
+    assert batch.getLinkProperty(obj1, "mass") == worlds[40].get_link_property(obj1, "mass")
+    batch.selectWorlds(70, 1)
+    assert batch.getLinkProperty(obj1, "ground_friction") == worlds[70].get_link_property(obj1, "ground_friction")
+    # per-world calls on a selection that does not start at a tile boundary still read the right parameter set
+    batch.selectWorlds(45, 30)   # worlds 45..74: tiles 1 and 2
+    q, qd = batch.getWorldState()
+    for i, w in enumerate(range(45, 75)):
+        oq, oqd = worlds[w].get_state()
+        assert np.array_equal(q[i], oq) and np.array_equal(qd[i], oqd)
+    # a selection inside a tile cannot carry its own parameters
+    batch.selectWorlds(33, 10)
+    with pytest.raises(b2g.B2GError):
+        batch.setLinkProperty(obj1, "mass", 1.0)
+    batch.selectWorlds(0, 0)
+    counts, cio, cfo = batch.checkCollision(max_per_world=32)
+    for w, ow in enumerate(worlds):
+        oio, ofo = ow.check_collision()
+        assert counts[w] == len(oio) and np.array_equal(cio[w, :len(oio)], oio), "world %d: checkCollision differs" % w
+    batch.stepPhysics(10)
+    for ow in worlds:
+        ow.step(10)
+    assert_same(batch, worlds, "after checkCollision and 10 more steps")
