@@ -197,6 +197,8 @@ DEV void setTarget(const Ctx& c, int object, const float* v) {
     int n = mI(c, mobj(c, object, MO_NDOFS));
     int tOff = mI(c, mobj(c, object, MO_TARGET_OFFSET));
     const float factor = scaleToLimits(c, object, v);
+    // the scaling rule is an assumption (sim_env is absent): worlds whose results depend on it say so in their status word
+    if (factor < 1.0f) stI(c, sslot(c, SS_STATUS), ldI(c, sslot(c, SS_STATUS)) | 4);
     for (int i = 0; i < n; ++i) stF(c, tslot(c, tOff + i), factor < 1.0f ? factor * v[i] : v[i]);
     int slot = 0;
     for (int r = 0; r < H().nrobots; ++r)
@@ -363,7 +365,7 @@ __global__ void k_step_guarded(const __grid_constant__ ModelHeader hdr, const ui
 __global__ void k_world_status(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
                                StepParams prm, int* __restrict__ out) {
     B2G_PROLOGUE();
-    int st = ldI(c, sslot(c, SS_STATUS)) & 1;
+    int st = ldI(c, sslot(c, SS_STATUS)) & 5;
     bool finite = true;
     for (int b = 0; b < H().nb; ++b) {
         const float4 p = ld4(c, bslot(c, b, SB_POS4)), v = ld4(c, bslot(c, b, SB_VEL4));

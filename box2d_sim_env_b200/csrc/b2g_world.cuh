@@ -390,8 +390,10 @@ DEVN void robotControl(Ctx c, int o, int robotSlot) {
             target[i] = kp * err;
         }
         const float factor = scaleToLimits(c, o, target);
-        if (factor < 1.0f)
+        if (factor < 1.0f) {
+            stI(c, sslot(c, SS_STATUS), ldI(c, sslot(c, SS_STATUS)) | 4);  // result depends on the assumed scaling rule
             for (int i = 0; i < n; ++i) target[i] = factor * target[i];
+        }
     } else {
         for (int i = 0; i < n; ++i) target[i] = ldF(c, tslot(c, tOff + i));
     }

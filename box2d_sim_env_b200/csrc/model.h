@@ -208,7 +208,8 @@ enum ScalarState {
     SS_INV_DT0 = B2G_F(0, 0),
     SS_FLAGS = B2G_F(0, 1),      // bit0 newFixture, bit1 the TOI loop ran since the sweeps' alpha0 were last reset
     SS_NCONTACTS = B2G_F(0, 2),
-    SS_STATUS = B2G_F(0, 3),     // bit0 contact capacity exceeded, bit1 non-finite
+    SS_STATUS = B2G_F(0, 3),     // bit0 contact capacity exceeded, bit1 non-finite (computed on request), bit2 a controller target
+                                 // lay outside the velocity limits and was scaled by the ASSUMED scaleToLimits rule
     SS_MOVED_LO = B2G_F(1, 0), SS_MOVED_HI = B2G_F(1, 1),
     SS_TARGET_AVAIL = B2G_F(1, 2),  // bit r: robot r has a controller target
     SS_ABORT = B2G_F(1, 3),      // guarded stepping: bit0 a forbidden BeginContact fired, bits 8.. steps executed

@@ -164,7 +164,9 @@ b2g_status b2g_batch_clone(b2g_batch* batch, b2g_batch** out);
  * fail with B2G_ERR_INVALID while a sub-range is selected. */
 b2g_status b2g_batch_select_worlds(b2g_batch* batch, int64_t first, int64_t count);
 b2g_status b2g_batch_set_params(b2g_batch* batch, float dt, int velocity_steps, int position_steps);
-/* per-world status after the last call: 0 ok, bit0 contact capacity exceeded, bit1 non-finite state */
+/* per-world status after the last call: 0 ok, bit0 contact capacity exceeded (-> B2G_ERR_CAPACITY), bit1 non-finite state,
+ * bit2 (a note, not an error) a controller target lay outside the robot's velocity limits and was scaled: the scaling rule of
+ * sim_env's utils::eigen::scaleToLimits is an assumption here (one uniform factor), so results of such worlds depend on it */
 b2g_status b2g_batch_status(b2g_batch* batch, int32_t* out);
 void* b2g_batch_stream(b2g_batch* batch); /* cudaStream_t the batch launches on */
 b2g_status b2g_batch_sync(b2g_batch* batch);

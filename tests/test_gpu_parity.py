@@ -1226,3 +1226,21 @@ def test_link_parameter_sets_per_tile(b2g, mode, monkeypatch):
     for ow in worlds:
         ow.step(10)
     assert_same(batch, worlds, "after checkCollision and 10 more steps")
+
+
+def test_status_marks_scaled_targets(b2g):
+    """the rule that scales a target beyond the velocity limits (sim_env's scaleToLimits) is an assumption;
+    worlds whose results depend on it carry bit 2 in their status word (a note: b2g_batch_status still returns B2G_OK)."""
+    n = 8
+    batch = make_batch(b2g, ENV_A, n)
+    lim = batch.model.dof_limits()[:7, 2:4]
+    tg = np.zeros((n, 7), np.float32)
+    tg[:] = 0.5 * lim[:, 1]
+    tg[3, 0] = 3.0 * lim[0, 1]          # world 3: base x beyond the limit
+    tg[6, 5] = 2.0 * lim[5, 0]          # world 6: a finger joint below its lower limit
+    batch.setTargetVelocity(0, tg)
+    batch.stepPhysics(2)
+    assert batch.status().tolist() == [0, 0, 0, 4, 0, 0, 4, 0]
+    q, qd = batch.getWorldState()
+    batch.setWorldState(q, qd, reset_caches=True)   # a fresh clone forgets it
+    assert np.all(batch.status() == 0)

@@ -97,7 +97,7 @@ def run(seed, env_name, n=12, n_ops=40):
                     "checkCollision differs, world %d after %s" % (w, log[-6:])
             log.append("checkCollision")
         t.assert_same(batch, worlds, "seed %d %s after %s" % (seed, env_name, log[-6:]))
-    assert np.all(batch.status() == 0), "status %s" % batch.status()
+    assert np.all((batch.status() & 3) == 0), "status %s" % batch.status()   # bit 2 only notes a target beyond the limits
 
 
 if __name__ != "__main__":
