@@ -94,14 +94,13 @@ DEV Vel zeroVel() {
 }
 
 // b2FrictionJoint / b2RevoluteJoint::InitVelocityConstraints
+// (friction and revolute joints; a prismatic joint goes to prismaticInit -- the caller dispatches, so that models without
+// prismatic joints run the loops of solveIslands without the third kind: carrying its branches and calls through the hot
+// loops cost 6 % on test_env.yaml)
 DEVN void prismaticInit(Ctx c, int j, float dtRatio);
 DEVN void jointInit(Ctx c, int j, float dtRatio) {
     const int jr = mjoint(c, j, 0);
     const int4 jh = mi4(c, jr + MJ_TYPE);     // type bodyA bodyB flags
-    if (jh.x == 2) {
-        prismaticInit(c, j, dtRatio);
-        return;
-    }
     const int4 off = mi4(c, jr + MJ_SOFF);    // js jw bodyA bodyB (state byte offsets)
     const float4 arm = m4(c, jr + MJ_RA0X);   // localAnchorA - localCenterA, localAnchorB - localCenterB
     const float4 im = m4(c, jr + MJ_MA);      // mA iA mB iB
@@ -379,6 +378,10 @@ DEV void revoluteSolveVel(Ctx c, int jr, int modelFlags) {
     if (!staticA) stVelAt(c, off.z, A);
     if (!staticB) stVelAt(c, off.w, B);
 }
+
+// non-inlined copies for the velocity loop of models WITH prismatic joints (that loop is the rare one: it stays small)
+DEVN void frictionSolveVelOutlined(Ctx c, int jr) { frictionSolveVel(c, jr); }
+DEVN void revoluteSolveVelOutlined(Ctx c, int jr, int modelFlags) { revoluteSolveVel(c, jr, modelFlags); }
 
 // ---- b2PrismaticJoint (2.3.1; created by the reference at Box2DWorld.cpp:920-940) ---------------------------------------------
 // b2Mat33::Solve22 of the symmetric K = [k11 k12; k12 k22]
@@ -765,6 +768,11 @@ DEV bool revoluteSolvePos(Ctx c, int jr, int modelFlags) {
     stPosAt(c, off.z, A);
     stPosAt(c, off.w, B);
     return positionError <= B2G_LINEAR_SLOP && angularError <= B2G_ANGULAR_SLOP;
+}
+
+// position solve of a revolute or prismatic joint, out of line: the position loop of models WITH prismatic joints
+DEVN bool positionSolveOutlined(Ctx c, int jr, int type, int modelFlags) {
+    return type == 1 ? revoluteSolvePos(c, jr, modelFlags) : prismaticSolvePos(c, jr, modelFlags);
 }
 
 // ================================================================================================= contacts
@@ -1351,24 +1359,43 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
     for (int i = 0; i < L.nc; ++i) contactWarmStart(c, L.contacts[i]);
     phaseSync<SYNC, 11>();
     tick(5);
-    for (int i = 0; i < L.nj; ++i) jointInit(c, L.joints[i], dtRatio);
+    const bool prismatic = H().nPrismatic != 0;   // warp-uniform: the model is shared
+    if (!prismatic) {
+        for (int i = 0; i < L.nj; ++i) jointInit(c, L.joints[i], dtRatio);
+    } else {
+        for (int i = 0; i < L.nj; ++i) {
+            const int j = L.joints[i];
+            if (mI(c, mjoint(c, j, MJ_TYPE)) == 2) prismaticInit(c, j, dtRatio); else jointInit(c, j, dtRatio);
+        }
+    }
     tick(6);
 
     const int velIters = PRM().velIters, posIters = PRM().posIters;
     phaseSync<SYNC, 4>();
-    for (int it = 0; it < velIters; ++it) {
-        for (int i = 0; i < L.nj; ++i) {
-            const int jr = mjoint(c, L.joints[i], 0);
-            const int4 jh = mi4(c, jr + MJ_TYPE);  // type bodyA bodyB flags
-            if (jh.x == 0) {
-                frictionSolveVel(c, jr);
-            } else if (jh.x == 1) {
-                revoluteSolveVel(c, jr, jh.w);
-            } else {
-                prismaticSolveVel(c, jr, jh.w);
+    if (!prismatic) {
+        for (int it = 0; it < velIters; ++it) {
+            for (int i = 0; i < L.nj; ++i) {
+                const int jr = mjoint(c, L.joints[i], 0);
+                const int4 jh = mi4(c, jr + MJ_TYPE);  // type bodyA bodyB flags
+                if (jh.x == 0) {
+                    frictionSolveVel(c, jr);
+                } else {
+                    revoluteSolveVel(c, jr, jh.w);
+                }
             }
+            for (int i = 0; i < L.nc; ++i) contactSolveVel(c, L.contacts[i]);
         }
-        for (int i = 0; i < L.nc; ++i) contactSolveVel(c, L.contacts[i]);
+    } else {
+        for (int it = 0; it < velIters; ++it) {
+            for (int i = 0; i < L.nj; ++i) {
+                const int jr = mjoint(c, L.joints[i], 0);
+                const int4 jh = mi4(c, jr + MJ_TYPE);  // type bodyA bodyB flags
+                if (jh.x == 2) prismaticSolveVel(c, jr, jh.w);
+                else if (jh.x == 0) frictionSolveVelOutlined(c, jr);
+                else revoluteSolveVelOutlined(c, jr, jh.w);
+            }
+            for (int i = 0; i < L.nc; ++i) contactSolveVel(c, L.contacts[i]);
+        }
     }
     phaseSync<SYNC, 5>();
     tick(7);
@@ -1404,7 +1431,10 @@ DEVN void solveIslands(Ctx c, float dtRatio, bool allowSleep) {
             if (jh.x == 0) continue;
             const int isl = L.bodyIsl[(jh.w & 4) ? jh.z : jh.y];
             if (((open >> isl) & 1ull) == 0ull) continue;
-            if (!(jh.x == 1 ? revoluteSolvePos(c, jr, jh.w) : prismaticSolvePos(c, jr, jh.w))) bad |= 1ull << isl;
+            bool ok;
+            if (!prismatic) ok = revoluteSolvePos(c, jr, jh.w);
+            else ok = positionSolveOutlined(c, jr, jh.x, jh.w);
+            if (!ok) bad |= 1ull << isl;
         }
         solved |= open & ~bad;
         open &= bad;

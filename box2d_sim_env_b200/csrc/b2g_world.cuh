@@ -32,7 +32,7 @@ DEV float jointSpeed(Ctx c, int j) {
     return ldF(c, bslot(c, bB, SB_W)) - ldF(c, bslot(c, bA, SB_W));
 }
 // b2PrismaticJoint::GetJointTranslation / GetJointSpeed (:974-977, :1039-1042): reported in Box2D units, like the reference
-DEV float prismaticTranslation(Ctx c, int j) {
+DEVN float prismaticTranslation(Ctx c, int j) {  // out of line: rare, keeps the DOF getters of the controller path small
     const int jr = mjoint(c, j, 0);
     int bA = mI(c, jr + MJ_BODYA), bB = mI(c, jr + MJ_BODYB);
     V2 pA = mul(ldXF(c, bA), mk(mF(c, jr + MJ_LAX), mF(c, jr + MJ_LAY)));
@@ -41,7 +41,7 @@ DEV float prismaticTranslation(Ctx c, int j) {
     V2 axis = mul(ldXF(c, bA).q, mk(mF(c, jr + MJ_AXISX), mF(c, jr + MJ_AXISY)));
     return dot(d, axis);
 }
-DEV float prismaticSpeed(Ctx c, int j) {
+DEVN float prismaticSpeed(Ctx c, int j) {
     const int jr = mjoint(c, j, 0);
     int bA = mI(c, jr + MJ_BODYA), bB = mI(c, jr + MJ_BODYB);
     const float4 arm = m4(c, jr + MJ_RA0X);
@@ -57,8 +57,8 @@ DEV float prismaticSpeed(Ctx c, int j) {
     return dot(d, cross(wA, axis)) + dot(axis, vB + cross(wB, rB) - vA - cross(wA, rA));
 }
 // Box2DJoint::getPosition / getVelocity (:965-981, :1030-1046)
-DEV float jointPosition(Ctx c, int j) { return mI(c, mjoint(c, j, MJ_TYPE)) == 2 ? prismaticTranslation(c, j) : jointAngle(c, j); }
-DEV float jointVelocity(Ctx c, int j) { return mI(c, mjoint(c, j, MJ_TYPE)) == 2 ? prismaticSpeed(c, j) : jointSpeed(c, j); }
+DEV float jointPosition(Ctx c, int j) { return H().nPrismatic != 0 && mI(c, mjoint(c, j, MJ_TYPE)) == 2 ? prismaticTranslation(c, j) : jointAngle(c, j); }
+DEV float jointVelocity(Ctx c, int j) { return H().nPrismatic != 0 && mI(c, mjoint(c, j, MJ_TYPE)) == 2 ? prismaticSpeed(c, j) : jointSpeed(c, j); }
 DEV int objJoint(Ctx c, int o, int i) { return mI(c, H().oObjJoint + mI(c, mobj(c, o, MO_JOINT_START)) + i) & 0xffff; }
 DEV int objJointChildPos(Ctx c, int o, int i) { return mI(c, H().oObjJoint + mI(c, mobj(c, o, MO_JOINT_START)) + i) >> 16; }
 DEV V2 jointAnchorA(Ctx c, int j) {  // b2RevoluteJoint::GetAnchorA
@@ -366,6 +366,23 @@ DEV float scaleToLimits(Ctx c, int object, const float* v) {
 // ---- controller ------------------------------------------------------------------------------------------------
 // Box2DRobot::control (:2284-2310) = Box2DRobotVelocityController::control (Box2DController.cpp:65-117)
 // followed by Box2DRobot::commandEfforts (:2319-2379) and Box2DJoint::setControlTorque (:1198-1222).
+// Position controller (b2g_batch_set_target_position): the velocity target of this control step.  ASSUMED law, see robotControl.
+DEVN void positionControlTarget(Ctx c, int o, int n, int isStatic, int tOff, float* target) {
+    float q[kMaxDofsPerObject];
+    getDofPositions(c, o, q);
+    const float kp = ldF(c, tslot(c, tOff + n));
+    for (int i = 0; i < n; ++i) {
+        float err = ldF(c, tslot(c, tOff + i)) - q[i];
+        if (!isStatic && i == 2) err = err - 6.2831855f * rintf(err * 0.15915494f);
+        target[i] = kp * err;
+    }
+    const float factor = scaleToLimits(c, o, target);
+    if (factor < 1.0f) {
+        stI(c, sslot(c, SS_STATUS), ldI(c, sslot(c, SS_STATUS)) | 4);  // result depends on the assumed scaling rule
+        for (int i = 0; i < n; ++i) target[i] = factor * target[i];
+    }
+}
+
 DEVN void robotControl(Ctx c, int o, int robotSlot) {
     const int avail = ldI(c, sslot(c, SS_TARGET_AVAIL));
     if (((avail >> robotSlot) & 1) == 0) return;  // "No target available."
@@ -381,19 +398,7 @@ DEVN void robotControl(Ctx c, int o, int robotSlot) {
     // sim_env classes that are not in the tree): every control step v_target = kp * (q_target - q), the heading error of a
     // moving base wrapped to (-pi, pi], handed to setTargetVelocity (scaleToLimits included), then the velocity controller.
     if (((avail >> (8 + robotSlot)) & 1) != 0) {
-        float q[kMaxDofsPerObject];
-        getDofPositions(c, o, q);
-        const float kp = ldF(c, tslot(c, tOff + n));
-        for (int i = 0; i < n; ++i) {
-            float err = ldF(c, tslot(c, tOff + i)) - q[i];
-            if (!isStatic && i == 2) err = err - 6.2831855f * rintf(err * 0.15915494f);
-            target[i] = kp * err;
-        }
-        const float factor = scaleToLimits(c, o, target);
-        if (factor < 1.0f) {
-            stI(c, sslot(c, SS_STATUS), ldI(c, sslot(c, SS_STATUS)) | 4);  // result depends on the assumed scaling rule
-            for (int i = 0; i < n; ++i) target[i] = factor * target[i];
-        }
+        positionControlTarget(c, o, n, isStatic, tOff, target);   // out of line: the velocity-controlled path stays small
     } else {
         for (int i = 0; i < n; ++i) target[i] = ldF(c, tslot(c, tOff + i));
     }

@@ -120,6 +120,8 @@ struct ModelHeader {
     int32_t maxc;       // contact slots per world
     int32_t cBody, cFix, cJoint, cJointW, cCont, cContW, cScalar, cTarget;
     int32_t stateChunks;
+    int32_t nPrismatic;  // prismatic joints in the model: 0 lets the solver loops run without the third joint kind
+    int32_t pad0;
 };
 
 // ---- per-world state ------------------------------------------------------------------------------------

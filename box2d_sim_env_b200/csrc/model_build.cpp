@@ -614,6 +614,7 @@ void buildModel(const EnvironmentDescription& env, int maxContacts, HostModel& o
     h.nb = nb; h.nf = nf; h.nj = nj; h.no = no; h.nrobots = (int)robotOrder.size(); h.nq = nq; h.ntarget = ntarget;
     h.scale = scale;
     h.invScale = 1.0f / scale;
+    for (const auto& ob : objects) h.nPrismatic += ob.hasPrismatic ? 1 : 0;
     std::vector<uint32_t>& B = out.blob;
     B.clear();
     auto allocWords = [&](int n) { int o = (int)B.size(); B.resize(B.size() + n, 0u); return o; };
