@@ -146,7 +146,9 @@ struct b2g_batch {
         l.stream = stream;
         l.block = block;
         l.stepBlock = stepBlock;
-        l.stepLanes = nSets() > 1 && stepLanes == 3 ? 4 : stepLanes;  // parameter sets: the worlds of a warp share a tile
+        l.stepLanes = stepLanes;
+        if (nSets() > 1)  // parameter sets: the worlds of a warp share a 32-world tile, so the lane count divides 32
+            while (32 % l.stepLanes) ++l.stepLanes;
         l.stepLpw = nSets() > 1 ? 1 : stepLpw;                        // the sub-warp kernel serves one-model batches only
         return l;
     }
@@ -491,10 +493,11 @@ static b2g_status createBatch(const HostModel& hostModel, int64_t n_worlds, int 
         // contact-rich workloads, 4096 worlds, ms per 100 steps (profiles/r2_mode_sweep.txt):
         //   cfg 2: 4 -> 27.2, 6 -> 20.4, 7 -> 17.2, 8 -> 16.8, 10 -> 15.6, 12 -> 15.8, 16 -> 15.9, 24 -> 16.7, 32 -> 17.3
         //   cfg 3: 7 -> 7.8, 8 -> 7.3, 12 -> 6.0, 16 -> 5.7, 24 -> 5.7, 32 -> 5.7
-        // (10 or 12 lanes are within 2 % of 16 on cfg 2 and lose 5-12 % on cfg 3.)
+        // Re-measured after the later kernel changes (cfg 2 / cfg 3 / contact-free inputs): 10 -> 15.4 / 6.8 / 8.4, 12 -> 15.3 / 6.3 / 8.35,
+        // 16 -> 15.5 / 5.8 / 8.5: 12 worlds per warp while that fits 518 warps (the headline shape), then 16.
         const long long warpsTarget = (long long)sms * 4 * 7 / 8;  // 518 on a 148-SM B200
         long long l = (n_worlds + warpsTarget - 1) / warpsTarget;
-        b->stepLanes = l <= 4 ? (int)l : (l <= 16 ? 16 : 32);
+        b->stepLanes = l <= 4 ? (int)l : (l <= 12 ? 12 : (l <= 16 ? 16 : 32));
     }
     if (b->stepLanes < 1 || b->stepLanes > 32) b->stepLanes = 32;
     // phase barriers of k_step (b2g_solver.cuh: phaseSync); B2G_SYNC_MASK overrides for experiments
