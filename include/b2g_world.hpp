@@ -557,6 +557,23 @@ public:
         check(b2g_batch_set_link_property(_batch, body, B2G_LINK_GROUND_TORQUE_INTEGRAL, val));
     }
     void setContactFriction(int body, float mu) { check(b2g_batch_set_link_property(_batch, body, B2G_LINK_CONTACT_FRICTION, mu)); }
+    // Per-world dynamics (domain randomisation): the same setters for worlds [first, first + count) only.  The range has to
+    // cover whole tiles of 32 worlds (first % 32 == 0, count % 32 == 0 or first + count == numWorlds()): those worlds then
+    // carry their own parameter set.  getLinkPropertyOfWorld answers for one world.
+    void setLinkPropertyOfWorlds(int64_t first, int64_t count, int body, b2g_link_property property, float value) {
+        check(b2g_batch_select_worlds(_batch, first, count));
+        const b2g_status st = b2g_batch_set_link_property(_batch, body, property, value);
+        b2g_batch_select_worlds(_batch, 0, 0);
+        check(st);
+    }
+    float getLinkPropertyOfWorld(int64_t world, int body, b2g_link_property property) const {
+        float v = 0.0f;
+        check(b2g_batch_select_worlds(_batch, world, 1));
+        const b2g_status st = b2g_batch_get_link_property(_batch, body, property, &v);
+        b2g_batch_select_worlds(_batch, 0, 0);
+        check(st);
+        return v;
+    }
     float getLinkProperty(int body, b2g_link_property property) const {
         float v = 0.0f;
         check(b2g_batch_get_link_property(_batch, body, property, &v));

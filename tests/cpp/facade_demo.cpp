@@ -167,6 +167,20 @@ int main(int argc, char** argv) {
         BatchBox2DWorld* twin = batch.clone();
         bad += twin->getMass(body) != m0;
         delete twin;
+        // per-world dynamics at tile granularity: the second tile of 32 worlds gets its own mass for obj1
+        if (n >= 64) {
+            const float mAll = batch.getMass(body);
+            batch.setLinkPropertyOfWorlds(32, 32, body, B2G_LINK_MASS, 3.0f * m0);
+            bad += batch.getLinkPropertyOfWorld(40, body, B2G_LINK_MASS) != 3.0f * m0;
+            bad += batch.getLinkPropertyOfWorld(5, body, B2G_LINK_MASS) != mAll || batch.getLinkPropertyOfWorld(31, body, B2G_LINK_MASS) != mAll;
+            bool insideTileThrew = false;
+            try {
+                batch.setLinkPropertyOfWorlds(33, 4, body, B2G_LINK_MASS, 1.0f);
+            } catch (const std::exception&) {
+                insideTileThrew = true;
+            }
+            bad += !insideTileThrew;
+        }
         batch.stepPhysics(2);
         bool groundThrew = false;
         try {
