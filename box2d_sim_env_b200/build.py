@@ -62,6 +62,7 @@ def build(force=False, verbose=False, out=None):
     if any(codes):
         raise subprocess.CalledProcessError(max(codes), "nvcc -c b2g_kernels.cu")
     subprocess.check_call(common + ["-shared", "-o", LIB] + objs + [x for x in SOURCES if x != "b2g_kernels.cu"] + ["-ldl"], cwd=CSRC)
+    shutil.rmtree(objdir, ignore_errors=True)   # the objects are not needed again (and would travel to the GPU box with the tree)
     return LIB
 
 
