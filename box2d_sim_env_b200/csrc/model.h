@@ -61,8 +61,13 @@ enum JointField {
     MJ_ROTMASS,                            // m = iA + iB; if (m > 0) m = 1 / m: b2FrictionJoint::m_angularMass / b2RevoluteJoint::m_motorMass
     MJ_AXISY,
     MJ_MA, MJ_IA, MJ_MB, MJ_IB,            // invMass / invI of bodyA and bodyB
+    // 36 words, not 32: with a 128-byte stride the same field of every joint sits in the same shared-memory banks, and lanes
+    // that read DIFFERENT joints (the one-body islands of a clutter scene, worlds whose lists differ) serialise 8 ways per
+    // LDS.128; 36 = 4 (mod 32) spreads eight consecutive records over all 32 banks (body records: 20 words, fixtures: 44)
+    MJ_PAD0, MJ_PAD1, MJ_PAD2, MJ_PAD3,
     MJ_STRIDE
 };
+static_assert(MJ_STRIDE == 36, "joint record stride");
 enum ObjectField {
     MO_STATIC = 0, MO_ROBOT, MO_BASE_BODY, MO_NDOFS, MO_DOF_OFFSET,
     MO_LINK_START,   // first entry of this object's pre-order link list
