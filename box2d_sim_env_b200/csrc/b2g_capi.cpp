@@ -998,7 +998,7 @@ b2g_status b2g_batch_set_link_property(b2g_batch* b, int body, int property, flo
     if ((b->selFirst & 31) != 0 || ((b->selCount & 31) != 0 && b->selFirst + b->selCount != b->N))
         return fail(B2G_ERR_INVALID, "link parameters are kept per tile of 32 worlds: select a range that starts at a multiple of 32 and "
                     "ends at a multiple of 32 or at the last world (b2g_batch_select_worlds)");
-    const size_t tiles = (size_t)paddedTiles(b->N);
+    const size_t tiles = ((size_t)paddedTiles(b->N) * kTileWorlds + 31) / 32;   // parameter-set tiles are always 32 worlds
     if (b->tileSet.size() != tiles) b->tileSet.assign(tiles, 0);
     const size_t t0 = (size_t)(b->selFirst >> 5), t1 = (size_t)((b->selFirst + b->selCount + 31) >> 5);
     const size_t lastRealTile = (size_t)((b->N + 31) >> 5);

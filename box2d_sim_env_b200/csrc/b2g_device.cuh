@@ -194,7 +194,7 @@ struct Ctx {
 template <int BYTES>
 DEV char* spn(Ctx c, int off) {
     __builtin_assume(__isGlobal(c.P));
-    B2G_ASSERT(off >= 0 && (off & 511) + BYTES <= 16 && (off >> 9) < H().stateChunks && (off & (BYTES - 1)) == 0,
+    B2G_ASSERT(off >= 0 && (off % kChunkBytes) + BYTES <= 16 && (off / kChunkBytes) < H().stateChunks && (off & (BYTES - 1)) == 0,
                "state access outside the world's chunks / misaligned", off, BYTES);
     return c.P + off;
 }

@@ -79,7 +79,7 @@ DEV int stageModel(const ModelHeader& hdr, const StepParams& prm, const uint32_t
 
 // &state[tile][0][lane] of world w
 DEV char* worldBase(float* S, int stateChunks, long long w) {
-    return reinterpret_cast<char*>(S) + (size_t)(w >> 5) * ((size_t)stateChunks * kChunkBytes) + (size_t)(w & 31) * 16;
+    return reinterpret_cast<char*>(S) + (size_t)(w >> kTileShift) * ((size_t)stateChunks * kChunkBytes) + (size_t)(w & (kTileWorlds - 1)) * 16;
 }
 
 __global__ void k_init(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S,
@@ -91,11 +91,11 @@ __global__ void k_init(const __grid_constant__ ModelHeader hdr, const uint32_t* 
 // broadcast the state of a template world (stored [chunk]) to worlds [first, first + count):
 // state[tile][chunk][lane] = tmpl[chunk]; walks whole tiles so that every store instruction is a coalesced 512-byte row
 __global__ void k_broadcast(float4* S, const float4* __restrict__ tmpl, long long first, long long count, int chunks) {
-    const long long tile0 = first >> 5, tile1 = (first + count + 31) >> 5;
+    const long long tile0 = first >> kTileShift, tile1 = (first + count + kTileWorlds - 1) >> kTileShift;
     const long long total = (tile1 - tile0) * chunks * kTileWorlds;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long world = ((tile0 + i / ((long long)chunks * kTileWorlds)) << 5) + (i & 31);
-        if (world >= first && world < first + count) S[tile0 * chunks * kTileWorlds + i] = tmpl[(i >> 5) % chunks];
+        const long long world = ((tile0 + i / ((long long)chunks * kTileWorlds)) << kTileShift) + (i & (kTileWorlds - 1));
+        if (world >= first && world < first + count) S[tile0 * chunks * kTileWorlds + i] = tmpl[(i >> kTileShift) % chunks];
     }
 }
 
@@ -111,7 +111,7 @@ __global__ void k_park(const __grid_constant__ ModelHeader hdr, const uint32_t* 
 }
 
 __global__ void k_extract_world(const float4* S, float4* tmpl, int chunks, long long world) {
-    const float4* base = S + (size_t)(world >> 5) * ((size_t)chunks * kTileWorlds) + (world & 31);
+    const float4* base = S + (size_t)(world >> kTileShift) * ((size_t)chunks * kTileWorlds) + (world & (kTileWorlds - 1));
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += gridDim.x * blockDim.x) tmpl[i] = base[(size_t)i * kTileWorlds];
 }
 
@@ -800,7 +800,7 @@ cudaError_t launchCheckCollision(const Launch& L, int* counts, int* iout, float*
 }
 cudaError_t launchBroadcast(const Launch& L, const float* tmpl) {  // worlds [prm.worldOffset, prm.worldOffset + N)
     const long long first = L.prm.worldOffset, count = L.N;
-    long long total = (((first + count + 31) >> 5) - (first >> 5)) * L.h.stateChunks * kTileWorlds;
+    long long total = (((first + count + kTileWorlds - 1) >> kTileShift) - (first >> kTileShift)) * L.h.stateChunks * kTileWorlds;
     int threads = 256;
     long long want = (total + threads - 1) / threads;
     unsigned blocks = (unsigned)(want < 4096 ? want : 4096);  // grid-stride copy: a few CTAs per SM saturate HBM

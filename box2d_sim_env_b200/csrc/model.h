@@ -135,14 +135,22 @@ struct ModelHeader {
 // LDG.128 / STG.128, and all chunks of a tile are contiguous, so a thread reaches any word of its world at
 //     base(tile, lane) + chunk * 512 + word * 4
 // Field enumerators below are such byte offsets relative to the first chunk of their record.
-constexpr int kTileWorlds = 32;
+// B2G_STATE_TILE (build-time experiment, default 32): worlds per tile of the state array.  32 = a warp's access to one chunk is
+// one 512-byte row.  Smaller tiles (4, 8) make a row 64 / 128 bytes: dense access then touches 8 / 4 rows per chunk, sparse
+// access (few worlds of a warp have a body awake) fetches less around what it needs.
+#ifndef B2G_STATE_TILE
+#define B2G_STATE_TILE 32
+#endif
+constexpr int kTileWorlds = B2G_STATE_TILE;
+constexpr int kTileShift = kTileWorlds == 32 ? 5 : kTileWorlds == 16 ? 4 : kTileWorlds == 8 ? 3 : kTileWorlds == 4 ? 2 : kTileWorlds == 2 ? 1 : 0;
+static_assert((1 << kTileShift) == kTileWorlds, "B2G_STATE_TILE must be a power of two <= 32");
 constexpr int kWorldPad = 1024;  // the largest CTA of k_step
 // Tiles of the state array of an n-world batch: n rounded up to a multiple of kWorldPad plus one more kWorldPad worlds.
 // The padding worlds are valid idle copies of the loaded world: every thread of every k_step CTA (any CTA size that is a
 // multiple of 32 up to kWorldPad) owns a world that exists in memory and can take part in the phase barriers.
-inline long long paddedTiles(long long n) { return ((n + kWorldPad - 1) / kWorldPad + 1) * (kWorldPad / 32); }
+inline long long paddedTiles(long long n) { return ((n + kWorldPad - 1) / kWorldPad + 1) * (kWorldPad / kTileWorlds); }
 constexpr int kChunkBytes = 16 * kTileWorlds;  // 512
-#define B2G_F(chunk, word) ((chunk) * 512 + (word) * 4)
+#define B2G_F(chunk, word) ((chunk) * (16 * B2G_STATE_TILE) + (word) * 4)
 
 enum BodyState {
     SB_PX = B2G_F(0, 0), SB_PY = B2G_F(0, 1), SB_QS = B2G_F(0, 2), SB_QC = B2G_F(0, 3),    // b2Body::m_xf
