@@ -93,7 +93,8 @@ struct SavedState {
 };
 }  // namespace
 
-constexpr int kStepWarpsPerSM = 20;  // k_step: __launch_bounds__(640), 96 registers per thread
+constexpr int kStepWarpsPerSM = 20;      // k_step<640>: 96 registers per thread
+constexpr int kStepWarpsPerSMBig = 28;   // k_step<896>: 72 registers per thread, batches that need more than 20 warps per SM
 
 struct b2g_batch {
     HostModel m;
@@ -475,13 +476,15 @@ static b2g_status createBatch(const HostModel& hostModel, int64_t n_worlds, int 
         // cfg 2 41.5 -> 38.8, cfg 3 10.5 -> 9.6, cfg 4 109.6 -> 103.0; cfg 2 x 262144 162.5 -> 151.8 (1 x 512: 40.0 / 10.0 /
         // 106.2 / 155.7; profiles/r2_block_sweep.txt).
         const long long warps = (n_worlds + 31) / 32;
-        const long long waves = (warps + sms * kStepWarpsPerSM - 1) / (sms * kStepWarpsPerSM);
+        // batches beyond one wave of 20 warps per SM run the 72-register kernel with up to 28 warps per SM (b2g_kernels.cu: k_step)
+        const long long cap = warps <= (long long)sms * kStepWarpsPerSM ? kStepWarpsPerSM : kStepWarpsPerSMBig;
+        const long long waves = (warps + sms * cap - 1) / (sms * cap);
         long long w = (warps + waves * sms - 1) / (waves * sms);
         if (w < 1) w = 1;
-        if (w > kStepWarpsPerSM) w = kStepWarpsPerSM;
+        if (w > cap) w = cap;
         b->stepBlock = (int)(32 * w);
     }
-    if (b->stepBlock < 32 || b->stepBlock > 32 * kStepWarpsPerSM || (b->stepBlock % 32)) b->stepBlock = 32;
+    if (b->stepBlock < 32 || b->stepBlock > 32 * kStepWarpsPerSMBig || (b->stepBlock % 32)) b->stepBlock = 32;
     // worlds per warp: a B200 has 148 x 4 warp schedulers; a batch with fewer than 592 x 16 worlds is spread over narrower
     // warps (k_step_narrow), one warp per scheduler at most, so that rare per-world events serialise fewer neighbours
     const char* envLanes = getenv("B2G_LANES");

@@ -260,10 +260,15 @@ __global__ void k_set_efforts(const __grid_constant__ ModelHeader hdr, const uin
 }
 
 // stepPhysics / rollout: nTargets segments of stepsPerTarget steps; targets == nullptr keeps the stored target
-// __launch_bounds__(640): 96 registers instead of 113 (about 100 bytes of spills in cold code), so that an SM holds 20 warps
-// instead of 16.  The kernel is latency-bound; measured on 148 CTAs (one per SM) of cfg 2, world-steps/s: 16 warps 1.85e8
-// (either register count), 20 warps 2.09e8, 24 warps at 80 registers 2.2e8 but 3 % slower below that (profiles/r2_block_sweep.txt).
-__global__ void __launch_bounds__(640) k_step(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
+// Two register budgets (the kernel is latency-bound: more resident warps hide more, up to a point where spills cost more):
+//   k_step<640>: 96 registers (about 100 bytes of spills in cold code), up to 20 warps per SM -- batches up to 148 x 640 worlds
+//   k_step<896>: 72 registers, up to 28 warps per SM -- larger batches
+// Measured on 148 CTAs (one per SM) of cfg 2, world-steps/s: 16 warps 1.85e8 (113 or 96 registers), 20 warps at 96 registers
+// 2.09e8, 24 warps at 80 2.2e8, 28 warps at 72 2.36e8, 32 warps at 64 2.34e8; at 14 warps per SM (65536 worlds) 96 registers
+// take 38.4 ms, 72 registers 41.6 ms (profiles/r2_block_sweep.txt).  131072 worlds: 76.9 ms in two waves of 14 warps -> 56.4 ms
+// in one wave of 28; 1 Mi worlds 505 -> 431 ms.
+template <int BOUNDS>
+__global__ void __launch_bounds__(BOUNDS) k_step(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
                        StepParams prm, int object, const float* __restrict__ targets, int nTargets, int stepsPerTarget,
                        int executeControllers, int allowSleeping) {
     // CTA-synchronised stepping: every thread of the CTA owns a world that exists in memory (the state array is padded to
@@ -752,11 +757,25 @@ cudaError_t launchStep(const Launch& L, int object, const float* targets, int nT
     // several parameter sets: one blob copy per warp has to fit the SM's shared memory (large scenes get smaller CTAs)
     while (threads > 32 && smemBytes(L, threads) > 200 * 1024) threads -= 32;
     const size_t bytes = smemBytes(L, threads);
-    cudaError_t e = prepare((const void*)k_step, bytes);
+#if B2G_SETS
+    if (threads > 640) threads = 640;   // the parameter-set build carries the 96-register kernel only
+#else
+    if (threads > 640) {
+        cudaError_t e = prepare((const void*)k_step<896>, bytes);
+        if (e != cudaSuccess) return e;
+        unsigned blocks = (unsigned)((L.N + threads - 1) / threads);  // every thread has a (possibly padding) world
+        k_step<896><<<blocks, threads, bytes, L.stream>>>(L.h, L.blob, L.S, L.N, L.prm, object, targets, nTargets, stepsPerTarget,
+                                                       execCtrl, allowSleep);
+        ++g_launches;
+        return cudaGetLastError();
+    }
+#endif
+    const size_t bytes640 = smemBytes(L, threads);
+    cudaError_t e = prepare((const void*)k_step<640>, bytes640);
     if (e != cudaSuccess) return e;
     unsigned blocks = (unsigned)((L.N + threads - 1) / threads);  // every thread has a (possibly padding) world
-    k_step<<<blocks, threads, bytes, L.stream>>>(L.h, L.blob, L.S, L.N, L.prm, object, targets, nTargets, stepsPerTarget,
-                                              execCtrl, allowSleep);
+    k_step<640><<<blocks, threads, bytes640, L.stream>>>(L.h, L.blob, L.S, L.N, L.prm, object, targets, nTargets, stepsPerTarget,
+                                                      execCtrl, allowSleep);
     ++g_launches;
     return cudaGetLastError();
 }
