@@ -439,11 +439,13 @@ def test_region_query_and_feasibility(b2g):
     assert_same(batch, worlds, "after isPhysicallyFeasible (runs UpdateContacts)")
 
 
-@pytest.mark.parametrize("env_name,n,step_block", [(ENV_A, 20000, None), (ENV_B, 12345, None), (ENV_A, 19999, 224), (ENV_B, 20001, 96)])
+@pytest.mark.parametrize("env_name,n,step_block", [(ENV_A, 20000, None), (ENV_B, 12345, None), (ENV_A, 19999, 224), (ENV_B, 20001, 96),
+                                                   (ENV_A, 95001, None), (ENV_B, 96000, 896)])
 def test_large_batch_full_warp_path(b2g, env_name, n, step_block, monkeypatch):
     """Batches large enough for the full-warp, CTA-synchronised stepping kernel (phase barriers, parked padding worlds in
     the last CTA; small batches use the narrow-warp kernel), with the CTA size of the heuristic and with explicit
-    non-power-of-two CTA sizes: final states of a 60-step rollout, all worlds, bit-exact."""
+    non-power-of-two CTA sizes: final states of a 60-step rollout, all worlds, bit-exact.  The two batches beyond 94720
+    worlds run the second instantiation of the kernel (72 registers, CTAs of up to 896 threads)."""
     from oracle import b2o
     if step_block:
         monkeypatch.setenv("B2G_STEP_BLOCK", str(step_block))
