@@ -118,6 +118,10 @@ struct b2g_batch {
     HostModel& set(int v) { return v == 0 ? m : *extraSets[(size_t)v - 1]; }
     const HostModel& set(int v) const { return v == 0 ? m : *extraSets[(size_t)v - 1]; }
     float* S = nullptr;
+    // regrouped rollouts (regroupedRollout): the second state array the worlds are sorted into, the slot <-> world tables
+    float* S2 = nullptr;
+    size_t stateBytes = 0;
+    DevBuf rgKey, rgNewSlot, rgWorldOfA, rgWorldOfB, rgCount, rgTargets;
     float* tmpl = nullptr;
     float* balls = nullptr;  // device copy of HostModel::balls (ball approximation queries)
     cudaStream_t stream = nullptr;
@@ -531,6 +535,7 @@ static b2g_status createBatch(const HostModel& hostModel, int64_t n_worlds, int 
     // take part in the phase barriers
     size_t tiles = (size_t)paddedTiles(n_worlds);
     size_t stateBytes = tiles * (size_t)b->m.h.stateChunks * kChunkBytes;
+    b->stateBytes = stateBytes;
     if ((e = cudaMalloc((void**)&b->S, stateBytes)) != cudaSuccess) return cleanup(e, "cudaMalloc(state)");
     if ((e = cudaMalloc((void**)&b->tmpl, (size_t)b->m.h.stateChunks * 16)) != cudaSuccess) return cleanup(e, "cudaMalloc(template)");
     // build the freshly loaded world once (world 0), keep its chunks as the template, broadcast to every world
@@ -565,9 +570,11 @@ void b2g_batch_destroy(b2g_batch* b) {
     for (auto& p : b->timed) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto& ev : b->eventPool) cudaEventDestroy(ev);
     b->stageA.release(); b->stageB.release(); b->stageC.release(); b->stageD.release(); b->stageE.release();
+    b->rgKey.release(); b->rgNewSlot.release(); b->rgWorldOfA.release(); b->rgWorldOfB.release(); b->rgCount.release(); b->rgTargets.release();
     if (b->blob) cudaFree(b->blob);
     if (b->dTileSet) cudaFree(b->dTileSet);
     if (b->S) cudaFree(b->S);
+    if (b->S2) cudaFree(b->S2);
     if (b->tmpl) cudaFree(b->tmpl);
     if (b->balls) cudaFree(b->balls);
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -827,6 +834,56 @@ b2g_status b2g_batch_set_control_efforts(b2g_batch* b, int object, const float* 
     return B2G_OK;
 }
 
+// Large rollouts, OPT-IN (B2G_REGROUP=1; measured: it does not pay): before every target segment the worlds are
+// sorted by island shape into the other state array (b2g_kernels.cu: k_regroup_*), so that the worlds of a warp walk the same
+// joint lists; after the last segment they go back to slot == world.  Single-model batches in the full-warp regime only.
+static bool regroupWanted(const b2g_batch* b, const float* targets, int nTargets, int stepsPerTarget) {
+    const char* env = getenv("B2G_REGROUP");
+    const int mode = env ? atoi(env) : 0;
+    return mode != 0 && targets != nullptr && nTargets >= 2 && stepsPerTarget >= 5 && b->nSets() == 1 && b->stepLpw == 1 &&
+           b->stepLanes == 32 && b->N >= 32768 && b->prm.recMode == 0;
+}
+
+static cudaError_t regroupedRollout(b2g_batch* b, int object, const float* targets, int nTargets, int stepsPerTarget, int execCtrl,
+                                    int allowSleep) {
+    cudaError_t e;
+    const int nd = b->m.objects[object].nDofs;
+    const size_t n = (size_t)b->N;
+    if (!b->S2) {
+        if ((e = cudaMalloc((void**)&b->S2, b->stateBytes)) != cudaSuccess) return e;
+        // whole array once: the parked padding worlds behind the batch have to exist in both arrays
+        if ((e = cudaMemcpyAsync(b->S2, b->S, b->stateBytes, cudaMemcpyDeviceToDevice, b->stream)) != cudaSuccess) return e;
+    }
+    if ((e = b->rgKey.reserve(n)) != cudaSuccess || (e = b->rgNewSlot.reserve(n * 4)) != cudaSuccess ||
+        (e = b->rgWorldOfA.reserve(n * 4)) != cudaSuccess || (e = b->rgWorldOfB.reserve(n * 4)) != cudaSuccess ||
+        (e = b->rgTargets.reserve(n * nd * 4)) != cudaSuccess)
+        return e;
+    // worlds are sorted inside the slot range of one CTA of the stepping kernel (B2G_REGROUP_GROUP overrides: 0 = the whole batch)
+    const char* groupStr = getenv("B2G_REGROUP_GROUP");
+    const long long groupEnv = groupStr ? atoll(groupStr) : -1ll;
+    const int groupSize = groupEnv < 0 ? b->stepBlock : (groupEnv == 0 ? (int)std::min<long long>(b->N, 1ll << 30) : (int)groupEnv);
+    const size_t groups = (n + groupSize - 1) / groupSize;
+    if ((e = b->rgCount.reserve(groups * 64 * 4)) != cudaSuccess) return e;
+    int* worldOf = (int*)b->rgWorldOfA.p;
+    int* worldOfNext = (int*)b->rgWorldOfB.p;
+    int* count = (int*)b->rgCount.p;
+    int* cursor = count + groups * 32;
+    if ((e = one::launchRegroupIota(b->L(), worldOf)) != cudaSuccess) return e;
+    for (int t = 0; t < nTargets; ++t) {
+        if ((e = one::launchRegroupKey(b->L(), (unsigned char*)b->rgKey.p, count, groupSize)) != cudaSuccess) return e;
+        if ((e = one::launchRegroupAssign(b->L(), (const unsigned char*)b->rgKey.p, count, cursor, (int*)b->rgNewSlot.p, groupSize)) != cudaSuccess) return e;
+        if ((e = one::launchRegroupMove(b->L(), b->S, b->S2, (const int*)b->rgNewSlot.p, worldOf, worldOfNext)) != cudaSuccess) return e;
+        std::swap(b->S, b->S2);
+        std::swap(worldOf, worldOfNext);
+        if ((e = one::launchRegroupTargets(b->L(), targets + (size_t)t * n * nd, (float*)b->rgTargets.p, worldOf, nd)) != cudaSuccess) return e;
+        if ((e = launchStep(b->L(), object, (const float*)b->rgTargets.p, 1, stepsPerTarget, execCtrl, allowSleep)) != cudaSuccess) return e;
+    }
+    // back to slot == world: the slot -> world table is the destination of every slot
+    if ((e = one::launchRegroupMove(b->L(), b->S, b->S2, worldOf, worldOf, worldOfNext)) != cudaSuccess) return e;
+    std::swap(b->S, b->S2);
+    return cudaSuccess;
+}
+
 static b2g_status timedStep(b2g_batch* b, int object, const float* targets, int nTargets, int stepsPerTarget, int execCtrl,
                             int allowSleep) {
     if (b->timed.size() >= kMaxTimed) {  // nobody collected the timings: forget the oldest launch, reuse its events
@@ -838,7 +895,9 @@ static b2g_status timedStep(b2g_batch* b, int object, const float* targets, int 
     cudaError_t e = getEvent(b, &e0);
     if (e == cudaSuccess) e = getEvent(b, &e1);
     if (e == cudaSuccess) e = cudaEventRecord(e0, b->stream);
-    if (e == cudaSuccess) e = launchStep(b->L(), object, targets, nTargets, stepsPerTarget, execCtrl, allowSleep);
+    if (e == cudaSuccess)
+        e = regroupWanted(b, targets, nTargets, stepsPerTarget) ? regroupedRollout(b, object, targets, nTargets, stepsPerTarget, execCtrl, allowSleep)
+                                                                 : launchStep(b->L(), object, targets, nTargets, stepsPerTarget, execCtrl, allowSleep);
     if (e == cudaSuccess) e = cudaEventRecord(e1, b->stream);
     if (e != cudaSuccess) {  // the events go back to the pool, nothing is leaked on the error path
         if (e0) b->eventPool.push_back(e0);

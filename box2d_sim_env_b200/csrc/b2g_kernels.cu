@@ -644,6 +644,102 @@ __global__ void k_status(float* S, long long N, int stateChunks, int statusOff, 
 // host-side launchers
 // ---------------------------------------------------------------------------------------------------------------
 // batches may be driven from different host threads (one stream per batch): the launch counter is shared
+#if !B2G_SETS
+// ---- regrouping worlds by island shape (large batches, b2g_capi.cpp: regroupedRollout) ----------------------------------------
+// The worlds of a warp execute the union of their paths: a world whose box sits in the robot's island walks a different joint
+// list, runs the contact solver and more position iterations, and every other lane of its warp waits.  Between the target
+// segments of a rollout the worlds are therefore SORTED by a key that predicts their path over the next steps -- live contacts
+// or not, which robot link a touching contact enters the robot through, whether a static body is involved (TOI candidates) --
+// and their state moves to the slot the sort assigns (a second state array; slot != world until the rollout ends, the
+// controller targets of a segment are gathered into slot order).  Worlds are independent: results are bit-identical.
+constexpr int kRegroupClasses = 32;
+
+__global__ void k_regroup_key(const __grid_constant__ ModelHeader hdr, const uint32_t* __restrict__ blob, float* S, long long N,
+                              StepParams prm, unsigned char* __restrict__ key, int* __restrict__ count, int groupSize) {
+    B2G_PROLOGUE();
+    const int n = contactCount(c);
+    int entry = 0, staticLive = 0, live = 0;
+    for (int k = 0; k < n; ++k) {
+        const int fl = ldI(c, cslot(c, k, SC_FLAGS));
+        if ((fl & CF_ENABLED) == 0) continue;
+        int fA, fB;
+        contactFixtures(c, k, fA, fB);
+        const int bA = mI(c, mfix(c, fA, MF_BODY)), bB = mI(c, mfix(c, fB, MF_BODY));
+        live = 1;
+        if (bodyType(c, bA) == 0 || bodyType(c, bB) == 0) staticLive = 1;
+        if (fl & CF_TOUCHING) {
+            const int lowBody = bA < bB ? bA : bB;   // the older body: for robot-vs-object contacts the robot link the DFS enters through
+            const int e = 1 + (lowBody % 13);
+            entry = entry == 0 || e < entry ? e : entry;
+        }
+    }
+    // 0: no contact at all; 1: live contacts, none touching; 2..14: touching, by entry link; + 16 with a static body involved
+    const int cls = (live ? (entry ? 1 + entry : 1) : 0) + (staticLive ? 16 : 0);
+    key[w] = (unsigned char)cls;
+    // worlds are sorted inside groups of `groupSize` consecutive slots (one CTA of the stepping kernel): every SM keeps its mix
+    // of cheap and expensive worlds, only the warps inside it become homogeneous
+    const int slot = (int)(w / groupSize) * kRegroupClasses + cls;
+    const unsigned m = __match_any_sync(__activemask(), slot);
+    if ((int)(threadIdx.x & 31) == __ffs((int)m) - 1) atomicAdd(&count[slot], __popc(m));
+}
+
+// exclusive scan of the class counts: cursor[c] = first slot of class c (classes in ascending order)
+__global__ void k_regroup_scan(const int* __restrict__ count, int* __restrict__ cursor, int groups, int groupSize) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) return;
+    int s = g * groupSize;
+    for (int i = 0; i < kRegroupClasses; ++i) {
+        cursor[g * kRegroupClasses + i] = s;
+        s += count[g * kRegroupClasses + i];
+    }
+}
+
+__global__ void k_regroup_assign(const unsigned char* __restrict__ key, int* __restrict__ cursor, int* __restrict__ newSlot, long long N,
+                                 int groupSize) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= N) return;
+    const int cls = (int)(w / groupSize) * kRegroupClasses + key[w];
+    const unsigned m = __match_any_sync(__activemask(), cls);
+    const int lane = threadIdx.x & 31, leader = __ffs((int)m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&cursor[cls], __popc(m));
+    base = __shfl_sync(m, base, leader);
+    newSlot[w] = base + __popc(m & ((1u << lane) - 1u));
+}
+
+__global__ void k_regroup_iota(int* __restrict__ a, long long N) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < N) a[w] = (int)w;
+}
+
+// state of slot s of `src` -> slot newSlot[s] of `dst`: everything but the unused contact slots and the contact scratch (dead
+// between steps); worldOfDst[newSlot[s]] = worldOfSrc[s]
+__global__ void k_regroup_move(const __grid_constant__ ModelHeader hdr, const float4* __restrict__ src, float4* __restrict__ dst,
+                               const int* __restrict__ newSlot, const int* __restrict__ worldOfSrc, int* __restrict__ worldOfDst,
+                               long long N) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    const long long d = newSlot[s];
+    const size_t tileChunks = (size_t)hdr.stateChunks * kTileWorlds;
+    const float4* ps = src + (size_t)(s >> kTileShift) * tileChunks + (size_t)(s & (kTileWorlds - 1));
+    float4* pd = dst + (size_t)(d >> kTileShift) * tileChunks + (size_t)(d & (kTileWorlds - 1));
+    for (int k = 0; k < hdr.cCont; ++k) pd[(size_t)k * kTileWorlds] = ps[(size_t)k * kTileWorlds];
+    const float4 sc0 = ps[(size_t)hdr.cScalar * kTileWorlds];
+    const int nc = __float_as_int(sc0.z);   // SS_NCONTACTS
+    for (int k = hdr.cCont; k < hdr.cCont + nc * SC_CHUNKS; ++k) pd[(size_t)k * kTileWorlds] = ps[(size_t)k * kTileWorlds];
+    for (int k = hdr.cScalar; k < hdr.stateChunks; ++k) pd[(size_t)k * kTileWorlds] = ps[(size_t)k * kTileWorlds];
+    worldOfDst[d] = worldOfSrc[s];
+}
+
+// controller targets of one segment, world order -> slot order
+__global__ void k_regroup_targets(const float* __restrict__ targets, float* __restrict__ out, const int* __restrict__ worldOf, long long N, int nd) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * nd) return;
+    const long long s = i / nd;
+    out[i] = targets[(size_t)worldOf[s] * nd + (i - s * nd)];
+}
+#endif
+
 }  // namespace B2G_VNS
 #if B2G_SETS
 extern std::atomic<unsigned long long> g_launches;
@@ -850,5 +946,41 @@ cudaError_t launchAbortFlags(const Launch& L, int* out) {
 }
 cudaError_t launchStatus(const Launch& L, int* out) { LAUNCH(k_world_status, out); }
 
+#if !B2G_SETS
+cudaError_t launchRegroupKey(const Launch& L, unsigned char* key, int* count, int groupSize) {
+    const long long groups = (L.N + groupSize - 1) / groupSize;
+    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int) * kRegroupClasses * groups, L.stream);
+    if (e != cudaSuccess) return e;
+    LAUNCH(k_regroup_key, key, count, groupSize);
+}
+cudaError_t launchRegroupAssign(const Launch& L, const unsigned char* key, const int* count, int* cursor, int* newSlot, int groupSize) {
+    const int groups = (int)((L.N + groupSize - 1) / groupSize);
+    k_regroup_scan<<<(unsigned)((groups + 127) / 128), 128, 0, L.stream>>>(count, cursor, groups, groupSize);
+    const int threads = 256;
+    k_regroup_assign<<<(unsigned)((L.N + threads - 1) / threads), threads, 0, L.stream>>>(key, cursor, newSlot, L.N, groupSize);
+    g_launches += 2;
+    return cudaGetLastError();
+}
+cudaError_t launchRegroupIota(const Launch& L, int* a) {
+    const int threads = 256;
+    k_regroup_iota<<<(unsigned)((L.N + threads - 1) / threads), threads, 0, L.stream>>>(a, L.N);
+    ++g_launches;
+    return cudaGetLastError();
+}
+cudaError_t launchRegroupMove(const Launch& L, const float* src, float* dst, const int* newSlot, const int* worldOfSrc, int* worldOfDst) {
+    const int threads = 128;
+    k_regroup_move<<<(unsigned)((L.N + threads - 1) / threads), threads, 0, L.stream>>>(L.h, (const float4*)src, (float4*)dst, newSlot,
+                                                                                       worldOfSrc, worldOfDst, L.N);
+    ++g_launches;
+    return cudaGetLastError();
+}
+cudaError_t launchRegroupTargets(const Launch& L, const float* targets, float* out, const int* worldOf, int nd) {
+    const int threads = 256;
+    const long long total = L.N * nd;
+    k_regroup_targets<<<(unsigned)((total + threads - 1) / threads), threads, 0, L.stream>>>(targets, out, worldOf, L.N, nd);
+    ++g_launches;
+    return cudaGetLastError();
+}
+#endif
 }  // namespace B2G_VNS
 }  // namespace b2g

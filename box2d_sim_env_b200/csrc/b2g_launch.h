@@ -76,6 +76,14 @@ B2G_LAUNCH_DECLS
 namespace sets {
 B2G_LAUNCH_DECLS
 }
+// regrouping worlds by island shape between the target segments of a large rollout (single-model batches only)
+namespace one {
+cudaError_t launchRegroupKey(const Launch& L, unsigned char* key, int* count, int groupSize);
+cudaError_t launchRegroupAssign(const Launch& L, const unsigned char* key, const int* count, int* cursor, int* newSlot, int groupSize);
+cudaError_t launchRegroupIota(const Launch& L, int* a);
+cudaError_t launchRegroupMove(const Launch& L, const float* src, float* dst, const int* newSlot, const int* worldOfSrc, int* worldOfDst);
+cudaError_t launchRegroupTargets(const Launch& L, const float* targets, float* out, const int* worldOf, int nd);
+}
 #define B2G_DISPATCH(name)                                                                     \
     template <class... A>                                                                      \
     inline cudaError_t name(const Launch& L, A... a) {                                         \

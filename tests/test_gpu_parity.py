@@ -1246,3 +1246,37 @@ def test_status_marks_scaled_targets(b2g):
     q, qd = batch.getWorldState()
     batch.setWorldState(q, qd, reset_caches=True)   # a fresh clone forgets it
     assert np.all(batch.status() == 0)
+
+
+@pytest.mark.parametrize("env_name,n,group", [(ENV_A, 40000, None), (ENV_B, 33333, "0"), (ENV_A, 96001, "4096")])
+def test_regrouped_rollout_parity(b2g, env_name, n, group, monkeypatch):
+    """Opt-in regrouping (B2G_REGROUP=1): large rollouts sort the worlds by island shape into a second state array before
+    every target segment -- inside the slot range of one CTA, of the whole batch or of a given group -- and move them back at
+    the end (b2g_capi.cpp: regroupedRollout).  Final states of all worlds, and bodies / joints / contact lists of a sample,
+    are bit-identical to the oracle; stepping on afterwards works on slot == world again."""
+    from oracle import b2o
+    monkeypatch.setenv("B2G_REGROUP", "1")
+    if group is not None:
+        monkeypatch.setenv("B2G_REGROUP_GROUP", group)
+    batch = make_batch(b2g, env_name, n)
+    q, qd = random_states(batch.model, n, seed=201, spread=0.6)
+    tg = random_targets(batch.model, 0, n, seed=202, segments=5)
+    gq, gqd = batch.rollout(0, tg, 8, q, qd, reset_caches=True)
+    ob = b2o.OracleBatch(env_dict(env_name), n)
+    oq, oqd = ob.rollout(q, qd, 0, tg, 8, os.cpu_count() or 4)
+    bad = np.nonzero(~(np.all(gq == oq, axis=1) & np.all(gqd == oqd, axis=1)))[0]
+    assert bad.size == 0, "%d of %d worlds differ, first %s" % (bad.size, n, bad[:5].tolist())
+    m = 300
+    worlds = [ob.world(w) for w in range(m)]
+    batch.selectWorlds(0, m)
+    assert_same(batch, worlds, "sample after the regrouped rollout")
+    batch.selectWorlds(0, 0)
+    assert int(batch.contacts(max_per_world=8)[1][..., 2].sum()) > 100, "scenario has too few touching contacts"
+    # stepping on without targets (plain launch, slot == world)
+    batch.stepPhysics(7)
+    for ow in worlds:
+        ow.step(7)
+    batch.selectWorlds(0, m)
+    assert_same(batch, worlds, "7 plain steps after the regrouped rollout")
+    batch.selectWorlds(0, 0)
+    assert np.all((batch.status() & 3) == 0)
