@@ -512,9 +512,16 @@ static b2g_status createBatch(const HostModel& hostModel, int64_t n_worlds, int 
         const char* envMask = getenv("B2G_SYNC_MASK");
         b->prm.syncMask = envMask ? (int)strtol(envMask, nullptr, 0) : (b->m.h.nb >= 16 ? 0x2aa : 0x7ff);
     }
-    // lanes per world (b2g_multi.cuh): experiments / tests choose with B2G_LPW
+    // lanes per world (b2g_multi.cuh: a world owned by a group of lanes).  One thread per world is the faster mapping for small
+    // models at every batch size; a scene with many bodies at a small batch is where the lanes of a group have
+    // enough per-body / per-joint / per-contact work to share: measured on the 38-body clutter scene, ms per 100 steps, one
+    // thread per world against the best group size: 128 worlds 26.9 -> 19.7 (32 lanes), 256: 29.7 -> 22.1, 512: 35.2 -> 23.0
+    // (16), 1024: 38.9 -> 26.4 (16), 2048: 45.1 -> 33.4 (8), 4096: 62.4 -> 60.9 (4: no gain).  B2G_LPW overrides.
     const char* envLpw = getenv("B2G_LPW");
-    b->stepLpw = envLpw ? atoi(envLpw) : 1;
+    if (envLpw) b->stepLpw = atoi(envLpw);
+    else if (b->m.h.nb >= 16 && !envLanes)
+        b->stepLpw = n_worlds <= 192 ? 32 : (n_worlds <= 1036 ? 16 : (n_worlds <= 2072 ? 8 : 1));
+    else b->stepLpw = 1;
     if (b->stepLpw != 1 && b->stepLpw != 2 && b->stepLpw != 4 && b->stepLpw != 8 && b->stepLpw != 16 && b->stepLpw != 32) b->stepLpw = 1;
     if (b->stepLpw > 1) {
         const int maxWorlds = 32 / b->stepLpw;

@@ -214,10 +214,15 @@ def test_error_behaviour(b2g):
         batch.setTargetVelocity("obj1", np.zeros((4, 3)))            # only robots have a velocity controller
 
 
-def test_clutter_shape_c_parity(b2g):
+@pytest.mark.parametrize("lpw", [None, "1", "8"])
+def test_clutter_shape_c_parity(b2g, lpw, monkeypatch):
     """Shape C (BASELINE.json configs[3]): robot + 32 convex polygons, 38 bodies / 39 proxies / 41 joints per world.
-    Dense sliding clutter: many simultaneous contacts, multi-body islands, contact creation/destruction order."""
+    Dense sliding clutter: many simultaneous contacts, multi-body islands, contact creation/destruction order.  A small batch
+    of a scene this size steps with a group of lanes per world by default (b2g_capi.cpp); one thread per world and another
+    group size are forced through B2G_LPW."""
     from box2d_sim_env_b200 import envgen
+    if lpw is not None:
+        monkeypatch.setenv("B2G_LPW", lpw)
     n = 24
     env = envgen.clutter_env()
     batch = b2g.BatchBox2DWorld(n).loadWorld(b2g.Model(env))
