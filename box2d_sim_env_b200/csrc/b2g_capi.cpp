@@ -514,13 +514,14 @@ static b2g_status createBatch(const HostModel& hostModel, int64_t n_worlds, int 
     }
     // lanes per world (b2g_multi.cuh: a world owned by a group of lanes).  One thread per world is the faster mapping for small
     // models at every batch size; a scene with many bodies at a small batch is where the lanes of a group have
-    // enough per-body / per-joint / per-contact work to share: measured on the 38-body clutter scene, ms per 100 steps, one
-    // thread per world against the best group size: 128 worlds 26.9 -> 19.7 (32 lanes), 256: 29.7 -> 22.1, 512: 35.2 -> 23.0
-    // (16), 1024: 38.9 -> 26.4 (16), 2048: 45.1 -> 33.4 (8), 4096: 62.4 -> 60.9 (4: no gain).  B2G_LPW overrides.
+    // enough per-body / per-joint / per-contact work to share (narrow phase and broad-phase box tests included).  Measured on
+    // the 38-body clutter scene, ms per 100 steps, one thread per world against the best group size: 512 worlds 35.3 -> 18.9
+    // (16 lanes), 1024: 39.1 -> 22.0 (16), 2048: 45.4 -> 31.6 (8), 4096: 62.6 -> 55.6 (8), 8192: 71.0 -> 90.0 (8: no).
+    // B2G_LPW overrides.
     const char* envLpw = getenv("B2G_LPW");
     if (envLpw) b->stepLpw = atoi(envLpw);
     else if (b->m.h.nb >= 16 && !envLanes)
-        b->stepLpw = n_worlds <= 192 ? 32 : (n_worlds <= 1036 ? 16 : (n_worlds <= 2072 ? 8 : 1));
+        b->stepLpw = n_worlds <= 192 ? 32 : (n_worlds <= 1036 ? 16 : (n_worlds <= 4144 ? 8 : 1));
     else b->stepLpw = 1;
     if (b->stepLpw != 1 && b->stepLpw != 2 && b->stepLpw != 4 && b->stepLpw != 8 && b->stepLpw != 16 && b->stepLpw != 32) b->stepLpw = 1;
     if (b->stepLpw > 1) {

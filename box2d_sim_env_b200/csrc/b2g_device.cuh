@@ -571,8 +571,20 @@ DEVN void onBeginContact(Ctx c, int k) {
     if ((p.recMode & 2) && p.allowed[bA * H().nb + bB] == 0) stI(c, sslot(c, SS_ABORT), ldI(c, sslot(c, SS_ABORT)) | 1);
 }
 
-// b2Contact::Update for slot k.  Returns bit0 = now touching, bit1 = was touching.
-DEVN int updateContact(Ctx c, int k) {
+// The side-effect-free part of b2Contact::Update for slot k: b2CollidePolygons on the fixtures' current transforms (the
+// sub-warp kernel evaluates the contacts of a world in parallel, one per lane, and commits them in list order afterwards)
+DEV void evalContact(Ctx c, int k, Manifold& m) {
+    const float4 head = ld4(c, cslot(c, k, SC_HEAD4));
+    const int fA = __float_as_int(head.x) & 0xff, fB = (__float_as_int(head.x) >> 8) & 0xff;
+    const XF xfA = ldXF(c, mI(c, mfix(c, fA, MF_BODY)));
+    const XF xfB = ldXF(c, mI(c, mfix(c, fB, MF_BODY)));
+    m.type = __float_as_int(head.z) & 0xff;
+    collidePolygons(c, m, fA, xfA, fB, xfB);
+}
+
+// b2Contact::Update for slot k.  Returns bit0 = now touching, bit1 = was touching.  `pre`: the manifold evalContact computed
+// for this slot from the same transforms, or nullptr to evaluate here.
+DEVN int updateContact(Ctx c, int k, const Manifold* pre = nullptr) {
     const int ck = cslot(c, k, 0);
     float4 head = ld4(c, ck + SC_HEAD4);
     float4 idn = ld4(c, ck + SC_ID4);
@@ -591,11 +603,15 @@ DEVN int updateContact(Ctx c, int k) {
     float oldN0 = p0.z, oldT0 = p0.w;
     float oldN1 = p1.z, oldT1 = p1.w;
 
-    XF xfA = ldXF(c, bA);
-    XF xfB = ldXF(c, bB);
     Manifold m;
-    m.type = oldMan & 0xff;
-    collidePolygons(c, m, fA, xfA, fB, xfB);
+    if (pre != nullptr) {
+        m = *pre;
+    } else {
+        XF xfA = ldXF(c, bA);
+        XF xfB = ldXF(c, bB);
+        m.type = oldMan & 0xff;
+        collidePolygons(c, m, fA, xfA, fB, xfB);
+    }
     bool touching = m.pointCount > 0;
     if (touching) {
         // b2CollidePolygons returns early (pointCount = 0) without touching the rest of the manifold, so the
@@ -681,34 +697,43 @@ DEV void addPair(Ctx c, int a, int b) {
 // b2ContactManager::FindNewContacts -> b2BroadPhase::UpdatePairs.  Upstream queries the tree for every
 // buffered proxy, sorts the (min,max) pairs and drops duplicates; iterating a < b in order over pairs with
 // at least one moved member and overlapping fat boxes visits exactly that sorted, de-duplicated sequence.
-DEVN void findNewContacts(Ctx c) {
+// fixtures b > a whose fat box overlaps fixture a's and that may pair with it in this UpdatePairs round (`moved` = move buffer)
+DEV uint64_t newPairHits(Ctx c, int a, uint64_t moved) {
+    uint64_t cand = (uint64_t)(uint32_t)mI(c, mfix(c, a, MF_PAIR_LO)) | ((uint64_t)(uint32_t)mI(c, mfix(c, a, MF_PAIR_HI)) << 32);
+    cand &= ~((2ull << a) - 1ull);
+    if (((moved >> a) & 1ull) == 0ull) cand &= moved;
+    if (cand == 0ull) return 0ull;
+    Box fa = ldFat(c, a);
+    // the overlap tests first (independent loads, nothing stored in between: they pipeline), the pairs are added afterwards
+    uint64_t hit = 0ull;
+    while (cand) {
+        const int b0 = __ffsll((long long)cand) - 1;
+        cand &= cand - 1ull;
+        const int b1 = cand ? __ffsll((long long)cand) - 1 : b0;
+        cand &= cand - 1ull;   // 0 & (0 - 1) = 0
+        const int b2 = cand ? __ffsll((long long)cand) - 1 : b0;
+        cand &= cand - 1ull;
+        const int b3 = cand ? __ffsll((long long)cand) - 1 : b0;
+        cand &= cand - 1ull;
+        const Box f0 = ldFat(c, b0), f1 = ldFat(c, b1), f2 = ldFat(c, b2), f3 = ldFat(c, b3);
+        if (boxOverlap(f0, fa)) hit |= 1ull << b0;
+        if (boxOverlap(f1, fa)) hit |= 1ull << b1;
+        if (boxOverlap(f2, fa)) hit |= 1ull << b2;
+        if (boxOverlap(f3, fa)) hit |= 1ull << b3;
+    }
+    return hit;
+}
+
+// b2ContactManager::FindNewContacts -> b2BroadPhase::UpdatePairs.  Upstream queries the tree for every
+// buffered proxy, sorts the (min,max) pairs and drops duplicates; iterating a < b in order over pairs with
+// at least one moved member and overlapping fat boxes visits exactly that sorted, de-duplicated sequence.
+// `hits`: per-fixture hit masks computed beforehand by the lanes of the world's group (sub-warp kernel), or nullptr.
+DEVN void findNewContacts(Ctx c, const uint64_t* hits = nullptr) {
     uint64_t moved = ldMoved(c);
     if (moved == 0ull) return;
     int nf = H().nf;
     for (int a = 0; a < nf; ++a) {
-        uint64_t cand = (uint64_t)(uint32_t)mI(c, mfix(c, a, MF_PAIR_LO)) | ((uint64_t)(uint32_t)mI(c, mfix(c, a, MF_PAIR_HI)) << 32);
-        cand &= ~((2ull << a) - 1ull);
-        if (((moved >> a) & 1ull) == 0ull) cand &= moved;
-        if (cand == 0ull) continue;
-        Box fa = ldFat(c, a);
-        // two passes: the overlap tests first (independent loads, nothing stored in between: they pipeline), then addPair for
-        // the hits in the same ascending order
-        uint64_t hit = 0ull;
-        while (cand) {
-            const int b0 = __ffsll((long long)cand) - 1;
-            cand &= cand - 1ull;
-            const int b1 = cand ? __ffsll((long long)cand) - 1 : b0;
-            cand &= cand - 1ull;   // 0 & (0 - 1) = 0
-            const int b2 = cand ? __ffsll((long long)cand) - 1 : b0;
-            cand &= cand - 1ull;
-            const int b3 = cand ? __ffsll((long long)cand) - 1 : b0;
-            cand &= cand - 1ull;
-            const Box f0 = ldFat(c, b0), f1 = ldFat(c, b1), f2 = ldFat(c, b2), f3 = ldFat(c, b3);
-            if (boxOverlap(f0, fa)) hit |= 1ull << b0;
-            if (boxOverlap(f1, fa)) hit |= 1ull << b1;
-            if (boxOverlap(f2, fa)) hit |= 1ull << b2;
-            if (boxOverlap(f3, fa)) hit |= 1ull << b3;
-        }
+        uint64_t hit = hits ? hits[a] : newPairHits(c, a, moved);
         while (hit) {
             const int b = __ffsll((long long)hit) - 1;
             hit &= hit - 1ull;
@@ -719,7 +744,8 @@ DEVN void findNewContacts(Ctx c) {
 }
 
 // b2ContactManager::Collide: contacts in upstream list order (newest first)
-DEVN void collide(Ctx c) {
+// `man` / `valid`: manifolds evalContact computed for slots k < 64 with bit k of `valid` set (sub-warp kernel), else none
+DEVN void collide(Ctx c, const Manifold* man = nullptr, uint64_t valid = 0ull) {
     for (int k = contactCount(c) - 1; k >= 0; --k) {
         int fA, fB;
         contactFixtures(c, k, fA, fB);
@@ -738,10 +764,11 @@ DEVN void collide(Ctx c) {
         Box a = ldFat(c, fA);
         Box b = ldFat(c, fB);
         if (!boxOverlap(a, b)) { destroyContact(c, k); continue; }
+        const Manifold* pre = (k < 64 && ((valid >> k) & 1ull)) ? man + k : nullptr;
 #ifndef B2G_NO_HOOK_COLLIDE
-        if (updateContact(c, k) == 1 && PRM().recMode != 0) onBeginContact(c, k);
+        if (updateContact(c, k, pre) == 1 && PRM().recMode != 0) onBeginContact(c, k);
 #else
-        updateContact(c, k);
+        updateContact(c, k, pre);
 #endif
     }
 }

@@ -31,6 +31,7 @@ namespace b2g {
 
 constexpr int kMaxNodes = 32;      // constraints (joints + contacts outside simple islands) one dataflow schedule handles
 constexpr int kMaxLaps = 255;      // velocity iterations a lap counter can count
+constexpr int kMultiManifolds = 48;  // contacts of a world whose manifolds the lanes evaluate in parallel (more: the rest sequentially)
 constexpr int kSlotBytes = 1024;   // schedule table per world: kSlotBytes / LPW slots of LPW node indices
 
 // Lists and schedule of one world, shared by the lanes of its group (shared memory).
@@ -58,6 +59,11 @@ struct WorldShared {
     // build-time scratch
     unsigned nodeW[kMaxNodes];  // bits 0-6 successor on the side-A body (node | side << 5 | wrap << 6), bit 7 side A is dynamic,
                                 // bits 8-15 the same for side B, bits 16-21 / 22-27 the side-A / side-B body
+    // narrow / broad phase shared by the lanes of the group: manifolds evaluated in parallel (one contact per lane) before the
+    // sequential b2ContactManager::Collide pass commits them, fat-box hit masks per fixture before UpdatePairs adds the pairs
+    Manifold man[kMultiManifolds];
+    unsigned manValidLo, manValidHi;
+    uint64_t hit[kMaxFixtures];
     unsigned char lap[kMaxBodies];   // laps (velocity iterations) the token of a dynamic body has completed
     unsigned char last[kMaxBodies];  // last node | side << 5 seen on a body, 0xff none
     unsigned char first[kMaxBodies];
@@ -466,8 +472,19 @@ DEV void solveIslandsMulti(Ctx c, const Grp<LPW>& g, WorldShared& W, float dtRat
         }
         const uint64_t moved = (uint64_t)W.movedLo | ((uint64_t)W.movedHi << 32);
         if (moved) stMoved(c, ldMoved(c) | moved);
-        findNewContacts(c);
     }
+    gsync(g);
+    // broad phase: the fat-box tests of every fixture against its candidates, fixtures strided over the lanes; lane 0 then adds
+    // the pairs in ascending (a, b) order (b2BroadPhase::UpdatePairs)
+    {
+        const uint64_t moved = ldMoved(c);
+        if (moved != 0ull) {
+            const int nf = H().nf;
+            for (int a = g.s; a < nf; a += LPW) W.hit[a] = newPairHits(c, a, moved);
+        }
+    }
+    gsync(g);
+    if (g.s == 0) findNewContacts(c, W.hit);
     gsync(g);
 }
 
@@ -488,8 +505,29 @@ DEV void stepWorldMulti(Ctx c, const Grp<LPW>& g, WorldShared& W, bool executeCo
             findNewContacts(c);
             stI(c, sslot(c, SS_FLAGS), flags & ~1);
         }
-        collide(c);
+        W.manValidLo = W.manValidHi = 0u;
     }
+    gsync(g);
+    // narrow phase, one contact per lane: b2CollidePolygons of every contact the Collide pass is going to update (an awake
+    // dynamic body, fat boxes still overlapping -- judged on the state before the pass; a contact the pass wants although it
+    // was skipped here, because an earlier contact of the pass woke its body, is evaluated by the pass itself)
+    {
+        const int n = contactCount(c);
+        const uint64_t awake = ldAwake(c);
+        for (int k = g.s; k < n && k < kMultiManifolds; k += LPW) {
+            int fA, fB;
+            contactFixtures(c, k, fA, fB);
+            const int bA = mI(c, mfix(c, fA, MF_BODY)), bB = mI(c, mfix(c, fB, MF_BODY));
+            const bool activeA = ((awake >> bA) & 1ull) && bodyType(c, bA) != 0;
+            const bool activeB = ((awake >> bB) & 1ull) && bodyType(c, bB) != 0;
+            if (!activeA && !activeB) continue;
+            if (!boxOverlap(ldFat(c, fA), ldFat(c, fB))) continue;
+            evalContact(c, k, W.man[k]);
+            if (k < 32) atomicOr(&W.manValidLo, 1u << k); else atomicOr(&W.manValidHi, 1u << (k - 32));
+        }
+    }
+    gsync(g);
+    if (g.s == 0) collide(c, W.man, (uint64_t)W.manValidLo | ((uint64_t)W.manValidHi << 32));
     dtRatio = ldF(c, sslot(c, SS_INV_DT0)) * PRM().dt;  // written at the end of the previous step, before a group barrier
     gsync(g);
     solveIslandsMulti<LPW>(c, g, W, dtRatio, allowSleeping);
